@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the fused superposition + per-frame RMSD pass (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU port of the reference
+
+A "step" is one pass of chem.Super + chem.RMSD (fit mode: RMSD, rotation, translations; frames not
+rewritten) over the whole resident trajectory of BASELINE.json configs[1]: 100,000 frames x 10,000
+atoms per GPU, float64 SoA, 24 GB in HBM -- far larger than the 126 MB L2, so nothing is cached between
+timed iterations.  N > 1: every rank holds its own 100k-frame shard (weak scaling), no data-path
+collective.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/sec superposed+RMSD"
+UNIT = "frames/s"
+NATOMS = 10000
+NFRAMES = 100000
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--atoms", type=int, default=NATOMS)
+    ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=4096, help="frames per end-to-end step (host buffers)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--write-back", type=int, default=0, help="1 = Super mode (frames rewritten, 48 B/atom)")
+    ap.add_argument("--variant", default="auto", choices=["auto", "generic", "cluster"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+# --------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    def __init__(self, want_gpus: int, cuda: bool):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if cuda:
+                torch.cuda.set_device(self.local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            else:
+                dist.init_process_group("gloo")
+            self.cuda = cuda
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda" if self.cuda else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda" if self.cuda else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        v = float(json.load(open(p))["hbm_gbs"])
+        return v, "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write bytes)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def recorded_traffic(write_back: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get("super_mode" if write_back else "fit_mode")
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(a):
+    """The reference's own CPU implementation of the path, timed on the host cores.  The Go reference
+    cannot be built here (no Go toolchain), so this is the oracle port (O(N) restatement: the stronger
+    baseline; the reference as written also multiplies by an N x N identity per frame,
+    geometric.go:145-149).  One worker thread per frame in flight, like align.RMSDTraj's goroutines."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from gochem_b200 import synth
+
+    cores = os.cpu_count() or 1
+    natoms = a.atoms
+    ref = synth.make_reference(natoms)
+    sig = synth.atom_sigmas(natoms)
+    base = synth.make_frames(ref, sig, 16)
+    # size the per-step sample from a probe so the whole run stays within a few minutes
+    probe = np.tile(base, (max(1, 4 * cores // 16), 1, 1)) if 4 * cores > 16 else base
+    t0 = time.perf_counter()
+    oracle.super_rmsd_traj(probe, ref, None, nthreads=cores, details=False)
+    rate = probe.shape[0] / (time.perf_counter() - t0)
+    budget = 90.0 / max(1, a.steps + a.warmup)
+    per_step = int(max(cores, min(4096, rate * min(budget, 4.0))))
+    per_step -= per_step % cores or 0
+    per_step = max(per_step, cores)
+    sample = np.tile(base, ((per_step + 15) // 16, 1, 1))[:per_step]
+    rm = np.zeros(per_step)
+    for _ in range(a.warmup):
+        oracle.super_rmsd_traj(sample, ref, None, nthreads=cores, details=False)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        rm = oracle.super_rmsd_traj(sample, ref, None, nthreads=cores, details=False)
+    dt = time.perf_counter() - t0
+    value = per_step * a.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"chem.Super + chem.RMSD per frame, {natoms} atoms, fit on all atoms (BASELINE configs[1] shape)",
+                   "frames_per_step": per_step, "natoms": natoms},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} frames x {natoms} atoms per step, O(N) restatement of geometric.go:127-208 + handy.go:175-214 + geometric.go:258-288, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "check": {"rmsd_mean": float(np.mean(rm))},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(a):
+    from gochem_b200 import _lib, synth
+
+    lib = _lib.load()
+    if _lib.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")
+    d = Dist(a.gpus, cuda=True)
+    dev = d.local
+    variant = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "cluster": _lib.KERNEL_CLUSTER}[a.variant]
+    _lib.check(lib.gcb_set_kernel_variant(variant))
+    natoms, nframes = a.atoms, a.frames
+    ref = synth.make_reference(natoms)
+    sig = synth.atom_sigmas(natoms)
+    traj = _lib.DeviceTraj(natoms, nframes, dev=dev)
+    # every rank generates its own shard: global frame ids [rank*F, (rank+1)*F)
+    traj.synth_fill(ref, sig, nframes, frame_id0=d.rank * nframes, frame0_is_ref=True)
+    wb = bool(a.write_back)
+
+    def step():
+        traj.super_rmsd_async(ref, write_back=wb)
+
+    for _ in range(a.warmup):
+        step()
+    traj.sync()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    d.barrier()
+    traj.sync()
+    launches0 = lib.gcb_launch_count()
+    traj.timer_start()
+    for _ in range(a.steps):
+        step()
+    ms = traj.timer_stop()
+    traj.sync()
+    d.barrier()
+    launches = lib.gcb_launch_count() - launches0
+    clocks = sampler.result()
+    ms = d.max(ms)
+    ms_per_step = ms / a.steps
+    total_frames = nframes * d.world
+    value = total_frames / (ms_per_step * 1e-3)
+    res = traj.fetch(want=("rmsd",))
+    rmsd_gpu = res["rmsd"]
+
+    # roofline of the dominant (only) kernel of the step: one launch per step
+    bytes_per_atom = 48 if wb else 24
+    alg_bytes = float(bytes_per_atom) * natoms * nframes
+    kernel_ms = ms_per_step  # exactly one kernel per step on the timed stream
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(a.write_back), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                "note": "per GPU; 24 B/atom/frame fit mode (48 with write-back), template re-reads excluded"}
+
+    # end to end through the C ABI with HOST buffers: pinned float64 AoS frames -> device -> kernel -> rmsd back
+    e2e_frames = min(a.e2e_frames, nframes)
+    frame_bytes = natoms * 3 * 8
+    chunk = max(1, min(e2e_frames, (64 << 20) // frame_bytes))
+    host_sample = traj.download(0, e2e_frames) if not wb else None
+    if host_sample is None:
+        host_sample = traj.download(0, e2e_frames)
+    pinned = _lib.PinnedBuffer(e2e_frames * frame_bytes)
+    pv = pinned.view(np.float64, (e2e_frames, natoms, 3))
+    pv[...] = host_sample
+    e2e_traj = _lib.DeviceTraj(natoms, e2e_frames, dev=dev)
+    out_rmsd = np.empty(e2e_frames)
+
+    def e2e_step():
+        k = 0
+        for first in range(0, e2e_frames, chunk):
+            n = min(chunk, e2e_frames - first)
+            e2e_traj.upload_async(pv[first:first + n], n, first, _lib.F64_AOS, 1.0, k & 1)
+            e2e_traj.super_rmsd_async(ref, first=first, nframes=n, write_back=wb)
+            k += 1
+        r = e2e_traj.fetch(0, e2e_frames, want=("rmsd",))
+        return r["rmsd"]
+
+    for _ in range(max(1, a.warmup)):
+        out_rmsd = e2e_step()
+    e2e_steps = max(3, min(a.steps, 10))
+    d.barrier()
+    e2e_traj.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out_rmsd = e2e_step()
+    e2e_traj.sync()
+    e2e_dt = d.max(time.perf_counter() - t0)
+    d.barrier()
+    e2e_value = e2e_frames * d.world * e2e_steps / e2e_dt
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_frames * frame_bytes,
+           "d2h_bytes_per_step": e2e_frames * 8, "frames_per_step": e2e_frames,
+           "h2d_gbs_per_gpu": e2e_frames * frame_bytes * e2e_steps / e2e_dt / 1e9,
+           "path": "pinned float64 AoS host frames -> gcb_traj_upload_async (2 slots) -> gcb_super_rmsd_async -> gcb_fetch_results"}
+    e2e_check = float(np.abs(out_rmsd - rmsd_gpu[:e2e_frames]).max()) if not wb else None
+
+    # CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample of the same frames
+    cpu = None
+    parity = None
+    if d.rank == 0 and d.world == 1 and not a.no_cpu_baseline:
+        import oracle
+
+        cores = os.cpu_count() or 1
+        probe_n = min(e2e_frames, 8 * cores)
+        t0 = time.perf_counter()
+        oracle.super_rmsd_traj(host_sample[:probe_n], ref, None, nthreads=cores, details=False)
+        rate = probe_n / (time.perf_counter() - t0)
+        n_cpu = int(max(cores, min(e2e_frames, rate * a.cpu_seconds)))
+        t0 = time.perf_counter()
+        rm_cpu, rot_cpu, _t1, _t2 = oracle.super_rmsd_traj(host_sample[:n_cpu], ref, None, nthreads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n_cpu} frames of the GPU's trajectory ({natoms} atoms), O(N) C restatement of the reference path, {cores} threads, {dt:.1f} s"}
+        if not wb:
+            got = traj.fetch(0, n_cpu, want=("rmsd", "rot"))
+            parity = {"frames_checked": n_cpu, "max_abs_rmsd_diff": float(np.abs(got["rmsd"] - rm_cpu).max()),
+                      "max_abs_rot_diff": float(np.abs(got["rot"] - rot_cpu).max())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": d.world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"fused chem.Super + per-frame chem.RMSD, {nframes} frames x {natoms} atoms per GPU resident in HBM (BASELINE configs[1])",
+                   "mode": "super (write-back, 48 B/atom)" if wb else "fit (RMSD + R + translations, 24 B/atom)",
+                   "frames_per_gpu": nframes, "natoms": natoms, "sharding": f"frames x{d.world}, no collective",
+                   "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9 if not wb else alg_bytes / 2e9),
+                   "kernel_variant": a.variant},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "check": {"rmsd_frame0": float(rmsd_gpu[0]), "rmsd_mean": float(rmsd_gpu.mean()), "e2e_vs_resident_max_abs": e2e_check,
+                  "parity_vs_oracle": parity},
+    }
+    if d.rank == 0:
+        print(json.dumps(line), flush=True)
+    pinned.free()
+    e2e_traj.close()
+    traj.close()
+    d.close()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,284 @@
+"""ctypes loader of the C-ABI library (include/gochem_b200.h).
+
+Plumbing for tests/ and bench.py: numpy arrays in, numpy arrays out.  It never falls back to a CPU
+implementation; a missing library or a failing CUDA call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgochem_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "gochem_b200.h")
+
+F64_AOS, F32_AOS, F32_SOA = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CLUSTER = 0, 1, 2
+OK, ERR_SHAPE, ERR_INDEXES, ERR_SVD, ERR_ALLOC, ERR_CUDA, ERR_ARG, EOF = 0, -1, -2, -4, -5, -7, -8, 11
+
+
+class GcbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gochem_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/gochem_b200.h declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GcbError(ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    P, I, L, D = C.c_void_p, C.c_int, C.c_long, C.c_double
+    sig = {
+        "gcb_version": (I, []),
+        "gcb_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+        "gcb_device_count": (I, [C.POINTER(I)]),
+        "gcb_device_info": (I, [I, C.POINTER(I), C.POINTER(C.c_size_t), C.POINTER(I), C.POINTER(I)]),
+        "gcb_set_kernel_variant": (I, [I]),
+        "gcb_pinned_alloc": (I, [C.c_size_t, C.POINTER(P)]),
+        "gcb_pinned_free": (I, [P]),
+        "gcb_traj_create": (I, [I, I, L, C.POINTER(P)]),
+        "gcb_traj_destroy": (I, [P]),
+        "gcb_traj_natoms": (I, [P]),
+        "gcb_traj_capacity": (L, [P]),
+        "gcb_traj_nframes": (L, [P]),
+        "gcb_traj_set_nframes": (I, [P, L]),
+        "gcb_traj_upload": (I, [P, L, P, L, I, D]),
+        "gcb_traj_upload_async": (I, [P, L, P, L, I, D, I]),
+        "gcb_traj_wait": (I, [P, I]),
+        "gcb_traj_download": (I, [P, L, L, P]),
+        "gcb_super_rmsd": (I, [P, L, L, P, I, P, P, I, I, P, P, P, P]),
+        "gcb_super_rmsd_async": (I, [P, L, L, P, I, P, P, I, I]),
+        "gcb_fetch_results": (I, [P, L, L, P, P, P, P]),
+        "gcb_rmsd": (I, [P, L, L, P, I, P, P, I, P]),
+        "gcb_peratom_dev_sum": (I, [P, L, L, P, P, I, I, P, P]),
+        "gcb_timer_start": (I, [P]),
+        "gcb_timer_stop": (I, [P, C.POINTER(C.c_float)]),
+        "gcb_sync": (I, [P]),
+        "gcb_launch_count": (L, []),
+        "gcb_synth_fill": (I, [P, L, L, P, P, C.c_ulonglong, L, I, I]),
+        "gcb_comm_unique_id": (I, [C.c_char_p]),
+        "gcb_comm_init": (I, [I, I, I, C.c_char_p, C.POINTER(P)]),
+        "gcb_comm_destroy": (I, [P]),
+        "gcb_allreduce_sum_f64": (I, [P, P, L]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(2048)
+    load().gcb_last_error(buf, 2048)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise GcbError(rc, last_error())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _idx(a):
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = load().gcb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class PinnedBuffer:
+    """C-owned page-locked staging buffer exposed as a numpy array."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(load().gcb_pinned_alloc(nbytes, C.byref(self.ptr)))
+        self.nbytes = nbytes
+        self.u8 = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def view(self, dtype, shape):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return self.u8[:n].view(dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            load().gcb_pinned_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Comm:
+    def __init__(self, dev: int, nranks: int, rank: int, unique_id: bytes):
+        self.h = C.c_void_p()
+        check(load().gcb_comm_init(dev, nranks, rank, unique_id, C.byref(self.h)))
+        self.nranks, self.rank = nranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(load().gcb_comm_unique_id(buf))
+        return buf.raw
+
+    def allreduce_sum(self, vec: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(vec, dtype=np.float64).copy()
+        check(load().gcb_allreduce_sum_f64(self.h, _ptr(v), v.size))
+        return v
+
+    def close(self):
+        if self.h:
+            load().gcb_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class DeviceTraj:
+    """Device-resident trajectory (the batch of v3 device matrices)."""
+
+    def __init__(self, natoms: int, cap_frames: int, dev: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        check(self.lib.gcb_traj_create(dev, natoms, cap_frames, C.byref(self.h)))
+        self.natoms, self.cap, self.dev = natoms, cap_frames, dev
+
+    # --- data movement ---
+    def upload(self, frames: np.ndarray, first: int = 0, layout: int = F64_AOS, scale: float = 1.0):
+        dt = np.float64 if layout == F64_AOS else np.float32
+        a = np.ascontiguousarray(frames, dtype=dt)
+        n = a.size // (3 * self.natoms)
+        check(self.lib.gcb_traj_upload(self.h, first, _ptr(a), n, layout, scale))
+        return n
+
+    def upload_async(self, pinned_view: np.ndarray, nframes: int, first: int, layout: int, scale: float, slot: int):
+        check(self.lib.gcb_traj_upload_async(self.h, first, _ptr(pinned_view), nframes, layout, scale, slot))
+
+    def wait(self, slot: int):
+        check(self.lib.gcb_traj_wait(self.h, slot))
+
+    def download(self, first: int = 0, nframes: int | None = None) -> np.ndarray:
+        n = self.nframes - first if nframes is None else nframes
+        out = np.empty((n, self.natoms, 3), dtype=np.float64)
+        check(self.lib.gcb_traj_download(self.h, first, n, _ptr(out)))
+        return out
+
+    @property
+    def nframes(self) -> int:
+        return self.lib.gcb_traj_nframes(self.h)
+
+    def set_nframes(self, n: int):
+        check(self.lib.gcb_traj_set_nframes(self.h, n))
+
+    def synth_fill(self, ref, sigma, nframes, first=0, seed=12347, frame_id0=0, frame0_is_ref=False, through_f32=False):
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        check(self.lib.gcb_synth_fill(self.h, first, nframes, _ptr(ref), _ptr(sigma), seed, frame_id0,
+                                      int(frame0_is_ref), int(through_f32)))
+
+    # --- compute ---
+    def super_rmsd(self, ref, idx_test=None, idx_ref=None, write_back=False, first=0, nframes=None,
+                   want=("rmsd", "rot", "trans1", "trans2")):
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        it, ir = _idx(idx_test), _idx(idx_ref)
+        nidx = 0 if it is None else it.size
+        out = {
+            "rmsd": np.empty(n) if "rmsd" in want else None,
+            "rot": np.empty((n, 3, 3)) if "rot" in want else None,
+            "trans1": np.empty((n, 3)) if "trans1" in want else None,
+            "trans2": np.empty((n, 3)) if "trans2" in want else None,
+        }
+        check(self.lib.gcb_super_rmsd(self.h, first, n, _ptr(ref), ref.shape[0], _ptr(it), _ptr(ir), nidx,
+                                      int(write_back), _ptr(out["rmsd"]), _ptr(out["rot"]), _ptr(out["trans1"]),
+                                      _ptr(out["trans2"])))
+        return out
+
+    def super_rmsd_async(self, ref, idx_test=None, idx_ref=None, write_back=False, first=0, nframes=None):
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        it, ir = _idx(idx_test), _idx(idx_ref)
+        nidx = 0 if it is None else it.size
+        check(self.lib.gcb_super_rmsd_async(self.h, first, n, _ptr(ref), ref.shape[0], _ptr(it), _ptr(ir), nidx,
+                                            int(write_back)))
+
+    def fetch(self, first=0, nframes=None, want=("rmsd",)):
+        n = self.nframes - first if nframes is None else nframes
+        out = {
+            "rmsd": np.empty(n) if "rmsd" in want else None,
+            "rot": np.empty((n, 3, 3)) if "rot" in want else None,
+            "trans1": np.empty((n, 3)) if "trans1" in want else None,
+            "trans2": np.empty((n, 3)) if "trans2" in want else None,
+        }
+        check(self.lib.gcb_fetch_results(self.h, first, n, _ptr(out["rmsd"]), _ptr(out["rot"]), _ptr(out["trans1"]),
+                                         _ptr(out["trans2"])))
+        return out
+
+    def rmsd(self, ref, idx_test=None, idx_ref=None, first=0, nframes=None) -> np.ndarray:
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        it, ir = _idx(idx_test), _idx(idx_ref)
+        nidx = 0 if it is None else it.size
+        out = np.empty(n)
+        check(self.lib.gcb_rmsd(self.h, first, n, _ptr(ref), ref.shape[0], _ptr(it), _ptr(ir), nidx, _ptr(out)))
+        return out
+
+    def peratom_dev_sum(self, ref, idx=None, write_back=False, first=0, nframes=None, comm: Comm | None = None):
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        it = _idx(idx)
+        nidx = 0 if it is None else it.size
+        out = np.empty(self.natoms)
+        check(self.lib.gcb_peratom_dev_sum(self.h, first, n, _ptr(ref), _ptr(it), nidx, int(write_back),
+                                           comm.h if comm else None, _ptr(out)))
+        return out
+
+    # --- timing on the library's stream ---
+    def timer_start(self):
+        check(self.lib.gcb_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(self.lib.gcb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        check(self.lib.gcb_sync(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.gcb_traj_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

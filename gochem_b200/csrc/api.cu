@@ -1,0 +1,576 @@
+// api.cu -- the extern "C" boundary declared in include/gochem_b200.h.
+//
+// Host-side work done here is only what has to happen once per call: argument checks that mirror
+// the reference's error returns, preparing the centred template (the reference centres templa in
+// chem.MassCenter, /root/reference/geometric.go:670-703, on every call; here it is centred once per
+// call and reused by every frame), staging copies, launches.  All arithmetic on frames runs in the
+// CUDA kernels; there is no CPU fallback.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcb {
+
+static thread_local std::string t_error;
+std::atomic<long> g_launches{0};
+int g_variant = GCB_KERNEL_AUTO;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+constexpr size_t kStageBytes = 64ull << 20;
+
+struct RefCache {
+    std::vector<double> ref;
+    std::vector<int> idx_t, idx_r;
+    int natoms_ref = -1;
+    int mode = -1;  // 0 all, 1 weighted, 2 gather
+    bool centred = false;
+    bool valid = false;
+    double n_fit = 0.0;
+    double bbar[3] = {0, 0, 0};
+};
+
+}  // namespace gcb
+
+struct gcb_traj_ext : gcb_traj {
+    gcb::RefCache cache;
+};
+
+using namespace gcb;
+
+static gcb_traj_ext* X(gcb_traj* t) { return static_cast<gcb_traj_ext*>(t); }
+
+static int check_window(const gcb_traj* t, long first, long nframes, bool within_nframes) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    const long lim = within_nframes ? t->nframes : t->cap;
+    if (first < 0 || nframes < 0 || first + nframes > lim) {
+        set_error("frame window [%ld, %ld) outside [0, %ld)", first, first + nframes, lim);
+        return GCB_ERR_ARG;
+    }
+    return GCB_OK;
+}
+
+extern "C" {
+
+int gcb_version(void) { return 100; }
+
+size_t gcb_last_error(char* buf, size_t cap) {
+    if (buf && cap) {
+        size_t n = t_error.size() < cap - 1 ? t_error.size() : cap - 1;
+        memcpy(buf, t_error.data(), n);
+        buf[n] = 0;
+    }
+    return t_error.size();
+}
+
+int gcb_device_count(int* n) {
+    if (!n) return GCB_ERR_ARG;
+    *n = 0;
+    GCB_CUDA(cudaGetDeviceCount(n));
+    return GCB_OK;
+}
+
+int gcb_device_info(int dev, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor) {
+    cudaDeviceProp pr;
+    GCB_CUDA(cudaGetDeviceProperties(&pr, dev));
+    if (sm_count) *sm_count = pr.multiProcessorCount;
+    if (total_mem) *total_mem = pr.totalGlobalMem;
+    if (cc_major) *cc_major = pr.major;
+    if (cc_minor) *cc_minor = pr.minor;
+    return GCB_OK;
+}
+
+int gcb_set_kernel_variant(int variant) {
+    if (variant < GCB_KERNEL_AUTO || variant > GCB_KERNEL_CLUSTER) { set_error("bad kernel variant %d", variant); return GCB_ERR_ARG; }
+    g_variant = variant;
+    return GCB_OK;
+}
+
+long gcb_launch_count(void) { return g_launches.load(); }
+
+int gcb_pinned_alloc(size_t bytes, void** p) {
+    if (!p) return GCB_ERR_ARG;
+    *p = nullptr;
+    GCB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return GCB_OK;
+}
+
+int gcb_pinned_free(void* p) {
+    if (!p) return GCB_OK;
+    GCB_CUDA(cudaFreeHost(p));
+    return GCB_OK;
+}
+
+int gcb_traj_destroy(gcb_traj* tb) {
+    if (!tb) return GCB_OK;
+    gcb_traj_ext* t = X(tb);
+    cudaSetDevice(t->dev);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    for (int s = 0; s < 2; s++) {
+        if (t->copy_stream[s]) { cudaStreamSynchronize(t->copy_stream[s]); cudaStreamDestroy(t->copy_stream[s]); }
+        if (t->copy_done[s]) cudaEventDestroy(t->copy_done[s]);
+        if (t->d_stage[s]) cudaFree(t->d_stage[s]);
+    }
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
+    cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status);
+    cudaFree(t->d_devpart); cudaFree(t->d_devsum);
+    if (t->h_scratch) cudaFreeHost(t->h_scratch);
+    delete t;
+    return GCB_OK;
+}
+
+int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj** out) {
+    if (!out) return GCB_ERR_ARG;
+    *out = nullptr;
+    if (natoms <= 0 || cap_frames <= 0) { set_error("natoms and cap_frames must be positive"); return GCB_ERR_SHAPE; }
+    GCB_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp pr;
+    GCB_CUDA(cudaGetDeviceProperties(&pr, dev));
+    if (pr.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", dev, pr.major, pr.minor);
+        return GCB_ERR_CUDA;
+    }
+    gcb_traj_ext* t = new gcb_traj_ext();
+    t->dev = dev;
+    t->natoms = natoms;
+    t->np = round_up(natoms, kPlaneAlign);
+    t->cap = cap_frames;
+    t->nframes = 0;
+    t->sm_count = pr.multiProcessorCount;
+    int rc = GCB_OK;
+#define TRY(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            set_error("%s failed: %s", #call, cudaGetErrorString(e__));                               \
+            rc = (e__ == cudaErrorMemoryAllocation) ? GCB_ERR_ALLOC : GCB_ERR_CUDA;                   \
+            goto fail;                                                                                \
+        }                                                                                             \
+    } while (0)
+    {
+        const size_t frame_bytes = sizeof(double) * 3 * (size_t)t->np;
+        TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; s++) {
+            TRY(cudaStreamCreateWithFlags(&t->copy_stream[s], cudaStreamNonBlocking));
+            TRY(cudaEventCreateWithFlags(&t->copy_done[s], cudaEventDisableTiming));
+        }
+        TRY(cudaEventCreate(&t->ev0));
+        TRY(cudaEventCreate(&t->ev1));
+        TRY(cudaMalloc(&t->d_frames, frame_bytes * (size_t)cap_frames));
+        t->stage_bytes = kStageBytes;
+        if (t->stage_bytes < frame_bytes) t->stage_bytes = frame_bytes;
+        for (int s = 0; s < 2; s++) TRY(cudaMalloc(&t->d_stage[s], t->stage_bytes));
+        TRY(cudaMalloc(&t->d_refc, frame_bytes));
+        TRY(cudaMalloc(&t->d_weight, sizeof(double) * (size_t)t->np));
+        TRY(cudaMalloc(&t->d_rmsd, sizeof(double) * (size_t)cap_frames));
+        TRY(cudaMalloc(&t->d_rot, sizeof(double) * 9 * (size_t)cap_frames));
+        TRY(cudaMalloc(&t->d_t1, sizeof(double) * 3 * (size_t)cap_frames));
+        TRY(cudaMalloc(&t->d_t2, sizeof(double) * 3 * (size_t)cap_frames));
+        TRY(cudaMalloc(&t->d_status, sizeof(int)));
+        TRY(cudaMemset(t->d_status, 0, sizeof(int)));
+        TRY(cudaMalloc(&t->d_devsum, sizeof(double) * (size_t)t->np));
+        t->h_scratch_bytes = sizeof(double) * 4 * (size_t)t->np + 64;
+        TRY(cudaHostAlloc((void**)&t->h_scratch, t->h_scratch_bytes, cudaHostAllocPortable));
+    }
+#undef TRY
+    *out = t;
+    return GCB_OK;
+fail:
+    gcb_traj_destroy(t);
+    return rc;
+}
+
+int gcb_traj_natoms(const gcb_traj* t) { return t ? t->natoms : -1; }
+long gcb_traj_capacity(const gcb_traj* t) { return t ? t->cap : -1; }
+long gcb_traj_nframes(const gcb_traj* t) { return t ? t->nframes : -1; }
+
+int gcb_traj_set_nframes(gcb_traj* t, long nframes) {
+    if (!t || nframes < 0 || nframes > t->cap) { set_error("nframes out of range"); return GCB_ERR_ARG; }
+    t->nframes = nframes;
+    return GCB_OK;
+}
+
+static size_t host_frame_bytes(const gcb_traj* t, int layout) {
+    return (layout == GCB_F64_AOS ? sizeof(double) : sizeof(float)) * 3 * (size_t)t->natoms;
+}
+
+int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int layout, double scale) {
+    int rc = check_window(t, first, nframes, false);
+    if (rc) return rc;
+    if (!host && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
+    if (layout < GCB_F64_AOS || layout > GCB_F32_SOA) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    const size_t fb = host_frame_bytes(t, layout);
+    const long per = (long)(t->stage_bytes / fb);
+    int slot = 0;
+    for (long done = 0; done < nframes; done += per, slot ^= 1) {
+        const long n = (nframes - done < per) ? nframes - done : per;
+        cudaStream_t s = t->copy_stream[slot];
+        GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], (const char*)host + (size_t)done * fb, (size_t)n * fb, cudaMemcpyHostToDevice, s));
+        rc = launch_upload_convert(t, s, t->d_stage[slot], first + done, n, layout, scale);
+        if (rc) return rc;
+    }
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+    if (first + nframes > t->nframes) t->nframes = first + nframes;
+    return GCB_OK;
+}
+
+int gcb_traj_upload_async(gcb_traj* t, long first, const void* pinned, long nframes, int layout, double scale, int slot) {
+    int rc = check_window(t, first, nframes, false);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1) { set_error("slot must be 0 or 1"); return GCB_ERR_ARG; }
+    if (layout < GCB_F64_AOS || layout > GCB_F32_SOA) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
+    const size_t bytes = host_frame_bytes(t, layout) * (size_t)nframes;
+    if (bytes > t->stage_bytes) { set_error("async upload of %zu bytes exceeds the %zu-byte staging slot", bytes, t->stage_bytes); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    cudaStream_t s = t->copy_stream[slot];
+    // do not overwrite frame slots a queued kernel still reads
+    GCB_CUDA(cudaEventRecord(t->ev1, t->stream));
+    GCB_CUDA(cudaStreamWaitEvent(s, t->ev1, 0));
+    GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], pinned, bytes, cudaMemcpyHostToDevice, s));
+    rc = launch_upload_convert(t, s, t->d_stage[slot], first, nframes, layout, scale);
+    if (rc) return rc;
+    GCB_CUDA(cudaEventRecord(t->copy_done[slot], s));
+    GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));  // later kernels see the frames
+    if (first + nframes > t->nframes) t->nframes = first + nframes;
+    return GCB_OK;
+}
+
+int gcb_traj_wait(gcb_traj* t, int slot) {
+    if (!t || slot < 0 || slot > 1) return GCB_ERR_ARG;
+    GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[slot]));
+    return GCB_OK;
+}
+
+int gcb_traj_download(gcb_traj* t, long first, long nframes, double* host_aos) {
+    int rc = check_window(t, first, nframes, true);
+    if (rc) return rc;
+    if (!host_aos && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    const size_t fb = sizeof(double) * 3 * (size_t)t->natoms;
+    const long per = (long)(t->stage_bytes / fb);
+    for (long done = 0; done < nframes; done += per) {
+        const long n = (nframes - done < per) ? nframes - done : per;
+        rc = launch_download_convert(t, t->stream, (double*)t->d_stage[0], first + done, n);
+        if (rc) return rc;
+        GCB_CUDA(cudaMemcpyAsync((char*)host_aos + (size_t)done * fb, t->d_stage[0], (size_t)n * fb, cudaMemcpyDeviceToHost, t->stream));
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    return GCB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// template preparation
+// ---------------------------------------------------------------------------
+namespace {
+
+enum { MODE_ALL = 0, MODE_WEIGHTED = 1, MODE_GATHER = 2 };
+
+// Decide the formulation, validate like the reference, centre the template (centred == true) or
+// keep it raw (no-fit RMSD), and make it resident.  Cached on content so back-to-back calls with the
+// same template and lists (bench loops, LOVO iterations that did not change the set) skip it.
+int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, const int* idx_test, const int* idx_ref,
+                     int nidx, bool centred, int* mode_out) {
+    if (!ref_aos) { set_error("NULL template"); return GCB_ERR_ARG; }
+    if (nidx < 0) { set_error("negative index count"); return GCB_ERR_ARG; }
+    const bool all = (idx_test == nullptr || nidx == 0);
+    if (all && natoms_ref != t->natoms) {
+        set_error("chem.Super: Ill formed coordinates for Superposition (test %d atoms, templa %d)", t->natoms, natoms_ref);
+        return GCB_ERR_SHAPE;
+    }
+    if (natoms_ref <= 0) { set_error("empty template"); return GCB_ERR_SHAPE; }
+    const int* ir = idx_ref ? idx_ref : idx_test;
+    int mode = MODE_ALL;
+    if (!all) {
+        bool same = (natoms_ref == t->natoms);
+        for (int k = 0; k < nidx; k++) {
+            if (idx_test[k] < 0 || idx_test[k] >= t->natoms || ir[k] < 0 || ir[k] >= natoms_ref) {
+                set_error("index %d of the fit lists is out of range (test %d, templa %d)", k, idx_test[k], ir[k]);
+                return GCB_ERR_INDEXES;
+            }
+            same = same && (idx_test[k] == ir[k]);
+        }
+        mode = same ? MODE_WEIGHTED : MODE_GATHER;
+    }
+    *mode_out = mode;
+    gcb::RefCache& c = t->cache;
+    const size_t nref = 3 * (size_t)natoms_ref;
+    if (c.valid && c.mode == mode && c.centred == centred && c.natoms_ref == natoms_ref && c.ref.size() == nref &&
+        memcmp(c.ref.data(), ref_aos, nref * sizeof(double)) == 0 && (int)c.idx_t.size() == (all ? 0 : nidx) &&
+        (all || (memcmp(c.idx_t.data(), idx_test, sizeof(int) * nidx) == 0 && memcmp(c.idx_r.data(), ir, sizeof(int) * nidx) == 0)))
+        return GCB_OK;
+
+    c.valid = false;
+    GCB_CUDA(cudaStreamSynchronize(t->stream));  // h_scratch and the device template may still be in use
+    const int np = t->np;
+    const int n = all ? t->natoms : nidx;
+    // centroid of the template fit subset, rows summed in list order like the 1 x n * n x 3 product of
+    // chem.MassCenter (geometric.go:684-690)
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int k = 0; k < n; k++) {
+        const int i = all ? k : ir[k];
+        s0 += ref_aos[3 * (size_t)i]; s1 += ref_aos[3 * (size_t)i + 1]; s2 += ref_aos[3 * (size_t)i + 2];
+    }
+    const double inv = 1.0 / (double)n;
+    c.bbar[0] = centred ? s0 * inv : 0.0;
+    c.bbar[1] = centred ? s1 * inv : 0.0;
+    c.bbar[2] = centred ? s2 * inv : 0.0;
+    c.n_fit = (double)n;
+    if (mode == MODE_GATHER) {
+        if (nidx > t->idx_cap) {
+            cudaFree(t->d_refpairs); cudaFree(t->d_idx);
+            t->d_refpairs = nullptr; t->d_idx = nullptr; t->idx_cap = 0;
+            GCB_CUDA(cudaMalloc(&t->d_refpairs, sizeof(double) * 3 * (size_t)nidx));
+            GCB_CUDA(cudaMalloc(&t->d_idx, sizeof(int) * (size_t)nidx));
+            t->idx_cap = nidx;
+        }
+        std::vector<double> pairs(3 * (size_t)nidx);
+        for (int k = 0; k < nidx; k++) {
+            const size_t i = (size_t)ir[k];
+            pairs[k] = ref_aos[3 * i] - c.bbar[0];
+            pairs[(size_t)nidx + k] = ref_aos[3 * i + 1] - c.bbar[1];
+            pairs[2 * (size_t)nidx + k] = ref_aos[3 * i + 2] - c.bbar[2];
+        }
+        GCB_CUDA(cudaMemcpyAsync(t->d_refpairs, pairs.data(), sizeof(double) * pairs.size(), cudaMemcpyHostToDevice, t->stream));
+        GCB_CUDA(cudaMemcpyAsync(t->d_idx, idx_test, sizeof(int) * (size_t)nidx, cudaMemcpyHostToDevice, t->stream));
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+    } else {
+        double* h = t->h_scratch;  // [3*np planes | np weights]
+        memset(h, 0, sizeof(double) * 4 * (size_t)np);
+        for (int i = 0; i < t->natoms; i++) {
+            h[i] = ref_aos[3 * (size_t)i] - c.bbar[0];
+            h[np + i] = ref_aos[3 * (size_t)i + 1] - c.bbar[1];
+            h[2 * (size_t)np + i] = ref_aos[3 * (size_t)i + 2] - c.bbar[2];
+        }
+        GCB_CUDA(cudaMemcpyAsync(t->d_refc, h, sizeof(double) * 3 * (size_t)np, cudaMemcpyHostToDevice, t->stream));
+        if (mode == MODE_WEIGHTED) {
+            double* w = h + 3 * (size_t)np;
+            for (int k = 0; k < nidx; k++) w[idx_test[k]] += 1.0;  // multiplicity: a repeated index counts twice, as in SomeVecs
+            GCB_CUDA(cudaMemcpyAsync(t->d_weight, w, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, t->stream));
+        }
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    c.ref.assign(ref_aos, ref_aos + nref);
+    c.idx_t.clear(); c.idx_r.clear();
+    if (!all) { c.idx_t.assign(idx_test, idx_test + nidx); c.idx_r.assign(ir, ir + nidx); }
+    c.natoms_ref = natoms_ref;
+    c.mode = mode;
+    c.centred = centred;
+    c.valid = true;
+    return GCB_OK;
+}
+
+void fill_params(gcb_traj_ext* t, long first, long nframes, int write_back, SuperParams* p) {
+    memset(p, 0, sizeof *p);
+    p->frames = t->d_frames + first * 3L * t->np;
+    p->frames_rw = write_back ? t->d_frames + first * 3L * t->np : nullptr;
+    p->frame_stride = 3L * t->np;
+    p->np = t->np;
+    p->natoms = t->natoms;
+    p->nframes = nframes;
+    p->refc = t->d_refc;
+    p->weight = nullptr;
+    p->n_fit = t->cache.n_fit;
+    p->inv_n = 1.0 / t->cache.n_fit;
+    p->bbar[0] = t->cache.bbar[0]; p->bbar[1] = t->cache.bbar[1]; p->bbar[2] = t->cache.bbar[2];
+    p->rmsd = t->d_rmsd + first;
+    p->rot = t->d_rot + 9 * first;
+    p->trans1 = t->d_t1 + 3 * first;
+    p->trans2 = t->d_t2 + 3 * first;
+    p->devpart = nullptr;
+    p->status = t->d_status;
+}
+
+int ensure_devpart(gcb_traj_ext* t, size_t rows) {
+    if (rows <= t->devpart_rows) return GCB_OK;
+    cudaFree(t->d_devpart);
+    t->d_devpart = nullptr;
+    t->devpart_rows = 0;
+    GCB_CUDA(cudaMalloc(&t->d_devpart, sizeof(double) * rows * (size_t)t->np));
+    t->devpart_rows = rows;
+    return GCB_OK;
+}
+
+int check_status(gcb_traj_ext* t) {
+    int st = 0;
+    GCB_CUDA(cudaMemcpyAsync(&st, t->d_status, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    GCB_CUDA(cudaStreamSynchronize(t->stream));
+    if (st != 0) {
+        cudaMemsetAsync(t->d_status, 0, sizeof(int), t->stream);
+        set_error("RotatorTranslatorToSuper: mat.SVD failed (non-finite correlation matrix in at least one frame)");
+        return GCB_ERR_SVD;
+    }
+    return GCB_OK;
+}
+
+bool use_cluster(const gcb_traj_ext* t) {
+    if (g_variant == GCB_KERNEL_GENERIC) return false;
+    return cluster_kernel_supported(t);
+}
+
+int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                 const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
+    int mode = MODE_ALL;
+    int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode);
+    if (rc) return rc;
+    if (nframes == 0) return GCB_OK;
+    SuperParams p;
+    fill_params(t, first, nframes, write_back, &p);
+    if (mode == MODE_GATHER) {
+        if (want_dev) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
+        return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
+    }
+    if (mode == MODE_WEIGHTED) p.weight = t->d_weight;
+    const bool cluster = use_cluster(t);
+    if (g_variant == GCB_KERNEL_CLUSTER && !cluster) {
+        set_error("cluster kernel requested but not available for %d atoms", t->natoms);
+        return GCB_ERR_ARG;
+    }
+    if (want_dev) {
+        const size_t rows = (size_t)t->sm_count * 8;
+        rc = ensure_devpart(t, rows);
+        if (rc) return rc;
+        GCB_CUDA(cudaMemsetAsync(t->d_devpart, 0, sizeof(double) * rows * (size_t)t->np, t->stream));
+        p.devpart = t->d_devpart;
+    }
+    int rows_used = 0;
+    rc = cluster ? launch_super_cluster(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used)
+                 : launch_super_generic(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used);
+    if (dev_rows) *dev_rows = rows_used;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcb_super_rmsd_async(gcb_traj* tb, long first, long nframes, const double* ref_aos, int natoms_ref,
+                         const int* idx_test, const int* idx_ref, int nidx, int write_back) {
+    int rc = check_window(tb, first, nframes, true);
+    if (rc) return rc;
+    gcb_traj_ext* t = X(tb);
+    GCB_CUDA(cudaSetDevice(t->dev));
+    return launch_super(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back, false, nullptr);
+}
+
+int gcb_fetch_results(gcb_traj* tb, long first, long nframes, double* rmsd, double* rot, double* trans1, double* trans2) {
+    int rc = check_window(tb, first, nframes, false);
+    if (rc) return rc;
+    gcb_traj_ext* t = X(tb);
+    GCB_CUDA(cudaSetDevice(t->dev));
+    cudaStream_t s = t->stream;
+    const size_t n = (size_t)nframes;
+    if (rmsd) GCB_CUDA(cudaMemcpyAsync(rmsd, t->d_rmsd + first, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (rot) GCB_CUDA(cudaMemcpyAsync(rot, t->d_rot + 9 * first, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, s));
+    if (trans1) GCB_CUDA(cudaMemcpyAsync(trans1, t->d_t1 + 3 * first, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    if (trans2) GCB_CUDA(cudaMemcpyAsync(trans2, t->d_t2 + 3 * first, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    return check_status(t);
+}
+
+int gcb_super_rmsd(gcb_traj* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                   const int* idx_ref, int nidx, int write_back, double* rmsd, double* rot, double* trans1, double* trans2) {
+    int rc = gcb_super_rmsd_async(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back);
+    if (rc) return rc;
+    return gcb_fetch_results(t, first, nframes, rmsd, rot, trans1, trans2);
+}
+
+int gcb_rmsd(gcb_traj* tb, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+             const int* idx_ref, int nidx, double* rmsd) {
+    int rc = check_window(tb, first, nframes, true);
+    if (rc) return rc;
+    gcb_traj_ext* t = X(tb);
+    GCB_CUDA(cudaSetDevice(t->dev));
+    int mode = MODE_ALL;
+    rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, false, &mode);
+    if (rc) return rc;
+    if (nframes == 0) return GCB_OK;
+    const double* frames = t->d_frames + first * 3L * t->np;
+    if (mode == MODE_GATHER) rc = launch_rmsd_nofit_gather(t, frames, nframes, t->d_refpairs, t->d_idx, nidx, t->d_rmsd + first);
+    else rc = launch_rmsd_nofit(t, frames, nframes, t->d_refc, mode == MODE_WEIGHTED ? t->d_weight : nullptr, t->cache.n_fit, t->d_rmsd + first);
+    if (rc) return rc;
+    if (rmsd) GCB_CUDA(cudaMemcpyAsync(rmsd, t->d_rmsd + first, sizeof(double) * (size_t)nframes, cudaMemcpyDeviceToHost, t->stream));
+    GCB_CUDA(cudaStreamSynchronize(t->stream));
+    return GCB_OK;
+}
+
+int gcb_timer_start(gcb_traj* t) {
+    if (!t) return GCB_ERR_ARG;
+    GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaEventRecord(t->ev0, t->stream));
+    return GCB_OK;
+}
+
+int gcb_timer_stop(gcb_traj* t, float* ms) {
+    if (!t || !ms) return GCB_ERR_ARG;
+    GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaEventRecord(t->ev1, t->stream));
+    GCB_CUDA(cudaEventSynchronize(t->ev1));
+    GCB_CUDA(cudaEventElapsedTime(ms, t->ev0, t->ev1));
+    return GCB_OK;
+}
+
+int gcb_sync(gcb_traj* t) {
+    if (!t) return GCB_ERR_ARG;
+    GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaStreamSynchronize(t->stream));
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+    return GCB_OK;
+}
+
+int gcb_synth_fill(gcb_traj* tb, long first, long nframes, const double* ref_aos, const double* sigma_atom,
+                   unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32) {
+    int rc = check_window(tb, first, nframes, false);
+    if (rc) return rc;
+    if (!ref_aos || !sigma_atom) { set_error("NULL reference or sigma"); return GCB_ERR_ARG; }
+    gcb_traj_ext* t = X(tb);
+    GCB_CUDA(cudaSetDevice(t->dev));
+    double *d_ref = nullptr, *d_sig = nullptr;
+    GCB_CUDA(cudaMalloc(&d_ref, sizeof(double) * 3 * (size_t)t->natoms));
+    GCB_CUDA(cudaMalloc(&d_sig, sizeof(double) * (size_t)t->natoms));
+    GCB_CUDA(cudaMemcpyAsync(d_ref, ref_aos, sizeof(double) * 3 * (size_t)t->natoms, cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaMemcpyAsync(d_sig, sigma_atom, sizeof(double) * (size_t)t->natoms, cudaMemcpyHostToDevice, t->stream));
+    rc = launch_synth(t, first, nframes, d_ref, d_sig, seed, frame_id0, frame0_is_ref, through_f32);
+    cudaStreamSynchronize(t->stream);
+    cudaFree(d_ref);
+    cudaFree(d_sig);
+    if (rc) return rc;
+    GCB_CUDA(cudaGetLastError());
+    if (first + nframes > t->nframes) t->nframes = first + nframes;
+    return GCB_OK;
+}
+
+}  // extern "C"
+
+// exported for comm.cu
+namespace gcb {
+int peratom_local(gcb_traj* tb, long first, long nframes, const double* ref_aos, const int* idx, int nidx, int write_back) {
+    gcb_traj_ext* t = X(tb);
+    int rows = 0;
+    int rc = launch_super(t, first, nframes, ref_aos, t->natoms, idx, idx, nidx, write_back, true, &rows);
+    if (rc) return rc;
+    if (nframes == 0) {
+        GCB_CUDA(cudaMemsetAsync(t->d_devsum, 0, sizeof(double) * (size_t)t->np, t->stream));
+        return GCB_OK;
+    }
+    return launch_dev_reduce(t, rows, t->d_devsum);
+}
+int peratom_finish(gcb_traj* tb) { return check_status(X(tb)); }
+}  // namespace gcb

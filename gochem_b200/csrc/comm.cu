@@ -1,0 +1,187 @@
+// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink.
+//
+// The reference has no collectives; frames shard across ranks with no data-path
+// exchange.  The one real exchange on this path is LOVO's per-iteration sum of the per-atom
+// deviation vector (what align.RMSDTraj accumulates over all frames, /root/reference/align/lovo.go:
+// 332-336): every rank contributes the sums of its frame shard.  It is done as an all-gather of the
+// per-rank vectors followed by a rank-ordered sum, so every rank holds bit-identical totals (the
+// index sets LOVO derives from them must agree exactly across ranks).
+//
+// NCCL is bound with dlopen at first use so the library itself loads on hosts without NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gcb {
+int peratom_local(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, int write_back);
+int peratom_finish(gcb_traj* t);
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+        }
+    }
+    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
+        set_error("NCCL (libnccl.so.2) is not loadable: %s", api.h ? "missing symbols" : dlerror());
+        return nullptr;
+    }
+    return &api;
+}
+
+#define GCB_NCCL(api, call)                                                                   \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess) {                                                             \
+            gcb::set_error("%s failed: %s", #call, (api)->GetErrorString ? (api)->GetErrorString(r__) : "?"); \
+            return GCB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// out[i] = sum over ranks (ascending) of gathered[r][i]
+__global__ void __launch_bounds__(256) rank_ordered_sum_kernel(const double* __restrict__ gathered, int nranks, long n,
+                                                              double* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < nranks; r++) s += gathered[(long)r * n + i];
+    out[i] = s;
+}
+
+}  // namespace gcb
+
+struct gcb_comm {
+    int dev = 0, nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    double* d_send = nullptr;
+    double* d_gather = nullptr;
+    long cap = 0;
+};
+
+using namespace gcb;
+
+static int comm_reserve(gcb_comm* c, long n) {
+    if (n <= c->cap) return GCB_OK;
+    cudaFree(c->d_send); cudaFree(c->d_gather);
+    c->d_send = c->d_gather = nullptr; c->cap = 0;
+    GCB_CUDA(cudaMalloc(&c->d_send, sizeof(double) * (size_t)n));
+    GCB_CUDA(cudaMalloc(&c->d_gather, sizeof(double) * (size_t)n * (size_t)c->nranks));
+    c->cap = n;
+    return GCB_OK;
+}
+
+// device vector d_vec[n] (on stream s) -> same vector summed over ranks in rank order
+static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s) {
+    NcclApi* api = nccl();
+    if (!api) return GCB_ERR_CUDA;
+    int rc = comm_reserve(c, n);
+    if (rc) return rc;
+    GCB_NCCL(api, api->AllGather(d_vec, c->d_gather, (size_t)n, ncclDouble, c->comm, s));
+    rank_ordered_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->d_gather, c->nranks, n, d_vec);
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
+extern "C" {
+
+int gcb_comm_unique_id(char* id128) {
+    if (!id128) return GCB_ERR_ARG;
+    NcclApi* api = nccl();
+    if (!api) return GCB_ERR_CUDA;
+    ncclUniqueId id;
+    GCB_NCCL(api, api->GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return GCB_OK;
+}
+
+int gcb_comm_init(int dev, int nranks, int rank, const char* id128, gcb_comm** out) {
+    if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad communicator arguments"); return GCB_ERR_ARG; }
+    *out = nullptr;
+    NcclApi* api = nccl();
+    if (!api) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaSetDevice(dev));
+    gcb_comm* c = new gcb_comm();
+    c->dev = dev; c->nranks = nranks; c->rank = rank;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+        delete c;
+        return GCB_ERR_CUDA;
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        api->CommDestroy(c->comm);
+        delete c;
+        return GCB_ERR_CUDA;
+    }
+    *out = c;
+    return GCB_OK;
+}
+
+int gcb_comm_destroy(gcb_comm* c) {
+    if (!c) return GCB_OK;
+    cudaSetDevice(c->dev);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    cudaFree(c->d_send); cudaFree(c->d_gather);
+    NcclApi* api = nccl();
+    if (api && c->comm) api->CommDestroy(c->comm);
+    delete c;
+    return GCB_OK;
+}
+
+int gcb_allreduce_sum_f64(gcb_comm* c, double* host_vec, long n) {
+    if (!c || !host_vec || n <= 0) { set_error("bad allreduce arguments"); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(c->dev));
+    int rc = comm_reserve(c, n);
+    if (rc) return rc;
+    GCB_CUDA(cudaMemcpyAsync(c->d_send, host_vec, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    rc = allreduce_device(c, c->d_send, n, c->stream);
+    if (rc) return rc;
+    GCB_CUDA(cudaMemcpyAsync(host_vec, c->d_send, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    GCB_CUDA(cudaStreamSynchronize(c->stream));
+    return GCB_OK;
+}
+
+int gcb_peratom_dev_sum(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx,
+                        int write_back, gcb_comm* comm, double* sum) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    if (first < 0 || nframes < 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
+    if (!sum) { set_error("NULL output"); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    int rc = peratom_local(t, first, nframes, ref_aos, idx, nidx, write_back);
+    if (rc) return rc;
+    if (comm && comm->nranks > 1) {
+        if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
+        rc = allreduce_device(comm, t->d_devsum, t->natoms, t->stream);
+        if (rc) return rc;
+    }
+    GCB_CUDA(cudaMemcpyAsync(sum, t->d_devsum, sizeof(double) * (size_t)t->natoms, cudaMemcpyDeviceToHost, t->stream));
+    return peratom_finish(t);
+}
+
+}  // extern "C"

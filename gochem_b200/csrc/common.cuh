@@ -1,0 +1,108 @@
+// common.cuh -- shared declarations of libgochem_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/gochem_b200.h"
+
+namespace gcb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long> g_launches;
+extern int g_variant;
+
+#define GCB_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            gcb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return GCB_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define GCB_LAUNCHED() (gcb::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Atoms per plane are padded to a multiple of 16 doubles (128 B) so every plane of every frame
+// starts on a 128-byte boundary: 16-byte TMA bulk copies and double2 loads are always legal.
+constexpr int kPlaneAlign = 16;
+
+// Modes of the fused superposition kernels
+struct SuperParams {
+    const double* frames;   // first frame of the window, SoA planes
+    double* frames_rw;      // same pointer when write_back, else nullptr
+    long frame_stride;      // doubles between frames = 3 * np
+    int np;                 // padded atoms per plane
+    int natoms;             // real atoms
+    long nframes;
+    const double* refc;     // centred reference planes (b - bbar), 3 * np
+    const double* weight;   // np multiplicities (nullptr = all ones)
+    double inv_n;           // 1 / (sum of weights)
+    double n_fit;           // sum of weights
+    double bbar[3];         // centroid of the reference fit subset
+    double* rmsd;           // per frame (window-relative), may be nullptr
+    double* rot;            // 9 per frame
+    double* trans1;         // 3 per frame
+    double* trans2;         // 3 per frame
+    double* devpart;        // [gridDim.x][np] per-CTA per-atom distance sums, nullptr = off
+    int* status;            // set non-zero when a frame's correlation matrix is not finite
+};
+
+}  // namespace gcb
+
+struct gcb_traj {
+    int dev = 0;
+    int natoms = 0;
+    int np = 0;
+    long cap = 0;
+    long nframes = 0;
+    int sm_count = 0;
+    double* d_frames = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    // reference workspace (device)
+    double* d_refc = nullptr;    // 3 * np
+    double* d_weight = nullptr;  // np
+    double* d_refpairs = nullptr;  // gather path: 3 * nidx compact centred template
+    int* d_idx = nullptr;          // gather path: test-side indexes
+    int idx_cap = 0;
+    // per-frame results (cap entries)
+    double* d_rmsd = nullptr;
+    double* d_rot = nullptr;
+    double* d_t1 = nullptr;
+    double* d_t2 = nullptr;
+    int* d_status = nullptr;
+    // LOVO accumulation
+    double* d_devpart = nullptr;
+    size_t devpart_rows = 0;
+    double* d_devsum = nullptr;
+    // host pinned scratch for small transfers
+    double* h_scratch = nullptr;
+    size_t h_scratch_bytes = 0;
+};
+
+namespace gcb {
+// kernels / launchers implemented across the .cu files
+int launch_upload_convert(gcb_traj* t, cudaStream_t s, const void* d_src, long first, long nframes, int layout, double scale);
+int launch_download_convert(gcb_traj* t, cudaStream_t s, double* d_dst, long first, long nframes);
+int launch_super_generic(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* grid_out);
+int launch_super_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx);
+int launch_rmsd_nofit(gcb_traj* t, const double* frames, long nframes, const double* ref_planes, const double* weight,
+                      double n_fit, double* rmsd);
+int launch_rmsd_nofit_gather(gcb_traj* t, const double* frames, long nframes, const double* refpairs_raw, const int* idx,
+                             int nidx, double* rmsd);
+int launch_dev_reduce(gcb_traj* t, int rows, double* out);
+int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos, const double* d_sigma,
+                 unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
+bool cluster_kernel_supported(const gcb_traj* t);
+int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out);
+}  // namespace gcb

@@ -1,0 +1,135 @@
+/*
+ * gochem_b200.h -- C ABI of the B200 superposition / RMSD / LOVO device path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status returns
+ * (0 = ok, like the reference's only FFI precedent, traj/xtc/libgoxtc.c:87-104), opaque
+ * handles closed explicitly (traj/xtc/xtc.go:173-183).  A cgo binding for the reference's Go
+ * packages is shown in INTEGRATION.md.  Every entry point sets the CUDA device of the handle it
+ * is given (cgo calls may hop OS threads) and is synchronous unless its name ends in _async.
+ *
+ * Coordinates cross the boundary as the reference stores them: float64, row-major N x 3 (AoS
+ * xyz), v3.Matrix (v3/gonum.go:54-58).  Reader staging may also hand over float32 AoS
+ * (xtc, traj/xtc/xtc.go:129-134) or float32 SoA planes (dcd, traj/dcd/dcd.go:380-413).
+ * On the device frames live as float64 SoA planes (x[], y[], z[] per frame).
+ *
+ * There is no CPU fallback: without a usable CUDA device every compute call fails with
+ * GCB_ERR_CUDA and gcb_last_error() says why.
+ */
+#ifndef GOCHEM_B200_H
+#define GOCHEM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define GCB_OK 0
+#define GCB_ERR_SHAPE -1     /* "Ill-formed matrices" (geometric.go:130-132), "Ill formed coordinates" (handy.go:199-201) */
+#define GCB_ERR_INDEXES -2   /* "Indexes don't match molecules" (handy.go:190) */
+#define GCB_ERR_SVD -4       /* "mat.SVD failed" (geometric.go:155-157): non-finite correlation matrix */
+#define GCB_ERR_ALLOC -5
+#define GCB_ERR_CUDA -7      /* CUDA runtime / driver / NCCL failure; see gcb_last_error */
+#define GCB_ERR_ARG -8       /* NULL handle, out-of-range frame window, bad enum */
+#define GCB_EOF 11           /* end of trajectory, same value libgoxtc returns (xtc.go:204-213) */
+
+/* host layouts accepted by gcb_traj_upload */
+#define GCB_F64_AOS 0 /* float64 [frame][atom][xyz]  -- v3.Matrix.RawSlice (v3/gonum.go:93-95) */
+#define GCB_F32_AOS 1 /* float32 [frame][atom][xyz]  -- libxdrfile output (libgoxtc.c:87-104) */
+#define GCB_F32_SOA 2 /* float32 [frame][xyz][atom]  -- DCD records (dcd.go:380-413) */
+
+/* kernel variants (gcb_set_kernel_variant): AUTO picks the fastest one the shape allows */
+#define GCB_KERNEL_AUTO 0
+#define GCB_KERNEL_GENERIC 1 /* one CTA per frame, second pass re-reads the frame from L2 */
+#define GCB_KERNEL_CLUSTER 2 /* TMA bulk-staged frame parts resident in shared memory, CTA cluster per frame */
+
+typedef struct gcb_traj gcb_traj; /* device-resident trajectory: cap_frames x natoms, float64 SoA */
+typedef struct gcb_comm gcb_comm; /* NCCL communicator wrapper */
+
+/* ---- library ---- */
+int gcb_version(void);
+/* Copies the calling thread's last error message; returns its length. */
+size_t gcb_last_error(char *buf, size_t cap);
+int gcb_device_count(int *n);
+/* Properties the host side sizes its work by: SM count, bytes of device memory, compute capability. */
+int gcb_device_info(int dev, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
+int gcb_set_kernel_variant(int variant);
+
+/* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
+int gcb_pinned_alloc(size_t bytes, void **p);
+int gcb_pinned_free(void *p);
+
+/* ---- device trajectory: the v3 device-matrix batch ---- */
+int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj **out);
+int gcb_traj_destroy(gcb_traj *t);
+int gcb_traj_natoms(const gcb_traj *t);
+long gcb_traj_capacity(const gcb_traj *t);
+long gcb_traj_nframes(const gcb_traj *t);
+int gcb_traj_set_nframes(gcb_traj *t, long nframes);
+/* Copy nframes host frames into slots [first, first+nframes); every coordinate is multiplied by
+ * scale while widening (xtc: 10.0, nm -> A, xtc.go:129-134; otherwise 1.0).  Blocks until the
+ * data is resident. */
+int gcb_traj_upload(gcb_traj *t, long first, const void *host, long nframes, int layout, double scale);
+/* Same, from a gcb_pinned_alloc buffer, on copy stream `slot` (0 or 1); returns once queued.
+ * The buffer may be reused after gcb_traj_wait(t, slot). */
+int gcb_traj_upload_async(gcb_traj *t, long first, const void *pinned, long nframes, int layout, double scale, int slot);
+int gcb_traj_wait(gcb_traj *t, int slot);
+/* Frames back to float64 AoS (what chem.Super leaves in `test`, handy.go:207-213). */
+int gcb_traj_download(gcb_traj *t, long first, long nframes, double *host_aos);
+
+/* ---- chem.Super + chem.RMSD over frames [first, first+nframes) ----
+ * Replaces the per-frame loop  chem.Super(frame, ref, idx_test, idx_ref)  (handy.go:175-214,
+ * geometric.go:127-208) followed by  chem.RMSD(frame, ref, idx_test, idx_ref)
+ * (geometric.go:232-288).
+ *   ref_aos   : template, natoms_ref x 3 float64 row-major (host).
+ *   idx_test / idx_ref, nidx : fit subset; NULL/0 = all atoms (handy.go:178-180).  Both lists must
+ *               have nidx entries; idx_ref == NULL with idx_test given means "same list".
+ *   write_back: 1 = frames are replaced by (frame + trans1) * R + trans2 for ALL atoms, the
+ *               reference's in-place semantics (handy.go:207-211); 0 = frames untouched.
+ *   rmsd[F]   : RMSD over the fit subset after the fit (explicit residual, geometric.go:284-286).
+ *   rot[9F]   : rotation, row-major, right-multiplying row vectors (geometric.go:180-188).
+ *   trans1[3F]: -centroid(test subset) (geometric.go:206).  trans2[3F]: Translation (:191-200).
+ *   Any output pointer may be NULL.  All outputs are host memory. */
+int gcb_super_rmsd(gcb_traj *t, long first, long nframes, const double *ref_aos, int natoms_ref,
+                   const int *idx_test, const int *idx_ref, int nidx, int write_back,
+                   double *rmsd, double *rot, double *trans1, double *trans2);
+/* Launch only: results stay in the handle's device buffers until gcb_fetch_results.  Used to time the
+ * kernel with inputs resident (bench.py `value`). */
+int gcb_super_rmsd_async(gcb_traj *t, long first, long nframes, const double *ref_aos, int natoms_ref,
+                         const int *idx_test, const int *idx_ref, int nidx, int write_back);
+int gcb_fetch_results(gcb_traj *t, long first, long nframes, double *rmsd, double *rot, double *trans1, double *trans2);
+
+/* chem.RMSD / chem.MemRMSD without superposition (geometric.go:232-288) for every frame. */
+int gcb_rmsd(gcb_traj *t, long first, long nframes, const double *ref_aos, int natoms_ref,
+             const int *idx_test, const int *idx_ref, int nidx, double *rmsd);
+
+/* ---- align.RMSDTraj inner pass (align/lovo.go:265-281, 328-340) ----
+ * For every frame: Super on the idx subset (both sides), then MemPerAtomRMSD against ref for ALL
+ * atoms; sum[i] = sum over frames of |frame_i - ref_i| (not divided).  write_back as above.
+ * sum is host memory, natoms doubles.  With comm != NULL the per-rank sums are combined across
+ * ranks (all-gather + rank-ordered sum, bit-identical on every rank). */
+int gcb_peratom_dev_sum(gcb_traj *t, long first, long nframes, const double *ref_aos,
+                        const int *idx, int nidx, int write_back, gcb_comm *comm, double *sum);
+
+/* ---- stream timing on the stream the kernels run on ---- */
+int gcb_timer_start(gcb_traj *t);
+int gcb_timer_stop(gcb_traj *t, float *ms);
+int gcb_sync(gcb_traj *t);
+/* Number of kernels this library has launched since load (bench.py gpu_launches). */
+long gcb_launch_count(void);
+
+/* ---- synthetic trajectories generated on the device (bench / tests only) ---- */
+int gcb_synth_fill(gcb_traj *t, long first, long nframes, const double *ref_aos, const double *sigma_atom,
+                   unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---- */
+int gcb_comm_unique_id(char *id128);                       /* rank 0 creates, host side broadcasts the 128 bytes */
+int gcb_comm_init(int dev, int nranks, int rank, const char *id128, gcb_comm **out);
+int gcb_comm_destroy(gcb_comm *c);
+int gcb_allreduce_sum_f64(gcb_comm *c, double *host_vec, long n); /* all-gather + rank-ordered sum */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOCHEM_B200_H */

@@ -198,6 +198,17 @@ static void mass_center(const double *in, int n, double *out, double *cen) {
     }
 }
 
+static __thread double *t_scratch[4];
+static __thread size_t t_scratch_n[4];
+static double *scratch_get(int slot, size_t n) {
+    if (t_scratch_n[slot] < n) {
+        free(t_scratch[slot]);
+        t_scratch[slot] = (double *)malloc(sizeof(double) * n);
+        t_scratch_n[slot] = t_scratch[slot] ? n : 0;
+    }
+    return t_scratch[slot];
+}
+
 /* ------------------------------------------------------------------ */
 /* chem.RotatorTranslatorToSuper (geometric.go:127-208).                 */
 /* test, templa: n x 3 row-major.  Outputs: transformed (n x 3, may be    */
@@ -211,13 +222,11 @@ static void mass_center(const double *in, int n, double *out, double *cen) {
 int orc_rotator_translator(const double *test, const double *templa, int n, double *transformed,
                            double *rot, double *trans1, double *trans2, int as_written) {
     if (n <= 0) return ORC_ERR_SHAPE; /* :130-132 */
-    double *ctest = (double *)malloc(sizeof(double) * 3 * (size_t)n);
-    double *ctempla = (double *)malloc(sizeof(double) * 3 * (size_t)n);
-    if (!ctest || !ctempla) {
-        free(ctest);
-        free(ctempla);
-        return ORC_ERR_ALLOC;
-    }
+    /* per-thread scratch instead of the reference's per-call allocations (the Go allocator is
+     * thread-cached; glibc would mmap/munmap 2 x 24n bytes per frame and serialise the workers) */
+    double *ctest = scratch_get(0, 3 * (size_t)n);
+    double *ctempla = scratch_get(1, 3 * (size_t)n);
+    if (!ctest || !ctempla) return ORC_ERR_ALLOC;
     double distest[3], distempla[3];
     double scal = 1.0 / (double)n;           /* :133-134 */
     mass_center(test, n, ctest, distest);     /* :136 */
@@ -233,8 +242,6 @@ int orc_rotator_translator(const double *test, const double *templa, int n, doub
             free(mid);
             free(sjp);
             free(aux2);
-            free(ctest);
-            free(ctempla);
             return ORC_ERR_ALLOC;
         }
         for (int i = 0; i < n; i++) mid[(size_t)i * n + i] = 1.0;
@@ -275,8 +282,6 @@ int orc_rotator_translator(const double *test, const double *templa, int n, doub
 
     double u[9], v[9], s[3];
     if (orc_svd3(h, u, s, v) != ORC_OK) { /* :154-157 */
-        free(ctest);
-        free(ctempla);
         return ORC_ERR_SVD;
     }
     for (int i = 0; i < 9; i++) { /* U.Scale(-1), V.Scale(-1) :174-175 */
@@ -324,8 +329,6 @@ int orc_rotator_translator(const double *test, const double *templa, int n, doub
     trans1[0] = -1.0 * distest[0]; /* :206 */
     trans1[1] = -1.0 * distest[1];
     trans1[2] = -1.0 * distest[2];
-    free(ctest);
-    free(ctempla);
     return ORC_OK;
 }
 

@@ -1,0 +1,54 @@
+"""Regenerates tests/golden/*.npz.
+
+The Go reference cannot run here (no Go toolchain), so these vectors come from oracle/oracle_np.py
+(numpy + LAPACK gesvd, the closest stand-in for gonum's Dgesvd) on seeded synthetic inputs.  They pin
+the oracle and the CUDA path against accidental change; they are NOT outputs of the reference itself
+(parity unpinned, DESIGN.md "Oracle").   Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from gochem_b200 import synth  # noqa: E402
+from oracle import oracle_np as onp  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def super_case(name, natoms, nframes, idx=None, frame0_is_ref=True):
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=frame0_is_ref, through_f32=True)
+    rm, rot, t1, t2 = [], [], [], []
+    moved = []
+    for f in range(nframes):
+        if idx is None:
+            _, r, a, b = onp.rotator_translator_to_super(frames[f], ref)
+            m = onp.super_(frames[f], ref)
+            rm.append(onp.mem_rmsd(m, ref))
+        else:
+            _, r, a, b = onp.rotator_translator_to_super(frames[f][idx], ref[idx])
+            m = onp.super_(frames[f], ref, idx, idx)
+            rm.append(onp.mem_rmsd(m, ref, idx, idx))
+        rot.append(r); t1.append(a); t2.append(b); moved.append(m)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ref=ref.astype(np.float32), frames=frames.astype(np.float32),
+                        idx=np.array([] if idx is None else idx, dtype=np.int32), rmsd=np.array(rm), rot=np.array(rot),
+                        trans1=np.array(t1), trans2=np.array(t2), moved_first=moved[1], moved_last=moved[-1])
+
+
+def lovo_case(name, natoms, nframes, cpus):
+    ref, frames = synth.make_case(natoms, nframes, through_f32=True)
+    res = onp.lovo(frames, ref, list(range(natoms)), cpus, less_than_rmsd=1.0, minimum_n=10)
+    rm, total = onp.rmsd_traj(frames, ref, list(range(natoms)), cpus)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ref=ref.astype(np.float32), frames=frames.astype(np.float32),
+                        cpus=cpus, N=res["N"], Natoms=res["Natoms"], RMSD=res["RMSD"], FramesRead=res["FramesRead"],
+                        Iterations=res["Iterations"], first_pass_rmsd=rm, first_pass_frames=total)
+
+
+if __name__ == "__main__":
+    super_case("super_all_n50", 50, 6)
+    super_case("super_subset_n203", 203, 5, idx=list(range(3, 203, 4)))
+    super_case("super_cfg1_sample_n1500", 1500, 6)
+    lovo_case("lovo_n150_f42", 150, 42, 4)
+    print("written", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

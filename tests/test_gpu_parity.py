@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances are BASELINE.json's: RMSD and translations within 1e-9 A, rotations within 1e-10
+(entries are <= 1, so absolute = relative to the matrix norm), LOVO index sets identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gochem_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_RMSD = 1e-9
+TOL_ROT = 1e-10
+TOL_XYZ = 1e-9
+
+VARIANTS = [_lib.KERNEL_GENERIC, _lib.KERNEL_AUTO]
+
+
+@pytest.fixture(params=VARIANTS, ids=["generic", "auto"])
+def variant(request):
+    _lib.check(_lib.load().gcb_set_kernel_variant(request.param))
+    yield request.param
+    _lib.load().gcb_set_kernel_variant(_lib.KERNEL_AUTO)
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def device_traj(frames):
+    t = _lib.DeviceTraj(frames.shape[1], frames.shape[0])
+    t.upload(frames)
+    return t
+
+
+@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
+def test_golden_vectors(golden_dir, name, variant):
+    g = load(golden_dir, name)
+    ref = g["ref"].astype(np.float64)
+    frames = g["frames"].astype(np.float64)
+    idx = g["idx"] if g["idx"].size else None
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, idx, idx)
+    assert np.abs(out["rmsd"] - g["rmsd"]).max() < TOL_RMSD
+    assert np.abs(out["rot"] - g["rot"]).max() < TOL_ROT
+    assert np.abs(out["trans1"] - g["trans1"]).max() < TOL_XYZ
+    assert np.abs(out["trans2"] - g["trans2"]).max() < TOL_XYZ
+    # frames untouched without write_back
+    assert np.array_equal(t.download(), frames)
+    out2 = t.super_rmsd(ref, idx, idx, write_back=True)
+    moved = t.download()
+    assert np.abs(moved[1] - g["moved_first"]).max() < TOL_XYZ
+    assert np.abs(moved[-1] - g["moved_last"]).max() < TOL_XYZ
+    assert np.abs(out2["rmsd"] - g["rmsd"]).max() < TOL_RMSD
+    t.close()
+
+
+def test_config1_full_vs_oracle(variant):
+    """BASELINE.json configs[0]: 1000 frames x 1500 atoms against frame 0."""
+    ref, frames = synth.make_case(1500, 1000, frame0_is_ref=True)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, write_back=True)
+    moved = t.download()
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None, write_back=True, nthreads=8)  # frames now superposed
+    assert out["rmsd"][0] < 1e-12  # frame 0 is the reference: explicit residual, no cancellation
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
+    assert np.abs(out["rot"] - rot).max() < TOL_ROT
+    assert np.abs(out["trans1"] - t1).max() < TOL_XYZ
+    assert np.abs(out["trans2"] - t2).max() < TOL_XYZ
+    assert np.abs(moved - frames).max() < TOL_XYZ
+    t.close()
+
+
+@pytest.mark.parametrize("natoms", [3, 17, 255, 256, 257, 1000, 4097])
+def test_ragged_sizes(natoms, variant):
+    ref, frames = synth.make_case(natoms, 5)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref)
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None)
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
+    assert np.abs(out["rot"] - rot).max() < (TOL_ROT if natoms > 3 else 1e-8)
+    t.close()
+
+
+def test_weighted_subset_with_duplicates(variant):
+    ref, frames = synth.make_case(300, 7)
+    idx = np.array(list(range(0, 300, 3)) + [3, 3, 9])  # repeated atoms count twice (SomeVecs copies rows)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, idx, idx, write_back=True)
+    moved = t.download()
+    for f in range(7):
+        s, r, a, b = oracle.super_(frames[f], ref, idx, idx, details=True)
+        assert np.abs(moved[f] - s).max() < TOL_XYZ
+        assert np.abs(out["rot"][f] - r).max() < TOL_ROT
+        assert abs(out["rmsd"][f] - oracle.rmsd(s, ref, idx, idx)) < TOL_RMSD
+    t.close()
+
+
+def test_gather_lists_and_smaller_template(variant):
+    ref, frames = synth.make_case(120, 4)
+    rng = np.random.default_rng(0)
+    it = rng.permutation(120)[:40]
+    ir = it.copy()
+    t = device_traj(frames)
+    # same pairs expressed through a permuted, smaller template: templa = ref[ir], lists (it, 0..39)
+    templa = ref[ir]
+    out = t.super_rmsd(templa, it, np.arange(40), write_back=True)
+    moved = t.download()
+    for f in range(4):
+        s, r, a, b = oracle.super_(frames[f], templa, it, np.arange(40), details=True)
+        assert np.abs(moved[f] - s).max() < TOL_XYZ
+        assert np.abs(out["rot"][f] - r).max() < TOL_ROT
+        assert abs(out["rmsd"][f] - oracle.rmsd(s, templa, it, np.arange(40))) < TOL_RMSD
+    # genuinely different pairing
+    t.upload(frames)
+    ir2 = rng.permutation(120)[:40]
+    out = t.super_rmsd(ref, it, ir2)
+    for f in range(4):
+        s, r, a, b = oracle.super_(frames[f], ref, it, ir2, details=True)
+        assert np.abs(out["rot"][f] - r).max() < 1e-8  # ill-conditioned on purpose (random pairing)
+        assert abs(out["rmsd"][f] - oracle.rmsd(s, ref, it, ir2)) < 1e-8
+    t.close()
+
+
+def test_rmsd_without_fit(variant):
+    ref, frames = synth.make_case(500, 6)
+    idx = np.arange(10, 400, 7)
+    t = device_traj(frames)
+    got = t.rmsd(ref)
+    got_idx = t.rmsd(ref, idx, idx)
+    got_pairs = t.rmsd(ref, idx, idx[::-1].copy())
+    for f in range(6):
+        assert abs(got[f] - oracle.rmsd(frames[f], ref)) < 1e-9 * max(1, got[f])
+        assert abs(got_idx[f] - oracle.rmsd(frames[f], ref, idx, idx)) < 1e-9 * max(1, got_idx[f])
+        assert abs(got_pairs[f] - oracle.rmsd(frames[f], ref, idx, idx[::-1].copy())) < 1e-9 * max(1, got_pairs[f])
+    t.close()
+
+
+def test_host_layouts_and_scale():
+    ref, frames = synth.make_case(77, 5, through_f32=True)
+    f32 = frames.astype(np.float32)
+    t = _lib.DeviceTraj(77, 5)
+    t.upload(f32, layout=_lib.F32_AOS)
+    assert np.array_equal(t.download(), frames)
+    soa = np.ascontiguousarray(f32.transpose(0, 2, 1))  # DCD: x[], y[], z[] per frame
+    t.upload(soa, layout=_lib.F32_SOA)
+    assert np.array_equal(t.download(), frames)
+    t.upload(f32, layout=_lib.F32_AOS, scale=10.0)  # xtc nm -> A, 10*float64(c) (xtc.go:131)
+    assert np.array_equal(t.download(), 10.0 * frames)
+    # partial window
+    t.upload(frames[:2], first=3)
+    d = t.download()
+    assert np.array_equal(d[3:], frames[:2])
+    t.close()
+
+
+def test_pinned_async_upload():
+    ref, frames = synth.make_case(64, 8, through_f32=True)
+    t = _lib.DeviceTraj(64, 8)
+    pb = [_lib.PinnedBuffer(4 * 64 * 3 * 4) for _ in range(2)]
+    f32 = frames.astype(np.float32)
+    for k in range(2):
+        v = pb[k].view(np.float32, (4, 64, 3))
+        v[...] = f32[4 * k:4 * k + 4]
+        t.upload_async(v, 4, 4 * k, _lib.F32_AOS, 1.0, k)
+    out = t.super_rmsd(ref)
+    t.wait(0); t.wait(1)
+    rm, *_ = oracle.super_rmsd_traj(frames, ref, None)
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
+    for p in pb:
+        p.free()
+    t.close()
+
+
+def test_peratom_dev_sum_matches_rmsdtraj(variant):
+    ref, frames = synth.make_case(333, 24)
+    idx = np.arange(0, 333, 2)
+    t = device_traj(frames)
+    got = t.peratom_dev_sum(ref, idx)
+    want, total = oracle.rmsd_traj(frames, ref, idx, cpus=4)
+    assert total == 24
+    assert np.abs(got / 24.0 - want).max() < 1e-10
+    # all atoms, write back the aligned trajectory (writeTraj path, lovo.go:337-339)
+    t.upload(frames)
+    got = t.peratom_dev_sum(ref, None, write_back=True)
+    want, total, aligned = oracle.rmsd_traj(frames, ref, np.arange(333), cpus=4, want_aligned=True)
+    assert np.abs(got / 24.0 - want).max() < 1e-10
+    assert np.abs(t.download() - aligned).max() < TOL_XYZ
+    t.close()
+
+
+def test_errors_mirror_the_reference():
+    ref, frames = synth.make_case(50, 3)
+    t = device_traj(frames)
+    with pytest.raises(_lib.GcbError) as e:
+        t.super_rmsd(ref[:40])  # "Ill formed coordinates for Superposition"
+    assert e.value.code == _lib.ERR_SHAPE
+    with pytest.raises(_lib.GcbError) as e:
+        t.super_rmsd(ref, np.array([1, 2, 99]), np.array([1, 2, 3]))
+    assert e.value.code == _lib.ERR_INDEXES
+    with pytest.raises(_lib.GcbError) as e:
+        t.super_rmsd(ref, first=2, nframes=5)
+    assert e.value.code == _lib.ERR_ARG
+    bad = frames.copy()
+    bad[1, 7, 2] = np.nan
+    t.upload(bad)
+    with pytest.raises(_lib.GcbError) as e:
+        t.super_rmsd(ref)  # mat.SVD failed
+    assert e.value.code == _lib.ERR_SVD
+    t.upload(frames)
+    assert np.isfinite(t.super_rmsd(ref)["rmsd"]).all()  # the error flag does not stick
+    t.close()
+
+
+def test_empty_window_is_a_noop():
+    ref, frames = synth.make_case(20, 2)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, first=1, nframes=0)
+    assert out["rmsd"].size == 0
+    t.close()
+
+
+def test_device_synth_properties_full_size(variant):
+    """Size-independent properties on a device-generated trajectory with the shape of
+    BASELINE.json configs[1] scaled to fit the test budget (10k atoms; 20k frames = 4.8 GB)."""
+    natoms, nframes = 10000, 20000
+    ref = synth.make_reference(natoms)
+    sig = synth.atom_sigmas(natoms)
+    t = _lib.DeviceTraj(natoms, nframes)
+    t.synth_fill(ref, sig, nframes, frame0_is_ref=True)
+    out = t.super_rmsd(ref)
+    assert out["rmsd"][0] < 1e-12
+    assert (out["rmsd"][1:] > 0.5).all() and (out["rmsd"] < 5).all()
+    # sampled frames against the oracle, on the exact bytes the GPU holds
+    for f in [0, 1, 4999, 19999]:
+        fr = t.download(f, 1)[0]
+        s, r, a, b = oracle.super_(fr, ref, details=True)
+        assert abs(out["rmsd"][f] - oracle.rmsd(s, ref)) < TOL_RMSD
+        assert np.abs(out["rot"][f] - r).max() < TOL_ROT
+        assert np.abs(out["trans1"][f] - a).max() < TOL_XYZ
+    # rotations are proper and orthogonal
+    rr = out["rot"]
+    assert np.abs(np.einsum("fij,fkj->fik", rr, rr) - np.eye(3)).max() < 1e-13
+    assert np.abs(np.linalg.det(rr) - 1).max() < 1e-13
+    # Super in place, then: RMSD without fit equals the fitted RMSD; a second Super is the identity
+    out_wb = t.super_rmsd(ref, write_back=True)
+    assert np.abs(out_wb["rmsd"] - out["rmsd"]).max() < 1e-12
+    nofit = t.rmsd(ref)
+    assert np.abs(nofit - out["rmsd"]).max() < TOL_RMSD
+    again = t.super_rmsd(ref)
+    assert np.abs(again["rot"] - np.eye(3)).max() < 1e-10
+    assert np.abs(again["rmsd"] - out["rmsd"]).max() < TOL_RMSD
+    # rigid copies of the reference give zero
+    t.synth_fill(ref, np.zeros(natoms), 2000)
+    z = t.super_rmsd(ref, nframes=2000)
+    assert z["rmsd"].max() < 1e-11
+    t.close()
