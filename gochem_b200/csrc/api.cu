@@ -96,6 +96,16 @@ int gcb_set_kernel_variant(int variant) {
     return GCB_OK;
 }
 
+int gcb_set_cluster_tuning(int cluster, int stages, int depth) {
+    if (!(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16) || stages < 0 ||
+        stages > 8 || depth < 0 || depth > 3) {
+        set_error("bad cluster tuning (%d, %d, %d)", cluster, stages, depth);
+        return GCB_ERR_ARG;
+    }
+    set_cluster_tuning(cluster, stages, depth == 0 ? -1 : depth);
+    return GCB_OK;
+}
+
 long gcb_launch_count(void) { return g_launches.load(); }
 
 int gcb_pinned_alloc(size_t bytes, void** p) {

@@ -1,9 +1,544 @@
-// super_cluster.cu -- placeholder until the shared-memory-resident cluster kernel lands.
+// super_cluster.cu -- the B200 path of the fused superposition + RMSD pass.
+//
+// Same arithmetic as super_generic.cu (chem.Super -> RotatorTranslatorToSuper -> MemRMSD /
+// MemPerAtomRMSD, /root/reference/handy.go:175-214, geometric.go:127-208, :258-321), organised so
+// that every byte of a frame crosses HBM -> SM exactly once and nothing else is re-read per frame:
+//
+//  * A thread-block cluster of C CTAs owns one frame at a time; CTA rank r always owns atoms
+//    [r*P, (r+1)*P).  The kernel is persistent: cluster g handles frames g, g+G, g+2G, ...
+//  * One producer thread per CTA streams its part of each frame (three plane segments) into a ring
+//    of S shared-memory stages with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) and an
+//    L2 evict-first policy; full/empty mbarriers hand stages to the consumers and back.
+//  * 256 consumer threads each own K fixed atom slots of the part.  The centred template b' and the
+//    weights of those slots live in REGISTERS for the whole kernel, so the template costs no
+//    shared-memory or L2 bandwidth per frame.
+//  * Pass 1 (S = sum w a, H = sum (w a) b'^T) reads the stage once; a 15-shuffle halving butterfly
+//    and a fixed-order cross-warp sum give the CTA's 12 partial sums, which 12 threads push to every
+//    CTA of the cluster with st.async (data + mbarrier complete_tx in one DSMEM transaction).
+//  * A solver warp per CTA adds the C partials in rank order (bit-identical in every CTA), solves the
+//    3x3 problem (kabsch3.cuh) and publishes R and centroid*R.
+//  * Pass 2 of a frame runs D iterations after its pass 1, from the SAME shared-memory stage, so the
+//    exchange + solve latency is hidden behind the pass 1 of the following frames.  It produces the
+//    explicit residual (RMSD), LOVO's per-atom distance sums (registers, written once at the end)
+//    and, on request, the superposed coordinates.
+//
+// Per-frame squared-error partials go to a small global array and a trailing kernel finishes
+// rmsd[f] = sqrt(sum_r E[f][r] / n) in rank order.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "kabsch3.cuh"
+
 namespace gcb {
-bool cluster_kernel_supported(const gcb_traj*) { return false; }
-int launch_super_cluster(gcb_traj*, const SuperParams&, bool, bool, int*) {
-    set_error("cluster kernel not built");
+
+namespace {
+
+constexpr int kConsumers = 256;          // consumer threads per CTA
+constexpr int kConsumerWarps = 8;
+constexpr int kThreadsCta = kConsumers + 64;  // + producer warp + solver warp
+constexpr int kMaxStages = 8;
+constexpr int kMaxSlots = 7;             // exchange slots, 2*D+1 with D <= 3
+constexpr int kMaxCluster = 16;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct ClusterParams {
+    SuperParams p;
+    int cluster;        // C
+    int part;           // P: atoms per CTA (multiple of 16)
+    int stages;         // S
+    int depth;          // D
+    int slots;          // NS = 2*D+1
+    int nclusters;      // G
+    int write_back;
+    double* epart;      // [nframes][C] squared-error partials
+};
+
+// ---- PTX helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// wait that also acquires writes made by other CTAs of the cluster (st.async partial sums)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// 12 per-lane values -> warp totals with 15 shuffles (halving butterfly).  On return, lanes with
+// (lane & 3) == 0 hold: t0 = total of value 6*b4 + 3*b3 + 2*b2, t1 = total of value 6*b4 + 3*b3 + 1,
+// where b4, b3, b2 are lane bits 4, 3, 2.  Fixed tree -> deterministic.
+__device__ __forceinline__ void warp_reduce12(const double (&v)[12], int lane, double& t0, double& t1) {
+    double w[6], u[3];
+    const bool h16 = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const double send = h16 ? v[j] : v[j + 6];
+        const double keep = h16 ? v[j + 6] : v[j];
+        w[j] = keep + shx(send, 16);
+    }
+    const bool h8 = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const double send = h8 ? w[j] : w[j + 3];
+        const double keep = h8 ? w[j + 3] : w[j];
+        u[j] = keep + shx(send, 8);
+    }
+    const bool h4 = lane & 4;
+    {
+        const double send = h4 ? u[0] : u[2];
+        const double keep = h4 ? u[2] : u[0];
+        t0 = keep + shx(send, 4);
+        t1 = u[1] + shx(u[1], 4);
+    }
+    t0 += shx(t0, 2); t1 += shx(t1, 2);
+    t0 += shx(t0, 1); t1 += shx(t1, 1);
+}
+
+struct __align__(16) Shared {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t part_full[kMaxSlots];
+    uint64_t solved[kMaxSlots];
+    double partials[kMaxSlots][kMaxCluster][12];
+    double xf[kMaxSlots][16];             // R[9], centroid*R [3]
+    double red[2][kConsumerWarps][14];    // cross-warp scratch, double-buffered by iteration parity
+};
+
+template <int K, bool WEIGHTED, bool DEV>
+__global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+    constexpr int kStageDoubles = 3 * K * kConsumers;
+    double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 127) / 128) * 128);
+
+    const SuperParams& p = cp.p;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int C = cp.cluster, S = cp.stages, D = cp.depth, NS = cp.slots, G = cp.nclusters;
+    const uint32_t rank = cluster_ctarank();
+    const long cid = cluster_id_x();
+    const int part0 = (int)rank * cp.part;                       // first atom of this CTA's part
+    int part_len = p.np - part0;                                 // atoms (incl. padding) actually loaded
+    if (part_len > cp.part) part_len = cp.part;
+    if (part_len < 0) part_len = 0;
+    const long nloc = (cid < p.nframes) ? (p.nframes - cid + G - 1) / G : 0;   // frames of this cluster
+
+    // zero the stage ring once: slots beyond part_len are never written by TMA and must read as 0
+    for (int i = tid; i < S * kStageDoubles; i += kThreadsCta) stage_base[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kConsumerWarps); }
+        for (int s = 0; s < NS; s++) { mbar_init(&sh.part_full[s], 1); mbar_init(&sh.solved[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // make the zero-fill (generic proxy) visible to the async proxy before any TMA write lands next to it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == kConsumerWarps + 1 && lane == 0) {
+        for (int s = 0; s < NS; s++) mbar_arrive_expect_tx(&sh.part_full[s], (uint32_t)(C * 12 * sizeof(double)));
+    }
+    cluster_sync_all();   // every CTA's barriers are initialised and armed before any remote store
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer =====================
+        if (lane == 0 && part_len > 0) {
+            const uint64_t pol = policy_evict_first();
+            const uint32_t seg_bytes = (uint32_t)part_len * 8u;
+            for (long j = 0; j < nloc; j++) {
+                const int s = (int)(j % S);
+                if (j >= S) mbar_wait(&sh.empty[s], (uint32_t)(((j / S) - 1) & 1));
+                const double* src = p.frames + (cid + j * G) * p.frame_stride + part0;
+                double* dst = stage_base + (long)s * kStageDoubles;
+                mbar_arrive_expect_tx(&sh.full[s], 3u * seg_bytes);
+                tma_load_1d(dst, src, seg_bytes, &sh.full[s], pol);
+                tma_load_1d(dst + K * kConsumers, src + p.np, seg_bytes, &sh.full[s], pol);
+                tma_load_1d(dst + 2 * K * kConsumers, src + 2L * p.np, seg_bytes, &sh.full[s], pol);
+            }
+        } else if (lane == 0) {
+            // an empty part still has to complete the full barriers its consumers wait on
+            for (long j = 0; j < nloc; j++) {
+                const int s = (int)(j % S);
+                if (j >= S) mbar_wait(&sh.empty[s], (uint32_t)(((j / S) - 1) & 1));
+                mbar_arrive(&sh.full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == kConsumerWarps + 1) {
+        // ===================== solver =====================
+        for (long j = 0; j < nloc; j++) {
+            const int slot = (int)(j % NS);
+            mbar_wait_cluster(&sh.part_full[slot], (uint32_t)((j / NS) & 1));
+            double s = 0.0;
+            if (lane < 12) {
+                for (int r = 0; r < C; r++) s += sh.partials[slot][r][lane];   // rank order: identical in every CTA
+            }
+            double sums[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) sums[k] = __shfl_sync(0xffffffffu, s, k);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&sh.part_full[slot], (uint32_t)(C * 12 * sizeof(double)));  // re-arm for frame j+NS
+                const long f = cid + j * G;
+                const double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
+                double h[9], r[9];
+                bool finite = true;
+#pragma unroll
+                for (int k = 0; k < 9; k++) { h[k] = sums[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
+                int rc = finite ? k3::kabsch3(h, r) : -4;
+                if (rc != 0) {
+                    if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                }
+                double* xf = sh.xf[slot];
+#pragma unroll
+                for (int k = 0; k < 9; k++) xf[k] = r[k];
+                xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
+                xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
+                xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
+                mbar_arrive(&sh.solved[slot]);
+                if (rank == 0) {
+                    if (p.rot) {
+#pragma unroll
+                        for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
+                    }
+                    if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
+                    if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== consumers =====================
+        // fixed atom slots: local index tid + k*256; template and weights stay in registers
+        double bx[K], by[K], bz[K], wk[K], dev[K];
+        uint32_t real_mask = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int li = tid + k * kConsumers;
+            const int gi = part0 + li;
+            const bool in = li < part_len;
+            bx[k] = in ? p.refc[gi] : 0.0;
+            by[k] = in ? p.refc[p.np + gi] : 0.0;
+            bz[k] = in ? p.refc[2L * p.np + gi] : 0.0;
+            wk[k] = (in && gi < p.natoms) ? (WEIGHTED ? p.weight[gi] : 1.0) : 0.0;
+            dev[k] = 0.0;
+            if (in && gi < p.natoms) real_mask |= 1u << k;   // slots that are real atoms of THIS part
+        }
+        // remote addresses of my partial-sum row and barrier in every CTA (threads 0..11 push)
+        const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][tid < 12 ? tid : 0]);
+        const uint32_t part_bar_addr = smem_u32(&sh.part_full[0]);
+
+        for (long j = 0; j < nloc + D; j++) {
+            double acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = 0.0;
+            double e = 0.0;
+            if (j < nloc) {
+                // ---- pass 1 of local frame j ----
+                const int s = (int)(j % S);
+                mbar_wait(&sh.full[s], (uint32_t)((j / S) & 1));
+                const double* sx = stage_base + (long)s * kStageDoubles + tid;
+                const double* sy = sx + K * kConsumers;
+                const double* sz = sy + K * kConsumers;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
+                    if (WEIGHTED) { x *= wk[k]; y *= wk[k]; z *= wk[k]; }
+                    acc[0] += x; acc[1] += y; acc[2] += z;
+                    acc[3] = fma(x, bx[k], acc[3]); acc[4] = fma(x, by[k], acc[4]); acc[5] = fma(x, bz[k], acc[5]);
+                    acc[6] = fma(y, bx[k], acc[6]); acc[7] = fma(y, by[k], acc[7]); acc[8] = fma(y, bz[k], acc[8]);
+                    acc[9] = fma(z, bx[k], acc[9]); acc[10] = fma(z, by[k], acc[10]); acc[11] = fma(z, bz[k], acc[11]);
+                }
+            }
+            if (j >= D) {
+                // ---- pass 2 of local frame jj = j - D ----
+                const long jj = j - D;
+                const int s2 = (int)(jj % S);
+                const int slot = (int)(jj % NS);
+                mbar_wait(&sh.solved[slot], (uint32_t)((jj / NS) & 1));
+                const double* xf = sh.xf[slot];
+                const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
+                const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
+                const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
+                const double* sy = sx + K * kConsumers;
+                const double* sz = sy + K * kConsumers;
+                double* frw = cp.write_back ? (p.frames_rw + (cid + jj * G) * p.frame_stride + part0 + tid) : nullptr;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
+                    // (a - centroid) R  computed as  a R - centroid R
+                    const double qx = fma(z, r6, fma(y, r3, fma(x, r0, g0)));
+                    const double qy = fma(z, r7, fma(y, r4, fma(x, r1, g1)));
+                    const double qz = fma(z, r8, fma(y, r5, fma(x, r2, g2)));
+                    const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
+                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    e = fma(wk[k], d2, e);
+                    if (DEV) dev[k] += sqrt(d2);
+                    if (frw != nullptr && ((real_mask >> k) & 1u)) {
+                        frw[k * kConsumers] = qx + p.bbar[0];
+                        frw[p.np + k * kConsumers] = qy + p.bbar[1];
+                        frw[2L * p.np + k * kConsumers] = qz + p.bbar[2];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
+            }
+            // ---- reductions: 12 sums of frame j, squared error of frame j-D ----
+            double t0, t1;
+            warp_reduce12(acc, lane, t0, t1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
+            double* red = sh.red[j & 1][warp];
+            if ((lane & 3) == 0) {
+                const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+                red[6 * b4 + 3 * b3 + 2 * b2] = t0;
+                if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
+            }
+            if (lane == 0) red[12] = e;
+            named_bar_sync(1, kConsumers);
+            if (tid < 12) {
+                if (j < nloc) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kConsumerWarps; w++) v += sh.red[j & 1][w][tid];
+                    const int slot = (int)(j % NS);
+                    const uint32_t off = (uint32_t)(slot * (int)sizeof(sh.partials[0]));
+                    for (int c = 0; c < C; c++) {
+                        st_async_f64(mapa(my_part_addr + off, (uint32_t)c), v,
+                                     mapa(part_bar_addr + (uint32_t)slot * 8u, (uint32_t)c));
+                    }
+                }
+            } else if (tid == 12 && j >= D) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < kConsumerWarps; w++) v += sh.red[j & 1][w][12];
+                cp.epart[(cid + (j - D) * G) * C + rank] = v;
+            }
+        }
+        if (DEV) {
+            double* row = p.devpart + cid * (long)p.np;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int li = tid + k * kConsumers;
+                if (li < part_len) row[part0 + li] = dev[k];
+            }
+        }
+    }
+    // nobody leaves while a peer may still store into this CTA's shared memory
+    __syncthreads();
+    cluster_sync_all();
+}
+
+__global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restrict__ epart, int C, long nframes, double inv_n,
+                                                         double* __restrict__ rmsd) {
+    const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    double s = 0.0;
+    for (int r = 0; r < C; r++) s += epart[f * C + r];
+    rmsd[f] = sqrt(s * inv_n);
+}
+
+struct Plan {
+    int cluster, part, kinst, stages, depth, slots;
+    size_t smem;
+};
+
+constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+
+int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0;
+
+bool make_plan(int np, Plan* pl) {
+    const size_t fixed = ((sizeof(Shared) + 127) / 128) * 128;
+    const int cands[] = {1, 2, 4, 8, 16};
+    for (int c : cands) {
+        if (g_tune_cluster && c != g_tune_cluster) continue;
+        const int part = round_up((np + c - 1) / c, 16);
+        const int kneed = (part + kConsumers - 1) / kConsumers;
+        int kinst = 0;
+        for (int k : kInst) if (k >= kneed) { kinst = k; break; }
+        if (!kinst) continue;
+        const size_t stage = (size_t)3 * kinst * kConsumers * sizeof(double);
+        int stages = (int)((kSmemBudget - fixed) / stage);
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (g_tune_stages && g_tune_stages < stages) stages = g_tune_stages;
+        if (stages < 3) continue;
+        if (!g_tune_cluster && kinst > 12 && c < 16) continue;   // prefer more CTAs over very fat threads
+        int depth = stages - 2;
+        if (depth > 2) depth = 2;
+        if (g_tune_depth >= 1 && g_tune_depth <= 3 && g_tune_depth <= stages - 2) depth = g_tune_depth;
+        pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
+        pl->slots = 2 * depth + 1;
+        pl->smem = fixed + stage * stages;
+        return true;
+    }
+    return false;
+}
+
+template <int K, bool W, bool DV>
+int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out, ClusterParams* final_cp) {
+    auto kern = super_cluster_kernel<K, W, DV>;
+    GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (pl.cluster > 8) GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kThreadsCta);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = t->stream;
+    cfg.gridDim = dim3(pl.cluster * (t->sm_count / pl.cluster));
+    int max_clusters = 0;
+    GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters < 1) { set_error("cluster of %d CTAs with %zu bytes of shared memory cannot be scheduled", pl.cluster, pl.smem); return GCB_ERR_CUDA; }
+    long g = max_clusters;
+    if (g > t->sm_count / pl.cluster) g = t->sm_count / pl.cluster;
+    if (g > cp.p.nframes) g = cp.p.nframes;
+    ClusterParams c2 = cp;
+    c2.nclusters = (int)g;
+    cfg.gridDim = dim3((unsigned)(g * pl.cluster));
+    GCB_CUDA(cudaLaunchKernelEx(&cfg, kern, c2));
+    GCB_LAUNCHED();
+    *nclusters_out = (int)g;
+    *final_cp = c2;
+    return GCB_OK;
+}
+
+template <bool W, bool DV>
+int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g, ClusterParams* fc) {
+    switch (pl.kinst) {
+        case 1: return launch_inst<1, W, DV>(t, cp, pl, g, fc);
+        case 2: return launch_inst<2, W, DV>(t, cp, pl, g, fc);
+        case 3: return launch_inst<3, W, DV>(t, cp, pl, g, fc);
+        case 4: return launch_inst<4, W, DV>(t, cp, pl, g, fc);
+        case 5: return launch_inst<5, W, DV>(t, cp, pl, g, fc);
+        case 6: return launch_inst<6, W, DV>(t, cp, pl, g, fc);
+        case 8: return launch_inst<8, W, DV>(t, cp, pl, g, fc);
+        case 10: return launch_inst<10, W, DV>(t, cp, pl, g, fc);
+        case 12: return launch_inst<12, W, DV>(t, cp, pl, g, fc);
+        case 16: return launch_inst<16, W, DV>(t, cp, pl, g, fc);
+    }
+    set_error("no kernel instance for %d atoms per thread", pl.kinst);
     return GCB_ERR_ARG;
 }
+
+double* g_epart[16] = {nullptr};
+size_t g_epart_cap[16] = {0};
+
+}  // namespace
+
+void set_cluster_tuning(int cluster, int stages, int depth) {
+    g_tune_cluster = cluster;
+    g_tune_stages = stages;
+    g_tune_depth = depth;
+}
+
+bool cluster_kernel_supported(const gcb_traj* t) {
+    Plan pl;
+    return make_plan(t->np, &pl);
+}
+
+int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
+    Plan pl;
+    if (!make_plan(t->np, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    const int dev = t->dev & 15;
+    const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster;
+    if (need > g_epart_cap[dev]) {
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+        cudaFree(g_epart[dev]);
+        g_epart[dev] = nullptr;
+        g_epart_cap[dev] = 0;
+        GCB_CUDA(cudaMalloc(&g_epart[dev], need));
+        g_epart_cap[dev] = need;
+    }
+    ClusterParams cp;
+    cp.p = p;
+    cp.cluster = pl.cluster;
+    cp.part = pl.part;
+    cp.stages = pl.stages;
+    cp.depth = pl.depth;
+    cp.slots = pl.slots;
+    cp.nclusters = 0;
+    cp.write_back = p.frames_rw != nullptr;
+    cp.epart = g_epart[dev];
+    int g = 0;
+    ClusterParams fc;
+    int rc;
+    if (weighted) rc = want_dev ? launch_k<true, true>(t, cp, pl, &g, &fc) : launch_k<true, false>(t, cp, pl, &g, &fc);
+    else rc = want_dev ? launch_k<false, true>(t, cp, pl, &g, &fc) : launch_k<false, false>(t, cp, pl, &g, &fc);
+    if (rc) return rc;
+    if (rows_out) *rows_out = g;
+    if (p.rmsd) {
+        finish_rmsd_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, t->stream>>>(cp.epart, pl.cluster, p.nframes, p.inv_n, p.rmsd);
+        GCB_LAUNCHED();
+    }
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
 }  // namespace gcb

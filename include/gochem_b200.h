@@ -55,6 +55,9 @@ int gcb_device_count(int *n);
 /* Properties the host side sizes its work by: SM count, bytes of device memory, compute capability. */
 int gcb_device_info(int dev, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
 int gcb_set_kernel_variant(int variant);
+/* Tuning hook for the cluster kernel: CTAs per frame (1, 2, 4, 8, 16), shared-memory stages, and how many
+ * frames pass 2 trails pass 1 (1..3).  0 / 0 / 0 restores the built-in choice. */
+int gcb_set_cluster_tuning(int cluster, int stages, int depth);
 
 /* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
 int gcb_pinned_alloc(size_t bytes, void **p);

@@ -260,3 +260,37 @@ def test_device_synth_properties_full_size(variant):
     z = t.super_rmsd(ref, nframes=2000)
     assert z["rmsd"].max() < 1e-11
     t.close()
+
+
+@pytest.mark.parametrize("natoms,cluster,stages,depth", [
+    (1500, 1, 0, 0), (1500, 1, 3, 1), (1500, 2, 0, 3), (1500, 4, 4, 2), (1500, 8, 0, 1),
+    (5000, 2, 0, 0), (5000, 4, 0, 2), (5000, 8, 5, 3), (10000, 4, 0, 0), (10000, 8, 0, 2), (10000, 8, 0, 3),
+    (10000, 16, 0, 2), (613, 1, 0, 0), (613, 8, 0, 2), (40, 4, 0, 1),
+])
+def test_cluster_kernel_tunings(natoms, cluster, stages, depth):
+    """Every cluster shape / pipeline depth must give the same answers as the oracle."""
+    lib = _lib.load()
+    nframes = 333
+    ref, frames = synth.make_case(natoms, 16)
+    frames = np.tile(frames, (21, 1, 1))[:nframes]
+    frames += np.random.default_rng(1).standard_normal(frames.shape) * 0.01
+    idx = np.arange(0, natoms, 3)
+    t = device_traj(frames)
+    try:
+        _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
+        _lib.check(lib.gcb_set_cluster_tuning(cluster, stages, depth))
+        out = t.super_rmsd(ref)
+        rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None, nthreads=8)
+        assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
+        assert np.abs(out["rot"] - rot).max() < TOL_ROT
+        assert np.abs(out["trans1"] - t1).max() < TOL_XYZ
+        # weighted subset + LOVO sums + write-back in one pass
+        dev = t.peratom_dev_sum(ref, idx, write_back=True)
+        want, total, aligned = oracle.rmsd_traj(frames, ref, idx, cpus=3, want_aligned=True, nthreads=3)
+        assert total == nframes
+        assert np.abs(dev / nframes - want).max() < 1e-10
+        assert np.abs(t.download() - aligned).max() < TOL_XYZ
+    finally:
+        lib.gcb_set_cluster_tuning(0, 0, 0)
+        lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
+        t.close()
