@@ -124,42 +124,61 @@ K3_HD int kabsch3_jacobi(const double* h, double* rot) {
     return 0;
 }
 
-// Scaled Newton iteration X <- (g X + X^-T / g) / 2 for the orthogonal polar factor of H.
-// Returns 1 when it converged to a proper rotation, 0 when the caller must use the Jacobi path.
+// Reciprocal / reciprocal square root with a short dependency chain: hardware seed + Newton steps
+// on the device, plain division on the host (same values to the last bits that matter here).
+K3_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);   // seed is good to ~2^-20; two Newton steps reach fp64 rounding level
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// Newton iteration X <- (X + X^-T) / 2 for the orthogonal polar factor of H, started from
+// H * sqrt(3) / ||H||_F (singular values of order one, so no per-step scaling, hence no square
+// roots or divisions inside the loop: one seeded reciprocal of the determinant per step).
+// Returns 1 when it converged to a proper rotation, 0 when the caller must use the Jacobi path
+// (det H <= 0, near-singular H, non-finite input).
 K3_HD int kabsch3_polar(const double* h, double* rot) {
     double x[9];
-    double nrm = 0.0;
+    const double n0 = fma(h[2], h[2], fma(h[1], h[1], h[0] * h[0]));
+    const double n1 = fma(h[5], h[5], fma(h[4], h[4], h[3] * h[3]));
+    const double n2 = fma(h[8], h[8], fma(h[7], h[7], h[6] * h[6]));
+    const double nrm = n0 + n1 + n2;
+    if (!(nrm > 1e-280) || !(nrm < 1e280)) return 0;
+#if defined(__CUDA_ARCH__)
+    const double sc = rsqrt(nrm) * 1.7320508075688772;
+#else
+    const double sc = 1.7320508075688772 / sqrt(nrm);
+#endif
 #pragma unroll
-    for (int i = 0; i < 9; i++) { x[i] = h[i]; nrm += h[i] * h[i]; }
-    if (!(nrm > 0.0) || !(nrm < 1.79e308)) return 0;
-    double d = det3(x);
-    // guard: proper and comfortably non-singular (det = s1 s2 s3; ||H||_F^3 >= 3^1.5 s1 s2 s3)
-    double fn = sqrt(nrm);
-    if (!(d > 1e-6 * fn * fn * fn)) return 0;
-    for (int it = 0; it < 24; it++) {
+    for (int i = 0; i < 9; i++) x[i] = h[i] * sc;
+    for (int it = 0; it < 40; it++) {
         // cofactor matrix c = det * X^-T
         double c[9];
-        c[0] = x[4] * x[8] - x[5] * x[7]; c[1] = x[5] * x[6] - x[3] * x[8]; c[2] = x[3] * x[7] - x[4] * x[6];
-        c[3] = x[2] * x[7] - x[1] * x[8]; c[4] = x[0] * x[8] - x[2] * x[6]; c[5] = x[1] * x[6] - x[0] * x[7];
-        c[6] = x[1] * x[5] - x[2] * x[4]; c[7] = x[2] * x[3] - x[0] * x[5]; c[8] = x[0] * x[4] - x[1] * x[3];
-        double det = x[0] * c[0] + x[1] * c[1] + x[2] * c[2];
-        if (!(det > 0.0)) return 0;
-        double nx = 0.0, nc = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) { nx += x[i] * x[i]; nc += c[i] * c[i]; }
-        // Frobenius scaling g = sqrt(||X^-T||_F / ||X||_F) with X^-T = c/det
-        double g2 = sqrt(nc / nx) / det;        // g^2
-        double g = sqrt(g2);
-        double a = 0.5 * g, b = 0.5 / (g * det);
-        double diff = 0.0;
+        c[0] = fma(x[4], x[8], -x[5] * x[7]); c[1] = fma(x[5], x[6], -x[3] * x[8]); c[2] = fma(x[3], x[7], -x[4] * x[6]);
+        c[3] = fma(x[2], x[7], -x[1] * x[8]); c[4] = fma(x[0], x[8], -x[2] * x[6]); c[5] = fma(x[1], x[6], -x[0] * x[7]);
+        c[6] = fma(x[1], x[5], -x[2] * x[4]); c[7] = fma(x[2], x[3], -x[0] * x[5]); c[8] = fma(x[0], x[4], -x[1] * x[3]);
+        const double det = fma(x[2], c[2], fma(x[1], c[1], x[0] * c[0]));
+        // guard: proper and comfortably non-singular.  At it == 0, det = det(H) 3^1.5 / ||H||_F^3.
+        if (!(det > 5e-6)) return 0;
+        const double b = 0.5 * fast_rcp(det);
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            double y = a * x[i] + b * c[i];
-            double e = y - x[i];
-            diff += e * e;
+            const double y = fma(b, c[i], 0.5 * x[i]);
+            const double e = y - x[i];
+            if (i % 3 == 0) d0 = fma(e, e, d0);
+            else if (i % 3 == 1) d1 = fma(e, e, d1);
+            else d2 = fma(e, e, d2);
             x[i] = y;
         }
-        if (diff <= 1e-26) {  // ||dX||_F <= 1e-13: quadratic convergence puts the remaining error near 1e-26
+        if (d0 + d1 + d2 <= 1e-15) {  // ||dX||_F <= 3e-8: the error after this step is ~ ||dX||^2 / 2 < 1e-15
 #pragma unroll
             for (int i = 0; i < 9; i++) rot[i] = x[i];
             return 1;

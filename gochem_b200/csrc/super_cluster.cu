@@ -35,9 +35,10 @@ namespace {
 
 constexpr int kConsumers = 256;          // consumer threads per CTA
 constexpr int kConsumerWarps = 8;
-constexpr int kThreadsCta = kConsumers + 64;  // + producer warp + solver warp
+constexpr int kSolverWarps = 3;
+constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
 constexpr int kMaxStages = 8;
-constexpr int kMaxSlots = 7;             // exchange slots, 2*D+1 with D <= 3
+constexpr int kMaxSlots = 7;             // exchange slots (>= 2*D+1 with D <= 3, and > kSolverWarps)
 constexpr int kMaxCluster = 16;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -76,17 +77,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
-}
-// wait that also acquires writes made by other CTAs of the cluster (st.async partial sums)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -156,15 +146,56 @@ __device__ __forceinline__ void warp_reduce12(const double (&v)[12], int lane, d
     t0 += shx(t0, 1); t1 += shx(t1, 1);
 }
 
+#ifdef GCB_TRACE
+__device__ long long g_trace[8][512];
+#define TRACE(row, j) do { if (blockIdx.x == 0 && (j) < 512) g_trace[row][j] = clock64(); } while (0)
+#else
+#define TRACE(row, j) do {} while (0)
+#endif
+
 struct __align__(16) Shared {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t part_full[kMaxSlots];
-    uint64_t solved[kMaxSlots];
+    uint64_t part_full[kMaxSlots];        // cluster -> solver: every CTA's partial sums of a frame have landed
+    uint64_t solved[kMaxSlots];           // solver -> consumers: xf[slot] holds the frame's transform
     double partials[kMaxSlots][kMaxCluster][12];
     double xf[kMaxSlots][16];             // R[9], centroid*R [3]
-    double red[2][kConsumerWarps][14];    // cross-warp scratch, double-buffered by iteration parity
+    double red[kMaxSlots][kConsumerWarps][14];   // [..][12] = squared error of the frame D iterations earlier
+    unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
+
+// pass 2 for one thread's K atom slots; WB = also store the superposed coordinates
+template <int K, bool DEV, bool WB>
+__device__ __forceinline__ double pass2_atoms(const double* __restrict__ sx, const double* xf, const double (&bx)[K],
+                                              const double (&by)[K], const double (&bz)[K], const double (&wk)[K],
+                                              double (&dev)[K], double* frw, int np, uint32_t real_mask,
+                                              double b0, double b1, double b2) {
+    const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
+    const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
+    const double* sy = sx + K * kConsumers;
+    const double* sz = sy + K * kConsumers;
+    double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
+        // (a - centroid) R  computed as  a R - centroid R
+        const double qx = fma(z, r6, fma(y, r3, fma(x, r0, g0)));
+        const double qy = fma(z, r7, fma(y, r4, fma(x, r1, g1)));
+        const double qz = fma(z, r8, fma(y, r5, fma(x, r2, g2)));
+        const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (k & 1) e1 = fma(wk[k], d2, e1); else e0 = fma(wk[k], d2, e0);
+        if (DEV) dev[k] += sqrt(d2);
+        if (WB) {
+            if ((real_mask >> k) & 1u) {
+                frw[k * kConsumers] = qx + b0;
+                frw[np + k * kConsumers] = qy + b1;
+                frw[2L * np + k * kConsumers] = qz + b2;
+            }
+        }
+    }
+    return e0 + e1;
+}
 
 template <int K, bool WEIGHTED, bool DEV>
 __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
@@ -176,20 +207,25 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     const SuperParams& p = cp.p;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int C = cp.cluster, S = cp.stages, D = cp.depth, NS = cp.slots, G = cp.nclusters;
+    const int C = cp.cluster, S = cp.stages, D = cp.depth, G = cp.nclusters;
+    constexpr int NS = kMaxSlots;
     const uint32_t rank = cluster_ctarank();
     const long cid = cluster_id_x();
     const int part0 = (int)rank * cp.part;                       // first atom of this CTA's part
     int part_len = p.np - part0;                                 // atoms (incl. padding) actually loaded
     if (part_len > cp.part) part_len = cp.part;
     if (part_len < 0) part_len = 0;
-    const long nloc = (cid < p.nframes) ? (p.nframes - cid + G - 1) / G : 0;   // frames of this cluster
+    const int nloc = (cid < p.nframes) ? (int)((p.nframes - cid + G - 1) / G) : 0;   // frames of this cluster
 
     // zero the stage ring once: slots beyond part_len are never written by TMA and must read as 0
     for (int i = tid; i < S * kStageDoubles; i += kThreadsCta) stage_base[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kConsumerWarps); }
-        for (int s = 0; s < NS; s++) { mbar_init(&sh.part_full[s], 1); mbar_init(&sh.solved[s], 1); }
+        for (int s = 0; s < NS; s++) {
+            sh.red_count[s] = 0;
+            mbar_init(&sh.part_full[s], 1);
+            mbar_init(&sh.solved[s], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // make the zero-fill (generic proxy) visible to the async proxy before any TMA write lands next to it
@@ -205,72 +241,85 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         if (lane == 0 && part_len > 0) {
             const uint64_t pol = policy_evict_first();
             const uint32_t seg_bytes = (uint32_t)part_len * 8u;
-            for (long j = 0; j < nloc; j++) {
-                const int s = (int)(j % S);
-                if (j >= S) mbar_wait(&sh.empty[s], (uint32_t)(((j / S) - 1) & 1));
-                const double* src = p.frames + (cid + j * G) * p.frame_stride + part0;
+            const double* src = p.frames + cid * p.frame_stride + part0;
+            const long src_step = (long)G * p.frame_stride;
+            int s = 0;
+            uint32_t ph = 1;   // parity of the previous use of the stage
+            for (int j = 0; j < nloc; j++, src += src_step) {
+                if (j >= S) mbar_wait(&sh.empty[s], ph);
                 double* dst = stage_base + (long)s * kStageDoubles;
                 mbar_arrive_expect_tx(&sh.full[s], 3u * seg_bytes);
                 tma_load_1d(dst, src, seg_bytes, &sh.full[s], pol);
                 tma_load_1d(dst + K * kConsumers, src + p.np, seg_bytes, &sh.full[s], pol);
                 tma_load_1d(dst + 2 * K * kConsumers, src + 2L * p.np, seg_bytes, &sh.full[s], pol);
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         } else if (lane == 0) {
             // an empty part still has to complete the full barriers its consumers wait on
-            for (long j = 0; j < nloc; j++) {
-                const int s = (int)(j % S);
-                if (j >= S) mbar_wait(&sh.empty[s], (uint32_t)(((j / S) - 1) & 1));
+            int s = 0;
+            uint32_t ph = 1;
+            for (int j = 0; j < nloc; j++) {
+                if (j >= S) mbar_wait(&sh.empty[s], ph);
                 mbar_arrive(&sh.full[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
-    } else if (warp == kConsumerWarps + 1) {
-        // ===================== solver =====================
-        for (long j = 0; j < nloc; j++) {
-            const int slot = (int)(j % NS);
-            mbar_wait_cluster(&sh.part_full[slot], (uint32_t)((j / NS) & 1));
-            double s = 0.0;
-            if (lane < 12) {
-                for (int r = 0; r < C; r++) s += sh.partials[slot][r][lane];   // rank order: identical in every CTA
-            }
-            double sums[12];
-#pragma unroll
-            for (int k = 0; k < 12; k++) sums[k] = __shfl_sync(0xffffffffu, s, k);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&sh.part_full[slot], (uint32_t)(C * 12 * sizeof(double)));  // re-arm for frame j+NS
-                const long f = cid + j * G;
-                const double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
-                double h[9], r[9];
-                bool finite = true;
-#pragma unroll
-                for (int k = 0; k < 9; k++) { h[k] = sums[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
-                int rc = finite ? k3::kabsch3(h, r) : -4;
-                if (rc != 0) {
-                    if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
-#pragma unroll
-                    for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    } else if (warp > kConsumerWarps) {
+        // ===================== solvers: warp w takes local frames w, w + kSolverWarps, ... =====================
+        // Per frame: rank-ordered sum of the cluster's partial sums, 3x3 solve, publish R and centroid R.
+        const int sw = warp - (kConsumerWarps + 1);
+        int slot = sw;                                  // NS = 7 > kSolverWarps
+        uint32_t sph = 0;
+        for (int j = sw; j < nloc; j += kSolverWarps) {
+            {
+                mbar_wait(&sh.part_full[slot], sph);
+                if (lane == 0) TRACE(2, j);
+                double s = 0.0;
+                if (lane < 12) {
+                    for (int r = 0; r < C; r++) s += sh.partials[slot][r][lane];   // rank order: identical in every CTA
                 }
-                double* xf = sh.xf[slot];
+                double sums[12];
 #pragma unroll
-                for (int k = 0; k < 9; k++) xf[k] = r[k];
-                xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
-                xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
-                xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
-                mbar_arrive(&sh.solved[slot]);
-                if (rank == 0) {
-                    if (p.rot) {
+                for (int k = 0; k < 12; k++) sums[k] = __shfl_sync(0xffffffffu, s, k);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&sh.part_full[slot], (uint32_t)(C * 12 * sizeof(double)));  // re-arm for frame j+NS
+                    const long f = cid + (long)j * G;
+                    const double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
+                    double h[9], r[9];
+                    bool finite = true;
 #pragma unroll
-                        for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
+                    for (int k = 0; k < 9; k++) { h[k] = sums[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
+                    int rc = finite ? k3::kabsch3(h, r) : -4;
+                    if (rc != 0) {
+                        if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
+#pragma unroll
+                        for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
                     }
-                    if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
-                    if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+                    double* xf = sh.xf[slot];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) xf[k] = r[k];
+                    xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
+                    xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
+                    xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
+                    TRACE(3, j);
+                    mbar_arrive(&sh.solved[slot]);
+                    if (rank == 0) {
+                        if (p.rot) {
+#pragma unroll
+                            for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
+                        }
+                        if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
+                        if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+                    }
                 }
             }
             __syncwarp();
+            slot += kSolverWarps;
+            if (slot >= NS) { slot -= NS; sph ^= 1u; }
         }
     } else {
-        // ===================== consumers =====================
+        // ===================== consumers (warps run free of one another) =====================
         // fixed atom slots: local index tid + k*256; template and weights stay in registers
         double bx[K], by[K], bz[K], wk[K], dev[K];
         uint32_t real_mask = 0;
@@ -286,20 +335,23 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             dev[k] = 0.0;
             if (in && gi < p.natoms) real_mask |= 1u << k;   // slots that are real atoms of THIS part
         }
-        // remote addresses of my partial-sum row and barrier in every CTA (threads 0..11 push)
-        const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][tid < 12 ? tid : 0]);
+        const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][0]);
         const uint32_t part_bar_addr = smem_u32(&sh.part_full[0]);
-
-        for (long j = 0; j < nloc + D; j++) {
+        int s1 = 0, s2 = 0, slot1 = 0, slot2 = 0;      // stage / exchange slot of pass 1 (frame j) and pass 2 (frame j-D)
+        uint32_t ph1 = 0, ph2 = 0;                     // parities: full[s1], solved[slot2]
+        double* frw = cp.write_back ? (p.frames_rw + cid * p.frame_stride + part0 + tid) : nullptr;
+        const long frw_step = (long)G * p.frame_stride;
+        for (int j = 0; j < nloc + D; j++) {
             double acc[12];
 #pragma unroll
             for (int k = 0; k < 12; k++) acc[k] = 0.0;
             double e = 0.0;
             if (j < nloc) {
                 // ---- pass 1 of local frame j ----
-                const int s = (int)(j % S);
-                mbar_wait(&sh.full[s], (uint32_t)((j / S) & 1));
-                const double* sx = stage_base + (long)s * kStageDoubles + tid;
+                if (tid == 0) TRACE(4, j);
+                mbar_wait(&sh.full[s1], ph1);
+                if (tid == 0) TRACE(5, j);
+                const double* sx = stage_base + (long)s1 * kStageDoubles + tid;
                 const double* sy = sx + K * kConsumers;
                 const double* sz = sy + K * kConsumers;
 #pragma unroll
@@ -313,68 +365,61 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 }
             }
             if (j >= D) {
-                // ---- pass 2 of local frame jj = j - D ----
-                const long jj = j - D;
-                const int s2 = (int)(jj % S);
-                const int slot = (int)(jj % NS);
-                mbar_wait(&sh.solved[slot], (uint32_t)((jj / NS) & 1));
-                const double* xf = sh.xf[slot];
-                const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
-                const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
+                // ---- pass 2 of local frame j - D, from the same shared-memory stage ----
+                mbar_wait(&sh.solved[slot2], ph2);
+                if (tid == 0) TRACE(6, j - D);
                 const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
-                const double* sy = sx + K * kConsumers;
-                const double* sz = sy + K * kConsumers;
-                double* frw = cp.write_back ? (p.frames_rw + (cid + jj * G) * p.frame_stride + part0 + tid) : nullptr;
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
-                    // (a - centroid) R  computed as  a R - centroid R
-                    const double qx = fma(z, r6, fma(y, r3, fma(x, r0, g0)));
-                    const double qy = fma(z, r7, fma(y, r4, fma(x, r1, g1)));
-                    const double qz = fma(z, r8, fma(y, r5, fma(x, r2, g2)));
-                    const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
-                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    e = fma(wk[k], d2, e);
-                    if (DEV) dev[k] += sqrt(d2);
-                    if (frw != nullptr && ((real_mask >> k) & 1u)) {
-                        frw[k * kConsumers] = qx + p.bbar[0];
-                        frw[p.np + k * kConsumers] = qy + p.bbar[1];
-                        frw[2L * p.np + k * kConsumers] = qz + p.bbar[2];
-                    }
-                }
+                if (frw) e = pass2_atoms<K, DEV, true>(sx, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                else e = pass2_atoms<K, DEV, false>(sx, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, 0.0, 0.0, 0.0);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
             }
-            // ---- reductions: 12 sums of frame j, squared error of frame j-D ----
-            double t0, t1;
-            warp_reduce12(acc, lane, t0, t1);
+            // ---- warp-level reductions: 12 sums of frame j, squared error of frame j-D ----
+            double t0 = 0.0, t1 = 0.0;
+            if (j < nloc) warp_reduce12(acc, lane, t0, t1);
+            if (j >= D) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
-            double* red = sh.red[j & 1][warp];
+                for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
+            }
+            double* red = sh.red[slot1][warp];
             if ((lane & 3) == 0) {
                 const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
                 red[6 * b4 + 3 * b3 + 2 * b2] = t0;
                 if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
             }
             if (lane == 0) red[12] = e;
-            named_bar_sync(1, kConsumers);
-            if (tid < 12) {
-                if (j < nloc) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kConsumerWarps; w++) v += sh.red[j & 1][w][tid];
-                    const int slot = (int)(j % NS);
-                    const uint32_t off = (uint32_t)(slot * (int)sizeof(sh.partials[0]));
-                    for (int c = 0; c < C; c++) {
-                        st_async_f64(mapa(my_part_addr + off, (uint32_t)c), v,
-                                     mapa(part_bar_addr + (uint32_t)slot * 8u, (uint32_t)c));
-                    }
-                }
-            } else if (tid == 12 && j >= D) {
+            __threadfence_block();
+            __syncwarp();
+            if (tid == 0) TRACE(7, j);
+            // the last warp to deliver sums the 8 warps in fixed order and pushes the CTA's partials to the cluster
+            unsigned int prev = 0;
+            if (lane == 0) prev = atomicAdd(&sh.red_count[slot1], 1u);   // relaxed RMW ...
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == kConsumerWarps - 1) {
+                __threadfence_block();                                  // ... ordered against the other warps' stores
                 double v = 0.0;
+                if (lane < 13) {
 #pragma unroll
-                for (int w = 0; w < kConsumerWarps; w++) v += sh.red[j & 1][w][12];
-                cp.epart[(cid + (j - D) * G) * C + rank] = v;
+                    for (int w = 0; w < kConsumerWarps; w++) v += sh.red[slot1][w][lane];
+                }
+                if (lane == 12 && j >= D) cp.epart[(cid + (long)(j - D) * G) * C + rank] = v;
+                if (lane < 12 && j < nloc) {
+                    const uint32_t off = (uint32_t)(slot1 * (int)sizeof(sh.partials[0]));
+                    for (int c = 0; c < C; c++)
+                        st_async_f64(mapa(my_part_addr + off + (uint32_t)lane * 8u, (uint32_t)c), v,
+                                     mapa(part_bar_addr + (uint32_t)slot1 * 8u, (uint32_t)c));
+                }
+                if (lane == 0) { atomicExch(&sh.red_count[slot1], 0u); TRACE(1, j); }
+            }
+            // advance the ring positions (no divisions in the loop)
+            if (++slot1 == NS) slot1 = 0;
+            if (j < nloc) {
+                if (++s1 == S) { s1 = 0; ph1 ^= 1u; }
+            }
+            if (j >= D) {
+                if (++s2 == S) s2 = 0;
+                if (++slot2 == NS) { slot2 = 0; ph2 ^= 1u; }
+                if (frw) frw += frw_step;
             }
         }
         if (DEV) {
@@ -491,6 +536,12 @@ double* g_epart[16] = {nullptr};
 size_t g_epart_cap[16] = {0};
 
 }  // namespace
+
+#ifdef GCB_TRACE
+extern "C" int gcb_trace_read(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 8 * 512) == cudaSuccess ? 0 : -7;
+}
+#endif
 
 void set_cluster_tuning(int cluster, int stages, int depth) {
     g_tune_cluster = cluster;

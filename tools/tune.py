@@ -1,0 +1,53 @@
+"""Sweep the cluster kernel's shape on one GPU: python tools/tune.py [natoms] [nframes] [mode]"""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from gochem_b200 import _lib, synth
+
+natoms = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+nframes = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+mode = sys.argv[3] if len(sys.argv) > 3 else "fit"
+lib = _lib.load()
+ref = synth.make_reference(natoms)
+sig = synth.atom_sigmas(natoms)
+t = _lib.DeviceTraj(natoms, nframes)
+t.synth_fill(ref, sig, nframes, frame0_is_ref=True)
+idx = np.arange(0, natoms, 2)
+
+
+def run(label):
+    def step():
+        if mode == "fit":
+            t.super_rmsd_async(ref)
+        elif mode == "wb":
+            t.super_rmsd_async(ref, write_back=True)
+        elif mode == "lovo":
+            t.peratom_dev_sum(ref, idx)
+    for _ in range(2):
+        step()
+    t.sync()
+    t.timer_start()
+    n = 5
+    for _ in range(n):
+        step()
+    ms = t.timer_stop() / n
+    bpa = 48 if mode == "wb" else 24
+    gbs = bpa * natoms * nframes / ms / 1e6
+    print(json.dumps({"cfg": label, "ms": round(ms, 4), "GBs": round(gbs, 1), "Mframes_s": round(nframes / ms / 1e3, 3)}), flush=True)
+
+
+_lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_GENERIC))
+run("generic")
+_lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
+for c in (1, 2, 4, 8, 16):
+    for s in (0, 3, 4, 6):
+        for d in (1, 2, 3):
+            try:
+                _lib.check(lib.gcb_set_cluster_tuning(c, s, d))
+                run(f"C{c} S{s} D{d}")
+            except _lib.GcbError as e:
+                print(json.dumps({"cfg": f"C{c} S{s} D{d}", "err": e.msg[:80]}), flush=True)
