@@ -253,6 +253,7 @@ def run_ours(a):
     ms_per_step = ms / a.steps
     total_frames = nframes * d.world
     value = total_frames / (ms_per_step * 1e-3)
+    plan = _lib.last_cluster_plan() if a.variant != "generic" else None
     res = traj.fetch(want=("rmsd",))
     rmsd_gpu = res["rmsd"]
 
@@ -319,12 +320,14 @@ def run_ours(a):
         t0 = time.perf_counter()
         oracle.super_rmsd_traj(host_sample[:probe_n], ref, None, nthreads=cores, details=False)
         rate = probe_n / (time.perf_counter() - t0)
-        n_cpu = int(max(cores, min(e2e_frames, rate * a.cpu_seconds)))
+        n_cpu = e2e_frames - e2e_frames % cores or e2e_frames
+        reps = int(max(1, min(200, round(rate * a.cpu_seconds / n_cpu))))
         t0 = time.perf_counter()
-        rm_cpu, rot_cpu, _t1, _t2 = oracle.super_rmsd_traj(host_sample[:n_cpu], ref, None, nthreads=cores)
+        for _ in range(reps):
+            rm_cpu, rot_cpu, _t1, _t2 = oracle.super_rmsd_traj(host_sample[:n_cpu], ref, None, nthreads=cores)
         dt = time.perf_counter() - t0
-        cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n_cpu} frames of the GPU's trajectory ({natoms} atoms), O(N) C restatement of the reference path, {cores} threads, {dt:.1f} s"}
+        cpu = {"value": n_cpu * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n_cpu} frames of the GPU's trajectory ({natoms} atoms) x {reps} passes, O(N) C restatement of the reference path (oracle/gochem_oracle.c), one worker thread per frame in flight, {cores} threads, {dt:.1f} s"}
         if not wb:
             got = traj.fetch(0, n_cpu, want=("rmsd", "rot"))
             parity = {"frames_checked": n_cpu, "max_abs_rmsd_diff": float(np.abs(got["rmsd"] - rm_cpu).max()),
@@ -338,7 +341,7 @@ def run_ours(a):
                    "mode": "super (write-back, 48 B/atom)" if wb else "fit (RMSD + R + translations, 24 B/atom)",
                    "frames_per_gpu": nframes, "natoms": natoms, "sharding": f"frames x{d.world}, no collective",
                    "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9 if not wb else alg_bytes / 2e9),
-                   "kernel_variant": a.variant},
+                   "kernel_variant": a.variant, "cluster_plan": plan},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "check": {"rmsd_frame0": float(rmsd_gpu[0]), "rmsd_mean": float(rmsd_gpu.mean()), "e2e_vs_resident_max_abs": e2e_check,
                   "parity_vs_oracle": parity},

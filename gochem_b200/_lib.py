@@ -51,7 +51,8 @@ def load() -> C.CDLL:
         "gcb_device_count": (I, [C.POINTER(I)]),
         "gcb_device_info": (I, [I, C.POINTER(I), C.POINTER(C.c_size_t), C.POINTER(I), C.POINTER(I)]),
         "gcb_set_kernel_variant": (I, [I]),
-        "gcb_set_cluster_tuning": (I, [I, I, I]),
+        "gcb_set_cluster_tuning": (I, [I, I, I, I]),
+        "gcb_last_cluster_plan": (I, [C.POINTER(I)]),
         "gcb_pinned_alloc": (I, [C.c_size_t, C.POINTER(P)]),
         "gcb_pinned_free": (I, [P]),
         "gcb_traj_create": (I, [I, I, L, C.POINTER(P)]),
@@ -106,6 +107,13 @@ def _idx(a):
     if a is None:
         return None
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def last_cluster_plan() -> dict:
+    out = (C.c_int * 8)()
+    check(load().gcb_last_cluster_plan(out))
+    keys = ["cluster", "part", "atoms_per_thread", "stages", "depth", "resident", "clusters", "smem"]
+    return dict(zip(keys, list(out)))
 
 
 def device_count() -> int:

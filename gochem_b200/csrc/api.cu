@@ -96,13 +96,18 @@ int gcb_set_kernel_variant(int variant) {
     return GCB_OK;
 }
 
-int gcb_set_cluster_tuning(int cluster, int stages, int depth) {
-    if (!(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16) || stages < 0 ||
-        stages > 8 || depth < 0 || depth > 3) {
-        set_error("bad cluster tuning (%d, %d, %d)", cluster, stages, depth);
+int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident) {
+    if (cluster < 0 || cluster > 8 || stages < 0 || stages > 8 || depth < 0 || depth > 6 || resident < -1 || resident > 1) {
+        set_error("bad cluster tuning (%d, %d, %d, %d)", cluster, stages, depth, resident);
         return GCB_ERR_ARG;
     }
-    set_cluster_tuning(cluster, stages, depth == 0 ? -1 : depth);
+    set_cluster_tuning(cluster, stages, depth == 0 ? -1 : depth, resident);
+    return GCB_OK;
+}
+
+int gcb_last_cluster_plan(int* out8) {
+    if (!out8) return GCB_ERR_ARG;
+    get_last_plan(out8);
     return GCB_OK;
 }
 

@@ -104,6 +104,7 @@ int launch_dev_reduce(gcb_traj* t, int rows, double* out);
 int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos, const double* d_sigma,
                  unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
 bool cluster_kernel_supported(const gcb_traj* t);
-void set_cluster_tuning(int cluster, int stages, int depth);
+void set_cluster_tuning(int cluster, int stages, int depth, int resident);
+void get_last_plan(int* out8);
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out);
 }  // namespace gcb

@@ -124,28 +124,41 @@ K3_HD int kabsch3_jacobi(const double* h, double* rot) {
     return 0;
 }
 
-// Reciprocal / reciprocal square root with a short dependency chain: hardware seed + Newton steps
-// on the device, plain division on the host (same values to the last bits that matter here).
+// Reciprocal with a short dependency chain: hardware seed (about 20 good bits) and one cubically
+// convergent correction r (1 + e + e^2), e = 1 - x r  -> relative error ~2^-60.  Plain division on the host.
 K3_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);   // seed is good to ~2^-20; two Newton steps reach fp64 rounding level
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 #else
     return 1.0 / x;
 #endif
 }
 
+// One Newton step X <- (X + X^-T) / 2 on a 3x3 held in nine scalars; returns det(X) of the input.
+#define K3_NEWTON_STEP(det_out)                                                                         \
+    {                                                                                                   \
+        const double c0 = fma(x4, x8, -x5 * x7), c1 = fma(x5, x6, -x3 * x8), c2 = fma(x3, x7, -x4 * x6); \
+        const double c3 = fma(x2, x7, -x1 * x8), c4 = fma(x0, x8, -x2 * x6), c5 = fma(x1, x6, -x0 * x7); \
+        const double c6 = fma(x1, x5, -x2 * x4), c7 = fma(x2, x3, -x0 * x5), c8 = fma(x0, x4, -x1 * x3); \
+        det_out = fma(x2, c2, fma(x1, c1, x0 * c0));                                                    \
+        const double r = fast_rcp(det_out);                                                             \
+        x0 = fma(0.5 * c0, r, 0.5 * x0); x1 = fma(0.5 * c1, r, 0.5 * x1); x2 = fma(0.5 * c2, r, 0.5 * x2); \
+        x3 = fma(0.5 * c3, r, 0.5 * x3); x4 = fma(0.5 * c4, r, 0.5 * x4); x5 = fma(0.5 * c5, r, 0.5 * x5); \
+        x6 = fma(0.5 * c6, r, 0.5 * x6); x7 = fma(0.5 * c7, r, 0.5 * x7); x8 = fma(0.5 * c8, r, 0.5 * x8); \
+    }
+
 // Newton iteration X <- (X + X^-T) / 2 for the orthogonal polar factor of H, started from
 // H * sqrt(3) / ||H||_F (singular values of order one, so no per-step scaling, hence no square
 // roots or divisions inside the loop: one seeded reciprocal of the determinant per step).
+// The dependency chain per step is cofactors (2) -> det (3) -> reciprocal (4) -> update (1); the
+// convergence test runs on every second step only, off the common path.
 // Returns 1 when it converged to a proper rotation, 0 when the caller must use the Jacobi path
 // (det H <= 0, near-singular H, non-finite input).
 K3_HD int kabsch3_polar(const double* h, double* rot) {
-    double x[9];
     const double n0 = fma(h[2], h[2], fma(h[1], h[1], h[0] * h[0]));
     const double n1 = fma(h[5], h[5], fma(h[4], h[4], h[3] * h[3]));
     const double n2 = fma(h[8], h[8], fma(h[7], h[7], h[6] * h[6]));
@@ -156,31 +169,25 @@ K3_HD int kabsch3_polar(const double* h, double* rot) {
 #else
     const double sc = 1.7320508075688772 / sqrt(nrm);
 #endif
-#pragma unroll
-    for (int i = 0; i < 9; i++) x[i] = h[i] * sc;
-    for (int it = 0; it < 40; it++) {
-        // cofactor matrix c = det * X^-T
-        double c[9];
-        c[0] = fma(x[4], x[8], -x[5] * x[7]); c[1] = fma(x[5], x[6], -x[3] * x[8]); c[2] = fma(x[3], x[7], -x[4] * x[6]);
-        c[3] = fma(x[2], x[7], -x[1] * x[8]); c[4] = fma(x[0], x[8], -x[2] * x[6]); c[5] = fma(x[1], x[6], -x[0] * x[7]);
-        c[6] = fma(x[1], x[5], -x[2] * x[4]); c[7] = fma(x[2], x[3], -x[0] * x[5]); c[8] = fma(x[0], x[4], -x[1] * x[3]);
-        const double det = fma(x[2], c[2], fma(x[1], c[1], x[0] * c[0]));
-        // guard: proper and comfortably non-singular.  At it == 0, det = det(H) 3^1.5 / ||H||_F^3.
-        if (!(det > 5e-6)) return 0;
-        const double b = 0.5 * fast_rcp(det);
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            const double y = fma(b, c[i], 0.5 * x[i]);
-            const double e = y - x[i];
-            if (i % 3 == 0) d0 = fma(e, e, d0);
-            else if (i % 3 == 1) d1 = fma(e, e, d1);
-            else d2 = fma(e, e, d2);
-            x[i] = y;
-        }
-        if (d0 + d1 + d2 <= 1e-15) {  // ||dX||_F <= 3e-8: the error after this step is ~ ||dX||^2 / 2 < 1e-15
-#pragma unroll
-            for (int i = 0; i < 9; i++) rot[i] = x[i];
+    double x0 = h[0] * sc, x1 = h[1] * sc, x2 = h[2] * sc, x3 = h[3] * sc, x4 = h[4] * sc, x5 = h[5] * sc,
+           x6 = h[6] * sc, x7 = h[7] * sc, x8 = h[8] * sc;
+    double det;
+    // guard on the first step: proper and comfortably non-singular (det = det(H) 3^1.5 / ||H||_F^3)
+    K3_NEWTON_STEP(det)
+    if (!(det > 5e-6)) return 0;
+    K3_NEWTON_STEP(det)
+    for (int it = 0; it < 20; it++) {
+        K3_NEWTON_STEP(det)
+        if (!(det > 0.0)) return 0;
+        const double p0 = x0, p1 = x1, p2 = x2, p3 = x3, p4 = x4, p5 = x5, p6 = x6, p7 = x7, p8 = x8;
+        K3_NEWTON_STEP(det)
+        const double e0 = x0 - p0, e1 = x1 - p1, e2 = x2 - p2, e3 = x3 - p3, e4 = x4 - p4, e5 = x5 - p5,
+                     e6 = x6 - p6, e7 = x7 - p7, e8 = x8 - p8;
+        const double d = fma(e2, e2, fma(e1, e1, e0 * e0)) + fma(e5, e5, fma(e4, e4, e3 * e3)) +
+                         fma(e8, e8, fma(e7, e7, e6 * e6));
+        // ||dX||_F <= 3e-8 on the last step: the error left is ~ ||dX||^2 / 2 < 1e-15
+        if (d <= 1e-15) {
+            rot[0] = x0; rot[1] = x1; rot[2] = x2; rot[3] = x3; rot[4] = x4; rot[5] = x5; rot[6] = x6; rot[7] = x7; rot[8] = x8;
             return 1;
         }
     }

@@ -38,8 +38,8 @@ constexpr int kConsumerWarps = 8;
 constexpr int kSolverWarps = 3;
 constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
 constexpr int kMaxStages = 8;
-constexpr int kMaxSlots = 7;             // exchange slots (>= 2*D+1 with D <= 3, and > kSolverWarps)
-constexpr int kMaxCluster = 16;
+constexpr int kMaxSlots = 13;            // exchange slots (>= 2*D+1 with D <= 6, and > kSolverWarps)
+constexpr int kMaxCluster = 8;
 constexpr int kSmemBudget = 227 * 1024;
 
 struct ClusterParams {
@@ -51,7 +51,7 @@ struct ClusterParams {
     int slots;          // NS = 2*D+1
     int nclusters;      // G
     int write_back;
-    double* epart;      // [nframes][C] squared-error partials
+    double* epart;      // [nframes][C][8 consumer warps] squared-error partials
 };
 
 // ---- PTX helpers --------------------------------------------------------------------------------
@@ -103,6 +103,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
@@ -164,24 +169,34 @@ struct __align__(16) Shared {
     unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
 
-// pass 2 for one thread's K atom slots; WB = also store the superposed coordinates
-template <int K, bool DEV, bool WB>
-__device__ __forceinline__ double pass2_atoms(const double* __restrict__ sx, const double* xf, const double (&bx)[K],
-                                              const double (&by)[K], const double (&bz)[K], const double (&wk)[K],
-                                              double (&dev)[K], double* frw, int np, uint32_t real_mask,
-                                              double b0, double b1, double b2) {
+// pass 2 for one thread's K atom slots.  RESIDENT: the frame part is still in its shared-memory stage
+// (plane stride K*256); otherwise it is re-read from global memory, where it still sits in L2 (plane
+// stride np, streaming loads).  WB = also store the superposed coordinates.
+template <int K, bool DEV, bool WB, bool RESIDENT>
+__device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, long plane, const double* xf,
+                                              const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
+                                              const double (&wk)[K], double (&dev)[K], double* frw, int np,
+                                              uint32_t real_mask, uint32_t in_mask, double b0, double b1, double b2) {
+    double x[K], y[K], z[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (RESIDENT) {
+            x[k] = src[k * kConsumers]; y[k] = src[plane + k * kConsumers]; z[k] = src[2 * plane + k * kConsumers];
+        } else if ((in_mask >> k) & 1u) {
+            x[k] = __ldcs(src + k * kConsumers); y[k] = __ldcs(src + plane + k * kConsumers); z[k] = __ldcs(src + 2 * plane + k * kConsumers);
+        } else {
+            x[k] = 0.0; y[k] = 0.0; z[k] = 0.0;
+        }
+    }
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
-    const double* sy = sx + K * kConsumers;
-    const double* sz = sy + K * kConsumers;
     double e0 = 0.0, e1 = 0.0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        const double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
         // (a - centroid) R  computed as  a R - centroid R
-        const double qx = fma(z, r6, fma(y, r3, fma(x, r0, g0)));
-        const double qy = fma(z, r7, fma(y, r4, fma(x, r1, g1)));
-        const double qz = fma(z, r8, fma(y, r5, fma(x, r2, g2)));
+        const double qx = fma(z[k], r6, fma(y[k], r3, fma(x[k], r0, g0)));
+        const double qy = fma(z[k], r7, fma(y[k], r4, fma(x[k], r1, g1)));
+        const double qz = fma(z[k], r8, fma(y[k], r5, fma(x[k], r2, g2)));
         const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
         const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
         if (k & 1) e1 = fma(wk[k], d2, e1); else e0 = fma(wk[k], d2, e0);
@@ -197,7 +212,7 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ sx, con
     return e0 + e1;
 }
 
-template <int K, bool WEIGHTED, bool DEV>
+template <int K, bool WEIGHTED, bool DEV, bool RESIDENT>
 __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -239,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     if (warp == kConsumerWarps) {
         // ===================== producer =====================
         if (lane == 0 && part_len > 0) {
-            const uint64_t pol = policy_evict_first();
+            const uint64_t pol = RESIDENT ? policy_evict_first() : policy_evict_normal();
             const uint32_t seg_bytes = (uint32_t)part_len * 8u;
             const double* src = p.frames + cid * p.frame_stride + part0;
             const long src_step = (long)G * p.frame_stride;
@@ -337,17 +352,22 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         }
         const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][0]);
         const uint32_t part_bar_addr = smem_u32(&sh.part_full[0]);
+        uint32_t in_mask = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) if (tid + k * kConsumers < part_len) in_mask |= 1u << k;
         int s1 = 0, s2 = 0, slot1 = 0, slot2 = 0;      // stage / exchange slot of pass 1 (frame j) and pass 2 (frame j-D)
         uint32_t ph1 = 0, ph2 = 0;                     // parities: full[s1], solved[slot2]
+        const long fstep = (long)G * p.frame_stride;
+        const double* fr2 = p.frames + cid * p.frame_stride + part0 + tid;     // frame of pass 2 (global / L2 copy)
         double* frw = cp.write_back ? (p.frames_rw + cid * p.frame_stride + part0 + tid) : nullptr;
-        const long frw_step = (long)G * p.frame_stride;
+        double* ep = cp.epart + (cid * C + rank) * kConsumerWarps + warp;
+        const long ep_step = (long)G * C * kConsumerWarps;
         for (int j = 0; j < nloc + D; j++) {
-            double acc[12];
-#pragma unroll
-            for (int k = 0; k < 12; k++) acc[k] = 0.0;
-            double e = 0.0;
             if (j < nloc) {
                 // ---- pass 1 of local frame j ----
+                double acc[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) acc[k] = 0.0;
                 if (tid == 0) TRACE(4, j);
                 mbar_wait(&sh.full[s1], ph1);
                 if (tid == 0) TRACE(5, j);
@@ -363,63 +383,65 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     acc[6] = fma(y, bx[k], acc[6]); acc[7] = fma(y, by[k], acc[7]); acc[8] = fma(y, bz[k], acc[8]);
                     acc[9] = fma(z, bx[k], acc[9]); acc[10] = fma(z, by[k], acc[10]); acc[11] = fma(z, bz[k], acc[11]);
                 }
+                if (!RESIDENT) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.empty[s1]);   // pass 2 re-reads the frame from L2: free the stage now
+                }
+                // ---- warp totals -> red[slot]; the last warp to deliver sums the 8 warps in fixed order and pushes
+                //      the CTA's partial sums to every CTA of the cluster ----
+                double t0, t1;
+                warp_reduce12(acc, lane, t0, t1);
+                double* red = sh.red[slot1][warp];
+                if ((lane & 3) == 0) {
+                    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+                    red[6 * b4 + 3 * b3 + 2 * b2] = t0;
+                    if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (tid == 0) TRACE(7, j);
+                unsigned int prev = 0;
+                if (lane == 0) prev = atomicAdd(&sh.red_count[slot1], 1u);
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                if (prev == kConsumerWarps - 1) {
+                    __threadfence_block();
+                    if (lane < 12) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int w = 0; w < kConsumerWarps; w++) v += sh.red[slot1][w][lane];
+                        const uint32_t off = (uint32_t)(slot1 * (int)sizeof(sh.partials[0]));
+                        for (int c = 0; c < C; c++)
+                            st_async_f64(mapa(my_part_addr + off + (uint32_t)lane * 8u, (uint32_t)c), v,
+                                         mapa(part_bar_addr + (uint32_t)slot1 * 8u, (uint32_t)c));
+                    }
+                    if (lane == 0) { atomicExch(&sh.red_count[slot1], 0u); TRACE(1, j); }
+                }
+                if (++s1 == S) { s1 = 0; ph1 ^= 1u; }
+                if (++slot1 == NS) slot1 = 0;
             }
             if (j >= D) {
-                // ---- pass 2 of local frame j - D, from the same shared-memory stage ----
+                // ---- pass 2 of local frame j - D ----
                 mbar_wait(&sh.solved[slot2], ph2);
                 if (tid == 0) TRACE(6, j - D);
-                const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
-                if (frw) e = pass2_atoms<K, DEV, true>(sx, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                else e = pass2_atoms<K, DEV, false>(sx, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, 0.0, 0.0, 0.0);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
-            }
-            // ---- warp-level reductions: 12 sums of frame j, squared error of frame j-D ----
-            double t0 = 0.0, t1 = 0.0;
-            if (j < nloc) warp_reduce12(acc, lane, t0, t1);
-            if (j >= D) {
+                double e;
+                if (RESIDENT) {
+                    const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
+                    if (frw) e = pass2_atoms<K, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
+                    if (++s2 == S) s2 = 0;
+                } else {
+                    if (frw) e = pass2_atoms<K, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
-            }
-            double* red = sh.red[slot1][warp];
-            if ((lane & 3) == 0) {
-                const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
-                red[6 * b4 + 3 * b3 + 2 * b2] = t0;
-                if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
-            }
-            if (lane == 0) red[12] = e;
-            __threadfence_block();
-            __syncwarp();
-            if (tid == 0) TRACE(7, j);
-            // the last warp to deliver sums the 8 warps in fixed order and pushes the CTA's partials to the cluster
-            unsigned int prev = 0;
-            if (lane == 0) prev = atomicAdd(&sh.red_count[slot1], 1u);   // relaxed RMW ...
-            prev = __shfl_sync(0xffffffffu, prev, 0);
-            if (prev == kConsumerWarps - 1) {
-                __threadfence_block();                                  // ... ordered against the other warps' stores
-                double v = 0.0;
-                if (lane < 13) {
-#pragma unroll
-                    for (int w = 0; w < kConsumerWarps; w++) v += sh.red[slot1][w][lane];
-                }
-                if (lane == 12 && j >= D) cp.epart[(cid + (long)(j - D) * G) * C + rank] = v;
-                if (lane < 12 && j < nloc) {
-                    const uint32_t off = (uint32_t)(slot1 * (int)sizeof(sh.partials[0]));
-                    for (int c = 0; c < C; c++)
-                        st_async_f64(mapa(my_part_addr + off + (uint32_t)lane * 8u, (uint32_t)c), v,
-                                     mapa(part_bar_addr + (uint32_t)slot1 * 8u, (uint32_t)c));
-                }
-                if (lane == 0) { atomicExch(&sh.red_count[slot1], 0u); TRACE(1, j); }
-            }
-            // advance the ring positions (no divisions in the loop)
-            if (++slot1 == NS) slot1 = 0;
-            if (j < nloc) {
-                if (++s1 == S) { s1 = 0; ph1 ^= 1u; }
-            }
-            if (j >= D) {
-                if (++s2 == S) s2 = 0;
+                if (lane == 0) *ep = e;              // per-warp squared error; finish_rmsd_kernel adds them in fixed order
+                ep += ep_step;
+                fr2 += fstep;
+                if (frw) frw += fstep;
                 if (++slot2 == NS) { slot2 = 0; ph2 ^= 1u; }
-                if (frw) frw += frw_step;
             }
         }
         if (DEV) {
@@ -441,51 +463,64 @@ __global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restri
     const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     double s = 0.0;
-    for (int r = 0; r < C; r++) s += epart[f * C + r];
+    for (int r = 0; r < C * kConsumerWarps; r++) s += epart[f * C * kConsumerWarps + r];
     rmsd[f] = sqrt(s * inv_n);
 }
 
 struct Plan {
-    int cluster, part, kinst, stages, depth, slots;
+    int cluster, part, kinst, stages, depth, resident;
     size_t smem;
 };
 
-constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12};
 
-int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0;
+// tuning overrides (0 / -1 = built-in choice)
+int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0, g_tune_resident = -1;
 
-bool make_plan(int np, Plan* pl) {
+// Choose CTAs per frame, atoms per thread, stage count, pipeline depth.
+//  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
+//  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
+bool make_plan(int np, bool heavy, Plan* pl) {
     const size_t fixed = ((sizeof(Shared) + 127) / 128) * 128;
-    const int cands[] = {1, 2, 4, 8, 16};
-    for (int c : cands) {
+    const int resident = g_tune_resident >= 0 ? g_tune_resident : 1;
+    for (int c = 1; c <= kMaxCluster; c++) {
         if (g_tune_cluster && c != g_tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
         const int kneed = (part + kConsumers - 1) / kConsumers;
         int kinst = 0;
         for (int k : kInst) if (k >= kneed) { kinst = k; break; }
         if (!kinst) continue;
+        // Measured on B200 (profiles/r1_tuning.md): with pass 2 that also stores or takes square roots
+        // (heavy), 4 stages and depth 2 win; for the pure fit pass the fattest threads that keep 3 stages win.
+        if (!g_tune_cluster && kinst > (heavy ? 8 : 10) && c < kMaxCluster) continue;
         const size_t stage = (size_t)3 * kinst * kConsumers * sizeof(double);
         int stages = (int)((kSmemBudget - fixed) / stage);
         if (stages > kMaxStages) stages = kMaxStages;
+        if (!resident && stages > 4) stages = 4;
         if (g_tune_stages && g_tune_stages < stages) stages = g_tune_stages;
-        if (stages < 3) continue;
-        if (!g_tune_cluster && kinst > 12 && c < 16) continue;   // prefer more CTAs over very fat threads
-        int depth = stages - 2;
-        if (depth > 2) depth = 2;
-        if (g_tune_depth >= 1 && g_tune_depth <= 3 && g_tune_depth <= stages - 2) depth = g_tune_depth;
+        if (stages < (resident ? 3 : 2)) continue;
+        int depth;
+        if (resident) {
+            depth = stages - 2 > 2 ? 2 : stages - 2;
+            if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && g_tune_depth <= 6) depth = g_tune_depth;
+        } else {
+            depth = 4;
+            if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
+        }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
-        pl->slots = 2 * depth + 1;
+        pl->resident = resident;
         pl->smem = fixed + stage * stages;
         return true;
     }
     return false;
 }
 
-template <int K, bool W, bool DV>
-int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out, ClusterParams* final_cp) {
-    auto kern = super_cluster_kernel<K, W, DV>;
+int g_last_plan[8] = {0};
+
+template <int K, bool W, bool DV, bool RES>
+int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
+    auto kern = super_cluster_kernel<K, W, DV, RES>;
     GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    if (pl.cluster > 8) GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -502,7 +537,6 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters < 1) { set_error("cluster of %d CTAs with %zu bytes of shared memory cannot be scheduled", pl.cluster, pl.smem); return GCB_ERR_CUDA; }
     long g = max_clusters;
-    if (g > t->sm_count / pl.cluster) g = t->sm_count / pl.cluster;
     if (g > cp.p.nframes) g = cp.p.nframes;
     ClusterParams c2 = cp;
     c2.nclusters = (int)g;
@@ -510,26 +544,33 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     GCB_CUDA(cudaLaunchKernelEx(&cfg, kern, c2));
     GCB_LAUNCHED();
     *nclusters_out = (int)g;
-    *final_cp = c2;
+    g_last_plan[0] = pl.cluster; g_last_plan[1] = pl.part; g_last_plan[2] = pl.kinst; g_last_plan[3] = pl.stages;
+    g_last_plan[4] = pl.depth; g_last_plan[5] = pl.resident; g_last_plan[6] = (int)g; g_last_plan[7] = (int)pl.smem;
     return GCB_OK;
 }
 
-template <bool W, bool DV>
-int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g, ClusterParams* fc) {
+template <bool W, bool DV, bool RES>
+int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g) {
     switch (pl.kinst) {
-        case 1: return launch_inst<1, W, DV>(t, cp, pl, g, fc);
-        case 2: return launch_inst<2, W, DV>(t, cp, pl, g, fc);
-        case 3: return launch_inst<3, W, DV>(t, cp, pl, g, fc);
-        case 4: return launch_inst<4, W, DV>(t, cp, pl, g, fc);
-        case 5: return launch_inst<5, W, DV>(t, cp, pl, g, fc);
-        case 6: return launch_inst<6, W, DV>(t, cp, pl, g, fc);
-        case 8: return launch_inst<8, W, DV>(t, cp, pl, g, fc);
-        case 10: return launch_inst<10, W, DV>(t, cp, pl, g, fc);
-        case 12: return launch_inst<12, W, DV>(t, cp, pl, g, fc);
-        case 16: return launch_inst<16, W, DV>(t, cp, pl, g, fc);
+        case 1: return launch_inst<1, W, DV, RES>(t, cp, pl, g);
+        case 2: return launch_inst<2, W, DV, RES>(t, cp, pl, g);
+        case 3: return launch_inst<3, W, DV, RES>(t, cp, pl, g);
+        case 4: return launch_inst<4, W, DV, RES>(t, cp, pl, g);
+        case 5: return launch_inst<5, W, DV, RES>(t, cp, pl, g);
+        case 6: return launch_inst<6, W, DV, RES>(t, cp, pl, g);
+        case 7: return launch_inst<7, W, DV, RES>(t, cp, pl, g);
+        case 8: return launch_inst<8, W, DV, RES>(t, cp, pl, g);
+        case 10: return launch_inst<10, W, DV, RES>(t, cp, pl, g);
+        case 12: return launch_inst<12, W, DV, RES>(t, cp, pl, g);
     }
     set_error("no kernel instance for %d atoms per thread", pl.kinst);
     return GCB_ERR_ARG;
+}
+
+template <bool RES>
+int launch_r(gcb_traj* t, const ClusterParams& cp, const Plan& pl, bool weighted, bool want_dev, int* g) {
+    if (weighted) return want_dev ? launch_k<true, true, RES>(t, cp, pl, g) : launch_k<true, false, RES>(t, cp, pl, g);
+    return want_dev ? launch_k<false, true, RES>(t, cp, pl, g) : launch_k<false, false, RES>(t, cp, pl, g);
 }
 
 double* g_epart[16] = {nullptr};
@@ -543,22 +584,25 @@ extern "C" int gcb_trace_read(long long* out) {
 }
 #endif
 
-void set_cluster_tuning(int cluster, int stages, int depth) {
+void get_last_plan(int* out8) { for (int i = 0; i < 8; i++) out8[i] = g_last_plan[i]; }
+
+void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
     g_tune_cluster = cluster;
     g_tune_stages = stages;
     g_tune_depth = depth;
+    g_tune_resident = resident;
 }
 
 bool cluster_kernel_supported(const gcb_traj* t) {
     Plan pl;
-    return make_plan(t->np, &pl);
+    return make_plan(t->np, false, &pl);
 }
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
     Plan pl;
-    if (!make_plan(t->np, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    if (!make_plan(t->np, want_dev || p.frames_rw != nullptr, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     const int dev = t->dev & 15;
-    const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster;
+    const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * kConsumerWarps;
     if (need > g_epart_cap[dev]) {
         GCB_CUDA(cudaStreamSynchronize(t->stream));
         cudaFree(g_epart[dev]);
@@ -573,15 +617,12 @@ int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     cp.part = pl.part;
     cp.stages = pl.stages;
     cp.depth = pl.depth;
-    cp.slots = pl.slots;
+    cp.slots = kMaxSlots;
     cp.nclusters = 0;
     cp.write_back = p.frames_rw != nullptr;
     cp.epart = g_epart[dev];
     int g = 0;
-    ClusterParams fc;
-    int rc;
-    if (weighted) rc = want_dev ? launch_k<true, true>(t, cp, pl, &g, &fc) : launch_k<true, false>(t, cp, pl, &g, &fc);
-    else rc = want_dev ? launch_k<false, true>(t, cp, pl, &g, &fc) : launch_k<false, false>(t, cp, pl, &g, &fc);
+    int rc = pl.resident ? launch_r<true>(t, cp, pl, weighted, want_dev, &g) : launch_r<false>(t, cp, pl, weighted, want_dev, &g);
     if (rc) return rc;
     if (rows_out) *rows_out = g;
     if (p.rmsd) {

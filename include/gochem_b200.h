@@ -55,9 +55,13 @@ int gcb_device_count(int *n);
 /* Properties the host side sizes its work by: SM count, bytes of device memory, compute capability. */
 int gcb_device_info(int dev, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
 int gcb_set_kernel_variant(int variant);
-/* Tuning hook for the cluster kernel: CTAs per frame (1, 2, 4, 8, 16), shared-memory stages, and how many
- * frames pass 2 trails pass 1 (1..3).  0 / 0 / 0 restores the built-in choice. */
-int gcb_set_cluster_tuning(int cluster, int stages, int depth);
+/* Tuning hook for the cluster kernel: CTAs per frame (1..8), shared-memory stages, how many frames pass 2
+ * trails pass 1 (1..6), and where pass 2 reads the frame from (1 = its shared-memory stage, 0 = L2,
+ * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice. */
+int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident);
+/* Shape of the last cluster-kernel launch: {CTAs per frame, atoms per CTA, atoms per thread, stages, depth,
+ * resident, clusters launched, dynamic shared memory bytes}. */
+int gcb_last_cluster_plan(int *out8);
 
 /* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
 int gcb_pinned_alloc(size_t bytes, void **p);

@@ -262,12 +262,14 @@ def test_device_synth_properties_full_size(variant):
     t.close()
 
 
-@pytest.mark.parametrize("natoms,cluster,stages,depth", [
-    (1500, 1, 0, 0), (1500, 1, 3, 1), (1500, 2, 0, 3), (1500, 4, 4, 2), (1500, 8, 0, 1),
-    (5000, 2, 0, 0), (5000, 4, 0, 2), (5000, 8, 5, 3), (10000, 4, 0, 0), (10000, 8, 0, 2), (10000, 8, 0, 3),
-    (10000, 16, 0, 2), (613, 1, 0, 0), (613, 8, 0, 2), (40, 4, 0, 1),
+@pytest.mark.parametrize("natoms,cluster,stages,depth,resident", [
+    (1500, 1, 0, 0, 1), (1500, 1, 3, 1, 1), (1500, 2, 0, 3, 1), (1500, 4, 4, 2, 1), (1500, 8, 0, 1, 1),
+    (5000, 2, 0, 0, 1), (5000, 4, 0, 2, 1), (5000, 8, 5, 3, 1), (10000, 4, 0, 0, 1), (10000, 8, 0, 3, 1),
+    (613, 1, 0, 0, 1), (613, 8, 0, 2, 1), (40, 4, 0, 1, 1),
+    (1500, 1, 0, 0, 0), (1500, 1, 2, 6, 0), (1500, 3, 0, 4, 0), (5000, 2, 0, 5, 0), (5000, 5, 3, 2, 0),
+    (10000, 4, 0, 0, 0), (10000, 6, 0, 6, 0), (10000, 7, 2, 1, 0), (10000, 8, 0, 4, 0), (613, 8, 0, 3, 0), (40, 4, 0, 1, 0),
 ])
-def test_cluster_kernel_tunings(natoms, cluster, stages, depth):
+def test_cluster_kernel_tunings(natoms, cluster, stages, depth, resident):
     """Every cluster shape / pipeline depth must give the same answers as the oracle."""
     lib = _lib.load()
     nframes = 333
@@ -278,7 +280,7 @@ def test_cluster_kernel_tunings(natoms, cluster, stages, depth):
     t = device_traj(frames)
     try:
         _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
-        _lib.check(lib.gcb_set_cluster_tuning(cluster, stages, depth))
+        _lib.check(lib.gcb_set_cluster_tuning(cluster, stages, depth, resident))
         out = t.super_rmsd(ref)
         rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None, nthreads=8)
         assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
@@ -291,6 +293,6 @@ def test_cluster_kernel_tunings(natoms, cluster, stages, depth):
         assert np.abs(dev / nframes - want).max() < 1e-10
         assert np.abs(t.download() - aligned).max() < TOL_XYZ
     finally:
-        lib.gcb_set_cluster_tuning(0, 0, 0)
+        lib.gcb_set_cluster_tuning(0, 0, 0, -1)
         lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
         t.close()

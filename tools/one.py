@@ -19,7 +19,7 @@ if c < 0:
     _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_GENERIC))
 else:
     _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
-    _lib.check(lib.gcb_set_cluster_tuning(c, s, d))
+    _lib.check(lib.gcb_set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1'))))
 idx = np.arange(0, natoms, 2)
 t.sync()
 t.timer_start()

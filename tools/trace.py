@@ -14,7 +14,7 @@ lib = _lib.load()
 ref = synth.make_reference(natoms)
 t = _lib.DeviceTraj(natoms, nframes)
 t.synth_fill(ref, synth.atom_sigmas(natoms), nframes, frame0_is_ref=True)
-_lib.check(lib.gcb_set_cluster_tuning(c, s, d))
+_lib.check(lib.gcb_set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1'))))
 for _ in range(2):
     t.super_rmsd_async(ref)
 t.sync()

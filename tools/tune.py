@@ -43,11 +43,18 @@ def run(label):
 _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_GENERIC))
 run("generic")
 _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
-for c in (1, 2, 4, 8, 16):
-    for s in (0, 3, 4, 6):
-        for d in (1, 2, 3):
-            try:
-                _lib.check(lib.gcb_set_cluster_tuning(c, s, d))
-                run(f"C{c} S{s} D{d}")
-            except _lib.GcbError as e:
-                print(json.dumps({"cfg": f"C{c} S{s} D{d}", "err": e.msg[:80]}), flush=True)
+cfgs = []
+for res in (0, 1):
+    for c in (1, 2, 3, 4, 5, 6, 7, 8):
+        for st in ((0, 2, 3) if res == 0 else (0,)):
+            for d in ((2, 4, 6) if res == 0 else (1, 2, 3)):
+                cfgs.append((c, st, d, res))
+if len(sys.argv) > 4:
+    cfgs = [tuple(int(x) for x in a.split(",")) for a in sys.argv[4:]]
+for c, st, d, res in cfgs:
+    try:
+        _lib.check(lib.gcb_set_cluster_tuning(c, st, d, res))
+        run(f"C{c} S{st} D{d} R{res}")
+        print("   plan", _lib.last_cluster_plan(), flush=True)
+    except _lib.GcbError as e:
+        print(json.dumps({"cfg": f"C{c} S{st} D{d} R{res}", "err": e.msg[:80]}), flush=True)
