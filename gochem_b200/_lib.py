@@ -69,6 +69,7 @@ def load() -> C.CDLL:
         "gcb_super_rmsd_async": (I, [P, L, L, P, I, P, P, I, I]),
         "gcb_fetch_results": (I, [P, L, L, P, P, P, P]),
         "gcb_rmsd": (I, [P, L, L, P, I, P, P, I, P]),
+        "gcb_peratom_dist": (I, [P, L, P, I, P, P, I, P]),
         "gcb_peratom_dev_sum": (I, [P, L, L, P, P, I, I, P, P]),
         "gcb_timer_start": (I, [P]),
         "gcb_timer_stop": (I, [P, C.POINTER(C.c_float)]),

@@ -54,5 +54,24 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(LIB_DIR, "libgochem_host.so")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ host-side mirror of the reference's Go API (gochem_b200/host), linked against the C ABI."""
+    build()
+    host = os.path.join(HERE, "host")
+    srcs = [os.path.join(host, f) for f in ("gochem.cpp", "capi.cpp")]
+    deps = srcs + [os.path.join(host, "gochem.hpp"), os.path.join(HERE, "..", "include", "gochem_host.h"),
+                   os.path.join(HERE, "..", "include", "gochem_b200.h")]
+    if force or _stale(HOST_LIB, deps):
+        cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_LIB, *srcs,
+               "-L" + LIB_DIR, "-lgochem_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+        subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
+    build_host()
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

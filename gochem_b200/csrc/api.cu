@@ -525,6 +525,49 @@ int gcb_rmsd(gcb_traj* tb, long first, long nframes, const double* ref_aos, int 
     return GCB_OK;
 }
 
+int gcb_peratom_dist(gcb_traj* tb, long frame, const double* ref_aos, int natoms_ref, const int* idx_test,
+                     const int* idx_ref, int nidx, double* out) {
+    int rc = check_window(tb, frame, 1, true);
+    if (rc) return rc;
+    gcb_traj_ext* t = X(tb);
+    if (!ref_aos || !out) { set_error("NULL template or output"); return GCB_ERR_ARG; }
+    const bool all = (idx_test == nullptr || nidx == 0);
+    if (all && natoms_ref != t->natoms) { set_error("chem.memMSD: Ill formed matrices for memMSD calculation"); return GCB_ERR_SHAPE; }
+    const int n = all ? t->natoms : nidx;
+    std::vector<int> it((size_t)n);
+    std::vector<double> pairs(3 * (size_t)n);
+    for (int k = 0; k < n; k++) {
+        const int a = all ? k : idx_test[k];
+        const int b = all ? k : (idx_ref ? idx_ref[k] : idx_test[k]);
+        if (a < 0 || a >= t->natoms || b < 0 || b >= natoms_ref) { set_error("index %d of the lists is out of range", k); return GCB_ERR_INDEXES; }
+        it[(size_t)k] = a;
+        pairs[(size_t)k] = ref_aos[3 * (size_t)b];
+        pairs[(size_t)n + k] = ref_aos[3 * (size_t)b + 1];
+        pairs[2 * (size_t)n + k] = ref_aos[3 * (size_t)b + 2];
+    }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    t->cache.valid = false;  // the gather buffers are shared with the template cache
+    GCB_CUDA(cudaStreamSynchronize(t->stream));
+    if (n > t->idx_cap) {
+        cudaFree(t->d_refpairs); cudaFree(t->d_idx);
+        t->d_refpairs = nullptr; t->d_idx = nullptr; t->idx_cap = 0;
+        GCB_CUDA(cudaMalloc(&t->d_refpairs, sizeof(double) * 3 * (size_t)n));
+        GCB_CUDA(cudaMalloc(&t->d_idx, sizeof(int) * (size_t)n));
+        t->idx_cap = n;
+    }
+    double* d_out = nullptr;
+    GCB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+    cudaMemcpyAsync(t->d_refpairs, pairs.data(), sizeof(double) * pairs.size(), cudaMemcpyHostToDevice, t->stream);
+    cudaMemcpyAsync(t->d_idx, it.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, t->stream);
+    rc = launch_peratom_dist(t, t->d_frames + frame * 3L * t->np, t->d_refpairs, t->d_idx, n, d_out);
+    if (rc == GCB_OK) cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, t->stream);
+    cudaError_t e = cudaStreamSynchronize(t->stream);
+    cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("per-atom distance kernel failed: %s", cudaGetErrorString(e)); return GCB_ERR_CUDA; }
+    return GCB_OK;
+}
+
 int gcb_timer_start(gcb_traj* t) {
     if (!t) return GCB_ERR_ARG;
     GCB_CUDA(cudaSetDevice(t->dev));

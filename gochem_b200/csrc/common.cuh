@@ -101,6 +101,7 @@ int launch_rmsd_nofit(gcb_traj* t, const double* frames, long nframes, const dou
 int launch_rmsd_nofit_gather(gcb_traj* t, const double* frames, long nframes, const double* refpairs_raw, const int* idx,
                              int nidx, double* rmsd);
 int launch_dev_reduce(gcb_traj* t, int rows, double* out);
+int launch_peratom_dist(gcb_traj* t, const double* frame, const double* refpairs, const int* idx, int nidx, double* out);
 int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos, const double* d_sigma,
                  unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
 bool cluster_kernel_supported(const gcb_traj* t);

@@ -280,6 +280,25 @@ rmsd_nofit_gather_kernel(const double* __restrict__ frames, long frame_stride, i
     }
 }
 
+// chem.MemPerAtomRMSD without superposition (geometric.go:294-321): out[k] = |test[idx[k]] - templa_k|
+__global__ void __launch_bounds__(256) peratom_dist_kernel(const double* __restrict__ frame, int np,
+                                                          const double* __restrict__ refpairs, const int* __restrict__ idx,
+                                                          int nidx, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nidx) return;
+    const int i = idx[k];
+    const double dx = frame[i] - refpairs[k], dy = frame[np + i] - refpairs[nidx + k],
+                 dz = frame[2L * np + i] - refpairs[2L * nidx + k];
+    out[k] = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+}
+
+int launch_peratom_dist(gcb_traj* t, const double* frame, const double* refpairs, const int* idx, int nidx, double* out) {
+    peratom_dist_kernel<<<(nidx + 255) / 256, 256, 0, t->stream>>>(frame, t->np, refpairs, idx, nidx, out);
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
 // Fixed-order sum of the per-CTA per-atom rows (deterministic for a fixed launch shape).
 __global__ void __launch_bounds__(256) dev_reduce_kernel(const double* __restrict__ part, int rows, int np, int natoms,
                                                         double* __restrict__ out) {

@@ -1,0 +1,244 @@
+// capi.cpp -- extern "C" shim of include/gochem_host.h over gochem.hpp (test plumbing for Python).
+#include <cstring>
+#include <string>
+
+#include "../../include/gochem_host.h"
+#include "gochem.hpp"
+
+using namespace gochem;
+
+static thread_local std::string t_err;
+static thread_local bool t_last_frame = false;
+
+static int fail(const Error& e) {
+    t_err = e.String();
+    t_last_frame = e.last_frame;
+    return e.code ? e.code : -1;
+}
+static int ret(const Error& e) { return e ? fail(e) : 0; }
+
+static v3::Matrix mat(const double* p, int n) {
+    v3::Matrix m = v3::Matrix::Zeros(n);
+    if (n > 0) memcpy(m.data(), p, sizeof(double) * 3 * (size_t)n);
+    return m;
+}
+
+static chem::IndexLists lists(const int* i0, int n0, const int* i1, int n1, int nlists) {
+    chem::IndexLists L;
+    if (nlists >= 1) L.emplace_back(i0 ? std::vector<int>(i0, i0 + n0) : std::vector<int>());
+    if (nlists >= 2) L.emplace_back(i1 ? std::vector<int>(i1, i1 + n1) : std::vector<int>());
+    return L;
+}
+
+namespace {
+struct FlatTopology : chem::Atomer {
+    std::vector<chem::Atom> atoms;
+    const chem::Atom& Atom(int i) const override { return atoms.at((size_t)i); }
+    int Len() const override { return (int)atoms.size(); }
+};
+FlatTopology topology(int natoms, const char* const* names, const char* const* chains, const int* molids) {
+    FlatTopology t;
+    t.atoms.resize((size_t)natoms);
+    for (int i = 0; i < natoms; i++) {
+        t.atoms[(size_t)i].Name = names ? names[i] : "CA";
+        t.atoms[(size_t)i].Chain = chains ? chains[i] : "A";
+        t.atoms[(size_t)i].MolID = molids ? molids[i] : i + 1;
+    }
+    return t;
+}
+}  // namespace
+
+extern "C" {
+
+size_t gch_last_error(char* buf, size_t cap) {
+    if (buf && cap) {
+        size_t n = t_err.size() < cap - 1 ? t_err.size() : cap - 1;
+        memcpy(buf, t_err.data(), n);
+        buf[n] = 0;
+    }
+    return t_err.size();
+}
+int gch_last_error_is_last_frame(void) { return t_last_frame ? 1 : 0; }
+int gch_set_device(int dev) { return ret(chem::SetDevice(dev)); }
+
+int gch_super(double* test, int ntest, const double* templa, int ntempla, const int* i0, int n0, const int* i1, int n1, int nlists) {
+    v3::Matrix t = mat(test, ntest), m = mat(templa, ntempla);
+    Error e = chem::Super(t, m, lists(i0, n0, i1, n1, nlists));
+    if (e) return fail(e);
+    memcpy(test, t.data(), sizeof(double) * 3 * (size_t)ntest);
+    return 0;
+}
+
+int gch_rmsd(const double* test, int ntest, const double* templa, int ntempla, const int* i0, int n0, const int* i1, int n1,
+             int nlists, double* out) {
+    return ret(chem::RMSD(mat(test, ntest), mat(templa, ntempla), out, lists(i0, n0, i1, n1, nlists)));
+}
+
+int gch_mem_per_atom_rmsd(const double* test, int ntest, const double* templa, int ntempla, const int* i0, int n0, const int* i1,
+                          int n1, int nlists, double* out) {
+    const int n = (nlists == 0 || n0 == 0) ? ntest : n0;
+    v3::Matrix tmp = v3::Matrix::Zeros(n), ct = v3::Matrix::Zeros(n), cm = v3::Matrix::Zeros(n);
+    std::vector<double> r;
+    Error e = chem::MemPerAtomRMSD(mat(test, ntest), mat(templa, ntempla), &ct, &cm, tmp, &r, lists(i0, n0, i1, n1, nlists));
+    if (e) return fail(e);
+    memcpy(out, r.data(), sizeof(double) * r.size());
+    return 0;
+}
+
+int gch_rotator_translator_to_super(const double* test, const double* templa, int n, double* transformed, double* rot, double* t1,
+                                    double* t2) {
+    v3::Matrix tr, r, a, b;
+    Error e = chem::RotatorTranslatorToSuper(mat(test, n), mat(templa, n), transformed ? &tr : nullptr, &r, &a, &b);
+    if (e) return fail(e);
+    if (transformed) memcpy(transformed, tr.data(), sizeof(double) * 3 * (size_t)n);
+    if (rot) memcpy(rot, r.data(), sizeof(double) * 9);
+    if (t1) memcpy(t1, a.data(), sizeof(double) * 3);
+    if (t2) memcpy(t2, b.data(), sizeof(double) * 3);
+    return 0;
+}
+
+int gch_mobile_limit(double limit, int tolerance, const double* v, int n, int* n_out, double* limit_out) {
+    return ret(align::mobileLimit(limit, tolerance, std::vector<double>(v, v + n), n_out, limit_out));
+}
+int gch_approx_eq(double i, double j, double eps) { return align::approxEq(i, j, eps) ? 1 : 0; }
+int gch_same_elements(const int* a, int na, const int* b, int nb) {
+    return align::sameElementsInt(std::vector<int>(a, a + na), std::vector<int>(b, b + nb)) ? 1 : 0;
+}
+int gch_disagreement(const int* a, int na, const int* b, int nb) {
+    return align::disagreementInt(std::vector<int>(a, a + na), std::vector<int>(b, b + nb));
+}
+long gch_selected_frames(long F, int cpus, int begin, int skip, long* out, long cap) {
+    std::vector<long> s = align::selectedFrames(F, cpus, begin, skip);
+    for (long i = 0; i < (long)s.size() && i < cap; i++) out[i] = s[(size_t)i];
+    return (long)s.size();
+}
+void gch_shard_range(long nsel, int rank, int nranks, long* first, long* count) { align::shardRange(nsel, rank, nranks, first, count); }
+
+void* gch_lovo_state_new(const int* full, int nfull, double less_than, int minimum_n) {
+    return new align::LovoState(std::vector<int>(full, full + nfull), less_than, minimum_n);
+}
+void gch_lovo_state_free(void* st) { delete static_cast<align::LovoState*>(st); }
+int gch_lovo_state_fit_indexes(void* st, int* out, int cap) {
+    const std::vector<int>& f = static_cast<align::LovoState*>(st)->FitIndexes();
+    for (int i = 0; i < (int)f.size() && i < cap; i++) out[i] = f[(size_t)i];
+    return (int)f.size();
+}
+int gch_lovo_state_step(void* st, const double* rmsd, int natoms, int* converged) {
+    Error e;
+    bool c = static_cast<align::LovoState*>(st)->Step(std::vector<double>(rmsd, rmsd + natoms), &e);
+    if (e) return fail(e);
+    *converged = c ? 1 : 0;
+    return 0;
+}
+int gch_lovo_state_disagreement(void* st) { return static_cast<align::LovoState*>(st)->Disagreement(); }
+int gch_lovo_state_finish(void* st, int natoms, int frames_read, int* N, int* natoms_out, double* rmsd_out, int* iterations) {
+    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    align::LOVOReturn r;
+    static_cast<align::LovoState*>(st)->Finish(top, frames_read, &r);
+    *N = r.N;
+    *iterations = r.Iterations;
+    for (int i = 0; i < r.N; i++) natoms_out[i] = r.Natoms[(size_t)i];
+    for (size_t i = 0; i < r.RMSD.size(); i++) rmsd_out[i] = r.RMSD[i];
+    return 0;
+}
+
+int gch_dcd_write(const char* path, const double* frames, long nframes, int natoms) {
+    std::unique_ptr<dcd::DCDWObj> w;
+    if (Error e = dcd::DCDWObj::NewWriter(path, natoms, &w)) return fail(e);
+    for (long f = 0; f < nframes; f++) {
+        v3::Matrix m = mat(frames + (size_t)f * 3 * (size_t)natoms, natoms);
+        if (Error e = w->WNext(m)) return fail(e);
+    }
+    w->Close();
+    return 0;
+}
+
+int gch_dcd_read(const char* path, double* out, long cap, long* nframes, int* natoms, int chunk) {
+    std::unique_ptr<dcd::DCDObj> d;
+    if (Error e = dcd::DCDObj::New(path, &d)) return fail(e);
+    *natoms = d->Len();
+    long n = 0;
+    const size_t fsz = 3 * (size_t)d->Len();
+    if (chunk <= 0) {
+        v3::Matrix m = v3::Matrix::Zeros(d->Len());
+        for (;;) {
+            Error e = d->Next(&m);
+            if (e) {
+                if (!e.last_frame) return fail(e);
+                break;
+            }
+            if (n < cap) memcpy(out + (size_t)n * fsz, m.data(), sizeof(double) * fsz);
+            n++;
+        }
+    } else {
+        std::vector<v3::Matrix> ms((size_t)chunk);
+        for (auto& m : ms) m = v3::Matrix::Zeros(d->Len());
+        for (;;) {
+            std::vector<v3::Matrix*> slots;
+            for (auto& m : ms) slots.push_back(&m);
+            Error e = d->NextConc(slots);
+            if (e) {
+                if (!e.last_frame) return fail(e);
+                break;  // a partial chunk is dropped, as in RMSDTraj
+            }
+            for (auto* m : slots) {
+                if (n < cap) memcpy(out + (size_t)n * fsz, m->data(), sizeof(double) * fsz);
+                n++;
+            }
+        }
+    }
+    *nframes = n;
+    return 0;
+}
+
+int gch_rmsd_traj(const char* path, const double* ref, int natoms, const int* indexes, int nidx, int cpus, int begin, int skip,
+                  const char* write_traj, int dev, int rank, int nranks, void* comm, double* rmsd, int* frames) {
+    std::unique_ptr<chem::ConcTraj> traj;
+    if (Error e = align::opentraj(path, &traj)) return fail(e);
+    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    align::Options o;
+    o.Cpus(&cpus);
+    o.Begin(&begin);
+    o.Skip(&skip);
+    o.DeviceID(&dev);
+    o.Shard(rank, nranks, static_cast<gcb_comm*>(comm));
+    if (write_traj && *write_traj) { std::string w(write_traj); o.TrajName(&w); }
+    std::vector<double> r;
+    Error e = align::RMSDTraj(top, mat(ref, natoms), *traj, std::vector<int>(indexes, indexes + nidx), &o, &r, frames);
+    if (e) return fail(e);
+    memcpy(rmsd, r.data(), sizeof(double) * r.size());
+    return 0;
+}
+
+int gch_lovo(const char* path, const double* ref, int natoms, const char* const* names, const char* const* chains, const int* molids,
+             const char* atom_name, int cpus, double less_than, int minimum_n, const char* write_traj, int dev, int rank, int nranks,
+             void* comm, int* N, int* natoms_out, double* rmsd_out, int* nrmsd, int* frames, int* iterations, char* text,
+             size_t text_cap) {
+    FlatTopology top = topology(natoms, names, chains, molids);
+    std::unique_ptr<align::Options> o(align::DefaultOptions());
+    o->Cpus(&cpus);
+    o->LessThanRMSD(&less_than);
+    o->MinimumN(&minimum_n);
+    o->DeviceID(&dev);
+    o->Shard(rank, nranks, static_cast<gcb_comm*>(comm));
+    if (atom_name && *atom_name) { std::vector<std::string> n{atom_name}; o->AtomNames(&n); }
+    if (write_traj && *write_traj) { std::string w(write_traj); o->TrajName(&w); }
+    align::LOVOReturn r;
+    Error e = align::LOVO(top, mat(ref, natoms), path, &r, o.get());
+    if (e) return fail(e);
+    *N = r.N;
+    *frames = r.FramesRead;
+    *iterations = r.Iterations;
+    *nrmsd = (int)r.RMSD.size();
+    for (int i = 0; i < r.N; i++) natoms_out[i] = r.Natoms[(size_t)i];
+    for (size_t i = 0; i < r.RMSD.size(); i++) rmsd_out[i] = r.RMSD[i];
+    if (text && text_cap) {
+        std::string s = r.PyMOLSel() + "\n" + r.GMX("A") + "\n" + r.String();
+        size_t n = s.size() < text_cap - 1 ? s.size() : text_cap - 1;
+        memcpy(text, s.data(), n);
+        text[n] = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

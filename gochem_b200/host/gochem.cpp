@@ -1,0 +1,983 @@
+// gochem.cpp -- implementation of the host-side mirror declared in gochem.hpp.
+// Everything that touches coordinates numerically goes through the C ABI (include/gochem_b200.h).
+#include "gochem.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <thread>
+
+#include "../../include/gochem_b200.h"
+
+namespace gochem {
+
+std::string Error::String() const {
+    std::string s = msg;
+    for (const auto& d : deco) s += " <- " + d;
+    return s;
+}
+
+Error errDecorate(Error e, const std::string& who) {
+    e.Decorate(who);
+    return e;
+}
+
+static Error deviceError(int rc, const std::string& who) {
+    char buf[1024];
+    gcb_last_error(buf, sizeof buf);
+    return Error(std::string(buf), {who}, rc);
+}
+
+// ------------------------------------------------------------------ v3.Matrix
+namespace v3 {
+
+Matrix Matrix::Zeros(int vecs) {
+    Matrix m;
+    m.d_.assign(3 * (size_t)(vecs > 0 ? vecs : 0), 0.0);
+    return m;
+}
+
+Error Matrix::NewMatrix(const std::vector<double>& data, Matrix* out) {
+    if (data.size() % 3 != 0) {
+        char b[160];
+        snprintf(b, sizeof b, "NewMatrix: Input slice lenght %zu not divisible by %d: %zu", data.size() / 3, 3, (data.size() / 3) % 3);
+        return Error(b);
+    }
+    out->d_ = data;
+    return Error();
+}
+
+double Matrix::At(int i, int j) const {
+    if (i < 0 || i >= NVecs() || j < 0 || j > 2) throw PanicMsg("goChem/v3: Index out of range");
+    return d_[3 * (size_t)i + j];
+}
+
+void Matrix::Set(int i, int j, double v) {
+    if (i < 0 || i >= NVecs() || j < 0 || j > 2) throw PanicMsg("goChem/v3: Index out of range");
+    d_[3 * (size_t)i + j] = v;
+}
+
+void Matrix::Copy(const Matrix& A) {
+    const size_t n = std::min(d_.size(), A.d_.size());
+    std::copy(A.d_.begin(), A.d_.begin() + (long)n, d_.begin());
+}
+
+void Matrix::SomeVecs(const Matrix& A, const std::vector<int>& clist) {
+    if (NVecs() != (int)clist.size() || A.NVecs() < (int)clist.size()) throw PanicMsg("goChem/v3: Wrong shape");
+    for (size_t k = 0; k < clist.size(); k++)
+        for (int j = 0; j < 3; j++) Set((int)k, j, A.At(clist[k], j));
+}
+
+void Matrix::SetVecs(const Matrix& A, const std::vector<int>& clist) {
+    if (NVecs() < (int)clist.size() || A.NVecs() < (int)clist.size()) throw PanicMsg("goChem/v3: Wrong shape");
+    for (size_t k = 0; k < clist.size(); k++)
+        for (int j = 0; j < 3; j++) Set(clist[k], j, A.At((int)k, j));
+}
+
+void Matrix::AddVec(const Matrix& A, const Matrix& vec) {
+    if (vec.NVecs() != 1 || A.NVecs() != NVecs()) throw PanicMsg("goChem/v3: Wrong shape");
+    for (int i = 0; i < NVecs(); i++)
+        for (int j = 0; j < 3; j++) d_[3 * (size_t)i + j] = A.d_[3 * (size_t)i + j] + vec.d_[(size_t)j];
+}
+
+void Matrix::SubVec(const Matrix& A, const Matrix& vec) {
+    if (vec.NVecs() != 1 || A.NVecs() != NVecs()) throw PanicMsg("goChem/v3: Wrong shape");
+    for (int i = 0; i < NVecs(); i++)
+        for (int j = 0; j < 3; j++) d_[3 * (size_t)i + j] = A.d_[3 * (size_t)i + j] - vec.d_[(size_t)j];
+}
+
+void Matrix::Mul(const Matrix& A, const Matrix& B) {
+    if (B.NVecs() != 3 || A.NVecs() != NVecs()) throw PanicMsg("goChem/v3: Wrong shape");
+    std::vector<double> r(d_.size());
+    for (int i = 0; i < A.NVecs(); i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+            for (int l = 0; l < 3; l++) s += A.d_[3 * (size_t)i + l] * B.d_[3 * (size_t)l + j];
+            r[3 * (size_t)i + j] = s;
+        }
+    d_.swap(r);
+}
+
+void Matrix::Scale(double v, const Matrix& A) {
+    if (A.NVecs() != NVecs()) throw PanicMsg("goChem/v3: Wrong shape");
+    for (size_t i = 0; i < d_.size(); i++) d_[i] = v * A.d_[i];
+}
+
+double Matrix::Norm(double) const {
+    double scale = 0.0, ssq = 1.0;  // Dlange('F'): scaled sum of squares
+    for (double v : d_) {
+        if (v == 0.0) continue;
+        const double a = std::fabs(v);
+        if (scale < a) { ssq = 1.0 + ssq * (scale / a) * (scale / a); scale = a; }
+        else ssq += (a / scale) * (a / scale);
+    }
+    return scale * std::sqrt(ssq);
+}
+
+Matrix Matrix::TrRet() const {
+    if (NVecs() != 3) throw PanicMsg("goChem/v3: Only 3x3 matrices are allowed for this function");
+    Matrix t = Zeros(3);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t.d_[3 * (size_t)j + i] = d_[3 * (size_t)i + j];
+    return t;
+}
+
+}  // namespace v3
+
+// ------------------------------------------------------------------ chem: single-structure calls
+namespace chem {
+
+namespace {
+std::mutex g_mu;
+int g_dev = 0;
+gcb_traj* g_one = nullptr;  // cached one-frame trajectory for single-structure calls
+int g_one_natoms = 0;
+
+// one-frame device trajectory holding `test`
+Error stage_one(const v3::Matrix& test, gcb_traj** t) {
+    const int n = test.NVecs();
+    if (n <= 0) return Error("goChem: Ill-formed matrices", {"stage_one"}, GCB_ERR_SHAPE);
+    if (!g_one || g_one_natoms != n) {
+        if (g_one) gcb_traj_destroy(g_one);
+        g_one = nullptr;
+        int rc = gcb_traj_create(g_dev, n, 1, &g_one);
+        if (rc) return deviceError(rc, "gcb_traj_create");
+        g_one_natoms = n;
+    }
+    int rc = gcb_traj_upload(g_one, 0, test.data(), 1, GCB_F64_AOS, 1.0);
+    if (rc) return deviceError(rc, "gcb_traj_upload");
+    *t = g_one;
+    return Error();
+}
+
+// The three forms of Go's variadic index argument (handy.go:178-201, geometric.go:261-283) as C-ABI lists.
+struct Lists {
+    const int* it = nullptr;
+    const int* ir = nullptr;
+    int n = 0;
+    std::vector<int> iota;
+};
+
+Error dispatch(const v3::Matrix& test, const v3::Matrix& templa, const IndexLists& indexes, const char* fn, const char* shape_msg,
+               Lists* L) {
+    if (indexes.empty() || indexes[0].empty()) {
+        if (test.NVecs() != templa.NVecs()) return Error(shape_msg, {}, GCB_ERR_SHAPE);
+        return Error();
+    }
+    if (indexes.size() == 1) {
+        const int len = (int)indexes[0].size();
+        if (test.NVecs() > len) {
+            // ctest = test[indexes[0]], ctempla = templa (whole): templa rows pair with the list positions
+            if (templa.NVecs() != len) return Error(shape_msg, {}, GCB_ERR_SHAPE);
+            L->iota.resize((size_t)len);
+            for (int k = 0; k < len; k++) L->iota[(size_t)k] = k;
+            L->it = indexes[0].data();
+            L->ir = L->iota.data();
+            L->n = len;
+            return Error();
+        }
+        if (templa.NVecs() > len)
+            return Error(std::string(fn) + ": the reference dereferences a nil matrix for a single index list that applies to templa "
+                                           "(handy.go:186-188, geometric.go:269-271); give both lists",
+                         {}, GCB_ERR_INDEXES);
+        return Error(std::string(fn) + ": Indexes don't match molecules", {}, GCB_ERR_INDEXES);
+    }
+    if (indexes[0].size() != indexes[1].size()) return Error(shape_msg, {}, GCB_ERR_SHAPE);
+    L->it = indexes[0].data();
+    L->ir = indexes[1].data();
+    L->n = (int)indexes[0].size();
+    return Error();
+}
+}  // namespace
+
+Error SetDevice(int dev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_one) { gcb_traj_destroy(g_one); g_one = nullptr; g_one_natoms = 0; }
+    g_dev = dev;
+    return Error();
+}
+int Device() { return g_dev; }
+
+Error newLastFrameError(const std::string& file, const std::string& who) {
+    Error e("EOF", {who});
+    e.msg = "EOF" + (file.empty() ? std::string() : " (" + file + ")");
+    e.last_frame = true;
+    e.critical = false;
+    e.code = GCB_EOF;
+    return e;
+}
+
+Error RotatorTranslatorToSuper(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix* transformed, v3::Matrix* rotation,
+                               v3::Matrix* trans1, v3::Matrix* trans2) {
+    if (test.NVecs() != templa.NVecs() || test.NVecs() == 0)
+        return Error("goChem: Ill-formed matrices", {"RotatorTranslatorToSuper"}, GCB_ERR_SHAPE);  // geometric.go:130-132
+    std::lock_guard<std::mutex> lk(g_mu);
+    gcb_traj* t = nullptr;
+    if (Error e = stage_one(test, &t)) return errDecorate(e, "RotatorTranslatorToSuper");
+    double rm, rot[9], t1[3], t2[3];
+    int rc = gcb_super_rmsd(t, 0, 1, templa.data(), templa.NVecs(), nullptr, nullptr, 0, transformed ? 1 : 0, &rm, rot, t1, t2);
+    if (rc) return deviceError(rc, "RotatorTranslatorToSuper");
+    if (transformed) {
+        *transformed = v3::Matrix::Zeros(test.NVecs());
+        rc = gcb_traj_download(t, 0, 1, transformed->data());
+        if (rc) return deviceError(rc, "RotatorTranslatorToSuper");
+    }
+    if (rotation) { *rotation = v3::Matrix::Zeros(3); std::copy(rot, rot + 9, rotation->data()); }
+    if (trans1) { *trans1 = v3::Matrix::Zeros(1); std::copy(t1, t1 + 3, trans1->data()); }
+    if (trans2) { *trans2 = v3::Matrix::Zeros(1); std::copy(t2, t2 + 3, trans2->data()); }
+    return Error();
+}
+
+Error Super(v3::Matrix& test, const v3::Matrix& templa, const IndexLists& indexes) {
+    Lists L;
+    if (Error e = dispatch(test, templa, indexes, "chem.Super", "chem.Super: Ill formed coordinates for Superposition", &L)) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    gcb_traj* t = nullptr;
+    if (Error e = stage_one(test, &t)) return errDecorate(e, "Super");
+    int rc = gcb_super_rmsd(t, 0, 1, templa.data(), templa.NVecs(), L.it, L.ir, L.n, 1, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return errDecorate(deviceError(rc, "RotatorTranslatorToSuper"), "Super");
+    rc = gcb_traj_download(t, 0, 1, test.data());  // test is modified in place (handy.go:207-213)
+    if (rc) return deviceError(rc, "Super");
+    return Error();
+}
+
+Error MemRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix& tmp, double* out, const IndexLists& indexes) {
+    *out = -1.0;  // geometric.go:273, 282
+    Lists L;
+    if (Error e = dispatch(test, templa, indexes, "chem.memRMSD", "chem.memRMSD: Ill formed matrices for memRMSD calculation", &L)) return e;
+    const int n = L.n ? L.n : test.NVecs();
+    if (tmp.NVecs() != n) return Error("chem.memRMSD: Ill formed matrices for memRMSD calculation", {}, GCB_ERR_SHAPE);
+    std::lock_guard<std::mutex> lk(g_mu);
+    gcb_traj* t = nullptr;
+    if (Error e = stage_one(test, &t)) return errDecorate(e, "MemRMSD");
+    double r = -1.0;
+    int rc = gcb_rmsd(t, 0, 1, templa.data(), templa.NVecs(), L.it, L.ir, L.n, &r);
+    if (rc) return deviceError(rc, "MemRMSD");
+    *out = r;
+    return Error();
+}
+
+Error RMSD(const v3::Matrix& test, const v3::Matrix& templa, double* out, const IndexLists& indexes) {
+    const int Lr = (indexes.empty() || indexes[0].empty()) ? test.NVecs() : (int)indexes[0].size();  // geometric.go:233-239
+    v3::Matrix tmp = v3::Matrix::Zeros(Lr);
+    return MemRMSD(test, templa, tmp, out, indexes);
+}
+
+Error MemPerAtomRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix* /*ctest*/, v3::Matrix* /*ctempla*/, v3::Matrix& tmp,
+                     std::vector<double>* out, const IndexLists& indexes) {
+    Lists L;
+    if (Error e = dispatch(test, templa, indexes, "chem.memMSD", "chem.memMSD: Ill formed matrices for memMSD calculation", &L)) return e;
+    const int n = L.n ? L.n : test.NVecs();
+    if (tmp.NVecs() != n) return Error("chem.memMSD: Ill formed matrices for memMSD calculation", {}, GCB_ERR_SHAPE);
+    std::lock_guard<std::mutex> lk(g_mu);
+    gcb_traj* t = nullptr;
+    if (Error e = stage_one(test, &t)) return errDecorate(e, "MemPerAtomRMSD");
+    out->assign((size_t)n, 0.0);
+    int rc = gcb_peratom_dist(t, 0, templa.data(), templa.NVecs(), L.it, L.ir, L.n, out->data());
+    if (rc) return deviceError(rc, "MemPerAtomRMSD");
+    return Error();
+}
+
+// ------------------------------------------------------------------ in-memory trajectory
+Error MemTraj::Next(v3::Matrix* V, std::vector<double>*) {
+    if (current_ >= Coords.size()) return newLastFrameError("", "Next");  // chem.go:706-708
+    current_++;
+    if (!V) return Error();
+    V->Copy(Coords[current_ - 1]);
+    return Error();
+}
+
+Error MemTraj::NextConc(std::vector<v3::Matrix*>& frames) {
+    bool used = false;
+    for (auto& slot : frames) {
+        if (slot == nullptr) {  // chem.go:733-737: discarded slots advance without an EOF check
+            current_++;
+            continue;
+        }
+        if (current_ >= Coords.size()) {
+            (void)used;  // chem.go:738-745: EOF either way, with or without the partial channel list
+            return newLastFrameError("", "NextConc");
+        }
+        used = true;
+        slot = &Coords[current_];  // the stored frame itself is handed out (chem.go:749-751)
+        current_++;
+    }
+    return Error();
+}
+
+}  // namespace chem
+
+// ------------------------------------------------------------------ DCD
+namespace dcd {
+
+static uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+
+static Error dcdError(const std::string& msg, const std::string& file, std::vector<std::string> deco) {
+    Error e(msg + (file.empty() ? "" : " (" + file + ")"), std::move(deco));
+    return e;
+}
+
+Error DCDObj::readI32(int32_t* v) {
+    uint32_t u;
+    if (fread(&u, 4, 1, f_) != 1) return dcdError("EOF", filename_, {"binary.Read"});
+    if (swap_) u = bswap32(u);
+    memcpy(v, &u, 4);
+    return Error();
+}
+
+Error DCDObj::New(const std::string& filename, std::unique_ptr<DCDObj>* out) {
+    std::unique_ptr<DCDObj> d(new DCDObj());
+    if (Error e = d->initRead(filename)) return errDecorate(e, "New");
+    d->fields_.assign(3 * (size_t)d->natoms_, 0.0f);
+    *out = std::move(d);
+    return Error();
+}
+
+DCDObj::~DCDObj() { Close(); }
+
+void DCDObj::Close() {
+    if (f_) fclose(f_);
+    f_ = nullptr;
+    readable_ = false;
+}
+
+Error DCDObj::initRead(const std::string& name) {  // dcd.go:156-281
+    filename_ = name;
+    f_ = fopen(name.c_str(), "rb");
+    if (!f_) return dcdError("open " + name + ": no such file or directory", name, {"os.Open", "initRead"});
+    int32_t check = 0;
+    if (Error e = readI32(&check)) return errDecorate(e, "initRead");
+    if (check != 84) {
+        swap_ = true;  // other endianness (dcd.go:172-174)
+        uint32_t u;
+        memcpy(&u, &check, 4);
+        u = bswap32(u);
+        memcpy(&check, &u, 4);
+        if (check != 84) return dcdError("Wrong format: first record is not 84 bytes", name, {"initRead"});
+    }
+    char magic[4];
+    if (fread(magic, 1, 4, f_) != 4) return dcdError("EOF", name, {"binary.Read", "initRead"});
+    if (memcmp(magic, "CORD", 4) != 0) return dcdError("Wrong format: Wrong magic number", name, {"initRead"});
+    unsigned char buf[80];
+    if (fread(buf, 1, 80, f_) != 80) return dcdError("EOF", name, {"binary.Read", "initRead"});
+    auto i32at = [&](int off) {
+        uint32_t u;
+        memcpy(&u, buf + off, 4);
+        if (swap_) u = bswap32(u);
+        int32_t v;
+        memcpy(&v, &u, 4);
+        return v;
+    };
+    if (i32at(76) != 0) {
+        charmm_ = true;
+        if (i32at(40) != 0) extrablock_ = true;
+        if (i32at(40) == 1) fourdim_ = true;  // the reference reads offset 40 twice (dcd.go:196-201)
+    } else {
+        return dcdError("Wrong format: X-plor DCD not supported", name, {"initRead"});
+    }
+    fixed_ = i32at(32);
+    if (Error e = readI32(&check)) return errDecorate(e, "initRead");
+    if (check != 84) return dcdError("Wrong format", name, {"initRead"});
+    int32_t input_int = 0, ntitle = 0;
+    if (Error e = readI32(&input_int)) return errDecorate(e, "initRead");
+    if (Error e = readI32(&ntitle)) return errDecorate(e, "initRead");
+    if (ntitle < 0 || ntitle > 1000000) return dcdError("Wrong format", name, {"initRead"});
+    std::vector<char> title(80 * (size_t)ntitle);
+    if (!title.empty() && fread(title.data(), 1, title.size(), f_) != title.size()) return dcdError("EOF", name, {"binary.Read", "initRead"});
+    if (Error e = readI32(&input_int)) return errDecorate(e, "initRead");
+    if (Error e = readI32(&check)) return errDecorate(e, "initRead");
+    if (check != 4) return dcdError("Wrong format", name, {"initRead"});
+    if (Error e = readI32(&natoms_)) return errDecorate(e, "initRead");
+    if (Error e = readI32(&check)) return errDecorate(e, "initRead");
+    if (check != 4) return dcdError("Wrong format", name, {"initRead"});
+    if (natoms_ <= 0) return dcdError("Wrong format", name, {"initRead"});
+    if (fixed_ == 0) {
+        readable_ = true;
+        return Error();
+    }
+    return dcdError("Fixed atoms not supported", name, {"initRead"});
+}
+
+Error DCDObj::readFloat32Block(int32_t blocksize, float* block, int n) {  // dcd.go:436-452
+    if (blocksize != n * 4) {
+        // the reference would read len(block) floats and then fail the trailer check
+        return dcdError("Wrong format", filename_, {"readFloat32Block"});
+    }
+    if (fread(block, 4, (size_t)n, f_) != (size_t)n) return dcdError("unexpected EOF", filename_, {"binary.Read", "readFloat32Block"});
+    if (swap_) {
+        for (int i = 0; i < n; i++) {
+            uint32_t u;
+            memcpy(&u, block + i, 4);
+            u = bswap32(u);
+            memcpy(block + i, &u, 4);
+        }
+    }
+    int32_t check;
+    if (Error e = readI32(&check)) return errDecorate(e, "readFloat32Block");
+    if (check != blocksize) return dcdError("Wrong format", filename_, {"readFloat32Block"});
+    return Error();
+}
+
+Error DCDObj::nextRaw(float* x, float* y, float* z) {  // dcd.go:349-434
+    if (!readable_) return dcdError("Traj object uninitialized to read", filename_, {"nextRaw"});
+    if (readLast_) {
+        Close();
+        return chem::newLastFrameError(filename_, "nextRaw");
+    }
+    int32_t blocksize = 0;
+    if (extrablock_) {
+        if (readI32(&blocksize)) { Close(); return chem::newLastFrameError(filename_, "nextRaw"); }
+        if (blocksize < natoms_ * 3) {
+            // unit cell: 6 doubles in CHARMM files; read and skip whatever the record holds
+            std::vector<char> cell((size_t)(blocksize > 0 ? blocksize : 0));
+            if (!cell.empty() && fread(cell.data(), 1, cell.size(), f_) != cell.size()) return dcdError("unexpected EOF", filename_, {"nextRaw"});
+            int32_t check;
+            if (Error e = readI32(&check)) return errDecorate(e, "nextRaw");
+            if (check != blocksize) return dcdError("Wrong format", filename_, {"nextRaw"});
+            blocksize = 0;
+        }
+    }
+    if (blocksize == 0) {
+        if (readI32(&blocksize)) { Close(); return chem::newLastFrameError(filename_, "nextRaw"); }
+    }
+    if (Error e = readFloat32Block(blocksize, x, natoms_)) return errDecorate(e, "nextRaw");
+    if (Error e = readI32(&blocksize)) return errDecorate(e, "nextRaw");
+    if (Error e = readFloat32Block(blocksize, y, natoms_)) return errDecorate(e, "nextRaw");
+    if (Error e = readI32(&blocksize)) return errDecorate(e, "nextRaw");
+    if (Error e = readFloat32Block(blocksize, z, natoms_)) return errDecorate(e, "nextRaw");
+    if (charmm_ && fourdim_) {
+        if (readI32(&blocksize)) {
+            readLast_ = true;
+        } else {
+            std::vector<char> skip((size_t)(blocksize > 0 ? blocksize : 0));
+            if (!skip.empty() && fread(skip.data(), 1, skip.size(), f_) != skip.size()) return dcdError("unexpected EOF", filename_, {"nextRaw"});
+            int32_t check;
+            if (Error e = readI32(&check)) return errDecorate(e, "nextRaw");
+            if (check != blocksize) return dcdError("Security check failed", filename_, {"readByteBlock"});
+        }
+    }
+    return Error();
+}
+
+Error DCDObj::Next(v3::Matrix* keep, std::vector<double>* box) {
+    float* b = fields_.data();
+    if (Error e = nextRaw(b, b + natoms_, b + 2 * (size_t)natoms_)) return errDecorate(e, "Next");
+    if (box) box->assign(box_, box_ + 6);
+    if (!keep) return Error();
+    if (keep->NVecs() < natoms_) throw v3::PanicMsg("Not enough space in matrix");
+    for (int i = 0; i < natoms_; i++) {  // widened per element (dcd.go:302-307)
+        keep->Set(i, 0, (double)b[i]);
+        keep->Set(i, 1, (double)b[natoms_ + i]);
+        keep->Set(i, 2, (double)b[2 * (size_t)natoms_ + i]);
+    }
+    return Error();
+}
+
+Error DCDObj::NextConc(std::vector<v3::Matrix*>& frames) {  // dcd.go:513-546
+    if (!Readable()) return dcdError("Traj object uninitialized to read", filename_, {"NextConc"});
+    for (auto* slot : frames) {
+        float* b = fields_.data();
+        if (Error e = nextRaw(b, b + natoms_, b + 2 * (size_t)natoms_)) return errDecorate(e, "NextConc");
+        if (!slot) continue;
+        for (int i = 0; i < natoms_; i++) {
+            slot->Set(i, 0, (double)b[i]);
+            slot->Set(i, 1, (double)b[natoms_ + i]);
+            slot->Set(i, 2, (double)b[2 * (size_t)natoms_ + i]);
+        }
+    }
+    return Error();
+}
+
+Error DCDObj::NextRaw(float* dst, int* layout, double* scale) {
+    *layout = GCB_F32_SOA;
+    *scale = 1.0;
+    if (dst) return nextRaw(dst, dst + natoms_, dst + 2 * (size_t)natoms_);
+    float* b = fields_.data();
+    return nextRaw(b, b + natoms_, b + 2 * (size_t)natoms_);
+}
+
+Error DCDWObj::NewWriter(const std::string& filename, int natoms, std::unique_ptr<DCDWObj>* out) {  // dcd_write.go:102-205
+    std::unique_ptr<DCDWObj> w(new DCDWObj());
+    w->filename_ = filename;
+    w->natoms_ = natoms;
+    w->f_ = fopen(filename.c_str(), "wb+");
+    if (!w->f_) return dcdError("open " + filename + ": cannot create", filename, {"os.Open", "initWrite", "NewWriter"});
+    auto wi = [&](int32_t v) { fwrite(&v, 4, 1, w->f_); };
+    wi(84);
+    fwrite("CORD", 1, 4, w->f_);
+    wi(0); wi(0); wi(1);
+    for (int i = 0; i < 6; i++) wi(0);
+    float one = 1.0f;
+    fwrite(&one, 4, 1, w->f_);
+    wi(0);
+    for (int i = 0; i < 8; i++) wi(0);
+    wi(24);
+    wi(84);
+    wi(244);
+    wi(2);
+    char title[160];
+    memset(title, 'l', sizeof title);
+    title[159] = 0;
+    fwrite(title, 1, sizeof title, w->f_);
+    wi(244);
+    wi(4);
+    if (natoms == 0) return dcdError("Trajectory not initialized correctly, the number of atoms is set to zero!", filename, {"initWrite"});
+    wi(natoms);
+    wi(4);
+    w->writable_ = true;
+    w->fields_.assign(3 * (size_t)natoms, 0.0f);
+    *out = std::move(w);
+    return Error();
+}
+
+DCDWObj::~DCDWObj() { Close(); }
+
+void DCDWObj::Close() {
+    if (f_) fclose(f_);
+    f_ = nullptr;
+    writable_ = false;
+}
+
+Error DCDWObj::WNextRaw(const double* aos, int natoms) {  // dcd_write.go:212-330
+    if (!writable_) return dcdError("Traj object uninitialized to read", filename_, {"WNext"});
+    if (!aos) return dcdError("got nil coordinates", filename_, {"WNext"});
+    if (natoms != natoms_) return dcdError("Coordinates don't match the trajectory size", filename_, {"WNext"});
+    float* b = fields_.data();
+    for (int k = 0; k < natoms_; k++) {
+        b[k] = (float)aos[3 * (size_t)k];
+        b[natoms_ + k] = (float)aos[3 * (size_t)k + 1];
+        b[2 * (size_t)natoms_ + k] = (float)aos[3 * (size_t)k + 2];
+    }
+    const int32_t bs = natoms_ * 4;
+    for (int c = 0; c < 3; c++) {
+        fwrite(&bs, 4, 1, f_);
+        fwrite(b + (size_t)c * natoms_, 4, (size_t)natoms_, f_);
+        fwrite(&bs, 4, 1, f_);
+    }
+    frames_++;
+    // updateFrames: rewrite the frame counter at the top of the file (dcd_write.go:300-330)
+    const long here = ftell(f_);
+    fseek(f_, 0, SEEK_SET);
+    int32_t v = 84;
+    fwrite(&v, 4, 1, f_);
+    fwrite("CORD", 1, 4, f_);
+    fwrite(&frames_, 4, 1, f_);
+    fseek(f_, here, SEEK_SET);
+    return Error();
+}
+
+Error DCDWObj::WNext(const v3::Matrix& towrite) { return WNextRaw(towrite.data(), towrite.NVecs()); }
+
+}  // namespace dcd
+
+// ------------------------------------------------------------------ align
+namespace align {
+
+Options* DefaultOptions() {
+    Options* r = new Options();
+    unsigned hc = std::thread::hardware_concurrency();
+    r->cpus_ = hc ? (int)hc : 1;
+    r->atomNames_ = {"CA"};
+    r->lessThanRMSD_ = 1.0;
+    r->minimumN_ = 10;
+    return r;
+}
+
+Options* DefaultCGOptions() {
+    Options* r = DefaultOptions();
+    r->atomNames_ = {"BB"};
+    return r;
+}
+
+std::string MolIDandChain::String() const {
+    char b[64];
+    snprintf(b, sizeof b, "molid:%04d-chain:%s", molid, chain.c_str());
+    return b;
+}
+
+static std::string fmtFloat(double v) {  // Go's %v for float64: shortest representation that round-trips
+    char b[40];
+    for (int prec = 1; prec <= 17; prec++) {
+        snprintf(b, sizeof b, "%.*g", prec, v);
+        if (strtod(b, nullptr) == v) break;
+    }
+    return b;
+}
+
+std::string LOVOReturn::String() const {  // lovo.go:79-86
+    std::ostringstream s;
+    s << "N: " << N << ",  Frames read: " << FramesRead << ", Iterations needed: " << Iterations << ", RMSD: [";
+    for (size_t i = 0; i < RMSD.size(); i++) s << (i ? " " : "") << fmtFloat(RMSD[i]);
+    s << "], Natoms: [";
+    for (size_t i = 0; i < Natoms.size(); i++) s << (i ? " " : "") << Natoms[i];
+    s << "], Nmols:";
+    for (const auto& m : Nmols) s << " " << m.String();
+    return s.str();
+}
+
+std::string LOVOReturn::PyMOLSel() const {  // lovo.go:102-116
+    std::string sel = "select rigid,";
+    char b[96];
+    for (size_t i = 0; i < Nmols.size(); i++) {
+        if (Nmols[i].chain.empty()) snprintf(b, sizeof b, " (resi %d) ", Nmols[i].molid);
+        else snprintf(b, sizeof b, " (resi %d and chain %s) ", Nmols[i].molid, Nmols[i].chain.c_str());
+        sel += b;
+        if (i + 1 < Nmols.size()) sel += "or";
+    }
+    return sel;
+}
+
+std::string LOVOReturn::GMX(const std::string& chain) const {  // lovo.go:128-150
+    bool first = true;
+    std::string ret;
+    char b[64];
+    for (const auto& v : Nmols) {
+        if (!chain.empty() && chain != v.chain) continue;
+        if (first) {
+            snprintf(b, sizeof b, "r %d ", v.molid);
+            ret = b;
+            first = false;
+            continue;
+        }
+        snprintf(b, sizeof b, " | r %d ", v.molid);
+        ret += b;
+    }
+    if (!chain.empty()) ret += " & chain " + chain;
+    return ret;
+}
+
+Error mobileLimit(double limit, int tolerance, const std::vector<double>& rmsd, int* nout, double* newlimit) {
+    int n = 0;
+    long guard = 0;
+    while (n < tolerance) {
+        n = 0;
+        for (; n < (int)rmsd.size(); n++) {
+            if (rmsd[(size_t)n] >= limit) {
+                n--;  // off by one on purpose: lovo.go:180-183
+                break;
+            }
+        }
+        limit *= 1.1;
+        if (++guard > 100000 || !std::isfinite(limit))
+            return Error("align.mobileLimit: fewer candidate atoms than MinimumN; the reference would loop forever here (lovo.go:177-186)");
+    }
+    *nout = n;
+    *newlimit = limit;
+    return Error();
+}
+
+bool approxEq(double i, double j, double epsilon) { return std::fabs(i) - std::fabs(j) <= epsilon; }
+
+static bool isInInt(int v, const std::vector<int>& c) { return std::find(c.begin(), c.end(), v) != c.end(); }
+
+bool sameElementsInt(const std::vector<int>& a, const std::vector<int>& b) {
+    if (a.size() != b.size()) return false;
+    for (int v : a)
+        if (!isInInt(v, b)) return false;
+    return true;
+}
+
+int disagreementInt(const std::vector<int>& a, const std::vector<int>& b) {
+    if (a.size() != b.size()) return -1;
+    int d = 0;
+    for (int v : a)
+        if (!isInInt(v, b)) d++;
+    return d;
+}
+
+std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::string>& names, const std::vector<std::string>& chains) {
+    std::vector<int> ret;
+    for (int i = 0; i < mol.Len(); i++) {
+        const chem::Atom& a = mol.Atom(i);
+        if (std::find(names.begin(), names.end(), a.Name) == names.end()) continue;
+        if (chains.empty() || std::find(chains.begin(), chains.end(), a.Chain) != chains.end()) ret.push_back(i);
+    }
+    return ret;
+}
+
+std::vector<MolIDandChain> iDs2MolIDandChains(const chem::Atomer& mol, const std::vector<int>& indexes) {
+    std::vector<MolIDandChain> ret;
+    for (int v : indexes) {
+        const chem::Atom& at = mol.Atom(v);
+        bool seen = false;
+        for (const auto& m : ret) seen = seen || (m.molid == at.MolID && m.chain == at.Chain);
+        if (!seen) ret.push_back(MolIDandChain{at.MolID, at.Chain});
+    }
+    return ret;
+}
+
+std::vector<long> selectedFrames(long F, int cpus, int begin_opt, int skip_opt) {
+    std::vector<long> sel;
+    if (cpus <= 0) return sel;
+    const long begin = begin_opt / cpus, skip = skip_opt / cpus;  // lovo.go:306-307
+    long cursor = 0;
+    for (long read = 0;; read++) {
+        if (read < begin || read % (skip + 1) != 0) {  // one chunk read and discarded, then NO continue (:316-322)
+            if (cursor + cpus > F) break;
+            cursor += cpus;
+        }
+        if (cursor + cpus > F) break;  // a chunk that cannot be filled is dropped (:323-326)
+        for (int s = 0; s < cpus; s++) sel.push_back(cursor + s);
+        cursor += cpus;
+    }
+    return sel;
+}
+
+void shardRange(long nsel, int rank, int nranks, long* first, long* count) {
+    if (nranks < 1) nranks = 1;
+    const long base = nsel / nranks, rem = nsel % nranks;
+    *first = rank * base + std::min<long>(rank, rem);
+    *count = base + (rank < rem ? 1 : 0);
+}
+
+LovoState::LovoState(std::vector<int> fullindexes, double lessThanRMSD, int minimumN)
+    : full_(std::move(fullindexes)), lessThan_(lessThanRMSD), minimumN_(minimumN) {
+    indexesold_ = full_;  // lovo.go:212-213
+    n_ = (int)full_.size();
+    fit_ = indexesold_;
+}
+
+bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
+    itercount_++;
+    // rmsdFilter (lovo.go:519-528) walks rmsd in atom order keeping the candidates; newRMSD pairs them with
+    // fullindexes position by position (:367-384)
+    std::vector<double> filtered;
+    filtered.reserve(full_.size());
+    for (int i = 0; i < (int)rmsd.size(); i++)
+        if (isInInt(i, full_)) filtered.push_back(rmsd[(size_t)i]);
+    if (filtered.size() != full_.size()) {
+        *err = Error("Inconsistent data, if given, the number of initial RMSD values must match the number of residues");  // :373-375 panic
+        return true;
+    }
+    std::vector<int> order(full_.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return filtered[(size_t)a] < filtered[(size_t)b]; });  // sort.Stable, :429-432
+    ids_.resize(order.size());
+    vals_.resize(order.size());
+    for (size_t k = 0; k < order.size(); k++) { ids_[k] = full_[(size_t)order[k]]; vals_[k] = filtered[(size_t)order[k]]; }
+    double newlim = 0.0;
+    if (lessThan_ > 0) {  // :238-240
+        if (Error e = mobileLimit(lessThan_, minimumN_, vals_, &n_, &newlim)) { *err = e; return true; }
+    }
+    if (n_ < 0 || n_ > (int)ids_.size()) { *err = Error("align.LOVO: slice bounds out of range (n outside the candidate list)"); return true; }
+    std::vector<int> a(ids_.begin(), ids_.begin() + n_), b(indexesold_.begin(), indexesold_.begin() + n_);
+    if (sameElementsInt(a, b) && (newlim == lessThan_ || approxEq(newlim, prevlim_, 0.01))) {  // :246-248
+        fit_.assign(indexesold_.begin(), indexesold_.begin() + n_);
+        return true;
+    }
+    prevlim_ = newlim;
+    disagreement_ = disagreementInt(a, b);
+    indexesold_ = ids_;
+    fit_.assign(indexesold_.begin(), indexesold_.begin() + n_);
+    return false;
+}
+
+void LovoState::Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const {
+    // RMSD.SortBy("molid") (:254): stable by candidate atom index
+    std::vector<int> order(ids_.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ids_[(size_t)a] < ids_[(size_t)b]; });
+    out->RMSD.resize(order.size());
+    for (size_t k = 0; k < order.size(); k++) out->RMSD[k] = vals_[(size_t)order[k]];
+    out->N = n_;
+    out->Natoms.assign(indexesold_.begin(), indexesold_.begin() + n_);  // previous order, new n (:255)
+    out->Nmols = iDs2MolIDandChains(mol, out->Natoms);
+    out->FramesRead = framesRead;
+    out->Iterations = itercount_;
+}
+
+// ---- device-resident trajectory ----
+DeviceTrajectory::~DeviceTrajectory() {
+    if (t_) gcb_traj_destroy(t_);
+}
+
+Error DeviceTrajectory::Load(chem::ConcTraj& traj, int natoms, const Options& o, std::unique_ptr<DeviceTrajectory>* out) {
+    if (!traj.Readable()) return Error("Traj object uninitialized to read", {"RMSDTraj"});
+    if (o.cpus_ <= 0) return Error("align.RMSDTraj: cpus must be positive");
+    if (traj.Len() != natoms) return Error("align.RMSDTraj: trajectory and molecule differ in the number of atoms");
+    const int chunksize = o.cpus_;
+    const long begin = o.begin_ / chunksize, skip = o.skip_ / chunksize;
+    const bool raw = traj.HasRawFeed();
+    const size_t fbytes = (raw ? sizeof(float) : sizeof(double)) * 3 * (size_t)natoms;
+    // Pass 1 over the source: keep the selected frames in host memory (the reader tells us nothing reliable
+    // about its length; the reference discovers EOF the same way).
+    std::vector<char> host;
+    std::vector<v3::Matrix> chunk((size_t)chunksize);
+    for (auto& m : chunk) m = v3::Matrix::Zeros(natoms);
+    std::vector<char> scratch(fbytes);
+    long nsel = 0;
+    int layout = GCB_F64_AOS;
+    double scale = 1.0;
+    Error err;
+    auto read_chunk = [&](bool keep) -> Error {
+        if (raw) {
+            const size_t base = host.size();
+            if (keep) host.resize(base + fbytes * (size_t)chunksize);
+            for (int s = 0; s < chunksize; s++) {
+                float* dst = keep ? reinterpret_cast<float*>(host.data() + base + fbytes * (size_t)s) : reinterpret_cast<float*>(scratch.data());
+                if (Error e = traj.NextRaw(dst, &layout, &scale)) {
+                    if (keep) host.resize(base);  // partial chunk dropped
+                    return e;
+                }
+            }
+            return Error();
+        }
+        std::vector<v3::Matrix*> slots((size_t)chunksize, nullptr);
+        if (keep) for (int s = 0; s < chunksize; s++) slots[(size_t)s] = &chunk[(size_t)s];
+        if (Error e = traj.NextConc(slots)) return e;
+        if (keep) {
+            const size_t base = host.size();
+            host.resize(base + fbytes * (size_t)chunksize);
+            for (int s = 0; s < chunksize; s++) memcpy(host.data() + base + fbytes * (size_t)s, slots[(size_t)s]->data(), fbytes);
+        }
+        return Error();
+    };
+    for (long read = 0;; read++) {
+        if (read < begin || read % (skip + 1) != 0) {
+            err = read_chunk(false);
+            if (err) break;
+        }
+        err = read_chunk(true);
+        if (err) break;
+        nsel += chunksize;
+    }
+    if (!err.last_frame)  // lovo.go:343-347
+        return Error("Error while reading trajectory, read " + std::to_string(nsel / chunksize) + " sets of frames. Error: " + err.String());
+    std::unique_ptr<DeviceTrajectory> d(new DeviceTrajectory());
+    d->natoms_ = natoms;
+    d->nselected_ = nsel;
+    long first = 0, count = 0;
+    shardRange(nsel, o.rank_, o.nranks_, &first, &count);
+    d->nlocal_ = count;
+    int rc = gcb_traj_create(o.device_, natoms, count > 0 ? count : 1, &d->t_);
+    if (rc) return deviceError(rc, "gcb_traj_create");
+    if (count > 0) {
+        // C-owned pinned double buffer -> async copies (Go memory may not be handed to an async copy)
+        const long per = std::max<long>(1, (long)((32u << 20) / fbytes));
+        void* pin[2] = {nullptr, nullptr};
+        for (int s = 0; s < 2; s++) {
+            rc = gcb_pinned_alloc((size_t)per * fbytes, &pin[s]);
+            if (rc) return deviceError(rc, "gcb_pinned_alloc");
+        }
+        int slot = 0;
+        Error up;
+        for (long done = 0; done < count && !up; done += per, slot ^= 1) {
+            const long n = std::min(per, count - done);
+            rc = gcb_traj_wait(d->t_, slot);
+            if (rc) { up = deviceError(rc, "gcb_traj_wait"); break; }
+            memcpy(pin[slot], host.data() + (size_t)(first + done) * fbytes, (size_t)n * fbytes);
+            rc = gcb_traj_upload_async(d->t_, done, pin[slot], n, raw ? layout : GCB_F64_AOS, raw ? scale : 1.0, slot);
+            if (rc) up = deviceError(rc, "gcb_traj_upload_async");
+        }
+        gcb_traj_wait(d->t_, 0);
+        gcb_traj_wait(d->t_, 1);
+        gcb_pinned_free(pin[0]);
+        gcb_pinned_free(pin[1]);
+        if (up) return up;
+    }
+    gcb_traj_set_nframes(d->t_, count);
+    *out = std::move(d);
+    return Error();
+}
+
+Error DeviceTrajectory::MeanDeviations(const v3::Matrix& ref, const std::vector<int>& indexes, const Options& o, bool write_back,
+                                       std::vector<double>* mean) {
+    if (ref.NVecs() != natoms_) return Error("chem.Super: Ill formed coordinates for Superposition", {"concproc"});
+    mean->assign((size_t)natoms_, 0.0);
+    int rc = gcb_peratom_dev_sum(t_, 0, nlocal_, ref.data(), indexes.empty() ? nullptr : indexes.data(), (int)indexes.size(),
+                                 write_back ? 1 : 0, o.comm_, mean->data());
+    if (rc) return deviceError(rc, "RMSDTraj");
+    if (!o.comm_ && o.allreduce_) {
+        if (Error e = o.allreduce_(mean->data(), (long)natoms_)) return e;
+    }
+    const double total = (double)nselected_;  // chunksread * chunksize (lovo.go:348)
+    for (auto& v : *mean) v = v / total;
+    return Error();
+}
+
+Error DeviceTrajectory::WriteDCD(const std::string& name) {
+    std::unique_ptr<dcd::DCDWObj> w;
+    if (Error e = dcd::DCDWObj::NewWriter(name, natoms_, &w)) {
+        fprintf(stderr, "Couldn't open %s for writing. Will not write aligned trajectory\n", name.c_str());  // lovo.go:299-301
+        return Error();
+    }
+    const long per = std::max<long>(1, (64L << 20) / (24L * natoms_));
+    std::vector<double> buf((size_t)per * 3 * (size_t)natoms_);
+    for (long done = 0; done < nlocal_; done += per) {
+        const long n = std::min(per, nlocal_ - done);
+        int rc = gcb_traj_download(t_, done, n, buf.data());
+        if (rc) return deviceError(rc, "WNext");
+        for (long f = 0; f < n; f++)
+            if (Error e = w->WNextRaw(buf.data() + (size_t)f * 3 * (size_t)natoms_, natoms_)) return e;
+    }
+    return Error();
+}
+
+Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
+               std::vector<double>* rmsd, int* frames) {
+    std::unique_ptr<DeviceTrajectory> d;
+    if (Error e = DeviceTrajectory::Load(traj, mol.Len(), *o, &d)) { *frames = -1; return e; }
+    const bool wb = !o->writeTraj_.empty();
+    if (Error e = d->MeanDeviations(ref, indexes, *o, wb, rmsd)) { *frames = -1; return e; }
+    if (wb)
+        if (Error e = d->WriteDCD(o->writeTraj_)) return e;
+    *frames = (int)d->SelectedFrames();
+    return Error();
+}
+
+Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out) {
+    const size_t dot = name.find_last_of('.');
+    std::string ext = dot == std::string::npos ? name : name.substr(dot + 1);
+    std::transform(ext.begin(), ext.end(), ext.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (ext == "dcd") {
+        std::unique_ptr<dcd::DCDObj> d;
+        if (Error e = dcd::DCDObj::New(name, &d)) return e;
+        *out = std::move(d);
+        return Error();
+    }
+    if (ext == "xtc" || ext == "stf" || ext == "pdb")
+        return Error("Trajectory format '" + ext + "' is decoded by a third-party CPU codec that is outside this build (SURVEY.md §2); "
+                     "feed its frames through a chem::ConcTraj and call align::RMSDTraj");
+    return Error("Trajectory fromat not supported. Must have concurrent read support in goChem");  // lovo.go:168-169
+}
+
+Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt) {
+    std::unique_ptr<Options> own;
+    Options* o = opt;
+    if (!o) { own.reset(DefaultOptions()); o = own.get(); }
+    const std::vector<int> fullindexes = res2atoms(mol, o->atomNames_, o->chains_);
+    const std::string printtraj = o->writeTraj_;
+    o->writeTraj_.clear();  // lovo.go:209-211
+    LovoState st(fullindexes, o->lessThanRMSD_, o->minimumN_);
+    std::unique_ptr<DeviceTrajectory> d;
+    auto load = [&]() -> Error {
+        std::unique_ptr<chem::ConcTraj> traj;
+        if (Error e = opentraj(trajname, &traj)) return e;  // :222 (the reference re-opens it on every iteration)
+        Error e = DeviceTrajectory::Load(*traj, mol.Len(), *o, &d);
+        traj->Close();
+        return e;
+    };
+    if (Error e = load()) return e;
+    std::vector<double> rmsd;
+    for (;;) {
+        if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228
+        const bool wb = !o->writeTraj_.empty();
+        if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd)) return e;
+        if (wb) {
+            if (Error e = d->WriteDCD(o->writeTraj_)) return e;
+            if (Error e = load()) return e;  // the pass rewrote the resident frames; later passes start from the file again
+        }
+        Error serr;
+        const bool converged = st.Step(rmsd, &serr);
+        if (serr) return serr;
+        if (converged) break;
+        if (st.Iterations() >= o->maxIter_) return Error("align.LOVO: no convergence after " + std::to_string(st.Iterations()) + " iterations");
+    }
+    st.Finish(mol, (int)d->SelectedFrames(), out);
+    return Error();
+}
+
+}  // namespace align
+}  // namespace gochem

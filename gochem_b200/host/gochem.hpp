@@ -1,0 +1,326 @@
+// gochem.hpp -- host-side mirror of the reference's Go API for the superposition / RMSD / LOVO
+// path, written above the C ABI of include/gochem_b200.h.
+//
+// The reference is Go (rmera/gochem); this image has no Go toolchain, so the host layer a Go
+// maintainer would write with cgo (INTEGRATION.md shows that binding) is written here in C++ with
+// the same names, argument meaning and error behaviour:
+//
+//   v3::Matrix                      /root/reference/v3/gonum.go:54-58, v3/gocoords.go
+//   chem::Super                     handy.go:175-214
+//   chem::RMSD / chem::MemRMSD      geometric.go:232-288
+//   chem::MemPerAtomRMSD            geometric.go:294-321
+//   chem::RotatorTranslatorToSuper  geometric.go:127-208
+//   chem::Traj / chem::ConcTraj     interfaces.go:36-64, LastFrameError :119-123
+//   chem::MemTraj                   chem.go:693-762 (Molecule as an in-memory ConcTraj)
+//   dcd::DCDObj / dcd::DCDWObj      traj/dcd/dcd.go, traj/dcd/dcd_write.go
+//   align::Options, LOVO, RMSDTraj  align/lovo_options.go, align/lovo.go
+//
+// Go's (value, error) returns become an Error return plus output arguments; a default-constructed
+// Error is nil.  All arithmetic on coordinates runs on the GPU through the C ABI; nothing here
+// computes a superposition on the CPU, and without a CUDA device every compute call returns the
+// library's error.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+struct gcb_traj;
+struct gcb_comm;
+
+namespace gochem {
+
+// chem.Error (interfaces.go:103-107): message plus the Decorate() call chain.
+struct Error {
+    bool set = false;
+    std::string msg;
+    std::vector<std::string> deco;
+    bool last_frame = false;  // satisfies chem.LastFrameError (interfaces.go:119-123)
+    bool critical = true;
+    int code = 0;             // C-ABI status when the error came from the device library
+    Error() = default;
+    Error(std::string m, std::vector<std::string> d = {}, int c = 0) : set(true), msg(std::move(m)), deco(std::move(d)), code(c) {}
+    explicit operator bool() const { return set; }
+    std::string String() const;
+    Error& Decorate(const std::string& who) { if (!who.empty()) deco.push_back(who); return *this; }
+};
+Error errDecorate(Error e, const std::string& who);  // chem.go:850-855
+
+namespace v3 {
+
+// N x 3 row-major float64 (v3/gonum.go:54-58).  Methods panic in Go on misuse (v3/gonum.go:513-532);
+// here they throw v3::PanicMsg.
+struct PanicMsg : std::runtime_error { using std::runtime_error::runtime_error; };
+
+class Matrix {
+  public:
+    Matrix() = default;
+    static Matrix Zeros(int vecs);                                         // gocoords.go:43-47
+    static Error NewMatrix(const std::vector<double>& data, Matrix* out);  // gonum.go:79-88
+    int NVecs() const { return (int)(d_.size() / 3); }                     // gocoords.go:116-123
+    int Len() const { return NVecs(); }
+    double At(int i, int j) const;
+    void Set(int i, int j, double v);
+    std::vector<double>& RawSlice() { return d_; }                         // gonum.go:93-95
+    const std::vector<double>& RawSlice() const { return d_; }
+    double* data() { return d_.data(); }
+    const double* data() const { return d_.data(); }
+    void Copy(const Matrix& A);
+    void SomeVecs(const Matrix& A, const std::vector<int>& clist);         // gocoords.go:155-166
+    void SetVecs(const Matrix& A, const std::vector<int>& clist);          // gocoords.go:139-150
+    void AddVec(const Matrix& A, const Matrix& vec);                       // gocoords.go:67-86
+    void SubVec(const Matrix& A, const Matrix& vec);                       // gocoords.go:220-224
+    void Mul(const Matrix& A, const Matrix& B3x3);                         // gonum.go:220-229 (N x 3 times 3 x 3)
+    void Scale(double v, const Matrix& A);
+    double Norm(double) const;                                             // gonum.go:268-275 (Frobenius)
+    Matrix TrRet() const;                                                  // gonum.go:486-502 (3 x 3 only)
+  private:
+    std::vector<double> d_;
+};
+
+}  // namespace v3
+
+namespace chem {
+
+using IndexLists = std::vector<std::vector<int>>;  // Go's variadic indexes ...[]int
+
+// One process-wide device context (device id, cached trajectory handle for single-frame calls).
+Error SetDevice(int dev);
+int Device();
+
+Error RotatorTranslatorToSuper(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix* transformed, v3::Matrix* rotation,
+                               v3::Matrix* trans1, v3::Matrix* trans2);
+Error Super(v3::Matrix& test, const v3::Matrix& templa, const IndexLists& indexes = {});
+Error RMSD(const v3::Matrix& test, const v3::Matrix& templa, double* out, const IndexLists& indexes = {});
+Error MemRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix& tmp, double* out, const IndexLists& indexes = {});
+Error MemPerAtomRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix* ctest, v3::Matrix* ctempla, v3::Matrix& tmp,
+                     std::vector<double>* out, const IndexLists& indexes = {});
+
+// Topology side: only what align.res2atoms reads (chem.go Atom fields, lovo.go:504-516).
+struct Atom {
+    std::string Name;
+    int MolID = 0;
+    std::string Chain;
+};
+class Atomer {  // interfaces.go:67-75
+  public:
+    virtual ~Atomer() = default;
+    virtual const chem::Atom& Atom(int i) const = 0;
+    virtual int Len() const = 0;
+};
+class Topology : public Atomer {
+  public:
+    std::vector<chem::Atom> Atoms;
+    const chem::Atom& Atom(int i) const override { return Atoms.at((size_t)i); }
+    int Len() const override { return (int)Atoms.size(); }
+};
+
+class Traj {  // interfaces.go:36-49
+  public:
+    virtual ~Traj() = default;
+    virtual bool Readable() const = 0;
+    virtual Error Next(v3::Matrix* output, std::vector<double>* box = nullptr) = 0;
+    virtual int Len() const = 0;
+};
+
+// interfaces.go:51-64.  Go returns one channel per slot; here every non-null slot is filled before the
+// call returns.  A null entry means "read and discard".  Readers that own their frames (MemTraj) may
+// repoint the slot at their own matrix, as Molecule.NextConc does (chem.go:749-751).
+class ConcTraj {
+  public:
+    virtual ~ConcTraj() = default;
+    virtual bool Readable() const = 0;
+    virtual Error NextConc(std::vector<v3::Matrix*>& frames) = 0;
+    virtual int Len() const = 0;
+    virtual void Close() {}
+    // Optional fast feed for device staging: fill `dst` (natoms*3 float32) with the next frame in the
+    // reader's native layout and say which (GCB_F32_SOA / GCB_F32_AOS) and what scale applies.
+    // Default: not available.
+    virtual bool HasRawFeed() const { return false; }
+    virtual Error NextRaw(float* /*dst*/, int* /*layout*/, double* /*scale*/) { return Error("raw feed not supported"); }
+};
+
+// chem.Molecule used as a RAM-backed trajectory (chem.go:693-762).
+class MemTraj : public Traj, public ConcTraj {
+  public:
+    std::vector<v3::Matrix> Coords;
+    bool Readable() const override { return true; }
+    Error Next(v3::Matrix* output, std::vector<double>* box = nullptr) override;
+    Error NextConc(std::vector<v3::Matrix*>& frames) override;
+    int Len() const override { return Coords.empty() ? 0 : Coords[0].NVecs(); }
+    void Close() override { current_ = 0; }
+  private:
+    size_t current_ = 0;
+};
+
+Error newLastFrameError(const std::string& file, const std::string& who);
+
+}  // namespace chem
+
+namespace dcd {
+
+// CHARMM / NAMD DCD reader (traj/dcd/dcd.go): little- or big-endian, CHARMM flavour with optional
+// unit-cell block and optional 4th dimension; fixed atoms unsupported, X-PLOR unsupported.
+class DCDObj : public chem::Traj, public chem::ConcTraj {
+  public:
+    static Error New(const std::string& filename, std::unique_ptr<DCDObj>* out);
+    ~DCDObj() override;
+    bool Readable() const override { return readable_; }
+    Error Next(v3::Matrix* output, std::vector<double>* box = nullptr) override;
+    Error NextConc(std::vector<v3::Matrix*>& frames) override;
+    int Len() const override { return natoms_; }
+    void Close() override;
+    bool HasRawFeed() const override { return true; }
+    Error NextRaw(float* dst, int* layout, double* scale) override;  // x[], y[], z[] planes, as stored on disk
+
+  private:
+    Error initRead(const std::string& name);
+    Error nextRaw(float* x, float* y, float* z);
+    Error readI32(int32_t* v);
+    Error readFloat32Block(int32_t blocksize, float* block, int n);
+    std::string filename_;
+    FILE* f_ = nullptr;
+    int32_t natoms_ = 0, fixed_ = 0;
+    bool readable_ = false, charmm_ = false, extrablock_ = false, fourdim_ = false, readLast_ = false, swap_ = false;
+    float box_[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<float> fields_;
+};
+
+// DCD writer (traj/dcd/dcd_write.go:102-330): same header bytes, frame counter rewritten after every frame.
+class DCDWObj {
+  public:
+    static Error NewWriter(const std::string& filename, int natoms, std::unique_ptr<DCDWObj>* out);
+    ~DCDWObj();
+    Error WNext(const v3::Matrix& towrite);
+    Error WNextRaw(const double* aos, int natoms);
+    void Close();
+    int Len() const { return natoms_; }
+
+  private:
+    std::string filename_;
+    FILE* f_ = nullptr;
+    int32_t natoms_ = 0, frames_ = 0;
+    bool writable_ = false;
+    std::vector<float> fields_;
+};
+
+}  // namespace dcd
+
+namespace align {
+
+// align.Options (lovo_options.go:6-142).  Getter/setter pairs keep the Go names; the Go setters index
+// n[0] even without an argument (logical OR where AND was meant, :64-87) and panic -- here the value is
+// an optional pointer and a missing value just reads.
+class Options {
+  public:
+    int Begin(const int* n = nullptr) { if (n && *n >= 0) begin_ = *n; return begin_; }
+    int Skip(const int* n = nullptr) { if (n && *n >= 0) skip_ = *n; return skip_; }
+    int Cpus(const int* n = nullptr) { if (n && *n > 0) cpus_ = *n; return cpus_; }
+    double LessThanRMSD(const double* r = nullptr) { if (r) lessThanRMSD_ = *r; return lessThanRMSD_; }
+    int MinimumN(const int* n = nullptr) { if (n && *n > 0) minimumN_ = *n; return minimumN_; }
+    std::vector<std::string> AtomNames(const std::vector<std::string>* n = nullptr) { if (n && !n->empty()) atomNames_ = *n; return atomNames_; }
+    std::vector<std::string> Chains(const std::vector<std::string>* c = nullptr) { if (c) chains_ = *c; return chains_; }
+    std::string TrajName(const std::string* n = nullptr) { if (n && !n->empty()) writeTraj_ = *n; return writeTraj_; }
+    // additions for the device path, same idiom
+    int DeviceID(const int* d = nullptr) { if (d && *d >= 0) device_ = *d; return device_; }
+    // frames of rank r of n: contiguous blocks of whole chunks; comm combines the per-atom sums
+    void Shard(int rank, int nranks, gcb_comm* comm) { rank_ = rank; nranks_ = nranks; comm_ = comm; }
+    // host-side replacement of the collective (gloo in the CPU tests); sums a vector across ranks in place
+    void AllReduce(std::function<Error(double*, long)> f) { allreduce_ = std::move(f); }
+    int MaxIterations(const int* n = nullptr) { if (n && *n > 0) maxIter_ = *n; return maxIter_; }
+
+    int begin_ = 0, skip_ = 0, cpus_ = 1;
+    std::vector<std::string> atomNames_, chains_;
+    std::string writeTraj_;
+    double lessThanRMSD_ = 1.0;
+    int minimumN_ = 10;
+    int device_ = 0, rank_ = 0, nranks_ = 1, maxIter_ = 1000;
+    gcb_comm* comm_ = nullptr;
+    std::function<Error(double*, long)> allreduce_;
+};
+Options* DefaultOptions();    // lovo_options.go:22-32: cpus = hardware threads, names {"CA"}, 1.0 A, minimumN 10
+Options* DefaultCGOptions();  // :35-41: names {"BB"}
+
+struct MolIDandChain {  // lovo.go:50-65
+    int molid = 0;
+    std::string chain;
+    std::string String() const;
+    int MolID() const { return molid; }
+    const std::string& Chain() const { return chain; }
+};
+
+struct LOVOReturn {  // lovo.go:68-150
+    int N = 0;
+    int FramesRead = 0;
+    std::vector<int> Natoms;
+    std::vector<MolIDandChain> Nmols;
+    std::vector<double> RMSD;
+    int Iterations = 0;
+    std::string String() const;
+    std::string PyMOLSel() const;
+    std::string GMX(const std::string& chain = "") const;
+};
+
+// lovo.go:175-188 and its helpers; exposed because the index sets must match the reference bit for bit.
+Error mobileLimit(double limit, int tolerance, const std::vector<double>& sorted_rmsd, int* n, double* newlimit);
+bool approxEq(double i, double j, double epsilon);                       // :436-442
+bool sameElementsInt(const std::vector<int>& a, const std::vector<int>& b);  // :446-457
+int disagreementInt(const std::vector<int>& a, const std::vector<int>& b);   // :459-471
+std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::string>& names, const std::vector<std::string>& chains);  // :504-516
+std::vector<MolIDandChain> iDs2MolIDandChains(const chem::Atomer& mol, const std::vector<int>& indexes);  // :540-551
+// frames RMSDTraj actually processes for a source of F frames (chunks of cpus, begin/skip quirks, dropped tail; :306-326)
+std::vector<long> selectedFrames(long F, int cpus, int begin, int skip);
+// contiguous share of those frames for one rank (whole frames, balanced to within one)
+void shardRange(long nselected, int rank, int nranks, long* first, long* count);
+
+// The bookkeeping of one LOVO run (lovo.go:198-258) without the trajectory pass: feed it the per-atom
+// mean deviations of each RMSDTraj pass and it says which atoms to fit next and when to stop.
+class LovoState {
+  public:
+    LovoState(std::vector<int> fullindexes, double lessThanRMSD, int minimumN);
+    const std::vector<int>& FitIndexes() const { return fit_; }  // indexesold[0:n]
+    // rmsd: mol.Len() per-atom means.  Returns converged; on error *err is set (mobileLimit cannot terminate).
+    bool Step(const std::vector<double>& rmsd, Error* err);
+    int Disagreement() const { return disagreement_; }
+    int Iterations() const { return itercount_; }
+    void Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const;
+
+  private:
+    std::vector<int> full_, indexesold_, fit_, ids_;
+    std::vector<double> vals_;
+    double lessThan_, prevlim_ = 0.0;
+    int minimumN_, n_, itercount_ = 0, disagreement_ = 0;
+};
+
+// A trajectory made resident on the device once and reused by every LOVO iteration (the reference
+// re-opens and re-decodes the file per iteration, lovo.go:222).
+class DeviceTrajectory {
+  public:
+    ~DeviceTrajectory();
+    // Reads `traj` to its end with RMSDTraj's chunk rules and stages this rank's share of the selected
+    // frames through C-owned pinned buffers (raw float32 feed when the reader has one).
+    static Error Load(chem::ConcTraj& traj, int natoms, const Options& o, std::unique_ptr<DeviceTrajectory>* out);
+    long LocalFrames() const { return nlocal_; }
+    long SelectedFrames() const { return nselected_; }
+    gcb_traj* Handle() { return t_; }
+    // one RMSDTraj pass over the resident frames: per-atom mean deviations over ALL selected frames (all ranks)
+    Error MeanDeviations(const v3::Matrix& ref, const std::vector<int>& indexes, const Options& o, bool write_back,
+                         std::vector<double>* mean);
+    Error WriteDCD(const std::string& name);  // local frames, as dcd.DCDWObj would (lovo.go:337-339)
+
+  private:
+    gcb_traj* t_ = nullptr;
+    int natoms_ = 0;
+    long nlocal_ = 0, nselected_ = 0;
+};
+
+Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
+               std::vector<double>* rmsd, int* frames);
+Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt = nullptr);
+Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out);  // lovo.go:152-172
+
+}  // namespace align
+}  // namespace gochem

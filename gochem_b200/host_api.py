@@ -1,0 +1,221 @@
+"""ctypes binding of the C shim (include/gochem_host.h) over the C++ host-side mirror of the reference's Go API.
+Test / example plumbing: the functions read like the reference's (chem.Super, chem.RMSD, align.LOVO ...)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgochem_host.so")
+HEADER = os.path.join(HERE, "..", "include", "gochem_host.h")
+
+
+class GoChemError(RuntimeError):
+    def __init__(self, code, msg, last_frame=False):
+        super().__init__(msg)
+        self.code, self.msg, self.last_frame = code, msg, last_frame
+
+
+_lib = None
+
+
+def declared_symbols():
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(gch_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GoChemError(-7, f"{LIB_PATH} missing: run __graft_entry__.build()")
+        lib = C.CDLL(LIB_PATH)
+        lib.gch_last_error.restype = C.c_size_t
+        lib.gch_selected_frames.restype = C.c_long
+        lib.gch_lovo_state_new.restype = C.c_void_p
+        lib.gch_shard_range.restype = None
+        lib.gch_lovo_state_free.restype = None
+        _lib = lib
+    return _lib
+
+
+def _err(rc):
+    buf = C.create_string_buffer(4096)
+    load().gch_last_error(buf, 4096)
+    return GoChemError(rc, buf.value.decode(errors="replace"), bool(load().gch_last_error_is_last_frame()))
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _lists(indexes):
+    out = []
+    for ix in indexes[:2]:
+        out.append(None if ix is None else np.ascontiguousarray(ix, dtype=np.int32))
+    while len(out) < 2:
+        out.append(None)
+    n = [0 if a is None else a.size for a in out]
+    return out[0], n[0], out[1], n[1], len(indexes)
+
+
+def Super(test, templa, *indexes):
+    """chem.Super: returns the superposed copy (the Go function mutates test and returns it)."""
+    t = np.array(test, dtype=np.float64, order="C")
+    m = np.ascontiguousarray(templa, dtype=np.float64)
+    i0, n0, i1, n1, nl = _lists(indexes)
+    rc = load().gch_super(_d(t), t.shape[0], _d(m), m.shape[0], _i(i0), n0, _i(i1), n1, nl)
+    if rc:
+        raise _err(rc)
+    return t
+
+
+def RMSD(test, templa, *indexes):
+    t = np.ascontiguousarray(test, dtype=np.float64)
+    m = np.ascontiguousarray(templa, dtype=np.float64)
+    i0, n0, i1, n1, nl = _lists(indexes)
+    out = C.c_double(0)
+    rc = load().gch_rmsd(_d(t), t.shape[0], _d(m), m.shape[0], _i(i0), n0, _i(i1), n1, nl, C.byref(out))
+    if rc:
+        raise _err(rc)
+    return out.value
+
+
+def MemPerAtomRMSD(test, templa, *indexes):
+    t = np.ascontiguousarray(test, dtype=np.float64)
+    m = np.ascontiguousarray(templa, dtype=np.float64)
+    i0, n0, i1, n1, nl = _lists(indexes)
+    out = np.zeros(n0 if (nl and n0) else t.shape[0])
+    rc = load().gch_mem_per_atom_rmsd(_d(t), t.shape[0], _d(m), m.shape[0], _i(i0), n0, _i(i1), n1, nl, _d(out))
+    if rc:
+        raise _err(rc)
+    return out
+
+
+def RotatorTranslatorToSuper(test, templa):
+    t = np.ascontiguousarray(test, dtype=np.float64)
+    m = np.ascontiguousarray(templa, dtype=np.float64)
+    if t.shape != m.shape:
+        # let the library produce the reference's error
+        n = min(t.shape[0], m.shape[0])
+        raise GoChemError(-1, "goChem: Ill-formed matrices")
+    n = t.shape[0]
+    tr, r, a, b = np.zeros((n, 3)), np.zeros((3, 3)), np.zeros(3), np.zeros(3)
+    rc = load().gch_rotator_translator_to_super(_d(t), _d(m), n, _d(tr), _d(r), _d(a), _d(b))
+    if rc:
+        raise _err(rc)
+    return tr, r, a, b
+
+
+def mobile_limit(limit, tolerance, sorted_rmsd):
+    v = np.ascontiguousarray(sorted_rmsd, dtype=np.float64)
+    n, lim = C.c_int(0), C.c_double(0)
+    rc = load().gch_mobile_limit(C.c_double(limit), tolerance, _d(v), v.size, C.byref(n), C.byref(lim))
+    if rc:
+        raise _err(rc)
+    return n.value, lim.value
+
+
+def selected_frames(F, cpus, begin=0, skip=0):
+    n = load().gch_selected_frames(C.c_long(F), cpus, begin, skip, None, C.c_long(0))
+    out = np.zeros(max(n, 1), dtype=np.int64)
+    load().gch_selected_frames(C.c_long(F), cpus, begin, skip, out.ctypes.data_as(C.POINTER(C.c_long)), C.c_long(n))
+    return out[:n]
+
+
+def shard_range(nsel, rank, nranks):
+    f, c = C.c_long(0), C.c_long(0)
+    load().gch_shard_range(C.c_long(nsel), rank, nranks, C.byref(f), C.byref(c))
+    return f.value, c.value
+
+
+class LovoState:
+    def __init__(self, fullindexes, less_than_rmsd=1.0, minimum_n=10):
+        full = np.ascontiguousarray(fullindexes, dtype=np.int32)
+        self.nfull = full.size
+        self.h = C.c_void_p(load().gch_lovo_state_new(_i(full), full.size, C.c_double(less_than_rmsd), minimum_n))
+
+    def fit_indexes(self):
+        out = np.zeros(max(self.nfull, 1), dtype=np.int32)
+        n = load().gch_lovo_state_fit_indexes(self.h, _i(out), out.size)
+        return out[:n].copy()
+
+    def step(self, rmsd):
+        r = np.ascontiguousarray(rmsd, dtype=np.float64)
+        conv = C.c_int(0)
+        rc = load().gch_lovo_state_step(self.h, _d(r), r.size, C.byref(conv))
+        if rc:
+            raise _err(rc)
+        return bool(conv.value)
+
+    def disagreement(self):
+        return load().gch_lovo_state_disagreement(self.h)
+
+    def finish(self, natoms, frames_read):
+        N, it = C.c_int(0), C.c_int(0)
+        nat = np.zeros(max(self.nfull, 1), dtype=np.int32)
+        rm = np.zeros(max(self.nfull, 1))
+        load().gch_lovo_state_finish(self.h, natoms, frames_read, C.byref(N), _i(nat), _d(rm), C.byref(it))
+        return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm[: self.nfull].copy(), FramesRead=frames_read,
+                    Iterations=it.value)
+
+    def __del__(self):
+        try:
+            load().gch_lovo_state_free(self.h)
+        except Exception:
+            pass
+
+
+def dcd_write(path, frames):
+    f = np.ascontiguousarray(frames, dtype=np.float64)
+    rc = load().gch_dcd_write(path.encode(), _d(f), C.c_long(f.shape[0]), f.shape[1])
+    if rc:
+        raise _err(rc)
+
+
+def dcd_read(path, cap_frames, natoms, chunk=0):
+    out = np.zeros((cap_frames, natoms, 3))
+    nf, na = C.c_long(0), C.c_int(0)
+    rc = load().gch_dcd_read(path.encode(), _d(out), C.c_long(cap_frames), C.byref(nf), C.byref(na), chunk)
+    if rc:
+        raise _err(rc)
+    return out[: min(nf.value, cap_frames)], nf.value, na.value
+
+
+def RMSDTraj(dcd_path, ref, indexes, cpus, begin=0, skip=0, write_traj="", dev=0, rank=0, nranks=1, comm=None):
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    idx = np.ascontiguousarray(indexes, dtype=np.int32)
+    out = np.zeros(ref.shape[0])
+    frames = C.c_int(0)
+    rc = load().gch_rmsd_traj(dcd_path.encode(), _d(ref), ref.shape[0], _i(idx), idx.size, cpus, begin, skip,
+                              write_traj.encode(), dev, rank, nranks, comm, _d(out), C.byref(frames))
+    if rc:
+        raise _err(rc)
+    return out, frames.value
+
+
+def LOVO(dcd_path, ref, cpus, less_than_rmsd=1.0, minimum_n=10, names=None, chains=None, molids=None, atom_name="CA",
+         write_traj="", dev=0, rank=0, nranks=1, comm=None):
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    n = ref.shape[0]
+    N, frames, it, nr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    nat = np.zeros(n, dtype=np.int32)
+    rm = np.zeros(n)
+    text = C.create_string_buffer(1 << 20)
+    arr = lambda lst: None if lst is None else (C.c_char_p * n)(*[s.encode() for s in lst])
+    mol = None if molids is None else np.ascontiguousarray(molids, dtype=np.int32)
+    rc = load().gch_lovo(dcd_path.encode(), _d(ref), n, arr(names), arr(chains), _i(mol), atom_name.encode(), cpus,
+                         C.c_double(less_than_rmsd), minimum_n, write_traj.encode(), dev, rank, nranks, comm, C.byref(N),
+                         _i(nat), _d(rm), C.byref(nr), C.byref(frames), C.byref(it), text, C.c_size_t(len(text)))
+    if rc:
+        raise _err(rc)
+    lines = text.value.decode().split("\n")
+    return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm[: nr.value].copy(), FramesRead=frames.value,
+                Iterations=it.value, PyMOLSel=lines[0], GMX=lines[1], String=lines[2] if len(lines) > 2 else "")

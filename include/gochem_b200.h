@@ -111,6 +111,11 @@ int gcb_fetch_results(gcb_traj *t, long first, long nframes, double *rmsd, doubl
 int gcb_rmsd(gcb_traj *t, long first, long nframes, const double *ref_aos, int natoms_ref,
              const int *idx_test, const int *idx_ref, int nidx, double *rmsd);
 
+/* chem.MemPerAtomRMSD (geometric.go:294-321) for one resident frame, no superposition:
+ * out[k] = |frame[idx_test[k]] - ref[idx_ref[k]]|, k < nidx (all atoms when idx_test is NULL). */
+int gcb_peratom_dist(gcb_traj *t, long frame, const double *ref_aos, int natoms_ref,
+                     const int *idx_test, const int *idx_ref, int nidx, double *out);
+
 /* ---- align.RMSDTraj inner pass (align/lovo.go:265-281, 328-340) ----
  * For every frame: Super on the idx subset (both sides), then MemPerAtomRMSD against ref for ALL
  * atoms; sum[i] = sum over frames of |frame_i - ref_i| (not divided).  write_back as above.

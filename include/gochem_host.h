@@ -1,0 +1,66 @@
+/*
+ * gochem_host.h -- C shim over the C++ host-side mirror of the reference's Go API
+ * (gochem_b200/host/gochem.hpp).  It exists so tests written in Python can call chem.Super, chem.RMSD,
+ * align.RMSDTraj, align.LOVO, the DCD reader / writer and the LOVO bookkeeping the way the reference's own
+ * tests call the Go functions.  Status 0 = ok (nil error); otherwise gch_last_error() holds err.Error().
+ * Arithmetic on coordinates happens on the GPU through include/gochem_b200.h; there is no CPU fallback.
+ */
+#ifndef GOCHEM_HOST_H
+#define GOCHEM_HOST_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+size_t gch_last_error(char *buf, size_t cap);
+int gch_last_error_is_last_frame(void);
+int gch_set_device(int dev);
+
+/* chem.Super (handy.go:175-214): nlists = number of index slices the Go caller passes (0, 1 or 2).
+ * test (ntest x 3, row-major) is modified in place. */
+int gch_super(double *test, int ntest, const double *templa, int ntempla, const int *idx0, int n0,
+              const int *idx1, int n1, int nlists);
+/* chem.RMSD (geometric.go:232-243); *out = -1 on error like the reference. */
+int gch_rmsd(const double *test, int ntest, const double *templa, int ntempla, const int *idx0, int n0,
+             const int *idx1, int n1, int nlists, double *out);
+/* chem.MemPerAtomRMSD (geometric.go:294-321); out has n0 entries (ntest when no lists). */
+int gch_mem_per_atom_rmsd(const double *test, int ntest, const double *templa, int ntempla, const int *idx0, int n0,
+                          const int *idx1, int n1, int nlists, double *out);
+/* chem.RotatorTranslatorToSuper (geometric.go:127-208). */
+int gch_rotator_translator_to_super(const double *test, const double *templa, int n, double *transformed,
+                                    double *rot, double *trans1, double *trans2);
+
+/* align bookkeeping (align/lovo.go:175-188, 306-326) */
+int gch_mobile_limit(double limit, int tolerance, const double *sorted_rmsd, int n, int *n_out, double *limit_out);
+int gch_approx_eq(double i, double j, double eps);
+int gch_same_elements(const int *a, int na, const int *b, int nb);
+int gch_disagreement(const int *a, int na, const int *b, int nb);
+long gch_selected_frames(long F, int cpus, int begin, int skip, long *out, long cap);
+void gch_shard_range(long nselected, int rank, int nranks, long *first, long *count);
+
+/* LOVO iteration state (lovo.go:198-258 without the trajectory pass) */
+void *gch_lovo_state_new(const int *fullindexes, int nfull, double less_than_rmsd, int minimum_n);
+void gch_lovo_state_free(void *st);
+int gch_lovo_state_fit_indexes(void *st, int *out, int cap);
+int gch_lovo_state_step(void *st, const double *rmsd, int natoms, int *converged);
+int gch_lovo_state_disagreement(void *st);
+/* topology for Finish: every atom "CA", chain "A", MolID = i + 1 */
+int gch_lovo_state_finish(void *st, int natoms, int frames_read, int *N, int *natoms_out, double *rmsd_out, int *iterations);
+
+/* traj/dcd */
+int gch_dcd_write(const char *path, const double *frames_aos, long nframes, int natoms);
+int gch_dcd_read(const char *path, double *out_aos, long cap_frames, long *nframes, int *natoms, int use_nextconc_chunk);
+
+/* align.RMSDTraj / align.LOVO on a DCD file.  names / chains / molids describe the topology (natoms entries);
+ * NULL names = all "CA", chain "A", MolID i + 1.  comm may be NULL. */
+int gch_rmsd_traj(const char *dcd_path, const double *ref, int natoms, const int *indexes, int nidx, int cpus, int begin,
+                  int skip, const char *write_traj, int dev, int rank, int nranks, void *comm, double *rmsd, int *frames);
+int gch_lovo(const char *dcd_path, const double *ref, int natoms, const char *const *names, const char *const *chains,
+             const int *molids, const char *atom_name, int cpus, double less_than_rmsd, int minimum_n, const char *write_traj,
+             int dev, int rank, int nranks, void *comm, int *N, int *natoms_out, double *rmsd_out, int *nrmsd, int *frames,
+             int *iterations, char *text, size_t text_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,184 @@
+"""CPU tests of the host-side mirror of the reference's Go API: LOVO bookkeeping, frame selection, sharding,
+the DCD reader / writer.  The trajectory pass itself is GPU-only; here the per-atom means fed to the LOVO state
+machine come from the oracle, so the bookkeeping is checked against oracle.lovo end to end."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from gochem_b200 import host_api as H
+from gochem_b200 import synth
+from oracle import oracle_np as onp
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = H.load()
+    names = H.declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_mobile_limit_matches_oracle():
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        vals = np.sort(rng.uniform(0.1, 4.0, int(rng.integers(12, 60))))
+        lim = float(rng.uniform(0.05, 3.0))
+        tol = int(rng.integers(0, 12))
+        assert H.mobile_limit(lim, tol, vals) == oracle.mobile_limit(lim, tol, vals)
+    with pytest.raises(H.GoChemError):
+        H.mobile_limit(1.0, 10, np.array([0.1, 2.0]))  # the reference would loop forever
+
+
+def test_selected_frames_follow_the_reference_quirks():
+    # chunks of cpus, tail dropped (lovo.go:323-326)
+    assert list(H.selected_frames(11, 4)) == list(range(8))
+    assert list(H.selected_frames(3, 4)) == []
+    # begin: begin/cpus chunks are "skipped" (:306), but each skipped chunk is followed, in the same loop turn, by a
+    # chunk that IS processed -- there is no `continue` (:316-322)
+    assert list(H.selected_frames(20, 4, begin=8)) == [4, 5, 6, 7, 12, 13, 14, 15, 16, 17, 18, 19]
+    assert list(H.selected_frames(20, 4, begin=7)) == list(range(4, 20))
+    # skip: a discarded chunk is followed by a processed one, no `continue` (:316-322)
+    assert list(H.selected_frames(24, 2, skip=2)) == [0, 1, 4, 5, 6, 7, 10, 11, 12, 13, 16, 17, 18, 19, 22, 23]
+    # against the oracle's chunk loop for random settings
+    rng = np.random.default_rng(3)
+    ref, frames = synth.make_case(5, 40)
+    for _ in range(30):
+        F, cpus = int(rng.integers(1, 40)), int(rng.integers(1, 7))
+        begin, skip = int(rng.integers(0, 12)), int(rng.integers(0, 12))
+        _, total = oracle.rmsd_traj(frames[:F], ref, np.arange(5), cpus, begin, skip)
+        assert len(H.selected_frames(F, cpus, begin, skip)) == total
+
+
+def test_shard_ranges_partition_the_selection():
+    for nsel in [0, 1, 7, 64, 1001]:
+        for nranks in [1, 2, 3, 8]:
+            got = []
+            for r in range(nranks):
+                f, c = H.shard_range(nsel, r, nranks)
+                got += list(range(f, f + c))
+                assert c in (nsel // nranks, nsel // nranks + 1)
+            assert got == list(range(nsel))
+
+
+def drive_lovo(frames, ref, full, cpus, less=1.0, minn=10, allreduce=None, shard=None):
+    """align.LOVO with the host bookkeeping from the product and the trajectory pass from the oracle."""
+    st = H.LovoState(full, less, minn)
+    sel = H.selected_frames(frames.shape[0], cpus)
+    used = frames[sel]
+    while True:
+        idx = st.fit_indexes()
+        if shard is None:
+            sums, total = oracle.rmsd_traj(used, ref, idx, cpus=1)
+            sums = sums * total
+        else:
+            f, c = shard
+            sums, total = oracle.rmsd_traj(used[f:f + c], ref, idx, cpus=1) if c else (np.zeros(ref.shape[0]), 0)
+            sums = allreduce(np.nan_to_num(sums) * total)
+        if st.step(sums / len(sel)):
+            break
+    return st.finish(ref.shape[0], len(sel))
+
+
+def test_lovo_state_machine_matches_oracle(golden_dir):
+    z = np.load(os.path.join(golden_dir, "lovo_n150_f42.npz"))
+    ref, frames, cpus = z["ref"].astype(np.float64), z["frames"].astype(np.float64), int(z["cpus"])
+    got = drive_lovo(frames, ref, np.arange(150), cpus)
+    assert got["N"] == int(z["N"]) and got["Iterations"] == int(z["Iterations"]) and got["FramesRead"] == 40
+    assert list(got["Natoms"]) == list(z["Natoms"])
+    assert np.abs(got["RMSD"] - z["RMSD"]).max() < 1e-11
+    # a second, larger case against the C oracle, candidates = every third atom
+    ref, frames = synth.make_case(240, 60)
+    full = np.arange(0, 240, 3)
+    want = oracle.lovo(frames, ref, full, cpus=5, less_than_rmsd=0.8, minimum_n=7)
+    got = drive_lovo(frames, ref, full, 5, 0.8, 7)
+    assert got["N"] == want["N"] and got["Iterations"] == want["Iterations"]
+    assert list(got["Natoms"]) == list(want["Natoms"])
+    assert np.abs(got["RMSD"] - want["RMSD"]).max() < 1e-11
+    # LessThanRMSD <= 0: n stays at the full candidate list
+    want = oracle.lovo(frames, ref, full, cpus=5, less_than_rmsd=0.0)
+    got = drive_lovo(frames, ref, full, 5, 0.0, 10)
+    assert got["N"] == want["N"] == 80 and got["Iterations"] == want["Iterations"]
+
+
+def test_dcd_round_trip(tmp_path):
+    ref, frames = synth.make_case(37, 9, through_f32=True)
+    p = str(tmp_path / "t.dcd")
+    H.dcd_write(p, frames)
+    raw = open(p, "rb").read()
+    # header bytes the reference's writer emits (dcd_write.go:102-205) and the running frame counter (:300-330)
+    assert struct.unpack("<i4si", raw[:12]) == (84, b"CORD", 9)
+    assert struct.unpack("<i", raw[84:88])[0] == 24 and struct.unpack("<i", raw[88:92])[0] == 84
+    assert struct.unpack("<f", raw[44:48])[0] == 1.0
+    natoms_off = 92 + 4 + 4 + 160 + 4 + 4
+    assert struct.unpack("<i", raw[natoms_off:natoms_off + 4])[0] == 37
+    assert len(raw) == natoms_off + 8 + 9 * 3 * (37 * 4 + 8)
+    back, nf, na = H.dcd_read(p, 20, 37)
+    assert (nf, na) == (9, 37) and np.array_equal(back, frames)
+    # NextConc in chunks of 4: the tail of 1 is dropped
+    back, nf, na = H.dcd_read(p, 20, 37, chunk=4)
+    assert nf == 8 and np.array_equal(back, frames[:8])
+    with pytest.raises(H.GoChemError):
+        H.dcd_read(str(tmp_path / "missing.dcd"), 1, 1)
+    # big-endian files are read too (dcd.go:172-174)
+    be = bytearray(raw)
+    for off in list(range(0, 4, 4)) + list(range(8, 92, 4)) + [92, 96, 260, 264, 268, 272]:
+        be[off:off + 4] = be[off:off + 4][::-1]
+    body = natoms_off + 8
+    for off in range(body, len(raw), 4):
+        be[off:off + 4] = be[off:off + 4][::-1]
+    pb = str(tmp_path / "be.dcd")
+    open(pb, "wb").write(bytes(be))
+    back, nf, na = H.dcd_read(pb, 20, 37)
+    assert nf == 9 and np.array_equal(back, frames)
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref, frames = synth.make_case(90, 33)
+    full = np.arange(90)
+    cpus = 4
+    nsel = len(H.selected_frames(frames.shape[0], cpus))
+
+    def allreduce(v):
+        # all-gather + rank-ordered sum: what gcb_allreduce_sum_f64 does with NCCL
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        out = torch.zeros_like(t)
+        for p in parts:
+            out += p
+        return out.numpy()
+
+    got = drive_lovo(frames, ref, full, cpus, allreduce=allreduce, shard=H.shard_range(nsel, rank, world))
+    np.savez(os.path.join(tmpdir, f"r{rank}.npz"), N=got["N"], Natoms=got["Natoms"], RMSD=got["RMSD"], It=got["Iterations"])
+    dist.destroy_process_group()
+
+
+def test_sharded_lovo_two_ranks_gloo(tmp_path):
+    """N > 1 path on CPU: frames sharded over 2 ranks, per-atom sums combined with a gloo all-gather in rank
+    order; both ranks must reach the single-rank answer with identical index lists."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref, frames = synth.make_case(90, 33)
+    want = oracle.lovo(frames, ref, np.arange(90), cpus=4)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    for r in (r0, r1):
+        assert int(r["N"]) == want["N"] and int(r["It"]) == want["Iterations"]
+        assert list(r["Natoms"]) == list(want["Natoms"])
+        assert np.abs(r["RMSD"] - want["RMSD"]).max() < 1e-12
+    assert np.array_equal(r0["RMSD"], r1["RMSD"])  # bit-identical across ranks
