@@ -4,9 +4,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <sstream>
 #include <thread>
 
 #include "../../include/gochem_b200.h"
@@ -607,14 +607,15 @@ static std::string fmtFloat(double v) {  // Go's %v for float64: shortest repres
 }
 
 std::string LOVOReturn::String() const {  // lovo.go:79-86
-    std::ostringstream s;
-    s << "N: " << N << ",  Frames read: " << FramesRead << ", Iterations needed: " << Iterations << ", RMSD: [";
-    for (size_t i = 0; i < RMSD.size(); i++) s << (i ? " " : "") << fmtFloat(RMSD[i]);
-    s << "], Natoms: [";
-    for (size_t i = 0; i < Natoms.size(); i++) s << (i ? " " : "") << Natoms[i];
-    s << "], Nmols:";
-    for (const auto& m : Nmols) s << " " << m.String();
-    return s.str();
+    // plain string appends: no iostreams in this library (their locale state is per libstdc++ copy)
+    std::string s = "N: " + std::to_string(N) + ",  Frames read: " + std::to_string(FramesRead) +
+                    ", Iterations needed: " + std::to_string(Iterations) + ", RMSD: [";
+    for (size_t i = 0; i < RMSD.size(); i++) { if (i) s += " "; s += fmtFloat(RMSD[i]); }
+    s += "], Natoms: [";
+    for (size_t i = 0; i < Natoms.size(); i++) { if (i) s += " "; s += std::to_string(Natoms[i]); }
+    s += "], Nmols:";
+    for (const auto& m : Nmols) s += " " + m.String();
+    return s;
 }
 
 std::string LOVOReturn::PyMOLSel() const {  // lovo.go:102-116
@@ -961,7 +962,9 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
     };
     if (Error e = load()) return e;
     std::vector<double> rmsd;
+    const bool dbg = getenv("GCH_DEBUG") != nullptr;
     for (;;) {
+        if (dbg) fprintf(stderr, "[LOVO] iteration %d, fit on %zu atoms, local frames %ld\n", st.Iterations(), st.FitIndexes().size(), d->LocalFrames());
         if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228
         const bool wb = !o->writeTraj_.empty();
         if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd)) return e;
@@ -969,13 +972,19 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
             if (Error e = d->WriteDCD(o->writeTraj_)) return e;
             if (Error e = load()) return e;  // the pass rewrote the resident frames; later passes start from the file again
         }
+        if (dbg) fprintf(stderr, "[LOVO] pass done, mean[0]=%g\n", rmsd.empty() ? -1.0 : rmsd[0]);
         Error serr;
         const bool converged = st.Step(rmsd, &serr);
+        if (dbg) fprintf(stderr, "[LOVO] step done converged=%d\n", (int)converged);
         if (serr) return serr;
         if (converged) break;
         if (st.Iterations() >= o->maxIter_) return Error("align.LOVO: no convergence after " + std::to_string(st.Iterations()) + " iterations");
     }
+    if (dbg) fprintf(stderr, "[LOVO] finishing\n");
     st.Finish(mol, (int)d->SelectedFrames(), out);
+    if (dbg) fprintf(stderr, "[LOVO] finished N=%d\n", out->N);
+    d.reset();
+    if (dbg) fprintf(stderr, "[LOVO] device trajectory released\n");
     return Error();
 }
 
