@@ -260,4 +260,24 @@ int gch_lovo(const char* path, const double* ref, int natoms, const char* const*
     return 0;
 }
 
+int gch_lovo_resident(void* traj_handle, long nlocal, long nselected_total, const double* ref, int natoms, int cpus,
+                      double less_than, int minimum_n, void* comm, int rank, int nranks, int* N, int* natoms_out, double* rmsd_out,
+                      int* iterations) {
+    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    std::unique_ptr<align::Options> o(align::DefaultOptions());
+    o->Cpus(&cpus);
+    o->LessThanRMSD(&less_than);
+    o->MinimumN(&minimum_n);
+    o->Shard(rank, nranks, static_cast<gcb_comm*>(comm));
+    std::unique_ptr<align::DeviceTrajectory> d = align::DeviceTrajectory::Adopt(static_cast<gcb_traj*>(traj_handle), natoms, nlocal, nselected_total);
+    align::LOVOReturn r;
+    Error e = align::LOVOResident(top, mat(ref, natoms), d, &r, o.get());
+    if (e) return fail(e);
+    *N = r.N;
+    *iterations = r.Iterations;
+    for (int i = 0; i < r.N; i++) natoms_out[i] = r.Natoms[(size_t)i];
+    for (size_t i = 0; i < r.RMSD.size(); i++) rmsd_out[i] = r.RMSD[i];
+    return 0;
+}
+
 }  // extern "C"

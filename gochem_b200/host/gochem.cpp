@@ -791,7 +791,17 @@ void LovoState::Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out)
 
 // ---- device-resident trajectory ----
 DeviceTrajectory::~DeviceTrajectory() {
-    if (t_) gcb_traj_destroy(t_);
+    if (t_ && owned_) gcb_traj_destroy(t_);
+}
+
+std::unique_ptr<DeviceTrajectory> DeviceTrajectory::Adopt(gcb_traj* t, int natoms, long nlocal, long nselected_total) {
+    std::unique_ptr<DeviceTrajectory> d(new DeviceTrajectory());
+    d->t_ = t;
+    d->owned_ = false;
+    d->natoms_ = natoms;
+    d->nlocal_ = nlocal;
+    d->nselected_ = nselected_total;
+    return d;
 }
 
 Error DeviceTrajectory::Load(chem::ConcTraj& traj, int natoms, const Options& o, std::unique_ptr<DeviceTrajectory>* out) {
@@ -944,23 +954,12 @@ Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out) {
     return Error("Trajectory fromat not supported. Must have concurrent read support in goChem");  // lovo.go:168-169
 }
 
-Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt) {
-    std::unique_ptr<Options> own;
-    Options* o = opt;
-    if (!o) { own.reset(DefaultOptions()); o = own.get(); }
+Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_ptr<DeviceTrajectory>& d, LOVOReturn* out, Options* o,
+                   const std::function<Error()>& reload) {
     const std::vector<int> fullindexes = res2atoms(mol, o->atomNames_, o->chains_);
     const std::string printtraj = o->writeTraj_;
     o->writeTraj_.clear();  // lovo.go:209-211
     LovoState st(fullindexes, o->lessThanRMSD_, o->minimumN_);
-    std::unique_ptr<DeviceTrajectory> d;
-    auto load = [&]() -> Error {
-        std::unique_ptr<chem::ConcTraj> traj;
-        if (Error e = opentraj(trajname, &traj)) return e;  // :222 (the reference re-opens it on every iteration)
-        Error e = DeviceTrajectory::Load(*traj, mol.Len(), *o, &d);
-        traj->Close();
-        return e;
-    };
-    if (Error e = load()) return e;
     std::vector<double> rmsd;
     const bool dbg = getenv("GCH_DEBUG") != nullptr;
     for (;;) {
@@ -970,22 +969,36 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
         if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd)) return e;
         if (wb) {
             if (Error e = d->WriteDCD(o->writeTraj_)) return e;
-            if (Error e = load()) return e;  // the pass rewrote the resident frames; later passes start from the file again
+            // the pass rewrote the resident frames; later passes start from the source again (the reference
+            // re-reads the file on every iteration, lovo.go:222).  reload() may replace d.
+            if (reload) { if (Error e = reload()) return e; }
         }
-        if (dbg) fprintf(stderr, "[LOVO] pass done, mean[0]=%g\n", rmsd.empty() ? -1.0 : rmsd[0]);
         Error serr;
         const bool converged = st.Step(rmsd, &serr);
-        if (dbg) fprintf(stderr, "[LOVO] step done converged=%d\n", (int)converged);
         if (serr) return serr;
         if (converged) break;
         if (st.Iterations() >= o->maxIter_) return Error("align.LOVO: no convergence after " + std::to_string(st.Iterations()) + " iterations");
     }
-    if (dbg) fprintf(stderr, "[LOVO] finishing\n");
     st.Finish(mol, (int)d->SelectedFrames(), out);
-    if (dbg) fprintf(stderr, "[LOVO] finished N=%d\n", out->N);
-    d.reset();
-    if (dbg) fprintf(stderr, "[LOVO] device trajectory released\n");
     return Error();
+}
+
+Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt) {
+    std::unique_ptr<Options> own;
+    Options* o = opt;
+    if (!o) { own.reset(DefaultOptions()); o = own.get(); }
+    std::unique_ptr<DeviceTrajectory> d;
+    auto load = [&]() -> Error {
+        std::unique_ptr<chem::ConcTraj> traj;
+        if (Error e = opentraj(trajname, &traj)) return e;  // :222 (the reference re-opens it on every iteration)
+        std::unique_ptr<DeviceTrajectory> fresh;
+        Error e = DeviceTrajectory::Load(*traj, mol.Len(), *o, &fresh);
+        traj->Close();
+        if (!e) d = std::move(fresh);
+        return e;
+    };
+    if (Error e = load()) return e;
+    return LOVOResident(mol, ref, d, out, o, load);
 }
 
 }  // namespace align

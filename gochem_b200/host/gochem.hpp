@@ -303,6 +303,8 @@ class DeviceTrajectory {
     // Reads `traj` to its end with RMSDTraj's chunk rules and stages this rank's share of the selected
     // frames through C-owned pinned buffers (raw float32 feed when the reader has one).
     static Error Load(chem::ConcTraj& traj, int natoms, const Options& o, std::unique_ptr<DeviceTrajectory>* out);
+    // Wrap a handle somebody else filled (nlocal resident frames of nselected_total over all ranks); not owned.
+    static std::unique_ptr<DeviceTrajectory> Adopt(gcb_traj* t, int natoms, long nlocal, long nselected_total);
     long LocalFrames() const { return nlocal_; }
     long SelectedFrames() const { return nselected_; }
     gcb_traj* Handle() { return t_; }
@@ -313,6 +315,7 @@ class DeviceTrajectory {
 
   private:
     gcb_traj* t_ = nullptr;
+    bool owned_ = true;
     int natoms_ = 0;
     long nlocal_ = 0, nselected_ = 0;
 };
@@ -320,6 +323,10 @@ class DeviceTrajectory {
 Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
                std::vector<double>* rmsd, int* frames);
 Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt = nullptr);
+// The LOVO iteration (lovo.go:221-252) over a trajectory that is already resident on the device.  `reload`, when
+// given, restores the frames after a pass that wrote the aligned trajectory back over them.
+Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_ptr<DeviceTrajectory>& d, LOVOReturn* out, Options* o,
+                   const std::function<Error()>& reload = nullptr);
 Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out);  // lovo.go:152-172
 
 }  // namespace align

@@ -219,3 +219,22 @@ def LOVO(dcd_path, ref, cpus, less_than_rmsd=1.0, minimum_n=10, names=None, chai
     lines = text.value.decode().split("\n")
     return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm[: nr.value].copy(), FramesRead=frames.value,
                 Iterations=it.value, PyMOLSel=lines[0], GMX=lines[1], String=lines[2] if len(lines) > 2 else "")
+
+
+def LOVOResident(traj, ref, nselected_total=None, cpus=8, less_than_rmsd=1.0, minimum_n=10, comm=None, rank=0, nranks=1):
+    """align.LOVO's iteration over a _lib.DeviceTraj that already holds this rank's frames."""
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    n = ref.shape[0]
+    nlocal = traj.nframes
+    total = nlocal if nselected_total is None else nselected_total
+    N, it = C.c_int(0), C.c_int(0)
+    nat = np.zeros(n, dtype=np.int32)
+    rm = np.zeros(n)
+    fn = load().gch_lovo_resident
+    fn.argtypes = [C.c_void_p, C.c_long, C.c_long, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                   C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    rc = fn(traj.h, nlocal, total, _d(ref), n, cpus, less_than_rmsd, minimum_n, comm.h if comm is not None else None, rank, nranks,
+            C.byref(N), _i(nat), _d(rm), C.byref(it))
+    if rc:
+        raise _err(rc)
+    return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm.copy(), FramesRead=total, Iterations=it.value)

@@ -60,6 +60,12 @@ int gch_lovo(const char *dcd_path, const double *ref, int natoms, const char *co
              int dev, int rank, int nranks, void *comm, int *N, int *natoms_out, double *rmsd_out, int *nrmsd, int *frames,
              int *iterations, char *text, size_t text_cap);
 
+/* The LOVO iteration over a trajectory already resident on the device (a gcb_traj handle holding nlocal of the
+ * nselected_total frames all ranks hold together); topology: all "CA", chain "A". */
+int gch_lovo_resident(void *traj_handle, long nlocal, long nselected_total, const double *ref, int natoms, int cpus,
+                      double less_than_rmsd, int minimum_n, void *comm, int rank, int nranks, int *N, int *natoms_out,
+                      double *rmsd_out, int *iterations);
+
 #ifdef __cplusplus
 }
 #endif

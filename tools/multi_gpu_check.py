@@ -1,0 +1,67 @@
+"""Run under torchrun on >= 2 GPUs: NCCL rank-ordered allreduce and sharded LOVO against the single-GPU answer.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from gochem_b200 import _lib, synth
+from gochem_b200 import host_api as H
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+# the library's own communicator: rank 0 makes the id, torch.distributed carries the 128 bytes
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid = torch.tensor(list(_lib.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+dist.broadcast(uid, 0)
+comm = _lib.Comm(local, world, rank, bytes(uid.cpu().tolist()))
+out = {}
+# 1. rank-ordered sum is bit-identical on every rank
+v = np.random.default_rng(rank).standard_normal(5000)
+s = comm.allreduce_sum(v)
+want = sum(np.random.default_rng(r).standard_normal(5000) for r in range(world))
+out["allreduce_max_abs_err"] = float(np.abs(s - want).max())
+g = [None] * world
+dist.all_gather_object(g, s.tobytes())
+out["allreduce_bit_identical"] = all(x == g[0] for x in g)
+# 2. sharded LOVO (config 3 shape) vs the single-GPU run
+natoms = int(os.environ.get("NATOMS", "5000"))
+total = int(os.environ.get("NFRAMES", "50000"))
+ref, sig = synth.make_reference(natoms), synth.atom_sigmas(natoms)
+first, count = H.shard_range(total, rank, world)
+t = _lib.DeviceTraj(natoms, count, dev=local)
+t.synth_fill(ref, sig, count, frame_id0=first)
+t.sync()
+dist.barrier()
+t0 = time.perf_counter()
+got = H.LOVOResident(t, ref, nselected_total=total, cpus=8, comm=comm, rank=rank, nranks=world)
+torch.cuda.synchronize()
+dist.barrier()
+dt = time.perf_counter() - t0
+out["lovo"] = {"N": got["N"], "iterations": got["Iterations"], "seconds": dt,
+               "frames_per_s_per_iteration": total * got["Iterations"] / dt}
+g = [None] * world
+dist.all_gather_object(g, got["Natoms"].tobytes())
+out["natoms_identical_across_ranks"] = all(x == g[0] for x in g)
+if rank == 0:
+    whole = _lib.DeviceTraj(natoms, total, dev=local)
+    whole.synth_fill(ref, sig, total)
+    t0 = time.perf_counter()
+    single = H.LOVOResident(whole, ref, cpus=8)
+    out["single_gpu_seconds"] = time.perf_counter() - t0
+    out["same_as_single_gpu"] = bool(single["N"] == got["N"] and list(single["Natoms"]) == list(got["Natoms"])
+                                     and single["Iterations"] == got["Iterations"])
+    out["max_abs_rmsd_diff_vs_single"] = float(np.abs(single["RMSD"] - got["RMSD"]).max())
+    whole.close()
+    print(json.dumps(out), flush=True)
+dist.barrier()
+t.close()
+comm.close()
+dist.destroy_process_group()
