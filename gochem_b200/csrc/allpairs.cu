@@ -1,0 +1,342 @@
+// allpairs.cu -- all-pairs frame RMSD matrix (BASELINE.json configs[3]) as an fp64 tensor-core GEMM.
+//
+// D_ij = chem.RMSD(X_i, X_j) = ||X_i - X_j||_F / sqrt(n) (/root/reference/geometric.go:232-288: no superposition
+// inside RMSD; frames are superposed beforehand with gcb_super_rmsd(write_back = 1)).  Expanding the square,
+//     D_ij^2 = (G_ii + G_jj - 2 G_ij) / n,   G = Y Y^T,
+// where Y is the F x 3n matrix of frame coordinates MINUS one common structure (the mean of the frames): a common
+// offset cancels in every difference, and removing it shrinks G_ii from ~3n*|x|^2 to ~3n*fluctuation^2, which is
+// what keeps the cancellation in G_ii + G_jj - 2 G_ij harmless.  Pairs whose D^2 is still below the rounding floor
+// of that expression are recomputed from the explicit differences.
+//
+// The contraction is the one dense GEMM of the path, so it runs on the tensor cores: tcgen05 has no fp64 kind, the
+// fp64 tensor path on sm_100a is mma.sync.m8n8k4.f64 (DMMA).  128 x 128 x 16 CTA tiles, 8 warps (64 x 32 each),
+// 3-stage cp.async pipeline, only tiles on or above the diagonal are computed and mirrored in the epilogue.
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int LDS = BK + 4;           // row stride in doubles: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = pred ? 16 : 0;   // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Y[f][c] = X[f][c] - mu[c] on the packed row layout (ld doubles per frame); norms[f] = sum_c Y[f][c]^2.
+__global__ void __launch_bounds__(256) centre_rows_kernel(const double* __restrict__ X, long ldx, const double* __restrict__ mu,
+                                                         double* __restrict__ Y, long ldy, int ncols, long nframes,
+                                                         double* __restrict__ norms) {
+    __shared__ double red[8];
+    for (long f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const double* x = X + f * ldx;
+        double* y = Y + f * ldy;
+        double s = 0.0;
+        for (int c = threadIdx.x; c < ncols; c += 256) {
+            const double v = x[c] - mu[c];
+            y[c] = v;
+            s = fma(v, v, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w];
+            norms[f] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// column means of X (nframes x ncols), fixed order per column
+__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long ldx, int ncols, long nframes,
+                                                      double* __restrict__ mu) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double s = 0.0;
+    for (long f = 0; f < nframes; f++) s += X[f * ldx + c];
+    mu[c] = s / (double)nframes;
+}
+
+// gather a subset of atoms into packed rows [x(idx) | y(idx) | z(idx)], padded to ncols_pad with zeros
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ frames, long stride, int np,
+                                                         const int* __restrict__ idx, int nidx, int ncols_pad, long nframes,
+                                                         double* __restrict__ out) {
+    const long total = nframes * (long)ncols_pad;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const long f = g / ncols_pad;
+        const int c = (int)(g - f * ncols_pad);
+        double v = 0.0;
+        if (c < 3 * nidx) {
+            const int plane = c / nidx, k = c - plane * nidx;
+            v = frames[f * stride + (long)plane * np + idx[k]];
+        }
+        out[g] = v;
+    }
+}
+
+struct PairList {
+    unsigned int* count;
+    uint2* pairs;
+    unsigned int cap;
+};
+
+// One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T for rows [row0, row0 + nrows) against all
+// columns, and writes D (both triangles when the mirrored block belongs to this rank's rows).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
+                     long row0, long nrows, const int2* __restrict__ tiles, double* __restrict__ D, long ldd, double floor_rel,
+                     PairList redo) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;                              // [STAGES][BM][LDS]
+    double* sB = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BN][LDS]
+    const int2 tile = tiles[blockIdx.x];
+    const long i0 = (long)tile.x * BM, j0 = (long)tile.y * BN;   // global frame indexes
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;        // 2 x 4 warps -> 64 x 32 warp tiles
+    const int g = lane >> 2, t = lane & 3;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int nk = (kdim + BK - 1) / BK;
+    // each thread copies 2 x 16 B of A and 2 x 16 B of B per stage: 128 rows x 16 doubles = 1024 chunks of 2 doubles
+    auto load_stage = [&](int stage, int kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int chunk = tid + r * GEMM_THREADS;   // 0..1023
+            const int row = chunk >> 3, kc = (chunk & 7) * 2;
+            const bool kin = k0 + kc < kdim;
+            {
+                const long fr = i0 + row;
+                const bool ok = kin && fr < nframes;
+                cp_async16(sA + ((size_t)stage * BM + row) * LDS + kc, Y + (ok ? fr : 0) * ld + (ok ? k0 + kc : 0), ok);
+            }
+            {
+                const long fr = j0 + row;
+                const bool ok = kin && fr < nframes;
+                cp_async16(sB + ((size_t)stage * BN + row) * LDS + kc, Y + (ok ? fr : 0) * ld + (ok ? k0 + kc : 0), ok);
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double* a = sA + ((size_t)(kt % STAGES) * BM + wm * 64) * LDS;
+        const double* b = sB + ((size_t)(kt % STAGES) * BN + wn * 32) * LDS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) bf[ni] = b[(ni * 8 + g) * LDS + kk + t];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+        const long i = i0 + wm * 64 + mi * 8 + g;
+        if (i >= nframes) continue;
+        const double ni_ = norms[i];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const long j = j0 + wn * 32 + ni * 8 + 2 * t + e;
+                if (j >= nframes) continue;
+                const double nj_ = norms[j];
+                double d2 = (ni_ + nj_ - 2.0 * acc[mi][ni][e]) * inv_n;
+                double d;
+                if (i == j) {
+                    d = 0.0;
+                } else {
+                    if (d2 < floor_rel * (ni_ + nj_) * inv_n && j > i) {
+                        // below the rounding floor of the expansion: recompute from explicit differences later
+                        const unsigned int slot = atomicAdd(redo.count, 1u);
+                        if (slot < redo.cap) redo.pairs[slot] = make_uint2((unsigned int)i, (unsigned int)j);
+                    }
+                    d = sqrt(d2 > 0.0 ? d2 : 0.0);
+                }
+                if (i >= row0 && i < row0 + nrows) D[(i - row0) * ldd + j] = d;
+                if (j != i && tile.x != tile.y && j >= row0 && j < row0 + nrows) D[(j - row0) * ldd + i] = d;
+            }
+        }
+    }
+}
+
+// explicit ||Y_i - Y_j|| for the flagged pairs: one warp per pair
+__global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restrict__ Y, long ld, int kdim, double inv_n, PairList redo,
+                                                        long row0, long nrows, double* __restrict__ D, long ldd) {
+    const unsigned int n = min(*redo.count, redo.cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < n; p += gridDim.x * 8) {
+        const uint2 ij = redo.pairs[p];
+        const double* a = Y + (long)ij.x * ld;
+        const double* b = Y + (long)ij.y * ld;
+        double s = 0.0;
+        for (int c = lane; c < kdim; c += 32) {
+            const double v = a[c] - b[c];
+            s = fma(v, v, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double d = sqrt(s * inv_n);
+            if ((long)ij.x >= row0 && (long)ij.x < row0 + nrows) D[((long)ij.x - row0) * ldd + ij.y] = d;
+            if ((long)ij.y >= row0 && (long)ij.y < row0 + nrows) D[((long)ij.y - row0) * ldd + ij.x] = d;
+        }
+    }
+}
+
+}  // namespace
+
+// Device-side driver.  Y source: the trajectory planes themselves (idx == nullptr: rows of 3*np doubles, padding
+// zeros) or a gathered subset.  Computes rows [row0, row0 + nrows) of the F x F matrix into d_out (ld = nframes).
+int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int nidx, long row0, long nrows, double* d_out,
+                    float* gemm_ms, long* redone) {
+    cudaStream_t s = t->stream;
+    const int natoms_used = d_idx ? nidx : t->natoms;
+    const int kdim = d_idx ? round_up(3 * nidx, 2) : 3 * t->np;
+    const long ld = kdim;
+    double *Y = nullptr, *mu = nullptr, *norms = nullptr, *X = nullptr;
+    int2* d_tiles = nullptr;
+    PairList redo{nullptr, nullptr, 1u << 22};
+    int rc = GCB_OK;
+    std::vector<int2> tiles;
+    const int nt = (int)((nframes + BM - 1) / BM);
+    const size_t smem = sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+#define AP_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            set_error("%s failed: %s", #call, cudaGetErrorString(e__));                           \
+            rc = (e__ == cudaErrorMemoryAllocation) ? GCB_ERR_ALLOC : GCB_ERR_CUDA;               \
+            goto done;                                                                            \
+        }                                                                                         \
+    } while (0)
+    AP_TRY(cudaMalloc(&Y, sizeof(double) * (size_t)nframes * (size_t)ld));
+    AP_TRY(cudaMalloc(&mu, sizeof(double) * (size_t)kdim));
+    AP_TRY(cudaMalloc(&norms, sizeof(double) * (size_t)nframes));
+    AP_TRY(cudaMalloc(&redo.count, sizeof(unsigned int)));
+    AP_TRY(cudaMalloc(&redo.pairs, sizeof(uint2) * (size_t)redo.cap));
+    AP_TRY(cudaMemsetAsync(redo.count, 0, sizeof(unsigned int), s));
+    {
+        const double* src = t->d_frames + first * 3L * t->np;
+        long ldx = 3L * t->np;
+        if (d_idx) {
+            AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * (size_t)ld));
+            gather_rows_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
+            GCB_LAUNCHED();
+            src = X;
+            ldx = ld;
+        }
+        col_mean_kernel<<<(kdim + 255) / 256, 256, 0, s>>>(src, ldx, kdim, nframes, mu);
+        GCB_LAUNCHED();
+        centre_rows_kernel<<<t->sm_count * 4, 256, 0, s>>>(src, ldx, mu, Y, ld, kdim, nframes, norms);
+        GCB_LAUNCHED();
+    }
+    // tiles on or above the diagonal that touch this rank's rows (directly or through the mirror)
+    for (int bi = 0; bi < nt; bi++)
+        for (int bj = bi; bj < nt; bj++) {
+            const long ia = (long)bi * BM, ib = ia + BM, ja = (long)bj * BN, jb = ja + BN;
+            const bool rows_hit = ia < row0 + nrows && ib > row0;
+            const bool mirror_hit = ja < row0 + nrows && jb > row0;
+            if (rows_hit || mirror_hit) tiles.push_back(make_int2(bi, bj));
+        }
+    AP_TRY(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    AP_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
+    AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AP_TRY(cudaEventCreate(&e0));
+    AP_TRY(cudaEventCreate(&e1));
+    AP_TRY(cudaEventRecord(e0, s));
+    allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used, row0,
+                                                                          nrows, d_tiles, d_out, nframes, 1e-7, redo);
+    GCB_LAUNCHED();
+    AP_TRY(cudaEventRecord(e1, s));
+    redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
+    GCB_LAUNCHED();
+    AP_TRY(cudaStreamSynchronize(s));
+    AP_TRY(cudaGetLastError());
+    if (gemm_ms) AP_TRY(cudaEventElapsedTime(gemm_ms, e0, e1));
+    if (redone) {
+        unsigned int c = 0;
+        AP_TRY(cudaMemcpy(&c, redo.count, sizeof c, cudaMemcpyDeviceToHost));
+        *redone = c;
+        if (c > redo.cap) {
+            set_error("all-pairs: %u near-duplicate pairs exceed the explicit-recompute list (%u)", c, redo.cap);
+            rc = GCB_ERR_ARG;
+        }
+    }
+done:
+#undef AP_TRY
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(Y); cudaFree(mu); cudaFree(norms); cudaFree(X); cudaFree(d_tiles); cudaFree(redo.count); cudaFree(redo.pairs);
+    return rc;
+}
+
+}  // namespace gcb
+
+extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows,
+                                 double* out_host, float* gemm_ms, long* redone) {
+    using namespace gcb;
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    if (first < 0 || nframes <= 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
+    if (row0 < 0 || nrows <= 0 || row0 + nrows > nframes || !out_host) { set_error("bad row block"); return GCB_ERR_ARG; }
+    if (nframes > 0xffffffffL) { set_error("too many frames"); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    int* d_idx = nullptr;
+    if (idx && nidx > 0) {
+        for (int k = 0; k < nidx; k++)
+            if (idx[k] < 0 || idx[k] >= t->natoms) { set_error("atom index %d out of range", idx[k]); return GCB_ERR_INDEXES; }
+        GCB_CUDA(cudaMalloc(&d_idx, sizeof(int) * (size_t)nidx));
+        GCB_CUDA(cudaMemcpy(d_idx, idx, sizeof(int) * (size_t)nidx, cudaMemcpyHostToDevice));
+    }
+    double* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)nrows * (size_t)nframes);
+    if (e != cudaSuccess) { cudaFree(d_idx); set_error("cudaMalloc of the %ld x %ld output block failed", nrows, nframes); return GCB_ERR_ALLOC; }
+    int rc = allpairs_device(t, first, nframes, d_idx, nidx, row0, nrows, d_out, gemm_ms, redone);
+    if (rc == GCB_OK) {
+        e = cudaMemcpy(out_host, d_out, sizeof(double) * (size_t)nrows * (size_t)nframes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("copying the RMSD matrix back failed: %s", cudaGetErrorString(e)); rc = GCB_ERR_CUDA; }
+    }
+    cudaFree(d_out);
+    cudaFree(d_idx);
+    return rc;
+}

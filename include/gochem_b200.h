@@ -124,6 +124,15 @@ int gcb_peratom_dist(gcb_traj *t, long frame, const double *ref_aos, int natoms_
 int gcb_peratom_dev_sum(gcb_traj *t, long first, long nframes, const double *ref_aos,
                         const int *idx, int nidx, int write_back, gcb_comm *comm, double *sum);
 
+/* ---- all-pairs frame RMSD matrix (BASELINE configs[3]) ----
+ * D[i][j] = chem.RMSD(frame_i, frame_j) over the atoms in idx (NULL = all), no superposition inside (geometric.go:
+ * 232-288; superpose first with gcb_super_rmsd(write_back = 1)).  Computed as one fp64 tensor-core GEMM (DMMA) on
+ * mean-centred coordinates; near-duplicate pairs are recomputed from explicit differences.  Rows [row0, row0+nrows)
+ * of the nframes x nframes matrix are written to out_host (row-major, ld = nframes): ranks of a multi-GPU run take
+ * disjoint row blocks.  gemm_ms (optional) = device time of the GEMM kernel, redone = pairs recomputed explicitly. */
+int gcb_allpairs_rmsd(gcb_traj *t, long first, long nframes, const int *idx, int nidx, long row0, long nrows,
+                      double *out_host, float *gemm_ms, long *redone);
+
 /* ---- stream timing on the stream the kernels run on ---- */
 int gcb_timer_start(gcb_traj *t);
 int gcb_timer_stop(gcb_traj *t, float *ms);
