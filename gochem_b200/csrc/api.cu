@@ -37,6 +37,7 @@ struct RefCache {
     bool centred = false;
     bool valid = false;
     double n_fit = 0.0;
+    double gb = 0.0;
     double bbar[3] = {0, 0, 0};
 };
 
@@ -105,6 +106,11 @@ int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident) {
     return GCB_OK;
 }
 
+int gcb_set_rmsd_mode(int explicit_only) {
+    set_force_explicit(explicit_only ? 1 : 0);
+    return GCB_OK;
+}
+
 int gcb_last_cluster_plan(int* out8) {
     if (!out8) return GCB_ERR_ARG;
     get_last_plan(out8);
@@ -140,7 +146,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     if (t->ev1) cudaEventDestroy(t->ev1);
     if (t->stream) cudaStreamDestroy(t->stream);
     cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
-    cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status);
+    cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
     cudaFree(t->d_devpart); cudaFree(t->d_devsum);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
     delete t;
@@ -194,6 +200,7 @@ int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj** out) {
         TRY(cudaMalloc(&t->d_rot, sizeof(double) * 9 * (size_t)cap_frames));
         TRY(cudaMalloc(&t->d_t1, sizeof(double) * 3 * (size_t)cap_frames));
         TRY(cudaMalloc(&t->d_t2, sizeof(double) * 3 * (size_t)cap_frames));
+        TRY(cudaMalloc(&t->d_flag, (size_t)cap_frames));
         TRY(cudaMalloc(&t->d_status, sizeof(int)));
         TRY(cudaMemset(t->d_status, 0, sizeof(int)));
         TRY(cudaMalloc(&t->d_devsum, sizeof(double) * (size_t)t->np));
@@ -375,11 +382,17 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
             h[2 * (size_t)np + i] = ref_aos[3 * (size_t)i + 2] - c.bbar[2];
         }
         GCB_CUDA(cudaMemcpyAsync(t->d_refc, h, sizeof(double) * 3 * (size_t)np, cudaMemcpyHostToDevice, t->stream));
+        double* w = h + 3 * (size_t)np;
         if (mode == MODE_WEIGHTED) {
-            double* w = h + 3 * (size_t)np;
             for (int k = 0; k < nidx; k++) w[idx_test[k]] += 1.0;  // multiplicity: a repeated index counts twice, as in SomeVecs
             GCB_CUDA(cudaMemcpyAsync(t->d_weight, w, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, t->stream));
         }
+        double gb = 0.0;
+        for (int i = 0; i < t->natoms; i++) {
+            const double wi = (mode == MODE_WEIGHTED) ? w[i] : 1.0;
+            gb += wi * (h[i] * h[i] + h[np + i] * h[np + i] + h[2 * (size_t)np + i] * h[2 * (size_t)np + i]);
+        }
+        c.gb = gb;
         GCB_CUDA(cudaStreamSynchronize(t->stream));
     }
     c.ref.assign(ref_aos, ref_aos + nref);
@@ -405,6 +418,8 @@ void fill_params(gcb_traj_ext* t, long first, long nframes, int write_back, Supe
     p->n_fit = t->cache.n_fit;
     p->inv_n = 1.0 / t->cache.n_fit;
     p->bbar[0] = t->cache.bbar[0]; p->bbar[1] = t->cache.bbar[1]; p->bbar[2] = t->cache.bbar[2];
+    p->gb = t->cache.gb;
+    p->need_explicit = t->d_flag + first;
     p->rmsd = t->d_rmsd + first;
     p->rot = t->d_rot + 9 * first;
     p->trans1 = t->d_t1 + 3 * first;

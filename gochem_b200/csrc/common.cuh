@@ -45,6 +45,8 @@ struct SuperParams {
     double inv_n;           // 1 / (sum of weights)
     double n_fit;           // sum of weights
     double bbar[3];         // centroid of the reference fit subset
+    double gb;              // sum w |b'|^2 (inner product of the centred template with itself)
+    unsigned char* need_explicit;  // per frame: 1 = the RMSD must come from the explicit residual (pass 2)
     double* rmsd;           // per frame (window-relative), may be nullptr
     double* rot;            // 9 per frame
     double* trans1;         // 3 per frame
@@ -81,6 +83,7 @@ struct gcb_traj {
     double* d_t1 = nullptr;
     double* d_t2 = nullptr;
     int* d_status = nullptr;
+    unsigned char* d_flag = nullptr;  // cap entries, see SuperParams::need_explicit
     // LOVO accumulation
     double* d_devpart = nullptr;
     size_t devpart_rows = 0;
@@ -107,5 +110,6 @@ int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos,
 bool cluster_kernel_supported(const gcb_traj* t);
 void set_cluster_tuning(int cluster, int stages, int depth, int resident);
 void get_last_plan(int* out8);
+void set_force_explicit(int on);
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out);
 }  // namespace gcb

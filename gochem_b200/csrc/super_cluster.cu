@@ -33,8 +33,11 @@ namespace gcb {
 
 namespace {
 
-constexpr int kConsumers = 256;          // consumer threads per CTA
-constexpr int kConsumerWarps = 8;
+#ifndef GCB_CONSUMER_WARPS
+#define GCB_CONSUMER_WARPS 8
+#endif
+constexpr int kConsumerWarps = GCB_CONSUMER_WARPS;
+constexpr int kConsumers = 32 * kConsumerWarps;   // consumer threads per CTA
 constexpr int kSolverWarps = 3;
 constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
 constexpr int kMaxStages = 8;
@@ -51,6 +54,7 @@ struct ClusterParams {
     int slots;          // NS = 2*D+1
     int nclusters;      // G
     int write_back;
+    int always_explicit;  // pass 2 runs for every frame (write-back / per-atom sums / caller's choice)
     double* epart;      // [nframes][C][8 consumer warps] squared-error partials
 };
 
@@ -163,49 +167,75 @@ struct __align__(16) Shared {
     uint64_t empty[kMaxStages];
     uint64_t part_full[kMaxSlots];        // cluster -> solver: every CTA's partial sums of a frame have landed
     uint64_t solved[kMaxSlots];           // solver -> consumers: xf[slot] holds the frame's transform
-    double partials[kMaxSlots][kMaxCluster][12];
-    double xf[kMaxSlots][16];             // R[9], centroid*R [3]
+    double partials[kMaxSlots][kMaxCluster][14];   // 12 sums + sum w|a|^2
+    double xf[kMaxSlots][16];             // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
     double red[kMaxSlots][kConsumerWarps][14];   // [..][12] = squared error of the frame D iterations earlier
     unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
 
+// sqrt of a non-negative double with a short dependency chain: hardware reciprocal-square-root seed (about 20 good
+// bits), two Newton steps (error squares each step), then x * rsqrt(x) and one residual correction.
+__device__ __forceinline__ double fast_sqrt(double x) {
+    const double xs = fmax(x, 1e-300);   // x = 0 would give inf * 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    const double hx = 0.5 * xs;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    double s = xs * y;
+    s = fma(fma(-s, s, xs), 0.5 * y, s);   // s + (x - s^2) / (2 s)
+    return x > 0.0 ? s : 0.0;
+}
+
 // pass 2 for one thread's K atom slots.  RESIDENT: the frame part is still in its shared-memory stage
 // (plane stride K*256); otherwise it is re-read from global memory, where it still sits in L2 (plane
 // stride np, streaming loads).  WB = also store the superposed coordinates.
-template <int K, bool DEV, bool WB, bool RESIDENT>
+template <int K, bool WEIGHTED, bool DEV, bool WB, bool RESIDENT>
 __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, long plane, const double* xf,
                                               const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
-                                              const double (&wk)[K], double (&dev)[K], double* frw, int np,
+                                              const double (&wk)[WEIGHTED ? K : 1], double (&dev)[DEV ? K : 1], double* frw, int np,
                                               uint32_t real_mask, uint32_t in_mask, double b0, double b1, double b2) {
-    double x[K], y[K], z[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        if (RESIDENT) {
-            x[k] = src[k * kConsumers]; y[k] = src[plane + k * kConsumers]; z[k] = src[2 * plane + k * kConsumers];
-        } else if ((in_mask >> k) & 1u) {
-            x[k] = __ldcs(src + k * kConsumers); y[k] = __ldcs(src + plane + k * kConsumers); z[k] = __ldcs(src + 2 * plane + k * kConsumers);
-        } else {
-            x[k] = 0.0; y[k] = 0.0; z[k] = 0.0;
-        }
-    }
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
+    constexpr int CH = 4;   // atoms in flight per thread: enough loads outstanding, bounded register use
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        // (a - centroid) R  computed as  a R - centroid R
-        const double qx = fma(z[k], r6, fma(y[k], r3, fma(x[k], r0, g0)));
-        const double qy = fma(z[k], r7, fma(y[k], r4, fma(x[k], r1, g1)));
-        const double qz = fma(z[k], r8, fma(y[k], r5, fma(x[k], r2, g2)));
-        const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
-        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        if (k & 1) e1 = fma(wk[k], d2, e1); else e0 = fma(wk[k], d2, e0);
-        if (DEV) dev[k] += sqrt(d2);
-        if (WB) {
-            if ((real_mask >> k) & 1u) {
-                frw[k * kConsumers] = qx + b0;
-                frw[np + k * kConsumers] = qy + b1;
-                frw[2L * np + k * kConsumers] = qz + b2;
+    for (int kb = 0; kb < K; kb += CH) {
+        double x[CH], y[CH], z[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int k = kb + c;
+            if (k >= K) { x[c] = y[c] = z[c] = 0.0; continue; }
+            if (RESIDENT) {
+                x[c] = src[k * kConsumers]; y[c] = src[plane + k * kConsumers]; z[c] = src[2 * plane + k * kConsumers];
+            } else if ((in_mask >> k) & 1u) {
+                x[c] = __ldcs(src + k * kConsumers); y[c] = __ldcs(src + plane + k * kConsumers); z[c] = __ldcs(src + 2 * plane + k * kConsumers);
+            } else {
+                x[c] = 0.0; y[c] = 0.0; z[c] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int k = kb + c;
+            if (k >= K) continue;
+            // (a - centroid) R  computed as  a R - centroid R
+            const double qx = fma(z[c], r6, fma(y[c], r3, fma(x[c], r0, g0)));
+            const double qy = fma(z[c], r7, fma(y[c], r4, fma(x[c], r1, g1)));
+            const double qz = fma(z[c], r8, fma(y[c], r5, fma(x[c], r2, g2)));
+            const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (WEIGHTED) {
+                if (k & 1) e1 = fma(wk[k], d2, e1); else e0 = fma(wk[k], d2, e0);
+            } else if ((real_mask >> k) & 1u) {   // unweighted: every real atom counts once; padding slots do not
+                if (k & 1) e1 += d2; else e0 += d2;
+            }
+            if (DEV) dev[k] += fast_sqrt(d2);
+            if (WB) {
+                if ((real_mask >> k) & 1u) {
+                    frw[k * kConsumers] = qx + b0;
+                    frw[np + k * kConsumers] = qy + b1;
+                    frw[2L * np + k * kConsumers] = qz + b2;
+                }
             }
         }
     }
@@ -247,7 +277,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (warp == kConsumerWarps + 1 && lane == 0) {
-        for (int s = 0; s < NS; s++) mbar_arrive_expect_tx(&sh.part_full[s], (uint32_t)(C * 12 * sizeof(double)));
+        for (int s = 0; s < NS; s++) mbar_arrive_expect_tx(&sh.part_full[s], (uint32_t)(C * 13 * sizeof(double)));
     }
     cluster_sync_all();   // every CTA's barriers are initialised and armed before any remote store
 
@@ -291,14 +321,14 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 mbar_wait(&sh.part_full[slot], sph);
                 if (lane == 0) TRACE(2, j);
                 double s = 0.0;
-                if (lane < 12) {
+                if (lane < 13) {
                     for (int r = 0; r < C; r++) s += sh.partials[slot][r][lane];   // rank order: identical in every CTA
                 }
-                double sums[12];
+                double sums[13];
 #pragma unroll
-                for (int k = 0; k < 12; k++) sums[k] = __shfl_sync(0xffffffffu, s, k);
+                for (int k = 0; k < 13; k++) sums[k] = __shfl_sync(0xffffffffu, s, k);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&sh.part_full[slot], (uint32_t)(C * 12 * sizeof(double)));  // re-arm for frame j+NS
+                    mbar_arrive_expect_tx(&sh.part_full[slot], (uint32_t)(C * 13 * sizeof(double)));  // re-arm for frame j+NS
                     const long f = cid + (long)j * G;
                     const double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
                     double h[9], r[9];
@@ -317,8 +347,25 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
                     xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
                     xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
+                    // RMSD without a second sweep when that is provably accurate: E = Ga + Gb - 2 tr(R^T H), the
+                    // inner-product (QCP) form.  Its rounding error is about kappa*eps*(sum w|a|^2 + Gb); it is used only when
+                    // that bound moves the RMSD by < 1e-10 A, i.e. when  kappa eps Smax <= 2e-10 sqrt(n E).  Otherwise
+                    // (frames very close to the template, e.g. the template itself) pass 2 forms the explicit residual as
+                    // the reference does (geometric.go:284-286).  Modes that run pass 2 anyway always use the explicit one.
+                    const double ga = sums[12] - (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) * p.inv_n;
+                    const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
+                                        fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
+                    const double e = ga + p.gb - 2.0 * trrh;
+                    const double smax = sums[12] + p.gb;
+                    const bool formula_ok = !cp.always_explicit && rc == 0 && e > 0.0 &&
+                                            (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
+                    xf[12] = formula_ok ? 0.0 : 1.0;
                     TRACE(3, j);
                     mbar_arrive(&sh.solved[slot]);
+                    if (rank == 0) {
+                        if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
+                        if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
+                    }
                     if (rank == 0) {
                         if (p.rot) {
 #pragma unroll
@@ -336,7 +383,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     } else {
         // ===================== consumers (warps run free of one another) =====================
         // fixed atom slots: local index tid + k*256; template and weights stay in registers
-        double bx[K], by[K], bz[K], wk[K], dev[K];
+        double bx[K], by[K], bz[K], wk[WEIGHTED ? K : 1], dev[DEV ? K : 1];
         uint32_t real_mask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -346,8 +393,8 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             bx[k] = in ? p.refc[gi] : 0.0;
             by[k] = in ? p.refc[p.np + gi] : 0.0;
             bz[k] = in ? p.refc[2L * p.np + gi] : 0.0;
-            wk[k] = (in && gi < p.natoms) ? (WEIGHTED ? p.weight[gi] : 1.0) : 0.0;
-            dev[k] = 0.0;
+            if (WEIGHTED) wk[k] = (in && gi < p.natoms) ? p.weight[gi] : 0.0;
+            if (DEV) dev[k] = 0.0;
             if (in && gi < p.natoms) real_mask |= 1u << k;   // slots that are real atoms of THIS part
         }
         const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][0]);
@@ -368,6 +415,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 double acc[12];
 #pragma unroll
                 for (int k = 0; k < 12; k++) acc[k] = 0.0;
+                double aa0 = 0.0, aa1 = 0.0;   // sum w |a|^2 for the one-pass RMSD
                 if (tid == 0) TRACE(4, j);
                 mbar_wait(&sh.full[s1], ph1);
                 if (tid == 0) TRACE(5, j);
@@ -377,6 +425,11 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
+                    {
+                        const double n2 = fma(z, z, fma(y, y, x * x));
+                        if (WEIGHTED) { if (k & 1) aa1 = fma(wk[k], n2, aa1); else aa0 = fma(wk[k], n2, aa0); }
+                        else { if (k & 1) aa1 += n2; else aa0 += n2; }
+                    }
                     if (WEIGHTED) { x *= wk[k]; y *= wk[k]; z *= wk[k]; }
                     acc[0] += x; acc[1] += y; acc[2] += z;
                     acc[3] = fma(x, bx[k], acc[3]); acc[4] = fma(x, by[k], acc[4]); acc[5] = fma(x, bz[k], acc[5]);
@@ -391,7 +444,11 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 //      the CTA's partial sums to every CTA of the cluster ----
                 double t0, t1;
                 warp_reduce12(acc, lane, t0, t1);
+                double aa = aa0 + aa1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) aa += shx(aa, o);
                 double* red = sh.red[slot1][warp];
+                if (lane == 0) red[12] = aa;
                 if ((lane & 3) == 0) {
                     const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
                     red[6 * b4 + 3 * b3 + 2 * b2] = t0;
@@ -405,7 +462,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 prev = __shfl_sync(0xffffffffu, prev, 0);
                 if (prev == kConsumerWarps - 1) {
                     __threadfence_block();
-                    if (lane < 12) {
+                    if (lane < 13) {
                         double v = 0.0;
 #pragma unroll
                         for (int w = 0; w < kConsumerWarps; w++) v += sh.red[slot1][w][lane];
@@ -423,21 +480,30 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 // ---- pass 2 of local frame j - D ----
                 mbar_wait(&sh.solved[slot2], ph2);
                 if (tid == 0) TRACE(6, j - D);
-                double e;
-                if (RESIDENT) {
+                double e = 0.0;
+                const bool run_pass2 = cp.always_explicit || sh.xf[slot2][12] != 0.0;   // warp-uniform
+                if (!run_pass2) {
+                    if (RESIDENT) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sh.empty[s2]);
+                        if (++s2 == S) s2 = 0;
+                    }
+                } else if (RESIDENT) {
                     const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
-                    if (frw) e = pass2_atoms<K, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, WEIGHTED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, WEIGHTED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
                     if (++s2 == S) s2 = 0;
                 } else {
-                    if (frw) e = pass2_atoms<K, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, WEIGHTED, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, WEIGHTED, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                 }
+                if (run_pass2) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
-                if (lane == 0) *ep = e;              // per-warp squared error; finish_rmsd_kernel adds them in fixed order
+                    for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
+                    if (lane == 0) *ep = e;          // per-warp squared error; finish_rmsd_kernel adds them in fixed order
+                }
                 ep += ep_step;
                 fr2 += fstep;
                 if (frw) frw += fstep;
@@ -459,9 +525,10 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 }
 
 __global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restrict__ epart, int C, long nframes, double inv_n,
-                                                         double* __restrict__ rmsd) {
+                                                         const unsigned char* __restrict__ need_explicit, double* __restrict__ rmsd) {
     const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
+    if (need_explicit && !need_explicit[f]) return;   // the solver already wrote the one-pass RMSD
     double s = 0.0;
     for (int r = 0; r < C * kConsumerWarps; r++) s += epart[f * C * kConsumerWarps + r];
     rmsd[f] = sqrt(s * inv_n);
@@ -472,17 +539,24 @@ struct Plan {
     size_t smem;
 };
 
-constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12};
+constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14};
 
 // tuning overrides (0 / -1 = built-in choice)
 int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0, g_tune_resident = -1;
+int g_force_explicit = 0;
 
 // Choose CTAs per frame, atoms per thread, stage count, pipeline depth.
 //  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
 //  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
 bool make_plan(int np, bool heavy, Plan* pl) {
     const size_t fixed = ((sizeof(Shared) + 127) / 128) * 128;
-    const int resident = g_tune_resident >= 0 ? g_tune_resident : 1;
+    // Measured on B200 (profiles/r1_tuning.md).  Fit-only passes skip pass 2 for almost every frame, so the stage can be
+    // released right after pass 1 (pass 2, when needed, re-reads the part from L2): two stages of the fattest part that
+    // fits win (up to 14 atoms per thread, fewest CTAs per frame, clusters of <= 3 tile the GPCs almost exactly).
+    // Passes that always run pass 2 (write-back, per-atom sums) keep the part resident in shared memory: <= 10 atoms per
+    // thread, >= 3 stages.
+    const int resident = g_tune_resident >= 0 ? g_tune_resident : (heavy ? 1 : 0);
+    const int kmax = resident ? (heavy ? 10 : 10) : 14;
     for (int c = 1; c <= kMaxCluster; c++) {
         if (g_tune_cluster && c != g_tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
@@ -490,13 +564,11 @@ bool make_plan(int np, bool heavy, Plan* pl) {
         int kinst = 0;
         for (int k : kInst) if (k >= kneed) { kinst = k; break; }
         if (!kinst) continue;
-        // Measured on B200 (profiles/r1_tuning.md): with pass 2 that also stores or takes square roots
-        // (heavy), 4 stages and depth 2 win; for the pure fit pass the fattest threads that keep 3 stages win.
-        if (!g_tune_cluster && kinst > (heavy ? 8 : 10) && c < kMaxCluster) continue;
+        if (!g_tune_cluster && kinst > kmax && c < kMaxCluster) continue;
         const size_t stage = (size_t)3 * kinst * kConsumers * sizeof(double);
         int stages = (int)((kSmemBudget - fixed) / stage);
         if (stages > kMaxStages) stages = kMaxStages;
-        if (!resident && stages > 4) stages = 4;
+        if (!resident && stages > (kinst <= 6 ? 4 : 2)) stages = (kinst <= 6 ? 4 : 2);
         if (g_tune_stages && g_tune_stages < stages) stages = g_tune_stages;
         if (stages < (resident ? 3 : 2)) continue;
         int depth;
@@ -504,7 +576,7 @@ bool make_plan(int np, bool heavy, Plan* pl) {
             depth = stages - 2 > 2 ? 2 : stages - 2;
             if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && g_tune_depth <= 6) depth = g_tune_depth;
         } else {
-            depth = 4;
+            depth = kinst <= 6 ? 2 : 1;
             if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
         }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
@@ -562,6 +634,7 @@ int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g) {
         case 8: return launch_inst<8, W, DV, RES>(t, cp, pl, g);
         case 10: return launch_inst<10, W, DV, RES>(t, cp, pl, g);
         case 12: return launch_inst<12, W, DV, RES>(t, cp, pl, g);
+        case 14: return launch_inst<14, W, DV, RES>(t, cp, pl, g);
     }
     set_error("no kernel instance for %d atoms per thread", pl.kinst);
     return GCB_ERR_ARG;
@@ -586,6 +659,8 @@ extern "C" int gcb_trace_read(long long* out) {
 
 void get_last_plan(int* out8) { for (int i = 0; i < 8; i++) out8[i] = g_last_plan[i]; }
 
+void set_force_explicit(int on) { g_force_explicit = on; }
+
 void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
     g_tune_cluster = cluster;
     g_tune_stages = stages;
@@ -600,7 +675,7 @@ bool cluster_kernel_supported(const gcb_traj* t) {
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
     Plan pl;
-    if (!make_plan(t->np, want_dev || p.frames_rw != nullptr, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    if (!make_plan(t->np, want_dev || p.frames_rw != nullptr || g_force_explicit, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     const int dev = t->dev & 15;
     const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * kConsumerWarps;
     if (need > g_epart_cap[dev]) {
@@ -620,13 +695,14 @@ int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     cp.slots = kMaxSlots;
     cp.nclusters = 0;
     cp.write_back = p.frames_rw != nullptr;
+    cp.always_explicit = (cp.write_back || want_dev || g_force_explicit) ? 1 : 0;
     cp.epart = g_epart[dev];
     int g = 0;
     int rc = pl.resident ? launch_r<true>(t, cp, pl, weighted, want_dev, &g) : launch_r<false>(t, cp, pl, weighted, want_dev, &g);
     if (rc) return rc;
     if (rows_out) *rows_out = g;
     if (p.rmsd) {
-        finish_rmsd_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, t->stream>>>(cp.epart, pl.cluster, p.nframes, p.inv_n, p.rmsd);
+        finish_rmsd_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, t->stream>>>(cp.epart, pl.cluster, p.nframes, p.inv_n, p.need_explicit, p.rmsd);
         GCB_LAUNCHED();
     }
     GCB_CUDA(cudaGetLastError());

@@ -59,6 +59,11 @@ int gcb_set_kernel_variant(int variant);
  * trails pass 1 (1..6), and where pass 2 reads the frame from (1 = its shared-memory stage, 0 = L2,
  * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice. */
 int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident);
+/* How the per-frame RMSD of a fit-only call (no write-back) is formed.  0 (default): from the inner products of
+ * the single sweep, E = Ga + Gb - 2 tr(R^T H), whenever its rounding bound moves the RMSD by < 1e-10 A, and from
+ * the explicit residual of a second sweep otherwise (frames within ~0.3 A of the template).  1: always the explicit
+ * residual, exactly as the reference computes it (geometric.go:284-286). */
+int gcb_set_rmsd_mode(int explicit_only);
 /* Shape of the last cluster-kernel launch: {CTAs per frame, atoms per CTA, atoms per thread, stages, depth,
  * resident, clusters launched, dynamic shared memory bytes}. */
 int gcb_last_cluster_plan(int *out8);

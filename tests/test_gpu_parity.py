@@ -326,3 +326,32 @@ def test_allpairs_rmsd_matrix(natoms, nframes):
     sub, _, _ = t.allpairs_rmsd(idx=idx, row0=10, nrows=20)
     assert np.abs(sub - _pairwise(aligned, idx)[10:30]).max() < 1e-9
     t.close()
+
+
+@pytest.mark.parametrize("natoms", [1500, 10000])
+def test_one_pass_rmsd_agrees_with_explicit_residual(natoms):
+    """Fit-only calls take the RMSD from the inner products of the single sweep when that is provably accurate and
+    from the explicit residual otherwise; across noise levels from 1e-7 A to 3 A both must agree with the oracle."""
+    lib = _lib.load()
+    ref = synth.make_reference(natoms)
+    rng = np.random.default_rng(5)
+    scales = np.concatenate([[0.0], np.logspace(-7, 0.5, 63)])
+    frames = np.empty((scales.size, natoms, 3))
+    for k, s in enumerate(scales):
+        q = rng.standard_normal(4); q /= np.linalg.norm(q)
+        frames[k] = (ref + rng.standard_normal((natoms, 3)) * s) @ synth.quat_to_rot(q) + rng.uniform(-50, 50, 3)
+    want, *_ = oracle.super_rmsd_traj(frames, ref, None, nthreads=8)
+    t = device_traj(frames)
+    try:
+        _lib.check(lib.gcb_set_rmsd_mode(0))
+        one = t.super_rmsd(ref)["rmsd"]
+        _lib.check(lib.gcb_set_rmsd_mode(1))
+        two = t.super_rmsd(ref)["rmsd"]
+    finally:
+        lib.gcb_set_rmsd_mode(0)
+    assert np.abs(two - want).max() < 1e-11          # explicit residual: rounding only
+    assert np.abs(one - want).max() < 5e-10          # one-pass where its bound allows, explicit elsewhere
+    assert one[0] < 1e-12                            # the template against itself goes through the explicit path
+    big = want > 1.0
+    assert big.sum() > 3 and np.abs(one[big] - want[big]).max() < 1e-10
+    t.close()

@@ -20,14 +20,19 @@ for _ in range(2):
 t.sync()
 buf = np.zeros((8, 512), dtype=np.int64)
 assert lib.gcb_trace_read(buf.ctypes.data_as(C.c_void_p)) == 0
-names = ["S:red_ready", "S:pushed", "S:parts_ready", "S:solved", "C:iter_start", "C:full_ready", "C:solved_seen", "C:red_arrive"]
+plan = _lib.last_cluster_plan()
+D = plan["depth"]
+print("plan", plan)
 sl = slice(40, 120)
-b = buf[:, sl].astype(np.float64)
-print("per-frame period (C:red_arrive):", np.diff(b[7]).mean())
-print("warp0 red_arrive -> pushed (last warp sums + st.async)", (b[1] - b[7]).mean())
-print("pushed -> S:parts_ready    ", (b[2] - b[1]).mean())
-print("S:parts_ready -> S:solved  ", (b[3] - b[2]).mean())
-print("S:solved -> C:solved_seen  ", (b[6] - b[3]).mean())
-print("total red_arrive -> solved_seen", (b[6] - b[7]).mean())
-print("C:iter_start -> full_ready (wait for data)", (b[5] - b[4]).mean())
-print("C:full_ready -> red_arrive (pass1 [+pass2 incl. solved wait] + reduce)", (b[7] - b[5]).mean())
+b = buf.astype(np.float64)
+per = np.diff(b[7, sl]).mean()
+print("per-frame period (C:red_arrive)            : %.0f" % per)
+print("C: wait for the stage (full)               : %.0f" % (b[5, sl] - b[4, sl]).mean())
+print("C: pass 1 + warp reduce (full->red_arrive) : %.0f" % (b[7, sl] - b[5, sl]).mean())
+print("   red_arrive(warp0) -> pushed (last warp) : %.0f" % (b[1, sl] - b[7, sl]).mean())
+print("S: pushed -> partials of all CTAs landed   : %.0f" % (b[2, sl] - b[1, sl]).mean())
+print("S: rank-ordered sum + 3x3 solve            : %.0f" % (b[3, sl] - b[2, sl]).mean())
+print("   solved -> consumer resumes pass 2       : %.0f" % (b[6, sl] - b[3, sl]).mean())
+print("   deliver(j) -> pass 2 of j starts        : %.0f" % (b[6, sl] - b[7, sl]).mean())
+nxt = slice(sl.start + 1, sl.stop + 1)
+print("C: pass 2 (solved_seen(j-D) -> iter_start(next)) : %.0f" % (b[4, slice(sl.start + D + 1, sl.stop + D + 1)] - b[6, sl]).mean())
