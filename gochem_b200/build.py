@@ -67,7 +67,7 @@ def build_host(force: bool = False) -> str:
     deps = srcs + [os.path.join(host, "gochem.hpp"), os.path.join(HERE, "..", "include", "gochem_host.h"),
                    os.path.join(HERE, "..", "include", "gochem_b200.h")]
     if force or _stale(HOST_LIB, deps):
-        cmd = [CXX, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_LIB, *srcs,
+        cmd = [CXX, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-o", HOST_LIB, *srcs,
                "-L" + LIB_DIR, "-lgochem_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
         subprocess.check_call(cmd)
     return HOST_LIB

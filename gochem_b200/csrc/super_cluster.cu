@@ -8,22 +8,26 @@
 //    [r*P, (r+1)*P).  The kernel is persistent: cluster g handles frames g, g+G, g+2G, ...
 //  * One producer thread per CTA streams its part of each frame (three plane segments) into a ring
 //    of S shared-memory stages with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) and an
-//    L2 evict-first policy; full/empty mbarriers hand stages to the consumers and back.
-//  * 256 consumer threads each own K fixed atom slots of the part.  The centred template b' and the
-//    weights of those slots live in REGISTERS for the whole kernel, so the template costs no
-//    shared-memory or L2 bandwidth per frame.
-//  * Pass 1 (S = sum w a, H = sum (w a) b'^T) reads the stage once; a 15-shuffle halving butterfly
-//    and a fixed-order cross-warp sum give the CTA's 12 partial sums, which 12 threads push to every
-//    CTA of the cluster with st.async (data + mbarrier complete_tx in one DSMEM transaction).
-//  * A solver warp per CTA adds the C partials in rank order (bit-identical in every CTA), solves the
-//    3x3 problem (kabsch3.cuh) and publishes R and centroid*R.
-//  * Pass 2 of a frame runs D iterations after its pass 1, from the SAME shared-memory stage, so the
-//    exchange + solve latency is hidden behind the pass 1 of the following frames.  It produces the
-//    explicit residual (RMSD), LOVO's per-atom distance sums (registers, written once at the end)
-//    and, on request, the superposed coordinates.
+//    L2 cache policy; full/empty mbarriers hand stages to the consumers and back.
+//  * 256 consumer threads (8 warps that never wait for one another) each own K fixed atom slots of
+//    the part.  The centred template b' and the weights of those slots live in REGISTERS for the
+//    whole kernel, so the template costs no shared-memory or L2 bandwidth per frame.
+//  * Pass 1 (S = sum w a, H = sum (w a) b'^T, sum w|a|^2) reads the stage once; a 15-shuffle halving
+//    butterfly gives warp totals; the last warp to arrive adds the 8 warps in fixed order and pushes the
+//    CTA's 13 partial sums to every CTA of the cluster with st.async (data + mbarrier complete_tx in one
+//    DSMEM transaction).
+//  * Solver warps add the C partials in rank order (bit-identical in every CTA), solve the 3x3
+//    problem (kabsch3.cuh), publish R and centroid*R, and decide where the RMSD comes from: the
+//    inner-product form E = Ga + Gb - 2 tr(R^T H) when its rounding bound moves the RMSD by less than
+//    1e-10 A, the explicit residual of pass 2 otherwise (frames close to the template).
+//  * Pass 2 runs only for flagged frames in fit mode, for every frame when the superposed coordinates
+//    are written back or LOVO's per-atom distances are accumulated.  It trails pass 1 by D frames so the
+//    exchange + solve latency hides behind later frames, and reads the part either from its
+//    shared-memory stage (RESIDENT) or again from L2 (the stage is then released right after pass 1,
+//    and two stages of a fat part are enough).
 //
-// Per-frame squared-error partials go to a small global array and a trailing kernel finishes
-// rmsd[f] = sqrt(sum_r E[f][r] / n) in rank order.
+// Per-warp squared-error partials of pass 2 go to a small global array and a trailing kernel finishes
+// rmsd[f] = sqrt(sum E[f][..] / n) in fixed order for the flagged frames.
 #include <cuda.h>
 
 #include "common.cuh"

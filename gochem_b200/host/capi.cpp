@@ -1,14 +1,11 @@
 // capi.cpp -- extern "C" shim of include/gochem_host.h over gochem.hpp (test plumbing for Python).
-#include <execinfo.h>
-#include <signal.h>
-#include <unistd.h>
-
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "../../include/gochem_host.h"
+#include "../csrc/kabsch3.cuh"
 #include "gochem.hpp"
 
 using namespace gochem;
@@ -65,16 +62,14 @@ size_t gch_last_error(char* buf, size_t cap) {
     return t_err.size();
 }
 int gch_last_error_is_last_frame(void) { return t_last_frame ? 1 : 0; }
-static void segv_trace(int sig) {
-    void* frames[64];
-    int n = backtrace(frames, 64);
-    backtrace_symbols_fd(frames, n, 2);
-    signal(sig, SIG_DFL);
-    raise(sig);
-}
-int gch_set_device(int dev) {
-    if (getenv("GCH_DEBUG")) signal(SIGSEGV, segv_trace);
-    return ret(chem::SetDevice(dev));
+int gch_set_device(int dev) { return ret(chem::SetDevice(dev)); }
+
+// The 3x3 rotation solve the kernels use (csrc/kabsch3.cuh is host + device code): exposed so the CPU tests can
+// check it against LAPACK.  which: 0 = the kernels' choice (polar Newton, Jacobi fallback), 1 = Jacobi, 2 = polar.
+int gch_kabsch3(const double* h, double* rot, int which) {
+    if (which == 1) return k3::kabsch3_jacobi(h, rot);
+    if (which == 2) return k3::kabsch3_polar(h, rot) ? 0 : 1;
+    return k3::kabsch3(h, rot);
 }
 
 int gch_super(double* test, int ntest, const double* templa, int ntempla, const int* i0, int n0, const int* i1, int n1, int nlists) {
@@ -242,21 +237,18 @@ int gch_lovo(const char* path, const double* ref, int natoms, const char* const*
     align::LOVOReturn r;
     Error e = align::LOVO(top, mat(ref, natoms), path, &r, o.get());
     if (e) return fail(e);
-    if (getenv("GCH_DEBUG")) fprintf(stderr, "[gch_lovo] returned N=%d nrmsd=%zu\n", r.N, r.RMSD.size());
     *N = r.N;
     *frames = r.FramesRead;
     *iterations = r.Iterations;
     *nrmsd = (int)r.RMSD.size();
     for (int i = 0; i < r.N; i++) natoms_out[i] = r.Natoms[(size_t)i];
     for (size_t i = 0; i < r.RMSD.size(); i++) rmsd_out[i] = r.RMSD[i];
-    if (getenv("GCH_DEBUG")) fprintf(stderr, "[gch_lovo] outputs written, text=%p cap=%zu\n", (void*)text, text_cap);
     if (text && text_cap) {
         std::string s = r.PyMOLSel() + "\n" + r.GMX("A") + "\n" + r.String();
         size_t n = s.size() < text_cap - 1 ? s.size() : text_cap - 1;
         memcpy(text, s.data(), n);
         text[n] = 0;
     }
-    if (getenv("GCH_DEBUG")) fprintf(stderr, "[gch_lovo] text written\n");
     return 0;
 }
 

@@ -16,6 +16,11 @@ size_t gch_last_error(char *buf, size_t cap);
 int gch_last_error_is_last_frame(void);
 int gch_set_device(int dev);
 
+/* The 3x3 rotation solve of the kernels (gochem_b200/csrc/kabsch3.cuh, host build): h and rot row-major, rot
+ * right-multiplies row vectors.  which: 0 = kernels' choice, 1 = one-sided Jacobi SVD, 2 = polar Newton (returns 1
+ * when it declines: det h <= 0 or near-singular). */
+int gch_kabsch3(const double *h, double *rot, int which);
+
 /* chem.Super (handy.go:175-214): nlists = number of index slices the Go caller passes (0, 1 or 2).
  * test (ntest x 3, row-major) is modified in place. */
 int gch_super(double *test, int ntest, const double *templa, int ntempla, const int *idx0, int n0,

@@ -182,3 +182,51 @@ def test_sharded_lovo_two_ranks_gloo(tmp_path):
         assert list(r["Natoms"]) == list(want["Natoms"])
         assert np.abs(r["RMSD"] - want["RMSD"]).max() < 1e-12
     assert np.array_equal(r0["RMSD"], r1["RMSD"])  # bit-identical across ranks
+
+
+def test_kernel_rotation_solver_against_lapack():
+    """csrc/kabsch3.cuh (the 3x3 solve the CUDA kernels run, compiled for the host here) against LAPACK gesvd with the
+    reference's reflection fix (geometric.go:174-190)."""
+    import ctypes as C
+
+    import scipy.linalg as sla
+
+    lib = H.load()
+    rng = np.random.default_rng(4)
+
+    def solve(h, which):
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        r = np.zeros((3, 3))
+        rc = lib.gch_kabsch3(h.ctypes.data_as(C.POINTER(C.c_double)), r.ctypes.data_as(C.POINTER(C.c_double)), which)
+        return rc, r
+
+    npolar = nrefl = 0
+    for k in range(3000):
+        if k % 2:
+            a = rng.standard_normal((40, 3)) * 12 * rng.uniform(0.1, 1, 3)
+            b = a + rng.standard_normal((40, 3)) * rng.uniform(0, 3)
+            if k % 10 == 1:
+                b = b * np.array([1.0, 1.0, -1.0])          # mirror image: forces the reflection branch
+            h = (a - a.mean(0)).T @ (b - b.mean(0))
+        else:
+            h = rng.standard_normal((3, 3)) * rng.uniform(1e-3, 1e6)
+        u, s, vt = sla.svd(h, lapack_driver="gesvd")
+        want = u @ vt
+        if np.linalg.det(want) < 0:
+            want = u @ np.diag([1.0, 1.0, -1.0]) @ vt
+            nrefl += 1
+        gap = (s[1] + s[2]) / s[0] if np.linalg.det(h) > 0 else (s[1] - s[2]) / s[0]
+        if gap < 1e-3:
+            continue                                          # rotation not unique enough to compare
+        rc, r = solve(h, 0)
+        assert rc == 0 and np.abs(r - want).max() < 1e-10 / min(1.0, gap)
+        assert np.abs(r @ r.T - np.eye(3)).max() < 1e-13 and np.linalg.det(r) > 0
+        rc, rj = solve(h, 1)
+        assert rc == 0 and np.abs(rj - want).max() < 1e-10 / min(1.0, gap)
+        rc, rp = solve(h, 2)
+        if rc == 0:
+            npolar += 1
+            assert np.linalg.det(h) > 0 and np.abs(rp - want).max() < 1e-10 / min(1.0, gap)
+    assert npolar > 1000 and nrefl > 300
+    # non-finite input is the reference's "mat.SVD failed"
+    assert solve(np.full((3, 3), np.nan), 0)[0] == -4
