@@ -355,3 +355,40 @@ def test_one_pass_rmsd_agrees_with_explicit_residual(natoms):
     big = want > 1.0
     assert big.sum() > 3 and np.abs(one[big] - want[big]).max() < 1e-10
     t.close()
+
+
+@pytest.mark.parametrize("natoms", [1, 2, 3, 4])
+def test_degenerate_atom_counts_do_not_nan(natoms):
+    """Fewer than 3 atoms make the rotation non-unique (SURVEY.md §7 'degenerate inputs'); the solver must still
+    return a proper rotation and the RMSD of the best fit."""
+    rng = np.random.default_rng(natoms)
+    ref = rng.standard_normal((natoms, 3)) * 5
+    frames = rng.standard_normal((6, natoms, 3)) * 5
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, write_back=True)
+    assert np.isfinite(out["rmsd"]).all() and np.isfinite(out["rot"]).all()
+    rr = out["rot"]
+    assert np.abs(np.einsum("fij,fkj->fik", rr, rr) - np.eye(3)).max() < 1e-12
+    assert (np.linalg.det(rr) > 0.999).all()
+    want, *_ = oracle.super_rmsd_traj(frames, ref, None)
+    assert np.abs(out["rmsd"] - want).max() < 1e-9      # the minimum is unique even when the rotation is not
+    t.close()
+
+
+def test_single_frame_and_larger_than_cluster_capacity():
+    # one frame: the persistent kernel launches a single cluster
+    ref, frames = synth.make_case(2000, 1)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref)
+    want, rot, *_ = oracle.super_rmsd_traj(frames, ref, None)
+    assert abs(out["rmsd"][0] - want[0]) < TOL_RMSD and np.abs(out["rot"] - rot).max() < TOL_ROT
+    t.close()
+    # 30,000 atoms exceed what 8 CTAs x 256 threads x 14 slots hold: the library falls back to the generic kernel
+    ref, frames = synth.make_case(30000, 3)
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, write_back=True)
+    want, rot, *_ = oracle.super_rmsd_traj(frames, ref, None, nthreads=4)
+    assert np.abs(out["rmsd"] - want).max() < TOL_RMSD and np.abs(out["rot"] - rot).max() < TOL_ROT
+    dev = t.peratom_dev_sum(ref)
+    assert np.isfinite(dev).all()
+    t.close()
