@@ -178,17 +178,16 @@ struct __align__(16) Shared {
 };
 
 // sqrt of a non-negative double with a short dependency chain: hardware reciprocal-square-root seed (about 20 good
-// bits), two Newton steps (error squares each step), then x * rsqrt(x) and one residual correction.
+// bits) and two Newton steps (the error squares each step: ~2^-77), then x * rsqrt(x).  A denormal-sized offset keeps
+// x = 0 away from inf * 0; it changes no representable result above 1e-290.
 __device__ __forceinline__ double fast_sqrt(double x) {
-    const double xs = fmax(x, 1e-300);   // x = 0 would give inf * 0
+    const double xs = x + 1e-300;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
     const double hx = 0.5 * xs;
     y = y * fma(-hx * y, y, 1.5);
     y = y * fma(-hx * y, y, 1.5);
-    double s = xs * y;
-    s = fma(fma(-s, s, xs), 0.5 * y, s);   // s + (x - s^2) / (2 s)
-    return x > 0.0 ? s : 0.0;
+    return xs * y;
 }
 
 // pass 2 for one thread's K atom slots.  RESIDENT: the frame part is still in its shared-memory stage
@@ -429,7 +428,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
-                    {
+                    if (!DEV) {   // only the one-pass RMSD needs sum w|a|^2; the per-atom-distance pass always runs pass 2
                         const double n2 = fma(z, z, fma(y, y, x * x));
                         if (WEIGHTED) { if (k & 1) aa1 = fma(wk[k], n2, aa1); else aa0 = fma(wk[k], n2, aa0); }
                         else { if (k & 1) aa1 += n2; else aa0 += n2; }
@@ -449,8 +448,10 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 double t0, t1;
                 warp_reduce12(acc, lane, t0, t1);
                 double aa = aa0 + aa1;
+                if (!DEV) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) aa += shx(aa, o);
+                    for (int o = 16; o > 0; o >>= 1) aa += shx(aa, o);
+                }
                 double* red = sh.red[slot1][warp];
                 if (lane == 0) red[12] = aa;
                 if ((lane & 3) == 0) {
