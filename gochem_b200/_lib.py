@@ -73,6 +73,7 @@ def load() -> C.CDLL:
         "gcb_peratom_dist": (I, [P, L, P, I, P, P, I, P]),
         "gcb_peratom_dev_sum": (I, [P, L, L, P, P, I, I, P, P]),
         "gcb_allpairs_rmsd": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
+        "gcb_allpairs_rmsd_fit": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_timer_start": (I, [P]),
         "gcb_timer_stop": (I, [P, C.POINTER(C.c_float)]),
         "gcb_sync": (I, [P]),
@@ -272,14 +273,14 @@ class DeviceTraj:
                                            comm.h if comm else None, _ptr(out)))
         return out
 
-    def allpairs_rmsd(self, idx=None, first=0, nframes=None, row0=0, nrows=None):
+    def allpairs_rmsd(self, idx=None, first=0, nframes=None, row0=0, nrows=None, fit=False):
         n = self.nframes - first if nframes is None else nframes
         nr = n - row0 if nrows is None else nrows
         it = _idx(idx)
         out = np.empty((nr, n))
         ms, redone = C.c_float(0), C.c_long(0)
-        check(self.lib.gcb_allpairs_rmsd(self.h, first, n, _ptr(it), 0 if it is None else it.size, row0, nr, _ptr(out),
-                                         C.byref(ms), C.byref(redone)))
+        fn = self.lib.gcb_allpairs_rmsd_fit if fit else self.lib.gcb_allpairs_rmsd
+        check(fn(self.h, first, n, _ptr(it), 0 if it is None else it.size, row0, nr, _ptr(out), C.byref(ms), C.byref(redone)))
         return out, ms.value, redone.value
 
     # --- timing on the library's stream ---

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kabsch3.cuh"
 
 namespace gcb {
 
@@ -88,6 +89,19 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restri
             v = frames[f * stride + (long)plane * np + idx[k]];
         }
         out[g] = v;
+    }
+}
+
+// gather a subset of atoms keeping the plane layout: out[f][c][k] = frame f plane c atom idx[k], plane stride ncols
+__global__ void __launch_bounds__(256) gather_planes_kernel(const double* __restrict__ frames, long stride, int np,
+                                                           const int* __restrict__ idx, int nidx, int ncols, long nframes,
+                                                           double* __restrict__ out) {
+    const long total = nframes * 3L * ncols;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const long f = g / (3L * ncols);
+        const int rem = (int)(g - f * 3L * ncols);
+        const int plane = rem / ncols, k = rem - plane * ncols;
+        out[g] = k < nidx ? frames[f * stride + (long)plane * np + idx[k]] : 0.0;
     }
 }
 
@@ -223,23 +237,238 @@ __global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant (ii): RMSD after the optimal superposition of every pair.  With every frame centred on its own centroid,
+// the 3x3 correlation of frames i and j is H_ij = Y_i^T Y_j, i.e. the (3i..3i+2, 3j..3j+2) block of Z Z^T where Z is
+// the (3F) x n matrix whose rows are the coordinate planes -- exactly how frames are stored.  The minimum over
+// rotations of ||Y_i R - Y_j||^2 is G_i + G_j - 2 tr(R^T H_ij) with R from the same 3x3 solve as everywhere else
+// (kabsch3.cuh; geometric.go:154-190), evaluated per pair in the epilogue.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FT = 32;              // frames per tile side
+constexpr int FM = 3 * FT;          // 96 rows
+constexpr int FLDC = FM + 1;        // padded row of the staged C tile
+
+// rows = planes: Zc[(3f+c)][k] = frame f plane c minus that plane's mean over the used atoms; norms[f] = sum |.|^2
+__global__ void __launch_bounds__(256) centre_frames_kernel(const double* __restrict__ X, long ldrow, int ncols_used, int ncols,
+                                                           long nframes, double* __restrict__ Z, double* __restrict__ norms) {
+    __shared__ double red[8][4];
+    __shared__ double cen[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const double* x = X + f * 3 * ldrow;
+        double s[3] = {0, 0, 0};
+        for (int k = threadIdx.x; k < ncols_used; k += 256) { s[0] += x[k]; s[1] += x[ldrow + k]; s[2] += x[2 * ldrow + k]; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_down_sync(0xffffffffu, s[c], o);
+            if (lane == 0) red[warp][c] = s[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+            cen[threadIdx.x] = t / (double)ncols_used;
+        }
+        __syncthreads();
+        double* z = Z + f * 3 * (long)ncols;
+        double g = 0.0;
+        for (int k = threadIdx.x; k < ncols; k += 256) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double v = k < ncols_used ? x[c * ldrow + k] - cen[c] : 0.0;
+                z[(long)c * ncols + k] = v;
+                g = fma(v, v, g);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_down_sync(0xffffffffu, g, o);
+        if (lane == 0) red[warp][3] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w][3];
+            norms[f] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
+                         long row0, long nrows, const int2* __restrict__ tiles, double* __restrict__ D, long ldd, double floor_rel,
+                         PairList redo) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;                               // [STAGES][FM][LDS]
+    double* sB = smem + (size_t)STAGES * FM * LDS;    // [STAGES][FM][LDS]
+    const int2 tile = tiles[blockIdx.x];
+    const long fi0 = (long)tile.x * FT, fj0 = (long)tile.y * FT;   // first frames of the tile
+    const long nrow_total = 3 * nframes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;         // 2 x 4 warps -> 48 x 24 warp tiles
+    const int g = lane >> 2, t = lane & 3;
+    double acc[6][3][2];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int nk = (kdim + BK - 1) / BK;
+    auto load_stage = [&](int stage, int kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int chunk = tid + r * GEMM_THREADS;   // 0..767: 96 rows x 8 chunks of 2 doubles
+            const int row = chunk >> 3, kc = (chunk & 7) * 2;
+            const bool kin = k0 + kc < kdim;
+            {
+                const long gr = 3 * fi0 + row;
+                const bool ok = kin && gr < nrow_total;
+                cp_async16(sA + ((size_t)stage * FM + row) * LDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
+            }
+            {
+                const long gr = 3 * fj0 + row;
+                const bool ok = kin && gr < nrow_total;
+                cp_async16(sB + ((size_t)stage * FM + row) * LDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double* a = sA + ((size_t)(kt % STAGES) * FM + wm * 48) * LDS;
+        const double* b = sB + ((size_t)(kt % STAGES) * FM + wn * 24) * LDS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[6], bf[3];
+#pragma unroll
+            for (int mi = 0; mi < 6; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
+#pragma unroll
+            for (int ni = 0; ni < 3; ni++) bf[ni] = b[(ni * 8 + g) * LDS + kk + t];
+#pragma unroll
+            for (int mi = 0; mi < 6; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 3; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // everyone is done with the pipeline buffers: reuse them for the C tile
+    double* sC = smem;  // [FM][FLDC]
+#pragma unroll
+    for (int mi = 0; mi < 6; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 3; ni++) {
+            const int r = wm * 48 + mi * 8 + g, c = wn * 24 + ni * 8 + 2 * t;
+            sC[r * FLDC + c] = acc[mi][ni][0];
+            sC[r * FLDC + c + 1] = acc[mi][ni][1];
+        }
+    __syncthreads();
+    // one 3x3 problem per frame pair of the tile: 1024 pairs, 4 per thread
+    for (int pidx = tid; pidx < FT * FT; pidx += GEMM_THREADS) {
+        const int pi = pidx / FT, pj = pidx % FT;
+        const long i = fi0 + pi, j = fj0 + pj;
+        if (i >= nframes || j >= nframes) continue;
+        if (tile.x == tile.y && j < i) continue;   // the diagonal tile holds both orders; keep one
+        double d;
+        if (i == j) {
+            d = 0.0;
+        } else {
+            double h[9], r[9];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) h[3 * a + b] = sC[(3 * pi + a) * FLDC + 3 * pj + b];
+            if (k3::kabsch3(h, r) != 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+            }
+            double tr = 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) tr = fma(r[k], h[k], tr);
+            const double gi = norms[i], gj = norms[j];
+            const double d2 = (gi + gj - 2.0 * tr) * inv_n;
+            if (d2 < floor_rel * (gi + gj) * inv_n) {
+                const unsigned int slot = atomicAdd(redo.count, 1u);
+                if (slot < redo.cap) redo.pairs[slot] = make_uint2((unsigned int)i, (unsigned int)j);
+            }
+            d = sqrt(d2 > 0.0 ? d2 : 0.0);
+        }
+        if (i >= row0 && i < row0 + nrows) D[(i - row0) * ldd + j] = d;
+        if (j != i && j >= row0 && j < row0 + nrows) D[(j - row0) * ldd + i] = d;
+    }
+}
+
+// flagged pairs again, from explicit sums: H by direct dot products, R, then sum |y_i R - y_j|^2 -- one warp per pair
+__global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __restrict__ Z, int kdim, double inv_n, PairList redo,
+                                                            long row0, long nrows, double* __restrict__ D, long ldd) {
+    const unsigned int n = min(*redo.count, redo.cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < n; p += gridDim.x * 8) {
+        const uint2 ij = redo.pairs[p];
+        const double* a = Z + (long)ij.x * 3 * kdim;
+        const double* b = Z + (long)ij.y * 3 * kdim;
+        double h[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) h[k] = 0.0;
+        for (int c = lane; c < kdim; c += 32) {
+            const double ax = a[c], ay = a[kdim + c], az = a[2L * kdim + c];
+            const double bx = b[c], by = b[kdim + c], bz = b[2L * kdim + c];
+            h[0] = fma(ax, bx, h[0]); h[1] = fma(ax, by, h[1]); h[2] = fma(ax, bz, h[2]);
+            h[3] = fma(ay, bx, h[3]); h[4] = fma(ay, by, h[4]); h[5] = fma(ay, bz, h[5]);
+            h[6] = fma(az, bx, h[6]); h[7] = fma(az, by, h[7]); h[8] = fma(az, bz, h[8]);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            for (int o = 16; o > 0; o >>= 1) h[k] += __shfl_xor_sync(0xffffffffu, h[k], o);
+        double r[9];
+        if (k3::kabsch3(h, r) != 0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+        }
+        double s = 0.0;
+        for (int c = lane; c < kdim; c += 32) {
+            const double ax = a[c], ay = a[kdim + c], az = a[2L * kdim + c];
+            const double dx = fma(az, r[6], fma(ay, r[3], ax * r[0])) - b[c];
+            const double dy = fma(az, r[7], fma(ay, r[4], ax * r[1])) - b[kdim + c];
+            const double dz = fma(az, r[8], fma(ay, r[5], ax * r[2])) - b[2L * kdim + c];
+            s = fma(dz, dz, fma(dy, dy, fma(dx, dx, s)));
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double d = sqrt(s * inv_n);
+            if ((long)ij.x >= row0 && (long)ij.x < row0 + nrows) D[((long)ij.x - row0) * ldd + ij.y] = d;
+            if ((long)ij.y >= row0 && (long)ij.y < row0 + nrows) D[((long)ij.y - row0) * ldd + ij.x] = d;
+        }
+    }
+}
+
 }  // namespace
 
 // Device-side driver.  Y source: the trajectory planes themselves (idx == nullptr: rows of 3*np doubles, padding
 // zeros) or a gathered subset.  Computes rows [row0, row0 + nrows) of the F x F matrix into d_out (ld = nframes).
 int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int nidx, long row0, long nrows, double* d_out,
-                    float* gemm_ms, long* redone) {
+                    float* gemm_ms, long* redone, bool fit) {
     cudaStream_t s = t->stream;
     const int natoms_used = d_idx ? nidx : t->natoms;
-    const int kdim = d_idx ? round_up(3 * nidx, 2) : 3 * t->np;
+    // (i): one row per frame, 3n columns.  (ii): three rows (planes) per frame, n columns.
+    const int kdim = fit ? (d_idx ? round_up(nidx, 2) : t->np) : (d_idx ? round_up(3 * nidx, 2) : 3 * t->np);
     const long ld = kdim;
     double *Y = nullptr, *mu = nullptr, *norms = nullptr, *X = nullptr;
     int2* d_tiles = nullptr;
     PairList redo{nullptr, nullptr, 1u << 22};
     int rc = GCB_OK;
     std::vector<int2> tiles;
-    const int nt = (int)((nframes + BM - 1) / BM);
-    const size_t smem = sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
+    const int tile_frames = fit ? FT : BM;
+    const int nt = (int)((nframes + tile_frames - 1) / tile_frames);
+    const size_t smem = fit ? sizeof(double) * (size_t)STAGES * 2 * FM * LDS : sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 #define AP_TRY(call)                                                                              \
     do {                                                                                          \
@@ -250,7 +479,7 @@ int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int
             goto done;                                                                            \
         }                                                                                         \
     } while (0)
-    AP_TRY(cudaMalloc(&Y, sizeof(double) * (size_t)nframes * (size_t)ld));
+    AP_TRY(cudaMalloc(&Y, sizeof(double) * (size_t)nframes * (size_t)(fit ? 3 * ld : ld)));
     AP_TRY(cudaMalloc(&mu, sizeof(double) * (size_t)kdim));
     AP_TRY(cudaMalloc(&norms, sizeof(double) * (size_t)nframes));
     AP_TRY(cudaMalloc(&redo.count, sizeof(unsigned int)));
@@ -259,38 +488,65 @@ int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int
     {
         const double* src = t->d_frames + first * 3L * t->np;
         long ldx = 3L * t->np;
-        if (d_idx) {
-            AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * (size_t)ld));
-            gather_rows_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
+        if (fit) {
+            long ldrow = t->np;   // plane stride inside a frame
+            int used = t->natoms;
+            if (d_idx) {
+                // gather the subset into packed planes [x(idx) | y(idx) | z(idx)] with plane stride kdim
+                AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * 3 * (size_t)kdim));
+                gather_planes_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
+                GCB_LAUNCHED();
+                src = X;
+                ldrow = kdim;
+                used = nidx;
+            }
+            centre_frames_kernel<<<t->sm_count * 4, 256, 0, s>>>(src, ldrow, used, kdim, nframes, Y, norms);
             GCB_LAUNCHED();
-            src = X;
-            ldx = ld;
+        } else {
+            if (d_idx) {
+                AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * (size_t)ld));
+                gather_rows_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
+                GCB_LAUNCHED();
+                src = X;
+                ldx = ld;
+            }
+            col_mean_kernel<<<(kdim + 255) / 256, 256, 0, s>>>(src, ldx, kdim, nframes, mu);
+            GCB_LAUNCHED();
+            centre_rows_kernel<<<t->sm_count * 4, 256, 0, s>>>(src, ldx, mu, Y, ld, kdim, nframes, norms);
+            GCB_LAUNCHED();
         }
-        col_mean_kernel<<<(kdim + 255) / 256, 256, 0, s>>>(src, ldx, kdim, nframes, mu);
-        GCB_LAUNCHED();
-        centre_rows_kernel<<<t->sm_count * 4, 256, 0, s>>>(src, ldx, mu, Y, ld, kdim, nframes, norms);
-        GCB_LAUNCHED();
     }
     // tiles on or above the diagonal that touch this rank's rows (directly or through the mirror)
     for (int bi = 0; bi < nt; bi++)
         for (int bj = bi; bj < nt; bj++) {
-            const long ia = (long)bi * BM, ib = ia + BM, ja = (long)bj * BN, jb = ja + BN;
+            const long ia = (long)bi * tile_frames, ib = ia + tile_frames, ja = (long)bj * tile_frames, jb = ja + tile_frames;
             const bool rows_hit = ia < row0 + nrows && ib > row0;
             const bool mirror_hit = ja < row0 + nrows && jb > row0;
             if (rows_hit || mirror_hit) tiles.push_back(make_int2(bi, bj));
         }
     AP_TRY(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
     AP_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
-    AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AP_TRY(cudaEventCreate(&e0));
     AP_TRY(cudaEventCreate(&e1));
-    AP_TRY(cudaEventRecord(e0, s));
-    allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used, row0,
-                                                                          nrows, d_tiles, d_out, nframes, 1e-7, redo);
-    GCB_LAUNCHED();
-    AP_TRY(cudaEventRecord(e1, s));
-    redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
-    GCB_LAUNCHED();
+    if (fit) {
+        AP_TRY(cudaFuncSetAttribute(allpairs_fit_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AP_TRY(cudaEventRecord(e0, s));
+        allpairs_fit_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                                  row0, nrows, d_tiles, d_out, nframes, 1e-7, redo);
+        GCB_LAUNCHED();
+        AP_TRY(cudaEventRecord(e1, s));
+        redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
+        GCB_LAUNCHED();
+    } else {
+        AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AP_TRY(cudaEventRecord(e0, s));
+        allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used, row0,
+                                                                              nrows, d_tiles, d_out, nframes, 1e-7, redo);
+        GCB_LAUNCHED();
+        AP_TRY(cudaEventRecord(e1, s));
+        redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
+        GCB_LAUNCHED();
+    }
     AP_TRY(cudaStreamSynchronize(s));
     AP_TRY(cudaGetLastError());
     if (gemm_ms) AP_TRY(cudaEventElapsedTime(gemm_ms, e0, e1));
@@ -313,13 +569,13 @@ done:
 
 }  // namespace gcb
 
-extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows,
-                                 double* out_host, float* gemm_ms, long* redone) {
+static int allpairs_entry(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows, double* out_host,
+                          float* gemm_ms, long* redone, bool fit) {
     using namespace gcb;
     if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
     if (first < 0 || nframes <= 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
     if (row0 < 0 || nrows <= 0 || row0 + nrows > nframes || !out_host) { set_error("bad row block"); return GCB_ERR_ARG; }
-    if (nframes > 0xffffffffL) { set_error("too many frames"); return GCB_ERR_ARG; }
+    if (nframes > 0x3fffffffL) { set_error("too many frames"); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     int* d_idx = nullptr;
     if (idx && nidx > 0) {
@@ -331,7 +587,7 @@ extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const in
     double* d_out = nullptr;
     cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)nrows * (size_t)nframes);
     if (e != cudaSuccess) { cudaFree(d_idx); set_error("cudaMalloc of the %ld x %ld output block failed", nrows, nframes); return GCB_ERR_ALLOC; }
-    int rc = allpairs_device(t, first, nframes, d_idx, nidx, row0, nrows, d_out, gemm_ms, redone);
+    int rc = allpairs_device(t, first, nframes, d_idx, nidx, row0, nrows, d_out, gemm_ms, redone, fit);
     if (rc == GCB_OK) {
         e = cudaMemcpy(out_host, d_out, sizeof(double) * (size_t)nrows * (size_t)nframes, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("copying the RMSD matrix back failed: %s", cudaGetErrorString(e)); rc = GCB_ERR_CUDA; }
@@ -339,4 +595,14 @@ extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const in
     cudaFree(d_out);
     cudaFree(d_idx);
     return rc;
+}
+
+extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows,
+                                 double* out_host, float* gemm_ms, long* redone) {
+    return allpairs_entry(t, first, nframes, idx, nidx, row0, nrows, out_host, gemm_ms, redone, false);
+}
+
+extern "C" int gcb_allpairs_rmsd_fit(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows,
+                                     double* out_host, float* gemm_ms, long* redone) {
+    return allpairs_entry(t, first, nframes, idx, nidx, row0, nrows, out_host, gemm_ms, redone, true);
 }

@@ -138,6 +138,12 @@ int gcb_peratom_dev_sum(gcb_traj *t, long first, long nframes, const double *ref
 int gcb_allpairs_rmsd(gcb_traj *t, long first, long nframes, const int *idx, int nidx, long row0, long nrows,
                       double *out_host, float *gemm_ms, long *redone);
 
+/* Same matrix with the optimal superposition of every pair: D[i][j] = chem.RMSD(chem.Super(frame_i, frame_j), frame_j)
+ * (handy.go:175-214 + geometric.go:232-288 for each of the F^2 pairs).  The 3x3 correlation blocks of all pairs come out
+ * of one DMMA GEMM over the coordinate planes; the rotation solve and the RMSD run per pair in its epilogue. */
+int gcb_allpairs_rmsd_fit(gcb_traj *t, long first, long nframes, const int *idx, int nidx, long row0, long nrows,
+                          double *out_host, float *gemm_ms, long *redone);
+
 /* ---- stream timing on the stream the kernels run on ---- */
 int gcb_timer_start(gcb_traj *t);
 int gcb_timer_stop(gcb_traj *t, float *ms);

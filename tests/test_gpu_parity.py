@@ -392,3 +392,31 @@ def test_single_frame_and_larger_than_cluster_capacity():
     dev = t.peratom_dev_sum(ref)
     assert np.isfinite(dev).all()
     t.close()
+
+
+@pytest.mark.parametrize("natoms,nframes", [(60, 45), (400, 100)])
+def test_allpairs_rmsd_matrix_with_per_pair_fit(natoms, nframes):
+    """Variant (ii) of BASELINE configs[3]: every pair optimally superposed first, D_ij = RMSD(Super(X_i, X_j), X_j)."""
+    ref, frames = synth.make_case(natoms, nframes)
+    frames[5] = frames[2] @ synth.quat_to_rot(np.array([0.5, 0.5, 0.5, 0.5])) + 3.0     # rigid copy: distance 0 after the fit
+    t = device_traj(frames)
+    got, ms, redone = t.allpairs_rmsd(fit=True)
+    assert np.array_equal(got, got.T) and (np.diag(got) == 0).all()
+    assert got[2, 5] < 1e-10 and redone >= 1
+    rng = np.random.default_rng(0)
+    pairs = [(1, 4), (0, nframes - 1), (7, 33)] + [tuple(rng.integers(0, nframes, 2)) for _ in range(60)]
+    for i, j in pairs:
+        if i == j:
+            continue
+        s = oracle.super_(frames[i], frames[j])
+        assert abs(got[i, j] - oracle.rmsd(s, frames[j])) < 1e-9
+    # fitted distances never exceed the unfitted ones of the same frames
+    plain, _, _ = t.allpairs_rmsd()
+    assert (got <= plain + 1e-9).all()
+    # subset of atoms, row block
+    idx = np.arange(0, natoms, 2)
+    sub, _, _ = t.allpairs_rmsd(idx=idx, row0=3, nrows=9, fit=True)
+    for i, j in [(3, 0), (5, 40), (11, 12)]:
+        s = oracle.super_(frames[i][idx], frames[j][idx])
+        assert abs(sub[i - 3, j] - oracle.rmsd(s, frames[j][idx])) < 1e-9
+    t.close()
