@@ -581,7 +581,7 @@ bool make_plan(int np, bool heavy, Plan* pl) {
             depth = stages - 2 > 2 ? 2 : stages - 2;
             if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && g_tune_depth <= 6) depth = g_tune_depth;
         } else {
-            depth = kinst <= 6 ? 2 : 1;
+            depth = kinst <= 6 ? 6 : 3;   // costs no shared memory here: only the exchange slots
             if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
         }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
