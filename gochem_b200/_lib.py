@@ -74,6 +74,7 @@ def load() -> C.CDLL:
         "gcb_peratom_dev_sum": (I, [P, L, L, P, P, I, I, P, P]),
         "gcb_allpairs_rmsd": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_allpairs_rmsd_fit": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
+        "gcb_moments": (I, [P, L, L, P, P, I, P, P]),
         "gcb_timer_start": (I, [P]),
         "gcb_timer_stop": (I, [P, C.POINTER(C.c_float)]),
         "gcb_sync": (I, [P]),
@@ -282,6 +283,15 @@ class DeviceTraj:
         fn = self.lib.gcb_allpairs_rmsd_fit if fit else self.lib.gcb_allpairs_rmsd
         check(fn(self.h, first, n, _ptr(it), 0 if it is None else it.size, row0, nr, _ptr(out), C.byref(ms), C.byref(redone)))
         return out, ms.value, redone.value
+
+    def moments(self, mass=None, idx=None, first=0, nframes=None):
+        """chem.CenterOfMass + chem.MomentTensor for every frame -> (F x 3, F x 3 x 3)."""
+        n = self.nframes - first if nframes is None else nframes
+        m = None if mass is None else np.ascontiguousarray(mass, dtype=np.float64)
+        it = _idx(idx)
+        cen, mom = np.empty((n, 3)), np.empty((n, 3, 3))
+        check(self.lib.gcb_moments(self.h, first, n, _ptr(m), _ptr(it), 0 if it is None else it.size, _ptr(cen), _ptr(mom)))
+        return cen, mom
 
     # --- timing on the library's stream ---
     def timer_start(self):

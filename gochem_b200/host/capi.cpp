@@ -108,6 +108,17 @@ int gch_rotator_translator_to_super(const double* test, const double* templa, in
     return 0;
 }
 
+int gch_center_and_moment(const double* a, int n, const double* mass, double* center, double* moment) {
+    std::vector<double> m;
+    if (mass) m.assign(mass, mass + n);
+    v3::Matrix c, mo;
+    if (Error e = chem::CenterOfMass(mat(a, n), &c, m)) return fail(e);
+    if (Error e = chem::MomentTensor(mat(a, n), &mo, m)) return fail(e);
+    if (center) memcpy(center, c.data(), sizeof(double) * 3);
+    if (moment) memcpy(moment, mo.data(), sizeof(double) * 9);
+    return 0;
+}
+
 int gch_mobile_limit(double limit, int tolerance, const double* v, int n, int* n_out, double* limit_out) {
     return ret(align::mobileLimit(limit, tolerance, std::vector<double>(v, v + n), n_out, limit_out));
 }

@@ -280,6 +280,29 @@ Error MemPerAtomRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matri
     return Error();
 }
 
+static Error moments_one(const v3::Matrix& A, const std::vector<double>& mass, v3::Matrix* center, v3::Matrix* moment, const char* who) {
+    if (A.NVecs() == 0) return Error("goChem: nil matrix to get the center of mass", {who}, GCB_ERR_SHAPE);
+    if (!mass.empty() && (int)mass.size() != A.NVecs())
+        return Error("goChem: Error in gonum function: mat: dimension mismatch", {"gnMaybe", who}, GCB_ERR_SHAPE);  // ScaleByCol panics
+    std::lock_guard<std::mutex> lk(g_mu);
+    gcb_traj* t = nullptr;
+    if (Error e = stage_one(A, &t)) return errDecorate(e, who);
+    double c[3], m[9];
+    int rc = gcb_moments(t, 0, 1, mass.empty() ? nullptr : mass.data(), nullptr, 0, c, m);
+    if (rc) return deviceError(rc, who);
+    if (center) { *center = v3::Matrix::Zeros(1); std::copy(c, c + 3, center->data()); }
+    if (moment) { *moment = v3::Matrix::Zeros(3); std::copy(m, m + 9, moment->data()); }
+    return Error();
+}
+
+Error CenterOfMass(const v3::Matrix& geometry, v3::Matrix* center, const std::vector<double>& mass) {
+    return moments_one(geometry, mass, center, nullptr, "CenterOfMass");
+}
+
+Error MomentTensor(const v3::Matrix& A, v3::Matrix* moment, const std::vector<double>& mass) {
+    return moments_one(A, mass, nullptr, moment, "MomentTensor");
+}
+
 // ------------------------------------------------------------------ in-memory trajectory
 Error MemTraj::Next(v3::Matrix* V, std::vector<double>*) {
     if (current_ >= Coords.size()) return newLastFrameError("", "Next");  // chem.go:706-708

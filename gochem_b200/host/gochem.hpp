@@ -99,6 +99,10 @@ Error MemRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix& tmp,
 Error MemPerAtomRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matrix* ctest, v3::Matrix* ctempla, v3::Matrix& tmp,
                      std::vector<double>* out, const IndexLists& indexes = {});
 
+// geometric.go:609-631 and :705-733.  mass empty = unit masses (geometric centre).
+Error CenterOfMass(const v3::Matrix& geometry, v3::Matrix* center, const std::vector<double>& mass = {});
+Error MomentTensor(const v3::Matrix& A, v3::Matrix* moment, const std::vector<double>& mass = {});
+
 // Topology side: only what align.res2atoms reads (chem.go Atom fields, lovo.go:504-516).
 struct Atom {
     std::string Name;

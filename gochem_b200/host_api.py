@@ -114,6 +114,17 @@ def RotatorTranslatorToSuper(test, templa):
     return tr, r, a, b
 
 
+def CenterAndMoment(a, mass=None):
+    """chem.CenterOfMass + chem.MomentTensor of one structure."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    m = None if mass is None else np.ascontiguousarray(mass, dtype=np.float64)
+    cen, mom = np.zeros(3), np.zeros((3, 3))
+    rc = load().gch_center_and_moment(_d(a), a.shape[0], _d(m), _d(cen), _d(mom))
+    if rc:
+        raise _err(rc)
+    return cen, mom
+
+
 def mobile_limit(limit, tolerance, sorted_rmsd):
     v = np.ascontiguousarray(sorted_rmsd, dtype=np.float64)
     n, lim = C.c_int(0), C.c_double(0)

@@ -144,6 +144,13 @@ int gcb_allpairs_rmsd(gcb_traj *t, long first, long nframes, const int *idx, int
 int gcb_allpairs_rmsd_fit(gcb_traj *t, long first, long nframes, const int *idx, int nidx, long row0, long nrows,
                           double *out_host, float *gemm_ms, long *redone);
 
+/* ---- per-frame centre of mass and moment tensor ----
+ * chem.CenterOfMass (geometric.go:609-631) and chem.MomentTensor (geometric.go:705-733) for every frame of the window:
+ * center[3F], moment[9F] (row-major symmetric 3x3).  mass: natoms entries or NULL (geometric centre, unit masses);
+ * idx/nidx: atoms considered (NULL = all).  Either output may be NULL. */
+int gcb_moments(gcb_traj *t, long first, long nframes, const double *mass, const int *idx, int nidx, double *center,
+                double *moment);
+
 /* ---- stream timing on the stream the kernels run on ---- */
 int gcb_timer_start(gcb_traj *t);
 int gcb_timer_stop(gcb_traj *t, float *ms);

@@ -35,6 +35,9 @@ int gch_mem_per_atom_rmsd(const double *test, int ntest, const double *templa, i
 int gch_rotator_translator_to_super(const double *test, const double *templa, int n, double *transformed,
                                     double *rot, double *trans1, double *trans2);
 
+/* chem.CenterOfMass (geometric.go:609-631) + chem.MomentTensor (geometric.go:705-733); mass NULL = unit masses. */
+int gch_center_and_moment(const double *a, int n, const double *mass, double *center, double *moment);
+
 /* align bookkeeping (align/lovo.go:175-188, 306-326) */
 int gch_mobile_limit(double limit, int tolerance, const double *sorted_rmsd, int n, int *n_out, double *limit_out);
 int gch_approx_eq(double i, double j, double eps);

@@ -206,3 +206,14 @@ def lovo(frames, ref, fullindexes, cpus, less_than_rmsd=1.0, minimum_n=10, begin
         raise OracleError(e)
     return dict(N=n.value, Natoms=natoms[: n.value].copy(), RMSD=rm[:nfull].copy(), FramesRead=fr.value,
                 Iterations=it.value)
+
+
+def center_and_moment(a, mass=None):
+    """chem.CenterOfMass (geometric.go:609-631) and chem.MomentTensor (geometric.go:705-733)."""
+    a = _f64(a)
+    m = None if mass is None else _f64(mass)
+    cen, mom = np.zeros(3), np.zeros((3, 3))
+    e = lib().orc_center_and_moment(_d(a), a.shape[0], _d(m) if m is not None else None, _d(cen), _d(mom))
+    if e:
+        raise OracleError(e)
+    return cen, mom

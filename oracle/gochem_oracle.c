@@ -812,6 +812,32 @@ int orc_lovo(const double *frames, long F, int N, const double *ref, const int *
     return err;
 }
 
+/* chem.CenterOfMass (geometric.go:609-631) and chem.MomentTensor (geometric.go:705-733) of one structure.
+ * mass == NULL: unit masses.  The moment tensor is center^T * center with rows of the centred matrix scaled by
+ * sqrt(m_i) (pow(mass, sqrmass, 0.5), :722-725), accumulated row by row as Dgemm does. */
+int orc_center_and_moment(const double *a, int n, const double *mass, double *center, double *moment) {
+    if (n <= 0) return ORC_ERR_SHAPE;
+    double s0 = 0, s1 = 0, s2 = 0, msum = 0;
+    for (int i = 0; i < n; i++) {
+        double m = mass ? mass[i] : 1.0;
+        s0 += a[3 * i] * m; s1 += a[3 * i + 1] * m; s2 += a[3 * i + 2] * m;
+        msum += m;
+    }
+    double inv = 1.0 / msum;
+    double c[3] = {s0 * inv, s1 * inv, s2 * inv};
+    if (center) memcpy(center, c, sizeof c);
+    if (moment) {
+        for (int k = 0; k < 9; k++) moment[k] = 0.0;
+        for (int i = 0; i < n; i++) {
+            double sq = sqrt(mass ? mass[i] : 1.0);
+            double r[3] = {(a[3 * i] - c[0]) * sq, (a[3 * i + 1] - c[1]) * sq, (a[3 * i + 2] - c[2]) * sq};
+            for (int p = 0; p < 3; p++)
+                for (int q = 0; q < 3; q++) moment[3 * p + q] += r[p] * r[q];
+        }
+    }
+    return ORC_OK;
+}
+
 /* exposed for tests */
 void orc_stable_sort_pairs(int *ids, double *vals, int n, int by_rmsd) {
     stable_sort_pairs(ids, vals, n, by_rmsd);

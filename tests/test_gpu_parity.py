@@ -420,3 +420,29 @@ def test_allpairs_rmsd_matrix_with_per_pair_fit(natoms, nframes):
         s = oracle.super_(frames[i][idx], frames[j][idx])
         assert abs(sub[i - 3, j] - oracle.rmsd(s, frames[j][idx])) < 1e-9
     t.close()
+
+
+def test_center_of_mass_and_moment_tensor_batched():
+    """chem.CenterOfMass / chem.MomentTensor for every resident frame."""
+    natoms, nframes = 777, 40
+    ref, frames = synth.make_case(natoms, nframes)
+    rng = np.random.default_rng(1)
+    mass = rng.uniform(1.0, 32.0, natoms)
+    idx = np.arange(3, natoms, 5)
+    t = device_traj(frames)
+    for m, ix in [(None, None), (mass, None), (mass, idx), (None, idx)]:
+        cen, mom = t.moments(m, ix)
+        for f in (0, 1, nframes - 1):
+            a = frames[f] if ix is None else frames[f][ix]
+            mm = None if m is None else (m if ix is None else m[ix])
+            oc, om = oracle.center_and_moment(a, mm)
+            assert np.abs(cen[f] - oc).max() < 1e-10
+            assert np.abs(mom[f] - om).max() < 1e-10 * np.abs(om).max()
+    t.close()
+    from gochem_b200 import host_api as H
+    oc, om = oracle.center_and_moment(frames[3], mass)
+    hc, hm = H.CenterAndMoment(frames[3], mass)
+    assert np.abs(hc - oc).max() < 1e-10 and np.abs(hm - om).max() < 1e-10 * np.abs(om).max()
+    oc, om = oracle.center_and_moment(frames[3])
+    hc, hm = H.CenterAndMoment(frames[3])
+    assert np.abs(hc - oc).max() < 1e-10 and np.abs(hm - om).max() < 1e-10 * np.abs(om).max()

@@ -193,3 +193,17 @@ def test_lovo_c_vs_numpy_and_golden(golden_dir):
     assert total == int(g["first_pass_frames"]) and np.abs(rm - g["first_pass_rmsd"]).max() < 1e-11
     res_t = oracle.lovo(frames, ref, np.arange(150), cpus, nthreads=4)
     assert list(res_t["Natoms"]) == list(res["Natoms"])
+
+
+def test_center_of_mass_and_moment_tensor():
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((70, 3)) * 9 + np.array([30.0, -12.0, 5.0])
+    m = rng.uniform(1.0, 32.0, 70)
+    for mass in (None, m):
+        w = np.ones(70) if mass is None else mass
+        cen, mom = oracle.center_and_moment(a, mass)
+        c2 = (a * w[:, None]).sum(0) / w.sum()
+        d = a - c2
+        assert np.abs(cen - c2).max() < 1e-13
+        assert np.abs(mom - (d * w[:, None]).T @ d).max() < 1e-10
+        assert np.array_equal(mom, mom.T)
