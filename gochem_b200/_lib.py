@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgochem_b200.so")
+LIB_PATH = os.environ.get("GCB_LIB") or os.path.join(HERE, "lib", "libgochem_b200.so")   # GCB_LIB: tuning builds (tools/)
 HEADER = os.path.join(HERE, "..", "include", "gochem_b200.h")
 
 F64_AOS, F32_AOS, F32_SOA = 0, 1, 2
