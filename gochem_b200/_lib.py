@@ -75,6 +75,8 @@ def load() -> C.CDLL:
         "gcb_allpairs_rmsd": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_allpairs_rmsd_fit": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_moments": (I, [P, L, L, P, P, I, P, P]),
+        "gcb_moments_async": (I, [P, L, L, P, P, I]),
+        "gcb_moments_fetch": (I, [P, L, P, P]),
         "gcb_timer_start": (I, [P]),
         "gcb_timer_stop": (I, [P, C.POINTER(C.c_float)]),
         "gcb_sync": (I, [P]),
@@ -292,6 +294,12 @@ class DeviceTraj:
         cen, mom = np.empty((n, 3)), np.empty((n, 3, 3))
         check(self.lib.gcb_moments(self.h, first, n, _ptr(m), _ptr(it), 0 if it is None else it.size, _ptr(cen), _ptr(mom)))
         return cen, mom
+
+    def moments_async(self, mass=None, idx=None, first=0, nframes=None):
+        n = self.nframes - first if nframes is None else nframes
+        m = None if mass is None else np.ascontiguousarray(mass, dtype=np.float64)
+        it = _idx(idx)
+        check(self.lib.gcb_moments_async(self.h, first, n, _ptr(m), _ptr(it), 0 if it is None else it.size))
 
     # --- timing on the library's stream ---
     def timer_start(self):

@@ -36,6 +36,7 @@ struct RefCache {
     int mode = -1;  // 0 all, 1 weighted, 2 gather
     bool centred = false;
     bool valid = false;
+    bool repeated = false;  // weighted mode: some index occurs more than once (multiplicities > 1)
     double n_fit = 0.0;
     double gb = 0.0;
     double bbar[3] = {0, 0, 0};
@@ -148,6 +149,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
     cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
     cudaFree(t->d_devpart); cudaFree(t->d_devsum);
+    cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
     delete t;
     return GCB_OK;
@@ -384,7 +386,11 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
         GCB_CUDA(cudaMemcpyAsync(t->d_refc, h, sizeof(double) * 3 * (size_t)np, cudaMemcpyHostToDevice, t->stream));
         double* w = h + 3 * (size_t)np;
         if (mode == MODE_WEIGHTED) {
-            for (int k = 0; k < nidx; k++) w[idx_test[k]] += 1.0;  // multiplicity: a repeated index counts twice, as in SomeVecs
+            c.repeated = false;
+            for (int k = 0; k < nidx; k++) {   // multiplicity: a repeated index counts twice, as in SomeVecs
+                w[idx_test[k]] += 1.0;
+                if (w[idx_test[k]] > 1.0) c.repeated = true;
+            }
             GCB_CUDA(cudaMemcpyAsync(t->d_weight, w, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, t->stream));
         }
         double gb = 0.0;
@@ -468,8 +474,9 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
     }
     if (mode == MODE_WEIGHTED) p.weight = t->d_weight;
-    const bool cluster = use_cluster(t);
-    if (g_variant == GCB_KERNEL_CLUSTER && !cluster) {
+    // the cluster kernel takes the fit subset as a 0/1 mask; index lists with repeats (multiplicities) go to the generic kernel
+    const bool cluster = use_cluster(t) && !(mode == MODE_WEIGHTED && t->cache.repeated);
+    if (g_variant == GCB_KERNEL_CLUSTER && !cluster && !(mode == MODE_WEIGHTED && t->cache.repeated)) {
         set_error("cluster kernel requested but not available for %d atoms", t->natoms);
         return GCB_ERR_ARG;
     }
@@ -479,6 +486,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         if (rc) return rc;
         GCB_CUDA(cudaMemsetAsync(t->d_devpart, 0, sizeof(double) * rows * (size_t)t->np, t->stream));
         p.devpart = t->d_devpart;
+        p.rmsd = nullptr;   // align.RMSDTraj (align/lovo.go:286-353) never looks at the per-frame RMSD
     }
     int rows_used = 0;
     rc = cluster ? launch_super_cluster(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used)

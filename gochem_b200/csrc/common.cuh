@@ -88,6 +88,11 @@ struct gcb_traj {
     double* d_devpart = nullptr;
     size_t devpart_rows = 0;
     double* d_devsum = nullptr;
+    // per-frame centre of mass / moment tensor (moments.cu)
+    double* d_mom_w = nullptr;   // np mass plane
+    double* d_mom_c = nullptr;   // 3 per frame
+    double* d_mom_m = nullptr;   // 9 per frame
+    long mom_cap = 0, mom_frames = 0;
     // host pinned scratch for small transfers
     double* h_scratch = nullptr;
     size_t h_scratch_bytes = 0;

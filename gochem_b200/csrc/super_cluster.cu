@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "kabsch3.cuh"
+#include "ptx.cuh"
 
 namespace gcb {
 
@@ -62,70 +63,7 @@ struct ClusterParams {
     double* epart;      // [nframes][C][8 consumer warps] squared-error partials
 };
 
-// ---- PTX helpers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                 ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_id_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+using namespace ptx;
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -177,31 +115,37 @@ struct __align__(16) Shared {
     unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
 
-// sqrt of a non-negative double with a short dependency chain: hardware reciprocal-square-root seed (about 20 good
-// bits) and two Newton steps (the error squares each step: ~2^-77), then x * rsqrt(x).  A denormal-sized offset keeps
-// x = 0 away from inf * 0; it changes no representable result above 1e-290.
+// sqrt of a non-negative double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
+// error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
+// 1/(1+e) = (1-2r)^(-1/2) = 1 + r + 3/2 r^2 + O(r^3), so sqrt(x) = g + g r (1 + 3/2 r) with relative error 2.5 |e|^3 <
+// 2^-58 -- one correction of cubic order, four dependent fp64 operations after the seed (six in all) instead of two Newton
+// steps.  Zero and denormal arguments (seed = inf) return 0: the error is below 1.5e-154.
 __device__ __forceinline__ double fast_sqrt(double x) {
-    const double xs = x + 1e-300;
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
-    const double hx = 0.5 * xs;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
-    return xs * y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y;
+    const double h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    const double p = fma(1.5, r, 1.0);
+    const double gr = g * r;
+    const double out = fma(gr, p, g);
+    return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
 }
 
 // pass 2 for one thread's K atom slots.  RESIDENT: the frame part is still in its shared-memory stage
 // (plane stride K*256); otherwise it is re-read from global memory, where it still sits in L2 (plane
 // stride np, streaming loads).  WB = also store the superposed coordinates.
-template <int K, bool WEIGHTED, bool DEV, bool WB, bool RESIDENT>
+// MASKED: the fit uses a subset of the atoms (fit_mask bit k = slot k is in it); otherwise every real atom is.
+// DEV: per-atom distances are accumulated and the frame's squared error is not (align.RMSDTraj never asks for it).
+template <int K, bool MASKED, bool DEV, bool WB, bool RESIDENT>
 __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, long plane, const double* xf,
                                               const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
-                                              const double (&wk)[WEIGHTED ? K : 1], double (&dev)[DEV ? K : 1], double* frw, int np,
+                                              uint32_t fit_mask, double (&dev)[DEV ? K : 1], double* frw, int np,
                                               uint32_t real_mask, uint32_t in_mask, double b0, double b1, double b2) {
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
-    constexpr int CH = 4;   // atoms in flight per thread: enough loads outstanding, bounded register use
+    constexpr int CH = (K % 5 == 0) ? 5 : 4;   // atoms in flight per thread: enough independent chains, bounded register use
 #pragma unroll
     for (int kb = 0; kb < K; kb += CH) {
         double x[CH], y[CH], z[CH];
@@ -227,12 +171,11 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
             const double qz = fma(z[c], r8, fma(y[c], r5, fma(x[c], r2, g2)));
             const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (WEIGHTED) {
-                if (k & 1) e1 = fma(wk[k], d2, e1); else e0 = fma(wk[k], d2, e0);
-            } else if ((real_mask >> k) & 1u) {   // unweighted: every real atom counts once; padding slots do not
+            if (DEV) {
+                dev[k] += fast_sqrt(d2);
+            } else if (((MASKED ? fit_mask : real_mask) >> k) & 1u) {   // atoms of the fit count once; padding slots never
                 if (k & 1) e1 += d2; else e0 += d2;
             }
-            if (DEV) dev[k] += fast_sqrt(d2);
             if (WB) {
                 if ((real_mask >> k) & 1u) {
                     frw[k * kConsumers] = qx + b0;
@@ -245,7 +188,7 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     return e0 + e1;
 }
 
-template <int K, bool WEIGHTED, bool DEV, bool RESIDENT>
+template <int K, bool MASKED, bool DEV, bool RESIDENT>
 __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -386,8 +329,8 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     } else {
         // ===================== consumers (warps run free of one another) =====================
         // fixed atom slots: local index tid + k*256; template and weights stay in registers
-        double bx[K], by[K], bz[K], wk[WEIGHTED ? K : 1], dev[DEV ? K : 1];
-        uint32_t real_mask = 0;
+        double bx[K], by[K], bz[K], dev[DEV ? K : 1];
+        uint32_t real_mask = 0, fit_mask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int li = tid + k * kConsumers;
@@ -396,7 +339,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             bx[k] = in ? p.refc[gi] : 0.0;
             by[k] = in ? p.refc[p.np + gi] : 0.0;
             bz[k] = in ? p.refc[2L * p.np + gi] : 0.0;
-            if (WEIGHTED) wk[k] = (in && gi < p.natoms) ? p.weight[gi] : 0.0;
+            if (MASKED && in && gi < p.natoms && p.weight[gi] != 0.0) fit_mask |= 1u << k;   // weights are 0 or 1 here
             if (DEV) dev[k] = 0.0;
             if (in && gi < p.natoms) real_mask |= 1u << k;   // slots that are real atoms of THIS part
         }
@@ -428,12 +371,14 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
+                    if (MASKED) {   // atoms outside the fit contribute zeros (selects, not fp64 multiplies)
+                        const bool on = (fit_mask >> k) & 1u;
+                        x = on ? x : 0.0; y = on ? y : 0.0; z = on ? z : 0.0;
+                    }
                     if (!DEV) {   // only the one-pass RMSD needs sum w|a|^2; the per-atom-distance pass always runs pass 2
                         const double n2 = fma(z, z, fma(y, y, x * x));
-                        if (WEIGHTED) { if (k & 1) aa1 = fma(wk[k], n2, aa1); else aa0 = fma(wk[k], n2, aa0); }
-                        else { if (k & 1) aa1 += n2; else aa0 += n2; }
+                        if (k & 1) aa1 += n2; else aa0 += n2;
                     }
-                    if (WEIGHTED) { x *= wk[k]; y *= wk[k]; z *= wk[k]; }
                     acc[0] += x; acc[1] += y; acc[2] += z;
                     acc[3] = fma(x, bx[k], acc[3]); acc[4] = fma(x, by[k], acc[4]); acc[5] = fma(x, bz[k], acc[5]);
                     acc[6] = fma(y, bx[k], acc[6]); acc[7] = fma(y, by[k], acc[7]); acc[8] = fma(y, bz[k], acc[8]);
@@ -495,16 +440,16 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     }
                 } else if (RESIDENT) {
                     const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
-                    if (frw) e = pass2_atoms<K, WEIGHTED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, WEIGHTED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
                     if (++s2 == S) s2 = 0;
                 } else {
-                    if (frw) e = pass2_atoms<K, WEIGHTED, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, WEIGHTED, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, wk, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                 }
-                if (run_pass2) {
+                if (run_pass2 && !DEV) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) e += shx(e, o);
                     if (lane == 0) *ep = e;          // per-warp squared error; finish_rmsd_kernel adds them in fixed order

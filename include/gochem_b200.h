@@ -150,6 +150,9 @@ int gcb_allpairs_rmsd_fit(gcb_traj *t, long first, long nframes, const int *idx,
  * idx/nidx: atoms considered (NULL = all).  Either output may be NULL. */
 int gcb_moments(gcb_traj *t, long first, long nframes, const double *mass, const int *idx, int nidx, double *center,
                 double *moment);
+/* Launch only (results stay on the device) and the matching fetch of the first nframes results of the last launch. */
+int gcb_moments_async(gcb_traj *t, long first, long nframes, const double *mass, const int *idx, int nidx);
+int gcb_moments_fetch(gcb_traj *t, long nframes, double *center, double *moment);
 
 /* ---- stream timing on the stream the kernels run on ---- */
 int gcb_timer_start(gcb_traj *t);

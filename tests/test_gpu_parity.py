@@ -446,3 +446,21 @@ def test_center_of_mass_and_moment_tensor_batched():
     oc, om = oracle.center_and_moment(frames[3])
     hc, hm = H.CenterAndMoment(frames[3])
     assert np.abs(hc - oc).max() < 1e-10 and np.abs(hm - om).max() < 1e-10 * np.abs(om).max()
+
+
+@pytest.mark.parametrize("natoms,nframes", [(1, 3), (17, 5), (2048, 300), (2049, 7), (5003, 333), (10000, 150)])
+def test_moments_stream_kernel_chunked_frames(natoms, nframes):
+    """Frames of one chunk, several chunks with a ragged last chunk, more frames than CTAs: every frame checked."""
+    ref, frames = synth.make_case(natoms, nframes)
+    mass = np.random.default_rng(natoms).uniform(1.0, 32.0, natoms)
+    t = device_traj(frames)
+    cen, mom = t.moments(mass)
+    t.close()
+    msum = mass.sum()
+    oc = (frames * mass[None, :, None]).sum(axis=1) / msum
+    d = frames - oc[:, None, :]
+    om = np.einsum("fi,fia,fib->fab", np.broadcast_to(mass, (nframes, natoms)), d, d)
+    assert np.abs(cen - oc).max() < 1e-10
+    assert np.abs(mom - om).max() < 1e-10 * np.abs(om).max()
+    c0, m0 = oracle.center_and_moment(frames[nframes - 1], mass)
+    assert np.abs(cen[-1] - c0).max() < 1e-10 and np.abs(mom[-1] - m0).max() < 1e-10 * np.abs(m0).max()
