@@ -86,6 +86,9 @@ def load() -> C.CDLL:
         "gcb_comm_init": (I, [I, I, I, C.c_char_p, C.POINTER(P)]),
         "gcb_comm_destroy": (I, [P]),
         "gcb_allreduce_sum_f64": (I, [P, P, L]),
+        "gcb_traj_allgather": (I, [P, P, C.POINTER(L)]),
+        "gcb_allpairs_rmsd_sharded": (I, [P, L, L, P, I, I, P, P, C.POINTER(L), C.POINTER(L), C.POINTER(C.c_float),
+                                          C.POINTER(C.c_float), C.POINTER(L)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -285,6 +288,25 @@ class DeviceTraj:
         fn = self.lib.gcb_allpairs_rmsd_fit if fit else self.lib.gcb_allpairs_rmsd
         check(fn(self.h, first, n, _ptr(it), 0 if it is None else it.size, row0, nr, _ptr(out), C.byref(ms), C.byref(redone)))
         return out, ms.value, redone.value
+
+    def allgather(self, comm: "Comm", counts):
+        """Frames sharded over the ranks (each rank's block already at its offset) -> all frames on every rank."""
+        c = (C.c_long * len(counts))(*[int(x) for x in counts])
+        check(self.lib.gcb_traj_allgather(self.h, comm.h, c))
+
+    def allpairs_rmsd_sharded(self, comm: "Comm", idx=None, first=0, nframes=None, fit=False, fetch=True):
+        """Multi-GPU all-pairs RMSD matrix: returns (this rank's row block or None, row0, gemm_ms, total_ms, redone)."""
+        n = self.nframes - first if nframes is None else nframes
+        it = _idx(idx)
+        base, rem = divmod(n, comm.nranks)
+        nr = base + (1 if comm.rank < rem else 0)
+        out = np.empty((nr, n)) if fetch else None
+        row0, nrows, redone = C.c_long(0), C.c_long(0), C.c_long(0)
+        gms, tms = C.c_float(0), C.c_float(0)
+        check(self.lib.gcb_allpairs_rmsd_sharded(self.h, first, n, _ptr(it), 0 if it is None else it.size, 1 if fit else 0, comm.h,
+                                                 _ptr(out), C.byref(row0), C.byref(nrows), C.byref(gms), C.byref(tms), C.byref(redone)))
+        assert nrows.value == nr
+        return out, row0.value, gms.value, tms.value, redone.value
 
     def moments(self, mass=None, idx=None, first=0, nframes=None):
         """chem.CenterOfMass + chem.MomentTensor for every frame -> (F x 3, F x 3 x 3)."""

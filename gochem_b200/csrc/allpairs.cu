@@ -24,6 +24,8 @@ constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int LDS = BK + 4;           // row stride in doubles: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts
 constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 256;
+constexpr int TLD = BN + 1;           // staging row stride: transposed reads touch every bank once per half warp
+constexpr int kMaxPeers = 8;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -111,12 +113,29 @@ struct PairList {
     unsigned int cap;
 };
 
-// One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T for rows [row0, row0 + nrows) against all
-// columns, and writes D (both triangles when the mirrored block belongs to this rank's rows).
+// Where the rows of the matrix live.  Row i belongs to owner o when row0[o] <= i < row0[o + 1] and is stored at
+// blk[o] + (i - row0[o]) * ld.  Single GPU: one owner (the caller's row block).  Multi-GPU: blk[o] is rank o's row block,
+// mapped into this process with cudaIpcOpenMemHandle, so a finished tile goes straight to its owners over NVLink.
+// Rows outside [row0[0], row0[nowners]) are not stored.
+struct PeerOut {
+    double* blk[kMaxPeers];
+    long row0[kMaxPeers + 1];
+    int nowners;
+};
+
+__device__ __forceinline__ double* peer_row(const PeerOut& po, long i, long ld) {
+    if (i < po.row0[0] || i >= po.row0[po.nowners]) return nullptr;
+    int o = 0;
+    while (o + 1 < po.nowners && i >= po.row0[o + 1]) o++;
+    return po.blk[o] + (i - po.row0[o]) * ld;
+}
+
+// One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T and delivers D for the block and for its mirror
+// image to the owners of those rows (PeerOut): the block is staged in shared memory, 64 rows at a time, and leaves as
+// whole-row segments (256-byte stores per warp), the mirror image read transposed from the same staging buffer.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
-                     long row0, long nrows, const int2* __restrict__ tiles, double* __restrict__ D, long ldd, double floor_rel,
-                     PairList redo) {
+                     const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
     extern __shared__ __align__(16) double smem[];
     double* sA = smem;                              // [STAGES][BM][LDS]
     double* sB = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BN][LDS]
@@ -182,41 +201,68 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
         }
     }
     cp_async_wait<0>();
+    __syncthreads();   // every warp is done with the pipeline buffers: reuse them as the staging buffer
     // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
+    double* sT = smem;   // [64][TLD]
+    for (int half = 0; half < 2; half++) {
+        if (wm == half) {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) {
-        const long i = i0 + wm * 64 + mi * 8 + g;
-        if (i >= nframes) continue;
-        const double ni_ = norms[i];
+            for (int mi = 0; mi < 8; mi++) {
+                const long i = i0 + wm * 64 + mi * 8 + g;
+                const double ni_ = i < nframes ? norms[i] : 0.0;
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
+                for (int ni = 0; ni < 4; ni++) {
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const long j = j0 + wn * 32 + ni * 8 + 2 * t + e;
-                if (j >= nframes) continue;
-                const double nj_ = norms[j];
-                double d2 = (ni_ + nj_ - 2.0 * acc[mi][ni][e]) * inv_n;
-                double d;
-                if (i == j) {
-                    d = 0.0;
-                } else {
-                    if (d2 < floor_rel * (ni_ + nj_) * inv_n && j > i) {
-                        // below the rounding floor of the expansion: recompute from explicit differences later
-                        const unsigned int slot = atomicAdd(redo.count, 1u);
-                        if (slot < redo.cap) redo.pairs[slot] = make_uint2((unsigned int)i, (unsigned int)j);
+                    for (int e = 0; e < 2; e++) {
+                        const int c = wn * 32 + ni * 8 + 2 * t + e;
+                        const long j = j0 + c;
+                        double d = 0.0;
+                        if (i < nframes && j < nframes && i != j) {
+                            const double nj_ = norms[j];
+                            const double d2 = (ni_ + nj_ - 2.0 * acc[mi][ni][e]) * inv_n;
+                            if (d2 < floor_rel * (ni_ + nj_) * inv_n && j > i) {
+                                // below the rounding floor of the expansion: recompute from explicit differences later
+                                const unsigned int slot = atomicAdd(redo.count, 1u);
+                                if (slot < redo.cap) redo.pairs[slot] = make_uint2((unsigned int)i, (unsigned int)j);
+                            }
+                            d = sqrt(d2 > 0.0 ? d2 : 0.0);
+                        }
+                        sT[(mi * 8 + g) * TLD + c] = d;
                     }
-                    d = sqrt(d2 > 0.0 ? d2 : 0.0);
                 }
-                if (i >= row0 && i < row0 + nrows) D[(i - row0) * ldd + j] = d;
-                if (j != i && tile.x != tile.y && j >= row0 && j < row0 + nrows) D[(j - row0) * ldd + i] = d;
             }
         }
+        __syncthreads();
+        const long ib = i0 + half * 64;   // first row staged
+        for (int r = warp; r < 64; r += 8) {          // rows of the block: 128 contiguous doubles each
+            const long i = ib + r;
+            if (i >= nframes) break;
+            double* dst = peer_row(po, i, ldd);
+            if (!dst) continue;
+            dst += j0;
+#pragma unroll
+            for (int c = lane; c < BN; c += 32)
+                if (j0 + c < nframes) dst[c] = sT[r * TLD + c];
+        }
+        if (tile.x != tile.y) {                       // mirror image: rows j of the matrix, 64 contiguous doubles each
+            for (int c = warp; c < BN; c += 8) {
+                const long j = j0 + c;
+                if (j >= nframes) break;
+                double* dst = peer_row(po, j, ldd);
+                if (!dst) continue;
+                dst += ib;
+#pragma unroll
+                for (int r = lane; r < 64; r += 32)
+                    if (ib + r < nframes) dst[r] = sT[r * TLD + c];
+            }
+        }
+        __syncthreads();
     }
 }
 
 // explicit ||Y_i - Y_j|| for the flagged pairs: one warp per pair
 __global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restrict__ Y, long ld, int kdim, double inv_n, PairList redo,
-                                                        long row0, long nrows, double* __restrict__ D, long ldd) {
+                                                        const PeerOut po, long ldd) {
     const unsigned int n = min(*redo.count, redo.cap);
     const int lane = threadIdx.x & 31;
     for (unsigned int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < n; p += gridDim.x * 8) {
@@ -231,8 +277,10 @@ __global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restric
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
             const double d = sqrt(s * inv_n);
-            if ((long)ij.x >= row0 && (long)ij.x < row0 + nrows) D[((long)ij.x - row0) * ldd + ij.y] = d;
-            if ((long)ij.y >= row0 && (long)ij.y < row0 + nrows) D[((long)ij.y - row0) * ldd + ij.x] = d;
+            double* ri = peer_row(po, (long)ij.x, ldd);
+            double* rj = peer_row(po, (long)ij.y, ldd);
+            if (ri) ri[ij.y] = d;
+            if (rj) rj[ij.x] = d;
         }
     }
 }
@@ -295,8 +343,7 @@ __global__ void __launch_bounds__(256) centre_frames_kernel(const double* __rest
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
-                         long row0, long nrows, const int2* __restrict__ tiles, double* __restrict__ D, long ldd, double floor_rel,
-                         PairList redo) {
+                         const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
     extern __shared__ __align__(16) double smem[];
     double* sA = smem;                               // [STAGES][FM][LDS]
     double* sB = smem + (size_t)STAGES * FM * LDS;    // [STAGES][FM][LDS]
@@ -401,14 +448,18 @@ allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, c
             }
             d = sqrt(d2 > 0.0 ? d2 : 0.0);
         }
-        if (i >= row0 && i < row0 + nrows) D[(i - row0) * ldd + j] = d;
-        if (j != i && j >= row0 && j < row0 + nrows) D[(j - row0) * ldd + i] = d;
+        double* ri = peer_row(po, i, ldd);
+        if (ri) ri[j] = d;
+        if (j != i) {
+            double* rj = peer_row(po, j, ldd);
+            if (rj) rj[i] = d;
+        }
     }
 }
 
 // flagged pairs again, from explicit sums: H by direct dot products, R, then sum |y_i R - y_j|^2 -- one warp per pair
 __global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __restrict__ Z, int kdim, double inv_n, PairList redo,
-                                                            long row0, long nrows, double* __restrict__ D, long ldd) {
+                                                            const PeerOut po, long ldd) {
     const unsigned int n = min(*redo.count, redo.cap);
     const int lane = threadIdx.x & 31;
     for (unsigned int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < n; p += gridDim.x * 8) {
@@ -444,8 +495,10 @@ __global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __res
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
             const double d = sqrt(s * inv_n);
-            if ((long)ij.x >= row0 && (long)ij.x < row0 + nrows) D[((long)ij.x - row0) * ldd + ij.y] = d;
-            if ((long)ij.y >= row0 && (long)ij.y < row0 + nrows) D[((long)ij.y - row0) * ldd + ij.x] = d;
+            double* ri = peer_row(po, (long)ij.x, ldd);
+            double* rj = peer_row(po, (long)ij.y, ldd);
+            if (ri) ri[ij.y] = d;
+            if (rj) rj[ij.x] = d;
         }
     }
 }
@@ -453,9 +506,13 @@ __global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __res
 }  // namespace
 
 // Device-side driver.  Y source: the trajectory planes themselves (idx == nullptr: rows of 3*np doubles, padding
-// zeros) or a gathered subset.  Computes rows [row0, row0 + nrows) of the F x F matrix into d_out (ld = nframes).
-int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int nidx, long row0, long nrows, double* d_out,
-                    float* gemm_ms, long* redone, bool fit) {
+// zeros) or a gathered subset.  The F x F matrix (ld = nframes) goes to the row owners in `po`.
+//   deal_n == 1: single-GPU call -- every tile on or above the diagonal that touches the owner's rows, directly or
+//                through its mirror image, is computed here.
+//   deal_n  > 1: the tiles on or above the diagonal are dealt round-robin to deal_n ranks (this one is deal_rank) and
+//                each finished tile is stored into the row blocks of its owners, local or peer.
+static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int nidx, const PeerOut& po, int deal_rank,
+                           int deal_n, float* gemm_ms, long* redone, bool fit) {
     cudaStream_t s = t->stream;
     const int natoms_used = d_idx ? nidx : t->natoms;
     // (i): one row per frame, 3n columns.  (ii): three rows (planes) per frame, n columns.
@@ -516,14 +573,22 @@ int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int
             GCB_LAUNCHED();
         }
     }
-    // tiles on or above the diagonal that touch this rank's rows (directly or through the mirror)
-    for (int bi = 0; bi < nt; bi++)
-        for (int bj = bi; bj < nt; bj++) {
-            const long ia = (long)bi * tile_frames, ib = ia + tile_frames, ja = (long)bj * tile_frames, jb = ja + tile_frames;
-            const bool rows_hit = ia < row0 + nrows && ib > row0;
-            const bool mirror_hit = ja < row0 + nrows && jb > row0;
-            if (rows_hit || mirror_hit) tiles.push_back(make_int2(bi, bj));
-        }
+    {
+        const long row0 = po.row0[0], row1 = po.row0[po.nowners];
+        long k = 0;
+        for (int bi = 0; bi < nt; bi++)
+            for (int bj = bi; bj < nt; bj++, k++) {
+                if (deal_n > 1) {
+                    if (k % deal_n == deal_rank) tiles.push_back(make_int2(bi, bj));
+                    continue;
+                }
+                const long ia = (long)bi * tile_frames, ib = ia + tile_frames, ja = (long)bj * tile_frames, jb = ja + tile_frames;
+                const bool rows_hit = ia < row1 && ib > row0;
+                const bool mirror_hit = ja < row1 && jb > row0;
+                if (rows_hit || mirror_hit) tiles.push_back(make_int2(bi, bj));
+            }
+    }
+    if (tiles.empty()) tiles.push_back(make_int2(nt, nt));   // a block outside the matrix: nothing is stored
     AP_TRY(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
     AP_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
     AP_TRY(cudaEventCreate(&e0));
@@ -532,19 +597,19 @@ int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int
         AP_TRY(cudaFuncSetAttribute(allpairs_fit_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AP_TRY(cudaEventRecord(e0, s));
         allpairs_fit_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, kdim, nframes, norms, 1.0 / (double)natoms_used,
-                                                                                  row0, nrows, d_tiles, d_out, nframes, 1e-7, redo);
+                                                                                  d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
         AP_TRY(cudaEventRecord(e1, s));
-        redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
+        redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
         GCB_LAUNCHED();
     } else {
         AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AP_TRY(cudaEventRecord(e0, s));
-        allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used, row0,
-                                                                              nrows, d_tiles, d_out, nframes, 1e-7, redo);
+        allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                              d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
         AP_TRY(cudaEventRecord(e1, s));
-        redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, row0, nrows, d_out, nframes);
+        redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
         GCB_LAUNCHED();
     }
     AP_TRY(cudaStreamSynchronize(s));
@@ -569,6 +634,17 @@ done:
 
 }  // namespace gcb
 
+static int upload_idx(gcb_traj* t, const int* idx, int nidx, int** d_idx) {
+    using namespace gcb;
+    *d_idx = nullptr;
+    if (!(idx && nidx > 0)) return GCB_OK;
+    for (int k = 0; k < nidx; k++)
+        if (idx[k] < 0 || idx[k] >= t->natoms) { set_error("atom index %d out of range", idx[k]); return GCB_ERR_INDEXES; }
+    GCB_CUDA(cudaMalloc(d_idx, sizeof(int) * (size_t)nidx));
+    GCB_CUDA(cudaMemcpy(*d_idx, idx, sizeof(int) * (size_t)nidx, cudaMemcpyHostToDevice));
+    return GCB_OK;
+}
+
 static int allpairs_entry(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows, double* out_host,
                           float* gemm_ms, long* redone, bool fit) {
     using namespace gcb;
@@ -578,16 +654,14 @@ static int allpairs_entry(gcb_traj* t, long first, long nframes, const int* idx,
     if (nframes > 0x3fffffffL) { set_error("too many frames"); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     int* d_idx = nullptr;
-    if (idx && nidx > 0) {
-        for (int k = 0; k < nidx; k++)
-            if (idx[k] < 0 || idx[k] >= t->natoms) { set_error("atom index %d out of range", idx[k]); return GCB_ERR_INDEXES; }
-        GCB_CUDA(cudaMalloc(&d_idx, sizeof(int) * (size_t)nidx));
-        GCB_CUDA(cudaMemcpy(d_idx, idx, sizeof(int) * (size_t)nidx, cudaMemcpyHostToDevice));
-    }
+    int rc = upload_idx(t, idx, nidx, &d_idx);
+    if (rc) return rc;
     double* d_out = nullptr;
     cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)nrows * (size_t)nframes);
     if (e != cudaSuccess) { cudaFree(d_idx); set_error("cudaMalloc of the %ld x %ld output block failed", nrows, nframes); return GCB_ERR_ALLOC; }
-    int rc = allpairs_device(t, first, nframes, d_idx, nidx, row0, nrows, d_out, gemm_ms, redone, fit);
+    PeerOut po = {};
+    po.blk[0] = d_out; po.row0[0] = row0; po.row0[1] = row0 + nrows; po.nowners = 1;
+    rc = allpairs_device(t, first, nframes, d_idx, nidx, po, 0, 1, gemm_ms, redone, fit);
     if (rc == GCB_OK) {
         e = cudaMemcpy(out_host, d_out, sizeof(double) * (size_t)nrows * (size_t)nframes, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("copying the RMSD matrix back failed: %s", cudaGetErrorString(e)); rc = GCB_ERR_CUDA; }
@@ -605,4 +679,57 @@ extern "C" int gcb_allpairs_rmsd(gcb_traj* t, long first, long nframes, const in
 extern "C" int gcb_allpairs_rmsd_fit(gcb_traj* t, long first, long nframes, const int* idx, int nidx, long row0, long nrows,
                                      double* out_host, float* gemm_ms, long* redone) {
     return allpairs_entry(t, first, nframes, idx, nidx, row0, nrows, out_host, gemm_ms, redone, true);
+}
+
+// Multi-GPU matrix: see include/gochem_b200.h.  Rank r owns rows [r*base + min(r, rem), ...) (base = F / nranks); the
+// upper-triangle tiles are dealt round-robin, so every rank does the same share of the GEMM whatever rows it owns, and
+// the epilogue of each tile stores it -- and its mirror image -- into the owners' row blocks through the peer mappings
+// of comm (cudaIpc over NVLink).  A stream synchronisation plus a barrier across the ranks completes every block.
+extern "C" int gcb_allpairs_rmsd_sharded(gcb_traj* t, long first, long nframes, const int* idx, int nidx, int fit, gcb_comm* comm,
+                                         double* out_host_rows, long* row0_out, long* nrows_out, float* gemm_ms, float* total_ms,
+                                         long* redone) {
+    using namespace gcb;
+    if (!t || !comm) { set_error("NULL trajectory or communicator"); return GCB_ERR_ARG; }
+    if (first < 0 || nframes <= 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
+    if (nframes > 0x3fffffffL) { set_error("too many frames"); return GCB_ERR_ARG; }
+    if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
+    if (comm->nranks > kMaxPeers) { set_error("at most %d ranks", kMaxPeers); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    const int n = comm->nranks;
+    const long base = nframes / n, rem = nframes % n;
+    PeerOut po = {};
+    po.nowners = n;
+    for (int r = 0; r <= n; r++) po.row0[r] = (long)r * base + (r < rem ? r : rem);
+    const size_t blk_bytes = sizeof(double) * (size_t)(base + (rem ? 1 : 0)) * (size_t)nframes;
+    double* blk[kMaxPeers] = {nullptr};
+    int rc = comm_peer_blocks(comm, blk_bytes, blk);   // collective
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) po.blk[r] = blk[r];
+    int* d_idx = nullptr;
+    rc = upload_idx(t, idx, nidx, &d_idx);
+    if (rc) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GCB_CUDA(cudaEventCreate(&e0));
+    GCB_CUDA(cudaEventCreate(&e1));
+    rc = comm_barrier(comm, t->stream);                  // nobody stores into a block its owner may still be reading
+    if (rc == GCB_OK) {
+        cudaEventRecord(e0, t->stream);
+        rc = allpairs_device(t, first, nframes, d_idx, nidx, po, comm->rank, n, gemm_ms, redone, fit != 0);
+    }
+    if (rc == GCB_OK) rc = comm_barrier(comm, t->stream);   // every rank's kernels have completed: all blocks are whole
+    if (rc == GCB_OK) {
+        cudaEventRecord(e1, t->stream);
+        if (cudaStreamSynchronize(t->stream) != cudaSuccess) { set_error("all-pairs: stream synchronisation failed"); rc = GCB_ERR_CUDA; }
+    }
+    if (rc == GCB_OK && total_ms) cudaEventElapsedTime(total_ms, e0, e1);
+    const long my0 = po.row0[comm->rank], myn = po.row0[comm->rank + 1] - my0;
+    if (row0_out) *row0_out = my0;
+    if (nrows_out) *nrows_out = myn;
+    if (rc == GCB_OK && out_host_rows && myn > 0) {
+        cudaError_t e = cudaMemcpy(out_host_rows, blk[comm->rank], sizeof(double) * (size_t)myn * (size_t)nframes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("copying the RMSD row block back failed: %s", cudaGetErrorString(e)); rc = GCB_ERR_CUDA; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_idx);
+    return rc;
 }

@@ -12,6 +12,8 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace gcb {
@@ -24,6 +26,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -39,10 +44,14 @@ static NcclApi* nccl() {
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
             api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+            api.Broadcast = (decltype(api.Broadcast))dlsym(api.h, "ncclBroadcast");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(api.h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.h, "ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
         }
     }
-    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
+    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Broadcast || !api.GroupStart ||
+        !api.GroupEnd) {
         set_error("NCCL (libnccl.so.2) is not loadable: %s", api.h ? "missing symbols" : dlerror());
         return nullptr;
     }
@@ -70,15 +79,6 @@ __global__ void __launch_bounds__(256) rank_ordered_sum_kernel(const double* __r
 
 }  // namespace gcb
 
-struct gcb_comm {
-    int dev = 0, nranks = 1, rank = 0;
-    ncclComm_t comm = nullptr;
-    cudaStream_t stream = nullptr;
-    double* d_send = nullptr;
-    double* d_gather = nullptr;
-    long cap = 0;
-};
-
 using namespace gcb;
 
 static int comm_reserve(gcb_comm* c, long n) {
@@ -104,7 +104,101 @@ static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s) 
     return GCB_OK;
 }
 
+namespace gcb {
+
+// Completes when every rank has reached this point of its stream s (a one-byte-per-rank all-gather).
+int comm_barrier(gcb_comm* c, cudaStream_t s) {
+    if (c->nranks == 1) return GCB_OK;
+    NcclApi* api = nccl();
+    if (!api) return GCB_ERR_CUDA;
+    if (!c->d_flags) {
+        GCB_CUDA(cudaMalloc(&c->d_flags, 16 + 16 * (size_t)c->nranks));
+        GCB_CUDA(cudaMemset(c->d_flags, 0, 16 + 16 * (size_t)c->nranks));
+    }
+    GCB_NCCL(api, api->AllGather(c->d_flags, c->d_flags + 16, 16, ncclChar, c->comm, s));
+    return GCB_OK;
+}
+
+// Collective: every rank ends up with a device block of at least `bytes` bytes of its own and a mapping of every
+// other rank's block (cudaIpcOpenMemHandle: peer access over NVLink).  blk[r] = rank r's block as seen from here.
+// The blocks are kept in the communicator and reused while they are large enough.
+int comm_peer_blocks(gcb_comm* c, size_t bytes, double** blk) {
+    if (bytes > c->blk_bytes) {
+        NcclApi* api = c->nranks > 1 ? nccl() : nullptr;
+        if (c->nranks > 1 && !api) return GCB_ERR_CUDA;
+        GCB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < c->nranks; r++)
+            if (r != c->rank && c->peer_blk[r]) { cudaIpcCloseMemHandle(c->peer_blk[r]); c->peer_blk[r] = nullptr; }
+        if (c->nranks > 1) {   // every rank has dropped its mappings of the old blocks before anybody frees one
+            int rc = comm_barrier(c, c->stream);
+            if (rc) return rc;
+            GCB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        cudaFree(c->peer_blk[c->rank]);
+        c->peer_blk[c->rank] = nullptr;
+        c->blk_bytes = 0;
+        void* mine = nullptr;
+        GCB_CUDA(cudaMalloc(&mine, bytes));
+        c->peer_blk[c->rank] = (double*)mine;
+        if (c->nranks > 1) {
+            cudaIpcMemHandle_t h;
+            GCB_CUDA(cudaIpcGetMemHandle(&h, mine));
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+            unsigned char* d_h = nullptr;
+            GCB_CUDA(cudaMalloc(&d_h, 64 * (size_t)(c->nranks + 1)));
+            GCB_CUDA(cudaMemcpyAsync(d_h, &h, 64, cudaMemcpyHostToDevice, c->stream));
+            GCB_NCCL(api, api->AllGather(d_h, d_h + 64, 64, ncclChar, c->comm, c->stream));
+            std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+            GCB_CUDA(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+            GCB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(d_h);
+            for (int r = 0; r < c->nranks; r++) {
+                if (r == c->rank) continue;
+                void* p = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    set_error("cudaIpcOpenMemHandle of rank %d's block failed: %s (peer access over NVLink is required)", r, cudaGetErrorString(e));
+                    return GCB_ERR_CUDA;
+                }
+                c->peer_blk[r] = (double*)p;
+            }
+        }
+        c->blk_bytes = bytes;
+    }
+    for (int r = 0; r < c->nranks; r++) blk[r] = c->peer_blk[r];
+    return GCB_OK;
+}
+
+}  // namespace gcb
+
 extern "C" {
+
+// Frames sharded over the ranks -> every rank holds all of them: rank r's counts[r] frames sit at frame offset
+// counts[0] + ... + counts[r-1] of its own trajectory buffer; one grouped broadcast per rank fills the rest over NVLink.
+int gcb_traj_allgather(gcb_traj* t, gcb_comm* c, const long* counts) {
+    if (!t || !c || !counts) { set_error("bad all-gather arguments"); return GCB_ERR_ARG; }
+    if (c->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
+    long total = 0;
+    for (int r = 0; r < c->nranks; r++) { if (counts[r] < 0) { set_error("negative frame count"); return GCB_ERR_ARG; } total += counts[r]; }
+    if (total > t->cap) { set_error("all-gather of %ld frames into a trajectory of capacity %ld", total, t->cap); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    if (c->nranks > 1) {
+        NcclApi* api = nccl();
+        if (!api) return GCB_ERR_CUDA;
+        const size_t fd = 3 * (size_t)t->np;
+        GCB_NCCL(api, api->GroupStart());
+        long off = 0;
+        for (int r = 0; r < c->nranks; r++) {
+            double* p = t->d_frames + (size_t)off * fd;
+            if (counts[r] > 0) GCB_NCCL(api, api->Broadcast(p, p, (size_t)counts[r] * fd, ncclDouble, r, c->comm, t->stream));
+            off += counts[r];
+        }
+        GCB_NCCL(api, api->GroupEnd());
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    t->nframes = total;
+    return GCB_OK;
+}
 
 int gcb_comm_unique_id(char* id128) {
     if (!id128) return GCB_ERR_ARG;
@@ -147,7 +241,11 @@ int gcb_comm_destroy(gcb_comm* c) {
     if (!c) return GCB_OK;
     cudaSetDevice(c->dev);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    cudaFree(c->d_send); cudaFree(c->d_gather);
+    cudaFree(c->d_send); cudaFree(c->d_gather); cudaFree(c->d_flags);
+    for (int r = 0; r < c->nranks; r++) {
+        if (!c->peer_blk[r]) continue;
+        if (r == c->rank) cudaFree(c->peer_blk[r]); else cudaIpcCloseMemHandle(c->peer_blk[r]);
+    }
     NcclApi* api = nccl();
     if (api && c->comm) api->CommDestroy(c->comm);
     delete c;

@@ -98,7 +98,23 @@ struct gcb_traj {
     size_t h_scratch_bytes = 0;
 };
 
+// NCCL communicator wrapper (comm.cu) plus the peer-mapped row blocks of the multi-GPU all-pairs matrix
+struct ncclComm;
+struct gcb_comm {
+    int dev = 0, nranks = 1, rank = 0;
+    ncclComm* comm = nullptr;
+    cudaStream_t stream = nullptr;
+    double* d_send = nullptr;
+    double* d_gather = nullptr;
+    long cap = 0;
+    unsigned char* d_flags = nullptr;     // barrier scratch
+    double* peer_blk[8] = {nullptr};      // [rank] own block (cudaMalloc), others: cudaIpcOpenMemHandle mappings
+    size_t blk_bytes = 0;
+};
+
 namespace gcb {
+int comm_barrier(gcb_comm* c, cudaStream_t s);
+int comm_peer_blocks(gcb_comm* c, size_t bytes, double** blk);
 // kernels / launchers implemented across the .cu files
 int launch_upload_convert(gcb_traj* t, cudaStream_t s, const void* d_src, long first, long nframes, int layout, double scale);
 int launch_download_convert(gcb_traj* t, cudaStream_t s, double* d_dst, long first, long nframes);

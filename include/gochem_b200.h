@@ -144,6 +144,18 @@ int gcb_allpairs_rmsd(gcb_traj *t, long first, long nframes, const int *idx, int
 int gcb_allpairs_rmsd_fit(gcb_traj *t, long first, long nframes, const int *idx, int nidx, long row0, long nrows,
                           double *out_host, float *gemm_ms, long *redone);
 
+/* Multi-GPU form (one process per GPU, all on one NVLink/NVSwitch node).  Every rank holds ALL nframes frames (see
+ * gcb_traj_allgather).  The tiles on or above the diagonal are dealt round-robin to the ranks, so the GEMM work is split
+ * evenly; rank r owns the rows [r*base + min(r, rem), (r+1)*base + min(r+1, rem)) (base = nframes / nranks) and the
+ * epilogue of every tile stores the tile and its mirror image straight into the owners' row blocks through peer mappings
+ * of their device memory (cudaIpc over NVLink) -- compute and gather are one kernel, there is no separate exchange.
+ * Collective: every rank of comm must call it with the same arguments.  out_host_rows (may be NULL: the block stays in
+ * the communicator's device buffer) receives this rank's nrows x nframes block; row0_out / nrows_out say which rows.
+ * gemm_ms = this rank's GEMM kernel, total_ms = first barrier to last barrier on the device (both optional). */
+int gcb_allpairs_rmsd_sharded(gcb_traj *t, long first, long nframes, const int *idx, int nidx, int fit, gcb_comm *comm,
+                              double *out_host_rows, long *row0_out, long *nrows_out, float *gemm_ms, float *total_ms,
+                              long *redone);
+
 /* ---- per-frame centre of mass and moment tensor ----
  * chem.CenterOfMass (geometric.go:609-631) and chem.MomentTensor (geometric.go:705-733) for every frame of the window:
  * center[3F], moment[9F] (row-major symmetric 3x3).  mass: natoms entries or NULL (geometric centre, unit masses);
@@ -170,6 +182,9 @@ int gcb_comm_unique_id(char *id128);                       /* rank 0 creates, ho
 int gcb_comm_init(int dev, int nranks, int rank, const char *id128, gcb_comm **out);
 int gcb_comm_destroy(gcb_comm *c);
 int gcb_allreduce_sum_f64(gcb_comm *c, double *host_vec, long n); /* all-gather + rank-ordered sum */
+/* Frames sharded over the ranks -> every rank holds all of them: rank r's counts[r] frames already sit at frame offset
+ * counts[0] + ... + counts[r-1] of its own trajectory; grouped ncclBroadcast calls fill in the other ranks' frames. */
+int gcb_traj_allgather(gcb_traj *t, gcb_comm *c, const long *counts);
 
 #ifdef __cplusplus
 }

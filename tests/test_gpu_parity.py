@@ -328,6 +328,28 @@ def test_allpairs_rmsd_matrix(natoms, nframes):
     t.close()
 
 
+@pytest.mark.parametrize("fit", [False, True])
+def test_allpairs_sharded_entry_single_rank(fit):
+    """The multi-GPU entry point with a one-rank communicator: same tiles, same owner-directed epilogue, one owner."""
+    natoms, nframes = 211, 301
+    ref, frames = synth.make_case(natoms, nframes)
+    frames[9] = frames[4] + 1e-7
+    t = device_traj(frames)
+    t.super_rmsd(ref, write_back=True)
+    comm = _lib.Comm(0, 1, 0, _lib.Comm.unique_id())
+    got, row0, gms, tms, redone = t.allpairs_rmsd_sharded(comm, fit=fit)
+    want, _, _ = t.allpairs_rmsd(fit=fit)
+    assert row0 == 0 and got.shape == (nframes, nframes)
+    assert np.array_equal(got, want)
+    if not fit:
+        assert np.abs(got - _pairwise(t.download())).max() < 1e-9
+    # a second call reuses the communicator's block
+    again, _, _, _, _ = t.allpairs_rmsd_sharded(comm, fit=fit)
+    assert np.array_equal(again, got)
+    comm.close()
+    t.close()
+
+
 @pytest.mark.parametrize("natoms", [1500, 10000])
 def test_one_pass_rmsd_agrees_with_explicit_residual(natoms):
     """Fit-only calls take the RMSD from the inner products of the single sweep when that is provably accurate and
@@ -461,6 +483,8 @@ def test_moments_stream_kernel_chunked_frames(natoms, nframes):
     d = frames - oc[:, None, :]
     om = np.einsum("fi,fia,fib->fab", np.broadcast_to(mass, (nframes, natoms)), d, d)
     assert np.abs(cen - oc).max() < 1e-10
-    assert np.abs(mom - om).max() < 1e-10 * np.abs(om).max()
+    # one sweep: M = sum m x x^T - (sum m) c c^T, so the rounding error scales with sum m |x|^2 (a single atom has M = 0)
+    scale = (mass[None, :, None] * frames ** 2).sum(axis=(1, 2)).max()
+    assert np.abs(mom - om).max() < 1e-10 * np.abs(om).max() + 1e-14 * scale
     c0, m0 = oracle.center_and_moment(frames[nframes - 1], mass)
-    assert np.abs(cen[-1] - c0).max() < 1e-10 and np.abs(mom[-1] - m0).max() < 1e-10 * np.abs(m0).max()
+    assert np.abs(cen[-1] - c0).max() < 1e-10 and np.abs(mom[-1] - m0).max() < 1e-10 * np.abs(m0).max() + 1e-14 * scale

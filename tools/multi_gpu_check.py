@@ -50,6 +50,26 @@ out["lovo"] = {"N": got["N"], "iterations": got["Iterations"], "seconds": dt,
 g = [None] * world
 dist.all_gather_object(g, got["Natoms"].tobytes())
 out["natoms_identical_across_ranks"] = all(x == g[0] for x in g)
+# 3. all-pairs matrix: frames sharded -> all-gather over NVLink -> tiles dealt round-robin, stored straight into the owners' rows
+ap_frames, ap_atoms = int(os.environ.get("AP_FRAMES", "3000")), int(os.environ.get("AP_ATOMS", "600"))
+aref, asig = synth.make_reference(ap_atoms), synth.atom_sigmas(ap_atoms)
+counts = [H.shard_range(ap_frames, r, world)[1] for r in range(world)]
+afirst = sum(counts[:rank])
+ta = _lib.DeviceTraj(ap_atoms, ap_frames, dev=local)
+ta.synth_fill(aref, asig, counts[rank], first=afirst, frame_id0=afirst)      # only this rank's shard is filled
+ta.set_nframes(ap_frames)
+ta.super_rmsd(aref, first=afirst, nframes=counts[rank], write_back=True, want=())
+ta.allgather(comm, counts)
+for fit in (False, True):
+    blk, row0, gms, tms, redone = ta.allpairs_rmsd_sharded(comm, fit=fit)
+    blk2, _, gms, tms, redone = ta.allpairs_rmsd_sharded(comm, fit=fit)
+    want, _, _ = ta.allpairs_rmsd(row0=row0, nrows=blk.shape[0], fit=fit)   # same rows computed locally by the single-GPU path
+    ok = bool(np.array_equal(blk, want) and np.array_equal(blk2, want))
+    g = [None] * world
+    dist.all_gather_object(g, (ok, gms, tms))
+    out["allpairs_fit" if fit else "allpairs"] = {"blocks_equal_single_gpu": all(x[0] for x in g), "gemm_ms": [x[1] for x in g],
+                                                  "total_ms": [x[2] for x in g], "frames": ap_frames, "atoms": ap_atoms}
+ta.close()
 if rank == 0:
     whole = _lib.DeviceTraj(natoms, total, dev=local)
     whole.synth_fill(ref, sig, total)
