@@ -67,13 +67,27 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const double* __restri
     }
 }
 
-// column means of X (nframes x ncols), fixed order per column
-__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long ldx, int ncols, long nframes,
-                                                      double* __restrict__ mu) {
+// column means of X (nframes x ncols) in two fixed-order steps: sums over kColChunks row chunks (grid.y), then the chunks in order
+constexpr int kColChunks = 64;
+__global__ void __launch_bounds__(256) col_partial_kernel(const double* __restrict__ X, long ldx, int ncols, long nframes,
+                                                         double* __restrict__ partial) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    const long per = (nframes + kColChunks - 1) / kColChunks;
+    const long f0 = (long)blockIdx.y * per, f1 = (f0 + per < nframes) ? f0 + per : nframes;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long f = f0;
+    for (; f + 3 < f1; f += 4) {
+        s0 += X[f * ldx + c]; s1 += X[(f + 1) * ldx + c]; s2 += X[(f + 2) * ldx + c]; s3 += X[(f + 3) * ldx + c];
+    }
+    for (; f < f1; f++) s0 += X[f * ldx + c];
+    partial[(long)blockIdx.y * ncols + c] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ partial, int ncols, long nframes, double* __restrict__ mu) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     double s = 0.0;
-    for (long f = 0; f < nframes; f++) s += X[f * ldx + c];
+    for (int k = 0; k < kColChunks; k++) s += partial[(long)k * ncols + c];
     mu[c] = s / (double)nframes;
 }
 
@@ -518,7 +532,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     // (i): one row per frame, 3n columns.  (ii): three rows (planes) per frame, n columns.
     const int kdim = fit ? (d_idx ? round_up(nidx, 2) : t->np) : (d_idx ? round_up(3 * nidx, 2) : 3 * t->np);
     const long ld = kdim;
-    double *Y = nullptr, *mu = nullptr, *norms = nullptr, *X = nullptr;
+    double *Y = nullptr, *mu = nullptr, *norms = nullptr, *X = nullptr, *colpart = nullptr;
     int2* d_tiles = nullptr;
     PairList redo{nullptr, nullptr, 1u << 22};
     int rc = GCB_OK;
@@ -536,11 +550,30 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
             goto done;                                                                            \
         }                                                                                         \
     } while (0)
-    AP_TRY(cudaMalloc(&Y, sizeof(double) * (size_t)nframes * (size_t)(fit ? 3 * ld : ld)));
-    AP_TRY(cudaMalloc(&mu, sizeof(double) * (size_t)kdim));
-    AP_TRY(cudaMalloc(&norms, sizeof(double) * (size_t)nframes));
-    AP_TRY(cudaMalloc(&redo.count, sizeof(unsigned int)));
-    AP_TRY(cudaMalloc(&redo.pairs, sizeof(uint2) * (size_t)redo.cap));
+    {
+        // one workspace per trajectory handle, grown on demand and kept: no cudaMalloc / cudaFree (both synchronise the
+        // device) inside repeated calls
+        const size_t ybytes = sizeof(double) * (size_t)nframes * (size_t)(fit ? 3 * ld : ld);
+        const size_t ntile_max = (size_t)nt * ((size_t)nt + 1) / 2 + 1;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t oY = carve(ybytes), oX = carve(d_idx ? ybytes : 0), oMu = carve(sizeof(double) * (size_t)kdim),
+                     oPart = carve(sizeof(double) * (size_t)kdim * kColChunks), oNorm = carve(sizeof(double) * (size_t)nframes),
+                     oCnt = carve(sizeof(unsigned int)), oPairs = carve(sizeof(uint2) * (size_t)redo.cap),
+                     oTiles = carve(sizeof(int2) * ntile_max);
+        if (off > t->ap_ws_bytes) {
+            AP_TRY(cudaStreamSynchronize(s));
+            cudaFree(t->d_ap_ws);
+            t->d_ap_ws = nullptr;
+            t->ap_ws_bytes = 0;
+            AP_TRY(cudaMalloc(&t->d_ap_ws, off));
+            t->ap_ws_bytes = off;
+        }
+        unsigned char* w = (unsigned char*)t->d_ap_ws;
+        Y = (double*)(w + oY); X = (double*)(w + oX); mu = (double*)(w + oMu); colpart = (double*)(w + oPart);
+        norms = (double*)(w + oNorm); redo.count = (unsigned int*)(w + oCnt); redo.pairs = (uint2*)(w + oPairs);
+        d_tiles = (int2*)(w + oTiles);
+    }
     AP_TRY(cudaMemsetAsync(redo.count, 0, sizeof(unsigned int), s));
     {
         const double* src = t->d_frames + first * 3L * t->np;
@@ -550,7 +583,6 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
             int used = t->natoms;
             if (d_idx) {
                 // gather the subset into packed planes [x(idx) | y(idx) | z(idx)] with plane stride kdim
-                AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * 3 * (size_t)kdim));
                 gather_planes_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
                 GCB_LAUNCHED();
                 src = X;
@@ -561,13 +593,14 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
             GCB_LAUNCHED();
         } else {
             if (d_idx) {
-                AP_TRY(cudaMalloc(&X, sizeof(double) * (size_t)nframes * (size_t)ld));
                 gather_rows_kernel<<<t->sm_count * 8, 256, 0, s>>>(src, 3L * t->np, t->np, d_idx, nidx, kdim, nframes, X);
                 GCB_LAUNCHED();
                 src = X;
                 ldx = ld;
             }
-            col_mean_kernel<<<(kdim + 255) / 256, 256, 0, s>>>(src, ldx, kdim, nframes, mu);
+            col_partial_kernel<<<dim3((kdim + 255) / 256, kColChunks), 256, 0, s>>>(src, ldx, kdim, nframes, colpart);
+            GCB_LAUNCHED();
+            col_mean_kernel<<<(kdim + 255) / 256, 256, 0, s>>>(colpart, kdim, nframes, mu);
             GCB_LAUNCHED();
             centre_rows_kernel<<<t->sm_count * 4, 256, 0, s>>>(src, ldx, mu, Y, ld, kdim, nframes, norms);
             GCB_LAUNCHED();
@@ -589,7 +622,6 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
             }
     }
     if (tiles.empty()) tiles.push_back(make_int2(nt, nt));   // a block outside the matrix: nothing is stored
-    AP_TRY(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
     AP_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
     AP_TRY(cudaEventCreate(&e0));
     AP_TRY(cudaEventCreate(&e1));
@@ -628,7 +660,6 @@ done:
 #undef AP_TRY
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(Y); cudaFree(mu); cudaFree(norms); cudaFree(X); cudaFree(d_tiles); cudaFree(redo.count); cudaFree(redo.pairs);
     return rc;
 }
 

@@ -150,6 +150,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
     cudaFree(t->d_devpart); cudaFree(t->d_devsum);
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
+    cudaFree(t->d_ap_ws);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
     delete t;
     return GCB_OK;

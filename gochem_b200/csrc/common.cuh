@@ -93,6 +93,9 @@ struct gcb_traj {
     double* d_mom_c = nullptr;   // 3 per frame
     double* d_mom_m = nullptr;   // 9 per frame
     long mom_cap = 0, mom_frames = 0;
+    // all-pairs workspace (allpairs.cu): centred copy, norms, tile list, near-duplicate list
+    void* d_ap_ws = nullptr;
+    size_t ap_ws_bytes = 0;
     // host pinned scratch for small transfers
     double* h_scratch = nullptr;
     size_t h_scratch_bytes = 0;

@@ -53,10 +53,32 @@ def run(compute: bool):
     return time.perf_counter() - t0
 
 
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+if world > 1:   # all ranks of one node stream at the same time: each has its own ring, copy streams and PCIe link
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo")
+    barrier = dist.barrier
+else:
+    barrier = lambda: None
 run(True)
+barrier()
 copy_only = run(False)
+barrier()
 total = run(True)
 rm = t.fetch(0, chunk, want=("rmsd",))["rmsd"]
-print(json.dumps({"format": fmt, "nframes": nframes, "natoms": natoms, "chunk_frames": chunk, "seconds": total,
-                  "frames_per_s": nframes / total, "h2d_GBs": nframes * fbytes / total / 1e9, "copy_only_seconds": copy_only,
-                  "overlap_efficiency": copy_only / total, "rmsd_mean_last_chunk": float(rm.mean())}), flush=True)
+res = {"format": fmt, "nframes": nframes, "natoms": natoms, "chunk_frames": chunk, "seconds": total,
+       "frames_per_s": nframes / total, "h2d_GBs": nframes * fbytes / total / 1e9, "copy_only_seconds": copy_only,
+       "overlap_efficiency": copy_only / total, "rmsd_mean_last_chunk": float(rm.mean())}
+if world > 1:
+    g = [None] * world
+    dist.all_gather_object(g, res)
+    if rank == 0:
+        slowest = max(x["seconds"] for x in g)
+        print(json.dumps({"format": fmt, "world": world, "frames_per_rank": nframes, "natoms": natoms, "seconds_max_over_ranks": slowest,
+                          "frames_per_s_aggregate": world * nframes / slowest, "h2d_GBs_aggregate": world * nframes * fbytes / slowest / 1e9,
+                          "per_rank_h2d_GBs": [round(x["h2d_GBs"], 2) for x in g],
+                          "per_rank_overlap": [round(x["overlap_efficiency"], 3) for x in g]}), flush=True)
+    dist.destroy_process_group()
+else:
+    print(json.dumps(res), flush=True)
