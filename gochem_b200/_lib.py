@@ -75,6 +75,7 @@ def load() -> C.CDLL:
         "gcb_allpairs_rmsd": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_allpairs_rmsd_fit": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_moments": (I, [P, L, L, P, P, I, P, P]),
+        "gcb_rdf_cdf_sum": (I, [P, L, L, P, P, P, P, I, I, D, D, I, P, P, C.POINTER(L)]),
         "gcb_moments_async": (I, [P, L, L, P, P, I]),
         "gcb_moments_fetch": (I, [P, L, P, P]),
         "gcb_timer_start": (I, [P]),
@@ -316,6 +317,19 @@ class DeviceTraj:
         cen, mom = np.empty((n, 3)), np.empty((n, 3, 3))
         check(self.lib.gcb_moments(self.h, first, n, _ptr(m), _ptr(it), 0 if it is None else it.size, _ptr(cen), _ptr(mom)))
         return cen, mom
+
+    def rdf_cdf_sum(self, molid, chain, flags, refidx, com=False, step=0.1, end=10.0, cpus=1, comm=None, first=0, nframes=None):
+        """Frame loop of solv.ConcMolRDF -> (summed cumulative counts per shell, frames read)."""
+        n = self.nframes - first if nframes is None else nframes
+        m = np.ascontiguousarray(molid, dtype=np.int32)
+        c = np.ascontiguousarray(chain, dtype=np.int32)
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        r = _idx(refidx)
+        out = np.zeros(int(end / step))
+        read = C.c_long(0)
+        check(self.lib.gcb_rdf_cdf_sum(self.h, first, n, _ptr(m), _ptr(c), _ptr(f), _ptr(r), r.size, int(com), step, end, cpus,
+                                       comm.h if comm is not None else None, _ptr(out), C.byref(read)))
+        return out, read.value
 
     def moments_async(self, mass=None, idx=None, first=0, nframes=None):
         n = self.nframes - first if nframes is None else nframes

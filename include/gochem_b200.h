@@ -166,6 +166,21 @@ int gcb_moments(gcb_traj *t, long first, long nframes, const double *mass, const
 int gcb_moments_async(gcb_traj *t, long first, long nframes, const double *mass, const int *idx, int nidx);
 int gcb_moments_fetch(gcb_traj *t, long nframes, double *center, double *moment);
 
+/* ---- solvent shells around a solute ----
+ * The frame loop of solv.ConcMolRDF (solv/solvation.go:140-218): cdf_sum[k], k < (int)(end / step), is the sum over the frames
+ * of solv.FrameUMolCRDF (:380-410) -- per frame, the number of solvent residues whose distance to the solute (solv.DistRank,
+ * :447-541) is below (k+1)*step, minus one when that number is not zero.  MDFFromCDF (:317-352) is left to the host.
+ *   molid[natoms], chain[natoms]: Atom.MolID and an integer id of Atom.Chain (0 = the empty string).
+ *   flags[natoms]: bit 0 = Atom.MolName is in the `residues` argument, bit 1 = it is SOL / WAT / HOH (atoms of those are
+ *                  passed over when further than end + 3 from the first solute atom, :480-483).
+ *   refidx[nref]: the solute atoms; com: solv.Options.COM (distance from the residue's centre).
+ *   cpus: frames are consumed in chunks of cpus; a trailing partial chunk is not read (as with a DCD source, dcd.go:520-523).
+ *   comm (may be NULL): ranks hold disjoint frame shards; the counts and frames_read are summed over the ranks.
+ * Topologies in which one (MolID, chain) pair names two separate solvent residues are refused (GCB_ERR_ARG). */
+int gcb_rdf_cdf_sum(gcb_traj *t, long first, long nframes, const int *molid, const int *chain, const unsigned char *flags,
+                    const int *refidx, int nref, int com, double step, double end, int cpus, gcb_comm *comm,
+                    double *cdf_sum, long *frames_read);
+
 /* ---- stream timing on the stream the kernels run on ---- */
 int gcb_timer_start(gcb_traj *t);
 int gcb_timer_stop(gcb_traj *t, float *ms);

@@ -217,3 +217,55 @@ def center_and_moment(a, mass=None):
     if e:
         raise OracleError(e)
     return cen, mom
+
+
+# ---- solv: molecular RDF (solv/solvation.go) ----
+def _topo(molid, chain, flags):
+    return (np.ascontiguousarray(molid, dtype=np.int32), np.ascontiguousarray(chain, dtype=np.int32),
+            np.ascontiguousarray(flags, dtype=np.uint8))
+
+
+def dist_rank(coord, molid, chain, flags, refidx, com=False, end=10.0):
+    """solv.DistRank (solvation.go:447-541) -> (distances, molids) in scan order."""
+    coord = _f64(coord)
+    m, c, f = _topo(molid, chain, flags)
+    r, nr = _idx(refidx)
+    n = coord.shape[0]
+    d, ids = np.empty(max(n, 1)), np.empty(max(n, 1), dtype=np.int32)
+    cnt = lib().orc_dist_rank(_d(coord), n, _i(m), _i(c), f.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(r), nr, int(com),
+                              C.c_double(end), _d(d), _i(ids))
+    return d[:cnt].copy(), ids[:cnt].copy()
+
+
+def frame_umol_crdf(coord, molid, chain, flags, refidx, com=False, step=0.1, end=10.0):
+    """solv.FrameUMolCRDF (solvation.go:380-410)."""
+    coord = _f64(coord)
+    m, c, f = _topo(molid, chain, flags)
+    r, nr = _idx(refidx)
+    ret = np.empty(int(end / step) + 1)
+    n = lib().orc_frame_umol_crdf(_d(coord), coord.shape[0], _i(m), _i(c), f.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(r), nr,
+                                  int(com), C.c_double(step), C.c_double(end), _d(ret))
+    return ret[:n].copy()
+
+
+def rdf_cdf_sum(frames, molid, chain, flags, refidx, com=False, step=0.1, end=10.0, cpus=1):
+    """The frame loop of solv.ConcMolRDF (solvation.go:166-214) -> (summed cumulative counts, frames read)."""
+    frames = _f64(frames)
+    m, c, f = _topo(molid, chain, flags)
+    r, nr = _idx(refidx)
+    out = np.empty(int(end / step) + 1)
+    fn = lib().orc_rdf_cdf_sum
+    fn.restype = C.c_long
+    read = fn(_d(frames), C.c_long(frames.shape[0]), frames.shape[1], _i(m), _i(c), f.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(r), nr,
+              int(com), C.c_double(step), C.c_double(end), int(cpus), _d(out))
+    return out[:int(end / step)].copy(), int(read)
+
+
+def mdf_from_cdf(cdf_sum, framesread, A, B, step):
+    """solv.MDFFromCDF (solvation.go:317-352) -> (normalised density, average cumulative number)."""
+    ret = _f64(cdf_sum, copy=True)
+    ret2 = np.empty_like(ret)
+    rc = lib().orc_mdf_from_cdf(_d(ret), ret.size, int(framesread), C.c_double(A), C.c_double(B), C.c_double(step), _d(ret2))
+    if rc:
+        raise OracleError(rc)
+    return ret, ret2

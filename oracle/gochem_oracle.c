@@ -845,3 +845,155 @@ void orc_stable_sort_pairs(int *ids, double *vals, int n, int by_rmsd) {
 int orc_approx_eq(double i, double j, double eps) { return approx_eq(i, j, eps); }
 int orc_same_elements(const int *a, const int *b, int n) { return same_elements(a, b, n); }
 int orc_disagreement(const int *a, const int *b, int n) { return disagreement(a, b, n); }
+
+/* ------------------------------------------------------------------ */
+/* solv: molecular RDF / MDDF, solv/solvation.go   */
+/* ------------------------------------------------------------------ */
+/* Topology crosses as integers: molid[i] = Atom.MolID, chain[i] = an id of the Atom.Chain string (0 = the empty string,
+ * the zero value chain_skip starts with, solvation.go:457-459), flags[i] bit 0 = MolName is in the `residues` list,
+ * bit 1 = MolName is SOL / WAT / HOH (the names pre-screened at solvation.go:480-483). */
+
+/* solvation.go:692-695: temp.Sub(r, t); temp.Norm(2) */
+static double dist3(const double *r, const double *t) {
+    double d[3] = {r[0] - t[0], r[1] - t[1], r[2] - t[2]};
+    return frob(d, 3);
+}
+
+/* solv.MolShortestDist (solvation.go:669-690): smallest |ref_j - test_i|, starting from 100000 */
+static double mol_shortest_dist(const double *test, int ntest, const double *ref, int nref) {
+    double dclosest = 100000;
+    for (int i = 0; i < ntest; i++)
+        for (int j = 0; j < nref; j++) {
+            double d1 = dist3(ref + 3 * j, test + 3 * i);
+            if (d1 < dclosest) dclosest = d1;
+        }
+    return dclosest;
+}
+
+/* solv.DistRank (solvation.go:447-541).  out_dist / out_molid need room for natoms entries.  With com != 0 the
+ * residue is replaced by its geometric centre: the mass vector is only built when Masses() FAILS (solvation.go:523-526),
+ * so chem.CenterOfMass receives nil and returns the unweighted centre (geometric.go:615-618), its sum scaled by
+ * 1.0 / n (geometric.go:628-629). */
+int orc_dist_rank(const double *coord, int natoms, const int *molid, const int *chain, const unsigned char *flags,
+                  const int *refidx, int nref, int com, double end, double *out_dist, int *out_molid) {
+    if (nref <= 0) return 0;
+    double *ref = (double *)malloc(sizeof(double) * 3 * (size_t)nref);
+    double *test = (double *)malloc(sizeof(double) * 3 * (size_t)natoms);
+    int *own_id = (int *)malloc(sizeof(int) * (size_t)nref), *own_chain = (int *)malloc(sizeof(int) * (size_t)nref);
+    int nown = 0, count = 0;
+    for (int k = 0; k < nref; k++) {   /* allResIDandChains, solvation.go:418-427 */
+        int id = molid[refidx[k]], ch = chain[refidx[k]], rep = 0;
+        for (int q = 0; q < nown; q++) if (own_chain[q] == ch && own_id[q] == id) { rep = 1; break; }
+        if (!rep) { own_id[nown] = id; own_chain[nown] = ch; nown++; }
+        memcpy(ref + 3 * k, coord + 3 * (size_t)refidx[k], 3 * sizeof(double));   /* ref.SomeVecs(coord, refindexes) */
+    }
+    const double cutoff = end, cutoffplus = cutoff + 3;
+    int molid_skip = -1, chain_skip = 0;
+    for (int i = 0; i < natoms; i++) {
+        const int id = molid[i], ch = chain[i];
+        if ((flags[i] & 2) && dist3(ref, coord + 3 * (size_t)i) > cutoffplus) continue;   /* :481-483 */
+        int own = 0;
+        for (int q = 0; q < nown; q++) if (own_chain[q] == ch && own_id[q] == id) { own = 1; break; }
+        if ((flags[i] & 1) && !own && (id != molid_skip || ch != chain_skip)) {
+            int n = 0;
+            memcpy(test, coord + 3 * (size_t)i, 3 * sizeof(double));
+            n = 1;
+            for (int j = i + 1; j < natoms; j++) {   /* :490-496: only MolID is compared */
+                if (molid[j] != id) break;
+                memcpy(test + 3 * n, coord + 3 * (size_t)j, 3 * sizeof(double));
+                n++;
+            }
+            double distance;
+            if (com) {
+                double c[3] = {0, 0, 0};
+                for (int a = 0; a < n; a++) { c[0] += test[3 * a] * 1.0; c[1] += test[3 * a + 1] * 1.0; c[2] += test[3 * a + 2] * 1.0; }
+                const double inv = 1.0 / (double)n;
+                c[0] *= inv; c[1] *= inv; c[2] *= inv;
+                distance = mol_shortest_dist(c, 1, ref, nref);
+            } else {
+                distance = mol_shortest_dist(test, n, ref, nref);
+            }
+            if (distance <= cutoff) { out_dist[count] = distance; out_molid[count] = id; count++; }
+            molid_skip = id;
+            chain_skip = ch;
+        }
+    }
+    free(ref); free(test); free(own_id); free(own_chain);
+    return count;
+}
+
+static int cmp_double(const void *a, const void *b) {
+    const double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+/* solv.FrameUMolCRDF (solvation.go:380-410): ret[i-1] = n(i) with n = sort.SearchFloat64s(dists, i*step) (the number
+ * of distances below the limit), reduced by one when it is not zero (:402-404).  Returns totalsteps = int(end/step). */
+int orc_frame_umol_crdf(const double *coord, int natoms, const int *molid, const int *chain, const unsigned char *flags,
+                        const int *refidx, int nref, int com, double step, double end, double *ret) {
+    const int totalsteps = (int)(end / step);
+    double *d = (double *)malloc(sizeof(double) * (size_t)(natoms > 0 ? natoms : 1));
+    int *ids = (int *)malloc(sizeof(int) * (size_t)(natoms > 0 ? natoms : 1));
+    const int cnt = orc_dist_rank(coord, natoms, molid, chain, flags, refidx, nref, com, end, d, ids);
+    qsort(d, (size_t)cnt, sizeof(double), cmp_double);
+    for (int i = 1; i <= totalsteps; i++) {
+        const double limit = (double)i * step;
+        int lo = 0, hi = cnt;   /* smallest index with d[idx] >= limit */
+        while (lo < hi) { int mid = lo + (hi - lo) / 2; if (d[mid] < limit) lo = mid + 1; else hi = mid; }
+        int n = lo;
+        if (n > 0) n--;
+        ret[i - 1] = (double)n;
+    }
+    free(d); free(ids);
+    return totalsteps;
+}
+
+/* solv.MDFFromCDF (solvation.go:317-352).  ret (the summed cumulative counts) is overwritten with the normalised
+ * density, ret2 receives the average cumulative number per shell.  Returns -1 when A or B < 1. */
+int orc_mdf_from_cdf(double *ret, int n, int framesread, double A, double B, double step, double *ret2) {
+    if (A < 1.0 || B < 1.0) return ORC_ERR_SHAPE;
+    const double vp = (4.0 / 3.0) * M_PI * A * B;
+    double acc = 0.0, vol;
+    for (int i = 0; i < n; i++) ret2[i] = 0.0;
+    for (int i = 0; i < n; i++) {
+        if (i >= 1) {
+            acc = acc + ret[i - 1];
+            ret2[i] = ret[i];
+            ret[i] = ret[i] - acc;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        if (i >= 1) {
+            const double fi = (double)i;
+            vol = vp * (pow((fi + 1) * step, 3) - pow(fi * step, 3));
+        } else {
+            vol = vp * pow(step, 3);
+        }
+        ret[i] = ret[i] / (double)framesread;
+        ret2[i] = ret2[i] / (double)framesread;
+        ret[i] = ret[i] / vol;
+    }
+    const double last = ret[n - 1];
+    for (int i = 0; i < n; i++) ret[i] = ret[i] / last;
+    return ORC_OK;
+}
+
+/* The frame loop of solv.ConcMolRDF (solvation.go:166-214): frames are taken cpus at a time and every frame read adds its
+ * FrameUMolCRDF to the sum (:200-206); a trailing chunk a reader cannot fill is lost (dcd.go:520-523 returns no channels).
+ * cdf_sum[totalsteps] is the sum before MDFFromCDF.  Returns the number of frames read. */
+long orc_rdf_cdf_sum(const double *frames, long F, int natoms, const int *molid, const int *chain, const unsigned char *flags,
+                     const int *refidx, int nref, int com, double step, double end, int cpus, double *cdf_sum) {
+    const int totalsteps = (int)(end / step);
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)(totalsteps > 0 ? totalsteps : 1));
+    for (int k = 0; k < totalsteps; k++) cdf_sum[k] = 0.0;
+    long read = 0;
+    if (cpus < 1) cpus = 1;
+    for (long c0 = 0; c0 + cpus <= F; c0 += cpus)
+        for (int s = 0; s < cpus; s++) {
+            orc_frame_umol_crdf(frames + (size_t)(c0 + s) * 3 * (size_t)natoms, natoms, molid, chain, flags, refidx, nref, com, step, end, tmp);
+            for (int k = 0; k < totalsteps; k++) cdf_sum[k] = cdf_sum[k] + tmp[k];
+            read++;
+        }
+    free(tmp);
+    return read;
+}

@@ -178,3 +178,39 @@ def lovo(frames, ref, fullindexes, cpus, less_than_rmsd=1.0, minimum_n=10, max_i
     by_id = sorted(range(len(ids)), key=lambda k: ids[k])
     return dict(N=n, Natoms=np.array(indexesold[:n]), RMSD=np.array([svals[k] for k in by_id]),
                 FramesRead=total, Iterations=it)
+
+
+# ---- solv: molecular RDF, second restatement (numpy, no shared code with the C oracle) ----
+def frame_umol_crdf(coord, molid, chain, flags, refidx, com=False, step=0.1, end=10.0):
+    """solv.DistRank + FrameUMolCRDF (solvation.go:380-410, 447-541), written from the description of what they compute:
+    for every solvent residue (first non-pre-screened atom to the last atom with the same MolID) the minimum distance to the
+    solute, kept when <= end; ret[i-1] = max(#{d < i*step} - 1, 0)."""
+    coord = np.asarray(coord, dtype=np.float64)
+    n = coord.shape[0]
+    ref = coord[np.asarray(refidx)]
+    own = {(int(molid[i]), int(chain[i])) for i in refidx}
+    dists = []
+    skip = (-1, 0)
+    i = 0
+    for i in range(n):
+        key = (int(molid[i]), int(chain[i]))
+        if flags[i] & 2 and np.linalg.norm(ref[0] - coord[i]) > end + 3:
+            continue
+        if flags[i] & 1 and key not in own and key != skip:
+            j = i + 1
+            while j < n and molid[j] == molid[i]:
+                j += 1
+            test = coord[i:j]
+            if com:
+                test = (test.sum(axis=0) * (1.0 / (j - i)))[None, :]
+            d = np.sqrt(((ref[None, :, :] - test[:, None, :]) ** 2).sum(axis=2)).min()
+            d = min(d, 100000.0)
+            if d <= end:
+                dists.append(d)
+            skip = key
+    dists = np.sort(np.array(dists))
+    out = []
+    for k in range(1, int(end / step) + 1):
+        c = int(np.searchsorted(dists, k * step, side="left"))
+        out.append(float(c - 1 if c > 0 else 0))
+    return np.array(out)
