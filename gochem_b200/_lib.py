@@ -56,6 +56,7 @@ def load() -> C.CDLL:
         "gcb_set_rmsd_mode": (I, [I]),
         "gcb_pinned_alloc": (I, [C.c_size_t, C.POINTER(P)]),
         "gcb_pinned_free": (I, [P]),
+        "gcb_bind_host_thread": (I, [I]),
         "gcb_traj_create": (I, [I, I, L, C.POINTER(P)]),
         "gcb_traj_destroy": (I, [P]),
         "gcb_traj_natoms": (I, [P]),

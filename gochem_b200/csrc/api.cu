@@ -5,7 +5,9 @@
 // chem.MassCenter, /root/reference/geometric.go:670-703, on every call; here it is centred once per
 // call and reused by every frame), staging copies, launches.  All arithmetic on frames runs in the
 // CUDA kernels; there is no CPU fallback.
+#include <sched.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -124,6 +126,39 @@ int gcb_pinned_alloc(size_t bytes, void** p) {
     if (!p) return GCB_ERR_ARG;
     *p = nullptr;
     GCB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return GCB_OK;
+}
+
+// Run the calling thread on the CPUs next to device `dev` (its PCIe root's NUMA node, sysfs local_cpulist), so that the pinned
+// buffers it allocates afterwards and the reader threads filling them are NUMA-local to the GPU's link.
+int gcb_bind_host_thread(int dev) {
+    char bus[32] = {0};
+    GCB_CUDA(cudaDeviceGetPCIBusId(bus, sizeof bus, dev));
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) { set_error("gcb_bind_host_thread: %s is not readable", path); return GCB_ERR_ARG; }
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int ncpu = 0;
+    if (got) {
+        for (char* p = line; *p;) {   // "0-31,64-95"
+            char* end = nullptr;
+            long a = strtol(p, &end, 10);
+            if (end == p) break;
+            long b = a;
+            p = end;
+            if (*p == '-') { b = strtol(p + 1, &end, 10); p = end; }
+            for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, &set); ncpu++; }
+            if (*p == ',') p++; else break;
+        }
+    }
+    if (ncpu == 0) { set_error("gcb_bind_host_thread: no CPU list for device %d (%s)", dev, path); return GCB_ERR_ARG; }
+    if (sched_setaffinity(0, sizeof set, &set) != 0) { set_error("gcb_bind_host_thread: sched_setaffinity failed"); return GCB_ERR_ARG; }
     return GCB_OK;
 }
 

@@ -283,4 +283,63 @@ int gch_lovo_resident(void* traj_handle, long nlocal, long nselected_total, cons
     return 0;
 }
 
+
+int gch_mdf_from_cdf(double* r, int n, int framesread, double A, double B, double step, double* ret2) {
+    std::vector<double> v(r, r + n), v2;
+    if (Error e = solv::MDFFromCDF(v, framesread, A, B, step, &v2)) return fail(e);
+    for (int i = 0; i < n; i++) { r[i] = v[(size_t)i]; ret2[i] = v2[(size_t)i]; }
+    return 0;
+}
+
+int gch_ellipsoid_axes(const double* coords, int n, const double* masses, double* rhos3) {
+    chem::Topology top;
+    top.Atoms.resize((size_t)n);
+    for (int i = 0; i < n; i++) top.Atoms[(size_t)i].Mass = masses ? masses[i] : 1.0;
+    std::vector<double> rhos;
+    if (Error e = solv::EllipsoidAxes(mat(coords, n), 0.0001, &top, &rhos)) return fail(e);
+    for (int k = 0; k < 3; k++) rhos3[k] = rhos[(size_t)k];
+    return 0;
+}
+
+int gch_conc_mol_rdf(const char* dcd_path, const double* coords0, int natoms, const char* const* molnames, const int* molids,
+                     const char* const* chains, const double* masses, const int* refidx, int nref, const char* const* residues,
+                     int nres, int com, int cpus, double step, double end, int dev, int rank, int nranks, void* comm, double* rdf,
+                     double* cumulative, int* frames_read) {
+    chem::Molecule mol;
+    mol.Atoms.resize((size_t)natoms);
+    for (int i = 0; i < natoms; i++) {
+        chem::Atom& a = mol.Atoms[(size_t)i];
+        a.MolName = molnames[i];
+        a.MolID = molids[i];
+        a.Chain = chains[i];
+        a.Mass = masses ? masses[i] : 0.0;
+    }
+    mol.Coords.push_back(mat(coords0, natoms));
+    std::unique_ptr<solv::Options> o(solv::DefaultOptions());
+    const bool c = com != 0;
+    o->COM(&c);
+    o->Cpus(&cpus);
+    o->Step(&step);
+    o->End(&end);
+    o->DeviceID(&dev);
+    o->Shard(rank, nranks, static_cast<gcb_comm*>(comm));
+    std::unique_ptr<chem::ConcTraj> traj;
+    if (Error e = align::opentraj(dcd_path, &traj)) return fail(e);
+    std::vector<std::string> res;
+    for (int i = 0; i < nres; i++) res.emplace_back(residues[i]);
+    std::vector<double> r1, r2;
+    int fr = 0;
+    Error e;
+    try {
+        e = solv::ConcMolRDF(*traj, mol, std::vector<int>(refidx, refidx + nref), res, &r1, &r2, o.get(), &fr);
+    } catch (const v3::PanicMsg& p) {
+        e = Error(std::string("panic: ") + p.what());
+    }
+    traj->Close();
+    if (e) return fail(e);
+    for (size_t i = 0; i < r1.size(); i++) { rdf[i] = r1[i]; cumulative[i] = r2[i]; }
+    if (frames_read) *frames_read = fr;
+    return 0;
+}
+
 }  // extern "C"

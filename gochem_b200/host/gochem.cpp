@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -1025,4 +1026,172 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
 }
 
 }  // namespace align
+
+// =====================================================================================================================
+namespace chem {
+
+Error Topology::Masses(std::vector<double>* out) const {  // chem.go:291-301
+    out->assign((size_t)Len(), 0.0);
+    for (int i = 0; i < Len(); i++) {
+        if (Atoms[(size_t)i].Mass == 0) {
+            out->clear();
+            return Error("goChem: Not all the masses have been obtained: " + std::to_string(i), {"Topology.Masses"});
+        }
+        (*out)[(size_t)i] = Atoms[(size_t)i].Mass;
+    }
+    return Error();
+}
+
+void Topology::SomeAtoms(const Atomer& T2, const std::vector<int>& indexes) {
+    Atoms.clear();
+    for (int i : indexes) Atoms.push_back(T2.Atom(i));
+}
+
+}  // namespace chem
+
+namespace solv {
+
+static const double kAppZero = 0.000000000001;  // matrixhelp.go:40
+
+Options* DefaultOptions() {
+    Options* o = new Options();
+    const unsigned hc = std::thread::hardware_concurrency();
+    o->cpus_ = hc ? (int)hc : 1;  // runtime.NumCPU()
+    return o;
+}
+
+// eigenvalues of a symmetric 3 x 3 matrix (cyclic Jacobi): stands in for mat.Eigen inside v3.EigenWrap (v3/gonum.go:363-401)
+static void symEigenvalues3(const double* m, double* ev) {
+    double a[3][3] = {{m[0], m[1], m[2]}, {m[3], m[4], m[5]}, {m[6], m[7], m[8]}};
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; k++) {  // columns
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq;
+                    a[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; k++) {  // rows
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk;
+                    a[q][k] = sn * apk + c * aqk;
+                }
+            }
+    }
+    ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
+}
+
+Error EllipsoidAxes(const v3::Matrix& coords, double /*epsilon*/, const chem::Topology* mol, std::vector<double>* rhos) {
+    std::vector<double> masses;
+    Error err2;
+    if (mol) {
+        if (Error e = mol->Masses(&masses)) { masses.clear(); err2 = e; }  // solvation.go:46-51
+    }
+    v3::Matrix moment;
+    if (Error e = chem::MomentTensor(coords, &moment, masses)) return e;
+    double ev[3];
+    symEigenvalues3(moment.data(), ev);
+    std::sort(ev, ev + 3);  // EigenWrap sorts the pairs by eigenvalue, ascending (v3/gonum.go:343-345, 400-401)
+    if (ev[2] <= kAppZero)  // geometric.go:535-537
+        return Error("goChem: Molecule colapsed to a single point. Check for blackholes", {"Rhos"});
+    rhos->assign({ev[2], ev[1], ev[0]});  // largest first (geometric.go:538-544)
+    return err2;
+}
+
+Error MDFFromCDF(std::vector<double>& ret, int framesread, double A, double B, double step, std::vector<double>* ret2) {
+    if (A < 1.0 || B < 1.0)
+        return Error("goChem/solvation.MDFFromCDF: A and B are the ratio between the lartest axis of an elipsoid to the smallest, they can't be smaller than 1.0");
+    const size_t n = ret.size();
+    ret2->assign(n, 0.0);
+    const double vp = (4.0 / 3.0) * M_PI * A * B;
+    double vol, acc = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        if (i >= 1) {
+            acc = acc + ret[i - 1];
+            (*ret2)[i] = ret[i];
+            ret[i] = ret[i] - acc;
+        }
+    }
+    for (size_t i = 0; i < n; i++) {
+        if (i >= 1) {
+            const double fi = (double)i;
+            vol = vp * (std::pow((fi + 1) * step, 3) - std::pow(fi * step, 3));
+        } else {
+            vol = vp * std::pow(step, 3);
+        }
+        ret[i] = ret[i] / (double)framesread;
+        (*ret2)[i] = (*ret2)[i] / (double)framesread;
+        ret[i] = ret[i] / vol;
+    }
+    if (n) {
+        const double last = ret[n - 1];
+        for (size_t i = 0; i < n; i++) ret[i] = ret[i] / last;
+    }
+    return Error();
+}
+
+static bool isInString(const std::vector<std::string>& c, const std::string& t) { return std::find(c.begin(), c.end(), t) != c.end(); }
+
+Error ConcMolRDF(chem::ConcTraj& traj, const chem::Molecule& mol, const std::vector<int>& refindexes,
+                 const std::vector<std::string>& residues, std::vector<double>* rdf, std::vector<double>* cumulative, Options* opt,
+                 int* frames_read) {
+    std::unique_ptr<Options> owned;
+    Options* o = opt;
+    if (!o) { owned.reset(DefaultOptions()); o = owned.get(); }
+    const int natoms = mol.Len();
+    for (int i : refindexes)
+        if (i < 0 || i >= natoms) throw v3::PanicMsg("goChem/v3: index out of range");  // SomeVecs panics (v3/gonum.go:513-532)
+    double A = 1.0, B = 1.0;
+    if (natoms > 1) {  // solvation.go:149-162
+        if (mol.Coords.empty()) return Error("goChem: the molecule holds no coordinates", {"ConcMolRDF"});
+        v3::Matrix scoords = v3::Matrix::Zeros((int)refindexes.size());
+        scoords.SomeVecs(mol.Coords[0], refindexes);
+        chem::Topology smol;
+        smol.SomeAtoms(mol, refindexes);
+        std::vector<double> elip;
+        if (Error e = EllipsoidAxes(scoords, 0.0001, &smol, &elip)) return e;
+        A = elip[0] / elip[2];
+        B = elip[1] / elip[2];
+    }
+    // the frame loop: every full chunk of o.cpus frames is read (solvation.go:166-214); the frames go to the device once
+    align::Options ao;
+    ao.cpus_ = o->cpus_;
+    ao.device_ = o->device_;
+    ao.rank_ = o->rank_;
+    ao.nranks_ = o->nranks_;
+    std::unique_ptr<align::DeviceTrajectory> d;
+    if (Error e = align::DeviceTrajectory::Load(traj, natoms, ao, &d)) return errDecorate(e, "ConcMolRDF");
+    std::vector<int> molid((size_t)natoms), chain((size_t)natoms);
+    std::vector<unsigned char> flags((size_t)natoms);
+    std::map<std::string, int> chain_ids;
+    chain_ids[""] = 0;
+    static const std::vector<std::string> waters = {"SOL", "WAT", "HOH"};  // solvation.go:481
+    for (int i = 0; i < natoms; i++) {
+        const chem::Atom& at = mol.Atom(i);
+        molid[(size_t)i] = at.MolID;
+        auto it = chain_ids.find(at.Chain);
+        if (it == chain_ids.end()) it = chain_ids.emplace(at.Chain, (int)chain_ids.size()).first;
+        chain[(size_t)i] = it->second;
+        flags[(size_t)i] = (unsigned char)((isInString(residues, at.MolName) ? 1 : 0) | (isInString(waters, at.MolName) ? 2 : 0));
+    }
+    const int totalsteps = (int)(o->end_ / o->step_);
+    std::vector<double> ret((size_t)(totalsteps > 0 ? totalsteps : 0), 0.0);
+    long read = 0;
+    int rc = gcb_rdf_cdf_sum(d->Handle(), 0, d->LocalFrames(), molid.data(), chain.data(), flags.data(), refindexes.data(),
+                             (int)refindexes.size(), o->com_ ? 1 : 0, o->step_, o->end_, 1, o->comm_, ret.data(), &read);
+    if (rc) return deviceError(rc, "ConcMolRDF");
+    if (frames_read) *frames_read = (int)read;
+    if (Error e = MDFFromCDF(ret, (int)read, A, B, o->step_, cumulative)) return e;
+    *rdf = std::move(ret);
+    return Error();
+}
+
+}  // namespace solv
 }  // namespace gochem

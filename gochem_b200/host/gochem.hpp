@@ -108,6 +108,8 @@ struct Atom {
     std::string Name;
     int MolID = 0;
     std::string Chain;
+    std::string MolName;  // residue / molecule name (solv.DistRank reads it, solvation.go:475-476)
+    double Mass = 0.0;    // 0 = not known (Topology.Masses fails, chem.go:291-301)
 };
 class Atomer {  // interfaces.go:67-75
   public:
@@ -120,6 +122,13 @@ class Topology : public Atomer {
     std::vector<chem::Atom> Atoms;
     const chem::Atom& Atom(int i) const override { return Atoms.at((size_t)i); }
     int Len() const override { return (int)Atoms.size(); }
+    Error Masses(std::vector<double>* out) const;                      // chem.go:291-301
+    void SomeAtoms(const Atomer& T2, const std::vector<int>& indexes);  // chem.go: copies the listed atoms
+};
+// chem.Molecule (chem.go): a topology plus its frames; only what solv.ConcMolRDF reads.
+class Molecule : public Topology {
+  public:
+    std::vector<v3::Matrix> Coords;
 };
 
 class Traj {  // interfaces.go:36-49
@@ -212,6 +221,40 @@ class DCDWObj {
 };
 
 }  // namespace dcd
+
+namespace solv {
+
+// solv.Options (solv/solvation.go:65-138), same getter/setter idiom as the Go methods.
+class Options {
+  public:
+    bool COM(const bool* c = nullptr) { const bool r = com_; if (c) com_ = *c; return r; }
+    int Cpus(const int* n = nullptr) { const int r = cpus_; if (n && *n > 0) cpus_ = *n; return r; }
+    int Skip(const int* n = nullptr) { const int r = skip_; if (n && *n > 0) skip_ = *n; return r; }
+    double Step(const double* s = nullptr) { const double r = step_; if (s && *s > 0) step_ = *s; return r; }
+    double End(const double* e = nullptr) { const double r = end_; if (e && *e > 0) end_ = *e; return r; }
+    // additions for the device path
+    int DeviceID(const int* d = nullptr) { if (d && *d >= 0) device_ = *d; return device_; }
+    void Shard(int rank, int nranks, gcb_comm* comm) { rank_ = rank; nranks_ = nranks; comm_ = comm; }
+
+    bool com_ = false;
+    int cpus_ = 1;
+    double step_ = 0.1, end_ = 10.0;
+    int skip_ = 1;
+    int device_ = 0, rank_ = 0, nranks_ = 1;
+    gcb_comm* comm_ = nullptr;
+};
+Options* DefaultOptions();  // solvation.go:75-83: com false, cpus = hardware threads, step 0.1, end 10, skip 1
+
+// solvation.go:39-63: the eigenvalues of the moment tensor, largest first (chem.Rhos, geometric.go:523-545).
+Error EllipsoidAxes(const v3::Matrix& coords, double epsilon, const chem::Topology* mol, std::vector<double>* rhos);
+// solvation.go:317-352.  ret (summed cumulative counts) is overwritten with the normalised density; ret2 = mean cumulative number.
+Error MDFFromCDF(std::vector<double>& ret, int framesread, double A, double B, double step, std::vector<double>* ret2);
+// solvation.go:140-218.  The frame loop (DistRank + FrameUMolCRDF for every frame) runs on the device.
+Error ConcMolRDF(chem::ConcTraj& traj, const chem::Molecule& mol, const std::vector<int>& refindexes,
+                 const std::vector<std::string>& residues, std::vector<double>* rdf, std::vector<double>* cumulative,
+                 Options* o = nullptr, int* frames_read = nullptr);
+
+}  // namespace solv
 
 namespace align {
 

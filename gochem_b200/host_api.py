@@ -249,3 +249,47 @@ def LOVOResident(traj, ref, nselected_total=None, cpus=8, less_than_rmsd=1.0, mi
     if rc:
         raise _err(rc)
     return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm.copy(), FramesRead=total, Iterations=it.value)
+
+
+# ---- solv (solv/solvation.go) ----
+def MDFFromCDF(cdf_sum, framesread, A, B, step):
+    ret = np.array(cdf_sum, dtype=np.float64, copy=True)
+    ret2 = np.zeros_like(ret)
+    rc = load().gch_mdf_from_cdf(_d(ret), ret.size, int(framesread), C.c_double(A), C.c_double(B), C.c_double(step), _d(ret2))
+    if rc:
+        raise _err(rc)
+    return ret, ret2
+
+
+def EllipsoidAxes(coords, masses=None):
+    c = np.ascontiguousarray(coords, dtype=np.float64)
+    m = None if masses is None else np.ascontiguousarray(masses, dtype=np.float64)
+    out = np.zeros(3)
+    rc = load().gch_ellipsoid_axes(_d(c), c.shape[0], _d(m), _d(out))
+    if rc:
+        raise _err(rc)
+    return out
+
+
+def _cstrings(items):
+    arr = (C.c_char_p * len(items))(*[s.encode() for s in items])
+    return arr
+
+
+def ConcMolRDF(dcd_path, coords0, molnames, molids, chains, masses, refindexes, residues, com=False, cpus=1, step=0.1, end=10.0,
+               dev=0, rank=0, nranks=1, comm=None):
+    """solv.ConcMolRDF (solvation.go:140-218) on a DCD file -> (rdf, cumulative, frames read)."""
+    c0 = np.ascontiguousarray(coords0, dtype=np.float64)
+    n = c0.shape[0]
+    ids = np.ascontiguousarray(molids, dtype=np.int32)
+    ms = None if masses is None else np.ascontiguousarray(masses, dtype=np.float64)
+    ref = np.ascontiguousarray(refindexes, dtype=np.int32)
+    steps = int(end / step)
+    rdf, cum = np.zeros(steps), np.zeros(steps)
+    fr = C.c_int(0)
+    rc = load().gch_conc_mol_rdf(dcd_path.encode(), _d(c0), n, _cstrings(list(molnames)), _i(ids), _cstrings(list(chains)), _d(ms),
+                                 _i(ref), ref.size, _cstrings(list(residues)), len(residues), int(com), int(cpus), C.c_double(step),
+                                 C.c_double(end), dev, rank, nranks, comm, _d(rdf), _d(cum), C.byref(fr))
+    if rc:
+        raise _err(rc)
+    return rdf, cum, fr.value

@@ -71,6 +71,9 @@ int gcb_last_cluster_plan(int *out8);
 /* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
 int gcb_pinned_alloc(size_t bytes, void **p);
 int gcb_pinned_free(void *p);
+/* Pin the calling thread to the CPUs local to device dev's PCIe link (sysfs local_cpulist) before allocating staging buffers,
+ * so the pinned memory is NUMA-local to the GPU.  Optional; an error leaves the affinity unchanged. */
+int gcb_bind_host_thread(int dev);
 
 /* ---- device trajectory: the v3 device-matrix batch ---- */
 int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj **out);

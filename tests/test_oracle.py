@@ -207,3 +207,28 @@ def test_center_of_mass_and_moment_tensor():
         assert np.abs(cen - c2).max() < 1e-13
         assert np.abs(mom - (d * w[:, None]).T @ d).max() < 1e-10
         assert np.array_equal(mom, mom.T)
+
+
+def test_rdf_two_restatements_agree():
+    """solv.DistRank / FrameUMolCRDF: the C restatement against the numpy one on a small solvated system."""
+    from oracle import oracle_np
+    rng = np.random.default_rng(3)
+    ns, nw = 40, 200
+    sol = rng.normal(0, 4, (ns, 3))
+    wo = rng.uniform(-18, 18, (nw, 3))
+    wat = (wo[:, None, :] + np.concatenate([np.zeros((nw, 1, 3)), rng.normal(0, 0.6, (nw, 2, 3))], axis=1)).reshape(-1, 3)
+    ions = rng.uniform(-15, 15, (20, 3))
+    coord = np.concatenate([sol, wat, ions])
+    molid = np.concatenate([np.repeat(np.arange(1, 5), 10), 5 + np.repeat(np.arange(nw), 3), 5 + nw + np.arange(20)])
+    chain = np.concatenate([np.ones(ns), np.full(3 * nw + 20, 2)]).astype(int)
+    flags = np.concatenate([np.zeros(ns), np.full(3 * nw, 3), np.full(20, 1)]).astype(np.uint8)
+    for com in (False, True):
+        a = oracle.frame_umol_crdf(coord, molid, chain, flags, np.arange(ns), com=com)
+        b = oracle_np.frame_umol_crdf(coord, molid, chain, flags, np.arange(ns), com=com)
+        assert a[-1] > 20 and np.array_equal(a, b)
+    # FrameUMolCRDF's "minus one" (solvation.go:402-404) and MDFFromCDF's closed form for a uniform count
+    cdf = np.arange(100, dtype=float)
+    rdf, cum = oracle.mdf_from_cdf(cdf * 7, 7, 1.0, 1.0, 0.1)
+    assert np.allclose(cum[1:], cdf[1:]) and rdf[-1] == 1.0
+    with pytest.raises(oracle.OracleError):
+        oracle.mdf_from_cdf(cdf, 1, 0.5, 1.0, 0.1)

@@ -29,6 +29,10 @@ if fmt == "f32soa":
     host = np.ascontiguousarray(host.astype(np.float32).transpose(0, 2, 1))
 elif fmt == "f32aos":
     host = host.astype(np.float32)
+if os.environ.get("GCB_NUMA_BIND", "1") == "1":
+    rc = _lib.load().gcb_bind_host_thread(dev)     # pinned ring NUMA-local to this GPU's PCIe link
+    if rc:
+        print("bind_host_thread:", _lib.last_error(), file=sys.stderr)
 ring = [_lib.PinnedBuffer(chunk * fbytes) for _ in range(2)]
 views = [r.view(dt, host.shape) for r in ring]
 for v in views:
