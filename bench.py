@@ -313,6 +313,36 @@ def run_ours(a):
            "pinned_numa_local": bool(numa_bound),
            "path": "pinned float64 AoS host frames -> gcb_traj_upload_async (2 slots) -> gcb_super_rmsd_async -> gcb_fetch_results"}
     e2e_check = float(np.abs(out_rmsd - rmsd_gpu[:e2e_frames]).max()) if not wb else None
+    # the same loop fed as a DCD reader feeds it: float32 x[] y[] z[] records in pinned memory (dcd.go:380-413), widened on the device
+    if numa_bound:
+        lib.gcb_bind_host_thread(dev)
+    pinned32 = _lib.PinnedBuffer(e2e_frames * frame_bytes // 2)
+    pv32 = pinned32.view(np.float32, (e2e_frames, 3, natoms))
+    pv32[...] = host_sample.astype(np.float32).transpose(0, 2, 1)
+    os.sched_setaffinity(0, affinity)
+    chunk32 = max(1, min(e2e_frames, (64 << 20) // (frame_bytes // 2)))
+
+    def e2e_step32():
+        k = 0
+        for first in range(0, e2e_frames, chunk32):
+            n = min(chunk32, e2e_frames - first)
+            e2e_traj.upload_async(pv32[first:first + n], n, first, _lib.F32_SOA, 1.0, k & 1)
+            e2e_traj.super_rmsd_async(ref, first=first, nframes=n, write_back=wb)
+            k += 1
+        return e2e_traj.fetch(0, e2e_frames, want=("rmsd",))["rmsd"]
+
+    e2e_step32()
+    d.barrier()
+    e2e_traj.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step32()
+    e2e_traj.sync()
+    e2e32_dt = d.max(time.perf_counter() - t0)
+    d.barrier()
+    e2e["f32_soa_feed"] = {"value": e2e_frames * d.world * e2e_steps / e2e32_dt, "unit": UNIT,
+                           "h2d_bytes_per_step": e2e_frames * frame_bytes // 2,
+                           "note": "same calls, host frames as float32 DCD records (what traj/dcd decodes), widened on the device"}
 
     # CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample of the same frames
     cpu = None
