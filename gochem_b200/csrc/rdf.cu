@@ -9,9 +9,10 @@
 // The topology is static, so the host turns it into "runs" (maximal stretches of consecutive atoms with one MolID:
 // the reference extends a residue from its first atom while the MolID stays the same, :490-496).  What depends on the
 // frame is (a) where a water run starts -- atoms of SOL/WAT/HOH further than end+3 from the first solute atom are passed
-// over before a residue begins (:480-483) -- and (b) the distances.  One CTA per frame; one thread per run; the solute
-// streams through shared memory in tiles.  An atom further from the solute's bounding sphere than `end` cannot come
-// within `end` of any solute atom, so it is skipped without changing any kept distance.  Counts are integers: the
+// over before a residue begins (:480-483) -- and (b) the distances.  One CTA per frame.  Runs are examined 1024 at a time:
+// those that begin a residue within reach of the solute are compacted into a dense list (most of a solvent box is not), then
+// one thread per listed residue ranks it against the solute, which streams through shared memory in tiles.  An atom
+// further from the solute's bounding sphere than `end` cannot come within `end` of any solute atom, so it is skipped without changing any kept distance.  Counts are integers: the
 // accumulation over frames (64-bit atomics) is exact and order-independent.
 //
 // Compute-bound (pairs x 7 fp64 operations), not HBM-bound: frames are read once, the solute once per tile.
@@ -28,7 +29,8 @@ namespace {
 
 constexpr int RT = 256;          // threads per CTA = runs per block of runs
 constexpr int kRefTile = 1024;   // solute atoms per shared-memory tile
-constexpr int kMaxSteps = 4096;
+constexpr int kMaxSteps = 2048;
+constexpr int kRunChunk = 1024;  // runs examined per compaction round
 
 struct Run {
     int s, e;   // atoms [s, e)
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
     __shared__ unsigned int hist[kMaxSteps + 1];
     __shared__ double red[RT / 32][4];
     __shared__ double sphere[4];   // centre of the solute's bounding sphere, radius
+    __shared__ int list_s[kRunChunk], list_e[kRunChunk];   // residues of the current chunk that can be within the cutoff: atoms [s, e)
+    __shared__ int nlist;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cutoff = p.end, cutoffplus = p.end + 3.0;
     for (long f = blockIdx.x; f < p.nframes; f += gridDim.x) {
@@ -96,14 +100,16 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
         const int a0 = p.refidx[0];
         const double fx = X[a0], fy = Y[a0], fz = Z[a0];   // ref.VecView(0)
 
-        for (int rb = 0; rb < p.nruns; rb += RT) {
-            const int r = rb + tid;
-            int start = -1, stop = 0;
-            double px = 0.0, py = 0.0, pz = 0.0;   // COM mode: the residue's centre
-            bool active = false;
-            if (r < p.nruns) {
+        bool tile_ready = false;   // CTA-uniform
+        for (int rb = 0; rb < p.nruns; rb += kRunChunk) {
+            // ---- step A: which runs of this chunk begin a residue within reach of the solute?  (compacted into a dense list) ----
+            __syncthreads();
+            if (tid == 0) nlist = 0;
+            __syncthreads();
+            const int rend = min(rb + kRunChunk, p.nruns);
+            for (int r = rb + tid; r < rend; r += RT) {
                 const Run run = p.runs[r];
-                stop = run.e;
+                int start = -1;
                 for (int a = run.s; a < run.e; a++) {   // first atom that begins the residue (solvation.go:478-486)
                     const unsigned char fl = p.flags[a];
                     if (fl & 2) {
@@ -112,69 +118,90 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
                     }
                     if (fl & 1) { start = a; break; }
                 }
-                if (start >= 0) {
-                    if (p.com) {   // chem.CenterOfMass with nil masses: column sums in row order times 1/n (geometric.go:615-629)
-                        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-                        for (int a = start; a < stop; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
-                        const double inv = 1.0 / (double)(stop - start);
-                        px = c0 * inv; py = c1 * inv; pz = c2 * inv;
-                        const double dx = px - cx, dy = py - cy, dz = pz - cz;
+                if (start < 0) continue;
+                bool active = false;
+                if (p.com) {
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                    for (int a = start; a < run.e; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
+                    const double inv = 1.0 / (double)(run.e - start);
+                    const double dx = c0 * inv - cx, dy = c1 * inv - cy, dz = c2 * inv - cz;
+                    active = dx * dx + dy * dy + dz * dz <= reach2;
+                } else {
+                    for (int a = start; a < run.e && !active; a++) {
+                        const double dx = X[a] - cx, dy = Y[a] - cy, dz = Z[a] - cz;
                         active = dx * dx + dy * dy + dz * dz <= reach2;
-                    } else {
-                        for (int a = start; a < stop && !active; a++) {
-                            const double dx = X[a] - cx, dy = Y[a] - cy, dz = Z[a] - cz;
-                            active = dx * dx + dy * dy + dz * dz <= reach2;
-                        }
                     }
                 }
+                if (active) {
+                    const int slot = atomicAdd(&nlist, 1);
+                    list_s[slot] = start;
+                    list_e[slot] = run.e;
+                }
             }
-            double best = 1e10;   // squared; MolShortestDist starts from 100000 (:674)
-            for (int t0 = 0; t0 < p.nref; t0 += kRefTile) {
-                const int tn = min(kRefTile, p.nref - t0);
-                __syncthreads();
-                for (int j = tid; j < tn; j += RT) { const int a = p.refidx[t0 + j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
-                __syncthreads();
-                if (!active) continue;
-                if (p.com) {
-                    double b0 = best, b1 = best;
-                    int j = 0;
-                    for (; j + 1 < tn; j += 2) {
-                        const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz;
-                        const double ex = rx[j + 1] - px, ey = ry[j + 1] - py, ez = rz[j + 1] - pz;
-                        b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
-                        b1 = fmin(b1, fma(ez, ez, fma(ey, ey, ex * ex)));
+            __syncthreads();
+            // ---- step B: every listed residue against the whole solute, one thread per residue ----
+            const int nl = nlist;
+            for (int base = 0; base < nl; base += RT) {
+                const bool mine = base + tid < nl;
+                const int start = mine ? list_s[base + tid] : 0, stop = mine ? list_e[base + tid] : 0;
+                double px = 0.0, py = 0.0, pz = 0.0;   // COM mode: the residue's centre
+                if (mine && p.com) {   // chem.CenterOfMass with nil masses: column sums in row order times 1/n (geometric.go:615-629)
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                    for (int a = start; a < stop; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
+                    const double inv = 1.0 / (double)(stop - start);
+                    px = c0 * inv; py = c1 * inv; pz = c2 * inv;
+                }
+                double best = 1e10;   // squared; MolShortestDist starts from 100000 (:674)
+                for (int t0 = 0; t0 < p.nref; t0 += kRefTile) {
+                    const int tn = min(kRefTile, p.nref - t0);
+                    if (p.nref > kRefTile || !tile_ready) {   // a solute of one tile is loaded once per frame
+                        __syncthreads();
+                        for (int j = tid; j < tn; j += RT) { const int a = p.refidx[t0 + j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
+                        __syncthreads();
+                        tile_ready = true;
                     }
-                    if (j < tn) { const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
-                    best = fmin(b0, b1);
-                } else {
-                    for (int a = start; a < stop; a++) {
-                        const double ax = X[a], ay = Y[a], az = Z[a];
-                        {
-                            const double dx = ax - cx, dy = ay - cy, dz = az - cz;
-                            if (dx * dx + dy * dy + dz * dz > reach2) continue;
-                        }
+                    if (!mine) continue;
+                    if (p.com) {
                         double b0 = best, b1 = best;
                         int j = 0;
                         for (; j + 1 < tn; j += 2) {
-                            const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az;
-                            const double ex = rx[j + 1] - ax, ey = ry[j + 1] - ay, ez = rz[j + 1] - az;
+                            const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz;
+                            const double ex = rx[j + 1] - px, ey = ry[j + 1] - py, ez = rz[j + 1] - pz;
                             b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
                             b1 = fmin(b1, fma(ez, ez, fma(ey, ey, ex * ex)));
                         }
-                        if (j < tn) { const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
+                        if (j < tn) { const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
                         best = fmin(b0, b1);
+                    } else {
+                        for (int a = start; a < stop; a++) {
+                            const double ax = X[a], ay = Y[a], az = Z[a];
+                            {
+                                const double dx = ax - cx, dy = ay - cy, dz = az - cz;
+                                if (dx * dx + dy * dy + dz * dz > reach2) continue;
+                            }
+                            double b0 = best, b1 = best;
+                            int j = 0;
+                            for (; j + 1 < tn; j += 2) {
+                                const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az;
+                                const double ex = rx[j + 1] - ax, ey = ry[j + 1] - ay, ez = rz[j + 1] - az;
+                                b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
+                                b1 = fmin(b1, fma(ez, ez, fma(ey, ey, ex * ex)));
+                            }
+                            if (j < tn) { const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
+                            best = fmin(b0, b1);
+                        }
                     }
                 }
-            }
-            if (active) {
-                const double d = sqrt(best);
-                if (d <= cutoff) {
-                    // smallest i >= 1 with d < i*step (the limits of solvation.go:398-399, same product)
-                    int i = (int)(d / p.step);
-                    if (i < 1) i = 1;
-                    while (i > 1 && d < (double)(i - 1) * p.step) i--;
-                    while (i <= p.nsteps && !(d < (double)i * p.step)) i++;
-                    if (i <= p.nsteps) atomicAdd(&hist[i], 1u);
+                if (mine) {
+                    const double d = sqrt(best);
+                    if (d <= cutoff) {
+                        // smallest i >= 1 with d < i*step (the limits of solvation.go:398-399, same product)
+                        int i = (int)(d / p.step);
+                        if (i < 1) i = 1;
+                        while (i > 1 && d < (double)(i - 1) * p.step) i--;
+                        while (i <= p.nsteps && !(d < (double)i * p.step)) i++;
+                        if (i <= p.nsteps) atomicAdd(&hist[i], 1u);
+                    }
                 }
             }
         }
