@@ -29,7 +29,6 @@
 // Per-warp squared-error partials of pass 2 go to a small global array and a trailing kernel finishes
 // rmsd[f] = sqrt(sum E[f][..] / n) in fixed order for the flagged frames.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "kabsch3.cuh"
@@ -50,8 +49,6 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxSlots = 13;            // exchange slots (>= 2*D+1 with D <= 6, and > kSolverWarps)
 constexpr int kMaxCluster = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kSmemBudget2 = 113 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
-constexpr int kSlots2 = 7;                 // exchange slots of the two-CTAs-per-SM instances (depth <= 3)
 
 struct ClusterParams {
     SuperParams p;
@@ -107,18 +104,16 @@ __device__ long long g_trace[8][512];
 #define TRACE(row, j) do {} while (0)
 #endif
 
-template <int NSLOTS>
-struct __align__(16) SharedT {
+struct __align__(16) Shared {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t part_full[NSLOTS];        // cluster -> solver: every CTA's partial sums of a frame have landed
-    uint64_t solved[NSLOTS];           // solver -> consumers: xf[slot] holds the frame's transform
-    double partials[NSLOTS][kMaxCluster][14];   // 12 sums + sum w|a|^2
-    double xf[NSLOTS][16];             // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
-    double red[NSLOTS][kConsumerWarps][14];   // [..][12] = squared error of the frame D iterations earlier
-    unsigned int red_count[NSLOTS];    // consumer warps that have delivered red[slot]; the last one sums and pushes
+    uint64_t part_full[kMaxSlots];        // cluster -> solver: every CTA's partial sums of a frame have landed
+    uint64_t solved[kMaxSlots];           // solver -> consumers: xf[slot] holds the frame's transform
+    double partials[kMaxSlots][kMaxCluster][14];   // 12 sums + sum w|a|^2
+    double xf[kMaxSlots][16];             // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
+    double red[kMaxSlots][kConsumerWarps][14];   // [..][12] = squared error of the frame D iterations earlier
+    unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
-using Shared = SharedT<kMaxSlots>;
 
 // sqrt of a non-negative double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
 // error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
@@ -142,7 +137,7 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 // stride np, streaming loads).  WB = also store the superposed coordinates.
 // MASKED: the fit uses a subset of the atoms (fit_mask bit k = slot k is in it); otherwise every real atom is.
 // DEV: per-atom distances are accumulated and the frame's squared error is not (align.RMSDTraj never asks for it).
-template <int K, bool MASKED, bool DEV, bool WB, bool RESIDENT, int CH>
+template <int K, bool MASKED, bool DEV, bool WB, bool RESIDENT>
 __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, long plane, const double* xf,
                                               const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
                                               uint32_t fit_mask, double (&dev)[DEV ? K : 1], double* frw, int np,
@@ -150,7 +145,7 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
-    // CH = atoms in flight per thread: enough independent chains, bounded register use
+    constexpr int CH = (K % 5 == 0) ? 5 : 4;   // atoms in flight per thread: enough independent chains, bounded register use
 #pragma unroll
     for (int kb = 0; kb < K; kb += CH) {
         double x[CH], y[CH], z[CH];
@@ -193,23 +188,18 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     return e0 + e1;
 }
 
-// MB = CTAs per SM the instance is built for.  MB = 2 (<= 80 registers per thread, half the shared memory, thin parts of <= 5
-// atoms per thread) puts two independent CTAs -- usually of different clusters, i.e. different frames -- on every SM: four
-// consumer warps per scheduler instead of two hide the fixed-latency fp64 dependencies of the per-atom-distance pass.
-template <int K, bool MASKED, bool DEV, bool RESIDENT, int MB>
-__global__ void __launch_bounds__(kThreadsCta, MB) super_cluster_kernel(const ClusterParams cp) {
+template <int K, bool MASKED, bool DEV, bool RESIDENT>
+__global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using Sh = SharedT<(MB == 2 ? kSlots2 : kMaxSlots)>;
-    Sh& sh = *reinterpret_cast<Sh*>(smem_raw);
+    Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
     constexpr int kStageDoubles = 3 * K * kConsumers;
-    double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Sh) + 127) / 128) * 128);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 127) / 128) * 128);
 
     const SuperParams& p = cp.p;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int C = cp.cluster, S = cp.stages, D = cp.depth, G = cp.nclusters;
-    constexpr int NS = (MB == 2 ? kSlots2 : kMaxSlots);
-    constexpr int kChunk = MB == 2 ? (K <= 3 ? K : 2) : ((K % 5 == 0) ? 5 : 4);   // pass-2 atoms in flight (80 registers when MB = 2)
+    constexpr int NS = kMaxSlots;
     const uint32_t rank = cluster_ctarank();
     const long cid = cluster_id_x();
     const int part0 = (int)rank * cp.part;                       // first atom of this CTA's part
@@ -450,14 +440,14 @@ __global__ void __launch_bounds__(kThreadsCta, MB) super_cluster_kernel(const Cl
                     }
                 } else if (RESIDENT) {
                     const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true, kChunk>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, MASKED, DEV, false, true, kChunk>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
                     if (++s2 == S) s2 = 0;
                 } else {
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false, kChunk>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, MASKED, DEV, false, false, kChunk>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                 }
                 if (run_pass2 && !DEV) {
 #pragma unroll
@@ -495,30 +485,28 @@ __global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restri
 }
 
 struct Plan {
-    int cluster, part, kinst, stages, depth, resident, mb;
+    int cluster, part, kinst, stages, depth, resident;
     size_t smem;
 };
 
 constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14};
 
 // tuning overrides (0 / -1 = built-in choice)
-int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0, g_tune_resident = -1, g_tune_mb = 0;
+int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0, g_tune_resident = -1;
 int g_force_explicit = 0;
 
 // Choose CTAs per frame, atoms per thread, stage count, pipeline depth.
 //  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
 //  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
-bool make_plan(int np, bool heavy, int mb, Plan* pl) {
-    const size_t fixed = mb == 2 ? ((sizeof(SharedT<kSlots2>) + 127) / 128) * 128 : ((sizeof(Shared) + 127) / 128) * 128;
-    const int budget = mb == 2 ? kSmemBudget2 : kSmemBudget;
+bool make_plan(int np, bool heavy, Plan* pl) {
+    const size_t fixed = ((sizeof(Shared) + 127) / 128) * 128;
     // Measured on B200 (profiles/r1_tuning.md).  Fit-only passes skip pass 2 for almost every frame, so the stage can be
     // released right after pass 1 (pass 2, when needed, re-reads the part from L2): two stages of the fattest part that
     // fits win (up to 14 atoms per thread, fewest CTAs per frame, clusters of <= 3 tile the GPCs almost exactly).
     // Passes that always run pass 2 (write-back, per-atom sums) keep the part resident in shared memory: <= 10 atoms per
     // thread, >= 3 stages.
     const int resident = g_tune_resident >= 0 ? g_tune_resident : (heavy ? 1 : 0);
-    const int kmax = mb == 2 ? 5 : (resident ? 10 : 14);
-    if (mb == 2 && !resident) return false;
+    const int kmax = resident ? (heavy ? 10 : 10) : 14;
     for (int c = 1; c <= kMaxCluster; c++) {
         if (g_tune_cluster && c != g_tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
@@ -528,7 +516,7 @@ bool make_plan(int np, bool heavy, int mb, Plan* pl) {
         if (!kinst) continue;
         if (!g_tune_cluster && kinst > kmax && c < kMaxCluster) continue;
         const size_t stage = (size_t)3 * kinst * kConsumers * sizeof(double);
-        int stages = (int)((budget - fixed) / stage);
+        int stages = (int)((kSmemBudget - fixed) / stage);
         if (stages > kMaxStages) stages = kMaxStages;
         if (!resident && stages > (kinst <= 6 ? 4 : 2)) stages = (kinst <= 6 ? 4 : 2);
         if (g_tune_stages && g_tune_stages < stages) stages = g_tune_stages;
@@ -537,14 +525,12 @@ bool make_plan(int np, bool heavy, int mb, Plan* pl) {
         if (resident) {
             depth = stages - 2 > 2 ? 2 : stages - 2;
             if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && g_tune_depth <= 6) depth = g_tune_depth;
-            if (mb == 2 && depth > (kSlots2 - 1) / 2) depth = (kSlots2 - 1) / 2;
         } else {
             depth = kinst <= 6 ? 6 : 3;   // costs no shared memory here: only the exchange slots
             if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
         }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
         pl->resident = resident;
-        pl->mb = mb;
         pl->smem = fixed + stage * stages;
         return true;
     }
@@ -553,9 +539,9 @@ bool make_plan(int np, bool heavy, int mb, Plan* pl) {
 
 int g_last_plan[8] = {0};
 
-template <int K, bool W, bool DV, bool RES, int MB = 1>
+template <int K, bool W, bool DV, bool RES>
 int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
-    auto kern = super_cluster_kernel<K, W, DV, RES, MB>;
+    auto kern = super_cluster_kernel<K, W, DV, RES>;
     GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -568,7 +554,7 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     cfg.blockDim = dim3(kThreadsCta);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = t->stream;
-    cfg.gridDim = dim3(pl.cluster * (MB * t->sm_count / pl.cluster));
+    cfg.gridDim = dim3(pl.cluster * (t->sm_count / pl.cluster));
     int max_clusters = 0;
     GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters < 1) { set_error("cluster of %d CTAs with %zu bytes of shared memory cannot be scheduled", pl.cluster, pl.smem); return GCB_ERR_CUDA; }
@@ -581,23 +567,12 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     GCB_LAUNCHED();
     *nclusters_out = (int)g;
     g_last_plan[0] = pl.cluster; g_last_plan[1] = pl.part; g_last_plan[2] = pl.kinst; g_last_plan[3] = pl.stages;
-    g_last_plan[4] = pl.depth; g_last_plan[5] = pl.resident | (pl.mb == 2 ? 2 : 0); g_last_plan[6] = (int)g; g_last_plan[7] = (int)pl.smem;
+    g_last_plan[4] = pl.depth; g_last_plan[5] = pl.resident; g_last_plan[6] = (int)g; g_last_plan[7] = (int)pl.smem;
     return GCB_OK;
 }
 
 template <bool W, bool DV, bool RES>
 int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g) {
-    if constexpr (DV && RES) {
-        if (pl.mb == 2) {
-            switch (pl.kinst) {
-                case 1: return launch_inst<1, W, DV, RES, 2>(t, cp, pl, g);
-                case 2: return launch_inst<2, W, DV, RES, 2>(t, cp, pl, g);
-                case 3: return launch_inst<3, W, DV, RES, 2>(t, cp, pl, g);
-                case 4: return launch_inst<4, W, DV, RES, 2>(t, cp, pl, g);
-                case 5: return launch_inst<5, W, DV, RES, 2>(t, cp, pl, g);
-            }
-        }
-    }
     switch (pl.kinst) {
         case 1: return launch_inst<1, W, DV, RES>(t, cp, pl, g);
         case 2: return launch_inst<2, W, DV, RES>(t, cp, pl, g);
@@ -645,18 +620,12 @@ void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
 
 bool cluster_kernel_supported(const gcb_traj* t) {
     Plan pl;
-    return make_plan(t->np, false, 1, &pl);
+    return make_plan(t->np, false, &pl);
 }
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
     Plan pl;
-    const bool heavy = want_dev || p.frames_rw != nullptr || g_force_explicit;
-    // two CTAs per SM: built for the per-atom-distance pass only
-    const char* env_mb = getenv("GCB_TUNE_MB");
-    const int want_mb = env_mb ? atoi(env_mb) : g_tune_mb;
-    bool planned = false;
-    if (want_mb == 2 && want_dev && !p.frames_rw) planned = make_plan(t->np, heavy, 2, &pl) && pl.resident;
-    if (!planned && !make_plan(t->np, heavy, 1, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    if (!make_plan(t->np, want_dev || p.frames_rw != nullptr || g_force_explicit, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     const int dev = t->dev & 15;
     const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * kConsumerWarps;
     if (need > g_epart_cap[dev]) {
