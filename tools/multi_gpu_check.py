@@ -70,6 +70,28 @@ for fit in (False, True):
     out["allpairs_fit" if fit else "allpairs"] = {"blocks_equal_single_gpu": all(x[0] for x in g), "gemm_ms": [x[1] for x in g],
                                                   "total_ms": [x[2] for x in g], "frames": ap_frames, "atoms": ap_atoms}
 ta.close()
+# 4. solvent shells (gcb_rdf_cdf_sum): frames sharded, integer counts summed over the ranks == single-GPU counts
+rng = np.random.default_rng(5)
+nsol, nwat, rf = 60, 900, 64 * world
+base = np.concatenate([rng.normal(0, 4, (nsol, 3)), np.repeat(rng.uniform(-20, 20, (nwat, 3)), 3, axis=0) + rng.normal(0, 0.5, (3 * nwat, 3))])
+rframes = base[None] + rng.normal(0, 0.4, (rf, base.shape[0], 3))
+molid = np.concatenate([np.repeat(np.arange(1, 7), 10), 7 + np.repeat(np.arange(nwat), 3)]).astype(np.int32)
+chain = np.concatenate([np.ones(nsol), np.full(3 * nwat, 2)]).astype(np.int32)
+flags = np.concatenate([np.zeros(nsol), np.full(3 * nwat, 3)]).astype(np.uint8)
+r0, rc = H.shard_range(rf, rank, world)
+tr = _lib.DeviceTraj(base.shape[0], max(rc, 1), dev=local)
+tr.upload(rframes[r0:r0 + rc])
+got_cdf, got_read = tr.rdf_cdf_sum(molid, chain, flags, np.arange(nsol), comm=comm)
+tr.close()
+g = [None] * world
+dist.all_gather_object(g, got_cdf.tobytes())
+out["rdf"] = {"identical_across_ranks": all(x == g[0] for x in g), "frames_read": got_read}
+if rank == 0:
+    tw = _lib.DeviceTraj(base.shape[0], rf, dev=local)
+    tw.upload(rframes)
+    want_cdf, want_read = tw.rdf_cdf_sum(molid, chain, flags, np.arange(nsol))
+    tw.close()
+    out["rdf"]["equal_single_gpu"] = bool(np.array_equal(want_cdf, got_cdf) and want_read == got_read)
 if rank == 0:
     whole = _lib.DeviceTraj(natoms, total, dev=local)
     whole.synth_fill(ref, sig, total)
