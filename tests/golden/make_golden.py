@@ -46,7 +46,29 @@ def lovo_case(name, natoms, nframes, cpus):
                         Iterations=res["Iterations"], first_pass_rmsd=rm, first_pass_frames=total)
 
 
+def rdf_case(name, nsolute=40, nwater=220, nions=12, nframes=10, seed=21, box=17.0):
+    """solv.ConcMolRDF's frame loop on a small solvated system, from the numpy restatement (oracle_np.frame_umol_crdf)."""
+    rng = np.random.default_rng(seed)
+    sol = rng.normal(0, 4, (nsolute, 3))
+    wo = rng.uniform(-box, box, (nwater, 3))
+    wat = (wo[:, None, :] + np.concatenate([np.zeros((nwater, 1, 3)), rng.normal(0, 0.6, (nwater, 2, 3))], axis=1)).reshape(-1, 3)
+    base = np.concatenate([sol, wat, rng.uniform(-box, box, (nions, 3))])
+    frames = (base[None] + rng.normal(0, 0.5, (nframes,) + base.shape)).astype(np.float32)
+    molid = np.concatenate([np.repeat(np.arange(1, 5), nsolute // 4), 5 + np.repeat(np.arange(nwater), 3), 5 + nwater + np.arange(nions)]).astype(np.int32)
+    chain = np.concatenate([np.ones(nsolute), np.full(3 * nwater + nions, 2)]).astype(np.int32)
+    flags = np.concatenate([np.zeros(nsolute), np.full(3 * nwater, 3), np.full(nions, 1)]).astype(np.uint8)
+    refidx = np.arange(nsolute, dtype=np.int32)
+    out = {}
+    for com in (0, 1):
+        per = np.array([onp.frame_umol_crdf(frames[f].astype(np.float64), molid, chain, flags, refidx, com=bool(com), step=0.1, end=10.0)
+                        for f in range(nframes)])
+        out["cdf_frames_com%d" % com] = per
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), frames=frames, molid=molid, chain=chain, flags=flags, refidx=refidx,
+                        step=0.1, end=10.0, **out)
+
+
 if __name__ == "__main__":
+    rdf_case("rdf_small")
     super_case("super_all_n50", 50, 6)
     super_case("super_subset_n203", 203, 5, idx=list(range(3, 203, 4)))
     super_case("super_cfg1_sample_n1500", 1500, 6)

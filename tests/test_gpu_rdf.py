@@ -117,3 +117,16 @@ def test_conc_mol_rdf_host_mirror_on_a_dcd(tmp_path):
     # missing masses are an error, as Topology.Masses reports (chem.go:291-301)
     with pytest.raises(H.GoChemError):
         H.ConcMolRDF(path, frames[0], names, molid, chains, None, refidx, ["SOL"], cpus=cpus)
+
+
+@pytest.mark.parametrize("com", [0, 1])
+def test_rdf_golden_fixture(golden_dir, com):
+    z = np.load(os.path.join(golden_dir, "rdf_small.npz"))
+    frames = z["frames"].astype(np.float64)
+    t = device_traj(frames)
+    got, read = t.rdf_cdf_sum(z["molid"], z["chain"], z["flags"], z["refidx"], com=bool(com), step=float(z["step"]), end=float(z["end"]))
+    assert read == frames.shape[0] and np.array_equal(got, z["cdf_frames_com%d" % com].sum(axis=0))
+    # frame by frame through the window arguments
+    one, _ = t.rdf_cdf_sum(z["molid"], z["chain"], z["flags"], z["refidx"], com=bool(com), first=4, nframes=1)
+    assert np.array_equal(one, z["cdf_frames_com%d" % com][4])
+    t.close()

@@ -230,3 +230,15 @@ def test_kernel_rotation_solver_against_lapack():
     assert npolar > 1000 and nrefl > 300
     # non-finite input is the reference's "mat.SVD failed"
     assert solve(np.full((3, 3), np.nan), 0)[0] == -4
+
+
+def test_mdf_from_cdf_matches_oracle():
+    """solv.MDFFromCDF (solvation.go:317-352) in the host mirror against the oracle; A, B < 1 is an error in both."""
+    rng = np.random.default_rng(4)
+    cdf = np.cumsum(rng.integers(0, 30, 100)).astype(np.float64) * 17
+    a, a2 = H.MDFFromCDF(cdf, 17, 1.7, 1.2, 0.1)
+    b, b2 = oracle.mdf_from_cdf(cdf, 17, 1.7, 1.2, 0.1)
+    assert np.array_equal(a, b) and np.array_equal(a2, b2)
+    assert a[-1] == 1.0
+    with pytest.raises(H.GoChemError):
+        H.MDFFromCDF(cdf, 17, 0.9, 1.2, 0.1)

@@ -232,3 +232,16 @@ def test_rdf_two_restatements_agree():
     assert np.allclose(cum[1:], cdf[1:]) and rdf[-1] == 1.0
     with pytest.raises(oracle.OracleError):
         oracle.mdf_from_cdf(cdf, 1, 0.5, 1.0, 0.1)
+
+
+def test_rdf_c_oracle_matches_golden(golden_dir):
+    g = load(golden_dir, "rdf_small")
+    frames = g["frames"].astype(np.float64)
+    for com in (0, 1):
+        want = g["cdf_frames_com%d" % com]
+        for f in range(frames.shape[0]):
+            got = oracle.frame_umol_crdf(frames[f], g["molid"], g["chain"], g["flags"], g["refidx"], com=bool(com),
+                                         step=float(g["step"]), end=float(g["end"]))
+            assert np.array_equal(got, want[f])
+        total, read = oracle.rdf_cdf_sum(frames, g["molid"], g["chain"], g["flags"], g["refidx"], com=bool(com), cpus=3)
+        assert read == 9 and np.array_equal(total, want[:9].sum(axis=0))
