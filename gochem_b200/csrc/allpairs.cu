@@ -20,9 +20,15 @@ namespace gcb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+#ifndef GCB_AP_BK
+#define GCB_AP_BK 32
+#endif
+#ifndef GCB_AP_STAGES
+#define GCB_AP_STAGES 2
+#endif
+constexpr int BM = 128, BN = 128, BK = GCB_AP_BK;
 constexpr int LDS = BK + 4;           // row stride in doubles: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts
-constexpr int STAGES = 3;
+constexpr int STAGES = GCB_AP_STAGES;  // BK = 32 double-buffered: one barrier per 8 DMMA k-steps (BK = 16 x 3 stages: per 4)
 constexpr int GEMM_THREADS = 256;
 constexpr int TLD = BN + 1;           // staging row stride: transposed reads touch every bank once per half warp
 constexpr int kMaxPeers = 8;
@@ -166,13 +172,13 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     const int nk = (kdim + BK - 1) / BK;
-    // each thread copies 2 x 16 B of A and 2 x 16 B of B per stage: 128 rows x 16 doubles = 1024 chunks of 2 doubles
+    // 128 rows x BK doubles per operand and stage = 64 * BK chunks of 2 doubles (16 B), BK / 4 per thread
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * BK;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int chunk = tid + r * GEMM_THREADS;   // 0..1023
-            const int row = chunk >> 3, kc = (chunk & 7) * 2;
+        for (int r = 0; r < BK / 4; r++) {
+            const int chunk = tid + r * GEMM_THREADS;
+            const int row = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
             const bool kin = k0 + kc < kdim;
             {
                 const long fr = i0 + row;
@@ -376,9 +382,9 @@ allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, c
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * BK;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const int chunk = tid + r * GEMM_THREADS;   // 0..767: 96 rows x 8 chunks of 2 doubles
-            const int row = chunk >> 3, kc = (chunk & 7) * 2;
+        for (int r = 0; r < 3 * BK / 16; r++) {
+            const int chunk = tid + r * GEMM_THREADS;   // 96 rows x BK / 2 chunks of 2 doubles
+            const int row = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
             const bool kin = k0 + kc < kdim;
             {
                 const long gr = 3 * fi0 + row;

@@ -30,6 +30,8 @@
 // rmsd[f] = sqrt(sum E[f][..] / n) in fixed order for the flagged frames.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kabsch3.cuh"
 #include "ptx.cuh"
@@ -542,7 +544,13 @@ int g_last_plan[8] = {0};
 template <int K, bool W, bool DV, bool RES>
 int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
     auto kern = super_cluster_kernel<K, W, DV, RES>;
-    GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    // the attribute call and the occupancy query cost tens of microseconds each: once per (instance, device, shape)
+    static std::mutex cache_mu;
+    static int cached_dev = -1, cached_cluster = 0, cached_max = 0;
+    static size_t cached_smem = 0;
+    std::lock_guard<std::mutex> lock(cache_mu);
+    const bool hit = cached_dev == t->dev && cached_cluster == pl.cluster && cached_smem == pl.smem;
+    if (!hit) GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -555,8 +563,11 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = t->stream;
     cfg.gridDim = dim3(pl.cluster * (t->sm_count / pl.cluster));
-    int max_clusters = 0;
-    GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    int max_clusters = cached_max;
+    if (!hit) {
+        GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        cached_dev = t->dev; cached_cluster = pl.cluster; cached_smem = pl.smem; cached_max = max_clusters;
+    }
     if (max_clusters < 1) { set_error("cluster of %d CTAs with %zu bytes of shared memory cannot be scheduled", pl.cluster, pl.smem); return GCB_ERR_CUDA; }
     long g = max_clusters;
     if (g > cp.p.nframes) g = cp.p.nframes;
