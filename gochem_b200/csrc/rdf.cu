@@ -9,9 +9,10 @@
 // The topology is static, so the host turns it into "runs" (maximal stretches of consecutive atoms with one MolID:
 // the reference extends a residue from its first atom while the MolID stays the same, :490-496).  What depends on the
 // frame is (a) where a water run starts -- atoms of SOL/WAT/HOH further than end+3 from the first solute atom are passed
-// over before a residue begins (:480-483) -- and (b) the distances.  One CTA per frame.  Runs are examined 1024 at a time:
-// those that begin a residue within reach of the solute are compacted into a dense list (most of a solvent box is not), then
-// one thread per listed residue ranks it against the solute, which streams through shared memory in tiles.  An atom
+// over before a residue begins (:480-483) -- and (b) the distances.  One CTA per frame, the solute staged in shared memory
+// (whole when it has at most 4096 atoms, else in tiles).  Runs are examined in chunks: the atoms of residues that begin and
+// lie within reach of the solute are compacted into a dense work list (most of a solvent box is out of reach), one thread
+// per listed atom ranks it against the solute, and the residues' minima are merged in shared memory.  An atom
 // further from the solute's bounding sphere than `end` cannot come within `end` of any solute atom, so it is skipped without changing any kept distance.  Counts are integers: the
 // accumulation over frames (64-bit atomics) is exact and order-independent.
 //
@@ -27,10 +28,10 @@ namespace gcb {
 
 namespace {
 
-constexpr int RT = 256;          // threads per CTA = runs per block of runs
-constexpr int kRefTile = 1024;   // solute atoms per shared-memory tile
+constexpr int RT = 256;            // threads per CTA
+constexpr int kRefTileMax = 4096;  // solute atoms held in shared memory at a time (96 KB); larger solutes stream through in tiles
 constexpr int kMaxSteps = 2048;
-constexpr int kRunChunk = 1024;  // runs examined per compaction round
+constexpr int kListCap = 4096;     // work-list entries (atoms within reach) per chunk of runs
 
 struct Run {
     int s, e;   // atoms [s, e)
@@ -43,29 +44,71 @@ struct RdfParams {
     long nframes;
     const Run* runs;
     int nruns;
+    const int* chunk_first;       // [nchunks + 1] run ranges whose atoms fit one work list
+    int nchunks;
     const unsigned char* flags;   // per atom: bit 0 = may start a residue, bit 1 = pre-screened water
     const int* refidx;
     int nref;
+    int tile;                     // solute atoms per shared-memory tile (even)
     int com;
     double step, end;
     int nsteps;
     unsigned long long* cdf;      // [nsteps] summed over frames
 };
 
+// smallest squared distance from (ax, ay, az) to the tn solute atoms staged in shared memory; four independent chains
+__device__ __forceinline__ double tile_min_d2(const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                              int tn, double ax, double ay, double az) {
+    double b0 = 1e300, b1 = 1e300, b2 = 1e300, b3 = 1e300;
+    int j = 0;
+    for (; j + 3 < tn; j += 4) {
+        const double2 x0 = *reinterpret_cast<const double2*>(rx + j), x1 = *reinterpret_cast<const double2*>(rx + j + 2);
+        const double2 y0 = *reinterpret_cast<const double2*>(ry + j), y1 = *reinterpret_cast<const double2*>(ry + j + 2);
+        const double2 z0 = *reinterpret_cast<const double2*>(rz + j), z1 = *reinterpret_cast<const double2*>(rz + j + 2);
+        const double d0x = x0.x - ax, d0y = y0.x - ay, d0z = z0.x - az;
+        const double d1x = x0.y - ax, d1y = y0.y - ay, d1z = z0.y - az;
+        const double d2x = x1.x - ax, d2y = y1.x - ay, d2z = z1.x - az;
+        const double d3x = x1.y - ax, d3y = y1.y - ay, d3z = z1.y - az;
+        b0 = fmin(b0, fma(d0z, d0z, fma(d0y, d0y, d0x * d0x)));
+        b1 = fmin(b1, fma(d1z, d1z, fma(d1y, d1y, d1x * d1x)));
+        b2 = fmin(b2, fma(d2z, d2z, fma(d2y, d2y, d2x * d2x)));
+        b3 = fmin(b3, fma(d3z, d3z, fma(d3y, d3y, d3x * d3x)));
+    }
+    for (; j < tn; j++) {
+        const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az;
+        b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
+    }
+    return fmin(fmin(b0, b1), fmin(b2, b3));
+}
+
+// One CTA per frame.  Per chunk of runs: (A) the atoms that can be within the cutoff are appended to a dense work list,
+// each tagged with the slot of its residue; (B) one thread per listed atom finds its smallest squared distance to the solute
+// (identical trip counts: the lanes of a warp stay together) and merges it into the residue's slot with a shared-memory
+// atomic minimum on the bit pattern (non-negative doubles order like unsigned integers); (C) one thread per slot bins the
+// residue's distance.  With Options.COM a list entry is a residue and its point is the residue's centre.
 __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
-    __shared__ double rx[kRefTile], ry[kRefTile], rz[kRefTile];
-    __shared__ unsigned int hist[kMaxSteps + 1];
+    extern __shared__ __align__(16) unsigned char rdf_smem[];
+    double* rx = reinterpret_cast<double*>(rdf_smem);
+    double* ry = rx + p.tile;
+    double* rz = ry + p.tile;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(rz + p.tile);   // [kListCap] min squared distance per slot
+    int2* ent = reinterpret_cast<int2*>(best + kListCap);                             // [kListCap] (atom, slot) or (start, stop)
+    unsigned int* hist = reinterpret_cast<unsigned int*>(ent + kListCap);             // [nsteps + 1]
     __shared__ double red[RT / 32][4];
     __shared__ double sphere[4];   // centre of the solute's bounding sphere, radius
-    __shared__ int list_s[kRunChunk], list_e[kRunChunk];   // residues of the current chunk that can be within the cutoff: atoms [s, e)
-    __shared__ int nlist;
+    __shared__ int nent, nslot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cutoff = p.end, cutoffplus = p.end + 3.0;
+    const unsigned long long far_bits = (unsigned long long)__double_as_longlong(1e10);   // MolShortestDist starts from 100000 (:674)
+    const bool one_tile = p.nref <= p.tile;
     for (long f = blockIdx.x; f < p.nframes; f += gridDim.x) {
         const double* X = p.frames + f * p.stride;
         const double* Y = X + p.np;
         const double* Z = Y + p.np;
+        __syncthreads();   // the previous frame's tile and histogram are no longer read
         for (int k = tid; k <= p.nsteps; k += RT) hist[k] = 0u;
+        if (one_tile)
+            for (int j = tid; j < p.nref; j += RT) { const int a = p.refidx[j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
         // bounding sphere of the solute: centre = mean position, radius = largest distance from it
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int j = tid; j < p.nref; j += RT) { const int a = p.refidx[j]; s0 += X[a]; s1 += Y[a]; s2 += Z[a]; }
@@ -100,14 +143,12 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
         const int a0 = p.refidx[0];
         const double fx = X[a0], fy = Y[a0], fz = Z[a0];   // ref.VecView(0)
 
-        bool tile_ready = false;   // CTA-uniform
-        for (int rb = 0; rb < p.nruns; rb += kRunChunk) {
-            // ---- step A: which runs of this chunk begin a residue within reach of the solute?  (compacted into a dense list) ----
+        for (int c = 0; c < p.nchunks; c++) {
+            // ---- step A: work list of this chunk ----
             __syncthreads();
-            if (tid == 0) nlist = 0;
+            if (tid == 0) { nent = 0; nslot = 0; }
             __syncthreads();
-            const int rend = min(rb + kRunChunk, p.nruns);
-            for (int r = rb + tid; r < rend; r += RT) {
+            for (int r = p.chunk_first[c] + tid; r < p.chunk_first[c + 1]; r += RT) {
                 const Run run = p.runs[r];
                 int start = -1;
                 for (int a = run.s; a < run.e; a++) {   // first atom that begins the residue (solvation.go:478-486)
@@ -119,89 +160,66 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
                     if (fl & 1) { start = a; break; }
                 }
                 if (start < 0) continue;
-                bool active = false;
-                if (p.com) {
+                if (p.com) {   // chem.CenterOfMass with nil masses: column sums in row order times 1/n (geometric.go:615-629)
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
                     for (int a = start; a < run.e; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
                     const double inv = 1.0 / (double)(run.e - start);
                     const double dx = c0 * inv - cx, dy = c1 * inv - cy, dz = c2 * inv - cz;
-                    active = dx * dx + dy * dy + dz * dz <= reach2;
-                } else {
-                    for (int a = start; a < run.e && !active; a++) {
-                        const double dx = X[a] - cx, dy = Y[a] - cy, dz = Z[a] - cz;
-                        active = dx * dx + dy * dy + dz * dz <= reach2;
+                    if (dx * dx + dy * dy + dz * dz <= reach2) {
+                        const int e = atomicAdd(&nent, 1);
+                        ent[e] = make_int2(start, run.e);
+                        best[e] = far_bits;
                     }
-                }
-                if (active) {
-                    const int slot = atomicAdd(&nlist, 1);
-                    list_s[slot] = start;
-                    list_e[slot] = run.e;
+                } else {
+                    int slot = -1;
+                    for (int a = start; a < run.e; a++) {
+                        const double dx = X[a] - cx, dy = Y[a] - cy, dz = Z[a] - cz;
+                        if (dx * dx + dy * dy + dz * dz > reach2) continue;
+                        if (slot < 0) { slot = atomicAdd(&nslot, 1); best[slot] = far_bits; }
+                        ent[atomicAdd(&nent, 1)] = make_int2(a, slot);
+                    }
                 }
             }
             __syncthreads();
-            // ---- step B: every listed residue against the whole solute, one thread per residue ----
-            const int nl = nlist;
-            for (int base = 0; base < nl; base += RT) {
-                const bool mine = base + tid < nl;
-                const int start = mine ? list_s[base + tid] : 0, stop = mine ? list_e[base + tid] : 0;
-                double px = 0.0, py = 0.0, pz = 0.0;   // COM mode: the residue's centre
-                if (mine && p.com) {   // chem.CenterOfMass with nil masses: column sums in row order times 1/n (geometric.go:615-629)
-                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-                    for (int a = start; a < stop; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
-                    const double inv = 1.0 / (double)(stop - start);
-                    px = c0 * inv; py = c1 * inv; pz = c2 * inv;
+            // ---- step B: every listed point against the solute ----
+            const int ne = nent;
+            for (int t0 = 0; t0 < p.nref; t0 += p.tile) {
+                const int tn = min(p.tile, p.nref - t0);
+                if (!one_tile) {
+                    __syncthreads();
+                    for (int j = tid; j < tn; j += RT) { const int a = p.refidx[t0 + j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
+                    __syncthreads();
                 }
-                double best = 1e10;   // squared; MolShortestDist starts from 100000 (:674)
-                for (int t0 = 0; t0 < p.nref; t0 += kRefTile) {
-                    const int tn = min(kRefTile, p.nref - t0);
-                    if (p.nref > kRefTile || !tile_ready) {   // a solute of one tile is loaded once per frame
-                        __syncthreads();
-                        for (int j = tid; j < tn; j += RT) { const int a = p.refidx[t0 + j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
-                        __syncthreads();
-                        tile_ready = true;
-                    }
-                    if (!mine) continue;
+                for (int e = tid; e < ne; e += RT) {
+                    const int2 en = ent[e];
+                    double ax, ay, az;
+                    int slot;
                     if (p.com) {
-                        double b0 = best, b1 = best;
-                        int j = 0;
-                        for (; j + 1 < tn; j += 2) {
-                            const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz;
-                            const double ex = rx[j + 1] - px, ey = ry[j + 1] - py, ez = rz[j + 1] - pz;
-                            b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
-                            b1 = fmin(b1, fma(ez, ez, fma(ey, ey, ex * ex)));
-                        }
-                        if (j < tn) { const double dx = rx[j] - px, dy = ry[j] - py, dz = rz[j] - pz; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
-                        best = fmin(b0, b1);
+                        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                        for (int a = en.x; a < en.y; a++) { c0 += X[a]; c1 += Y[a]; c2 += Z[a]; }
+                        const double inv = 1.0 / (double)(en.y - en.x);
+                        ax = c0 * inv; ay = c1 * inv; az = c2 * inv;
+                        slot = e;
                     } else {
-                        for (int a = start; a < stop; a++) {
-                            const double ax = X[a], ay = Y[a], az = Z[a];
-                            {
-                                const double dx = ax - cx, dy = ay - cy, dz = az - cz;
-                                if (dx * dx + dy * dy + dz * dz > reach2) continue;
-                            }
-                            double b0 = best, b1 = best;
-                            int j = 0;
-                            for (; j + 1 < tn; j += 2) {
-                                const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az;
-                                const double ex = rx[j + 1] - ax, ey = ry[j + 1] - ay, ez = rz[j + 1] - az;
-                                b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx)));
-                                b1 = fmin(b1, fma(ez, ez, fma(ey, ey, ex * ex)));
-                            }
-                            if (j < tn) { const double dx = rx[j] - ax, dy = ry[j] - ay, dz = rz[j] - az; b0 = fmin(b0, fma(dz, dz, fma(dy, dy, dx * dx))); }
-                            best = fmin(b0, b1);
-                        }
+                        ax = X[en.x]; ay = Y[en.x]; az = Z[en.x];
+                        slot = en.y;
                     }
+                    const double d2 = tile_min_d2(rx, ry, rz, tn, ax, ay, az);
+                    atomicMin(&best[slot], (unsigned long long)__double_as_longlong(d2));
                 }
-                if (mine) {
-                    const double d = sqrt(best);
-                    if (d <= cutoff) {
-                        // smallest i >= 1 with d < i*step (the limits of solvation.go:398-399, same product)
-                        int i = (int)(d / p.step);
-                        if (i < 1) i = 1;
-                        while (i > 1 && d < (double)(i - 1) * p.step) i--;
-                        while (i <= p.nsteps && !(d < (double)i * p.step)) i++;
-                        if (i <= p.nsteps) atomicAdd(&hist[i], 1u);
-                    }
+            }
+            __syncthreads();
+            // ---- step C: one distance per residue -> shell ----
+            const int ns = p.com ? ne : nslot;
+            for (int sl = tid; sl < ns; sl += RT) {
+                const double d = sqrt(__longlong_as_double((long long)best[sl]));
+                if (d <= cutoff) {
+                    // smallest i >= 1 with d < i*step (the limits of solvation.go:398-399, same product)
+                    int i = (int)(d / p.step);
+                    if (i < 1) i = 1;
+                    while (i > 1 && d < (double)(i - 1) * p.step) i--;
+                    while (i <= p.nsteps && !(d < (double)i * p.step)) i++;
+                    if (i <= p.nsteps) atomicAdd(&hist[i], 1u);
                 }
             }
         }
@@ -214,7 +232,6 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
                 if (c > 1u) atomicAdd(&p.cdf[i - 1], (unsigned long long)(c - 1u));
             }
         }
-        __syncthreads();
     }
 }
 
@@ -266,11 +283,25 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         }
         s = e;
     }
+    // chunks of runs whose atoms fit one work list
+    std::vector<int> chunk_first{0};
+    {
+        int atoms_in = 0, runs_in = 0;
+        for (size_t r = 0; r < runs.size(); r++) {
+            const int len = runs[r].e - runs[r].s;
+            if (len > kListCap) { set_error("gcb_rdf_cdf_sum: a solvent residue of %d atoms (at most %d supported)", len, kListCap); return GCB_ERR_ARG; }
+            if (atoms_in + len > kListCap || runs_in + 1 > kListCap) { chunk_first.push_back((int)r); atoms_in = 0; runs_in = 0; }
+            atoms_in += len;
+            runs_in++;
+        }
+        chunk_first.push_back((int)runs.size());
+    }
     const int totalsteps = nsteps;
     for (int k = 0; k < totalsteps; k++) cdf_sum[k] = 0.0;
     const long used = (nframes / cpus) * cpus;   // whole chunks only (solvation.go:166-214 with dcd.go:520-523)
     if (frames_read) *frames_read = used;
     Run* d_runs = nullptr;
+    int* d_chunks = nullptr;
     unsigned char* d_fl = nullptr;
     int* d_ref = nullptr;
     unsigned long long* d_cdf = nullptr;
@@ -280,6 +311,8 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
 #define RDF_TRY(call) do { e = (call); if (e != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e)); rc = GCB_ERR_CUDA; goto done; } } while (0)
     RDF_TRY(cudaMalloc(&d_runs, sizeof(Run) * std::max<size_t>(runs.size(), 1)));
     RDF_TRY(cudaMalloc(&d_fl, (size_t)t->np));
+    RDF_TRY(cudaMalloc(&d_chunks, sizeof(int) * chunk_first.size()));
+    RDF_TRY(cudaMemcpyAsync(d_chunks, chunk_first.data(), sizeof(int) * chunk_first.size(), cudaMemcpyHostToDevice, t->stream));
     RDF_TRY(cudaMalloc(&d_ref, sizeof(int) * (size_t)nref));
     RDF_TRY(cudaMalloc(&d_cdf, sizeof(unsigned long long) * (size_t)totalsteps));
     RDF_TRY(cudaMemcpyAsync(d_runs, runs.data(), sizeof(Run) * runs.size(), cudaMemcpyHostToDevice, t->stream));
@@ -294,6 +327,9 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         p.nframes = used;
         p.runs = d_runs;
         p.nruns = (int)runs.size();
+        p.chunk_first = d_chunks;
+        p.nchunks = (int)chunk_first.size() - 1;
+        p.tile = nref <= kRefTileMax ? (nref + 1) / 2 * 2 : kRefTileMax;
         p.flags = d_fl;
         p.refidx = d_ref;
         p.nref = nref;
@@ -302,9 +338,14 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         p.end = end;
         p.nsteps = totalsteps;
         p.cdf = d_cdf;
-        long grid = (long)t->sm_count * 4;
+        const size_t smem = sizeof(double) * 3 * (size_t)p.tile + (sizeof(unsigned long long) + sizeof(int2)) * kListCap +
+                            sizeof(unsigned int) * (size_t)(totalsteps + 1);
+        RDF_TRY(cudaFuncSetAttribute(rdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        RDF_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rdf_kernel, RT, smem));
+        long grid = (long)t->sm_count * (per_sm > 0 ? per_sm : 1);
         if (grid > used) grid = used;
-        rdf_kernel<<<(unsigned)grid, RT, 0, t->stream>>>(p);
+        rdf_kernel<<<(unsigned)grid, RT, smem, t->stream>>>(p);
         GCB_LAUNCHED();
     }
     RDF_TRY(cudaMemcpyAsync(h_cdf.data(), d_cdf, sizeof(unsigned long long) * (size_t)totalsteps, cudaMemcpyDeviceToHost, t->stream));
@@ -313,7 +354,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     for (int k = 0; k < totalsteps; k++) cdf_sum[k] = (double)h_cdf[(size_t)k];
 done:
 #undef RDF_TRY
-    cudaFree(d_runs); cudaFree(d_fl); cudaFree(d_ref); cudaFree(d_cdf);
+    cudaFree(d_runs); cudaFree(d_chunks); cudaFree(d_fl); cudaFree(d_ref); cudaFree(d_cdf);
     if (rc) return rc;
     if (comm) {   // frames sharded over ranks: the counts add up (integers below 2^53: exact in any order)
         rc = gcb_allreduce_sum_f64(comm, cdf_sum, totalsteps);

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <thread>
+#include <unordered_set>
 
 #include "../../include/gochem_b200.h"
 
@@ -695,20 +696,22 @@ Error mobileLimit(double limit, int tolerance, const std::vector<double>& rmsd, 
 
 bool approxEq(double i, double j, double epsilon) { return std::fabs(i) - std::fabs(j) <= epsilon; }
 
-static bool isInInt(int v, const std::vector<int>& c) { return std::find(c.begin(), c.end(), v) != c.end(); }
-
+// The reference answers "is v in the list" with a linear search (lovo.go:474-484), O(n^2) per LOVO iteration -- 75 M
+// comparisons at 5000 candidates, three times the device time of the pass.  Same answers from a hash set.
 bool sameElementsInt(const std::vector<int>& a, const std::vector<int>& b) {
     if (a.size() != b.size()) return false;
+    const std::unordered_set<int> inb(b.begin(), b.end());
     for (int v : a)
-        if (!isInInt(v, b)) return false;
+        if (!inb.count(v)) return false;
     return true;
 }
 
 int disagreementInt(const std::vector<int>& a, const std::vector<int>& b) {
     if (a.size() != b.size()) return -1;
+    const std::unordered_set<int> inb(b.begin(), b.end());
     int d = 0;
     for (int v : a)
-        if (!isInInt(v, b)) d++;
+        if (!inb.count(v)) d++;
     return d;
 }
 
@@ -770,8 +773,9 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
     // fullindexes position by position (:367-384)
     std::vector<double> filtered;
     filtered.reserve(full_.size());
+    const std::unordered_set<int> infull(full_.begin(), full_.end());
     for (int i = 0; i < (int)rmsd.size(); i++)
-        if (isInInt(i, full_)) filtered.push_back(rmsd[(size_t)i]);
+        if (infull.count(i)) filtered.push_back(rmsd[(size_t)i]);
     if (filtered.size() != full_.size()) {
         *err = Error("Inconsistent data, if given, the number of initial RMSD values must match the number of residues");  // :373-375 panic
         return true;
