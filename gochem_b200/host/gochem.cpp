@@ -697,21 +697,47 @@ Error mobileLimit(double limit, int tolerance, const std::vector<double>& rmsd, 
 bool approxEq(double i, double j, double epsilon) { return std::fabs(i) - std::fabs(j) <= epsilon; }
 
 // The reference answers "is v in the list" with a linear search (lovo.go:474-484), O(n^2) per LOVO iteration -- 75 M
-// comparisons at 5000 candidates, three times the device time of the pass.  Same answers from a hash set.
+// comparisons at 5000 candidates, three times the device time of the pass.  Same answers from a bitmap (Membership).
+namespace {
+// "is v in the list": a bitmap over [min, max] of the list (atom indexes), a hash set when the span is unreasonable
+class Membership {
+  public:
+    explicit Membership(const std::vector<int>& c) {
+        if (c.empty()) return;
+        lo_ = *std::min_element(c.begin(), c.end());
+        const long span = (long)*std::max_element(c.begin(), c.end()) - lo_ + 1;
+        if (span <= (1L << 26)) {
+            bits_.assign((size_t)span, 0);
+            for (int v : c) bits_[(size_t)(v - lo_)] = 1;
+        } else {
+            set_.insert(c.begin(), c.end());
+        }
+    }
+    bool has(int v) const {
+        if (!bits_.empty()) return v >= lo_ && (size_t)(v - lo_) < bits_.size() && bits_[(size_t)(v - lo_)];
+        return set_.count(v) != 0;
+    }
+  private:
+    int lo_ = 0;
+    std::vector<char> bits_;
+    std::unordered_set<int> set_;
+};
+}  // namespace
+
 bool sameElementsInt(const std::vector<int>& a, const std::vector<int>& b) {
     if (a.size() != b.size()) return false;
-    const std::unordered_set<int> inb(b.begin(), b.end());
+    const Membership inb(b);
     for (int v : a)
-        if (!inb.count(v)) return false;
+        if (!inb.has(v)) return false;
     return true;
 }
 
 int disagreementInt(const std::vector<int>& a, const std::vector<int>& b) {
     if (a.size() != b.size()) return -1;
-    const std::unordered_set<int> inb(b.begin(), b.end());
+    const Membership inb(b);
     int d = 0;
     for (int v : a)
-        if (!inb.count(v)) d++;
+        if (!inb.has(v)) d++;
     return d;
 }
 
@@ -726,12 +752,13 @@ std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::strin
 }
 
 std::vector<MolIDandChain> iDs2MolIDandChains(const chem::Atomer& mol, const std::vector<int>& indexes) {
+    // first occurrences in list order, as the reference's search over the growing result (lovo.go:540-551)
     std::vector<MolIDandChain> ret;
+    std::map<std::pair<int, std::string>, bool> seen;
     for (int v : indexes) {
         const chem::Atom& at = mol.Atom(v);
-        bool seen = false;
-        for (const auto& m : ret) seen = seen || (m.molid == at.MolID && m.chain == at.Chain);
-        if (!seen) ret.push_back(MolIDandChain{at.MolID, at.Chain});
+        auto ins = seen.emplace(std::make_pair(at.MolID, at.Chain), true);
+        if (ins.second) ret.push_back(MolIDandChain{at.MolID, at.Chain});
     }
     return ret;
 }
@@ -773,9 +800,9 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
     // fullindexes position by position (:367-384)
     std::vector<double> filtered;
     filtered.reserve(full_.size());
-    const std::unordered_set<int> infull(full_.begin(), full_.end());
+    const Membership infull(full_);
     for (int i = 0; i < (int)rmsd.size(); i++)
-        if (infull.count(i)) filtered.push_back(rmsd[(size_t)i]);
+        if (infull.has(i)) filtered.push_back(rmsd[(size_t)i]);
     if (filtered.size() != full_.size()) {
         *err = Error("Inconsistent data, if given, the number of initial RMSD values must match the number of residues");  // :373-375 panic
         return true;
