@@ -39,6 +39,7 @@ struct RefCache {
     bool centred = false;
     bool valid = false;
     bool repeated = false;  // weighted mode: some index occurs more than once (multiplicities > 1)
+    bool paired = false;    // weighted mode built from two different lists (template planes laid out by test atom)
     double n_fit = 0.0;
     double gb = 0.0;
     double bbar[3] = {0, 0, 0};
@@ -358,6 +359,7 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
     if (natoms_ref <= 0) { set_error("empty template"); return GCB_ERR_SHAPE; }
     const int* ir = idx_ref ? idx_ref : idx_test;
     int mode = MODE_ALL;
+    bool paired = false;   // different lists, no test atom twice: the pairing is folded into the template planes
     if (!all) {
         bool same = (natoms_ref == t->natoms);
         for (int k = 0; k < nidx; k++) {
@@ -367,7 +369,18 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
             }
             same = same && (idx_test[k] == ir[k]);
         }
-        mode = same ? MODE_WEIGHTED : MODE_GATHER;
+        if (!same) {
+            // Test atom idx_test[k] is fitted onto template atom idx_ref[k].  When no test atom occurs twice the template can be
+            // laid out by TEST atom (plane entry idx_test[k] = templa[idx_ref[k]]) and the fit becomes a subset fit of the
+            // streaming kernels -- no gather of the frame.  Lists that repeat a test atom keep the gather kernels.
+            std::vector<unsigned char> used((size_t)t->natoms, 0);
+            paired = true;
+            for (int k = 0; k < nidx && paired; k++) {
+                if (used[(size_t)idx_test[k]]) paired = false;
+                used[(size_t)idx_test[k]] = 1;
+            }
+        }
+        mode = (same || paired) ? MODE_WEIGHTED : MODE_GATHER;
     }
     *mode_out = mode;
     gcb::RefCache& c = t->cache;
@@ -378,6 +391,7 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
         return GCB_OK;
 
     c.valid = false;
+    c.paired = false;
     GCB_CUDA(cudaStreamSynchronize(t->stream));  // h_scratch and the device template may still be in use
     const int np = t->np;
     const int n = all ? t->natoms : nidx;
@@ -414,11 +428,21 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
     } else {
         double* h = t->h_scratch;  // [3*np planes | np weights]
         memset(h, 0, sizeof(double) * 4 * (size_t)np);
-        for (int i = 0; i < t->natoms; i++) {
-            h[i] = ref_aos[3 * (size_t)i] - c.bbar[0];
-            h[np + i] = ref_aos[3 * (size_t)i + 1] - c.bbar[1];
-            h[2 * (size_t)np + i] = ref_aos[3 * (size_t)i + 2] - c.bbar[2];
+        if (paired) {
+            for (int k = 0; k < nidx; k++) {
+                const size_t i = (size_t)idx_test[k], j = (size_t)ir[k];
+                h[i] = ref_aos[3 * j] - c.bbar[0];
+                h[np + i] = ref_aos[3 * j + 1] - c.bbar[1];
+                h[2 * (size_t)np + i] = ref_aos[3 * j + 2] - c.bbar[2];
+            }
+        } else {
+            for (int i = 0; i < t->natoms; i++) {
+                h[i] = ref_aos[3 * (size_t)i] - c.bbar[0];
+                h[np + i] = ref_aos[3 * (size_t)i + 1] - c.bbar[1];
+                h[2 * (size_t)np + i] = ref_aos[3 * (size_t)i + 2] - c.bbar[2];
+            }
         }
+        c.paired = paired;
         GCB_CUDA(cudaMemcpyAsync(t->d_refc, h, sizeof(double) * 3 * (size_t)np, cudaMemcpyHostToDevice, t->stream));
         double* w = h + 3 * (size_t)np;
         if (mode == MODE_WEIGHTED) {
@@ -510,6 +534,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
     }
     if (mode == MODE_WEIGHTED) p.weight = t->d_weight;
+    if (want_dev && mode == MODE_WEIGHTED && t->cache.paired) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
     // the cluster kernel takes the fit subset as a 0/1 mask; index lists with repeats (multiplicities) go to the generic kernel
     const bool cluster = use_cluster(t) && !(mode == MODE_WEIGHTED && t->cache.repeated);
     if (g_variant == GCB_KERNEL_CLUSTER && !cluster && !(mode == MODE_WEIGHTED && t->cache.repeated)) {

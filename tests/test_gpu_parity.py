@@ -124,6 +124,20 @@ def test_gather_lists_and_smaller_template(variant):
         s, r, a, b = oracle.super_(frames[f], ref, it, ir2, details=True)
         assert np.abs(out["rot"][f] - r).max() < 1e-8  # ill-conditioned on purpose (random pairing)
         assert abs(out["rmsd"][f] - oracle.rmsd(s, ref, it, ir2)) < 1e-8
+    # chem.RMSD without a fit through the same two lists
+    nf = t.rmsd(ref, it, ir2)
+    for f in range(4):
+        assert abs(nf[f] - oracle.mem_rmsd(frames[f], ref, it, ir2)) < TOL_RMSD
+    # a test atom used twice, paired with different template atoms: the pairing cannot be folded into the template planes
+    it3 = np.array([5, 5, 9, 33, 64, 64, 100, 2, 17, 80, 41, 42])
+    ir3 = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
+    out = t.super_rmsd(ref, it3, ir3)
+    nf = t.rmsd(ref, it3, ir3)
+    for f in range(4):
+        s, r, a, b = oracle.super_(frames[f], ref, it3, ir3, details=True)
+        assert np.abs(out["rot"][f] - r).max() < 1e-8
+        assert abs(out["rmsd"][f] - oracle.rmsd(s, ref, it3, ir3)) < 1e-8
+        assert abs(nf[f] - oracle.mem_rmsd(frames[f], ref, it3, ir3)) < TOL_RMSD
     t.close()
 
 
