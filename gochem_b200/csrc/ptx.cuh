@@ -30,6 +30,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// shared-memory counter bump that releases the caller's earlier writes and acquires those of the previous bumpers
+// (with __syncwarp() on both sides it hands a warp's shared-memory stores to the warp that arrives last; no MEMBAR)
+__device__ __forceinline__ uint32_t atom_add_acq_rel_cta(unsigned int* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));

@@ -406,14 +406,13 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     red[6 * b4 + 3 * b3 + 2 * b2] = t0;
                     if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
                 }
-                __threadfence_block();
-                __syncwarp();
+                __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below
                 if (tid == 0) TRACE(7, j);
                 unsigned int prev = 0;
-                if (lane == 0) prev = atomicAdd(&sh.red_count[slot1], 1u);
+                if (lane == 0) prev = atom_add_acq_rel_cta(&sh.red_count[slot1], 1u);
                 prev = __shfl_sync(0xffffffffu, prev, 0);
                 if (prev == kConsumerWarps - 1) {
-                    __threadfence_block();
+                    __syncwarp();   // lane 0's acquire is ordered before the other lanes' loads of red[]
                     if (lane < 13) {
                         double v = 0.0;
 #pragma unroll
