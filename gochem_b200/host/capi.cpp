@@ -232,6 +232,48 @@ int gch_rmsd_traj(const char* path, const double* ref, int natoms, const int* in
     return 0;
 }
 
+int gch_rmsd_traj_streamed(const char* path, const double* ref, int natoms, const int* indexes, int nidx, int cpus, int begin, int skip,
+                           const char* write_traj, long window_frames, int dev, int rank, int nranks, void* comm, double* rmsd,
+                           int* frames) {
+    std::unique_ptr<chem::ConcTraj> traj;
+    if (Error e = align::opentraj(path, &traj)) return fail(e);
+    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    align::Options o;
+    o.Cpus(&cpus);
+    o.Begin(&begin);
+    o.Skip(&skip);
+    o.DeviceID(&dev);
+    o.StreamWindow(&window_frames);
+    o.Shard(rank, nranks, static_cast<gcb_comm*>(comm));
+    if (write_traj && *write_traj) { std::string w(write_traj); o.TrajName(&w); }
+    std::vector<double> r;
+    Error e = align::RMSDTrajStreamed(top, mat(ref, natoms), *traj, std::vector<int>(indexes, indexes + nidx), &o, &r, frames);
+    if (e) return fail(e);
+    memcpy(rmsd, r.data(), sizeof(double) * r.size());
+    return 0;
+}
+
+int gch_lovo_streamed(const char* path, const double* ref, int natoms, int cpus, double less_than, int minimum_n, long window_frames,
+                      int dev, int* N, int* natoms_out, double* rmsd_out, int* nrmsd, int* frames, int* iterations) {
+    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    std::unique_ptr<align::Options> o(align::DefaultOptions());
+    o->Cpus(&cpus);
+    o->LessThanRMSD(&less_than);
+    o->MinimumN(&minimum_n);
+    o->DeviceID(&dev);
+    o->StreamWindow(&window_frames);
+    align::LOVOReturn r;
+    Error e = align::LOVO(top, mat(ref, natoms), path, &r, o.get());
+    if (e) return fail(e);
+    *N = r.N;
+    *frames = r.FramesRead;
+    *iterations = r.Iterations;
+    *nrmsd = (int)r.RMSD.size();
+    for (int i = 0; i < r.N; i++) natoms_out[i] = r.Natoms[(size_t)i];
+    for (size_t i = 0; i < r.RMSD.size(); i++) rmsd_out[i] = r.RMSD[i];
+    return 0;
+}
+
 int gch_lovo(const char* path, const double* ref, int natoms, const char* const* names, const char* const* chains, const int* molids,
              const char* atom_name, int cpus, double less_than, int minimum_n, const char* write_traj, int dev, int rank, int nranks,
              void* comm, int* N, int* natoms_out, double* rmsd_out, int* nrmsd, int* frames, int* iterations, char* text,

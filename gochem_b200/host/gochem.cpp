@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <sys/stat.h>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -983,6 +984,7 @@ Error DeviceTrajectory::WriteDCD(const std::string& name) {
 
 Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
                std::vector<double>* rmsd, int* frames) {
+    if (o->stream_ > 0) return RMSDTrajStreamed(mol, ref, traj, indexes, o, rmsd, frames);
     std::unique_ptr<DeviceTrajectory> d;
     if (Error e = DeviceTrajectory::Load(traj, mol.Len(), *o, &d)) { *frames = -1; return e; }
     const bool wb = !o->writeTraj_.empty();
@@ -990,6 +992,136 @@ Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& t
     if (wb)
         if (Error e = d->WriteDCD(o->writeTraj_)) return e;
     *frames = (int)d->SelectedFrames();
+    return Error();
+}
+
+// Streams the frames RMSDTraj selects (chunks of o.cpus, begin / skip, dropped tail: lovo.go:306-326) through a device
+// window.  Windows (whole chunks, at most `per` frames) are dealt to the ranks in turn; a rank reads and discards the
+// windows of the others.  process(handle, first, n) runs for window k while the reader already fills window k + 1.
+static Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
+                            const std::function<Error(gcb_traj*, long, long)>& process, long* nselected, long* nlocal) {
+    if (!traj.Readable()) return Error("Traj object uninitialized to read", {"RMSDTraj"});
+    if (o.cpus_ <= 0) return Error("align.RMSDTraj: cpus must be positive");
+    if (traj.Len() != natoms) return Error("align.RMSDTraj: trajectory and molecule differ in the number of atoms");
+    const int chunksize = o.cpus_;
+    const long begin = o.begin_ / chunksize, skip = o.skip_ / chunksize;
+    const bool raw = traj.HasRawFeed();
+    const size_t fbytes = (raw ? sizeof(float) : sizeof(double)) * 3 * (size_t)natoms;
+    long per = o.stream_ > 0 ? o.stream_ : (long)((64u << 20) / fbytes);
+    per = std::max<long>(chunksize, per / chunksize * chunksize);
+    gcb_traj* t = nullptr;
+    int rc = gcb_traj_create(o.device_, natoms, 2 * per, &t);
+    if (rc) return deviceError(rc, "gcb_traj_create");
+    void* pin[2] = {nullptr, nullptr};
+    Error err;
+    for (int s = 0; s < 2 && !err; s++)
+        if ((rc = gcb_pinned_alloc((size_t)per * fbytes, &pin[s]))) err = deviceError(rc, "gcb_pinned_alloc");
+    std::vector<v3::Matrix> chunk((size_t)chunksize);
+    if (!raw) for (auto& m : chunk) m = v3::Matrix::Zeros(natoms);
+    int layout = GCB_F64_AOS;
+    double scale = 1.0;
+    long nsel = 0, mine_total = 0, window = 0, filled = 0;
+    int slot = 0;
+    long pending_first = -1, pending_n = 0;   // the window uploaded but not yet processed
+    auto read_chunk = [&](char* dst) -> Error {   // dst == nullptr: read and discard
+        if (raw) {
+            for (int s = 0; s < chunksize; s++)
+                if (Error e = traj.NextRaw(dst ? reinterpret_cast<float*>(dst + fbytes * (size_t)s) : nullptr, &layout, &scale)) return e;
+            return Error();
+        }
+        std::vector<v3::Matrix*> slots((size_t)chunksize, nullptr);
+        if (dst) for (int s = 0; s < chunksize; s++) slots[(size_t)s] = &chunk[(size_t)s];
+        if (Error e = traj.NextConc(slots)) return e;
+        if (dst) for (int s = 0; s < chunksize; s++) memcpy(dst + fbytes * (size_t)s, slots[(size_t)s]->data(), fbytes);
+        return Error();
+    };
+    auto run_pending = [&]() -> Error {
+        if (pending_first < 0) return Error();
+        Error e = process(t, pending_first, pending_n);
+        pending_first = -1;
+        return e;
+    };
+    auto flush = [&]() -> Error {   // the window in `slot` is complete
+        const bool mine = window % o.nranks_ == o.rank_;
+        if (mine && filled > 0) {
+            rc = gcb_traj_upload_async(t, (long)slot * per, pin[slot], filled, raw ? layout : GCB_F64_AOS, raw ? scale : 1.0, slot);
+            if (rc) return deviceError(rc, "gcb_traj_upload_async");
+            if (Error e = run_pending()) return e;   // the previous window, while this upload is in flight
+            pending_first = (long)slot * per;
+            pending_n = filled;
+            mine_total += filled;
+            slot ^= 1;
+            rc = gcb_traj_wait(t, slot);                // the staging buffer about to be refilled is free again
+            if (rc) return deviceError(rc, "gcb_traj_wait");
+        }
+        window++;
+        filled = 0;
+        return Error();
+    };
+    Error rerr;
+    for (long read = 0; !err; read++) {
+        if (read < begin || read % (skip + 1) != 0) {
+            rerr = read_chunk(nullptr);
+            if (rerr) break;
+        }
+        const bool mine = window % o.nranks_ == o.rank_;
+        rerr = read_chunk(mine ? static_cast<char*>(pin[slot]) + fbytes * (size_t)filled : nullptr);
+        if (rerr) break;   // a chunk that cannot be filled is dropped (:323-326)
+        filled += chunksize;
+        nsel += chunksize;
+        if (filled + chunksize > per) err = flush();
+    }
+    if (!err && !rerr.last_frame)  // lovo.go:343-347
+        err = Error("Error while reading trajectory, read " + std::to_string(nsel / chunksize) + " sets of frames. Error: " + rerr.String());
+    if (!err) err = flush();
+    if (!err) err = run_pending();
+    gcb_traj_wait(t, 0);
+    gcb_traj_wait(t, 1);
+    gcb_pinned_free(pin[0]);
+    gcb_pinned_free(pin[1]);
+    gcb_traj_destroy(t);
+    *nselected = nsel;
+    *nlocal = mine_total;
+    return err;
+}
+
+Error RMSDTrajStreamed(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
+                       std::vector<double>* rmsd, int* frames) {
+    const int natoms = mol.Len();
+    *frames = -1;
+    if (ref.NVecs() != natoms) return Error("chem.Super: Ill formed coordinates for Superposition", {"concproc"});
+    rmsd->assign((size_t)natoms, 0.0);
+    std::vector<double> part((size_t)natoms);
+    const bool wb = !o->writeTraj_.empty();
+    std::unique_ptr<dcd::DCDWObj> w;
+    if (wb && dcd::DCDWObj::NewWriter(o->writeTraj_, natoms, &w))
+        fprintf(stderr, "Couldn't open %s for writing. Will not write aligned trajectory\n", o->writeTraj_.c_str());  // lovo.go:299-301
+    std::vector<double> moved;
+    auto process = [&](gcb_traj* t, long first, long n) -> Error {
+        int rc = gcb_peratom_dev_sum(t, first, n, ref.data(), indexes.empty() ? nullptr : indexes.data(), (int)indexes.size(),
+                                     wb ? 1 : 0, nullptr, part.data());
+        if (rc) return deviceError(rc, "RMSDTraj");
+        for (int i = 0; i < natoms; i++) (*rmsd)[(size_t)i] += part[(size_t)i];
+        if (wb && w) {   // the superposed frames of this window, in reading order (lovo.go:337-339)
+            moved.resize((size_t)n * 3 * (size_t)natoms);
+            rc = gcb_traj_download(t, first, n, moved.data());
+            if (rc) return deviceError(rc, "WNext");
+            for (long f = 0; f < n; f++)
+                if (Error e = w->WNextRaw(moved.data() + (size_t)f * 3 * (size_t)natoms, natoms)) return e;
+        }
+        return Error();
+    };
+    long nsel = 0, nlocal = 0;
+    if (Error e = streamSelected(traj, natoms, *o, process, &nsel, &nlocal)) return e;
+    if (o->comm_) {
+        int rc = gcb_allreduce_sum_f64(o->comm_, rmsd->data(), natoms);
+        if (rc) return deviceError(rc, "RMSDTraj");
+    } else if (o->allreduce_) {
+        if (Error e = o->allreduce_(rmsd->data(), (long)natoms)) return e;
+    }
+    const double total = (double)nsel;  // chunksread * chunksize (lovo.go:348)
+    for (auto& v : *rmsd) v = v / total;
+    *frames = (int)nsel;
     return Error();
 }
 
@@ -1052,8 +1184,41 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
         if (!e) d = std::move(fresh);
         return e;
     };
-    if (Error e = load()) return e;
-    return LOVOResident(mol, ref, d, out, o, load);
+    // Resident when the frames fit in device memory (a DCD file holds float32, the device float64: 2 bytes per byte),
+    // otherwise -- or when the caller set a stream window -- every iteration streams the file again (lovo.go:222).
+    bool streamed = o->stream_ > 0;
+    if (!streamed) {
+        struct stat st;
+        int sm = 0, ccmaj = 0, ccmin = 0;
+        size_t total_mem = 0;
+        if (stat(trajname.c_str(), &st) == 0 && gcb_device_info(o->device_, &sm, &total_mem, &ccmaj, &ccmin) == 0 && total_mem > 0)
+            streamed = 2.0 * (double)st.st_size / (double)(o->nranks_ > 0 ? o->nranks_ : 1) > 0.8 * (double)total_mem;
+    }
+    if (!streamed) {
+        if (Error e = load()) return e;
+        return LOVOResident(mol, ref, d, out, o, load);
+    }
+    const std::vector<int> fullindexes = res2atoms(mol, o->atomNames_, o->chains_);
+    const std::string printtraj = o->writeTraj_;
+    o->writeTraj_.clear();  // lovo.go:209-211
+    LovoState st(fullindexes, o->lessThanRMSD_, o->minimumN_);
+    std::vector<double> rmsd;
+    int frames = 0;
+    for (;;) {
+        if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228
+        std::unique_ptr<chem::ConcTraj> traj;
+        if (Error e = opentraj(trajname, &traj)) return e;
+        Error e = RMSDTrajStreamed(mol, ref, *traj, st.FitIndexes(), o, &rmsd, &frames);
+        traj->Close();
+        if (e) return e;
+        Error serr;
+        const bool converged = st.Step(rmsd, &serr);
+        if (serr) return serr;
+        if (converged) break;
+        if (st.Iterations() >= o->maxIter_) return Error("align.LOVO: no convergence after " + std::to_string(st.Iterations()) + " iterations");
+    }
+    st.Finish(mol, frames, out);
+    return Error();
 }
 
 }  // namespace align

@@ -278,6 +278,10 @@ class Options {
     // host-side replacement of the collective (gloo in the CPU tests); sums a vector across ranks in place
     void AllReduce(std::function<Error(double*, long)> f) { allreduce_ = std::move(f); }
     int MaxIterations(const int* n = nullptr) { if (n && *n > 0) maxIter_ = *n; return maxIter_; }
+    // Frames per device window when the trajectory is streamed instead of made resident (0 = resident; LOVO switches to
+    // streaming by itself when the file cannot fit in device memory and then re-reads it on every iteration, as the
+    // reference does, lovo.go:222).
+    long StreamWindow(const long* frames = nullptr) { if (frames && *frames >= 0) stream_ = *frames; return stream_; }
 
     int begin_ = 0, skip_ = 0, cpus_ = 1;
     std::vector<std::string> atomNames_, chains_;
@@ -285,6 +289,7 @@ class Options {
     double lessThanRMSD_ = 1.0;
     int minimumN_ = 10;
     int device_ = 0, rank_ = 0, nranks_ = 1, maxIter_ = 1000;
+    long stream_ = 0;
     gcb_comm* comm_ = nullptr;
     std::function<Error(double*, long)> allreduce_;
 };
@@ -369,6 +374,10 @@ class DeviceTrajectory {
 
 Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
                std::vector<double>* rmsd, int* frames);
+// The same pass with bounded memory: the selected frames go through two pinned staging buffers and a device window of
+// 2 x o->StreamWindow() frames (the upload of one window overlaps the reader filling the next); ranks take windows in turn.
+Error RMSDTrajStreamed(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& traj, const std::vector<int>& indexes, Options* o,
+                       std::vector<double>* rmsd, int* frames);
 Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& trajname, LOVOReturn* out, Options* opt = nullptr);
 // The LOVO iteration (lovo.go:221-252) over a trajectory that is already resident on the device.  `reload`, when
 // given, restores the frames after a pass that wrote the aligned trajectory back over them.

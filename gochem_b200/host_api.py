@@ -293,3 +293,28 @@ def ConcMolRDF(dcd_path, coords0, molnames, molids, chains, masses, refindexes, 
     if rc:
         raise _err(rc)
     return rdf, cum, fr.value
+
+
+# ---- streamed variants: bounded memory, the file goes through a device window (config 5 through the reference's API) ----
+def RMSDTrajStreamed(dcd_path, ref, indexes, cpus, window_frames, begin=0, skip=0, write_traj="", dev=0, rank=0, nranks=1, comm=None):
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    idx = np.ascontiguousarray(indexes, dtype=np.int32)
+    out = np.zeros(ref.shape[0])
+    frames = C.c_int(0)
+    rc = load().gch_rmsd_traj_streamed(dcd_path.encode(), _d(ref), ref.shape[0], _i(idx), idx.size, cpus, begin, skip,
+                                       write_traj.encode(), C.c_long(window_frames), dev, rank, nranks, comm, _d(out), C.byref(frames))
+    if rc:
+        raise _err(rc)
+    return out, frames.value
+
+
+def LOVOStreamed(dcd_path, ref, cpus, window_frames, less_than_rmsd=1.0, minimum_n=10, dev=0):
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    n = ref.shape[0]
+    N, nr, fr, it = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    nat, rm = np.zeros(n, dtype=np.int32), np.zeros(n)
+    rc = load().gch_lovo_streamed(dcd_path.encode(), _d(ref), n, cpus, C.c_double(less_than_rmsd), minimum_n, C.c_long(window_frames), dev,
+                                  C.byref(N), _i(nat), _d(rm), C.byref(nr), C.byref(fr), C.byref(it))
+    if rc:
+        raise _err(rc)
+    return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm[: nr.value].copy(), FramesRead=fr.value, Iterations=it.value)

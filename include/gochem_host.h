@@ -68,6 +68,14 @@ int gch_lovo(const char *dcd_path, const double *ref, int natoms, const char *co
              int dev, int rank, int nranks, void *comm, int *N, int *natoms_out, double *rmsd_out, int *nrmsd, int *frames,
              int *iterations, char *text, size_t text_cap);
 
+/* Same two calls with the trajectory streamed through a device window of 2 x window_frames frames instead of made resident
+ * (bounded memory; LOVO then re-reads the file on every iteration like the reference, lovo.go:222). */
+int gch_rmsd_traj_streamed(const char *dcd_path, const double *ref, int natoms, const int *indexes, int nidx, int cpus, int begin,
+                           int skip, const char *write_traj, long window_frames, int dev, int rank, int nranks, void *comm,
+                           double *rmsd, int *frames);
+int gch_lovo_streamed(const char *dcd_path, const double *ref, int natoms, int cpus, double less_than_rmsd, int minimum_n,
+                      long window_frames, int dev, int *N, int *natoms_out, double *rmsd_out, int *nrmsd, int *frames, int *iterations);
+
 /* The LOVO iteration over a trajectory already resident on the device (a gcb_traj handle holding nlocal of the
  * nselected_total frames all ranks hold together); topology: all "CA", chain "A". */
 int gch_lovo_resident(void *traj_handle, long nlocal, long nselected_total, const double *ref, int natoms, int cpus,

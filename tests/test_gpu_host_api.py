@@ -90,6 +90,36 @@ def test_sharded_rmsdtraj_partials_add_up(tmp_path):
     assert np.abs(sum(parts) - whole).max() < 1e-12
 
 
+def test_streamed_rmsdtraj_and_lovo_match_the_resident_path(tmp_path):
+    """Bounded-memory variants: the DCD file goes through a device window of a few frames (several windows, a ragged last one,
+    windows dealt to ranks in turn); same chunk rules, same results as the resident path and the oracle."""
+    ref, frames = synth.make_case(300, 61, through_f32=True)
+    p = str(tmp_path / "traj.dcd")
+    H.dcd_write(p, frames)
+    idx = np.arange(0, 300, 3)
+    for cpus, begin, skip, window in [(4, 0, 0, 8), (3, 0, 0, 7), (2, 4, 2, 2), (5, 0, 0, 1000)]:
+        got, nframes = H.RMSDTrajStreamed(p, ref, idx, cpus, window, begin, skip)
+        want, total = oracle.rmsd_traj(frames, ref, idx, cpus, begin, skip)
+        res, nres = H.RMSDTraj(p, ref, idx, cpus, begin, skip)
+        assert nframes == total == nres
+        assert np.abs(got - want).max() < 1e-10 and np.abs(got - res).max() < 1e-12
+    # ranks take windows in turn; without a communicator each returns its share / total
+    parts = [H.RMSDTrajStreamed(p, ref, idx, 4, 8, rank=r, nranks=3)[0] for r in range(3)]
+    whole, _ = H.RMSDTrajStreamed(p, ref, idx, 4, 8)
+    assert np.abs(sum(parts) - whole).max() < 1e-12
+    # writeTraj while streaming: the aligned frames in reading order
+    out = str(tmp_path / "aligned_stream.dcd")
+    H.RMSDTrajStreamed(p, ref, idx, 4, 8, write_traj=out)
+    _, total, aligned = oracle.rmsd_traj(frames, ref, idx, 4, want_aligned=True)
+    back, nf, na = H.dcd_read(out, 80, 300)
+    assert nf == total == 60 and np.abs(back - aligned.astype(np.float32)).max() < 1e-4
+    # LOVO re-reading the file on every iteration (lovo.go:222) == LOVO on the resident trajectory
+    a = H.LOVOStreamed(p, ref, 4, 12)
+    b = H.LOVO(p, ref, 4)
+    assert a["N"] == b["N"] and a["Iterations"] == b["Iterations"] and list(a["Natoms"]) == list(b["Natoms"])
+    assert a["FramesRead"] == b["FramesRead"] and np.abs(a["RMSD"] - b["RMSD"]).max() < 1e-12
+
+
 def test_lovo_like_TestLovo(tmp_path, golden_dir):
     z = np.load(os.path.join(golden_dir, "lovo_n150_f42.npz"))
     ref, frames, cpus = z["ref"].astype(np.float64), z["frames"].astype(np.float64), int(z["cpus"])
