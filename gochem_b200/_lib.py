@@ -66,6 +66,8 @@ def load() -> C.CDLL:
         "gcb_traj_upload": (I, [P, L, P, L, I, D]),
         "gcb_traj_upload_async": (I, [P, L, P, L, I, D, I]),
         "gcb_traj_wait": (I, [P, I]),
+        "gcb_traj_upload_records_async": (I, [P, L, P, L, L, L, L, L, D, I]),
+        "gcb_traj_stage_bytes": (C.c_size_t, [P]),
         "gcb_traj_download": (I, [P, L, L, P]),
         "gcb_super_rmsd": (I, [P, L, L, P, I, P, P, I, I, P, P, P, P]),
         "gcb_super_rmsd_async": (I, [P, L, L, P, I, P, P, I, I]),

@@ -255,6 +255,7 @@ fail:
 }
 
 int gcb_traj_natoms(const gcb_traj* t) { return t ? t->natoms : -1; }
+size_t gcb_traj_stage_bytes(const gcb_traj* t) { return t ? t->stage_bytes : 0; }
 long gcb_traj_capacity(const gcb_traj* t) { return t ? t->cap : -1; }
 long gcb_traj_nframes(const gcb_traj* t) { return t ? t->nframes : -1; }
 
@@ -307,6 +308,33 @@ int gcb_traj_upload_async(gcb_traj* t, long first, const void* pinned, long nfra
     if (rc) return rc;
     GCB_CUDA(cudaEventRecord(t->copy_done[slot], s));
     GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));  // later kernels see the frames
+    if (first + nframes > t->nframes) t->nframes = first + nframes;
+    return GCB_OK;
+}
+
+int gcb_traj_upload_records_async(gcb_traj* t, long first, const void* pinned, long nframes, long record_bytes, long off_x,
+                                  long off_y, long off_z, double scale, int slot) {
+    int rc = check_window(t, first, nframes, false);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1) { set_error("slot must be 0 or 1"); return GCB_ERR_ARG; }
+    const long plane = 4L * t->natoms;
+    if (record_bytes <= 0 || (record_bytes & 3) || ((off_x | off_y | off_z) & 3) || off_x < 0 || off_y < 0 || off_z < 0 ||
+        off_x + plane > record_bytes || off_y + plane > record_bytes || off_z + plane > record_bytes) {
+        set_error("record layout (%ld bytes, planes at %ld / %ld / %ld) does not hold three float32 planes of %d atoms", record_bytes,
+                  off_x, off_y, off_z, t->natoms);
+        return GCB_ERR_ARG;
+    }
+    const size_t bytes = (size_t)record_bytes * (size_t)nframes;
+    if (bytes > t->stage_bytes) { set_error("async upload of %zu bytes exceeds the %zu-byte staging slot", bytes, t->stage_bytes); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    cudaStream_t s = t->copy_stream[slot];
+    GCB_CUDA(cudaEventRecord(t->ev1, t->stream));   // do not overwrite frame slots a queued kernel still reads
+    GCB_CUDA(cudaStreamWaitEvent(s, t->ev1, 0));
+    GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], pinned, bytes, cudaMemcpyHostToDevice, s));
+    rc = launch_upload_records(t, s, t->d_stage[slot], first, nframes, record_bytes, off_x, off_y, off_z, scale);
+    if (rc) return rc;
+    GCB_CUDA(cudaEventRecord(t->copy_done[slot], s));
+    GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));
     if (first + nframes > t->nframes) t->nframes = first + nframes;
     return GCB_OK;
 }

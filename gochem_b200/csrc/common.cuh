@@ -121,6 +121,8 @@ int comm_peer_blocks(gcb_comm* c, size_t bytes, double** blk);
 // kernels / launchers implemented across the .cu files
 int launch_upload_convert(gcb_traj* t, cudaStream_t s, const void* d_src, long first, long nframes, int layout, double scale);
 int launch_download_convert(gcb_traj* t, cudaStream_t s, double* d_dst, long first, long nframes);
+int launch_upload_records(gcb_traj* t, cudaStream_t s, const void* d_src, long first, long nframes, long record_bytes, long ox,
+                          long oy, long oz, double scale);
 int launch_super_generic(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* grid_out);
 int launch_super_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx);
 int launch_rmsd_nofit(gcb_traj* t, const double* frames, long nframes, const double* ref_planes, const double* weight,

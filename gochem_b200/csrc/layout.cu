@@ -39,6 +39,30 @@ __global__ void __launch_bounds__(256) upload_convert_kernel(const T* __restrict
     }
 }
 
+// float32 planes inside fixed-size records (raw DCD frames with their Fortran record markers, optional unit-cell block included):
+// record f starts at src + f * record_bytes and holds x[], y[], z[] at byte offsets ox, oy, oz (traj/dcd/dcd.go:380-413).
+__global__ void __launch_bounds__(256) upload_records_kernel(const unsigned char* __restrict__ src, double* __restrict__ dst, int natoms,
+                                                            int np, long nframes, long record_bytes, long ox, long oy, long oz,
+                                                            double scale) {
+    const long total = nframes * (long)np;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        const long f = g / np;
+        const int i = (int)(g - f * np);
+        double x = 0.0, y = 0.0, z = 0.0;
+        if (i < natoms) {
+            const unsigned char* r = src + f * record_bytes;
+            x = (double)reinterpret_cast<const float*>(r + ox)[i];
+            y = (double)reinterpret_cast<const float*>(r + oy)[i];
+            z = (double)reinterpret_cast<const float*>(r + oz)[i];
+            if (scale != 1.0) { x = scale * x; y = scale * y; z = scale * z; }
+        }
+        double* d = dst + f * 3L * np;
+        d[i] = x;
+        d[np + i] = y;
+        d[2L * np + i] = z;
+    }
+}
+
 __global__ void __launch_bounds__(256) download_convert_kernel(const double* __restrict__ src, double* __restrict__ dst,
                                                               int natoms, int np, long nframes) {
     const long total = nframes * (long)natoms;
@@ -80,6 +104,17 @@ int launch_upload_convert(gcb_traj* t, cudaStream_t s, const void* d_src, long f
             set_error("unknown host layout %d", layout);
             return GCB_ERR_ARG;
     }
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
+int launch_upload_records(gcb_traj* t, cudaStream_t s, const void* d_src, long first, long nframes, long record_bytes, long ox,
+                          long oy, long oz, double scale) {
+    if (nframes <= 0) return GCB_OK;
+    double* dst = t->d_frames + first * 3L * t->np;
+    const int grid = grid_for(nframes * (long)t->np, t->sm_count);
+    upload_records_kernel<<<grid, 256, 0, s>>>((const unsigned char*)d_src, dst, t->natoms, t->np, nframes, record_bytes, ox, oy, oz, scale);
     GCB_LAUNCHED();
     GCB_CUDA(cudaGetLastError());
     return GCB_OK;

@@ -516,6 +516,70 @@ Error DCDObj::NextConc(std::vector<v3::Matrix*>& frames) {  // dcd.go:513-546
     return Error();
 }
 
+// Works out how one frame sits in the file (dcd.go:349-434 read in one go): [4 | cell | 4] (CHARMM extra block, when present)
+// [4 | x | 4] [4 | y | 4] [4 | z | 4] and [4 | fourth dimension | 4] when flagged.  The file position is left unchanged.
+Error DCDObj::probeRecord() {
+    if (rec_bytes_ > 0) return Error();
+    const long pos = ftell(f_);
+    if (pos < 0) return dcdError("ftell failed", filename_, {"NextRecords"});
+    const long plane = 4L * natoms_;
+    long off = 0;
+    int32_t b = 0;
+    auto back = [&]() { fseek(f_, pos, SEEK_SET); };
+    if (fread(&b, 4, 1, f_) != 1) { back(); return chem::newLastFrameError(filename_, "NextRecords"); }
+    if (extrablock_ && b < natoms_ * 3) {   // the unit-cell record comes first (dcd.go:361-376)
+        off = 4 + (long)b + 4;
+        if (fseek(f_, pos + off, SEEK_SET) != 0 || fread(&b, 4, 1, f_) != 1) { back(); return chem::newLastFrameError(filename_, "NextRecords"); }
+    }
+    if ((long)b != plane) { back(); return dcdError("Wrong format", filename_, {"NextRecords"}); }
+    rec_off_[0] = off + 4;
+    rec_off_[1] = rec_off_[0] + plane + 8;
+    rec_off_[2] = rec_off_[1] + plane + 8;
+    long total = rec_off_[2] + plane + 4;
+    if (charmm_ && fourdim_) {
+        int32_t b4 = 0;
+        if (fseek(f_, pos + total, SEEK_SET) == 0 && fread(&b4, 4, 1, f_) == 1 && b4 >= 0) total += 4 + (long)b4 + 4;
+    }
+    back();
+    rec_bytes_ = total;
+    return Error();
+}
+
+Error DCDObj::NextRecords(char* dst, long max_frames, long* got, long* record_bytes, long* off, double* scale) {
+    *got = 0;
+    *scale = 1.0;
+    if (!readable_) return dcdError("Traj object uninitialized to read", filename_, {"NextRecords"});
+    if (Error e = probeRecord()) { if (e.last_frame) Close(); return e; }
+    *record_bytes = rec_bytes_;
+    off[0] = rec_off_[0]; off[1] = rec_off_[1]; off[2] = rec_off_[2];
+    if (max_frames <= 0) return Error();
+    long n = 0;
+    if (dst) {
+        const size_t bytes = fread(dst, 1, (size_t)rec_bytes_ * (size_t)max_frames, f_);
+        n = (long)(bytes / (size_t)rec_bytes_);   // a trailing partial frame is not a frame
+        const int32_t plane = 4 * natoms_;
+        for (long f = 0; f < n; f++) {   // the markers around every plane (dcd.go:436-452 checks them per block)
+            const char* r = dst + (size_t)f * (size_t)rec_bytes_;
+            for (int c = 0; c < 3; c++) {
+                int32_t a, b;
+                memcpy(&a, r + rec_off_[c] - 4, 4);
+                memcpy(&b, r + rec_off_[c] + plane, 4);
+                if (a != plane || b != plane) return dcdError("Wrong format", filename_, {"NextRecords"});
+            }
+        }
+    } else {
+        const long pos = ftell(f_);
+        struct stat st;
+        if (pos < 0 || fstat(fileno(f_), &st) != 0) return dcdError("cannot size the file", filename_, {"NextRecords"});
+        const long avail = ((long)st.st_size - pos) / rec_bytes_;
+        n = avail < max_frames ? (avail < 0 ? 0 : avail) : max_frames;
+        if (fseek(f_, pos + n * rec_bytes_, SEEK_SET) != 0) return dcdError("seek failed", filename_, {"NextRecords"});
+    }
+    *got = n;
+    if (n == 0) { Close(); return chem::newLastFrameError(filename_, "NextRecords"); }
+    return Error();
+}
+
 Error DCDObj::NextRaw(float* dst, int* layout, double* scale) {
     *layout = GCB_F32_SOA;
     *scale = 1.0;
@@ -1006,9 +1070,21 @@ static Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
     const int chunksize = o.cpus_;
     const long begin = o.begin_ / chunksize, skip = o.skip_ / chunksize;
     const bool raw = traj.HasRawFeed();
-    const size_t fbytes = (raw ? sizeof(float) : sizeof(double)) * 3 * (size_t)natoms;
-    long per = o.stream_ > 0 ? o.stream_ : (long)((64u << 20) / fbytes);
+    // bulk path: whole runs of frames read() straight into the pinned buffer as they sit in the file (no begin / skip gaps)
+    bool records = traj.HasRecordFeed() && begin == 0 && skip == 0;
+    long rec_bytes = 0, rec_off[3] = {0, 0, 0};
+    double rec_scale = 1.0;
+    if (records) {
+        long got = 0;
+        Error e = traj.NextRecords(nullptr, 0, &got, &rec_bytes, rec_off, &rec_scale);   // layout only
+        if (e && e.last_frame) { *nselected = 0; *nlocal = 0; return Error(); }
+        if (e || rec_bytes <= 0) records = false;
+    }
+    const size_t fbytes = records ? (size_t)rec_bytes : (raw ? sizeof(float) : sizeof(double)) * 3 * (size_t)natoms;
+    long per = (long)((64u << 20) / fbytes);
+    if (o.stream_ > 0 && o.stream_ < per) per = o.stream_;
     per = std::max<long>(chunksize, per / chunksize * chunksize);
+    if (records && (size_t)per * fbytes > (64u << 20)) records = false;   // one chunk of records must fit a staging slot
     gcb_traj* t = nullptr;
     int rc = gcb_traj_create(o.device_, natoms, 2 * per, &t);
     if (rc) return deviceError(rc, "gcb_traj_create");
@@ -1059,7 +1135,31 @@ static Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
         return Error();
     };
     Error rerr;
-    for (long read = 0; !err; read++) {
+    if (records) {
+        rerr = chem::newLastFrameError("", "RMSDTraj");
+        while (!err) {
+            const bool mine = window % o.nranks_ == o.rank_;
+            long got = 0;
+            Error e = traj.NextRecords(mine ? static_cast<char*>(pin[slot]) : nullptr, per, &got, &rec_bytes, rec_off, &rec_scale);
+            if (e) { rerr = e; break; }
+            const long usable = got - got % chunksize;   // a chunk the file cannot fill is dropped (:323-326)
+            nsel += usable;
+            if (mine && usable > 0) {
+                rc = gcb_traj_upload_records_async(t, (long)slot * per, pin[slot], usable, rec_bytes, rec_off[0], rec_off[1], rec_off[2],
+                                                   rec_scale, slot);
+                if (rc) { err = deviceError(rc, "gcb_traj_upload_records_async"); break; }
+                if ((err = run_pending())) break;
+                pending_first = (long)slot * per;
+                pending_n = usable;
+                mine_total += usable;
+                slot ^= 1;
+                if ((rc = gcb_traj_wait(t, slot))) { err = deviceError(rc, "gcb_traj_wait"); break; }
+            }
+            window++;
+            if (got < per) break;   // the file ended inside this window
+        }
+    }
+    for (long read = 0; !err && !records; read++) {
         if (read < begin || read % (skip + 1) != 0) {
             rerr = read_chunk(nullptr);
             if (rerr) break;
@@ -1073,7 +1173,7 @@ static Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
     }
     if (!err && !rerr.last_frame)  // lovo.go:343-347
         err = Error("Error while reading trajectory, read " + std::to_string(nsel / chunksize) + " sets of frames. Error: " + rerr.String());
-    if (!err) err = flush();
+    if (!err && !records) err = flush();
     if (!err) err = run_pending();
     gcb_traj_wait(t, 0);
     gcb_traj_wait(t, 1);

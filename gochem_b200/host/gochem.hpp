@@ -154,6 +154,13 @@ class ConcTraj {
     // Default: not available.
     virtual bool HasRawFeed() const { return false; }
     virtual Error NextRaw(float* /*dst*/, int* /*layout*/, double* /*scale*/) { return Error("raw feed not supported"); }
+    // Optional bulk feed: the next up-to-`max_frames` frames exactly as they sit in the file, one read() into dst
+    // (dst == nullptr: skip them).  Every frame is a record of *record_bytes bytes with float32 x[], y[], z[] at byte
+    // offsets off[0..2]; *got frames were delivered (0 with a LastFrameError at the end).
+    virtual bool HasRecordFeed() const { return false; }
+    virtual Error NextRecords(char* /*dst*/, long /*max_frames*/, long* /*got*/, long* /*record_bytes*/, long* /*off*/, double* /*scale*/) {
+        return Error("record feed not supported");
+    }
 };
 
 // chem.Molecule used as a RAM-backed trajectory (chem.go:693-762).
@@ -188,12 +195,16 @@ class DCDObj : public chem::Traj, public chem::ConcTraj {
     void Close() override;
     bool HasRawFeed() const override { return true; }
     Error NextRaw(float* dst, int* layout, double* scale) override;  // x[], y[], z[] planes, as stored on disk
+    bool HasRecordFeed() const override { return readable_ && !swap_; }
+    Error NextRecords(char* dst, long max_frames, long* got, long* record_bytes, long* off, double* scale) override;
 
   private:
     Error initRead(const std::string& name);
     Error nextRaw(float* x, float* y, float* z);
     Error readI32(int32_t* v);
     Error readFloat32Block(int32_t blocksize, float* block, int n);
+    Error probeRecord();
+    long rec_bytes_ = 0, rec_off_[3] = {0, 0, 0};
     std::string filename_;
     FILE* f_ = nullptr;
     int32_t natoms_ = 0, fixed_ = 0;

@@ -89,6 +89,13 @@ int gcb_traj_upload(gcb_traj *t, long first, const void *host, long nframes, int
 /* Same, from a gcb_pinned_alloc buffer, on copy stream `slot` (0 or 1); returns once queued.
  * The buffer may be reused after gcb_traj_wait(t, slot). */
 int gcb_traj_upload_async(gcb_traj *t, long first, const void *pinned, long nframes, int layout, double scale, int slot);
+/* Same for float32 planes that sit inside fixed-size records: frame f is the record_bytes bytes at pinned + f * record_bytes with
+ * x[], y[], z[] at byte offsets off_x / off_y / off_z.  This is a raw DCD frame -- Fortran record markers and the optional
+ * unit-cell block included (traj/dcd/dcd.go:349-434) -- so a reader can read() whole runs of frames straight into the pinned
+ * buffer with one call and no host-side pass over the data.  How many bytes one staging slot takes: gcb_traj_stage_bytes. */
+int gcb_traj_upload_records_async(gcb_traj *t, long first, const void *pinned, long nframes, long record_bytes, long off_x,
+                                  long off_y, long off_z, double scale, int slot);
+size_t gcb_traj_stage_bytes(const gcb_traj *t);
 int gcb_traj_wait(gcb_traj *t, int slot);
 /* Frames back to float64 AoS (what chem.Super leaves in `test`, handy.go:207-213). */
 int gcb_traj_download(gcb_traj *t, long first, long nframes, double *host_aos);
