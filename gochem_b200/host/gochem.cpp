@@ -546,6 +546,15 @@ Error DCDObj::probeRecord() {
     return Error();
 }
 
+long DCDObj::RecordsAvailable() {
+    if (!readable_ || probeRecord()) return -1;
+    const long pos = ftell(f_);
+    struct stat st;
+    if (pos < 0 || fstat(fileno(f_), &st) != 0) return -1;
+    const long n = ((long)st.st_size - pos) / rec_bytes_;
+    return n < 0 ? 0 : n;
+}
+
 Error DCDObj::NextRecords(char* dst, long max_frames, long* got, long* record_bytes, long* off, double* scale) {
     *got = 0;
     *scale = 1.0;
@@ -565,7 +574,7 @@ Error DCDObj::NextRecords(char* dst, long max_frames, long* got, long* record_by
         n = avail < max_frames ? (avail < 0 ? 0 : avail) : max_frames;
         const size_t bytes = (size_t)n * (size_t)rec_bytes_;
         const int fd = fileno(f_);
-        unsigned nthreads = bytes >= (16u << 20) ? std::min(4u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+        unsigned nthreads = bytes >= (16u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
         std::vector<std::thread> th;
         std::vector<int> ok(nthreads, 1);
         const size_t slice = (bytes / nthreads + 4095) / 4096 * 4096;
@@ -957,6 +966,51 @@ Error DeviceTrajectory::Load(chem::ConcTraj& traj, int natoms, const Options& o,
     if (traj.Len() != natoms) return Error("align.RMSDTraj: trajectory and molecule differ in the number of atoms");
     const int chunksize = o.cpus_;
     const long begin = o.begin_ / chunksize, skip = o.skip_ / chunksize;
+    // A source that hands out raw records and knows how many are left (a DCD file) goes straight from the file to the device:
+    // this rank's block of the selected frames is read window by window into pinned memory and uploaded as it sits in the file.
+    if (traj.HasRecordFeed() && begin == 0 && skip == 0) {
+        long rb = 0, off[3] = {0, 0, 0}, got = 0;
+        double sc = 1.0;
+        const long avail = traj.RecordsAvailable();
+        Error pe = traj.NextRecords(nullptr, 0, &got, &rb, off, &sc);
+        if (avail >= 0 && !pe && rb > 0 && (size_t)chunksize * (size_t)rb <= (64u << 20)) {
+            std::unique_ptr<DeviceTrajectory> d(new DeviceTrajectory());
+            d->natoms_ = natoms;
+            d->nselected_ = avail / chunksize * chunksize;   // a chunk the file cannot fill is dropped (:323-326)
+            long first = 0, count = 0;
+            shardRange(d->nselected_, o.rank_, o.nranks_, &first, &count);
+            d->nlocal_ = count;
+            int rc = gcb_traj_create(o.device_, natoms, count > 0 ? count : 1, &d->t_);
+            if (rc) return deviceError(rc, "gcb_traj_create");
+            const long per = std::max<long>(1, (long)((64u << 20) / (size_t)rb));
+            void* pin[2] = {nullptr, nullptr};
+            for (int s = 0; s < 2; s++)
+                if ((rc = gcb_pinned_alloc((size_t)per * (size_t)rb, &pin[s]))) { gcb_pinned_free(pin[0]); return deviceError(rc, "gcb_pinned_alloc"); }
+            Error up;
+            if (first > 0) {
+                Error e = traj.NextRecords(nullptr, first, &got, &rb, off, &sc);
+                if (e || got != first) up = e ? e : Error("align.RMSDTraj: the trajectory ended before this rank's block");
+            }
+            int slot = 0;
+            for (long done = 0; done < count && !up; slot ^= 1) {
+                const long want = std::min(per, count - done);
+                if ((rc = gcb_traj_wait(d->t_, slot))) { up = deviceError(rc, "gcb_traj_wait"); break; }
+                Error e = traj.NextRecords(static_cast<char*>(pin[slot]), want, &got, &rb, off, &sc);
+                if (e || got != want) { up = e ? e : Error("align.RMSDTraj: short read"); break; }
+                rc = gcb_traj_upload_records_async(d->t_, done, pin[slot], got, rb, off[0], off[1], off[2], sc, slot);
+                if (rc) up = deviceError(rc, "gcb_traj_upload_records_async");
+                done += got;
+            }
+            gcb_traj_wait(d->t_, 0);
+            gcb_traj_wait(d->t_, 1);
+            gcb_pinned_free(pin[0]);
+            gcb_pinned_free(pin[1]);
+            if (up) return up;
+            gcb_traj_set_nframes(d->t_, count);
+            *out = std::move(d);
+            return Error();
+        }
+    }
     const bool raw = traj.HasRawFeed();
     const size_t fbytes = (raw ? sizeof(float) : sizeof(double)) * 3 * (size_t)natoms;
     // Pass 1 over the source: keep the selected frames in host memory (the reader tells us nothing reliable

@@ -158,6 +158,7 @@ class ConcTraj {
     // (dst == nullptr: skip them).  Every frame is a record of *record_bytes bytes with float32 x[], y[], z[] at byte
     // offsets off[0..2]; *got frames were delivered (0 with a LastFrameError at the end).
     virtual bool HasRecordFeed() const { return false; }
+    virtual long RecordsAvailable() { return -1; }   // whole frames left in the source, when it can tell
     virtual Error NextRecords(char* /*dst*/, long /*max_frames*/, long* /*got*/, long* /*record_bytes*/, long* /*off*/, double* /*scale*/) {
         return Error("record feed not supported");
     }
@@ -196,6 +197,7 @@ class DCDObj : public chem::Traj, public chem::ConcTraj {
     bool HasRawFeed() const override { return true; }
     Error NextRaw(float* dst, int* layout, double* scale) override;  // x[], y[], z[] planes, as stored on disk
     bool HasRecordFeed() const override { return readable_ && !swap_; }
+    long RecordsAvailable() override;
     Error NextRecords(char* dst, long max_frames, long* got, long* record_bytes, long* off, double* scale) override;
 
   private:

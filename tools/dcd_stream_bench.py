@@ -32,7 +32,15 @@ with open(path, "rb") as f:
     while f.read(64 << 20):
         pass
 dt_read = time.perf_counter() - t0
+t0 = time.perf_counter()
+lv = H.LOVO(path, ref, cpus)                           # align.LOVO from the file: load once, iterate on the resident frames
+dt_lovo = time.perf_counter() - t0
+t0 = time.perf_counter()
+ls = H.LOVOStreamed(path, ref, cpus, 0)                # the file re-read on every iteration (lovo.go:222), bounded memory
+dt_lovo_s = time.perf_counter() - t0
 os.remove(path)
-print(json.dumps({"natoms": natoms, "nframes": n, "file_GB": size / 1e9, "streamed_seconds": dt, "streamed_frames_per_s": n / dt,
+print(json.dumps({"lovo_resident_seconds": dt_lovo, "lovo_streamed_seconds": dt_lovo_s, "lovo_iterations": lv["Iterations"],
+                  "lovo_same_core": bool(list(lv["Natoms"]) == list(ls["Natoms"])), "lovo_N": lv["N"],
+                  "natoms": natoms, "nframes": n, "file_GB": size / 1e9, "streamed_seconds": dt, "streamed_frames_per_s": n / dt,
                   "streamed_file_GBs": size / dt / 1e9, "resident_seconds": dt_res, "resident_frames_per_s": n2 / dt_res,
                   "plain_file_read_seconds": dt_read, "max_abs_diff_streamed_vs_resident": float(np.abs(got - res).max())}))
