@@ -181,7 +181,36 @@ int gch_dcd_read(const char* path, double* out, long cap, long* nframes, int* na
     *natoms = d->Len();
     long n = 0;
     const size_t fsz = 3 * (size_t)d->Len();
-    if (chunk <= 0) {
+    if (chunk < 0) {
+        // the bulk record feed (NextRecords) in windows of -chunk frames, unpacked on the host: what the device kernel
+        // upload_records_kernel does with the same bytes
+        if (!d->HasRecordFeed()) return fail(Error("record feed not available for this file"));
+        const long win = -(long)chunk;
+        std::vector<char> buf;
+        for (;;) {
+            long got = 0, rb = 0, off[3] = {0, 0, 0};
+            double sc = 1.0;
+            if (buf.empty()) {
+                if (Error e = d->NextRecords(nullptr, 0, &got, &rb, off, &sc)) { if (e.last_frame) break; return fail(e); }
+                buf.resize((size_t)rb * (size_t)win);
+            }
+            Error e = d->NextRecords(buf.data(), win, &got, &rb, off, &sc);
+            if (e) {
+                if (!e.last_frame) return fail(e);
+                break;
+            }
+            for (long f = 0; f < got; f++, n++) {
+                if (n >= cap) continue;
+                const char* r = buf.data() + (size_t)f * (size_t)rb;
+                for (int i = 0; i < d->Len(); i++)
+                    for (int c = 0; c < 3; c++) {
+                        float v;
+                        memcpy(&v, r + off[c] + 4 * (size_t)i, 4);
+                        out[(size_t)n * fsz + 3 * (size_t)i + c] = sc * (double)v;
+                    }
+            }
+        }
+    } else if (chunk == 0) {
         v3::Matrix m = v3::Matrix::Zeros(d->Len());
         for (;;) {
             Error e = d->Next(&m);

@@ -135,6 +135,43 @@ def test_dcd_round_trip(tmp_path):
     assert nf == 9 and np.array_equal(back, frames)
 
 
+def test_dcd_bulk_record_feed(tmp_path):
+    """ConcTraj::NextRecords: whole runs of raw frames in one read, every window size, against the frame-by-frame reader; also on
+    CHARMM files that carry a unit-cell record before every frame and a fourth-dimension record after it (dcd.go:361-376, 404-417)."""
+    natoms, nframes = 37, 11
+    ref, frames = synth.make_case(natoms, nframes, through_f32=True)
+    p = str(tmp_path / "plain.dcd")
+    H.dcd_write(p, frames)
+    for win in (1, 4, 11, 1000):
+        back, nf, na = H.dcd_read(p, 20, natoms, chunk=-win)
+        assert (nf, na) == (nframes, natoms) and np.array_equal(back, frames)
+    raw = open(p, "rb").read()
+    body = 92 + 4 + 4 + 160 + 4 + 4 + 8
+    plane = 4 * natoms
+    rec = 3 * (plane + 8)
+    assert len(raw) == body + nframes * rec
+    cell = struct.pack("<i6di", 48, 50.0, 90.0, 50.0, 90.0, 90.0, 50.0, 48)
+    for flag in (2, 1):   # 2: unit cell only; 1: the reference then also expects a fourth-dimension record (dcd.go:196-201)
+        out = bytearray(raw[:body])
+        out[48:52] = struct.pack("<i", flag)
+        for f in range(nframes):
+            out += cell + raw[body + f * rec: body + (f + 1) * rec]
+            if flag == 1:
+                out += struct.pack("<i", plane) + bytes(plane) + struct.pack("<i", plane)
+        pc = str(tmp_path / f"charmm{flag}.dcd")
+        open(pc, "wb").write(bytes(out))
+        slow, nf, na = H.dcd_read(pc, 20, natoms)
+        assert nf == nframes and np.array_equal(slow, frames)
+        for win in (1, 3, 1000):
+            back, nf, na = H.dcd_read(pc, 20, natoms, chunk=-win)
+            assert nf == nframes and np.array_equal(back, frames)
+    # a file cut in the middle of a frame: the partial frame is not delivered
+    pt = str(tmp_path / "cut.dcd")
+    open(pt, "wb").write(raw[: body + 5 * rec + 40])
+    back, nf, na = H.dcd_read(pt, 20, natoms, chunk=-4)
+    assert nf == 5 and np.array_equal(back, frames[:5])
+
+
 def _gloo_worker(rank, world, port, tmpdir):
     import torch
     import torch.distributed as dist
