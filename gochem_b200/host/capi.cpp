@@ -374,8 +374,8 @@ int gch_ellipsoid_axes(const double* coords, int n, const double* masses, double
 
 int gch_conc_mol_rdf(const char* dcd_path, const double* coords0, int natoms, const char* const* molnames, const int* molids,
                      const char* const* chains, const double* masses, const int* refidx, int nref, const char* const* residues,
-                     int nres, int com, int cpus, double step, double end, int dev, int rank, int nranks, void* comm, double* rdf,
-                     double* cumulative, int* frames_read) {
+                     int nres, int com, int cpus, double step, double end, long window_frames, int dev, int rank, int nranks, void* comm,
+                     double* rdf, double* cumulative, int* frames_read) {
     chem::Molecule mol;
     mol.Atoms.resize((size_t)natoms);
     for (int i = 0; i < natoms; i++) {
@@ -393,6 +393,7 @@ int gch_conc_mol_rdf(const char* dcd_path, const double* coords0, int natoms, co
     o->Step(&step);
     o->End(&end);
     o->DeviceID(&dev);
+    o->StreamWindow(&window_frames);
     o->Shard(rank, nranks, static_cast<gcb_comm*>(comm));
     std::unique_ptr<chem::ConcTraj> traj;
     if (Error e = align::opentraj(dcd_path, &traj)) return fail(e);

@@ -1143,8 +1143,8 @@ Error RMSDTraj(const chem::Atomer& mol, const v3::Matrix& ref, chem::ConcTraj& t
 // Streams the frames RMSDTraj selects (chunks of o.cpus, begin / skip, dropped tail: lovo.go:306-326) through a device
 // window.  Windows (whole chunks, at most `per` frames) are dealt to the ranks in turn; a rank reads and discards the
 // windows of the others.  process(handle, first, n) runs for window k while the reader already fills window k + 1.
-static Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
-                            const std::function<Error(gcb_traj*, long, long)>& process, long* nselected, long* nlocal) {
+Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
+                     const std::function<Error(gcb_traj*, long, long)>& process, long* nselected, long* nlocal) {
     if (!traj.Readable()) return Error("Traj object uninitialized to read", {"RMSDTraj"});
     if (o.cpus_ <= 0) return Error("align.RMSDTraj: cpus must be positive");
     if (traj.Len() != natoms) return Error("align.RMSDTraj: trajectory and molecule differ in the number of atoms");
@@ -1554,8 +1554,6 @@ Error ConcMolRDF(chem::ConcTraj& traj, const chem::Molecule& mol, const std::vec
     ao.device_ = o->device_;
     ao.rank_ = o->rank_;
     ao.nranks_ = o->nranks_;
-    std::unique_ptr<align::DeviceTrajectory> d;
-    if (Error e = align::DeviceTrajectory::Load(traj, natoms, ao, &d)) return errDecorate(e, "ConcMolRDF");
     std::vector<int> molid((size_t)natoms), chain((size_t)natoms);
     std::vector<unsigned char> flags((size_t)natoms);
     std::map<std::string, int> chain_ids;
@@ -1572,9 +1570,32 @@ Error ConcMolRDF(chem::ConcTraj& traj, const chem::Molecule& mol, const std::vec
     const int totalsteps = (int)(o->end_ / o->step_);
     std::vector<double> ret((size_t)(totalsteps > 0 ? totalsteps : 0), 0.0);
     long read = 0;
-    int rc = gcb_rdf_cdf_sum(d->Handle(), 0, d->LocalFrames(), molid.data(), chain.data(), flags.data(), refindexes.data(),
-                             (int)refindexes.size(), o->com_ ? 1 : 0, o->step_, o->end_, 1, o->comm_, ret.data(), &read);
-    if (rc) return deviceError(rc, "ConcMolRDF");
+    if (o->stream_ > 0) {
+        // bounded memory: the counts of every window are integers and simply add up; the ranks' totals are combined at the end
+        ao.stream_ = o->stream_;
+        std::vector<double> part(ret.size());
+        auto process = [&](gcb_traj* t, long first, long n) -> Error {
+            long r = 0;
+            int rc = gcb_rdf_cdf_sum(t, first, n, molid.data(), chain.data(), flags.data(), refindexes.data(), (int)refindexes.size(),
+                                     o->com_ ? 1 : 0, o->step_, o->end_, 1, nullptr, part.data(), &r);
+            if (rc) return deviceError(rc, "ConcMolRDF");
+            for (size_t k = 0; k < ret.size(); k++) ret[k] += part[k];
+            return Error();
+        };
+        long nsel = 0, nlocal = 0;
+        if (Error e = align::streamSelected(traj, natoms, ao, process, &nsel, &nlocal)) return errDecorate(e, "ConcMolRDF");
+        read = nsel;
+        if (o->comm_) {
+            int rc = gcb_allreduce_sum_f64(o->comm_, ret.data(), (long)ret.size());
+            if (rc) return deviceError(rc, "ConcMolRDF");
+        }
+    } else {
+        std::unique_ptr<align::DeviceTrajectory> d;
+        if (Error e = align::DeviceTrajectory::Load(traj, natoms, ao, &d)) return errDecorate(e, "ConcMolRDF");
+        int rc = gcb_rdf_cdf_sum(d->Handle(), 0, d->LocalFrames(), molid.data(), chain.data(), flags.data(), refindexes.data(),
+                                 (int)refindexes.size(), o->com_ ? 1 : 0, o->step_, o->end_, 1, o->comm_, ret.data(), &read);
+        if (rc) return deviceError(rc, "ConcMolRDF");
+    }
     if (frames_read) *frames_read = (int)read;
     if (Error e = MDFFromCDF(ret, (int)read, A, B, o->step_, cumulative)) return e;
     *rdf = std::move(ret);

@@ -248,7 +248,10 @@ class Options {
     // additions for the device path
     int DeviceID(const int* d = nullptr) { if (d && *d >= 0) device_ = *d; return device_; }
     void Shard(int rank, int nranks, gcb_comm* comm) { rank_ = rank; nranks_ = nranks; comm_ = comm; }
+    // frames per device window when the trajectory is streamed instead of made resident (0 = resident)
+    long StreamWindow(const long* frames = nullptr) { if (frames && *frames >= 0) stream_ = *frames; return stream_; }
 
+    long stream_ = 0;
     bool com_ = false;
     int cpus_ = 1;
     double step_ = 0.1, end_ = 10.0;
@@ -397,6 +400,9 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
 Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_ptr<DeviceTrajectory>& d, LOVOReturn* out, Options* o,
                    const std::function<Error()>& reload = nullptr);
 Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out);  // lovo.go:152-172
+// The frames RMSDTraj selects, streamed through a device window; process(handle, first, n) sees every window of this rank.
+Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o, const std::function<Error(gcb_traj*, long, long)>& process,
+                     long* nselected, long* nlocal);
 
 }  // namespace align
 }  // namespace gochem

@@ -277,7 +277,7 @@ def _cstrings(items):
 
 
 def ConcMolRDF(dcd_path, coords0, molnames, molids, chains, masses, refindexes, residues, com=False, cpus=1, step=0.1, end=10.0,
-               dev=0, rank=0, nranks=1, comm=None):
+               dev=0, rank=0, nranks=1, comm=None, window_frames=0):
     """solv.ConcMolRDF (solvation.go:140-218) on a DCD file -> (rdf, cumulative, frames read)."""
     c0 = np.ascontiguousarray(coords0, dtype=np.float64)
     n = c0.shape[0]
@@ -289,7 +289,7 @@ def ConcMolRDF(dcd_path, coords0, molnames, molids, chains, masses, refindexes, 
     fr = C.c_int(0)
     rc = load().gch_conc_mol_rdf(dcd_path.encode(), _d(c0), n, _cstrings(list(molnames)), _i(ids), _cstrings(list(chains)), _d(ms),
                                  _i(ref), ref.size, _cstrings(list(residues)), len(residues), int(com), int(cpus), C.c_double(step),
-                                 C.c_double(end), dev, rank, nranks, comm, _d(rdf), _d(cum), C.byref(fr))
+                                 C.c_double(end), C.c_long(window_frames), dev, rank, nranks, comm, _d(rdf), _d(cum), C.byref(fr))
     if rc:
         raise _err(rc)
     return rdf, cum, fr.value

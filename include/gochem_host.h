@@ -84,13 +84,14 @@ int gch_lovo_resident(void *traj_handle, long nlocal, long nselected_total, cons
 
 /* solv (solv/solvation.go): MDFFromCDF (:317-352), EllipsoidAxes (:39-63; masses NULL = unit masses), and ConcMolRDF
  * (:140-218) on a DCD file.  Topology: molnames / chains (natoms C strings), molids, masses (0 = unknown -> error, as
- * Topology.Masses); coords0 = mol.Coords[0].  rdf / cumulative: (int)(end / step) doubles each.  comm may be NULL. */
+ * Topology.Masses); coords0 = mol.Coords[0].  rdf / cumulative: (int)(end / step) doubles each.  window_frames > 0 streams
+ * the file through a device window instead of making it resident.  comm may be NULL. */
 int gch_mdf_from_cdf(double *ret, int n, int framesread, double A, double B, double step, double *ret2);
 int gch_ellipsoid_axes(const double *coords, int n, const double *masses, double *rhos3);
 int gch_conc_mol_rdf(const char *dcd_path, const double *coords0, int natoms, const char *const *molnames, const int *molids,
                      const char *const *chains, const double *masses, const int *refidx, int nref, const char *const *residues,
-                     int nres, int com, int cpus, double step, double end, int dev, int rank, int nranks, void *comm,
-                     double *rdf, double *cumulative, int *frames_read);
+                     int nres, int com, int cpus, double step, double end, long window_frames, int dev, int rank, int nranks,
+                     void *comm, double *rdf, double *cumulative, int *frames_read);
 
 #ifdef __cplusplus
 }

@@ -191,6 +191,37 @@ def test_pinned_async_upload():
     t.close()
 
 
+def test_upload_of_raw_records():
+    """gcb_traj_upload_records_async: float32 planes inside fixed-size records (raw DCD frames: markers, a unit-cell block, a
+    trailing block), picked apart on the device; bad layouts are argument errors."""
+    natoms, nframes = 77, 9
+    ref, frames = synth.make_case(natoms, nframes, through_f32=True)
+    plane = 4 * natoms
+    off = (4 + 48 + 4 + 4, 0, 0)
+    off = (off[0], off[0] + plane + 8, off[0] + 2 * (plane + 8))
+    rec = off[2] + plane + 4 + (4 + plane + 4)
+    pb = _lib.PinnedBuffer(rec * nframes)
+    pb.u8[:] = 0xAB                                   # whatever sits between the planes must not matter
+    f32 = frames.astype(np.float32)
+    for f in range(nframes):
+        for c in range(3):
+            pb.u8[f * rec + off[c]: f * rec + off[c] + plane] = f32[f, :, c].copy().view(np.uint8)
+    t = _lib.DeviceTraj(natoms, nframes + 3)
+    lib = _lib.load()
+    _lib.check(lib.gcb_traj_upload_records_async(t.h, 3, pb.ptr, nframes, rec, off[0], off[1], off[2], 1.0, 1))
+    t.wait(1)
+    assert lib.gcb_traj_stage_bytes(t.h) >= 64 << 20
+    back = t.download(3, nframes)
+    assert np.array_equal(back, frames)
+    _lib.check(lib.gcb_traj_upload_records_async(t.h, 0, pb.ptr, 2, rec, off[0], off[1], off[2], 10.0, 0))   # the xtc-style scale
+    t.wait(0)
+    assert np.array_equal(t.download(0, 2), 10.0 * frames[:2])
+    for bad in [(rec, off[0] + 2, off[1], off[2]), (rec, off[0], off[1], rec - 8), (0, 0, 0, 0), (rec + 2, off[0], off[1], off[2])]:
+        assert lib.gcb_traj_upload_records_async(t.h, 0, pb.ptr, 1, bad[0], bad[1], bad[2], bad[3], 1.0, 0) == _lib.ERR_ARG
+    pb.free()
+    t.close()
+
+
 def test_peratom_dev_sum_matches_rmsdtraj(variant):
     ref, frames = synth.make_case(333, 24)
     idx = np.arange(0, 333, 2)

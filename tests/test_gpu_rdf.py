@@ -114,6 +114,9 @@ def test_conc_mol_rdf_host_mirror_on_a_dcd(tmp_path):
     assert np.abs(rdf - want_rdf).max() <= 1e-10 * np.abs(want_rdf).max()
     rho = H.EllipsoidAxes(frames[0][refidx], masses[refidx])
     assert np.abs(rho - ev).max() < 1e-9 * ev[0]
+    # the same file streamed through a device window of a few frames: identical counts, identical result
+    rdf_s, cum_s, read_s = H.ConcMolRDF(path, frames[0], names, molid, chains, masses, refidx, ["SOL", "NA"], cpus=cpus, window_frames=8)
+    assert read_s == read and np.array_equal(cum_s, cum) and np.array_equal(rdf_s, rdf)
     # missing masses are an error, as Topology.Masses reports (chem.go:291-301)
     with pytest.raises(H.GoChemError):
         H.ConcMolRDF(path, frames[0], names, molid, chains, None, refidx, ["SOL"], cpus=cpus)
