@@ -569,8 +569,10 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         set_error("cluster kernel requested but not available for %d atoms", t->natoms);
         return GCB_ERR_ARG;
     }
+    // structures of at most 512 atoms: every warp owns frames (super_small.cu); the explicit variants keep their meaning
+    const bool small = g_variant == GCB_KERNEL_AUTO && small_kernel_supported(t) && !(mode == MODE_WEIGHTED && t->cache.repeated);
     if (want_dev) {
-        const size_t rows = (size_t)t->sm_count * 8;
+        const size_t rows = small ? (size_t)small_kernel_rows(t) : (size_t)t->sm_count * 8;
         rc = ensure_devpart(t, rows);
         if (rc) return rc;
         GCB_CUDA(cudaMemsetAsync(t->d_devpart, 0, sizeof(double) * rows * (size_t)t->np, t->stream));
@@ -578,8 +580,9 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         p.rmsd = nullptr;   // align.RMSDTraj (align/lovo.go:286-353) never looks at the per-frame RMSD
     }
     int rows_used = 0;
-    rc = cluster ? launch_super_cluster(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used)
-                 : launch_super_generic(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used);
+    rc = small ? launch_super_small(t, p, mode == MODE_WEIGHTED, want_dev, force_explicit_mode(), &rows_used)
+         : cluster ? launch_super_cluster(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used)
+                   : launch_super_generic(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used);
     if (dev_rows) *dev_rows = rows_used;
     return rc;
 }

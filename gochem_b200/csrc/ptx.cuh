@@ -79,5 +79,37 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 
+__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// 12 per-lane values -> warp totals with 15 shuffles (halving butterfly).  On return, lanes with
+// (lane & 3) == 0 hold: t0 = total of value 6*b4 + 3*b3 + 2*b2, t1 = total of value 6*b4 + 3*b3 + 1,
+// where b4, b3, b2 are lane bits 4, 3, 2.  Fixed tree -> deterministic.
+__device__ __forceinline__ void warp_reduce12(const double (&v)[12], int lane, double& t0, double& t1) {
+    double w[6], u[3];
+    const bool h16 = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const double send = h16 ? v[j] : v[j + 6];
+        const double keep = h16 ? v[j + 6] : v[j];
+        w[j] = keep + shx(send, 16);
+    }
+    const bool h8 = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const double send = h8 ? w[j] : w[j + 3];
+        const double keep = h8 ? w[j + 3] : w[j];
+        u[j] = keep + shx(send, 8);
+    }
+    const bool h4 = lane & 4;
+    {
+        const double send = h4 ? u[0] : u[2];
+        const double keep = h4 ? u[2] : u[0];
+        t0 = keep + shx(send, 4);
+        t1 = u[1] + shx(u[1], 4);
+    }
+    t0 += shx(t0, 2); t1 += shx(t1, 2);
+    t0 += shx(t0, 1); t1 += shx(t1, 1);
+}
+
 }  // namespace ptx
 }  // namespace gcb

@@ -67,38 +67,6 @@ struct ClusterParams {
 
 using namespace ptx;
 
-__device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-
-// 12 per-lane values -> warp totals with 15 shuffles (halving butterfly).  On return, lanes with
-// (lane & 3) == 0 hold: t0 = total of value 6*b4 + 3*b3 + 2*b2, t1 = total of value 6*b4 + 3*b3 + 1,
-// where b4, b3, b2 are lane bits 4, 3, 2.  Fixed tree -> deterministic.
-__device__ __forceinline__ void warp_reduce12(const double (&v)[12], int lane, double& t0, double& t1) {
-    double w[6], u[3];
-    const bool h16 = lane & 16;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-        const double send = h16 ? v[j] : v[j + 6];
-        const double keep = h16 ? v[j + 6] : v[j];
-        w[j] = keep + shx(send, 16);
-    }
-    const bool h8 = lane & 8;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const double send = h8 ? w[j] : w[j + 3];
-        const double keep = h8 ? w[j + 3] : w[j];
-        u[j] = keep + shx(send, 8);
-    }
-    const bool h4 = lane & 4;
-    {
-        const double send = h4 ? u[0] : u[2];
-        const double keep = h4 ? u[2] : u[0];
-        t0 = keep + shx(send, 4);
-        t1 = u[1] + shx(u[1], 4);
-    }
-    t0 += shx(t0, 2); t1 += shx(t1, 2);
-    t0 += shx(t0, 1); t1 += shx(t1, 1);
-}
-
 #ifdef GCB_TRACE
 __device__ long long g_trace[8][512];
 #define TRACE(row, j) do { if (blockIdx.x == 0 && (j) < 512) g_trace[row][j] = clock64(); } while (0)
@@ -620,6 +588,7 @@ extern "C" int gcb_trace_read(long long* out) {
 void get_last_plan(int* out8) { for (int i = 0; i < 8; i++) out8[i] = g_last_plan[i]; }
 
 void set_force_explicit(int on) { g_force_explicit = on; }
+int force_explicit_mode() { return g_force_explicit; }
 
 void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
     g_tune_cluster = cluster;

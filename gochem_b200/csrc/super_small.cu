@@ -1,0 +1,272 @@
+// super_small.cu -- the fused superposition + RMSD pass for small structures (at most 512 atoms per frame).
+//
+// Same arithmetic as super_cluster.cu (chem.Super -> RotatorTranslatorToSuper -> MemRMSD / MemPerAtomRMSD,
+// /root/reference/handy.go:175-214, geometric.go:127-208, :258-321).  A frame of a few hundred atoms is a few kilobytes:
+// with one frame per CTA at a time the per-frame costs that do not shrink with the frame -- the cross-warp reduction,
+// the hand-off to the solver, a 3x3 solve on one lane -- dominate (200 M frames/s whatever the size below ~500 atoms).
+// Here every WARP owns frames:
+//
+//  * a warp takes batches of 32 consecutive frames.  Sweep 1 walks the batch frame by frame: lane l holds atoms
+//    l, l+32, ... (K per lane, coalesced streaming loads, two frames in flight), the centred template comes from
+//    shared memory, and a shuffle butterfly leaves the frame's 13 sums in shared memory;
+//  * then the 32 lanes solve the 32 frames of the batch AT ONCE -- lane l runs the 3x3 solve of frame l
+//    (kabsch3.cuh), decides between the one-pass RMSD and the explicit residual exactly as the cluster kernel does, and
+//    writes R, the translations and the RMSD.  No lane idles through somebody else's solve;
+//  * sweep 2, only for the frames that need it (write-back, per-atom distances, explicit residual): the frames are
+//    read again (they were read microseconds ago: L2), rotated, written back / accumulated.
+//
+// Deterministic: every sum has a fixed order.  HBM-bound above ~300 atoms, instruction-bound below.
+#include "common.cuh"
+#include "kabsch3.cuh"
+#include "ptx.cuh"
+
+namespace gcb {
+
+namespace {
+using ptx::warp_reduce12;
+
+constexpr int kSmallWarps = 8;
+constexpr int kSmallThreads = 32 * kSmallWarps;
+constexpr int kSmallMaxAtoms = 512;
+
+__device__ __forceinline__ double shx2(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+struct SmallShared {
+    double sums[kSmallWarps][32][13];   // per frame of the batch: S (3), H (9), sum w|a|^2
+    double xf[kSmallWarps][32][13];     // R (9), centroid*R (3), [12] != 0: sweep 2 must form the explicit residual
+};
+
+// sqrt with a short dependency chain (see super_cluster.cu: cubic-order correction of the rsqrt seed)
+__device__ __forceinline__ double small_sqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y, h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    const double out = fma(g * r, fma(1.5, r, 1.0), g);
+    return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
+}
+
+template <int K, bool MASKED, bool DEV>
+__global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperParams p, int always_explicit, long nbatches) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
+    double* tb = reinterpret_cast<double*>(small_smem + sizeof(SmallShared));   // template planes bx | by | bz, 32*K each
+    constexpr int NP = 32 * K;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 3 * NP; i += kSmallThreads) {
+        const int c = i / NP, a = i - c * NP;
+        tb[i] = a < p.np ? p.refc[(long)c * p.np + a] : 0.0;
+    }
+    uint32_t real_mask = 0, fit_mask = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int a = lane + 32 * k;
+        if (a < p.natoms) {
+            real_mask |= 1u << k;
+            if (!MASKED || p.weight[a] != 0.0) fit_mask |= 1u << k;
+        }
+    }
+    __syncthreads();
+    const double* bx = tb + lane;
+    const double* by = bx + NP;
+    const double* bz = by + NP;
+    double dev[DEV ? K : 1];
+#pragma unroll
+    for (int k = 0; k < (DEV ? K : 1); k++) dev[k] = 0.0;
+    const bool wb = p.frames_rw != nullptr;
+    const bool sweep2_all = always_explicit || wb || DEV;
+    const long gwarp = (long)blockIdx.x * kSmallWarps + warp, nwarps = (long)gridDim.x * kSmallWarps;
+
+    for (long b = gwarp; b < nbatches; b += nwarps) {
+        const long f0 = b * 32;
+        const int nf = (int)((p.nframes - f0 < 32) ? (p.nframes - f0) : 32);
+        // ---------------- sweep 1: the 13 sums of every frame of the batch ----------------
+        double x[K], y[K], z[K];
+        auto load = [&](int i, auto& lx, auto& ly, auto& lz) {
+            const double* fr = p.frames + (f0 + i) * p.frame_stride + lane;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const bool in = lane + 32 * k < p.np;   // planes are padded to 16: the padding atoms read as zeros
+                lx[k] = in ? __ldcs(fr + 32 * k) : 0.0;
+                ly[k] = in ? __ldcs(fr + p.np + 32 * k) : 0.0;
+                lz[k] = in ? __ldcs(fr + 2L * p.np + 32 * k) : 0.0;
+            }
+        };
+        constexpr bool PF = K <= 8;   // two frames in flight while the registers allow it
+        constexpr int KN = PF ? K : 1;
+        if (PF) load(0, x, y, z);
+        for (int i = 0; i < nf; i++) {
+            double nx[KN], ny[KN], nz[KN];
+            if constexpr (PF) {
+                if (i + 1 < nf) load(i + 1, nx, ny, nz);   // the next frame is in flight while this one is reduced
+            } else {
+                load(i, x, y, z);
+            }
+            double acc[12], aa = 0.0;
+#pragma unroll
+            for (int q = 0; q < 12; q++) acc[q] = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                double ax = x[k], ay = y[k], az = z[k];
+                if (MASKED) {
+                    const bool on = (fit_mask >> k) & 1u;
+                    ax = on ? ax : 0.0; ay = on ? ay : 0.0; az = on ? az : 0.0;
+                }
+                const double tx = bx[32 * k], ty = by[32 * k], tz = bz[32 * k];
+                aa = fma(az, az, fma(ay, ay, fma(ax, ax, aa)));
+                acc[0] += ax; acc[1] += ay; acc[2] += az;
+                acc[3] = fma(ax, tx, acc[3]); acc[4] = fma(ax, ty, acc[4]); acc[5] = fma(ax, tz, acc[5]);
+                acc[6] = fma(ay, tx, acc[6]); acc[7] = fma(ay, ty, acc[7]); acc[8] = fma(ay, tz, acc[8]);
+                acc[9] = fma(az, tx, acc[9]); acc[10] = fma(az, ty, acc[10]); acc[11] = fma(az, tz, acc[11]);
+            }
+            // halving butterfly (15 shuffles for the 12 sums, 5 for sum |a|^2), fixed order
+            double t0, t1;
+            warp_reduce12(acc, lane, t0, t1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) aa += shx2(aa, o);
+            double* sm = sh.sums[warp][i];
+            if (lane == 0) sm[12] = aa;
+            if ((lane & 3) == 0) {
+                const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+                sm[6 * b4 + 3 * b3 + 2 * b2] = t0;
+                if (b2 == 0) sm[6 * b4 + 3 * b3 + 1] = t1;
+            }
+            if constexpr (PF) {
+                if (i + 1 < nf) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) { x[k] = nx[k]; y[k] = ny[k]; z[k] = nz[k]; }
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- the 32 solves of the batch, one per lane ----------------
+        bool any_sweep2 = sweep2_all;
+        if (lane < nf) {
+            const long f = f0 + lane;
+            const double* s = sh.sums[warp][lane];
+            const double cen[3] = {s[0] * p.inv_n, s[1] * p.inv_n, s[2] * p.inv_n};
+            double h[9], r[9];
+            bool finite = true;
+#pragma unroll
+            for (int k = 0; k < 9; k++) { h[k] = s[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
+            int rc = finite ? k3::kabsch3(h, r) : -4;
+            if (rc != 0) {
+                if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
+#pragma unroll
+                for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+            }
+            double* xf = sh.xf[warp][lane];
+#pragma unroll
+            for (int k = 0; k < 9; k++) xf[k] = r[k];
+            xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
+            xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
+            xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
+            // one-pass RMSD when its rounding bound allows, explicit residual otherwise: same rule as super_cluster.cu
+            const double ga = s[12] - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * p.inv_n;
+            const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
+                                fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
+            const double e = ga + p.gb - 2.0 * trrh;
+            const double smax = s[12] + p.gb;
+            const bool formula_ok = !sweep2_all && rc == 0 && e > 0.0 &&
+                                    (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
+            xf[12] = formula_ok ? 0.0 : 1.0;
+            if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
+            if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
+            if (p.rot) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
+            }
+            if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
+            if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+            any_sweep2 = any_sweep2 || !formula_ok;
+        }
+        any_sweep2 = __any_sync(0xffffffffu, any_sweep2);
+        __syncwarp();
+        if (!any_sweep2) continue;
+        // ---------------- sweep 2: rotate, explicit residual, per-atom distances, write-back ----------------
+        for (int i = 0; i < nf; i++) {
+            const double* xf = sh.xf[warp][i];
+            if (!sweep2_all && xf[12] == 0.0) continue;   // warp-uniform
+            const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
+            const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
+            const long fo = (f0 + i) * p.frame_stride + lane;
+            double e = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (lane + 32 * k >= p.np) continue;
+                const double ax = p.frames[fo + 32 * k], ay = p.frames[fo + p.np + 32 * k], az = p.frames[fo + 2L * p.np + 32 * k];
+                const double qx = fma(az, r6, fma(ay, r3, fma(ax, r0, g0)));
+                const double qy = fma(az, r7, fma(ay, r4, fma(ax, r1, g1)));
+                const double qz = fma(az, r8, fma(ay, r5, fma(ax, r2, g2)));
+                const double dx = qx - bx[32 * k], dy = qy - by[32 * k], dz = qz - bz[32 * k];
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if ((fit_mask >> k) & 1u) e += d2;
+                if (DEV) dev[k] += small_sqrt(d2);
+                if (wb && ((real_mask >> k) & 1u)) {
+                    p.frames_rw[fo + 32 * k] = qx + p.bbar[0];
+                    p.frames_rw[fo + p.np + 32 * k] = qy + p.bbar[1];
+                    p.frames_rw[fo + 2L * p.np + 32 * k] = qz + p.bbar[2];
+                }
+            }
+            if (p.rmsd) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) e += shx2(e, o);
+                if (lane == 0) p.rmsd[f0 + i] = sqrt(e * p.inv_n);
+            }
+        }
+        __syncwarp();
+    }
+    if (DEV) {
+        double* row = p.devpart + gwarp * (long)p.np;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < p.np) row[lane + 32 * k] = dev[k];
+    }
+}
+
+template <int K>
+int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int grid, long nbatches, size_t smem) {
+#define GCB_SMALL_LAUNCH(M, D)                                                                                   \
+    do {                                                                                                         \
+        GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<K, M, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        super_small_kernel<K, M, D><<<grid, kSmallThreads, smem, t->stream>>>(p, always_explicit, nbatches);        \
+    } while (0)
+    if (masked) { if (want_dev) GCB_SMALL_LAUNCH(true, true); else GCB_SMALL_LAUNCH(true, false); }
+    else { if (want_dev) GCB_SMALL_LAUNCH(false, true); else GCB_SMALL_LAUNCH(false, false); }
+#undef GCB_SMALL_LAUNCH
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
+}  // namespace
+
+bool small_kernel_supported(const gcb_traj* t) { return t->np <= kSmallMaxAtoms; }
+
+// rows of the per-atom distance partials this kernel writes (one per warp of the grid)
+int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 3 * kSmallWarps; }
+
+int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out) {
+    const int k_needed = (t->np + 31) / 32;
+    const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
+    const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
+    const long nbatches = (p.nframes + 31) / 32;
+    long grid = (long)t->sm_count * 3;   // 3 CTAs of 8 warps per SM (67 KB of shared memory each)
+    const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    const int always = (force_explicit || want_dev || p.frames_rw != nullptr) ? 1 : 0;
+    if (want_dev) GCB_CUDA(cudaMemsetAsync(p.devpart, 0, sizeof(double) * (size_t)small_kernel_rows(t) * (size_t)t->np, t->stream));
+    int rc;
+    switch (K) {
+        case 1: rc = launch_small_k<1>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+        case 2: rc = launch_small_k<2>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+        case 4: rc = launch_small_k<4>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+        case 8: rc = launch_small_k<8>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+        default: rc = launch_small_k<16>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+    }
+    if (rows_out) *rows_out = (int)grid * kSmallWarps;
+    return rc;
+}
+
+}  // namespace gcb

@@ -191,6 +191,44 @@ def test_pinned_async_upload():
     t.close()
 
 
+@pytest.mark.parametrize("natoms", [3, 33, 100, 257, 512])
+def test_small_structure_kernel(natoms):
+    """Structures of at most 512 atoms take the warp-per-frame kernel under KERNEL_AUTO: every mode against the oracle, with a
+    frame count that is not a multiple of the 32-frame batches and a near-template frame that needs the explicit residual."""
+    lib = _lib.load()
+    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    nframes = 75
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
+    frames[40] = frames[0] + 1e-6                      # almost the template: the one-pass RMSD is not allowed here
+    t = device_traj(frames)
+    out = t.super_rmsd(ref)
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None)
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
+    if natoms >= 33:
+        assert np.abs(out["rot"] - rot).max() < TOL_ROT
+    assert np.abs(out["trans1"] - t1).max() < TOL_XYZ and np.abs(out["trans2"] - t2).max() < TOL_XYZ
+    if natoms >= 33:
+        idx = np.arange(1, natoms, 3)
+        sub = t.super_rmsd(ref, idx, idx)
+        rm_s, rot_s, _, _ = oracle.super_rmsd_traj(frames, ref, idx)
+        assert np.abs(sub["rmsd"] - rm_s).max() < TOL_RMSD and np.abs(sub["rot"] - rot_s).max() < TOL_ROT
+        dev = t.peratom_dev_sum(ref, idx, write_back=True)
+        want, total, aligned = oracle.rmsd_traj(frames, ref, idx, cpus=5, want_aligned=True)
+        assert total == nframes and np.abs(dev / nframes - want).max() < 1e-10
+        assert np.abs(t.download() - aligned).max() < TOL_XYZ
+        t.upload(frames)
+    _lib.check(lib.gcb_set_rmsd_mode(1))               # explicit residual for every frame
+    try:
+        ex = t.super_rmsd(ref, write_back=True)
+    finally:
+        lib.gcb_set_rmsd_mode(0)
+    assert np.abs(ex["rmsd"] - rm).max() < TOL_RMSD
+    moved = t.download()
+    for f in (0, 31, 32, 74):
+        assert np.abs(moved[f] - oracle.super_(frames[f], ref)).max() < TOL_XYZ
+    t.close()
+
+
 def test_upload_of_raw_records():
     """gcb_traj_upload_records_async: float32 planes inside fixed-size records (raw DCD frames: markers, a unit-cell block, a
     trailing block), picked apart on the device; bad layouts are argument errors."""
