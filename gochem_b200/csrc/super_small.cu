@@ -46,6 +46,45 @@ __device__ __forceinline__ double small_sqrt(double x) {
     return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
 }
 
+// The 3x3 problem of one frame from its 13 sums (one lane per frame): rotation, centroid, the one-pass RMSD when its
+// rounding bound allows (same rule as super_cluster.cu) and the per-frame outputs.  Returns true when sweep 2 must form the
+// explicit residual for this frame.
+__device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* s, double* xf, long f, bool sweep2_all) {
+    const double cen[3] = {s[0] * p.inv_n, s[1] * p.inv_n, s[2] * p.inv_n};
+    double h[9], r[9];
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { h[k] = s[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
+    int rc = finite ? k3::kabsch3(h, r) : -4;
+    if (rc != 0) {
+        if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
+#pragma unroll
+        for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) xf[k] = r[k];
+    xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
+    xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
+    xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
+    const double ga = s[12] - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * p.inv_n;
+    const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
+                        fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
+    const double e = ga + p.gb - 2.0 * trrh;
+    const double smax = s[12] + p.gb;
+    const bool formula_ok = !sweep2_all && rc == 0 && e > 0.0 &&
+                            (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
+    xf[12] = formula_ok ? 0.0 : 1.0;
+    if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
+    if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
+    if (p.rot) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
+    }
+    if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
+    if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+    return !formula_ok;
+}
+
 template <int K, bool MASKED, bool DEV>
 __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperParams p, int always_explicit, long nbatches) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -141,45 +180,7 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
         __syncwarp();
         // ---------------- the 32 solves of the batch, one per lane ----------------
         bool any_sweep2 = sweep2_all;
-        if (lane < nf) {
-            const long f = f0 + lane;
-            const double* s = sh.sums[warp][lane];
-            const double cen[3] = {s[0] * p.inv_n, s[1] * p.inv_n, s[2] * p.inv_n};
-            double h[9], r[9];
-            bool finite = true;
-#pragma unroll
-            for (int k = 0; k < 9; k++) { h[k] = s[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
-            int rc = finite ? k3::kabsch3(h, r) : -4;
-            if (rc != 0) {
-                if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
-#pragma unroll
-                for (int k = 0; k < 9; k++) r[k] = (k % 4 == 0) ? 1.0 : 0.0;
-            }
-            double* xf = sh.xf[warp][lane];
-#pragma unroll
-            for (int k = 0; k < 9; k++) xf[k] = r[k];
-            xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
-            xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
-            xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
-            // one-pass RMSD when its rounding bound allows, explicit residual otherwise: same rule as super_cluster.cu
-            const double ga = s[12] - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * p.inv_n;
-            const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
-                                fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
-            const double e = ga + p.gb - 2.0 * trrh;
-            const double smax = s[12] + p.gb;
-            const bool formula_ok = !sweep2_all && rc == 0 && e > 0.0 &&
-                                    (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
-            xf[12] = formula_ok ? 0.0 : 1.0;
-            if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
-            if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
-            if (p.rot) {
-#pragma unroll
-                for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
-            }
-            if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
-            if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
-            any_sweep2 = any_sweep2 || !formula_ok;
-        }
+        if (lane < nf) any_sweep2 = solve_lane(p, sh.sums[warp][lane], sh.xf[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
         any_sweep2 = __any_sync(0xffffffffu, any_sweep2);
         __syncwarp();
         if (!any_sweep2) continue;
@@ -224,6 +225,139 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
     }
 }
 
+
+// ---- 512 < atoms <= 2048: the same scheme with the frame walked in chunks of 128 atoms (4 per lane), the next chunk in
+// flight while the current one is accumulated.  Fit, subset fit, explicit residual and write-back; per-atom distance sums of
+// structures this size stay with the cluster kernel.
+constexpr int kMidChunk = 4;                 // atoms per lane per chunk
+constexpr int kMidMaxAtoms = 2048;
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
+    double* tb = reinterpret_cast<double*>(small_smem + sizeof(SmallShared));   // template planes, NP each
+    constexpr int CH = kMidChunk;
+    const int NP = 32 * CH * nch;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 3 * NP; i += kSmallThreads) {
+        const int c = i / NP, a = i - c * NP;
+        tb[i] = a < p.np ? p.refc[(long)c * p.np + a] : 0.0;
+    }
+    unsigned long long real_mask = 0, fit_mask = 0;   // bit c*CH + k: atom lane + 32*(c*CH + k)
+    for (int q = 0; q < CH * nch; q++) {
+        const int a = lane + 32 * q;
+        if (a < p.natoms) {
+            real_mask |= 1ull << q;
+            if (!MASKED || p.weight[a] != 0.0) fit_mask |= 1ull << q;
+        }
+    }
+    __syncthreads();
+    const double* bx = tb + lane;
+    const double* by = bx + NP;
+    const double* bz = by + NP;
+    const bool wb = p.frames_rw != nullptr;
+    const bool sweep2_all = always_explicit || wb;
+    const long gwarp = (long)blockIdx.x * kSmallWarps + warp, nwarps = (long)gridDim.x * kSmallWarps;
+    for (long b = gwarp; b < nbatches; b += nwarps) {
+        const long f0 = b * 32;
+        const int nf = (int)((p.nframes - f0 < 32) ? (p.nframes - f0) : 32);
+        double x[CH], y[CH], z[CH];
+        auto load = [&](int i, int c, double (&lx)[CH], double (&ly)[CH], double (&lz)[CH]) {
+            const double* fr = p.frames + (f0 + i) * p.frame_stride + lane + 32 * CH * c;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const bool in = lane + 32 * (CH * c + k) < p.np;
+                lx[k] = in ? __ldcs(fr + 32 * k) : 0.0;
+                ly[k] = in ? __ldcs(fr + p.np + 32 * k) : 0.0;
+                lz[k] = in ? __ldcs(fr + 2L * p.np + 32 * k) : 0.0;
+            }
+        };
+        load(0, 0, x, y, z);
+        for (int i = 0; i < nf; i++) {
+            double acc[12], aa = 0.0;
+#pragma unroll
+            for (int q = 0; q < 12; q++) acc[q] = 0.0;
+            for (int c = 0; c < nch; c++) {
+                double nx[CH], ny[CH], nz[CH];
+                const bool last = c + 1 == nch;
+                if (!last) load(i, c + 1, nx, ny, nz);
+                else if (i + 1 < nf) load(i + 1, 0, nx, ny, nz);
+                const uint32_t fm = (uint32_t)(fit_mask >> (CH * c));
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    double ax = x[k], ay = y[k], az = z[k];
+                    if (MASKED) {
+                        const bool on = (fm >> k) & 1u;
+                        ax = on ? ax : 0.0; ay = on ? ay : 0.0; az = on ? az : 0.0;
+                    }
+                    const int o = 32 * (CH * c + k);
+                    const double tx = bx[o], ty = by[o], tz = bz[o];
+                    aa = fma(az, az, fma(ay, ay, fma(ax, ax, aa)));
+                    acc[0] += ax; acc[1] += ay; acc[2] += az;
+                    acc[3] = fma(ax, tx, acc[3]); acc[4] = fma(ax, ty, acc[4]); acc[5] = fma(ax, tz, acc[5]);
+                    acc[6] = fma(ay, tx, acc[6]); acc[7] = fma(ay, ty, acc[7]); acc[8] = fma(ay, tz, acc[8]);
+                    acc[9] = fma(az, tx, acc[9]); acc[10] = fma(az, ty, acc[10]); acc[11] = fma(az, tz, acc[11]);
+                }
+                if (!last || i + 1 < nf) {
+#pragma unroll
+                    for (int k = 0; k < CH; k++) { x[k] = nx[k]; y[k] = ny[k]; z[k] = nz[k]; }
+                }
+            }
+            double t0, t1;
+            warp_reduce12(acc, lane, t0, t1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) aa += shx2(aa, o);
+            double* sm = sh.sums[warp][i];
+            if (lane == 0) sm[12] = aa;
+            if ((lane & 3) == 0) {
+                const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+                sm[6 * b4 + 3 * b3 + 2 * b2] = t0;
+                if (b2 == 0) sm[6 * b4 + 3 * b3 + 1] = t1;
+            }
+        }
+        __syncwarp();
+        bool any_sweep2 = sweep2_all;
+        if (lane < nf) any_sweep2 = solve_lane(p, sh.sums[warp][lane], sh.xf[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
+        any_sweep2 = __any_sync(0xffffffffu, any_sweep2);
+        __syncwarp();
+        if (!any_sweep2) continue;
+        for (int i = 0; i < nf; i++) {
+            const double* xf = sh.xf[warp][i];
+            if (!sweep2_all && xf[12] == 0.0) continue;   // warp-uniform
+            const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
+            const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
+            const long fo = (f0 + i) * p.frame_stride + lane;
+            double e = 0.0;
+            for (int c = 0; c < nch; c++) {
+                const uint32_t fm = (uint32_t)(fit_mask >> (CH * c)), rm = (uint32_t)(real_mask >> (CH * c));
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    const int o = 32 * (CH * c + k);
+                    if (lane + o >= p.np) continue;
+                    const double ax = p.frames[fo + o], ay = p.frames[fo + p.np + o], az = p.frames[fo + 2L * p.np + o];
+                    const double qx = fma(az, r6, fma(ay, r3, fma(ax, r0, g0)));
+                    const double qy = fma(az, r7, fma(ay, r4, fma(ax, r1, g1)));
+                    const double qz = fma(az, r8, fma(ay, r5, fma(ax, r2, g2)));
+                    const double dx = qx - bx[o], dy = qy - by[o], dz = qz - bz[o];
+                    if ((fm >> k) & 1u) e += fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (wb && ((rm >> k) & 1u)) {
+                        p.frames_rw[fo + o] = qx + p.bbar[0];
+                        p.frames_rw[fo + p.np + o] = qy + p.bbar[1];
+                        p.frames_rw[fo + 2L * p.np + o] = qz + p.bbar[2];
+                    }
+                }
+            }
+            if (p.rmsd) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) e += shx2(e, o);
+                if (lane == 0) p.rmsd[f0 + i] = sqrt(e * p.inv_n);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int K>
 int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int grid, long nbatches, size_t smem) {
 #define GCB_SMALL_LAUNCH(M, D)                                                                                   \
@@ -241,12 +375,33 @@ int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev
 
 }  // namespace
 
-bool small_kernel_supported(const gcb_traj* t) { return t->np <= kSmallMaxAtoms; }
+bool small_kernel_supported(const gcb_traj* t, bool want_dev) { return t->np <= (want_dev ? kSmallMaxAtoms : kMidMaxAtoms); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)
 int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 3 * kSmallWarps; }
 
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out) {
+    if (t->np > kSmallMaxAtoms) {   // chunked form
+        const int nch = (t->np + 32 * kMidChunk - 1) / (32 * kMidChunk);
+        const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
+        const long nbatches = (p.nframes + 31) / 32;
+        long grid = (long)t->sm_count * 2;
+        const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        const int always = (force_explicit || p.frames_rw != nullptr) ? 1 : 0;
+        if (masked) {
+            GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            super_mid_kernel<true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nbatches, nch);
+        } else {
+            GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            super_mid_kernel<false><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nbatches, nch);
+        }
+        GCB_LAUNCHED();
+        GCB_CUDA(cudaGetLastError());
+        if (rows_out) *rows_out = 0;
+        return GCB_OK;
+    }
     const int k_needed = (t->np + 31) / 32;
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;

@@ -191,10 +191,11 @@ def test_pinned_async_upload():
     t.close()
 
 
-@pytest.mark.parametrize("natoms", [3, 33, 100, 257, 512])
+@pytest.mark.parametrize("natoms", [3, 33, 100, 257, 512, 513, 1500, 2048])
 def test_small_structure_kernel(natoms):
-    """Structures of at most 512 atoms take the warp-per-frame kernel under KERNEL_AUTO: every mode against the oracle, with a
-    frame count that is not a multiple of the 32-frame batches and a near-template frame that needs the explicit residual."""
+    """Structures of at most 512 atoms take the warp-per-frame kernel under KERNEL_AUTO, up to 2048 atoms its chunked form (the
+    per-atom sums of those go to the cluster kernel): every mode against the oracle, with a frame count that is not a multiple of
+    the 32-frame batches and a near-template frame that needs the explicit residual."""
     lib = _lib.load()
     _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
     nframes = 75
