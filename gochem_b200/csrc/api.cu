@@ -570,7 +570,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
         return GCB_ERR_ARG;
     }
     // structures of at most 512 atoms: every warp owns frames (super_small.cu); the explicit variants keep their meaning
-    const bool small = g_variant == GCB_KERNEL_AUTO && small_kernel_supported(t, want_dev) && !(mode == MODE_WEIGHTED && t->cache.repeated);
+    const bool small = g_variant == GCB_KERNEL_AUTO && small_kernel_supported(t, want_dev || write_back != 0 || force_explicit_mode() != 0) && !(mode == MODE_WEIGHTED && t->cache.repeated);
     if (want_dev) {
         const size_t rows = small ? (size_t)small_kernel_rows(t) : (size_t)t->sm_count * 8;
         rc = ensure_devpart(t, rows);

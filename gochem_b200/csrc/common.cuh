@@ -139,7 +139,7 @@ void get_last_plan(int* out8);
 void set_force_explicit(int on);
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out);
 int force_explicit_mode();
-bool small_kernel_supported(const gcb_traj* t, bool want_dev);
+bool small_kernel_supported(const gcb_traj* t, bool heavy);
 int small_kernel_rows(const gcb_traj* t);
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out);
 }  // namespace gcb

@@ -185,24 +185,33 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
         __syncwarp();
         if (!any_sweep2) continue;
         // ---------------- sweep 2: rotate, explicit residual, per-atom distances, write-back ----------------
+        // (the frames were read microseconds ago: L2.  When every frame takes part the next one is in flight meanwhile.)
+        const bool pf2 = PF && sweep2_all;
+        if (pf2) load(0, x, y, z);
         for (int i = 0; i < nf; i++) {
             const double* xf = sh.xf[warp][i];
             if (!sweep2_all && xf[12] == 0.0) continue;   // warp-uniform
+            double nx[KN], ny[KN], nz[KN];
+            if constexpr (PF) {
+                if (pf2) { if (i + 1 < nf) load(i + 1, nx, ny, nz); }
+                else load(i, x, y, z);
+            } else {
+                load(i, x, y, z);
+            }
             const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
             const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
             const long fo = (f0 + i) * p.frame_stride + lane;
             double e = 0.0;
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                if (lane + 32 * k >= p.np) continue;
-                const double ax = p.frames[fo + 32 * k], ay = p.frames[fo + p.np + 32 * k], az = p.frames[fo + 2L * p.np + 32 * k];
+                const double ax = x[k], ay = y[k], az = z[k];
                 const double qx = fma(az, r6, fma(ay, r3, fma(ax, r0, g0)));
                 const double qy = fma(az, r7, fma(ay, r4, fma(ax, r1, g1)));
                 const double qz = fma(az, r8, fma(ay, r5, fma(ax, r2, g2)));
                 const double dx = qx - bx[32 * k], dy = qy - by[32 * k], dz = qz - bz[32 * k];
                 const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
                 if ((fit_mask >> k) & 1u) e += d2;
-                if (DEV) dev[k] += small_sqrt(d2);
+                if (DEV) { if (lane + 32 * k < p.np) dev[k] += small_sqrt(d2); }
                 if (wb && ((real_mask >> k) & 1u)) {
                     p.frames_rw[fo + 32 * k] = qx + p.bbar[0];
                     p.frames_rw[fo + p.np + 32 * k] = qy + p.bbar[1];
@@ -213,6 +222,12 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e += shx2(e, o);
                 if (lane == 0) p.rmsd[f0 + i] = sqrt(e * p.inv_n);
+            }
+            if constexpr (PF) {
+                if (pf2 && i + 1 < nf) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) { x[k] = nx[k]; y[k] = ny[k]; z[k] = nz[k]; }
+                }
             }
         }
         __syncwarp();
@@ -375,7 +390,11 @@ int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev
 
 }  // namespace
 
-bool small_kernel_supported(const gcb_traj* t, bool want_dev) { return t->np <= (want_dev ? kSmallMaxAtoms : kMidMaxAtoms); }
+// Measured on B200 (tools/small_sweep.py, profiles/r1_s3_small_sweep.jsonl): for fit-only passes the warp-per-frame kernels win
+// up to ~1250 atoms (6.1 vs 3.8 TB/s at 1000 atoms, 1.37 G vs 0.19 G frames/s at 100 atoms); passes whose second sweep touches
+// every frame (write-back, per-atom sums, explicit residual) only up to 256 atoms -- above that the cluster kernel's
+// shared-memory-resident second sweep is faster.
+bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? 256 : 1280); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)
 int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 3 * kSmallWarps; }
