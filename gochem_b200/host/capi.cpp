@@ -414,4 +414,40 @@ int gch_conc_mol_rdf(const char* dcd_path, const double* coords0, int natoms, co
     return 0;
 }
 
+
+int gch_xtc_available(void) { return xtc::XTCObj::Available() ? 1 : 0; }
+
+int gch_xtc_write(const char* path, const double* frames, long nframes, int natoms) {
+    return ret(xtc::XTCObj::WriteFile(path, frames, nframes, natoms));
+}
+
+int gch_xtc_read(const char* path, double* out, long cap, long* nframes, int* natoms, int use_raw) {
+    std::unique_ptr<xtc::XTCObj> x;
+    if (Error e = xtc::XTCObj::New(path, &x)) return fail(e);
+    *natoms = x->Len();
+    const size_t fsz = 3 * (size_t)x->Len();
+    long n = 0;
+    v3::Matrix m = v3::Matrix::Zeros(x->Len());
+    std::vector<float> raw(fsz);
+    for (;;) {
+        Error e;
+        if (use_raw) {
+            int layout = 0;
+            double scale = 0;
+            e = x->NextRaw(raw.data(), &layout, &scale);
+            if (!e) for (size_t i = 0; i < fsz; i++) m.data()[i] = scale * (double)raw[i];
+        } else {
+            e = x->Next(&m);
+        }
+        if (e) {
+            if (!e.last_frame) return fail(e);
+            break;
+        }
+        if (n < cap) memcpy(out + (size_t)n * fsz, m.data(), sizeof(double) * fsz);
+        n++;
+    }
+    *nframes = n;
+    return 0;
+}
+
 }  // extern "C"

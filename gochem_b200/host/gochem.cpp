@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <map>
@@ -1327,7 +1328,13 @@ Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out) {
         *out = std::move(d);
         return Error();
     }
-    if (ext == "xtc" || ext == "stf" || ext == "pdb")
+    if (ext == "xtc") {   // lovo.go:157-160
+        std::unique_ptr<xtc::XTCObj> x;
+        if (Error e = xtc::XTCObj::New(name, &x)) return e;
+        *out = std::move(x);
+        return Error();
+    }
+    if (ext == "stf" || ext == "pdb")
         return Error("Trajectory format '" + ext + "' is decoded by a third-party CPU codec that is outside this build (SURVEY.md §2); "
                      "feed its frames through a chem::ConcTraj and call align::RMSDTraj");
     return Error("Trajectory fromat not supported. Must have concurrent read support in goChem");  // lovo.go:168-169
@@ -1416,6 +1423,135 @@ Error LOVO(const chem::Atomer& mol, const v3::Matrix& ref, const std::string& tr
 }  // namespace align
 
 // =====================================================================================================================
+namespace xtc {
+
+namespace {
+struct XdrApi {
+    void* h = nullptr;
+    int (*read_xtc_natoms)(char*, int*) = nullptr;
+    void* (*xdrfile_open)(const char*, const char*) = nullptr;
+    int (*xdrfile_close)(void*) = nullptr;
+    int (*read_xtc)(void*, int, int*, float*, float (*)[3], float (*)[3], float*) = nullptr;
+    int (*write_xtc)(void*, int, int, float, float (*)[3], float (*)[3], float) = nullptr;
+    std::string why;
+};
+XdrApi* xdr() {
+    static XdrApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* env = getenv("GOCHEM_XDRFILE");
+        const char* names[] = {env, "libxdrfile.so", "libxdrfile.so.4", "libxdrfile.so.2.1.2"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.h) break;
+        }
+        if (!api.h) { api.why = "libxdrfile is not loadable (set GOCHEM_XDRFILE to its path)"; return; }
+        api.read_xtc_natoms = (decltype(api.read_xtc_natoms))dlsym(api.h, "read_xtc_natoms");
+        api.xdrfile_open = (decltype(api.xdrfile_open))dlsym(api.h, "xdrfile_open");
+        api.xdrfile_close = (decltype(api.xdrfile_close))dlsym(api.h, "xdrfile_close");
+        api.read_xtc = (decltype(api.read_xtc))dlsym(api.h, "read_xtc");
+        api.write_xtc = (decltype(api.write_xtc))dlsym(api.h, "write_xtc");
+        if (!api.read_xtc_natoms || !api.xdrfile_open || !api.xdrfile_close || !api.read_xtc) {
+            api.why = "libxdrfile lacks read_xtc / xdrfile_open";
+            dlclose(api.h);
+            api.h = nullptr;
+        }
+    });
+    return &api;
+}
+Error xtcError(const std::string& msg, const std::string& file, std::vector<std::string> deco) {
+    return Error(msg + (file.empty() ? "" : " (" + file + ")"), std::move(deco));
+}
+}  // namespace
+
+bool XTCObj::Available(std::string* why) {
+    XdrApi* a = xdr();
+    if (!a->h && why) *why = a->why;
+    return a->h != nullptr;
+}
+
+Error XTCObj::New(const std::string& filename, std::unique_ptr<XTCObj>* out) {
+    XdrApi* a = xdr();
+    if (!a->h) return xtcError("xtc: " + a->why + "; the XTC codec is a third-party CPU library", filename, {"initRead"});
+    std::unique_ptr<XTCObj> x(new XTCObj());
+    x->filename_ = filename;
+    std::vector<char> name(filename.begin(), filename.end());
+    name.push_back(0);
+    int natoms = 0;
+    a->read_xtc_natoms(name.data(), &natoms);
+    if (natoms == 0) return xtcError("Probem opening the file", filename, {"C.read_natoms", "initRead"});   // xtc.go:84-86
+    x->fp_ = a->xdrfile_open(name.data(), "r");
+    if (!x->fp_) return xtcError("Probem opening the file", filename, {"C.openfile", "initRead"});          // xtc.go:79-81
+    x->natoms_ = natoms;
+    x->coords_.assign(3 * (size_t)natoms, 0.0f);
+    x->readable_ = true;
+    *out = std::move(x);
+    return Error();
+}
+
+XTCObj::~XTCObj() { Close(); }
+
+void XTCObj::Close() {
+    if (fp_) xdr()->xdrfile_close(fp_);
+    fp_ = nullptr;
+    readable_ = false;
+}
+
+Error XTCObj::readInto(float* dst) {   // libgoxtc.c:87-104 get_coords
+    if (!readable_) return xtcError("Traj object uninitialized to read", filename_, {"Next"});
+    int step = 0;
+    float time = 0, prec = 0;
+    const int worked = xdr()->read_xtc(fp_, natoms_, &step, &time, reinterpret_cast<float (*)[3]>(box_),
+                                       reinterpret_cast<float (*)[3]>(dst ? dst : coords_.data()), &prec);
+    if (worked == 11) { Close(); return chem::newLastFrameError(filename_, "Next"); }   // xtc.go:114-117
+    if (worked != 0) { Close(); return xtcError("Error reading frame", filename_, {"Next"}); }
+    return Error();
+}
+
+Error XTCObj::Next(v3::Matrix* output, std::vector<double>* box) {
+    if (Error e = readInto(nullptr)) return e;
+    if (!output) return Error();
+    if (output->NVecs() < natoms_) throw v3::PanicMsg("Buffer v3.Matrix too small to hold trajectory frame");
+    for (int j = 0; j < natoms_; j++)
+        for (int k = 0; k < 3; k++) output->Set(j, k, 10 * (double)coords_[(size_t)(k + 3 * j)]);   // nm to Angstroms (xtc.go:129-134)
+    if (box && box->size() >= 9)
+        for (int k = 0; k < 9; k++) (*box)[(size_t)k] = 10 * (double)box_[k];
+    return Error();
+}
+
+Error XTCObj::NextConc(std::vector<v3::Matrix*>& frames) {
+    if (!readable_) return xtcError("Traj object uninitialized to read", filename_, {"NextConc"});
+    for (auto* slot : frames)
+        if (Error e = Next(slot)) return errDecorate(e, "NextConc");
+    return Error();
+}
+
+Error XTCObj::NextRaw(float* dst, int* layout, double* scale) {
+    *layout = GCB_F32_AOS;
+    *scale = 10.0;
+    return readInto(dst);
+}
+
+Error XTCObj::WriteFile(const std::string& filename, const double* frames, long nframes, int natoms) {
+    XdrApi* a = xdr();
+    if (!a->h || !a->write_xtc) return xtcError("xtc: libxdrfile (with write_xtc) is not loadable", filename, {"WriteFile"});
+    void* fp = a->xdrfile_open(filename.c_str(), "w");
+    if (!fp) return xtcError("cannot open for writing", filename, {"WriteFile"});
+    std::vector<float> x(3 * (size_t)natoms);
+    float box[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10};
+    Error err;
+    for (long f = 0; f < nframes && !err; f++) {
+        for (size_t i = 0; i < x.size(); i++) x[i] = (float)(frames[(size_t)f * x.size() + i] / 10.0);
+        if (a->write_xtc(fp, natoms, (int)f, (float)f, reinterpret_cast<float (*)[3]>(box), reinterpret_cast<float (*)[3]>(x.data()), 1000.0f) != 0)
+            err = xtcError("write_xtc failed", filename, {"WriteFile"});
+    }
+    a->xdrfile_close(fp);
+    return err;
+}
+
+}  // namespace xtc
+
 namespace chem {
 
 Error Topology::Masses(std::vector<double>* out) const {  // chem.go:291-301

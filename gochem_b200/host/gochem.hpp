@@ -235,6 +235,40 @@ class DCDWObj {
 
 }  // namespace dcd
 
+namespace xtc {
+
+// GROMACS XTC reader (traj/xtc/xtc.go) over libxdrfile, the third-party C codec the reference links (traj/xtc/xtc.go:30-38;
+// it ships as a binary there).  The library is bound with dlopen when the first file is opened (GOCHEM_XDRFILE names it,
+// otherwise libxdrfile.so); without it New() fails.  The codec stays on the CPU; what changes is where it writes: NextRaw
+// points it at the caller's (pinned) buffer and the x10 nm -> A, the widening and the transposition happen on the device
+// (GCB_F32_AOS with scale 10, traj/xtc/xtc.go:129-134).
+class XTCObj : public chem::Traj, public chem::ConcTraj {
+  public:
+    static Error New(const std::string& filename, std::unique_ptr<XTCObj>* out);   // xtc.go:62-103
+    ~XTCObj() override;
+    bool Readable() const override { return readable_; }
+    Error Next(v3::Matrix* output, std::vector<double>* box = nullptr) override;     // xtc.go:108-146
+    Error NextConc(std::vector<v3::Matrix*>& frames) override;                       // xtc.go:189-238
+    int Len() const override { return natoms_; }
+    void Close() override;                                                           // xtc.go:173-183
+    bool HasRawFeed() const override { return true; }
+    Error NextRaw(float* dst, int* layout, double* scale) override;                  // float32 xyz per atom, nanometres
+    static bool Available(std::string* why = nullptr);
+    // test helper: frames in Angstrom written as an .xtc with libxdrfile's own writer (precision 1000: 0.001 nm)
+    static Error WriteFile(const std::string& filename, const double* frames_aos_angstrom, long nframes, int natoms);
+
+  private:
+    Error readInto(float* dst);
+    std::string filename_;
+    void* fp_ = nullptr;
+    int natoms_ = 0;
+    bool readable_ = false;
+    std::vector<float> coords_;
+    float box_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+}  // namespace xtc
+
 namespace solv {
 
 // solv.Options (solv/solvation.go:65-138), same getter/setter idiom as the Go methods.

@@ -318,3 +318,24 @@ def LOVOStreamed(dcd_path, ref, cpus, window_frames, less_than_rmsd=1.0, minimum
     if rc:
         raise _err(rc)
     return dict(N=N.value, Natoms=nat[: N.value].copy(), RMSD=rm[: nr.value].copy(), FramesRead=fr.value, Iterations=it.value)
+
+
+# ---- traj/xtc over libxdrfile (the third-party codec the reference links; bound with dlopen, GOCHEM_XDRFILE names it) ----
+def xtc_available():
+    return bool(load().gch_xtc_available())
+
+
+def xtc_write(path, frames):
+    f = np.ascontiguousarray(frames, dtype=np.float64)
+    rc = load().gch_xtc_write(path.encode(), _d(f), C.c_long(f.shape[0]), f.shape[1])
+    if rc:
+        raise _err(rc)
+
+
+def xtc_read(path, cap_frames, natoms, raw=False):
+    out = np.zeros((cap_frames, natoms, 3))
+    nf, na = C.c_long(0), C.c_int(0)
+    rc = load().gch_xtc_read(path.encode(), _d(out), C.c_long(cap_frames), C.byref(nf), C.byref(na), int(raw))
+    if rc:
+        raise _err(rc)
+    return out[: min(nf.value, cap_frames)], nf.value, na.value

@@ -82,6 +82,13 @@ int gch_lovo_resident(void *traj_handle, long nlocal, long nselected_total, cons
                       double less_than_rmsd, int minimum_n, void *comm, int rank, int nranks, int *N, int *natoms_out,
                       double *rmsd_out, int *iterations);
 
+/* traj/xtc over libxdrfile (dlopen; GOCHEM_XDRFILE names the library).  gch_xtc_available: 1 when the codec could be loaded.
+ * gch_xtc_write: frames in Angstrom -> .xtc (libxdrfile's writer, precision 1000); gch_xtc_read: frames back in Angstrom through
+ * XTCObj.Next (use_raw = 0) or through the raw float32 feed widened and scaled by 10 on the host exactly as the device kernel does. */
+int gch_xtc_available(void);
+int gch_xtc_write(const char *path, const double *frames_aos, long nframes, int natoms);
+int gch_xtc_read(const char *path, double *out_aos, long cap_frames, long *nframes, int *natoms, int use_raw);
+
 /* solv (solv/solvation.go): MDFFromCDF (:317-352), EllipsoidAxes (:39-63; masses NULL = unit masses), and ConcMolRDF
  * (:140-218) on a DCD file.  Topology: molnames / chains (natoms C strings), molids, masses (0 = unknown -> error, as
  * Topology.Masses); coords0 = mol.Coords[0].  rdf / cumulative: (int)(end / step) doubles each.  window_frames > 0 streams

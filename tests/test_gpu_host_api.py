@@ -76,8 +76,11 @@ def test_rmsdtraj_on_a_dcd_file(tmp_path):
     back, nf, na = H.dcd_read(out, 30, 256)
     assert nf == total == 20
     assert np.abs(back - aligned.astype(np.float32)).max() < 1e-4
-    with pytest.raises(H.GoChemError, match="not supported|outside this build"):
+    # no such file (or no libxdrfile on this host): an error, as opentraj reports it (lovo.go:157-160)
+    with pytest.raises(H.GoChemError, match="libxdrfile|Probem opening"):
         H.RMSDTraj(str(tmp_path / "x.xtc"), ref, idx, 4)
+    with pytest.raises(H.GoChemError, match="not supported|outside this build"):
+        H.RMSDTraj(str(tmp_path / "x.stf"), ref, idx, 4)
 
 
 def test_sharded_rmsdtraj_partials_add_up(tmp_path):
@@ -153,3 +156,20 @@ def test_lovo_larger_case_and_topology_filter(tmp_path):
     # happens depends on the data, so only check that asking for it does not change the answer
     got2 = H.LOVO(p, ref, cpus, names=names, chains=chains, molids=molids, write_traj=str(tmp_path / "al.dcd"))
     assert list(got2["Natoms"]) == list(want["Natoms"])
+
+
+def test_rmsdtraj_on_an_xtc_file(tmp_path):
+    """traj/xtc through libxdrfile (third-party codec, bound with dlopen): frames decoded straight into pinned memory as float32
+    nanometres, x10 / widened / transposed on the device.  Skipped where the codec library is not installed."""
+    if not H.xtc_available():
+        pytest.skip("libxdrfile is not installed on this host")
+    ref, frames = synth.make_case(200, 26, through_f32=True)
+    p = str(tmp_path / "traj.xtc")
+    H.xtc_write(p, frames)
+    decoded, nf, na = H.xtc_read(p, 40, 200)          # what the codec hands back (lossy: 0.001 nm)
+    assert (nf, na) == (26, 200) and np.abs(decoded - frames).max() < 0.006
+    idx = np.arange(0, 200, 2)
+    for cpus, window in [(4, 0), (3, 0), (4, 8)]:
+        got, n = (H.RMSDTrajStreamed(p, ref, idx, cpus, window) if window else H.RMSDTraj(p, ref, idx, cpus))
+        want, total = oracle.rmsd_traj(decoded, ref, idx, cpus)
+        assert n == total and np.abs(got - want).max() < 1e-9

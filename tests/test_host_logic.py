@@ -135,6 +135,25 @@ def test_dcd_round_trip(tmp_path):
     assert nf == 9 and np.array_equal(back, frames)
 
 
+def test_xtc_reader_over_libxdrfile(tmp_path):
+    """traj/xtc mirror: XTCObj.Next (x10, widened per element, xtc.go:129-134) and the raw float32 feed the device staging uses,
+    on a file written with the codec's own writer.  The codec is the third-party libxdrfile the reference links; skipped when
+    it cannot be loaded."""
+    if not H.xtc_available():
+        pytest.skip("libxdrfile is not installed on this host")
+    rng = np.random.default_rng(0)
+    frames = rng.normal(0, 15, (9, 61, 3))
+    p = str(tmp_path / "t.xtc")
+    H.xtc_write(p, frames)
+    a, nf, na = H.xtc_read(p, 20, 61)
+    assert (nf, na) == (9, 61)
+    assert np.abs(a - frames).max() < 0.006          # precision 1000 per nm: 0.01 A steps
+    b, nf2, _ = H.xtc_read(p, 20, 61, raw=True)
+    assert nf2 == 9 and np.array_equal(a, b)          # 10 * float64(float32) either way
+    with pytest.raises(H.GoChemError):
+        H.xtc_read(str(tmp_path / "missing.xtc"), 1, 1)
+
+
 def test_dcd_bulk_record_feed(tmp_path):
     """ConcTraj::NextRecords: whole runs of raw frames in one read, every window size, against the frame-by-frame reader; also on
     CHARMM files that carry a unit-cell record before every frame and a fourth-dimension record after it (dcd.go:361-376, 404-417)."""
