@@ -376,7 +376,7 @@ enum { MODE_ALL = 0, MODE_WEIGHTED = 1, MODE_GATHER = 2 };
 // keep it raw (no-fit RMSD), and make it resident.  Cached on content so back-to-back calls with the
 // same template and lists (bench loops, LOVO iterations that did not change the set) skip it.
 int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, const int* idx_test, const int* idx_ref,
-                     int nidx, bool centred, int* mode_out) {
+                     int nidx, bool centred, int* mode_out, bool prefer_gather = false) {
     if (!ref_aos) { set_error("NULL template"); return GCB_ERR_ARG; }
     if (nidx < 0) { set_error("negative index count"); return GCB_ERR_ARG; }
     const bool all = (idx_test == nullptr || nidx == 0);
@@ -409,6 +409,9 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
             }
         }
         mode = (same || paired) ? MODE_WEIGHTED : MODE_GATHER;
+        // a small subset of a large frame, frames left untouched: reading just those atoms (3 sectors each) beats streaming
+        // the whole frame
+        if (prefer_gather) mode = MODE_GATHER;
     }
     *mode_out = mode;
     gcb::RefCache& c = t->cache;
@@ -444,12 +447,15 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
             t->idx_cap = nidx;
         }
         std::vector<double> pairs(3 * (size_t)nidx);
+        double gb = 0.0;
         for (int k = 0; k < nidx; k++) {
             const size_t i = (size_t)ir[k];
             pairs[k] = ref_aos[3 * i] - c.bbar[0];
             pairs[(size_t)nidx + k] = ref_aos[3 * i + 1] - c.bbar[1];
             pairs[2 * (size_t)nidx + k] = ref_aos[3 * i + 2] - c.bbar[2];
+            gb += pairs[k] * pairs[k] + pairs[(size_t)nidx + k] * pairs[(size_t)nidx + k] + pairs[2 * (size_t)nidx + k] * pairs[2 * (size_t)nidx + k];
         }
+        c.gb = gb;
         GCB_CUDA(cudaMemcpyAsync(t->d_refpairs, pairs.data(), sizeof(double) * pairs.size(), cudaMemcpyHostToDevice, t->stream));
         GCB_CUDA(cudaMemcpyAsync(t->d_idx, idx_test, sizeof(int) * (size_t)nidx, cudaMemcpyHostToDevice, t->stream));
         GCB_CUDA(cudaStreamSynchronize(t->stream));
@@ -552,13 +558,19 @@ bool use_cluster(const gcb_traj_ext* t) {
 int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
     int mode = MODE_ALL;
-    int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode);
+    // Subset fits that leave the frames untouched need only the subset's atoms.  Gathering them costs 3 sectors (96 bytes) per atom,
+    // streaming the frame 24 bytes per atom of the WHOLE frame: gather when the subset is at most a quarter of the atoms.
+    const bool prefer_gather = g_variant == GCB_KERNEL_AUTO && !write_back && !want_dev && idx_test && nidx > 0 &&
+                               4L * nidx <= t->natoms;
+    int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode, prefer_gather);
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;
     SuperParams p;
     fill_params(t, first, nframes, write_back, &p);
     if (mode == MODE_GATHER) {
         if (want_dev) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
+        if (g_variant == GCB_KERNEL_AUTO && !write_back && nidx <= 512)
+            return launch_super_small_gather(t, p, t->d_refpairs, t->d_idx, nidx, force_explicit_mode());
         return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
     }
     if (mode == MODE_WEIGHTED) p.weight = t->d_weight;

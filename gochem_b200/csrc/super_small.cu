@@ -85,22 +85,30 @@ __device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* s
     return !formula_ok;
 }
 
-template <int K, bool MASKED, bool DEV>
-__global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperParams p, int always_explicit, long nbatches) {
+// GATHER: the fit uses nidx atoms picked out of a (possibly much larger) frame -- slot q of the warp is atom idx[q] and the
+// template is the compact list refpairs (3 x nidx).  Only those atoms are read: 3 sectors per atom instead of the whole frame.
+template <int K, bool MASKED, bool DEV, bool GATHER = false>
+__global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperParams p, int always_explicit, long nbatches,
+                                                                  const double* __restrict__ refpairs = nullptr,
+                                                                  const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
     SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
     double* tb = reinterpret_cast<double*>(small_smem + sizeof(SmallShared));   // template planes bx | by | bz, 32*K each
     constexpr int NP = 32 * K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nslots = GATHER ? nidx : p.np;       // slots that hold data
+    const int nreal = GATHER ? nidx : p.natoms;    // slots that hold real atoms
     for (int i = tid; i < 3 * NP; i += kSmallThreads) {
         const int c = i / NP, a = i - c * NP;
-        tb[i] = a < p.np ? p.refc[(long)c * p.np + a] : 0.0;
+        tb[i] = a < nslots ? (GATHER ? refpairs[(long)c * nidx + a] : p.refc[(long)c * p.np + a]) : 0.0;
     }
     uint32_t real_mask = 0, fit_mask = 0;
+    int at[K];                                      // where slot lane + 32 k sits in a coordinate plane
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int a = lane + 32 * k;
-        if (a < p.natoms) {
+        at[k] = a < nslots ? (GATHER ? idx[a] : a) : 0;
+        if (a < nreal) {
             real_mask |= 1u << k;
             if (!MASKED || p.weight[a] != 0.0) fit_mask |= 1u << k;
         }
@@ -122,13 +130,13 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
         // ---------------- sweep 1: the 13 sums of every frame of the batch ----------------
         double x[K], y[K], z[K];
         auto load = [&](int i, auto& lx, auto& ly, auto& lz) {
-            const double* fr = p.frames + (f0 + i) * p.frame_stride + lane;
+            const double* fr = p.frames + (f0 + i) * p.frame_stride;
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                const bool in = lane + 32 * k < p.np;   // planes are padded to 16: the padding atoms read as zeros
-                lx[k] = in ? __ldcs(fr + 32 * k) : 0.0;
-                ly[k] = in ? __ldcs(fr + p.np + 32 * k) : 0.0;
-                lz[k] = in ? __ldcs(fr + 2L * p.np + 32 * k) : 0.0;
+                const bool in = lane + 32 * k < nslots;   // planes are padded to 16: the padding atoms read as zeros
+                lx[k] = in ? __ldcs(fr + at[k]) : 0.0;
+                ly[k] = in ? __ldcs(fr + p.np + at[k]) : 0.0;
+                lz[k] = in ? __ldcs(fr + 2L * p.np + at[k]) : 0.0;
             }
         };
         constexpr bool PF = K <= 8;   // two frames in flight while the registers allow it
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
             }
             const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
             const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
-            const long fo = (f0 + i) * p.frame_stride + lane;
+            const long fo = (f0 + i) * p.frame_stride;
             double e = 0.0;
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -211,11 +219,11 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
                 const double dx = qx - bx[32 * k], dy = qy - by[32 * k], dz = qz - bz[32 * k];
                 const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
                 if ((fit_mask >> k) & 1u) e += d2;
-                if (DEV) { if (lane + 32 * k < p.np) dev[k] += small_sqrt(d2); }
+                if (DEV) { if (lane + 32 * k < nslots) dev[k] += small_sqrt(d2); }
                 if (wb && ((real_mask >> k) & 1u)) {
-                    p.frames_rw[fo + 32 * k] = qx + p.bbar[0];
-                    p.frames_rw[fo + p.np + 32 * k] = qy + p.bbar[1];
-                    p.frames_rw[fo + 2L * p.np + 32 * k] = qz + p.bbar[2];
+                    p.frames_rw[fo + at[k]] = qx + p.bbar[0];
+                    p.frames_rw[fo + p.np + at[k]] = qy + p.bbar[1];
+                    p.frames_rw[fo + 2L * p.np + at[k]] = qz + p.bbar[2];
                 }
             }
             if (p.rmsd) {
@@ -394,6 +402,34 @@ int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev
 // up to ~1250 atoms (6.1 vs 3.8 TB/s at 1000 atoms, 1.37 G vs 0.19 G frames/s at 100 atoms); passes whose second sweep touches
 // every frame (write-back, per-atom sums, explicit residual) only up to 256 atoms -- above that the cluster kernel's
 // shared-memory-resident second sweep is faster.
+// Fit-only pass over nidx <= 512 atoms gathered out of every frame (RMSD, rotation, translations; frames untouched).
+int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx, int force_explicit) {
+    const int k_needed = (nidx + 31) / 32;
+    const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
+    const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
+    const long nbatches = (p.nframes + 31) / 32;
+    long grid = (long)t->sm_count * 3;
+    const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+#define GCB_GATHER_LAUNCH(KK)                                                                                                  \
+    do {                                                                                                                       \
+        GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<KK, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        super_small_kernel<KK, false, false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nbatches, refpairs, idx, nidx); \
+    } while (0)
+    switch (K) {
+        case 1: GCB_GATHER_LAUNCH(1); break;
+        case 2: GCB_GATHER_LAUNCH(2); break;
+        case 4: GCB_GATHER_LAUNCH(4); break;
+        case 8: GCB_GATHER_LAUNCH(8); break;
+        default: GCB_GATHER_LAUNCH(16); break;
+    }
+#undef GCB_GATHER_LAUNCH
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
 bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? 256 : 1280); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)

@@ -572,3 +572,30 @@ def test_moments_stream_kernel_chunked_frames(natoms, nframes):
     assert np.abs(mom - om).max() < 1e-10 * np.abs(om).max() + 1e-14 * scale
     c0, m0 = oracle.center_and_moment(frames[nframes - 1], mass)
     assert np.abs(cen[-1] - c0).max() < 1e-10 and np.abs(mom[-1] - m0).max() < 1e-10 * np.abs(m0).max() + 1e-14 * scale
+
+
+@pytest.mark.parametrize("nidx", [1, 30, 257, 512, 700])
+def test_small_subset_of_a_large_frame(nidx):
+    """A fit on a subset of at most a quarter of the atoms that leaves the frames untouched reads only those atoms (gather): the
+    warp-per-frame form up to 512 atoms, the generic gather kernel above; same results as the streaming kernels and the oracle."""
+    natoms, nframes = 4000, 70
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
+    idx = np.sort(np.random.default_rng(nidx).choice(natoms, nidx, replace=False))
+    t = device_traj(frames)
+    lib = _lib.load()
+    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    got = t.super_rmsd(ref, idx, idx)
+    if nidx >= 30:
+        rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, idx)
+        assert np.abs(got["rmsd"] - rm).max() < TOL_RMSD and np.abs(got["rot"] - rot).max() < TOL_ROT
+        assert np.abs(got["trans1"] - t1).max() < TOL_XYZ and np.abs(got["trans2"] - t2).max() < TOL_XYZ
+    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
+    try:
+        ref_path = t.super_rmsd(ref, idx, idx)       # the streaming kernel with the subset as a mask
+    finally:
+        lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
+    assert np.abs(got["rmsd"] - ref_path["rmsd"]).max() < TOL_RMSD
+    if nidx >= 30:
+        assert np.abs(got["rot"] - ref_path["rot"]).max() < TOL_ROT
+    assert np.array_equal(t.download(), frames)       # untouched
+    t.close()

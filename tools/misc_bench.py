@@ -8,6 +8,7 @@ from gochem_b200 import _lib, synth
 from gochem_b200 import host_api as H
 
 out = {}
+lib = _lib.load()
 
 
 def timed(t, fn, reps=5):
@@ -47,6 +48,22 @@ for na, nf in ((1500, 100000), (500, 200000), (100, 500000)):
     ms = timed(tt, lambda: tt.super_rmsd_async(r))
     out["fit_%dx%d" % (nf, na)] = {"ms": ms, "frames_per_s": nf / ms * 1e3, "GBs": 24.0 * na * nf / ms / 1e6, "plan": _lib.last_cluster_plan()}
     tt.close()
+# a solvated system: 100 000 atoms per frame, the fit on a small subset (frames untouched: RMSD + rotation only)
+na, nf = 100000, 20000
+r, sg = synth.make_reference(na), synth.atom_sigmas(na)
+tb = _lib.DeviceTraj(na, nf)
+tb.synth_fill(r, sg, nf)
+for n_sub in (300, 3000, 20000):
+    sub = np.sort(np.random.default_rng(n_sub).choice(na, n_sub, replace=False))
+    res = {}
+    for name, var in (("auto", _lib.KERNEL_AUTO), ("generic", _lib.KERNEL_GENERIC)):
+        _lib.check(lib.gcb_set_kernel_variant(var))
+        ms = timed(tb, lambda: tb.super_rmsd_async(r, sub, sub))
+        res[name + "_ms"] = ms
+        res[name + "_frames_per_s"] = nf / ms * 1e3
+    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    out["solvated_100k_atoms_subset_%d" % n_sub] = res
+tb.close()
 # latency of one chem.Super on host matrices (batch of one through the host mirror)
 a = synth.make_case(1500, 2)[1]
 H.Super(a[1].copy(), a[0])
