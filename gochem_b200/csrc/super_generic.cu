@@ -57,7 +57,9 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red, doubl
 }
 
 // thread 0: turn the reduced sums into the frame's transform; publish R and the centroid in xf[12].
-__device__ __forceinline__ void solve_frame(const SuperParams& p, long f, const double* sums, double* xf) {
+// one_pass: sums[12] = sum w|a|^2 is there and the RMSD may come from the inner products (E = Ga + Gb - 2 tr(R^T H)) when the
+// rounding bound of that form moves it by < 1e-10 A -- the rule of super_cluster.cu; xf[12] = 1 then, and the second sweep is skipped.
+__device__ __forceinline__ void solve_frame(const SuperParams& p, long f, const double* sums, double* xf, bool one_pass = false) {
     double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
     double h[9], r[9];
     bool finite = true;
@@ -81,13 +83,26 @@ __device__ __forceinline__ void solve_frame(const SuperParams& p, long f, const 
     }
     if (p.trans1) { p.trans1[f * 3] = -cen[0]; p.trans1[f * 3 + 1] = -cen[1]; p.trans1[f * 3 + 2] = -cen[2]; }
     if (p.trans2) { p.trans2[f * 3] = p.bbar[0]; p.trans2[f * 3 + 1] = p.bbar[1]; p.trans2[f * 3 + 2] = p.bbar[2]; }
+    bool formula_ok = false;
+    if (one_pass) {
+        const double ga = sums[12] - (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) * p.inv_n;
+        const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
+                            fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
+        const double e = ga + p.gb - 2.0 * trrh;
+        const double smax = sums[12] + p.gb;
+        formula_ok = rc == 0 && e > 0.0 && (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
+        if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
+        xf[12] = formula_ok ? 1.0 : 0.0;
+    }
+    if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
 }
 
 template <bool WEIGHTED, bool WRITE_BACK, bool DEV>
-__global__ void __launch_bounds__(kThreads, 3) super_generic_kernel(const SuperParams p) {
-    __shared__ double s_red[kWarps * 12];
-    __shared__ double s_sum[12];
-    __shared__ double s_xf[12];
+__global__ void __launch_bounds__(kThreads, 3) super_generic_kernel(const SuperParams p, int one_pass_arg) {
+    __shared__ double s_red[kWarps * 13];
+    __shared__ double s_sum[13];
+    __shared__ double s_xf[13];
+    const bool one_pass = !WRITE_BACK && !DEV && one_pass_arg != 0;   // the second sweep only when the RMSD needs it
     const int np = p.np, np2 = np >> 1;
     const double2* __restrict__ BX = reinterpret_cast<const double2*>(p.refc);
     const double2* __restrict__ BY = reinterpret_cast<const double2*>(p.refc + np);
@@ -99,13 +114,18 @@ __global__ void __launch_bounds__(kThreads, 3) super_generic_kernel(const SuperP
         const double2* __restrict__ X = reinterpret_cast<const double2*>(fr);
         const double2* __restrict__ Y = reinterpret_cast<const double2*>(fr + np);
         const double2* __restrict__ Z = reinterpret_cast<const double2*>(fr + 2L * np);
-        double acc[12];
+        double acc[13];
 #pragma unroll
-        for (int k = 0; k < 12; k++) acc[k] = 0.0;
+        for (int k = 0; k < 13; k++) acc[k] = 0.0;
 #pragma unroll 2
         for (int j = threadIdx.x; j < np2; j += kThreads) {
             double2 x = X[j], y = Y[j], z = Z[j];
             const double2 bx = BX[j], by = BY[j], bz = BZ[j];
+            if (!WRITE_BACK && !DEV) {   // sum w |a|^2 for the one-pass RMSD
+                const double n0 = fma(z.x, z.x, fma(y.x, y.x, x.x * x.x)), n1 = fma(z.y, z.y, fma(y.y, y.y, x.y * x.y));
+                if (WEIGHTED) { const double2 w = W[j]; acc[12] = fma(w.y, n1, fma(w.x, n0, acc[12])); }
+                else acc[12] += n0 + n1;
+            }
             if (WEIGHTED) {
                 const double2 w = W[j];
                 x.x *= w.x; y.x *= w.x; z.x *= w.x;
@@ -120,9 +140,10 @@ __global__ void __launch_bounds__(kThreads, 3) super_generic_kernel(const SuperP
             acc[6] = fma(y.y, bx.y, acc[6]); acc[7] = fma(y.y, by.y, acc[7]); acc[8] = fma(y.y, bz.y, acc[8]);
             acc[9] = fma(z.y, bx.y, acc[9]); acc[10] = fma(z.y, by.y, acc[10]); acc[11] = fma(z.y, bz.y, acc[11]);
         }
-        block_reduce<12>(acc, s_red, s_sum);
-        if (threadIdx.x == 0) solve_frame(p, f, s_sum, s_xf);
+        block_reduce<13>(acc, s_red, s_sum);
+        if (threadIdx.x == 0) solve_frame(p, f, s_sum, s_xf, one_pass);
         __syncthreads();
+        if (one_pass && s_xf[12] != 0.0) continue;   // block-uniform: the RMSD is already written
         const double r0 = s_xf[0], r1 = s_xf[1], r2 = s_xf[2], r3 = s_xf[3], r4 = s_xf[4], r5 = s_xf[5], r6 = s_xf[6],
                      r7 = s_xf[7], r8 = s_xf[8];
         const double cx = s_xf[9], cy = s_xf[10], cz = s_xf[11];
@@ -320,7 +341,7 @@ int launch_super_generic(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     const int grid = frames_grid(t, p.nframes, 3);
     if (grid_out) *grid_out = grid;
     const bool wb = p.frames_rw != nullptr;
-#define GCB_GEN(W, B, D) super_generic_kernel<W, B, D><<<grid, kThreads, 0, t->stream>>>(p)
+#define GCB_GEN(W, B, D) super_generic_kernel<W, B, D><<<grid, kThreads, 0, t->stream>>>(p, force_explicit_mode() ? 0 : 1)
     if (weighted) {
         if (wb) { if (want_dev) GCB_GEN(true, true, true); else GCB_GEN(true, true, false); }
         else    { if (want_dev) GCB_GEN(true, false, true); else GCB_GEN(true, false, false); }
