@@ -558,10 +558,12 @@ bool use_cluster(const gcb_traj_ext* t) {
 int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
     int mode = MODE_ALL;
-    // Subset fits that leave the frames untouched need only the subset's atoms.  Gathering them costs 3 sectors (96 bytes) per atom,
-    // streaming the frame 24 bytes per atom of the WHOLE frame: gather when the subset is at most a quarter of the atoms.
+    // Subset fits that leave the frames untouched need only the subset's atoms.  Gathering them costs 3 sectors (96 bytes) per atom
+    // plus a per-frame cost, streaming the frame 24 bytes per atom of the WHOLE frame.  Measured (tools/misc_bench.py): the
+    // warp-per-frame gather (<= 512 atoms, ~20 ns per frame at 300 atoms) wins once the frame is 16 times the subset; the
+    // CTA-per-frame gather kernel (~0.2 us per frame) only against frames the cluster kernel cannot take (> 28 672 atoms).
     const bool prefer_gather = g_variant == GCB_KERNEL_AUTO && !write_back && !want_dev && idx_test && nidx > 0 &&
-                               4L * nidx <= t->natoms;
+                               (nidx <= 512 ? 16L * nidx <= t->natoms : (t->natoms > 28672 && 12L * nidx <= t->natoms));
     int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode, prefer_gather);
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;

@@ -578,7 +578,7 @@ def test_moments_stream_kernel_chunked_frames(natoms, nframes):
 def test_small_subset_of_a_large_frame(nidx):
     """A fit on a subset of at most a quarter of the atoms that leaves the frames untouched reads only those atoms (gather): the
     warp-per-frame form up to 512 atoms, the generic gather kernel above; same results as the streaming kernels and the oracle."""
-    natoms, nframes = 4000, 70
+    natoms, nframes = (9000, 40) if nidx <= 512 else (30000, 12)   # sizes at which the gather forms are chosen (api.cu: launch_super)
     ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
     idx = np.sort(np.random.default_rng(nidx).choice(natoms, nidx, replace=False))
     t = device_traj(frames)
@@ -589,7 +589,7 @@ def test_small_subset_of_a_large_frame(nidx):
         rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, idx)
         assert np.abs(got["rmsd"] - rm).max() < TOL_RMSD and np.abs(got["rot"] - rot).max() < TOL_ROT
         assert np.abs(got["trans1"] - t1).max() < TOL_XYZ and np.abs(got["trans2"] - t2).max() < TOL_XYZ
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
+    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER if natoms <= 28672 else _lib.KERNEL_GENERIC))
     try:
         ref_path = t.super_rmsd(ref, idx, idx)       # the streaming kernel with the subset as a mask
     finally:
