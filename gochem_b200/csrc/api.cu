@@ -563,7 +563,9 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     // warp-per-frame gather (<= 512 atoms, ~20 ns per frame at 300 atoms) wins once the frame is 16 times the subset; the
     // CTA-per-frame gather kernel (~0.2 us per frame) only against frames the cluster kernel cannot take (> 28 672 atoms).
     const bool prefer_gather = g_variant == GCB_KERNEL_AUTO && !write_back && !want_dev && idx_test && nidx > 0 &&
-                               (nidx <= 512 ? 16L * nidx <= t->natoms : (t->natoms > 28672 && 12L * nidx <= t->natoms));
+                               (nidx <= 512 ? 16L * nidx <= t->natoms
+                                : nidx <= small_gather_max_atoms() ? 8L * nidx <= t->natoms
+                                                                   : (t->natoms > 28672 && 12L * nidx <= t->natoms));
     int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode, prefer_gather);
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;
@@ -571,7 +573,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     fill_params(t, first, nframes, write_back, &p);
     if (mode == MODE_GATHER) {
         if (want_dev) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
-        if (g_variant == GCB_KERNEL_AUTO && !write_back && nidx <= 512)
+        if (g_variant == GCB_KERNEL_AUTO && !write_back && nidx <= small_gather_max_atoms())
             return launch_super_small_gather(t, p, t->d_refpairs, t->d_idx, nidx, force_explicit_mode());
         return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
     }

@@ -142,5 +142,6 @@ int force_explicit_mode();
 bool small_kernel_supported(const gcb_traj* t, bool heavy);
 int small_kernel_rows(const gcb_traj* t);
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out);
+int small_gather_max_atoms();
 int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx, int force_explicit);
 }  // namespace gcb

@@ -254,25 +254,33 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
 // structures this size stay with the cluster kernel.
 constexpr int kMidChunk = 4;                 // atoms per lane per chunk
 constexpr int kMidMaxAtoms = 2048;
+constexpr int kGatherMaxAtoms = 4096;        // gathered subsets: template planes of 96 KB in shared memory
 
-template <bool MASKED>
-__global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch) {
+template <bool MASKED, bool GATHER = false>
+__global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch,
+                                                                   const double* __restrict__ refpairs = nullptr,
+                                                                   const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
     SmallShared& sh = *reinterpret_cast<SmallShared*>(small_smem);
     double* tb = reinterpret_cast<double*>(small_smem + sizeof(SmallShared));   // template planes, NP each
     constexpr int CH = kMidChunk;
     const int NP = 32 * CH * nch;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nslots = GATHER ? nidx : p.np, nreal = GATHER ? nidx : p.natoms;
     for (int i = tid; i < 3 * NP; i += kSmallThreads) {
         const int c = i / NP, a = i - c * NP;
-        tb[i] = a < p.np ? p.refc[(long)c * p.np + a] : 0.0;
+        tb[i] = a < nslots ? (GATHER ? refpairs[(long)c * nidx + a] : p.refc[(long)c * p.np + a]) : 0.0;
     }
-    unsigned long long real_mask = 0, fit_mask = 0;   // bit c*CH + k: atom lane + 32*(c*CH + k)
-    for (int q = 0; q < CH * nch; q++) {
-        const int a = lane + 32 * q;
-        if (a < p.natoms) {
-            real_mask |= 1ull << q;
-            if (!MASKED || p.weight[a] != 0.0) fit_mask |= 1ull << q;
+    // streaming form: bit c*CH + k of the masks = atom lane + 32*(c*CH + k) (at most 16 chunks); the gather form has no subset
+    // inside its list, a slot is real when it is below nidx
+    unsigned long long real_mask = 0, fit_mask = 0;
+    if (!GATHER) {
+        for (int q = 0; q < CH * nch; q++) {
+            const int a = lane + 32 * q;
+            if (a < p.natoms) {
+                real_mask |= 1ull << q;
+                if (!MASKED || p.weight[a] != 0.0) fit_mask |= 1ull << q;
+            }
         }
     }
     __syncthreads();
@@ -287,13 +295,15 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
         const int nf = (int)((p.nframes - f0 < 32) ? (p.nframes - f0) : 32);
         double x[CH], y[CH], z[CH];
         auto load = [&](int i, int c, double (&lx)[CH], double (&ly)[CH], double (&lz)[CH]) {
-            const double* fr = p.frames + (f0 + i) * p.frame_stride + lane + 32 * CH * c;
+            const double* fr = p.frames + (f0 + i) * p.frame_stride;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
-                const bool in = lane + 32 * (CH * c + k) < p.np;
-                lx[k] = in ? __ldcs(fr + 32 * k) : 0.0;
-                ly[k] = in ? __ldcs(fr + p.np + 32 * k) : 0.0;
-                lz[k] = in ? __ldcs(fr + 2L * p.np + 32 * k) : 0.0;
+                const int slot = lane + 32 * (CH * c + k);
+                const bool in = slot < nslots;
+                const int a = GATHER ? (in ? __ldg(idx + slot) : 0) : slot;
+                lx[k] = in ? __ldcs(fr + a) : 0.0;
+                ly[k] = in ? __ldcs(fr + p.np + a) : 0.0;
+                lz[k] = in ? __ldcs(fr + 2L * p.np + a) : 0.0;
             }
         };
         load(0, 0, x, y, z);
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
                 const bool last = c + 1 == nch;
                 if (!last) load(i, c + 1, nx, ny, nz);
                 else if (i + 1 < nf) load(i + 1, 0, nx, ny, nz);
-                const uint32_t fm = (uint32_t)(fit_mask >> (CH * c));
+                const uint32_t fm = GATHER ? 0u : (uint32_t)(fit_mask >> (CH * c));
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     double ax = x[k], ay = y[k], az = z[k];
@@ -353,21 +363,23 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
             const long fo = (f0 + i) * p.frame_stride + lane;
             double e = 0.0;
             for (int c = 0; c < nch; c++) {
-                const uint32_t fm = (uint32_t)(fit_mask >> (CH * c)), rm = (uint32_t)(real_mask >> (CH * c));
+                uint32_t fm = (uint32_t)(fit_mask >> (CH * c)), rm = (uint32_t)(real_mask >> (CH * c));
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     const int o = 32 * (CH * c + k);
-                    if (lane + o >= p.np) continue;
-                    const double ax = p.frames[fo + o], ay = p.frames[fo + p.np + o], az = p.frames[fo + 2L * p.np + o];
+                    if (lane + o >= nslots) continue;
+                    if (GATHER) { fm |= 1u << k; rm |= 1u << k; }   // every listed atom is a real atom of the fit
+                    const long at = GATHER ? (long)__ldg(idx + lane + o) - lane : (long)o;   // offset from fo
+                    const double ax = p.frames[fo + at], ay = p.frames[fo + p.np + at], az = p.frames[fo + 2L * p.np + at];
                     const double qx = fma(az, r6, fma(ay, r3, fma(ax, r0, g0)));
                     const double qy = fma(az, r7, fma(ay, r4, fma(ax, r1, g1)));
                     const double qz = fma(az, r8, fma(ay, r5, fma(ax, r2, g2)));
                     const double dx = qx - bx[o], dy = qy - by[o], dz = qz - bz[o];
                     if ((fm >> k) & 1u) e += fma(dz, dz, fma(dy, dy, dx * dx));
                     if (wb && ((rm >> k) & 1u)) {
-                        p.frames_rw[fo + o] = qx + p.bbar[0];
-                        p.frames_rw[fo + p.np + o] = qy + p.bbar[1];
-                        p.frames_rw[fo + 2L * p.np + o] = qz + p.bbar[2];
+                        p.frames_rw[fo + at] = qx + p.bbar[0];
+                        p.frames_rw[fo + p.np + at] = qy + p.bbar[1];
+                        p.frames_rw[fo + 2L * p.np + at] = qz + p.bbar[2];
                     }
                 }
             }
@@ -404,6 +416,20 @@ int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev
 // shared-memory-resident second sweep is faster.
 // Fit-only pass over nidx <= 512 atoms gathered out of every frame (RMSD, rotation, translations; frames untouched).
 int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx, int force_explicit) {
+    if (nidx > kSmallMaxAtoms) {   // chunked form, up to kGatherMaxAtoms
+        const int nch = (nidx + 32 * kMidChunk - 1) / (32 * kMidChunk);
+        const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
+        const long nbatches = (p.nframes + 31) / 32;
+        long grid = (long)t->sm_count * (smem <= 110 * 1024 ? 2 : 1);
+        const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        super_mid_kernel<false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nbatches, nch, refpairs, idx, nidx);
+        GCB_LAUNCHED();
+        GCB_CUDA(cudaGetLastError());
+        return GCB_OK;
+    }
     const int k_needed = (nidx + 31) / 32;
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
@@ -429,6 +455,8 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     GCB_CUDA(cudaGetLastError());
     return GCB_OK;
 }
+
+int small_gather_max_atoms() { return kGatherMaxAtoms; }
 
 bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? 256 : 1280); }
 

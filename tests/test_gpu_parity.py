@@ -574,11 +574,11 @@ def test_moments_stream_kernel_chunked_frames(natoms, nframes):
     assert np.abs(cen[-1] - c0).max() < 1e-10 and np.abs(mom[-1] - m0).max() < 1e-10 * np.abs(m0).max() + 1e-14 * scale
 
 
-@pytest.mark.parametrize("nidx", [1, 30, 257, 512, 700])
+@pytest.mark.parametrize("nidx", [1, 30, 257, 512, 700, 3000, 4096])
 def test_small_subset_of_a_large_frame(nidx):
     """A fit on a subset of at most a quarter of the atoms that leaves the frames untouched reads only those atoms (gather): the
     warp-per-frame form up to 512 atoms, the generic gather kernel above; same results as the streaming kernels and the oracle."""
-    natoms, nframes = (9000, 40) if nidx <= 512 else (30000, 12)   # sizes at which the gather forms are chosen (api.cu: launch_super)
+    natoms, nframes = (9000, 40) if nidx <= 512 else (33000, 37)   # sizes at which the gather forms are chosen (api.cu: launch_super)
     ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
     idx = np.sort(np.random.default_rng(nidx).choice(natoms, nidx, replace=False))
     t = device_traj(frames)
