@@ -599,3 +599,15 @@ def test_small_subset_of_a_large_frame(nidx):
         assert np.abs(got["rot"] - ref_path["rot"]).max() < TOL_ROT
     assert np.array_equal(t.download(), frames)       # untouched
     t.close()
+
+
+def test_rmsd_without_fit_on_a_small_subset_of_a_large_frame():
+    """chem.RMSD (no fit) over a small subset of a 20 000-atom frame takes the gather kernel; same numbers as the oracle."""
+    natoms, nframes = 20000, 9
+    ref, frames = synth.make_case(natoms, nframes)
+    idx = np.sort(np.random.default_rng(2).choice(natoms, 400, replace=False))
+    t = device_traj(frames)
+    got = t.rmsd(ref, idx, idx)
+    for f in range(nframes):
+        assert abs(got[f] - oracle.rmsd(frames[f], ref, idx, idx)) < 1e-9 * max(1, got[f])
+    t.close()
