@@ -30,6 +30,13 @@ constexpr int BM = 128, BN = 128, BK = GCB_AP_BK;
 constexpr int LDS = BK + 4;           // row stride in doubles: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts
 constexpr int STAGES = GCB_AP_STAGES;  // BK = 32 double-buffered: one barrier per 8 DMMA k-steps (BK = 16 x 3 stages: per 4)
 constexpr int GEMM_THREADS = 256;
+#ifndef GCB_AP_WARPS
+#define GCB_AP_WARPS 8
+#endif
+constexpr int AP_WARPS = GCB_AP_WARPS;            // warps of the no-fit GEMM CTA: (AP_WARPS / 4) x 4 warp tiles
+constexpr int AP_THREADS = 32 * AP_WARPS;
+constexpr int AP_WR = BM / (AP_WARPS / 4);        // rows of a warp tile: 64 (8 warps) or 32 (16 warps)
+constexpr int AP_MI = AP_WR / 8;
 constexpr int TLD = BN + 1;           // staging row stride: transposed reads touch every bank once per half warp
 constexpr int kMaxPeers = 8;
 
@@ -153,7 +160,7 @@ __device__ __forceinline__ double* peer_row(const PeerOut& po, long i, long ld) 
 // One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T and delivers D for the block and for its mirror
 // image to the owners of those rows (PeerOut): the block is staged in shared memory, 64 rows at a time, and leaves as
 // whole-row segments (256-byte stores per warp), the mirror image read transposed from the same staging buffer.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(AP_THREADS, 1)
 allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
                      const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
     extern __shared__ __align__(16) double smem[];
@@ -162,12 +169,12 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
     const int2 tile = tiles[blockIdx.x];
     const long i0 = (long)tile.x * BM, j0 = (long)tile.y * BN;   // global frame indexes
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2, wn = warp & 3;        // 2 x 4 warps -> 64 x 32 warp tiles
+    const int wm = warp >> 2, wn = warp & 3;        // (AP_WARPS / 4) x 4 warps -> AP_WR x 32 warp tiles
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[8][4][2];
+    double acc[AP_MI][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < AP_MI; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
@@ -176,8 +183,8 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * BK;
 #pragma unroll
-        for (int r = 0; r < BK / 4; r++) {
-            const int chunk = tid + r * GEMM_THREADS;
+        for (int r = 0; r < 64 * BK / AP_THREADS; r++) {
+            const int chunk = tid + r * AP_THREADS;
             const int row = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
             const bool kin = k0 + kc < kdim;
             {
@@ -205,17 +212,17 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
             if (nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* a = sA + ((size_t)(kt % STAGES) * BM + wm * 64) * LDS;
+        const double* a = sA + ((size_t)(kt % STAGES) * BM + wm * AP_WR) * LDS;
         const double* b = sB + ((size_t)(kt % STAGES) * BN + wn * 32) * LDS;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double af[8], bf[4];
+            double af[AP_MI], bf[4];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
+            for (int mi = 0; mi < AP_MI; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) bf[ni] = b[(ni * 8 + g) * LDS + kk + t];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++)
+            for (int mi = 0; mi < AP_MI; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
@@ -225,10 +232,11 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
     // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
     double* sT = smem;   // [64][TLD]
     for (int half = 0; half < 2; half++) {
-        if (wm == half) {
+        if ((wm * AP_WR) / 64 == half) {
+            const int rbase = wm * AP_WR - half * 64;   // first staged row of this warp
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) {
-                const long i = i0 + wm * 64 + mi * 8 + g;
+            for (int mi = 0; mi < AP_MI; mi++) {
+                const long i = i0 + wm * AP_WR + mi * 8 + g;
                 const double ni_ = i < nframes ? norms[i] : 0.0;
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) {
@@ -247,14 +255,14 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
                             }
                             d = sqrt(d2 > 0.0 ? d2 : 0.0);
                         }
-                        sT[(mi * 8 + g) * TLD + c] = d;
+                        sT[(rbase + mi * 8 + g) * TLD + c] = d;
                     }
                 }
             }
         }
         __syncthreads();
         const long ib = i0 + half * 64;   // first row staged
-        for (int r = warp; r < 64; r += 8) {          // rows of the block: 128 contiguous doubles each
+        for (int r = warp; r < 64; r += AP_WARPS) {          // rows of the block: 128 contiguous doubles each
             const long i = ib + r;
             if (i >= nframes) break;
             double* dst = peer_row(po, i, ldd);
@@ -265,7 +273,7 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
                 if (j0 + c < nframes) dst[c] = sT[r * TLD + c];
         }
         if (tile.x != tile.y) {                       // mirror image: rows j of the matrix, 64 contiguous doubles each
-            for (int c = warp; c < BN; c += 8) {
+            for (int c = warp; c < BN; c += AP_WARPS) {
                 const long j = j0 + c;
                 if (j >= nframes) break;
                 double* dst = peer_row(po, j, ldd);
@@ -643,7 +651,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     } else {
         AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AP_TRY(cudaEventRecord(e0, s));
-        allpairs_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used,
+        allpairs_dmma_kernel<<<(unsigned)tiles.size(), AP_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used,
                                                                               d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
         AP_TRY(cudaEventRecord(e1, s));
