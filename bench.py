@@ -363,6 +363,24 @@ def run_ours(a):
         dt = time.perf_counter() - t0
         cpu = {"value": n_cpu * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {n_cpu} frames of the GPU's trajectory ({natoms} atoms) x {reps} passes, O(N) C restatement of the reference path (oracle/gochem_oracle.c), one worker thread per frame in flight, {cores} threads, {dt:.1f} s"}
+        # the reference AS WRITTEN also forms an N x N identity / ones product per frame (geometric.go:145-149): 1.6 GB per frame at
+        # 10 000 atoms, so that cost model is only runnable at the size of BASELINE configs[0] (1500 atoms); reported beside the port
+        try:
+            from gochem_b200 import synth as _synth
+
+            ref_s, frames_s = _synth.make_case(1500, max(cores, 16), frame0_is_ref=True)
+            oracle.super_rmsd_traj(frames_s[:cores], ref_s, None, as_written=True, nthreads=cores, details=False)
+            t1 = time.perf_counter()
+            oracle.super_rmsd_traj(frames_s, ref_s, None, as_written=True, nthreads=cores, details=False)
+            dt_w = time.perf_counter() - t1
+            t1 = time.perf_counter()
+            for _ in range(20):
+                oracle.super_rmsd_traj(frames_s, ref_s, None, nthreads=cores, details=False)
+            dt_p = (time.perf_counter() - t1) / 20
+            cpu["as_written_1500_atoms"] = {"value": frames_s.shape[0] / dt_w, "unit": UNIT, "port_same_size": frames_s.shape[0] / dt_p,
+                                           "sample": f"{frames_s.shape[0]} frames x 1500 atoms, {cores} threads; N x N identity product per frame as in geometric.go:145-149"}
+        except Exception as exc:  # the as-written model is informational
+            cpu["as_written_1500_atoms"] = {"error": str(exc)[:200]}
         if not wb:
             got = traj.fetch(0, n_cpu, want=("rmsd", "rot"))
             parity = {"frames_checked": n_cpu, "max_abs_rmsd_diff": float(np.abs(got["rmsd"] - rm_cpu).max()),

@@ -31,9 +31,19 @@ constexpr int kSmallMaxAtoms = 512;
 
 __device__ __forceinline__ double shx2(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
+// CTAs per SM the instances are built for (measured, tools/small_sweep.py): two (128 registers) for K <= 4 and K = 16; the K = 8
+// instance keeps two frames of 8 atoms per lane in registers and is faster unbounded (183 registers) than squeezed into 128.
+#ifndef GCB_SMALL_MINB
+#define GCB_SMALL_MINB 2
+#endif
+#ifndef GCB_MID_MINB
+#define GCB_MID_MINB 2
+#endif
+// One 13-double record per frame of the batch, used twice: first the frame's sums -- S (3), H (9), sum w|a|^2 -- written by sweep 1,
+// then, in place, what the lane that solved the frame leaves for sweep 2 -- R (9), centroid*R (3), [12] != 0: form the explicit
+// residual.  (Lane l reads record l completely before it writes it.)
 struct SmallShared {
-    double sums[kSmallWarps][32][13];   // per frame of the batch: S (3), H (9), sum w|a|^2
-    double xf[kSmallWarps][32][13];     // R (9), centroid*R (3), [12] != 0: sweep 2 must form the explicit residual
+    double rec[kSmallWarps][32][13];
 };
 
 // sqrt with a short dependency chain (see super_cluster.cu: cubic-order correction of the rsqrt seed)
@@ -49,7 +59,10 @@ __device__ __forceinline__ double small_sqrt(double x) {
 // The 3x3 problem of one frame from its 13 sums (one lane per frame): rotation, centroid, the one-pass RMSD when its
 // rounding bound allows (same rule as super_cluster.cu) and the per-frame outputs.  Returns true when sweep 2 must form the
 // explicit residual for this frame.
-__device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* s, double* xf, long f, bool sweep2_all) {
+__device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* sums, double* xf, long f, bool sweep2_all) {
+    double s[13];   // xf may alias sums: take a copy first
+#pragma unroll
+    for (int k = 0; k < 13; k++) s[k] = sums[k];
     const double cen[3] = {s[0] * p.inv_n, s[1] * p.inv_n, s[2] * p.inv_n};
     double h[9], r[9];
     bool finite = true;
@@ -88,7 +101,7 @@ __device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* s
 // GATHER: the fit uses nidx atoms picked out of a (possibly much larger) frame -- slot q of the warp is atom idx[q] and the
 // template is the compact list refpairs (3 x nidx).  Only those atoms are read: 3 sectors per atom instead of the whole frame.
 template <int K, bool MASKED, bool DEV, bool GATHER = false>
-__global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperParams p, int always_explicit, long nbatches,
+__global__ void __launch_bounds__(kSmallThreads, (K == 8 ? 1 : GCB_SMALL_MINB)) super_small_kernel(const SuperParams p, int always_explicit, long nbatches,
                                                                   const double* __restrict__ refpairs = nullptr,
                                                                   const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
             warp_reduce12(acc, lane, t0, t1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) aa += shx2(aa, o);
-            double* sm = sh.sums[warp][i];
+            double* sm = sh.rec[warp][i];
             if (lane == 0) sm[12] = aa;
             if ((lane & 3) == 0) {
                 const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
         __syncwarp();
         // ---------------- the 32 solves of the batch, one per lane ----------------
         bool any_sweep2 = sweep2_all;
-        if (lane < nf) any_sweep2 = solve_lane(p, sh.sums[warp][lane], sh.xf[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
+        if (lane < nf) any_sweep2 = solve_lane(p, sh.rec[warp][lane], sh.rec[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
         any_sweep2 = __any_sync(0xffffffffu, any_sweep2);
         __syncwarp();
         if (!any_sweep2) continue;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(kSmallThreads) super_small_kernel(const SuperP
         const bool pf2 = PF && sweep2_all;
         if (pf2) load(0, x, y, z);
         for (int i = 0; i < nf; i++) {
-            const double* xf = sh.xf[warp][i];
+            const double* xf = sh.rec[warp][i];
             if (!sweep2_all && xf[12] == 0.0) continue;   // warp-uniform
             double nx[KN], ny[KN], nz[KN];
             if constexpr (PF) {
@@ -257,7 +270,7 @@ constexpr int kMidMaxAtoms = 2048;
 constexpr int kGatherMaxAtoms = 4096;        // gathered subsets: template planes of 96 KB in shared memory
 
 template <bool MASKED, bool GATHER = false>
-__global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch,
+__global__ void __launch_bounds__(kSmallThreads, GCB_MID_MINB) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch,
                                                                    const double* __restrict__ refpairs = nullptr,
                                                                    const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
             warp_reduce12(acc, lane, t0, t1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) aa += shx2(aa, o);
-            double* sm = sh.sums[warp][i];
+            double* sm = sh.rec[warp][i];
             if (lane == 0) sm[12] = aa;
             if ((lane & 3) == 0) {
                 const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
@@ -351,12 +364,12 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
         }
         __syncwarp();
         bool any_sweep2 = sweep2_all;
-        if (lane < nf) any_sweep2 = solve_lane(p, sh.sums[warp][lane], sh.xf[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
+        if (lane < nf) any_sweep2 = solve_lane(p, sh.rec[warp][lane], sh.rec[warp][lane], f0 + lane, sweep2_all) || any_sweep2;
         any_sweep2 = __any_sync(0xffffffffu, any_sweep2);
         __syncwarp();
         if (!any_sweep2) continue;
         for (int i = 0; i < nf; i++) {
-            const double* xf = sh.xf[warp][i];
+            const double* xf = sh.rec[warp][i];
             if (!sweep2_all && xf[12] == 0.0) continue;   // warp-uniform
             const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
             const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
@@ -394,10 +407,15 @@ __global__ void __launch_bounds__(kSmallThreads, 2) super_mid_kernel(const Super
 }
 
 template <int K>
-int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int grid, long nbatches, size_t smem) {
+int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int& grid, long nbatches, size_t smem) {
 #define GCB_SMALL_LAUNCH(M, D)                                                                                   \
     do {                                                                                                         \
         GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<K, M, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm = 1;                                                                                          \
+        GCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, super_small_kernel<K, M, D>, kSmallThreads, smem)); \
+        if (per_sm < 1) per_sm = 1;                                                                              \
+        if (per_sm > 4) per_sm = 4;                                                                              \
+        if (grid > t->sm_count * per_sm) grid = t->sm_count * per_sm;                                            \
         super_small_kernel<K, M, D><<<grid, kSmallThreads, smem, t->stream>>>(p, always_explicit, nbatches);        \
     } while (0)
     if (masked) { if (want_dev) GCB_SMALL_LAUNCH(true, true); else GCB_SMALL_LAUNCH(true, false); }
@@ -420,7 +438,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
         const int nch = (nidx + 32 * kMidChunk - 1) / (32 * kMidChunk);
         const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
         const long nbatches = (p.nframes + 31) / 32;
-        long grid = (long)t->sm_count * (smem <= 110 * 1024 ? 2 : 1);
+        long grid = (long)t->sm_count * (smem <= 110 * 1024 ? GCB_MID_MINB : 1);
         const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
@@ -434,7 +452,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
     const long nbatches = (p.nframes + 31) / 32;
-    long grid = (long)t->sm_count * 3;
+    long grid = (long)t->sm_count * GCB_SMALL_MINB;
     const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -461,14 +479,14 @@ int small_gather_max_atoms() { return kGatherMaxAtoms; }
 bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? 256 : 1280); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)
-int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 3 * kSmallWarps; }
+int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 4 * kSmallWarps; }
 
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out) {
     if (t->np > kSmallMaxAtoms) {   // chunked form
         const int nch = (t->np + 32 * kMidChunk - 1) / (32 * kMidChunk);
         const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
         const long nbatches = (p.nframes + 31) / 32;
-        long grid = (long)t->sm_count * 2;
+        long grid = (long)t->sm_count * GCB_MID_MINB;
         const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
@@ -489,21 +507,22 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
     const long nbatches = (p.nframes + 31) / 32;
-    long grid = (long)t->sm_count * 3;   // 3 CTAs of 8 warps per SM (67 KB of shared memory each)
+    long grid = (long)t->sm_count * 4;   // trimmed to what an SM can hold (occupancy query at launch)
     const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    int g = (int)grid;
     const int always = (force_explicit || want_dev || p.frames_rw != nullptr) ? 1 : 0;
     if (want_dev) GCB_CUDA(cudaMemsetAsync(p.devpart, 0, sizeof(double) * (size_t)small_kernel_rows(t) * (size_t)t->np, t->stream));
     int rc;
     switch (K) {
-        case 1: rc = launch_small_k<1>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
-        case 2: rc = launch_small_k<2>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
-        case 4: rc = launch_small_k<4>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
-        case 8: rc = launch_small_k<8>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
-        default: rc = launch_small_k<16>(t, p, masked, want_dev, always, (int)grid, nbatches, smem); break;
+        case 1: rc = launch_small_k<1>(t, p, masked, want_dev, always, g, nbatches, smem); break;
+        case 2: rc = launch_small_k<2>(t, p, masked, want_dev, always, g, nbatches, smem); break;
+        case 4: rc = launch_small_k<4>(t, p, masked, want_dev, always, g, nbatches, smem); break;
+        case 8: rc = launch_small_k<8>(t, p, masked, want_dev, always, g, nbatches, smem); break;
+        default: rc = launch_small_k<16>(t, p, masked, want_dev, always, g, nbatches, smem); break;
     }
-    if (rows_out) *rows_out = (int)grid * kSmallWarps;
+    if (rows_out) *rows_out = g * kSmallWarps;
     return rc;
 }
 
