@@ -184,7 +184,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     if (t->stream) cudaStreamDestroy(t->stream);
     cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
     cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
-    cudaFree(t->d_devpart); cudaFree(t->d_devsum);
+    cudaFree(t->d_devpart); cudaFree(t->d_devsum); cudaFree(t->d_refplanes);
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     cudaFree(t->d_ap_ws);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
@@ -550,13 +550,20 @@ int check_status(gcb_traj_ext* t) {
     return GCB_OK;
 }
 
-bool use_cluster(const gcb_traj_ext* t) {
+bool use_cluster(const gcb_traj_ext* t, bool heavy) {
     if (g_variant == GCB_KERNEL_GENERIC) return false;
-    return cluster_kernel_supported(t);
+    return cluster_kernel_supported(t, heavy);
 }
+
+int launch_super_split(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                       const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows);
 
 int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
+    // Frames beyond the cluster kernel's capacity whose every atom must be visited a second time (write-back, per-atom sums):
+    // the fit and the elementwise sweep are separate launches (transform.cu) instead of the generic kernel's re-read.
+    if (g_variant == GCB_KERNEL_AUTO && (write_back || want_dev) && nframes > 0 && !cluster_kernel_supported(t, true))
+        return launch_super_split(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back, want_dev, dev_rows);
     int mode = MODE_ALL;
     // Subset fits that leave the frames untouched need only the subset's atoms.  Gathering them costs 3 sectors (96 bytes) per atom
     // plus a per-frame cost, streaming the frame 24 bytes per atom of the WHOLE frame.  Measured (tools/misc_bench.py): the
@@ -580,7 +587,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     if (mode == MODE_WEIGHTED) p.weight = t->d_weight;
     if (want_dev && mode == MODE_WEIGHTED && t->cache.paired) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
     // the cluster kernel takes the fit subset as a 0/1 mask; index lists with repeats (multiplicities) go to the generic kernel
-    const bool cluster = use_cluster(t) && !(mode == MODE_WEIGHTED && t->cache.repeated);
+    const bool cluster = use_cluster(t, write_back != 0 || want_dev) && !(mode == MODE_WEIGHTED && t->cache.repeated);
     if (g_variant == GCB_KERNEL_CLUSTER && !cluster && !(mode == MODE_WEIGHTED && t->cache.repeated)) {
         set_error("cluster kernel requested but not available for %d atoms", t->natoms);
         return GCB_ERR_ARG;
@@ -600,6 +607,48 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
          : cluster ? launch_super_cluster(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used)
                    : launch_super_generic(t, p, mode == MODE_WEIGHTED, want_dev, &rows_used);
     if (dev_rows) *dev_rows = rows_used;
+    return rc;
+}
+
+int launch_super_split(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                       const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
+    if (want_dev) {
+        // align.concproc (align/lovo.go:270-274) passes the same list for both structures, which have the same atoms
+        const bool all = (idx_test == nullptr || nidx == 0);
+        bool same = natoms_ref == t->natoms;
+        const int* ir = idx_ref ? idx_ref : idx_test;
+        for (int k = 0; same && !all && k < nidx; k++) same = idx_test[k] == ir[k];
+        if (!same) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
+    }
+    // 1. the fit: R, trans1, trans2 and the RMSD of every frame, frames untouched
+    int rc = launch_super(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, 0, false, nullptr);
+    if (rc) return rc;
+    SuperParams p;
+    fill_params(t, first, nframes, write_back, &p);
+    if (want_dev) {
+        // 2a. per-atom distances to the template after the fit, summed over the frames (before any write-back: they are
+        //     formed from the original coordinates and the transform)
+        const int np = t->np;
+        if (!t->d_refplanes) GCB_CUDA(cudaMalloc(&t->d_refplanes, sizeof(double) * 3 * (size_t)np));
+        GCB_CUDA(cudaStreamSynchronize(t->stream));   // h_scratch may still feed an earlier copy
+        double* h = t->h_scratch;
+        memset(h, 0, sizeof(double) * 3 * (size_t)np);
+        for (int i = 0; i < t->natoms; i++) {
+            h[i] = ref_aos[3 * (size_t)i] - p.bbar[0];
+            h[np + i] = ref_aos[3 * (size_t)i + 1] - p.bbar[1];
+            h[2 * (size_t)np + i] = ref_aos[3 * (size_t)i + 2] - p.bbar[2];
+        }
+        GCB_CUDA(cudaMemcpyAsync(t->d_refplanes, h, sizeof(double) * 3 * (size_t)np, cudaMemcpyHostToDevice, t->stream));
+        rc = ensure_devpart(t, (size_t)peratom_accum_rows(t, nframes));
+        if (rc) return rc;
+        p.devpart = t->d_devpart;
+        int rows = 0;
+        rc = launch_peratom_accum(t, p, t->d_refplanes, &rows);
+        if (rc) return rc;
+        if (dev_rows) *dev_rows = rows;
+    }
+    // 2b. test = (test + trans1) R + trans2 for every atom, in place (handy.go:207-211)
+    if (write_back) rc = launch_transform_frames(t, p);
     return rc;
 }
 

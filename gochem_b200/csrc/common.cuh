@@ -88,6 +88,7 @@ struct gcb_traj {
     double* d_devpart = nullptr;
     size_t devpart_rows = 0;
     double* d_devsum = nullptr;
+    double* d_refplanes = nullptr;  // split path of large frames (transform.cu): centred template planes of ALL atoms, 3 * np
     // per-frame centre of mass / moment tensor (moments.cu)
     double* d_mom_w = nullptr;   // np mass plane
     double* d_mom_c = nullptr;   // 3 per frame
@@ -133,7 +134,7 @@ int launch_dev_reduce(gcb_traj* t, int rows, double* out);
 int launch_peratom_dist(gcb_traj* t, const double* frame, const double* refpairs, const int* idx, int nidx, double* out);
 int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos, const double* d_sigma,
                  unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
-bool cluster_kernel_supported(const gcb_traj* t);
+bool cluster_kernel_supported(const gcb_traj* t, bool heavy = false);
 void set_cluster_tuning(int cluster, int stages, int depth, int resident);
 void get_last_plan(int* out8);
 void set_force_explicit(int on);
@@ -143,5 +144,8 @@ bool small_kernel_supported(const gcb_traj* t, bool heavy);
 int small_kernel_rows(const gcb_traj* t);
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out);
 int small_gather_max_atoms();
+int launch_transform_frames(gcb_traj* t, const SuperParams& p);
+int peratom_accum_rows(const gcb_traj* t, long nframes);
+int launch_peratom_accum(gcb_traj* t, const SuperParams& p, const double* ref_planes, int* rows_out);
 int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx, int force_explicit);
 }  // namespace gcb

@@ -597,9 +597,11 @@ void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
     g_tune_resident = resident;
 }
 
-bool cluster_kernel_supported(const gcb_traj* t) {
+// heavy: the pass visits every atom twice (write-back, per-atom sums, explicit residuals on request) and keeps the part resident
+// in shared memory, which holds fewer atoms per CTA (20 480 per frame against 28 672 for fit-only passes)
+bool cluster_kernel_supported(const gcb_traj* t, bool heavy) {
     Plan pl;
-    return make_plan(t->np, false, &pl);
+    return make_plan(t->np, heavy || g_force_explicit, &pl);
 }
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {

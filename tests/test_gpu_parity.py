@@ -611,3 +611,33 @@ def test_rmsd_without_fit_on_a_small_subset_of_a_large_frame():
     for f in range(nframes):
         assert abs(got[f] - oracle.rmsd(frames[f], ref, idx, idx)) < 1e-9 * max(1, got[f])
     t.close()
+
+
+@pytest.mark.parametrize("natoms,nidx", [(33000, 0), (33000, 300), (33000, 5000), (40010, 977), (24000, 0), (24000, 450)])
+def test_large_frames_write_back_and_per_atom_sums(natoms, nidx):
+    """Frames beyond what the cluster kernel keeps resident (20 480 atoms for passes that visit every atom twice): the fit and the
+    elementwise sweep over the whole frame are separate launches (transform.cu).  chem.Super's in-place result, the per-frame
+    outputs and align.RMSDTraj's per-atom sums against the oracle, for all-atom fits and for subset fits (gathered)."""
+    nframes = 21
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
+    idx = np.sort(np.random.default_rng(natoms + nidx).choice(natoms, nidx, replace=False)) if nidx else None
+    t = device_traj(frames)
+    out = t.super_rmsd(ref, idx, idx, write_back=True)
+    moved = t.download()
+    work = frames.copy()
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(work, ref, idx, write_back=True, nthreads=8)
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD and np.abs(out["rot"] - rot).max() < TOL_ROT
+    assert np.abs(out["trans1"] - t1).max() < TOL_XYZ and np.abs(out["trans2"] - t2).max() < TOL_XYZ
+    assert np.abs(moved - work).max() < TOL_XYZ
+    # per-atom sums (align.RMSDTraj), then with the aligned trajectory written back (writeTraj, lovo.go:337-339)
+    t.upload(frames)
+    got = t.peratom_dev_sum(ref, idx)
+    sel = idx if idx is not None else np.arange(natoms)
+    want, total, aligned = oracle.rmsd_traj(frames, ref, sel, cpus=7, want_aligned=True)
+    assert total == nframes
+    assert np.abs(got / nframes - want).max() < 1e-10
+    assert np.array_equal(t.download(), frames)       # untouched without write_back
+    got = t.peratom_dev_sum(ref, idx, write_back=True)
+    assert np.abs(got / nframes - want).max() < 1e-10
+    assert np.abs(t.download() - aligned).max() < TOL_XYZ
+    t.close()
