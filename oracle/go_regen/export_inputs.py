@@ -1,0 +1,44 @@
+"""Inputs for oracle/go_regen/main.go: every superposition case of tests/golden as a flat little-endian file.
+    python oracle/go_regen/export_inputs.py     ->  tests/golden/go_reference/<case>.in.bin
+Test infrastructure only (see oracle/__init__.py)."""
+import glob
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+OUT = os.path.join(GOLDEN, "go_reference")
+CPUS = 3   # chunk size of align.RMSDTraj in the Go run; frames beyond the last full chunk are dropped (lovo.go:323-326)
+
+
+def export(path: str) -> str:
+    z = np.load(path)
+    ref = z["ref"].astype("<f8")
+    frames = z["frames"].astype("<f8")
+    idx = z["idx"].astype("<i8") if "idx" in z.files else np.zeros(0, "<i8")
+    os.makedirs(OUT, exist_ok=True)
+    out = os.path.join(OUT, os.path.basename(path)[:-4] + ".in.bin")
+    with open(out, "wb") as f:
+        np.array([ref.shape[0], frames.shape[0], idx.size, CPUS], "<i8").tofile(f)
+        ref.tofile(f)
+        frames.tofile(f)
+        idx.tofile(f)
+    return out
+
+
+def read_outputs(path: str, natoms: int, nframes: int) -> dict:
+    """<case>.go.bin as written by main.go."""
+    with open(path, "rb") as f:
+        def take(n, dt="<f8"):
+            return np.fromfile(f, dt, n)
+        out = {"rmsd": take(nframes), "rot": take(nframes * 9).reshape(nframes, 3, 3), "trans1": take(nframes * 3).reshape(nframes, 3),
+               "trans2": take(nframes * 3).reshape(nframes, 3), "moved": take(nframes * natoms * 3).reshape(nframes, natoms, 3)}
+        out["frames_read"] = int(take(1, "<i8")[0])
+        out["rmsdtraj"] = take(natoms)
+    return out
+
+
+if __name__ == "__main__":
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "super_*.npz"))):
+        print(export(p))

@@ -19,6 +19,55 @@ def load(golden_dir, name):
     return {k: z[k] for k in z.files}
 
 
+def _go_regen():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "go_regen_export", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "go_regen", "export_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_go_regen_input_files_round_trip(golden_dir, tmp_path):
+    """The flat files oracle/go_regen/main.go reads hold exactly the golden inputs (header, ref, frames, index list)."""
+    ex = _go_regen()
+    ex.OUT = str(tmp_path)
+    g = load(golden_dir, "super_subset_n203")
+    path = ex.export(os.path.join(golden_dir, "super_subset_n203.npz"))
+    raw = np.fromfile(path, "<i8", 4)
+    natoms, nframes, nidx, cpus = (int(v) for v in raw)
+    assert (natoms, nframes, nidx, cpus) == (g["ref"].shape[0], g["frames"].shape[0], g["idx"].size, ex.CPUS)
+    body = np.fromfile(path, "<f8", offset=32, count=3 * natoms * (1 + nframes))
+    assert np.array_equal(body[: 3 * natoms].reshape(natoms, 3), g["ref"].astype(np.float64))
+    assert np.array_equal(body[3 * natoms:].reshape(nframes, natoms, 3), g["frames"].astype(np.float64))
+    assert np.array_equal(np.fromfile(path, "<i8", offset=32 + 8 * body.size), g["idx"])
+
+
+@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
+def test_go_reference_outputs(golden_dir, name):
+    """Pins the oracle against the real goChem when somebody with a Go toolchain has run oracle/go_regen (this image has none,
+    so the files are absent and the oracle stays 'parity unpinned'): BASELINE.json's tolerances, 1e-9 A and 1e-10."""
+    path = os.path.join(golden_dir, "go_reference", name + ".go.bin")
+    if not os.path.exists(path):
+        pytest.skip("no output of the Go reference committed (oracle/go_regen/main.go needs a Go toolchain)")
+    ex = _go_regen()
+    g = load(golden_dir, name)
+    ref, frames = g["ref"].astype(np.float64), g["frames"].astype(np.float64)
+    idx = g["idx"] if g["idx"].size else None
+    go = ex.read_outputs(path, ref.shape[0], frames.shape[0])
+    work = frames.copy()
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(work, ref, idx, write_back=True)
+    assert np.abs(rm - go["rmsd"]).max() < 1e-9
+    assert np.abs(rot - go["rot"]).max() < 1e-10
+    assert np.abs(t1 - go["trans1"]).max() < 1e-9 and np.abs(t2 - go["trans2"]).max() < 1e-9
+    assert np.abs(work - go["moved"]).max() < 1e-9
+    sel = idx if idx is not None else np.arange(ref.shape[0])
+    want, total = oracle.rmsd_traj(frames, ref, sel, cpus=ex.CPUS)
+    assert total == go["frames_read"]
+    assert np.abs(want - go["rmsdtraj"]).max() < 1e-9
+
+
 @pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
 def test_c_oracle_matches_golden(golden_dir, name):
     g = load(golden_dir, name)
