@@ -49,6 +49,10 @@ constexpr int kSolverWarps = 3;
 constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
 constexpr int kMaxStages = 8;
 constexpr int kMaxSlots = 13;            // exchange slots (>= 2*D+1 with D <= 6, and > kSolverWarps)
+constexpr int kResidentSlots = 7;        // plans that keep the part resident run at most D = 3 frames ahead
+constexpr int kRedRow = 33;              // transposition scratch of the per-frame reduction: [13 sums][32 lanes], rows padded by one
+constexpr int kRedWarpDoubles = 13 * kRedRow;
+constexpr size_t kRedScratchBytes = ((sizeof(double) * kRedWarpDoubles * kConsumerWarps + 127) / 128) * 128;
 constexpr int kMaxCluster = 8;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -74,16 +78,21 @@ __device__ long long g_trace[8][512];
 #define TRACE(row, j) do {} while (0)
 #endif
 
-struct __align__(16) Shared {
+template <int NSLOTS>
+struct __align__(16) SharedT {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t part_full[kMaxSlots];        // cluster -> solver: every CTA's partial sums of a frame have landed
-    uint64_t solved[kMaxSlots];           // solver -> consumers: xf[slot] holds the frame's transform
-    double partials[kMaxSlots][kMaxCluster][14];   // 12 sums + sum w|a|^2
-    double xf[kMaxSlots][16];             // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
-    double red[kMaxSlots][kConsumerWarps][14];   // [..][12] = squared error of the frame D iterations earlier
-    unsigned int red_count[kMaxSlots];    // consumer warps that have delivered red[slot]; the last one sums and pushes
+    uint64_t part_full[NSLOTS];           // cluster -> solver: every CTA's partial sums of a frame have landed
+    uint64_t solved[NSLOTS];              // solver -> consumers: xf[slot] holds the frame's transform
+    double partials[NSLOTS][kMaxCluster][14];   // 12 sums + sum w|a|^2
+    double xf[NSLOTS][16];                // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
+    double red[NSLOTS][kConsumerWarps][14];     // per-warp totals of a frame's sums
+    unsigned int red_count[NSLOTS];       // consumer warps that have delivered red[slot]; the last one sums and pushes
 };
+// bytes in front of the stage ring: barriers and exchange slots, then the reduction scratch
+constexpr size_t fixed_smem(bool resident) {
+    return ((resident ? sizeof(SharedT<kResidentSlots>) : sizeof(SharedT<kMaxSlots>)) + 127) / 128 * 128 + kRedScratchBytes;
+}
 
 // sqrt of a non-negative double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
 // error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
@@ -161,15 +170,17 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
 template <int K, bool MASKED, bool DEV, bool RESIDENT>
 __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NS = RESIDENT ? kResidentSlots : kMaxSlots;
+    using Shared = SharedT<NS>;
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
     constexpr int kStageDoubles = 3 * K * kConsumers;
-    double* stage_base = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 127) / 128) * 128);
+    double* red_scratch = reinterpret_cast<double*>(smem_raw + fixed_smem(RESIDENT) - kRedScratchBytes);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + fixed_smem(RESIDENT));
 
     const SuperParams& p = cp.p;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int C = cp.cluster, S = cp.stages, D = cp.depth, G = cp.nclusters;
-    constexpr int NS = kMaxSlots;
     const uint32_t rank = cluster_ctarank();
     const long cid = cluster_id_x();
     const int part0 = (int)rank * cp.part;                       // first atom of this CTA's part
@@ -360,21 +371,28 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 }
                 // ---- warp totals -> red[slot]; the last warp to deliver sums the 8 warps in fixed order and pushes
                 //      the CTA's partial sums to every CTA of the cluster ----
-                double t0, t1;
-                warp_reduce12(acc, lane, t0, t1);
-                double aa = aa0 + aa1;
-                if (!DEV) {
+                // The 32 x 13 per-lane sums are transposed through the warp's own scratch (rows padded to 33: stores and loads
+                // are conflict-free): lane q + 16 h adds half h of sum q in a fixed tree and one shuffle joins the halves --
+                // 13 stores, 16 loads and one shuffle per lane instead of a 15-shuffle butterfly with its selects.
+                {
+                    double* tr = red_scratch + warp * kRedWarpDoubles;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) aa += shx(aa, o);
+                    for (int q = 0; q < 12; q++) tr[q * kRedRow + lane] = acc[q];
+                    if (!DEV) tr[12 * kRedRow + lane] = aa0 + aa1;
+                    __syncwarp();
+                    constexpr int NQ = DEV ? 12 : 13;
+                    const int q = lane & 15;
+                    double v = 0.0;
+                    if (q < NQ) {
+                        const double* row = tr + q * kRedRow + (lane & 16);
+                        const double s0 = row[0] + row[1], s1 = row[2] + row[3], s2 = row[4] + row[5], s3 = row[6] + row[7];
+                        const double s4 = row[8] + row[9], s5 = row[10] + row[11], s6 = row[12] + row[13], s7 = row[14] + row[15];
+                        v = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+                    }
+                    v += __shfl_down_sync(0xffffffffu, v, 16);
+                    if (lane < 13) sh.red[slot1][warp][lane] = v;   // DEV: entry 12 is 0 (no sum w|a|^2 in that mode)
                 }
-                double* red = sh.red[slot1][warp];
-                if (lane == 0) red[12] = aa;
-                if ((lane & 3) == 0) {
-                    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
-                    red[6 * b4 + 3 * b3 + 2 * b2] = t0;
-                    if (b2 == 0) red[6 * b4 + 3 * b3 + 1] = t1;
-                }
-                __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below
+                __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below; the scratch is free again
                 if (tid == 0) TRACE(7, j);
                 unsigned int prev = 0;
                 if (lane == 0) prev = atom_add_acq_rel_cta(&sh.red_count[slot1], 1u);
@@ -468,7 +486,6 @@ int g_force_explicit = 0;
 //  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
 //  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
 bool make_plan(int np, bool heavy, Plan* pl) {
-    const size_t fixed = ((sizeof(Shared) + 127) / 128) * 128;
     // Measured on B200 (profiles/r1_tuning.md).  Fit-only passes skip pass 2 for almost every frame, so the stage can be
     // released right after pass 1 (pass 2, when needed, re-reads the part from L2): two stages of the fattest part that
     // fits win (up to 14 atoms per thread, fewest CTAs per frame, clusters of <= 3 tile the GPCs almost exactly).
@@ -476,6 +493,7 @@ bool make_plan(int np, bool heavy, Plan* pl) {
     // thread, >= 3 stages.
     const int resident = g_tune_resident >= 0 ? g_tune_resident : (heavy ? 1 : 0);
     const int kmax = resident ? (heavy ? 10 : 10) : 14;
+    const size_t fixed = fixed_smem(resident != 0);
     for (int c = 1; c <= kMaxCluster; c++) {
         if (g_tune_cluster && c != g_tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
@@ -493,7 +511,7 @@ bool make_plan(int np, bool heavy, Plan* pl) {
         int depth;
         if (resident) {
             depth = stages - 2 > 2 ? 2 : stages - 2;
-            if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && g_tune_depth <= 6) depth = g_tune_depth;
+            if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && 2 * g_tune_depth + 1 <= kResidentSlots) depth = g_tune_depth;
         } else {
             depth = kinst <= 6 ? 6 : 3;   // costs no shared memory here: only the exchange slots
             if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
