@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCB_LIB") or os.path.join(HERE, "lib", "libgochem_b200.so")   # GCB_LIB: tuning builds (tools/)
 HEADER = os.path.join(HERE, "..", "include", "gochem_b200.h")
 
-F64_AOS, F32_AOS, F32_SOA = 0, 1, 2
+F64_AOS, F32_AOS, F32_SOA, I32_AOS = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_CLUSTER = 0, 1, 2
 OK, ERR_SHAPE, ERR_INDEXES, ERR_SVD, ERR_ALLOC, ERR_CUDA, ERR_ARG, EOF = 0, -1, -2, -4, -5, -7, -8, 11
 
@@ -195,7 +195,7 @@ class DeviceTraj:
 
     # --- data movement ---
     def upload(self, frames: np.ndarray, first: int = 0, layout: int = F64_AOS, scale: float = 1.0):
-        dt = np.float64 if layout == F64_AOS else np.float32
+        dt = np.float64 if layout == F64_AOS else np.int32 if layout == I32_AOS else np.float32
         a = np.ascontiguousarray(frames, dtype=dt)
         n = a.size // (3 * self.natoms)
         check(self.lib.gcb_traj_upload(self.h, first, _ptr(a), n, layout, scale))

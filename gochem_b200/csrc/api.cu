@@ -273,7 +273,7 @@ int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int
     int rc = check_window(t, first, nframes, false);
     if (rc) return rc;
     if (!host && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
-    if (layout < GCB_F64_AOS || layout > GCB_F32_SOA) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
+    if (layout < GCB_F64_AOS || layout > GCB_I32_AOS) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     const size_t fb = host_frame_bytes(t, layout);
     const long per = (long)(t->stage_bytes / fb);
@@ -295,7 +295,7 @@ int gcb_traj_upload_async(gcb_traj* t, long first, const void* pinned, long nfra
     int rc = check_window(t, first, nframes, false);
     if (rc) return rc;
     if (slot < 0 || slot > 1) { set_error("slot must be 0 or 1"); return GCB_ERR_ARG; }
-    if (layout < GCB_F64_AOS || layout > GCB_F32_SOA) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
+    if (layout < GCB_F64_AOS || layout > GCB_I32_AOS) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
     const size_t bytes = host_frame_bytes(t, layout) * (size_t)nframes;
     if (bytes > t->stage_bytes) { set_error("async upload of %zu bytes exceeds the %zu-byte staging slot", bytes, t->stage_bytes); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));

@@ -4,13 +4,14 @@
 // 16).  Host layouts: float64 AoS (v3.Matrix, /root/reference/v3/gonum.go:54-58), float32 AoS
 // (libxdrfile output, traj/xtc/libgoxtc.c:87-104, widened and scaled by 10 in
 // traj/xtc/xtc.go:129-134), float32 SoA planes (DCD records, traj/dcd/dcd.go:380-413, widened
-// in :302-307).  The widening / scaling / transposition the reference does on the CPU per
+// in :302-307), int32 AoS fixed point (STF text lines, traj/stf/stf.go:324-345, divided by 10^prec).  The widening / scaling / transposition the reference does on the CPU per
 // element happens here, after the raw bytes crossed PCIe.
 #include "common.cuh"
 
 namespace gcb {
 
-template <typename T, bool SOA>
+// DIV: fixed-point sources (STF) divide by the scale after widening, float64(f) / p as traj/stf/stf.go:341 does.
+template <typename T, bool SOA, bool DIV = false>
 __global__ void __launch_bounds__(256) upload_convert_kernel(const T* __restrict__ src, double* __restrict__ dst,
                                                             int natoms, int np, long nframes, double scale) {
     const long total = nframes * (long)np;
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(256) upload_convert_kernel(const T* __restrict
                 z = (double)s[3L * i + 2];
             }
             // the reference multiplies after widening: 10*float64(c) (xtc.go:131)
-            if (scale != 1.0) { x = scale * x; y = scale * y; z = scale * z; }
+            if (DIV) { x = x / scale; y = y / scale; z = z / scale; }
+            else if (scale != 1.0) { x = scale * x; y = scale * y; z = scale * z; }
         }
         double* d = dst + f * 3L * np;
         d[i] = x;
@@ -99,6 +101,10 @@ int launch_upload_convert(gcb_traj* t, cudaStream_t s, const void* d_src, long f
             break;
         case GCB_F32_SOA:
             upload_convert_kernel<float, true><<<grid, 256, 0, s>>>((const float*)d_src, dst, t->natoms, t->np, nframes, scale);
+            break;
+        case GCB_I32_AOS:
+            if (scale == 0.0) { set_error("fixed-point layout needs a non-zero divisor"); return GCB_ERR_ARG; }
+            upload_convert_kernel<int, false, true><<<grid, 256, 0, s>>>((const int*)d_src, dst, t->natoms, t->np, nframes, scale);
             break;
         default:
             set_error("unknown host layout %d", layout);

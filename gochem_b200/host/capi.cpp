@@ -2,8 +2,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 
+#include "../../include/gochem_b200.h"
 #include "../../include/gochem_host.h"
 #include "../csrc/kabsch3.cuh"
 #include "gochem.hpp"
@@ -446,6 +448,78 @@ int gch_xtc_read(const char* path, double* out, long cap, long* nframes, int* na
         if (n < cap) memcpy(out + (size_t)n * fsz, m.data(), sizeof(double) * fsz);
         n++;
     }
+    *nframes = n;
+    return 0;
+}
+
+
+int gch_stf_zstd_available(void) { return stf::StfR::ZstdAvailable() ? 1 : 0; }
+
+/* header_text: "key=value\n" lines or NULL */
+int gch_stf_write(const char* path, const double* frames, long nframes, int natoms, int level, const char* header_text, const double* box9) {
+    std::map<std::string, std::string> header;
+    if (header_text) {
+        std::string h(header_text);
+        size_t a = 0;
+        while (a < h.size()) {
+            size_t b = h.find('\n', a);
+            if (b == std::string::npos) b = h.size();
+            const std::string line = h.substr(a, b - a);
+            const size_t eq = line.find('=');
+            if (eq != std::string::npos) header[line.substr(0, eq)] = line.substr(eq + 1);
+            a = b + 1;
+        }
+    }
+    std::unique_ptr<stf::StfW> w;
+    if (Error e = stf::StfW::NewWriter(path, natoms, header, &w, level)) return fail(e);
+    v3::Matrix m = v3::Matrix::Zeros(natoms);
+    std::vector<double> box;
+    if (box9) box.assign(box9, box9 + 9);
+    for (long f = 0; f < nframes; f++) {
+        memcpy(m.data(), frames + (size_t)f * 3 * (size_t)natoms, sizeof(double) * 3 * (size_t)natoms);
+        if (Error e = w->WNext(&m, box9 ? &box : nullptr)) return fail(e);
+    }
+    w->Close();
+    return 0;
+}
+
+/* use_raw = 1: through the int32 feed the device staging uses, divided by its scale on the host as the device kernel does;
+ * header_text (cap bytes) receives the header map as sorted "key=value\n" lines; box9 the box of the LAST frame read */
+int gch_stf_read(const char* path, double* out, long cap, long* nframes, int* natoms, int use_raw, char* header_text, size_t header_cap,
+                 double* box9) {
+    std::unique_ptr<stf::StfR> x;
+    std::map<std::string, std::string> header;
+    if (Error e = stf::StfR::New(path, &x, &header)) return fail(e);
+    if (header_text && header_cap) {
+        std::string h;
+        for (const auto& kv : header) h += kv.first + "=" + kv.second + "\n";
+        snprintf(header_text, header_cap, "%s", h.c_str());
+    }
+    *natoms = x->Len();
+    const size_t fsz = 3 * (size_t)x->Len();
+    long n = 0;
+    v3::Matrix m = v3::Matrix::Zeros(x->Len());
+    std::vector<int32_t> raw(fsz);
+    std::vector<double> box(9, 0.0);
+    for (;;) {
+        Error e;
+        if (use_raw) {
+            int layout = 0;
+            double scale = 0;
+            e = x->NextRaw(reinterpret_cast<float*>(raw.data()), &layout, &scale);
+            if (!e && layout != GCB_I32_AOS) return fail(Error("stf raw feed announced layout " + std::to_string(layout)));
+            if (!e) for (size_t i = 0; i < fsz; i++) m.data()[i] = (double)raw[i] / scale;
+        } else {
+            e = x->Next(&m, box9 ? &box : nullptr);
+        }
+        if (e) {
+            if (!e.last_frame) return fail(e);
+            break;
+        }
+        if (n < cap) memcpy(out + (size_t)n * fsz, m.data(), sizeof(double) * fsz);
+        n++;
+    }
+    if (box9) memcpy(box9, box.data(), sizeof(double) * 9);
     *nframes = n;
     return 0;
 }

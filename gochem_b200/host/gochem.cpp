@@ -1334,8 +1334,14 @@ Error opentraj(const std::string& name, std::unique_ptr<chem::ConcTraj>* out) {
         *out = std::move(x);
         return Error();
     }
-    if (ext == "stf" || ext == "pdb")
-        return Error("Trajectory format '" + ext + "' is decoded by a third-party CPU codec that is outside this build (SURVEY.md §2); "
+    if (ext == "stf") {   // lovo.go:161-162
+        std::unique_ptr<stf::StfR> x;
+        if (Error e = stf::StfR::New(name, &x)) return e;
+        *out = std::move(x);
+        return Error();
+    }
+    if (ext == "pdb")
+        return Error("Trajectory format 'pdb' (multi-model PDB text, chem.PDBFileRead) is outside this build (SURVEY.md §2); "
                      "feed its frames through a chem::ConcTraj and call align::RMSDTraj");
     return Error("Trajectory fromat not supported. Must have concurrent read support in goChem");  // lovo.go:168-169
 }

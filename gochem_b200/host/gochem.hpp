@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -268,6 +269,63 @@ class XTCObj : public chem::Traj, public chem::ConcTraj {
 };
 
 }  // namespace xtc
+
+namespace stf {
+
+// goChem's own "simple trajectory format" (traj/stf/stf.go): text lines of three fixed-point integers per atom
+// ("%d %d %d\n", coordinate * 100 rounded to even, stf.go:216-225), a line starting with '*' after every frame
+// (optionally followed by nine box numbers), a header of key=value lines closed by "** natoms", all of it inside one
+// compressed stream chosen by the LAST letter of the file name (stf.go:245-285): 'z' gzip, 'r' raw deflate, 'l' LZW,
+// anything else ("stf", "sts") zstd.  gzip and deflate are decoded with zlib, zstd with libzstd bound by dlopen
+// (GOCHEM_ZSTD names it, else libzstd.so.1); LZW files are refused with an error.  The decompressor and the text
+// parser stay on the CPU; the raw feed hands the device the integers as they were parsed (GCB_I32_AOS, divisor 100)
+// and the division float64(f)/p of stf.go:341 happens there.
+//
+// Quirk kept: both reader and writer try to honour a "prec" header entry but the test on strconv.Atoi's error is
+// inverted (stf.go:174-181, 304-313), so the precision is 2 decimals (p = 100) whatever the header says.
+class ByteStream;   // decompressed bytes of the file (defined in gochem.cpp)
+class ByteSink;     // compressor in front of the file
+
+class StfR : public chem::Traj, public chem::ConcTraj {
+  public:
+    static Error New(const std::string& name, std::unique_ptr<StfR>* out, std::map<std::string, std::string>* header = nullptr);  // stf.go:230-318
+    ~StfR() override;
+    bool Readable() const override { return readable_; }
+    Error Next(v3::Matrix* output, std::vector<double>* box = nullptr) override;   // stf.go:352-424
+    Error NextConc(std::vector<v3::Matrix*>& frames) override;                     // stf.go:440-455
+    int Len() const override { return natoms_; }
+    void Close() override;                                                         // stf.go:427-434
+    bool HasRawFeed() const override { return true; }
+    Error NextRaw(float* dst, int* layout, double* scale) override;                // int32 x y z per atom, divisor 100
+    static bool ZstdAvailable(std::string* why = nullptr);
+
+  private:
+    Error nextInto(int32_t* ints, v3::Matrix* output, std::vector<double>* box);
+    std::string filename_;
+    std::unique_ptr<ByteStream> h_;
+    int natoms_ = -1;
+    bool readable_ = false;
+};
+
+class StfW {
+  public:
+    // stf.go:113-190.  level: flate / gzip level (the reference's default 11 is out of zlib's range and is clamped to 9;
+    // zstd files use its best-compression preset as the reference does)
+    static Error NewWriter(const std::string& name, int natoms, const std::map<std::string, std::string>& header, std::unique_ptr<StfW>* out,
+                           int level = 11);
+    ~StfW();
+    Error WNext(const v3::Matrix* coord, const std::vector<double>* box = nullptr);   // stf.go:64-110
+    int Len() const { return natoms_; }
+    void Close();                                                                    // stf.go:39-50
+
+  private:
+    std::string filename_;
+    std::unique_ptr<ByteSink> h_;
+    int natoms_ = 0;
+    bool writeable_ = false;
+};
+
+}  // namespace stf
 
 namespace solv {
 

@@ -339,3 +339,32 @@ def xtc_read(path, cap_frames, natoms, raw=False):
     if rc:
         raise _err(rc)
     return out[: min(nf.value, cap_frames)], nf.value, na.value
+
+
+# ---- traj/stf: goChem's own text format inside a compressed stream (zlib for .stz / .str, libzstd through dlopen for .stf) ----
+def stf_zstd_available():
+    return bool(load().gch_stf_zstd_available())
+
+
+def stf_write(path, frames, level=6, header=None, box=None):
+    f = np.ascontiguousarray(frames, dtype=np.float64)
+    text = None if not header else "".join(f"{k}={v}\n" for k, v in header.items()).encode()
+    b = None if box is None else np.ascontiguousarray(box, dtype=np.float64)
+    rc = load().gch_stf_write(path.encode(), _d(f), C.c_long(f.shape[0]), f.shape[1], level, text, _d(b) if b is not None else None)
+    if rc:
+        raise _err(rc)
+
+
+def stf_read(path, cap_frames, natoms, raw=False, want_box=False):
+    """-> (frames, frames in the file, atoms per frame, header dict[, box of the last frame])"""
+    out = np.zeros((cap_frames, natoms, 3))
+    nf, na = C.c_long(0), C.c_int(0)
+    head = C.create_string_buffer(4096)
+    box = np.zeros(9)
+    rc = load().gch_stf_read(path.encode(), _d(out), C.c_long(cap_frames), C.byref(nf), C.byref(na), int(raw), head, C.c_size_t(4096),
+                             _d(box) if want_box else None)
+    if rc:
+        raise _err(rc)
+    header = dict(line.split("=", 1) for line in head.value.decode().splitlines() if "=" in line)
+    res = (out[: min(nf.value, cap_frames)], nf.value, na.value, header)
+    return res + (box,) if want_box else res

@@ -38,6 +38,7 @@ extern "C" {
 #define GCB_F64_AOS 0 /* float64 [frame][atom][xyz]  -- v3.Matrix.RawSlice (v3/gonum.go:93-95) */
 #define GCB_F32_AOS 1 /* float32 [frame][atom][xyz]  -- libxdrfile output (libgoxtc.c:87-104) */
 #define GCB_F32_SOA 2 /* float32 [frame][xyz][atom]  -- DCD records (dcd.go:380-413) */
+#define GCB_I32_AOS 3 /* int32 [frame][atom][xyz], fixed point -- STF lines (traj/stf/stf.go:324-345); coordinate = float64(value) / scale */
 
 /* kernel variants (gcb_set_kernel_variant): AUTO picks the fastest one the shape allows */
 #define GCB_KERNEL_AUTO 0

@@ -89,6 +89,18 @@ int gch_xtc_available(void);
 int gch_xtc_write(const char *path, const double *frames_aos, long nframes, int natoms);
 int gch_xtc_read(const char *path, double *out_aos, long cap_frames, long *nframes, int *natoms, int use_raw);
 
+/* traj/stf (goChem's own text-in-a-compressed-stream format, traj/stf/stf.go).  The codec follows the last letter of the
+ * file name as in the reference: 'z' gzip, 'r' raw deflate (zlib), anything else zstd (libzstd through dlopen, GOCHEM_ZSTD
+ * names it); gch_stf_zstd_available: 1 when that library could be loaded.  gch_stf_write: frames -> file through StfW
+ * (level: flate / gzip level; the reference's default 11 is rejected by those codecs there too).  gch_stf_read: frames back
+ * through StfR.Next (use_raw = 0) or through the raw int32 feed divided by its scale on the host exactly as the device
+ * kernel does (GCB_I32_AOS). */
+int gch_stf_zstd_available(void);
+int gch_stf_write(const char *path, const double *frames_aos, long nframes, int natoms, int level, const char *header_text,
+                  const double *box9);
+int gch_stf_read(const char *path, double *out_aos, long cap_frames, long *nframes, int *natoms, int use_raw, char *header_text,
+                 size_t header_cap, double *box9);
+
 /* solv (solv/solvation.go): MDFFromCDF (:317-352), EllipsoidAxes (:39-63; masses NULL = unit masses), and ConcMolRDF
  * (:140-218) on a DCD file.  Topology: molnames / chains (natoms C strings), molids, masses (0 = unknown -> error, as
  * Topology.Masses); coords0 = mol.Coords[0].  rdf / cumulative: (int)(end / step) doubles each.  window_frames > 0 streams

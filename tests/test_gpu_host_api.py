@@ -79,8 +79,12 @@ def test_rmsdtraj_on_a_dcd_file(tmp_path):
     # no such file (or no libxdrfile on this host): an error, as opentraj reports it (lovo.go:157-160)
     with pytest.raises(H.GoChemError, match="libxdrfile|Probem opening"):
         H.RMSDTraj(str(tmp_path / "x.xtc"), ref, idx, 4)
-    with pytest.raises(H.GoChemError, match="not supported|outside this build"):
+    with pytest.raises(H.GoChemError, match="no such file|libzstd"):      # traj/stf is opened like the others (lovo.go:161-162)
         H.RMSDTraj(str(tmp_path / "x.stf"), ref, idx, 4)
+    with pytest.raises(H.GoChemError, match="not supported|outside this build"):
+        H.RMSDTraj(str(tmp_path / "x.pdb"), ref, idx, 4)
+    with pytest.raises(H.GoChemError, match="not supported"):
+        H.RMSDTraj(str(tmp_path / "x.trr"), ref, idx, 4)
 
 
 def test_sharded_rmsdtraj_partials_add_up(tmp_path):
@@ -173,3 +177,26 @@ def test_rmsdtraj_on_an_xtc_file(tmp_path):
         got, n = (H.RMSDTrajStreamed(p, ref, idx, cpus, window) if window else H.RMSDTraj(p, ref, idx, cpus))
         want, total = oracle.rmsd_traj(decoded, ref, idx, cpus)
         assert n == total and np.abs(got - want).max() < 1e-9
+
+
+@pytest.mark.parametrize("ext", ["stf"])      # opentraj knows the extension "stf" only (lovo.go:161), i.e. the zstd form
+def test_rmsdtraj_and_lovo_on_an_stf_file(tmp_path, ext):
+    """traj/stf: the integers of the text lines go to the device as parsed (GCB_I32_AOS) and are divided by 100 there; the frames
+    the device sees equal float64(f) / 100 of stf.go:341 bit for bit, so RMSDTraj on the file matches the oracle on the decoded
+    frames.  zstd through libzstd (skipped where it does not load); the gzip / deflate forms are covered on the CPU
+    (tests/test_host_logic.py)."""
+    if ext == "stf" and not H.stf_zstd_available():
+        pytest.skip("libzstd is not loadable on this host")
+    ref, frames = synth.make_case(150, 42)
+    p = str(tmp_path / ("traj." + ext))
+    H.stf_write(p, frames, level=6)
+    decoded, nf, na, _ = H.stf_read(p, 50, 150)
+    assert (nf, na) == (42, 150) and np.array_equal(decoded, np.rint(frames * 100.0) / 100.0)
+    idx = np.arange(0, 150, 2)
+    for cpus, window in [(4, 0), (5, 0), (4, 8)]:
+        got, n = (H.RMSDTrajStreamed(p, ref, idx, cpus, window) if window else H.RMSDTraj(p, ref, idx, cpus))
+        want, total = oracle.rmsd_traj(decoded, ref, idx, cpus)
+        assert n == total and np.abs(got - want).max() < 1e-10
+    got = H.LOVO(p, ref, 6)
+    want = oracle.lovo(decoded, ref, list(range(150)), 6, less_than_rmsd=1.0, minimum_n=10)
+    assert got["N"] == want["N"] and list(got["Natoms"]) == list(want["Natoms"]) and got["Iterations"] == want["Iterations"]

@@ -170,6 +170,13 @@ def test_host_layouts_and_scale():
     t.upload(frames[:2], first=3)
     d = t.download()
     assert np.array_equal(d[3:], frames[:2])
+    # STF fixed point: int32 per coordinate, float64(f) / 100 on the device (traj/stf/stf.go:341), bit for bit
+    ints = np.rint(frames * 100.0).astype(np.int32)
+    ints[0, 0] = [2147483647, -2147483648, 7]
+    t.upload(ints, layout=_lib.I32_AOS, scale=100.0)
+    assert np.array_equal(t.download(), ints.astype(np.float64) / 100.0)
+    with pytest.raises(_lib.GcbError):
+        t.upload(ints, layout=_lib.I32_AOS, scale=0.0)
     t.close()
 
 

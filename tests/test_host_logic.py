@@ -298,3 +298,116 @@ def test_mdf_from_cdf_matches_oracle():
     assert a[-1] == 1.0
     with pytest.raises(H.GoChemError):
         H.MDFFromCDF(cdf, 17, 0.9, 1.2, 0.1)
+
+
+def _stf_text(frames, natoms_line=True, header=None, box=None):
+    """An STF stream as the reference's writer lays it out (stf.go:64-110, 165-189): header lines, '** natoms', per frame
+    one '%d %d %d' line per atom (coordinate * 100 rounded half to even) and a line starting with '*'."""
+    out = []
+    for k, v in (header or {}).items():
+        out.append(f"{k}={v}\n")
+    out.append(f"** {frames.shape[1]}\n")
+    for fr in frames:
+        for x, y, z in np.rint(fr * 100.0).astype(np.int64):
+            out.append(f"{x} {y} {z}\n")
+        out.append("*\n" if box is None else "* " + " ".join("%4.2f" % b for b in box) + "\n")
+    return "".join(out).encode()
+
+
+def test_stf_reader_against_files_written_by_python(tmp_path):
+    """traj/stf mirror: files built here with Python's gzip / zlib (the 'z' and 'r' forms of stf.go:245-285) read back through
+    StfR.Next and through the raw int32 feed of the device staging: float64(f) / 100 exactly (stf.go:341)."""
+    import gzip
+    import zlib
+
+    rng = np.random.default_rng(7)
+    frames = rng.normal(0, 30, (9, 37, 3))
+    frames[0, 0] = [0.005, 0.015, -0.025]          # ties: rounded half to even -> 0, 2, -2 hundredths
+    want = np.rint(frames * 100.0) / 100.0
+    text = _stf_text(frames, header={"origin": "python", "prec": "3"}, box=[10, 0, 0, 0, 20.5, 0, 0, 0, 30])
+    pz = str(tmp_path / "t.stz")
+    with gzip.open(pz, "wb") as f:
+        f.write(text)
+    pr = str(tmp_path / "t.str")
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    with open(pr, "wb") as f:
+        f.write(co.compress(text) + co.flush())
+    for p in (pz, pr):
+        got, nf, na, header, box = H.stf_read(p, 20, 37, want_box=True)
+        assert (nf, na) == (9, 37) and np.array_equal(got, want)
+        assert header == {"origin": "python", "prec": "3"}      # the "prec" entry is read and ignored (stf.go:311-318): p stays 100
+        assert np.array_equal(box, [10, 0, 0, 0, 20.5, 0, 0, 0, 30])
+        raw, nf2, _, _ = H.stf_read(p, 20, 37, raw=True)
+        assert nf2 == 9 and np.array_equal(raw, want)
+    assert want[0, 0].tolist() == [0.0, 0.02, -0.02]
+    # two gzip members back to back read as one stream (gzip.Reader's default)
+    pm = str(tmp_path / "multi.stz")
+    cut = text.index(b"*\n") + 2 if b"*\n" in text else len(text) // 2
+    with open(pm, "wb") as f:
+        f.write(gzip.compress(text[: len(text) // 2]) + gzip.compress(text[len(text) // 2:]))
+    got, nf, _, _ = H.stf_read(pm, 20, 37)
+    assert nf == 9 and np.array_equal(got, want)
+
+
+def test_stf_writer_round_trip_and_text_layout(tmp_path):
+    """StfW writes what the reference writes ('%d %d %d' lines, '*' terminators, '** natoms' after the header), readable by
+    Python's gzip, and the zstd form ('.stf', the default codec) round-trips through libzstd where that library loads."""
+    import gzip
+
+    rng = np.random.default_rng(8)
+    frames = rng.normal(0, 25, (6, 50, 3))
+    want = np.rint(frames * 100.0) / 100.0
+    p = str(tmp_path / "w.stz")
+    H.stf_write(p, frames, level=5, header={"a": "1", "b": "two"})
+    with gzip.open(p, "rb") as f:
+        assert f.read() == _stf_text(frames, header={"a": "1", "b": "two"})
+    got, nf, na, header = H.stf_read(p, 10, 50)
+    assert (nf, na, header) == (6, 50, {"a": "1", "b": "two"}) and np.array_equal(got, want)
+    H.stf_write(str(tmp_path / "w.str"), frames, level=9)
+    got, nf, _, _ = H.stf_read(str(tmp_path / "w.str"), 10, 50)
+    assert nf == 6 and np.array_equal(got, want)
+    # the reference's default level 11 is refused by flate / gzip there as well (stf.go:115, 131-135)
+    with pytest.raises(H.GoChemError, match="invalid compression level"):
+        H.stf_write(str(tmp_path / "bad.stz"), frames, level=11)
+    with pytest.raises(H.GoChemError, match="LZW"):
+        H.stf_write(str(tmp_path / "bad.stl"), frames)
+    if H.stf_zstd_available():
+        pf = str(tmp_path / "w.stf")
+        H.stf_write(pf, frames, level=11, box=[1, 2, 3, 4, 5, 6, 7, 8, 9])
+        got, nf, _, _, box = H.stf_read(pf, 10, 50, want_box=True)
+        assert nf == 6 and np.array_equal(got, want) and np.array_equal(box, np.arange(1.0, 10.0))
+
+
+def test_stf_reader_errors(tmp_path):
+    """Malformed streams fail where the reference fails (stf.go:324-345, 352-389): field counts, non-integers, a missing
+    terminator, a stream that ends inside a frame; a missing file; the end of the trajectory is a LastFrameError (nf counts)."""
+    import gzip
+
+    def write(name, text):
+        p = str(tmp_path / name)
+        with gzip.open(p, "wb") as f:
+            f.write(text)
+        return p
+
+    good = b"** 2\n1 2 3\n4 5 6\n*\n"
+    got, nf, na, _ = H.stf_read(write("ok.stz", good), 4, 2)
+    assert (nf, na) == (1, 2) and np.array_equal(got[0], [[0.01, 0.02, 0.03], [0.04, 0.05, 0.06]])
+    for name, text, msg in [
+        ("few.stz", b"** 2\n1 2\n4 5 6\n*\n", "Too few fields"),
+        ("many.stz", b"** 2\n1 2 3 4\n4 5 6\n*\n", "Too many fields"),
+        ("nan.stz", b"** 2\n1 2 x\n4 5 6\n*\n", "Can't parse coordinate 2"),
+        ("float.stz", b"** 2\n1 2 3.5\n4 5 6\n*\n", "Can't parse coordinate 2"),
+        ("term.stz", b"** 2\n1 2 3\n4 5 6\n7 8 9\n*\n", "Wrong number of atoms in frame"),
+        ("cut.stz", b"** 2\n1 2 3\n4 5 6\n*\n1 2 3\n", "EOF"),
+        ("head.stz", b"no header here\n", "Malformed header"),
+        ("nat.stz", b"** many\n", "Can't read atom number"),
+    ]:
+        with pytest.raises(H.GoChemError, match=msg):
+            H.stf_read(write(name, text), 4, 2)
+    with pytest.raises(H.GoChemError, match="no such file"):
+        H.stf_read(str(tmp_path / "missing.stz"), 1, 1)
+    p = str(tmp_path / "trunc.stz")
+    with open(p, "wb") as f:
+        f.write(gzip.compress(good * 50)[:-20])       # compressed stream cut short
+    with pytest.raises(H.GoChemError):
+        H.stf_read(p, 100, 2)
