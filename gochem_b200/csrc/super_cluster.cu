@@ -124,7 +124,11 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
+#ifdef GCB_PASS2_CH
+    constexpr int CH = GCB_PASS2_CH < K ? GCB_PASS2_CH : K;   // tuning builds
+#else
     constexpr int CH = (K % 5 == 0) ? 5 : 4;   // atoms in flight per thread: enough independent chains, bounded register use
+#endif
 #pragma unroll
     for (int kb = 0; kb < K; kb += CH) {
         double x[CH], y[CH], z[CH];
