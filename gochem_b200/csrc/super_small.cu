@@ -478,7 +478,13 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
 
 int small_gather_max_atoms() { return kGatherMaxAtoms; }
 
-bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? 256 : 1280); }
+// Passes whose second sweep touches every frame (write-back, per-atom sums): warp-per-frame up to 448 atoms, the cluster kernel above
+// (tools/heavy_small_probe.py, profiles/r1_s5_heavy_small_threshold.jsonl: 300 atoms 3.49 -> 2.64 ms write-back, 3.27 -> 2.63 ms
+// per-atom sums; 400 atoms 2.63 -> 2.51 / 2.47 -> 2.08; at 512 atoms the cluster kernel wins the write-back, 2.09 against 2.32 ms)
+#ifndef GCB_SMALL_HEAVY_MAX
+#define GCB_SMALL_HEAVY_MAX 448
+#endif
+bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? GCB_SMALL_HEAVY_MAX : 1280); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)
 int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 4 * kSmallWarps; }

@@ -198,7 +198,7 @@ def test_pinned_async_upload():
     t.close()
 
 
-@pytest.mark.parametrize("natoms", [3, 33, 100, 257, 512, 513, 1500, 2048])
+@pytest.mark.parametrize("natoms", [3, 33, 100, 257, 440, 512, 513, 1500, 2048])
 def test_small_structure_kernel(natoms):
     """Structures of at most 512 atoms take the warp-per-frame kernel under KERNEL_AUTO, up to 2048 atoms its chunked form (the
     per-atom sums of those go to the cluster kernel): every mode against the oracle, with a frame count that is not a multiple of
