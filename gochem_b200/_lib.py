@@ -283,6 +283,16 @@ class DeviceTraj:
                                            comm.h if comm else None, _ptr(out)))
         return out
 
+    def peratom_dev_sum_atoms(self, ref, idx, want, first=0, nframes=None, comm: Comm | None = None):
+        """Per-atom sums for the atoms of `want` only (align.LOVO's candidates)."""
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        it, iw = _idx(idx), _idx(want)
+        out = np.empty(iw.size)
+        check(self.lib.gcb_peratom_dev_sum_atoms(self.h, first, n, _ptr(ref), _ptr(it), 0 if it is None else it.size, _ptr(iw), iw.size,
+                                                 comm.h if comm else None, _ptr(out)))
+        return out
+
     def allpairs_rmsd(self, idx=None, first=0, nframes=None, row0=0, nrows=None, fit=False):
         n = self.nframes - first if nframes is None else nframes
         nr = n - row0 if nrows is None else nrows

@@ -184,7 +184,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     if (t->stream) cudaStreamDestroy(t->stream);
     cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
     cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
-    cudaFree(t->d_devpart); cudaFree(t->d_devsum); cudaFree(t->d_refplanes);
+    cudaFree(t->d_devpart); cudaFree(t->d_devsum); cudaFree(t->d_refplanes); cudaFree(t->d_want); cudaFree(t->d_wantref);
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     cudaFree(t->d_ap_ws);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
@@ -813,4 +813,49 @@ int peratom_local(gcb_traj* tb, long first, long nframes, const double* ref_aos,
     return launch_dev_reduce(t, rows, t->d_devsum);
 }
 int peratom_finish(gcb_traj* tb) { return check_status(X(tb)); }
+
+// per-atom sums for the atoms of `want` only: d_devsum[k] belongs to want[k]
+int peratom_local_atoms(gcb_traj* tb, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want, int nwant) {
+    gcb_traj_ext* t = X(tb);
+    if (!want || nwant <= 0 || nwant > t->np) { set_error("the list of atoms asked for is empty or longer than a frame"); return GCB_ERR_ARG; }
+    for (int k = 0; k < nwant; k++)
+        if (want[k] < 0 || want[k] >= t->natoms) { set_error("atom %d of the list asked for is out of range (%d)", k, want[k]); return GCB_ERR_INDEXES; }
+    // the fit: R and trans1 of every frame (frames untouched)
+    int rc = launch_super(t, first, nframes, ref_aos, t->natoms, idx, idx, nidx, 0, false, nullptr);
+    if (rc) return rc;
+    if (nframes == 0) {
+        GCB_CUDA(cudaMemsetAsync(t->d_devsum, 0, sizeof(double) * (size_t)t->np, t->stream));
+        return GCB_OK;
+    }
+    if (nwant > t->want_cap) {
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+        cudaFree(t->d_want); cudaFree(t->d_wantref);
+        t->d_want = nullptr; t->d_wantref = nullptr; t->want_cap = 0;
+        GCB_CUDA(cudaMalloc(&t->d_want, sizeof(int) * (size_t)nwant));
+        GCB_CUDA(cudaMalloc(&t->d_wantref, sizeof(double) * 3 * (size_t)nwant));
+        t->want_cap = nwant;
+    }
+    SuperParams p;
+    fill_params(t, first, nframes, 0, &p);
+    std::vector<double> bw(3 * (size_t)nwant);
+    for (int k = 0; k < nwant; k++) {
+        const size_t i = (size_t)want[k];
+        bw[(size_t)k] = ref_aos[3 * i] - p.bbar[0];
+        bw[(size_t)nwant + k] = ref_aos[3 * i + 1] - p.bbar[1];
+        bw[2 * (size_t)nwant + k] = ref_aos[3 * i + 2] - p.bbar[2];
+    }
+    GCB_CUDA(cudaMemcpyAsync(t->d_want, want, sizeof(int) * (size_t)nwant, cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaMemcpyAsync(t->d_wantref, bw.data(), sizeof(double) * bw.size(), cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaStreamSynchronize(t->stream));   // bw and want are pageable host memory of this call
+    // partial rows are nwant long (padded to 16), not a whole frame: the workspace is counted in frame-sized rows
+    const int stride = round_up(nwant, 16);
+    const size_t part_doubles = (size_t)peratom_accum_gather_rows(t, nframes, nwant) * (size_t)stride;
+    rc = ensure_devpart(t, (part_doubles + (size_t)t->np - 1) / (size_t)t->np);
+    if (rc) return rc;
+    p.devpart = t->d_devpart;
+    int rows = 0;
+    rc = launch_peratom_accum_gather(t, p, t->d_want, nwant, t->d_wantref, stride, &rows);
+    if (rc) return rc;
+    return launch_dev_reduce_n(t, rows, stride, nwant, t->d_devsum);
+}
 }  // namespace gcb

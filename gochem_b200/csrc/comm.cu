@@ -19,6 +19,7 @@
 namespace gcb {
 int peratom_local(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, int write_back);
 int peratom_finish(gcb_traj* t);
+int peratom_local_atoms(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want, int nwant);
 
 struct NcclApi {
     void* h = nullptr;
@@ -279,6 +280,23 @@ int gcb_peratom_dev_sum(gcb_traj* t, long first, long nframes, const double* ref
         if (rc) return rc;
     }
     GCB_CUDA(cudaMemcpyAsync(sum, t->d_devsum, sizeof(double) * (size_t)t->natoms, cudaMemcpyDeviceToHost, t->stream));
+    return peratom_finish(t);
+}
+
+int gcb_peratom_dev_sum_atoms(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want,
+                              int nwant, gcb_comm* comm, double* sum_want) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    if (first < 0 || nframes < 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
+    if (!sum_want) { set_error("NULL output"); return GCB_ERR_ARG; }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    int rc = peratom_local_atoms(t, first, nframes, ref_aos, idx, nidx, want, nwant);
+    if (rc) return rc;
+    if (comm && comm->nranks > 1) {
+        if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
+        rc = allreduce_device(comm, t->d_devsum, nwant, t->stream);
+        if (rc) return rc;
+    }
+    GCB_CUDA(cudaMemcpyAsync(sum_want, t->d_devsum, sizeof(double) * (size_t)nwant, cudaMemcpyDeviceToHost, t->stream));
     return peratom_finish(t);
 }
 

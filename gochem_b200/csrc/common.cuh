@@ -89,6 +89,9 @@ struct gcb_traj {
     size_t devpart_rows = 0;
     double* d_devsum = nullptr;
     double* d_refplanes = nullptr;  // split path of large frames (transform.cu): centred template planes of ALL atoms, 3 * np
+    int* d_want = nullptr;          // gcb_peratom_dev_sum_atoms: the atoms asked for, and their compact centred template (3 * want_cap)
+    double* d_wantref = nullptr;
+    int want_cap = 0;
     // per-frame centre of mass / moment tensor (moments.cu)
     double* d_mom_w = nullptr;   // np mass plane
     double* d_mom_c = nullptr;   // 3 per frame
@@ -147,5 +150,9 @@ int small_gather_max_atoms();
 int launch_transform_frames(gcb_traj* t, const SuperParams& p);
 int peratom_accum_rows(const gcb_traj* t, long nframes);
 int launch_peratom_accum(gcb_traj* t, const SuperParams& p, const double* ref_planes, int* rows_out);
+int peratom_accum_gather_rows(const gcb_traj* t, long nframes, int nwant);
+int launch_peratom_accum_gather(gcb_traj* t, const SuperParams& p, const int* d_want, int nwant, const double* d_wantref, int stride,
+                                int* rows_out);
+int launch_dev_reduce_n(gcb_traj* t, int rows, int stride, int n, double* out);
 int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* refpairs, const int* idx, int nidx, int force_explicit);
 }  // namespace gcb

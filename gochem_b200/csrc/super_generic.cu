@@ -385,6 +385,13 @@ int launch_rmsd_nofit_gather(gcb_traj* t, const double* frames, long nframes, co
     return GCB_OK;
 }
 
+int launch_dev_reduce_n(gcb_traj* t, int rows, int stride, int n, double* out) {
+    dev_reduce_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(t->d_devpart, rows, stride, n, out);
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    return GCB_OK;
+}
+
 int launch_dev_reduce(gcb_traj* t, int rows, double* out) {
     dev_reduce_kernel<<<(t->natoms + 255) / 256, 256, 0, t->stream>>>(t->d_devpart, rows, t->np, t->natoms, out);
     GCB_LAUNCHED();

@@ -150,7 +150,81 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_kernel(const double*
     }
 }
 
+// The same sums for a chosen list of atoms only (align.LOVO reads the means of its candidate atoms only, rmsdFilter,
+// align/lovo.go:519-528): thread k of a CTA owns atom want[k], reads its three sectors per frame and nothing else.
+// bw = compact centred template of those atoms (3 x nwant); part[split][stride].
+__global__ void __launch_bounds__(kTfThreads) peratom_accum_gather_kernel(const double* __restrict__ frames, long frame_stride, int np,
+                                                                         long nframes, int nsplits, const double* __restrict__ rot,
+                                                                         const double* __restrict__ trans1, const int* __restrict__ want,
+                                                                         int nwant, const double* __restrict__ bw,
+                                                                         double* __restrict__ part, int stride) {
+    __shared__ double s_xf[kAccFrames][12];
+    const int split = blockIdx.y;
+    const long per = (nframes + nsplits - 1) / nsplits;
+    const long f0 = split * per;
+    long f1 = f0 + per;
+    if (f1 > nframes) f1 = nframes;
+    const int k = blockIdx.x * kTfThreads + threadIdx.x;
+    const bool in = k < nwant;
+    const int at = in ? want[k] : 0;
+    const double bx = in ? bw[k] : 0.0, by = in ? bw[nwant + k] : 0.0, bz = in ? bw[2L * nwant + k] : 0.0;
+    double s0 = 0.0, s1 = 0.0;   // two chains: even and odd frames of a batch
+    for (long fb = f0; fb < f1; fb += kAccFrames) {
+        const int nb = (int)((f1 - fb) < kAccFrames ? (f1 - fb) : kAccFrames);
+        __syncthreads();
+        for (int e12 = threadIdx.x; e12 < nb * 12; e12 += kTfThreads) {
+            const int ff = e12 / 12, e = e12 - ff * 12;
+            double v;
+            if (e < 9) v = rot[9 * (fb + ff) + e];
+            else {
+                const double* r = rot + 9 * (fb + ff);
+                const double* t = trans1 + 3 * (fb + ff);
+                const int col = e - 9;
+                v = fma(t[2], r[6 + col], fma(t[1], r[3 + col], t[0] * r[col]));
+            }
+            s_xf[ff][e] = v;
+        }
+        __syncthreads();
+        if (!in) continue;
+        const double* fr = frames + fb * frame_stride + at;
+#pragma unroll 4
+        for (int ff = 0; ff < nb; ff++, fr += frame_stride) {
+            const double x = __ldg(fr), y = __ldg(fr + np), z = __ldg(fr + 2L * np);
+            const double* xf = s_xf[ff];
+            const double dx = fma(z, xf[6], fma(y, xf[3], fma(x, xf[0], xf[9]))) - bx;
+            const double dy = fma(z, xf[7], fma(y, xf[4], fma(x, xf[1], xf[10]))) - by;
+            const double dz = fma(z, xf[8], fma(y, xf[5], fma(x, xf[2], xf[11]))) - bz;
+            const double d = ptx::sqrt_cubic(fma(dz, dz, fma(dy, dy, dx * dx)));
+            if (ff & 1) s1 += d; else s0 += d;
+        }
+    }
+    if (in) part[(long)split * stride + k] = s0 + s1;
+}
+
 }  // namespace
+
+int peratom_accum_gather_rows(const gcb_traj* t, long nframes, int nwant) {
+    const int tiles = (nwant + kTfThreads - 1) / kTfThreads;
+    long want = ((long)t->sm_count * 8 + tiles - 1) / tiles;
+    if (want > 512) want = 512;
+    const long by_batch = (nframes + kAccFrames - 1) / kAccFrames;   // a split of less than one batch of transforms is wasted staging
+    if (want > by_batch) want = by_batch;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+int launch_peratom_accum_gather(gcb_traj* t, const SuperParams& p, const int* d_want, int nwant, const double* d_wantref, int stride,
+                                int* rows_out) {
+    const int tiles = (nwant + kTfThreads - 1) / kTfThreads;
+    const int splits = peratom_accum_gather_rows(t, p.nframes, nwant);
+    peratom_accum_gather_kernel<<<dim3((unsigned)tiles, (unsigned)splits), kTfThreads, 0, t->stream>>>(p.frames, p.frame_stride, p.np, p.nframes, splits,
+                                                                                                       p.rot, p.trans1, d_want, nwant, d_wantref,
+                                                                                                       p.devpart, stride);
+    GCB_LAUNCHED();
+    GCB_CUDA(cudaGetLastError());
+    if (rows_out) *rows_out = splits;
+    return GCB_OK;
+}
 
 int launch_transform_frames(gcb_traj* t, const SuperParams& p) {
     const int np2 = t->np >> 1;

@@ -1096,9 +1096,18 @@ Error DeviceTrajectory::Load(chem::ConcTraj& traj, int natoms, const Options& o,
 }
 
 Error DeviceTrajectory::MeanDeviations(const v3::Matrix& ref, const std::vector<int>& indexes, const Options& o, bool write_back,
-                                       std::vector<double>* mean) {
+                                       std::vector<double>* mean, const std::vector<int>* only) {
     if (ref.NVecs() != natoms_) return Error("chem.Super: Ill formed coordinates for Superposition", {"concproc"});
     mean->assign((size_t)natoms_, 0.0);
+    if (only && !write_back && !only->empty() && 8 * only->size() <= (size_t)natoms_ && (o.comm_ || !o.allreduce_)) {
+        std::vector<double> part(only->size());
+        int rc = gcb_peratom_dev_sum_atoms(t_, 0, nlocal_, ref.data(), indexes.empty() ? nullptr : indexes.data(), (int)indexes.size(),
+                                           only->data(), (int)only->size(), o.comm_, part.data());
+        if (rc) return deviceError(rc, "RMSDTraj");
+        const double total = (double)nselected_;
+        for (size_t k = 0; k < only->size(); k++) (*mean)[(size_t)(*only)[k]] = part[k] / total;
+        return Error();
+    }
     int rc = gcb_peratom_dev_sum(t_, 0, nlocal_, ref.data(), indexes.empty() ? nullptr : indexes.data(), (int)indexes.size(),
                                  write_back ? 1 : 0, o.comm_, mean->data());
     if (rc) return deviceError(rc, "RMSDTraj");
@@ -1358,7 +1367,7 @@ Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_p
         if (dbg) fprintf(stderr, "[LOVO] iteration %d, fit on %zu atoms, local frames %ld\n", st.Iterations(), st.FitIndexes().size(), d->LocalFrames());
         if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228
         const bool wb = !o->writeTraj_.empty();
-        if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd)) return e;
+        if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd, &fullindexes)) return e;
         if (wb) {
             if (Error e = d->WriteDCD(o->writeTraj_)) return e;
             // the pass rewrote the resident frames; later passes start from the source again (the reference

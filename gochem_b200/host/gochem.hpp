@@ -469,8 +469,10 @@ class DeviceTrajectory {
     long SelectedFrames() const { return nselected_; }
     gcb_traj* Handle() { return t_; }
     // one RMSDTraj pass over the resident frames: per-atom mean deviations over ALL selected frames (all ranks)
+    // only != nullptr: the caller reads the means of these atoms alone (align.LOVO: its candidates, lovo.go:519-528); when they
+    // are at most an eighth of the frame and nothing is written back, only their sectors are read and the other entries are 0
     Error MeanDeviations(const v3::Matrix& ref, const std::vector<int>& indexes, const Options& o, bool write_back,
-                         std::vector<double>* mean);
+                         std::vector<double>* mean, const std::vector<int>* only = nullptr);
     Error WriteDCD(const std::string& name);  // local frames, as dcd.DCDWObj would (lovo.go:337-339)
 
   private:

@@ -139,6 +139,12 @@ int gcb_peratom_dist(gcb_traj *t, long frame, const double *ref_aos, int natoms_
  * ranks (all-gather + rank-ordered sum, bit-identical on every rank). */
 int gcb_peratom_dev_sum(gcb_traj *t, long first, long nframes, const double *ref_aos,
                         const int *idx, int nidx, int write_back, gcb_comm *comm, double *sum);
+/* The same sums for the atoms of `want` only: sum_want[k] belongs to atom want[k] (nwant doubles of host memory).
+ * align.LOVO looks at the means of its candidate atoms only (rmsdFilter, align/lovo.go:519-528); when those are a small
+ * part of the frame -- a protein in its solvent box -- this reads their sectors instead of streaming whole frames.
+ * Frames are left untouched. */
+int gcb_peratom_dev_sum_atoms(gcb_traj *t, long first, long nframes, const double *ref_aos, const int *idx, int nidx,
+                              const int *want, int nwant, gcb_comm *comm, double *sum_want);
 
 /* ---- all-pairs frame RMSD matrix (BASELINE configs[3]) ----
  * D[i][j] = chem.RMSD(frame_i, frame_j) over the atoms in idx (NULL = all), no superposition inside (geometric.go:

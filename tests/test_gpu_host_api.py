@@ -200,3 +200,22 @@ def test_rmsdtraj_and_lovo_on_an_stf_file(tmp_path, ext):
     got = H.LOVO(p, ref, 6)
     want = oracle.lovo(decoded, ref, list(range(150)), 6, less_than_rmsd=1.0, minimum_n=10)
     assert got["N"] == want["N"] and list(got["Natoms"]) == list(want["Natoms"]) and got["Iterations"] == want["Iterations"]
+
+
+def test_lovo_on_a_solvated_system_reads_the_candidates_only(tmp_path):
+    """A protein in its solvent box: one atom in ten is a CA, the rest never enter LOVO's bookkeeping (rmsdFilter,
+    lovo.go:519-528).  The host mirror then asks the device for the candidates' sums alone (gcb_peratom_dev_sum_atoms);
+    N, the ordered atom list, the iteration count and the candidates' mean distances equal the oracle's."""
+    natoms, nframes, cpus = 2000, 96, 8
+    ref, frames = synth.make_case(natoms, nframes, through_f32=True)
+    p = str(tmp_path / "solvated.dcd")
+    H.dcd_write(p, frames)
+    names = ["CA" if i % 10 == 0 else "OW" for i in range(natoms)]
+    chains = ["A"] * natoms
+    molids = [i // 10 + 1 for i in range(natoms)]
+    full = np.arange(0, natoms, 10)
+    want = oracle.lovo(frames, ref, full, cpus, less_than_rmsd=1.0, minimum_n=10, nthreads=8)
+    got = H.LOVO(p, ref, cpus, names=names, chains=chains, molids=molids)
+    assert got["N"] == want["N"] and got["Iterations"] == want["Iterations"] and got["FramesRead"] == want["FramesRead"]
+    assert list(got["Natoms"]) == list(want["Natoms"])
+    assert np.abs(got["RMSD"] - want["RMSD"]).max() < 1e-10

@@ -648,3 +648,24 @@ def test_large_frames_write_back_and_per_atom_sums(natoms, nidx):
     assert np.abs(got / nframes - want).max() < 1e-10
     assert np.abs(t.download() - aligned).max() < TOL_XYZ
     t.close()
+
+
+@pytest.mark.parametrize("natoms,nfit,nwant,nframes", [(9000, 300, 500, 70), (33000, 900, 1500, 33), (700, 0, 40, 129), (5000, 2000, 1, 10)])
+def test_per_atom_sums_of_chosen_atoms(natoms, nfit, nwant, nframes):
+    """gcb_peratom_dev_sum_atoms: the sums align.RMSDTraj forms, for a chosen list of atoms only (in the caller's order), against
+    the full-frame entry point and the oracle; frames stay untouched."""
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
+    rng = np.random.default_rng(natoms + nwant)
+    idx = np.sort(rng.choice(natoms, nfit, replace=False)) if nfit else None
+    want = rng.choice(natoms, nwant, replace=False)          # not sorted on purpose
+    t = device_traj(frames)
+    got = t.peratom_dev_sum_atoms(ref, idx, want)
+    full = t.peratom_dev_sum(ref, idx)
+    assert np.abs(got - full[want]).max() < 1e-10 * nframes
+    sel = idx if idx is not None else np.arange(natoms)
+    orc, total = oracle.rmsd_traj(frames, ref, sel, cpus=1)
+    assert total == nframes and np.abs(got / nframes - orc[want]).max() < 1e-10
+    assert np.array_equal(t.download(), frames)
+    with pytest.raises(_lib.GcbError):
+        t.peratom_dev_sum_atoms(ref, idx, np.array([0, natoms]))
+    t.close()

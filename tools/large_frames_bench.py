@@ -37,5 +37,10 @@ for n_sub in (300, 3000, 0):
         res[name + "_per_atom_sums_GBs_24B"] = 24.0 * na * nf / ms / 1e6
     _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
     out["fit_on_%s" % (n_sub or "all")] = res
+# align.LOVO on such a system only needs the sums of its candidates (the CA atoms): 1000 atoms asked for, fit on 300 of them
+cand = np.sort(np.random.default_rng(5).choice(na, 1000, replace=False))
+fit = cand[:300]
+ms = timed(lambda: t.peratom_dev_sum_atoms(r, fit, cand))
+out["candidates_only_1000_atoms_fit_on_300"] = {"per_atom_sums_ms": ms, "full_frame_entry_point_ms": timed(lambda: t.peratom_dev_sum(r, fit))}
 t.close()
 print(json.dumps(out))
