@@ -1072,7 +1072,7 @@ Error DeviceTrajectory::Load(chem::ConcTraj& traj, int natoms, const Options& o,
         void* pin[2] = {nullptr, nullptr};
         for (int s = 0; s < 2; s++) {
             rc = gcb_pinned_alloc((size_t)per * fbytes, &pin[s]);
-            if (rc) return deviceError(rc, "gcb_pinned_alloc");
+            if (rc) { gcb_pinned_free(pin[0]); return deviceError(rc, "gcb_pinned_alloc"); }
         }
         int slot = 0;
         Error up;
