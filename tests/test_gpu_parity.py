@@ -669,3 +669,31 @@ def test_per_atom_sums_of_chosen_atoms(natoms, nfit, nwant, nframes):
     with pytest.raises(_lib.GcbError):
         t.peratom_dev_sum_atoms(ref, idx, np.array([0, natoms]))
     t.close()
+
+
+@pytest.mark.skipif(not os.environ.get("GCB_RUN_UNVERIFIED"), reason="not yet run on a GPU (pod had no free slot)")
+def test_large_frame_split_path_on_a_window():
+    """The split path on a window of the trajectory (first > 0): only those frames move, the per-frame outputs land at the window's
+    offsets, and the sums cover the window's frames alone (full-frame and chosen-atoms entry points)."""
+    natoms, nframes, first, n = 26000, 12, 3, 7
+    ref, frames = synth.make_case(natoms, nframes)
+    idx = np.sort(np.random.default_rng(11).choice(natoms, 400, replace=False))
+    t = device_traj(frames)
+    win = frames[first:first + n].copy()
+    want, total = oracle.rmsd_traj(win, ref, idx, cpus=1)
+    got = t.peratom_dev_sum(ref, idx, first=first, nframes=n)
+    assert total == n and np.abs(got / n - want).max() < 1e-10
+    cand = np.array([25999, 0, 17, 13000])
+    got_c = t.peratom_dev_sum_atoms(ref, idx, cand, first=first, nframes=n)
+    assert np.abs(got_c / n - want[cand]).max() < 1e-10
+    out = t.super_rmsd(ref, idx, idx, write_back=True, first=first, nframes=n)
+    rm, rot, t1, t2 = oracle.super_rmsd_traj(win, ref, idx, write_back=True)
+    assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD and np.abs(out["rot"] - rot).max() < TOL_ROT
+    moved = t.download()
+    assert np.abs(moved[first:first + n] - win).max() < TOL_XYZ
+    assert np.array_equal(moved[:first], frames[:first]) and np.array_equal(moved[first + n:], frames[first + n:])
+    # one frame, and an empty window
+    one = t.super_rmsd(ref, None, None, write_back=True, first=0, nframes=1)
+    assert abs(one["rmsd"][0] - oracle.super_rmsd_traj(frames[:1], ref, None)[0][0]) < TOL_RMSD
+    assert np.array_equal(t.peratom_dev_sum(ref, idx, first=2, nframes=0), np.zeros(natoms))
+    t.close()
