@@ -671,7 +671,6 @@ def test_per_atom_sums_of_chosen_atoms(natoms, nfit, nwant, nframes):
     t.close()
 
 
-@pytest.mark.skipif(not os.environ.get("GCB_RUN_UNVERIFIED"), reason="not yet run on a GPU (pod had no free slot)")
 def test_large_frame_split_path_on_a_window():
     """The split path on a window of the trajectory (first > 0): only those frames move, the per-frame outputs land at the window's
     offsets, and the sums cover the window's frames alone (full-frame and chosen-atoms entry points)."""
