@@ -28,6 +28,7 @@ using ptx::warp_reduce12;
 constexpr int kSmallWarps = 8;
 constexpr int kSmallThreads = 32 * kSmallWarps;
 constexpr int kSmallMaxAtoms = 512;
+constexpr int kMinRun = 4;   // no more warps than frames / 4: a warp's fixed costs (template, solve) want a few frames to spread over
 
 __device__ __forceinline__ double shx2(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -137,9 +138,13 @@ __global__ void __launch_bounds__(kSmallThreads, (K == 8 ? 1 : GCB_SMALL_MINB)) 
     const bool sweep2_all = always_explicit || wb || DEV;
     const long gwarp = (long)blockIdx.x * kSmallWarps + warp, nwarps = (long)gridDim.x * kSmallWarps;
 
-    for (long b = gwarp; b < nbatches; b += nwarps) {
-        const long f0 = b * 32;
-        const int nf = (int)((p.nframes - f0 < 32) ? (p.nframes - f0) : 32);
+    // Every warp owns one contiguous run of frames, all runs of (almost) equal length, and walks it in batches of up to 32: the
+    // warps finish together.  (Dealing whole batches of 32 left the last round partly empty: 100 000 frames over 2368 warps are
+    // 1.3 batches per warp -- two rounds, the second a third full.)
+    const long run = p.nframes / nwarps, extra = p.nframes % nwarps;
+    const long lo = gwarp * run + (gwarp < extra ? gwarp : extra), hi = lo + run + (gwarp < extra ? 1 : 0);
+    for (long f0 = lo; f0 < hi; f0 += 32) {
+        const int nf = (int)((hi - f0 < 32) ? (hi - f0) : 32);
         // ---------------- sweep 1: the 13 sums of every frame of the batch ----------------
         double x[K], y[K], z[K];
         auto load = [&](int i, auto& lx, auto& ly, auto& lz) {
@@ -303,9 +308,10 @@ __global__ void __launch_bounds__(kSmallThreads, GATHER ? 1 : GCB_MID_MINB) supe
     const bool wb = p.frames_rw != nullptr;
     const bool sweep2_all = always_explicit || wb;
     const long gwarp = (long)blockIdx.x * kSmallWarps + warp, nwarps = (long)gridDim.x * kSmallWarps;
-    for (long b = gwarp; b < nbatches; b += nwarps) {
-        const long f0 = b * 32;
-        const int nf = (int)((p.nframes - f0 < 32) ? (p.nframes - f0) : 32);
+    const long run = p.nframes / nwarps, extra = p.nframes % nwarps;   // contiguous runs of equal length, see super_small_kernel
+    const long lo = gwarp * run + (gwarp < extra ? gwarp : extra), hi = lo + run + (gwarp < extra ? 1 : 0);
+    for (long f0 = lo; f0 < hi; f0 += 32) {
+        const int nf = (int)((hi - f0 < 32) ? (hi - f0) : 32);
         double x[CH], y[CH], z[CH];
         auto load = [&](int i, int c, double (&lx)[CH], double (&ly)[CH], double (&lz)[CH]) {
             const double* fr = p.frames + (f0 + i) * p.frame_stride;
@@ -441,7 +447,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
         // one CTA per SM: with two, a subset of 3000 atoms of a 100 000-atom frame takes 6.6 ms per 20 000 frames instead of 2.8
         // (the gathered sectors live in what the shared-memory carve-out leaves of L1)
         long grid = (long)t->sm_count;
-        const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+        const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
         GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -455,7 +461,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
     const long nbatches = (p.nframes + 31) / 32;
     long grid = (long)t->sm_count * GCB_SMALL_MINB;
-    const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+    const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
 #define GCB_GATHER_LAUNCH(KK)                                                                                                  \
@@ -495,7 +501,7 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
         const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
         const long nbatches = (p.nframes + 31) / 32;
         long grid = (long)t->sm_count * GCB_MID_MINB;
-        const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+        const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
         const int always = (force_explicit || p.frames_rw != nullptr) ? 1 : 0;
@@ -516,7 +522,7 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
     const long nbatches = (p.nframes + 31) / 32;
     long grid = (long)t->sm_count * 4;   // trimmed to what an SM can hold (occupancy query at launch)
-    const long need = (nbatches + kSmallWarps - 1) / kSmallWarps;
+    const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     int g = (int)grid;
