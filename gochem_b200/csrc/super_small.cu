@@ -490,7 +490,13 @@ int small_gather_max_atoms() { return kGatherMaxAtoms; }
 #ifndef GCB_SMALL_HEAVY_MAX
 #define GCB_SMALL_HEAVY_MAX 448
 #endif
-bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? GCB_SMALL_HEAVY_MAX : 1280); }
+// Fit-only passes: the chunked warp-per-frame kernel up to 1664 atoms (13 chunks), the cluster kernel above (100 000 frames,
+// tools/mid_threshold_probe.py, profiles/r1_s5_mid_threshold.jsonl: 1400 atoms 634 -> 526 us, 1500 atoms 634 -> 573 us, a tie at
+// 1700, the cluster kernel ahead at 2000: 715 against 776 us)
+#ifndef GCB_MID_FIT_MAX
+#define GCB_MID_FIT_MAX 1664
+#endif
+bool small_kernel_supported(const gcb_traj* t, bool heavy) { return t->np <= (heavy ? GCB_SMALL_HEAVY_MAX : GCB_MID_FIT_MAX); }
 
 // rows of the per-atom distance partials this kernel writes (one per warp of the grid)
 int small_kernel_rows(const gcb_traj* t) { return t->sm_count * 4 * kSmallWarps; }
