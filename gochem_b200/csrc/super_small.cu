@@ -102,7 +102,7 @@ __device__ __forceinline__ bool solve_lane(const SuperParams& p, const double* s
 // GATHER: the fit uses nidx atoms picked out of a (possibly much larger) frame -- slot q of the warp is atom idx[q] and the
 // template is the compact list refpairs (3 x nidx).  Only those atoms are read: 3 sectors per atom instead of the whole frame.
 template <int K, bool MASKED, bool DEV, bool GATHER = false>
-__global__ void __launch_bounds__(kSmallThreads, (K == 8 ? 1 : GCB_SMALL_MINB)) super_small_kernel(const SuperParams p, int always_explicit, long nbatches,
+__global__ void __launch_bounds__(kSmallThreads, (K == 8 ? 1 : GCB_SMALL_MINB)) super_small_kernel(const SuperParams p, int always_explicit,
                                                                   const double* __restrict__ refpairs = nullptr,
                                                                   const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -275,7 +275,7 @@ constexpr int kMidMaxAtoms = 2048;
 constexpr int kGatherMaxAtoms = 4096;        // gathered subsets: template planes of 96 KB in shared memory
 
 template <bool MASKED, bool GATHER = false>
-__global__ void __launch_bounds__(kSmallThreads, GATHER ? 1 : GCB_MID_MINB) super_mid_kernel(const SuperParams p, int always_explicit, long nbatches, int nch,
+__global__ void __launch_bounds__(kSmallThreads, GATHER ? 1 : GCB_MID_MINB) super_mid_kernel(const SuperParams p, int always_explicit, int nch,
                                                                    const double* __restrict__ refpairs = nullptr,
                                                                    const int* __restrict__ idx = nullptr, int nidx = 0) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kSmallThreads, GATHER ? 1 : GCB_MID_MINB) supe
 }
 
 template <int K>
-int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int& grid, long nbatches, size_t smem) {
+int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int& grid, size_t smem) {
 #define GCB_SMALL_LAUNCH(M, D)                                                                                   \
     do {                                                                                                         \
         GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<K, M, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -422,7 +422,7 @@ int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev
         if (per_sm < 1) per_sm = 1;                                                                              \
         if (per_sm > 4) per_sm = 4;                                                                              \
         if (grid > t->sm_count * per_sm) grid = t->sm_count * per_sm;                                            \
-        super_small_kernel<K, M, D><<<grid, kSmallThreads, smem, t->stream>>>(p, always_explicit, nbatches);        \
+        super_small_kernel<K, M, D><<<grid, kSmallThreads, smem, t->stream>>>(p, always_explicit);        \
     } while (0)
     if (masked) { if (want_dev) GCB_SMALL_LAUNCH(true, true); else GCB_SMALL_LAUNCH(true, false); }
     else { if (want_dev) GCB_SMALL_LAUNCH(false, true); else GCB_SMALL_LAUNCH(false, false); }
@@ -443,7 +443,6 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     if (nidx > kSmallMaxAtoms) {   // chunked form, up to kGatherMaxAtoms
         const int nch = (nidx + 32 * kMidChunk - 1) / (32 * kMidChunk);
         const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
-        const long nbatches = (p.nframes + 31) / 32;
         // one CTA per SM: with two, a subset of 3000 atoms of a 100 000-atom frame takes 6.6 ms per 20 000 frames instead of 2.8
         // (the gathered sectors live in what the shared-memory carve-out leaves of L1)
         long grid = (long)t->sm_count;
@@ -451,7 +450,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
         GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        super_mid_kernel<false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nbatches, nch, refpairs, idx, nidx);
+        super_mid_kernel<false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nch, refpairs, idx, nidx);
         GCB_LAUNCHED();
         GCB_CUDA(cudaGetLastError());
         return GCB_OK;
@@ -459,7 +458,6 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     const int k_needed = (nidx + 31) / 32;
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
-    const long nbatches = (p.nframes + 31) / 32;
     long grid = (long)t->sm_count * GCB_SMALL_MINB;
     const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
     if (grid > need) grid = need;
@@ -467,7 +465,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
 #define GCB_GATHER_LAUNCH(KK)                                                                                                  \
     do {                                                                                                                       \
         GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<KK, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        super_small_kernel<KK, false, false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nbatches, refpairs, idx, nidx); \
+        super_small_kernel<KK, false, false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, refpairs, idx, nidx); \
     } while (0)
     switch (K) {
         case 1: GCB_GATHER_LAUNCH(1); break;
@@ -505,7 +503,6 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
     if (t->np > kSmallMaxAtoms) {   // chunked form
         const int nch = (t->np + 32 * kMidChunk - 1) / (32 * kMidChunk);
         const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * kMidChunk * (size_t)nch;
-        const long nbatches = (p.nframes + 31) / 32;
         long grid = (long)t->sm_count * GCB_MID_MINB;
         const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
         if (grid > need) grid = need;
@@ -513,10 +510,10 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
         const int always = (force_explicit || p.frames_rw != nullptr) ? 1 : 0;
         if (masked) {
             GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            super_mid_kernel<true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nbatches, nch);
+            super_mid_kernel<true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nch);
         } else {
             GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            super_mid_kernel<false><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nbatches, nch);
+            super_mid_kernel<false><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nch);
         }
         GCB_LAUNCHED();
         GCB_CUDA(cudaGetLastError());
@@ -526,7 +523,6 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
     const int k_needed = (t->np + 31) / 32;
     const int K = k_needed <= 1 ? 1 : k_needed <= 2 ? 2 : k_needed <= 4 ? 4 : k_needed <= 8 ? 8 : 16;
     const size_t smem = sizeof(SmallShared) + sizeof(double) * 3 * 32 * (size_t)K;
-    const long nbatches = (p.nframes + 31) / 32;
     long grid = (long)t->sm_count * 4;   // trimmed to what an SM can hold (occupancy query at launch)
     const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
     if (grid > need) grid = need;
@@ -536,11 +532,11 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
     if (want_dev) GCB_CUDA(cudaMemsetAsync(p.devpart, 0, sizeof(double) * (size_t)small_kernel_rows(t) * (size_t)t->np, t->stream));
     int rc;
     switch (K) {
-        case 1: rc = launch_small_k<1>(t, p, masked, want_dev, always, g, nbatches, smem); break;
-        case 2: rc = launch_small_k<2>(t, p, masked, want_dev, always, g, nbatches, smem); break;
-        case 4: rc = launch_small_k<4>(t, p, masked, want_dev, always, g, nbatches, smem); break;
-        case 8: rc = launch_small_k<8>(t, p, masked, want_dev, always, g, nbatches, smem); break;
-        default: rc = launch_small_k<16>(t, p, masked, want_dev, always, g, nbatches, smem); break;
+        case 1: rc = launch_small_k<1>(t, p, masked, want_dev, always, g, smem); break;
+        case 2: rc = launch_small_k<2>(t, p, masked, want_dev, always, g, smem); break;
+        case 4: rc = launch_small_k<4>(t, p, masked, want_dev, always, g, smem); break;
+        case 8: rc = launch_small_k<8>(t, p, masked, want_dev, always, g, smem); break;
+        default: rc = launch_small_k<16>(t, p, masked, want_dev, always, g, smem); break;
     }
     if (rows_out) *rows_out = g * kSmallWarps;
     return rc;
