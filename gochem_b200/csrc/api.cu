@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -188,6 +189,10 @@ int gcb_traj_destroy(gcb_traj* tb) {
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     cudaFree(t->d_ap_ws);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
+    for (int s = 0; s < 2; s++) {
+        if (t->h_bounce[s]) cudaFreeHost(t->h_bounce[s]);
+        if (t->bounce_done[s]) cudaEventDestroy(t->bounce_done[s]);
+    }
     delete t;
     return GCB_OK;
 }
@@ -269,6 +274,56 @@ static size_t host_frame_bytes(const gcb_traj* t, int layout) {
     return (layout == GCB_F64_AOS ? sizeof(double) : sizeof(float)) * 3 * (size_t)t->natoms;
 }
 
+// ---- pageable host memory ----
+// A Go slice (or any malloc'ed buffer) is pageable: handed to cudaMemcpyAsync it goes through the driver's own bounce buffer, one
+// thread, ~10 GB/s.  The synchronous entry points copy it through two library-owned pinned buffers instead, several threads per
+// copy, the DMA of one chunk under the memcpy of the next.
+constexpr size_t kBounceBytes = 16ull << 20;
+
+static int copy_threads() {
+    static const int n = [] {
+        const char* e = getenv("GCB_COPY_THREADS");
+        int v = e ? atoi(e) : 0;
+        if (v <= 0) { v = (int)std::thread::hardware_concurrency() / 2; if (v > 8) v = 8; }
+        return v < 1 ? 1 : v;
+    }();
+    return n;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const int nt = bytes >= (2u << 20) ? copy_threads() : 1;
+    if (nt == 1) { memcpy(dst, src, bytes); return; }
+    const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; i++) {
+        const size_t off = part * i;
+        if (off >= bytes) break;
+        const size_t n = (off + part < bytes) ? part : bytes - off;
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, n); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto& x : th) x.join();
+}
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int ensure_bounce(gcb_traj* t) {
+    if (t->h_bounce[0]) return GCB_OK;
+    size_t bytes = kBounceBytes < t->stage_bytes ? kBounceBytes : t->stage_bytes;
+    const size_t frame = sizeof(double) * 3 * (size_t)t->natoms;
+    if (bytes < frame) bytes = frame;
+    for (int s = 0; s < 2; s++) {
+        GCB_CUDA(cudaHostAlloc(&t->h_bounce[s], bytes, cudaHostAllocPortable));
+        GCB_CUDA(cudaEventCreateWithFlags(&t->bounce_done[s], cudaEventDisableTiming));
+    }
+    t->bounce_bytes = bytes;
+    return GCB_OK;
+}
+
 int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int layout, double scale) {
     int rc = check_window(t, first, nframes, false);
     if (rc) return rc;
@@ -276,6 +331,26 @@ int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int
     if (layout < GCB_F64_AOS || layout > GCB_I32_AOS) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     const size_t fb = host_frame_bytes(t, layout);
+    if (nframes > 0 && (size_t)nframes * fb >= (1u << 20) && is_pageable(host)) {
+        rc = ensure_bounce(t);
+        if (rc) return rc;
+        const long per = (long)(t->bounce_bytes / fb);
+        int slot = 0;
+        for (long done = 0; done < nframes; done += per, slot ^= 1) {
+            const long n = (nframes - done < per) ? nframes - done : per;
+            cudaStream_t s = t->copy_stream[slot];
+            if (done >= 2 * per) GCB_CUDA(cudaEventSynchronize(t->bounce_done[slot]));   // the DMA out of this buffer has finished
+            parallel_memcpy(t->h_bounce[slot], (const char*)host + (size_t)done * fb, (size_t)n * fb);
+            GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], t->h_bounce[slot], (size_t)n * fb, cudaMemcpyHostToDevice, s));
+            GCB_CUDA(cudaEventRecord(t->bounce_done[slot], s));
+            rc = launch_upload_convert(t, s, t->d_stage[slot], first + done, n, layout, scale);
+            if (rc) return rc;
+        }
+        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
+        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+        if (first + nframes > t->nframes) t->nframes = first + nframes;
+        return GCB_OK;
+    }
     const long per = (long)(t->stage_bytes / fb);
     int slot = 0;
     for (long done = 0; done < nframes; done += per, slot ^= 1) {
@@ -352,6 +427,32 @@ int gcb_traj_download(gcb_traj* t, long first, long nframes, double* host_aos) {
     if (!host_aos && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     const size_t fb = sizeof(double) * 3 * (size_t)t->natoms;
+    if (nframes > 0 && (size_t)nframes * fb >= (1u << 20) && is_pageable(host_aos)) {
+        // chunk c: layout kernel -> device staging slot -> pinned buffer (DMA); the memcpy of chunk c - 1 into the caller's
+        // memory runs on the host meanwhile
+        rc = ensure_bounce(t);
+        if (rc) return rc;
+        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));   // the staging slots may still feed an upload
+        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+        const long per = (long)(t->bounce_bytes / fb);
+        long prev_done = -1, prev_n = 0;
+        int slot = 0;
+        for (long done = 0; done < nframes; done += per, slot ^= 1) {
+            const long n = (nframes - done < per) ? nframes - done : per;
+            rc = launch_download_convert(t, t->stream, (double*)t->d_stage[slot], first + done, n);
+            if (rc) return rc;
+            GCB_CUDA(cudaMemcpyAsync(t->h_bounce[slot], t->d_stage[slot], (size_t)n * fb, cudaMemcpyDeviceToHost, t->stream));
+            GCB_CUDA(cudaEventRecord(t->bounce_done[slot], t->stream));
+            if (prev_done >= 0) {
+                GCB_CUDA(cudaEventSynchronize(t->bounce_done[slot ^ 1]));
+                parallel_memcpy((char*)host_aos + (size_t)prev_done * fb, t->h_bounce[slot ^ 1], (size_t)prev_n * fb);
+            }
+            prev_done = done; prev_n = n;
+        }
+        GCB_CUDA(cudaEventSynchronize(t->bounce_done[slot ^ 1]));
+        parallel_memcpy((char*)host_aos + (size_t)prev_done * fb, t->h_bounce[slot ^ 1], (size_t)prev_n * fb);
+        return GCB_OK;
+    }
     const long per = (long)(t->stage_bytes / fb);
     for (long done = 0; done < nframes; done += per) {
         const long n = (nframes - done < per) ? nframes - done : per;

@@ -103,6 +103,10 @@ struct gcb_traj {
     // host pinned scratch for small transfers
     double* h_scratch = nullptr;
     size_t h_scratch_bytes = 0;
+    // pinned bounce buffers for the synchronous upload / download of pageable host memory (api.cu), allocated on first use
+    void* h_bounce[2] = {nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    cudaEvent_t bounce_done[2] = {nullptr, nullptr};
 };
 
 // NCCL communicator wrapper (comm.cu) plus the peer-mapped row blocks of the multi-GPU all-pairs matrix
