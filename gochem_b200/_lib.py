@@ -54,6 +54,7 @@ def load() -> C.CDLL:
         "gcb_set_cluster_tuning": (I, [I, I, I, I]),
         "gcb_last_cluster_plan": (I, [C.POINTER(I)]),
         "gcb_set_rmsd_mode": (I, [I]),
+        "gcb_set_split_thresholds": (I, [I, I]),
         "gcb_pinned_alloc": (I, [C.c_size_t, C.POINTER(P)]),
         "gcb_pinned_free": (I, [P]),
         "gcb_bind_host_thread": (I, [I]),

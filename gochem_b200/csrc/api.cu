@@ -20,6 +20,13 @@ namespace gcb {
 static thread_local std::string t_error;
 std::atomic<long> g_launches{0};
 int g_variant = GCB_KERNEL_AUTO;
+// Small structures, passes that visit every atom twice: up to these atom counts the fit-only launch plus one elementwise sweep
+// (transform.cu) beats the fused kernels, whose second sweep misses L2 there (gcb_set_split_thresholds; measured defaults)
+// 100 000 frames, tools/split_small_probe.py, profiles/r1_s5_split_small_probe.jsonl: write-back 300 atoms 510 -> 392 us, 512 atoms
+// 720 -> 627 us, a tie at 600, the cluster kernel ahead above (and the fused warp-per-frame kernel below 64 atoms); per-atom sums
+// 300 atoms 644 -> 416 us, 800 atoms 827 -> 773 us, the cluster kernel ahead from 1000 atoms
+constexpr int kSplitWbMinAtoms = 64, kSplitWbMaxDefault = 560, kSplitDevMaxDefault = 900;
+int g_split_wb_max = kSplitWbMaxDefault, g_split_dev_max = kSplitDevMaxDefault;
 
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -108,6 +115,12 @@ int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident) {
         return GCB_ERR_ARG;
     }
     set_cluster_tuning(cluster, stages, depth == 0 ? -1 : depth, resident);
+    return GCB_OK;
+}
+
+int gcb_set_split_thresholds(int write_back_max_atoms, int per_atom_max_atoms) {
+    g_split_wb_max = write_back_max_atoms < 0 ? kSplitWbMaxDefault : write_back_max_atoms;
+    g_split_dev_max = per_atom_max_atoms < 0 ? kSplitDevMaxDefault : per_atom_max_atoms;
     return GCB_OK;
 }
 
@@ -663,7 +676,10 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
     // Frames beyond the cluster kernel's capacity whose every atom must be visited a second time (write-back, per-atom sums):
     // the fit and the elementwise sweep are separate launches (transform.cu) instead of the generic kernel's re-read.
-    if (g_variant == GCB_KERNEL_AUTO && (write_back || want_dev) && nframes > 0 && !cluster_kernel_supported(t, true))
+    const bool small_split = (write_back && !want_dev && t->natoms >= kSplitWbMinAtoms && t->natoms <= g_split_wb_max) ||
+                             (want_dev && !write_back && t->natoms <= g_split_dev_max);
+    if (g_variant == GCB_KERNEL_AUTO && (write_back || want_dev) && nframes > 0 && !force_explicit_mode() &&
+        (small_split || !cluster_kernel_supported(t, true)))
         return launch_super_split(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back, want_dev, dev_rows);
     int mode = MODE_ALL;
     // Subset fits that leave the frames untouched need only the subset's atoms.  Gathering them costs 3 sectors (96 bytes) per atom

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_kernel(const double*
     const long f0 = split * per;
     long f1 = f0 + per;
     if (f1 > nframes) f1 = nframes;
-    const int j = tile * kTfThreads + threadIdx.x;
+    const int j = tile * (int)blockDim.x + threadIdx.x;
     const bool in = j < np2;
     double2 bx = make_double2(0.0, 0.0), by = bx, bz = bx;
     if (in) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_kernel(const double*
     for (long fb = f0; fb < f1; fb += kAccFrames) {
         const int nb = (int)((f1 - fb) < kAccFrames ? (f1 - fb) : kAccFrames);
         __syncthreads();   // the previous batch's transforms are no longer read
-        for (int k = threadIdx.x; k < nb * 12; k += kTfThreads) {
+        for (int k = threadIdx.x; k < nb * 12; k += (int)blockDim.x) {
             const int ff = k / 12, e = k - ff * 12;
             // R, then centroid R (so that (a - c) R = a R - c R costs nothing per atom); the warp that stores element 9..11
             // recomputes it from R and trans1 = -c
@@ -147,6 +147,62 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_kernel(const double*
         if (2 * j >= natoms) s0 = 0.0;
         if (2 * j + 1 >= natoms) s1 = 0.0;
         reinterpret_cast<double2*>(part + (long)split * np)[j] = make_double2(s0, s1);
+    }
+}
+
+// Write-back with the accumulation kernel's shape, for frames of a few hundred atoms (the tile kernel above would leave most
+// of its threads without a column): a thread owns one double2 column and walks the frames of its range.
+__global__ void __launch_bounds__(kTfThreads) transform_cols_kernel(double* __restrict__ frames, long frame_stride, int np, int natoms,
+                                                                   long nframes, int nsplits, const double* __restrict__ rot,
+                                                                   const double* __restrict__ trans1, double b0, double b1, double b2) {
+    __shared__ double s_xf[kAccFrames][12];
+    const int np2 = np >> 1;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const long per = (nframes + nsplits - 1) / nsplits;
+    const long f0 = split * per;
+    long f1 = f0 + per;
+    if (f1 > nframes) f1 = nframes;
+    const int j = tile * (int)blockDim.x + threadIdx.x;
+    const bool in = j < np2;
+    const bool v0 = 2 * j < natoms, v1 = 2 * j + 1 < natoms;   // padding atoms stay zero
+    for (long fb = f0; fb < f1; fb += kAccFrames) {
+        const int nb = (int)((f1 - fb) < kAccFrames ? (f1 - fb) : kAccFrames);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nb * 12; k += (int)blockDim.x) {
+            const int ff = k / 12, e = k - ff * 12;
+            double v;
+            if (e < 9) v = rot[9 * (fb + ff) + e];
+            else {
+                const double* r = rot + 9 * (fb + ff);
+                const double* t = trans1 + 3 * (fb + ff);
+                const int col = e - 9;
+                v = fma(t[2], r[6 + col], fma(t[1], r[3 + col], t[0] * r[col]));   // (trans1 R)[col] = -(centroid R)[col]
+            }
+            s_xf[ff][e] = v;
+        }
+        __syncthreads();
+        if (!in) continue;
+        double* fr = frames + fb * frame_stride;
+#pragma unroll 4
+        for (int ff = 0; ff < nb; ff++, fr += frame_stride) {
+            double2* X = reinterpret_cast<double2*>(fr) + j;
+            double2* Y = reinterpret_cast<double2*>(fr + np) + j;
+            double2* Z = reinterpret_cast<double2*>(fr + 2L * np) + j;
+            const double2 x = __ldcs(X), y = __ldcs(Y), z = __ldcs(Z);
+            const double* xf = s_xf[ff];
+            const double g0 = xf[9] + b0, g1 = xf[10] + b1, g2 = xf[11] + b2;
+            double2 qx, qy, qz;
+            // (a + trans1) R + trans2 = a R + (trans1 R + trans2)
+            qx.x = fma(z.x, xf[6], fma(y.x, xf[3], x.x * xf[0])) + g0;
+            qy.x = fma(z.x, xf[7], fma(y.x, xf[4], x.x * xf[1])) + g1;
+            qz.x = fma(z.x, xf[8], fma(y.x, xf[5], x.x * xf[2])) + g2;
+            qx.y = fma(z.y, xf[6], fma(y.y, xf[3], x.y * xf[0])) + g0;
+            qy.y = fma(z.y, xf[7], fma(y.y, xf[4], x.y * xf[1])) + g1;
+            qz.y = fma(z.y, xf[8], fma(y.y, xf[5], x.y * xf[2])) + g2;
+            if (!v0) { qx.x = 0.0; qy.x = 0.0; qz.x = 0.0; }
+            if (!v1) { qx.y = 0.0; qy.y = 0.0; qz.y = 0.0; }
+            __stcs(X, qx); __stcs(Y, qy); __stcs(Z, qz);
+        }
     }
 }
 
@@ -226,8 +282,32 @@ int launch_peratom_accum_gather(gcb_traj* t, const SuperParams& p, const int* d_
     return GCB_OK;
 }
 
+// threads per CTA and frame splits of the column-owning kernels: whole warps covering the frame's double2 columns (at most 256),
+// about 8 CTAs of 256 threads per SM in all, never less than one batch of transforms per split
+static void cols_shape(const gcb_traj* t, long nframes, int* threads, int* tiles, int* splits) {
+    const int np2 = t->np >> 1;
+    *threads = np2 >= kTfThreads ? kTfThreads : round_up(np2, 32);
+    *tiles = (np2 + *threads - 1) / *threads;
+    long want = ((long)t->sm_count * 8 * kTfThreads / *threads + *tiles - 1) / *tiles;
+    const long cap = t->np >= 4096 ? 64 : 1024;
+    if (want > cap) want = cap;
+    const long by_batch = (nframes + kAccFrames - 1) / kAccFrames;
+    if (want > by_batch) want = by_batch;
+    if (want < 1) want = 1;
+    *splits = (int)want;
+}
+
 int launch_transform_frames(gcb_traj* t, const SuperParams& p) {
     const int np2 = t->np >> 1;
+    if (np2 < kTfTile) {   // small frames: a thread per column
+        int threads, tiles, splits;
+        cols_shape(t, p.nframes, &threads, &tiles, &splits);
+        transform_cols_kernel<<<dim3((unsigned)tiles, (unsigned)splits), threads, 0, t->stream>>>(p.frames_rw, p.frame_stride, p.np, p.natoms, p.nframes,
+                                                                                                 splits, p.rot, p.trans1, p.bbar[0], p.bbar[1], p.bbar[2]);
+        GCB_LAUNCHED();
+        GCB_CUDA(cudaGetLastError());
+        return GCB_OK;
+    }
     const long tiles = p.nframes * ((np2 + kTfTile - 1) / kTfTile);
     long grid = (long)t->sm_count * 8;
     if (grid > tiles) grid = tiles;
@@ -241,21 +321,16 @@ int launch_transform_frames(gcb_traj* t, const SuperParams& p) {
 
 // rows of per-atom partial sums the accumulation writes for nframes frames (one per frame split)
 int peratom_accum_rows(const gcb_traj* t, long nframes) {
-    const int np2 = t->np >> 1;
-    const int tiles = (np2 + kTfThreads - 1) / kTfThreads;
-    long want = ((long)t->sm_count * 8 + tiles - 1) / tiles;   // about 8 CTAs per SM in all
-    if (want > 64) want = 64;
-    if (want > nframes) want = nframes;
-    if (want < 1) want = 1;
-    return (int)want;
+    int threads, tiles, splits;
+    cols_shape(t, nframes, &threads, &tiles, &splits);
+    return splits;
 }
 
 int launch_peratom_accum(gcb_traj* t, const SuperParams& p, const double* ref_planes, int* rows_out) {
-    const int np2 = t->np >> 1;
-    const int tiles = (np2 + kTfThreads - 1) / kTfThreads;
-    const int splits = peratom_accum_rows(t, p.nframes);
-    peratom_accum_kernel<<<dim3((unsigned)tiles, (unsigned)splits), kTfThreads, 0, t->stream>>>(p.frames, p.frame_stride, p.np, p.natoms, p.nframes,
-                                                                                                splits, p.rot, p.trans1, ref_planes, p.devpart);
+    int threads, tiles, splits;
+    cols_shape(t, p.nframes, &threads, &tiles, &splits);
+    peratom_accum_kernel<<<dim3((unsigned)tiles, (unsigned)splits), threads, 0, t->stream>>>(p.frames, p.frame_stride, p.np, p.natoms, p.nframes,
+                                                                                            splits, p.rot, p.trans1, ref_planes, p.devpart);
     GCB_LAUNCHED();
     GCB_CUDA(cudaGetLastError());
     if (rows_out) *rows_out = splits;

@@ -60,6 +60,9 @@ int gcb_set_kernel_variant(int variant);
  * trails pass 1 (1..6), and where pass 2 reads the frame from (1 = its shared-memory stage, 0 = L2,
  * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice. */
 int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident);
+/* Tuning hook: structures of at most this many atoms take the split form (a fit-only launch, then one elementwise sweep) for
+ * write-back / per-atom-sum passes instead of the fused kernels.  A negative value restores the built-in threshold. */
+int gcb_set_split_thresholds(int write_back_max_atoms, int per_atom_max_atoms);
 /* How the per-frame RMSD of a fit-only call (no write-back) is formed.  0 (default): from the inner products of
  * the single sweep, E = Ga + Gb - 2 tr(R^T H), whenever its rounding bound moves the RMSD by < 1e-10 A, and from
  * the explicit residual of a second sweep otherwise (frames within ~0.3 A of the template).  1: always the explicit

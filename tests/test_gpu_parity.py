@@ -696,3 +696,35 @@ def test_large_frame_split_path_on_a_window():
     assert abs(one["rmsd"][0] - oracle.super_rmsd_traj(frames[:1], ref, None)[0][0]) < TOL_RMSD
     assert np.array_equal(t.peratom_dev_sum(ref, idx, first=2, nframes=0), np.zeros(natoms))
     t.close()
+
+
+@pytest.mark.parametrize("natoms", [64, 100, 300, 333, 560, 561, 900, 901])
+def test_small_structures_split_form(natoms):
+    """Write-back and per-atom sums on a few hundred atoms take the split form by default (fit-only launch, then one elementwise
+    sweep whose threads own a column and walk the frames): against the oracle and against the fused kernels."""
+    lib = _lib.load()
+    nframes = 203
+    ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
+    idx = np.arange(1, natoms, 3)
+    t = device_traj(frames)
+    try:
+        for sel in (None, idx):
+            dev = t.peratom_dev_sum(ref, sel)
+            s = sel if sel is not None else np.arange(natoms)
+            want, total = oracle.rmsd_traj(frames, ref, s, cpus=7)
+            assert total == nframes and np.abs(dev / nframes - want).max() < 1e-10
+            _lib.check(lib.gcb_set_split_thresholds(0, 0))
+            fused = t.peratom_dev_sum(ref, sel)
+            _lib.check(lib.gcb_set_split_thresholds(-1, -1))
+            assert np.abs(dev - fused).max() < 1e-10 * nframes
+            assert np.array_equal(t.download(), frames)
+            out = t.super_rmsd(ref, sel, sel, write_back=True)
+            work = frames.copy()
+            rm, rot, t1, t2 = oracle.super_rmsd_traj(work, ref, sel, write_back=True, nthreads=4)
+            assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD and np.abs(out["rot"] - rot).max() < TOL_ROT
+            assert np.abs(out["trans1"] - t1).max() < TOL_XYZ and np.abs(out["trans2"] - t2).max() < TOL_XYZ
+            assert np.abs(t.download() - work).max() < TOL_XYZ
+            t.upload(frames)
+    finally:
+        lib.gcb_set_split_thresholds(-1, -1)
+        t.close()
