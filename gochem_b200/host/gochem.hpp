@@ -277,7 +277,7 @@ namespace stf {
 // (optionally followed by nine box numbers), a header of key=value lines closed by "** natoms", all of it inside one
 // compressed stream chosen by the LAST letter of the file name (stf.go:245-285): 'z' gzip, 'r' raw deflate, 'l' LZW,
 // anything else ("stf", "sts") zstd.  gzip and deflate are decoded with zlib, zstd with libzstd bound by dlopen
-// (GOCHEM_ZSTD names it, else libzstd.so.1); LZW files are refused with an error.  The decompressor and the text
+// (GOCHEM_ZSTD names it, else libzstd.so.1), LZW (Go's compress/lzw, MSB order, 8-bit literals) by a decoder of its own.  The decompressor and the text
 // parser stay on the CPU; the raw feed hands the device the integers as they were parsed (GCB_I32_AOS, divisor 100)
 // and the division float64(f)/p of stf.go:341 happens there.
 //

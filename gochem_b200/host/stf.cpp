@@ -234,6 +234,79 @@ class ZstdStream : public ByteStream {
     bool frame_open_ = false;
 };
 
+// LZW as Go's compress/lzw reads it with lzw.MSB and a literal width of 8 (stf.go:262: the 'l' files): codes of 9 to 12 bits packed
+// most significant bit first, 256 = clear, 257 = end of data, dictionary entries from 258; the width grows when the next free
+// entry reaches 1 << width.  The package is part of the Go standard library (source not in the reference tree); this is its
+// documented algorithm (the GIF variant with MSB packing, not TIFF's early change), checked here by round trips only.
+class LzwStream : public ByteStream {
+  public:
+    explicit LzwStream(FILE* fp) { fp_ = fp; reset(); }
+    ~LzwStream() override { if (fp_) fclose(fp_); }
+
+  protected:
+    long fill(char* dst, size_t cap, std::string* why) override {
+        size_t o = 0;
+        // bytes of an expansion that did not fit the previous call
+        while (pend_ > 0 && o < cap) dst[o++] = (char)stack_[--pend_];
+        while (o < cap && !done_) {
+            int code = read_code(why);
+            if (code == -2) return -1;
+            if (code == -1) { *why = "unexpected EOF"; return -1; }   // the stream must end with the end-of-data code
+            if (code == kClear) { reset(); continue; }
+            if (code == kEof) { done_ = true; break; }
+            int n = 0;   // expansion of the code, last byte first, into stack_
+            if (code < kClear) {
+                stack_[n++] = (unsigned char)code;
+                if (last_ != kInvalid) { suffix_[hi_] = (unsigned char)code; prefix_[hi_] = (uint16_t)last_; }
+            } else if (code <= hi_) {
+                int c = code;
+                if (code == hi_ && last_ != kInvalid) {   // the entry being defined: last expansion + its own first byte
+                    c = last_;
+                    while (c >= kClear) c = prefix_[c];
+                    stack_[n++] = (unsigned char)c;
+                    c = last_;
+                }
+                while (c >= kClear) { stack_[n++] = suffix_[c]; c = prefix_[c]; }
+                stack_[n++] = (unsigned char)c;
+                if (last_ != kInvalid) { suffix_[hi_] = (unsigned char)c; prefix_[hi_] = (uint16_t)last_; }
+            } else {
+                *why = "lzw: invalid code";
+                return -1;
+            }
+            last_ = code;
+            hi_++;
+            if (hi_ >= overflow_) {
+                if (width_ == kMaxWidth) { last_ = kInvalid; hi_--; }
+                else { width_++; overflow_ = 1 << width_; }
+            }
+            pend_ = n;
+            while (pend_ > 0 && o < cap) dst[o++] = (char)stack_[--pend_];
+        }
+        return (long)o;
+    }
+
+  private:
+    static constexpr int kClear = 256, kEof = 257, kMaxWidth = 12, kInvalid = 0xffff;
+    void reset() { width_ = 9; hi_ = kEof; overflow_ = 1 << 9; last_ = kInvalid; }
+    int read_code(std::string* why) {   // -1 = end of input, -2 = read error
+        while (nbits_ < width_) {
+            if (!more_input(why)) return why->empty() ? -1 : -2;
+            bits_ |= (uint32_t)(unsigned char)in_[in_pos_++] << (24 - nbits_);
+            nbits_ += 8;
+        }
+        const int code = (int)(bits_ >> (32 - width_));
+        bits_ <<= width_;
+        nbits_ -= width_;
+        return code;
+    }
+    uint32_t bits_ = 0;
+    int nbits_ = 0, width_ = 9, hi_ = kEof, overflow_ = 512, last_ = kInvalid, pend_ = 0;
+    bool done_ = false;
+    unsigned char suffix_[1 << 12];
+    uint16_t prefix_[1 << 12];
+    unsigned char stack_[(1 << 12) + 2];
+};
+
 // strings.Fields + strconv.Atoi on one coordinate line (stf.go:324-345): exactly three integers
 const char* parseLine(const char* p, size_t n, long out[3], std::string* why) {
     const char* e = p + n;
@@ -285,11 +358,12 @@ Error StfR::New(const std::string& name, std::unique_ptr<StfR>* out, std::map<st
     std::unique_ptr<StfR> s(new StfR());
     s->filename_ = name;
     const Codec codec = codecOf(name);
-    if (codec == Codec::Lzw) return stfError("Can't read header: LZW-compressed STF files are not supported by this build", name, {"NewStfR"});
     if (codec == Codec::Zstd && !zstd()->h) return stfError("Can't read header: " + zstd()->why, name, {"NewStfR"});
     FILE* fp = fopen(name.c_str(), "rb");
     if (!fp) return Error("open " + name + ": no such file or directory");   // os.Open's error goes back undecorated (stf.go:237-240)
-    if (codec == Codec::Zstd) {
+    if (codec == Codec::Lzw) {
+        s->h_.reset(new LzwStream(fp));
+    } else if (codec == Codec::Zstd) {
         std::unique_ptr<ZstdStream> z(new ZstdStream(fp));
         if (!z->ok()) return stfError("Can't read header: zstd decoder could not be created", name, {"NewStfR"});
         s->h_ = std::move(z);
@@ -496,6 +570,74 @@ class ZstdSink : public ByteSink {
     char out_[1 << 16];
 };
 
+// The matching encoder (lzw.NewWriter(a, lzw.MSB, 8), stf.go:143): a clear code first, the longest known string per code, the
+// dictionary dropped with a clear code when entry 4095 would be assigned, the end-of-data code at Close.
+class LzwSink : public ByteSink {
+  public:
+    explicit LzwSink(FILE* fp) : fp_(fp), table_(1 << 20, -1) {}
+    ~LzwSink() override { finish(); }
+    bool write(const char* p, size_t n) override {
+        if (!fp_) return false;
+        size_t i = 0;
+        if (code_ < 0 && n > 0) {
+            if (!emit(kClear)) return false;
+            code_ = (unsigned char)p[i++];
+        }
+        for (; i < n; i++) {
+            const int lit = (unsigned char)p[i];
+            const int key = code_ << 8 | lit;   // code_ < 4096: 20 bits
+            if (table_[(size_t)key] >= 0) { code_ = table_[(size_t)key]; continue; }
+            if (!emit(code_)) return false;
+            code_ = lit;
+            if (!inc_hi()) continue;            // out of codes: the dictionary starts over
+            table_[(size_t)key] = hi_;
+            used_.push_back(key);
+        }
+        return true;
+    }
+    bool finish() override {
+        if (!fp_) return true;
+        bool good = true;
+        if (code_ >= 0) { good = emit(code_); inc_hi(); }
+        else good = emit(kClear);
+        good = good && emit(kEof);
+        if (nbits_ > 0) good = good && fputc((int)(bits_ >> 24), fp_) != EOF;
+        const bool closed = fclose(fp_) == 0;
+        fp_ = nullptr;
+        return good && closed;
+    }
+
+  private:
+    static constexpr int kClear = 256, kEof = 257, kMaxCode = 4095;
+    bool emit(int code) {
+        bits_ |= (uint32_t)code << (32 - width_ - nbits_);
+        nbits_ += width_;
+        while (nbits_ >= 8) {
+            if (fputc((int)(bits_ >> 24), fp_) == EOF) return false;
+            bits_ <<= 8;
+            nbits_ -= 8;
+        }
+        return true;
+    }
+    bool inc_hi() {   // false: the code space ran out and a clear code was written
+        hi_++;
+        if (hi_ == overflow_) { width_++; overflow_ <<= 1; }
+        if (hi_ == kMaxCode) {
+            emit(kClear);
+            width_ = 9; hi_ = kEof; overflow_ = 512;
+            for (int k : used_) table_[(size_t)k] = -1;
+            used_.clear();
+            return false;
+        }
+        return true;
+    }
+    FILE* fp_;
+    std::vector<int> table_;   // (prefix code << 8 | byte) -> code
+    std::vector<int> used_;
+    uint32_t bits_ = 0;
+    int nbits_ = 0, width_ = 9, hi_ = kEof, overflow_ = 512, code_ = -1;
+};
+
 }  // namespace
 
 StfW::~StfW() { Close(); }
@@ -510,7 +652,6 @@ Error StfW::NewWriter(const std::string& name, int natoms, const std::map<std::s
     std::unique_ptr<StfW> s(new StfW());
     s->filename_ = name;
     const Codec codec = codecOf(name);
-    if (codec == Codec::Lzw) return stfError("Can't read header LZW-compressed STF files are not supported by this build", name, {"NewWriter"});
     // flate.NewWriter and gzip.NewWriterLevel refuse levels outside [-2, 9] -- including the reference's own default of 11
     // (stf.go:115, 131-135): with the default level only the zstd forms can be written there
     if (codec == Codec::Flate && (level < -2 || level > 9))
@@ -520,7 +661,9 @@ Error StfW::NewWriter(const std::string& name, int natoms, const std::map<std::s
     if (codec == Codec::Zstd && !zstd()->h) return stfError("Can't read header " + zstd()->why, name, {"NewWriter"});
     FILE* fp = fopen(name.c_str(), "wb");
     if (!fp) return Error("open " + name + ": cannot create");
-    if (codec == Codec::Zstd) {
+    if (codec == Codec::Lzw) {
+        s->h_.reset(new LzwSink(fp));
+    } else if (codec == Codec::Zstd) {
         std::unique_ptr<ZstdSink> z(new ZstdSink(fp));
         if (!z->ok()) return stfError("Can't read header zstd encoder could not be created", name, {"NewWriter"});
         s->h_ = std::move(z);

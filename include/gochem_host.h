@@ -90,7 +90,7 @@ int gch_xtc_write(const char *path, const double *frames_aos, long nframes, int 
 int gch_xtc_read(const char *path, double *out_aos, long cap_frames, long *nframes, int *natoms, int use_raw);
 
 /* traj/stf (goChem's own text-in-a-compressed-stream format, traj/stf/stf.go).  The codec follows the last letter of the
- * file name as in the reference: 'z' gzip, 'r' raw deflate (zlib), anything else zstd (libzstd through dlopen, GOCHEM_ZSTD
+ * file name as in the reference: 'z' gzip, 'r' raw deflate (zlib), 'l' LZW, anything else zstd (libzstd through dlopen, GOCHEM_ZSTD
  * names it); gch_stf_zstd_available: 1 when that library could be loaded.  gch_stf_write: frames -> file through StfW
  * (level: flate / gzip level; the reference's default 11 is rejected by those codecs there too).  gch_stf_read: frames back
  * through StfR.Next (use_raw = 0) or through the raw int32 feed divided by its scale on the host exactly as the device

@@ -369,8 +369,6 @@ def test_stf_writer_round_trip_and_text_layout(tmp_path):
     # the reference's default level 11 is refused by flate / gzip there as well (stf.go:115, 131-135)
     with pytest.raises(H.GoChemError, match="invalid compression level"):
         H.stf_write(str(tmp_path / "bad.stz"), frames, level=11)
-    with pytest.raises(H.GoChemError, match="LZW"):
-        H.stf_write(str(tmp_path / "bad.stl"), frames)
     if H.stf_zstd_available():
         pf = str(tmp_path / "w.stf")
         H.stf_write(pf, frames, level=11, box=[1, 2, 3, 4, 5, 6, 7, 8, 9])
@@ -411,3 +409,79 @@ def test_stf_reader_errors(tmp_path):
         f.write(gzip.compress(good * 50)[:-20])       # compressed stream cut short
     with pytest.raises(H.GoChemError):
         H.stf_read(p, 100, 2)
+
+
+def _lzw_msb_decode(data: bytes) -> bytes:
+    """Go's compress/lzw reader with lzw.MSB and 8-bit literals, restated: 9..12-bit codes packed most significant bit first,
+    256 = clear, 257 = end of data, entries from 258, the width grows when the next free entry reaches 1 << width."""
+    out = bytearray()
+    prefix, suffix = {}, {}
+    width, hi, overflow, last = 9, 257, 512, None
+    bits = nbits = 0
+    pos = 0
+    while True:
+        while nbits < width:
+            bits = (bits << 8) | data[pos]
+            pos += 1
+            nbits += 8
+        code = (bits >> (nbits - width)) & ((1 << width) - 1)
+        nbits -= width
+        if code == 256:
+            width, hi, overflow, last = 9, 257, 512, None
+            continue
+        if code == 257:
+            return bytes(out)
+        if code < 256:
+            exp = bytes([code])
+        elif code <= hi:
+            def expand(c):
+                b = bytearray()
+                while c >= 256:
+                    b.append(suffix[c])
+                    c = prefix[c]
+                b.append(c)
+                return bytes(reversed(b))
+            if code == hi and last is not None:
+                e = expand(last)
+                exp = e + e[:1]
+            else:
+                exp = expand(code)
+        else:
+            raise ValueError("lzw: invalid code")
+        if last is not None:
+            suffix[hi], prefix[hi] = exp[0], last
+        out += exp
+        last, hi = code, hi + 1
+        if hi >= overflow:
+            if width == 12:
+                last, hi = None, hi - 1
+            else:
+                width += 1
+                overflow = 1 << width
+
+
+def test_stf_lzw_form(tmp_path):
+    """The 'l' files (lzw.NewWriter / NewReader with lzw.MSB and 8-bit literals, stf.go:143, 262): what StfW writes decodes with an
+    independent restatement of Go's reader to the expected text, and StfR reads it back -- a stream long enough for the code width to
+    grow to 12 bits and the dictionary to be dropped several times."""
+    rng = np.random.default_rng(9)
+    frames = rng.normal(0, 25, (40, 400, 3))
+    want = np.rint(frames * 100.0) / 100.0
+    p = str(tmp_path / "w.stl")
+    H.stf_write(p, frames, header={"codec": "lzw"})
+    raw = open(p, "rb").read()
+    text = _stf_text(frames, header={"codec": "lzw"})
+    assert len(text) > 200_000 and len(raw) < len(text)
+    assert _lzw_msb_decode(raw) == text
+    got, nf, na, header = H.stf_read(p, 50, 400)
+    assert (nf, na, header) == (40, 400, {"codec": "lzw"}) and np.array_equal(got, want)
+    raw_feed, nf2, _, _ = H.stf_read(p, 50, 400, raw=True)
+    assert nf2 == 40 and np.array_equal(raw_feed, want)
+    # a tiny stream (no width change), and a truncated one
+    H.stf_write(str(tmp_path / "tiny.stl"), frames[:1, :3])
+    got, nf, na, _ = H.stf_read(str(tmp_path / "tiny.stl"), 2, 3)
+    assert (nf, na) == (1, 3) and np.array_equal(got[0], want[0, :3])
+    with open(str(tmp_path / "cut.stl"), "wb") as f:
+        f.write(raw[: len(raw) // 2])
+    with pytest.raises(H.GoChemError):
+        H.stf_read(str(tmp_path / "cut.stl"), 50, 400)
