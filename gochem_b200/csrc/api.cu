@@ -308,13 +308,20 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     if (nt == 1) { memcpy(dst, src, bytes); return; }
     const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
     std::vector<std::thread> th;
-    for (int i = 1; i < nt; i++) {
-        const size_t off = part * i;
-        if (off >= bytes) break;
+    size_t mine = part < bytes ? part : bytes;   // [0, mine) is copied by the calling thread, and so is whatever no helper took
+    size_t handed = mine;
+    for (int i = 1; i < nt && handed < bytes; i++) {
+        const size_t off = handed;
         const size_t n = (off + part < bytes) ? part : bytes - off;
-        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, n); });
+        try {
+            th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, n); });
+        } catch (...) {   // no more threads to be had: the caller copies the rest
+            break;
+        }
+        handed += n;
     }
-    memcpy(dst, src, part < bytes ? part : bytes);
+    memcpy(dst, src, mine);
+    if (handed < bytes) memcpy((char*)dst + handed, (const char*)src + handed, bytes - handed);
     for (auto& x : th) x.join();
 }
 
