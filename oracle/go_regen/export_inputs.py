@@ -39,6 +39,29 @@ def read_outputs(path: str, natoms: int, nframes: int) -> dict:
     return out
 
 
+def export_lovo(path: str) -> str:
+    """The align.LOVO case: same layout, no index list, the chunk size of the golden run."""
+    z = np.load(path)
+    ref, frames = z["ref"].astype("<f8"), z["frames"].astype("<f8")
+    os.makedirs(OUT, exist_ok=True)
+    out = os.path.join(OUT, os.path.basename(path)[:-4] + ".lovo.in.bin")
+    with open(out, "wb") as f:
+        np.array([ref.shape[0], frames.shape[0], 0, int(z["cpus"])], "<i8").tofile(f)
+        ref.tofile(f)
+        frames.tofile(f)
+    return out
+
+
+def read_lovo_outputs(path: str) -> dict:
+    """<case>.lovo.go.bin as written by main.go."""
+    with open(path, "rb") as f:
+        n, frames_read, iterations, nnat, nrmsd = (int(v) for v in np.fromfile(f, "<i8", 5))
+        return {"N": n, "FramesRead": frames_read, "Iterations": iterations, "Natoms": np.fromfile(f, "<i8", nnat),
+                "RMSD": np.fromfile(f, "<f8", nrmsd)}
+
+
 if __name__ == "__main__":
     for p in sorted(glob.glob(os.path.join(GOLDEN, "super_*.npz"))):
         print(export(p))
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "lovo_*.npz"))):
+        print(export_lovo(p))

@@ -9,9 +9,9 @@
 //	go run . ../../tests/golden/go_reference         # writes <case>.go.bin beside every <case>.in.bin
 //	python -m pytest tests/test_oracle.py -k go_reference
 //
-// tests/test_oracle.py::test_go_reference_outputs then compares the oracle with these files (it is skipped while they
-// are absent).  The program calls only the reference's public API:
-// chem.RotatorTranslatorToSuper, chem.Super, chem.RMSD, chem.MemPerAtomRMSD and align.RMSDTraj.
+// tests/test_oracle.py::test_go_reference_outputs and ::test_go_reference_lovo_output then compare the oracle with these
+// files (they are skipped while the files are absent).  The program calls only the reference's public API:
+// chem.RotatorTranslatorToSuper, chem.Super, chem.RMSD, align.RMSDTraj, align.LOVO and dcd.NewWriter.
 //
 // File formats (little endian).
 //
@@ -20,6 +20,9 @@
 //	<case>.go.bin : float64 rmsd[nframes]; rot[nframes*9]; trans1[nframes*3]; trans2[nframes*3];
 //	                moved[nframes*natoms*3] (the frames after chem.Super); int64 framesRead;
 //	                float64 rmsdtraj[natoms] (align.RMSDTraj over the ORIGINAL frames, chunk = cpus)
+//	<case>.lovo.in.bin : the same header and ref / frames blocks (nidx = 0): the input of align.LOVO -- the frames are written
+//	                to a DCD file first (dcd.NewWriter), every atom is a CA of chain A with MolID i+1, lessThanRMSD 1.0, minimumN 10
+//	<case>.lovo.go.bin : int64 N, framesRead, iterations, nNatoms, nRMSD; int64 Natoms[nNatoms]; float64 RMSD[nRMSD]
 package main
 
 import (
@@ -31,6 +34,7 @@ import (
 
 	chem "github.com/rmera/gochem"
 	"github.com/rmera/gochem/align"
+	"github.com/rmera/gochem/traj/dcd"
 	v3 "github.com/rmera/gochem/v3"
 )
 
@@ -154,6 +158,61 @@ func runCase(in string) {
 	fmt.Printf("%s: %d frames x %d atoms, fit on %d, RMSD[0] = %.12g, RMSDTraj read %d frames\n", filepath.Base(out), nframes, natoms, len(sel), rmsd[0], read)
 }
 
+func caTopology(natoms int64) *chem.Topology {
+	atoms := make([]*chem.Atom, natoms)
+	for i := range atoms {
+		a := new(chem.Atom)
+		a.Name = "CA"
+		a.Symbol = "C"
+		a.ID = i + 1
+		a.MolID = i + 1
+		a.MolName = "GLY"
+		a.Chain = "A"
+		atoms[i] = a
+	}
+	return chem.NewTopology(0, 1, atoms)
+}
+
+// align.LOVO on a DCD file written from the frames of the case (align/lovo.go:198-258)
+func runLovoCase(in string) {
+	f, err := os.Open(in)
+	must(err)
+	defer f.Close()
+	var hdr [4]int64
+	must(binary.Read(f, binary.LittleEndian, &hdr))
+	natoms, nframes, cpus := hdr[0], hdr[1], hdr[3]
+	ref := readF64(f, natoms*3)
+	frames := readF64(f, nframes*natoms*3)
+	tmp := strings.TrimSuffix(in, ".lovo.in.bin") + ".lovo.tmp.dcd"
+	w, err := dcd.NewWriter(tmp, int(natoms))
+	must(err)
+	for fr := int64(0); fr < nframes; fr++ {
+		must(w.WNext(matrix(clone(frames[fr*natoms*3 : (fr+1)*natoms*3]))))
+	}
+	w.Close()
+	defer os.Remove(tmp)
+	opt := align.DefaultOptions()
+	opt.Cpus(int(cpus))
+	opt.Begin(0)
+	opt.Skip(0)
+	opt.LessThanRMSD(1.0)
+	opt.MinimumN(10)
+	ret, err := align.LOVO(caTopology(natoms), matrix(clone(ref)), tmp, opt)
+	must(err)
+	out := strings.TrimSuffix(in, ".in.bin") + ".go.bin"
+	g, err := os.Create(out)
+	must(err)
+	defer g.Close()
+	nat := make([]int64, len(ret.Natoms))
+	for i, v := range ret.Natoms {
+		nat[i] = int64(v)
+	}
+	must(binary.Write(g, binary.LittleEndian, []int64{int64(ret.N), int64(ret.FramesRead), int64(ret.Iterations), int64(len(nat)), int64(len(ret.RMSD))}))
+	must(binary.Write(g, binary.LittleEndian, nat))
+	must(binary.Write(g, binary.LittleEndian, ret.RMSD))
+	fmt.Printf("%s: N = %d, %d frames read, %d iterations\n", filepath.Base(out), ret.N, ret.FramesRead, ret.Iterations)
+}
+
 func main() {
 	dir := "../../tests/golden/go_reference"
 	if len(os.Args) > 1 {
@@ -165,6 +224,10 @@ func main() {
 		must(fmt.Errorf("no *.in.bin under %s: run oracle/go_regen/export_inputs.py first", dir))
 	}
 	for _, in := range ins {
-		runCase(in)
+		if strings.HasSuffix(in, ".lovo.in.bin") {
+			runLovoCase(in)
+		} else {
+			runCase(in)
+		}
 	}
 }

@@ -68,6 +68,26 @@ def test_go_reference_outputs(golden_dir, name):
     assert np.abs(want - go["rmsdtraj"]).max() < 1e-9
 
 
+def test_go_reference_lovo_output(golden_dir, tmp_path):
+    """align.LOVO of the real goChem on the golden LOVO case (oracle/go_regen writes the frames to a DCD file and calls it):
+    N, the ordered atom list, the iteration count and the per-candidate means.  Skipped while that output is absent; the
+    exporter's file layout is checked either way."""
+    ex = _go_regen()
+    ex.OUT = str(tmp_path)
+    g = load(golden_dir, "lovo_n150_f42")
+    p = ex.export_lovo(os.path.join(golden_dir, "lovo_n150_f42.npz"))
+    assert [int(v) for v in np.fromfile(p, "<i8", 4)] == [g["ref"].shape[0], g["frames"].shape[0], 0, int(g["cpus"])]
+    path = os.path.join(golden_dir, "go_reference", "lovo_n150_f42.lovo.go.bin")
+    if not os.path.exists(path):
+        pytest.skip("no output of the Go reference committed (oracle/go_regen/main.go needs a Go toolchain)")
+    go = ex.read_lovo_outputs(path)
+    ref, frames = g["ref"].astype(np.float64), g["frames"].astype(np.float64)
+    want = oracle.lovo(frames, ref, list(range(ref.shape[0])), int(g["cpus"]), less_than_rmsd=1.0, minimum_n=10)
+    assert (go["N"], go["Iterations"], go["FramesRead"]) == (want["N"], want["Iterations"], want["FramesRead"])
+    assert list(go["Natoms"]) == list(want["Natoms"])
+    assert np.abs(go["RMSD"] - want["RMSD"]).max() < 1e-9
+
+
 @pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
 def test_c_oracle_matches_golden(golden_dir, name):
     g = load(golden_dir, name)
