@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(kTfThreads) transform_frames_kernel(double* __
     }
 }
 
+#ifndef GCB_ACC_UNROLL
+#define GCB_ACC_UNROLL 4   // frames in flight per thread in the column-owning sweeps
+#endif
+constexpr int kAccUnroll = GCB_ACC_UNROLL;
 constexpr int kAccFrames = 32;   // per-frame transforms staged in shared memory at a time
 
 // CTA (tile, split): double2 columns [tile*256, tile*256+256) of the frames [f0, f1) of its split; the two per-atom sums of a
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_kernel(const double*
         __syncthreads();
         if (!in) continue;
         const double* fr = frames + fb * frame_stride;
-#pragma unroll 4
+#pragma unroll kAccUnroll
         for (int ff = 0; ff < nb; ff++, fr += frame_stride) {
             const double2 x = __ldcs(reinterpret_cast<const double2*>(fr) + j);
             const double2 y = __ldcs(reinterpret_cast<const double2*>(fr + np) + j);
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kTfThreads) transform_cols_kernel(double* __re
         __syncthreads();
         if (!in) continue;
         double* fr = frames + fb * frame_stride;
-#pragma unroll 4
+#pragma unroll kAccUnroll
         for (int ff = 0; ff < nb; ff++, fr += frame_stride) {
             double2* X = reinterpret_cast<double2*>(fr) + j;
             double2* Y = reinterpret_cast<double2*>(fr + np) + j;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kTfThreads) peratom_accum_gather_kernel(const 
         __syncthreads();
         if (!in) continue;
         const double* fr = frames + fb * frame_stride + at;
-#pragma unroll 4
+#pragma unroll kAccUnroll
         for (int ff = 0; ff < nb; ff++, fr += frame_stride) {
             const double x = __ldg(fr), y = __ldg(fr + np), z = __ldg(fr + 2L * np);
             const double* xf = s_xf[ff];
