@@ -453,6 +453,38 @@ int gch_xtc_read(const char* path, double* out, long cap, long* nframes, int* na
 }
 
 
+/* chem.Rhos + chem.RhoShapeIndexes on a 3 x 3 moment tensor (CPU only) */
+int gch_rhos_shape(const double* moment9, double* rhos3, double* linear, double* circular) {
+    v3::Matrix m = v3::Matrix::Zeros(3);
+    memcpy(m.data(), moment9, sizeof(double) * 9);
+    std::vector<double> rhos;
+    Error e = chem::Rhos(m, &rhos);
+    for (size_t i = 0; i < 3 && i < rhos.size(); i++) rhos3[i] = rhos[i];
+    if (e) { *linear = -1; *circular = -1; return fail(e); }
+    return ret(chem::RhoShapeIndexes(rhos, linear, circular));
+}
+
+/* chem.EasyShape of one structure (masses may be NULL) */
+int gch_easy_shape(const double* coords, int n, const double* masses, double* linear, double* circular) {
+    v3::Matrix c = v3::Matrix::Zeros(n);
+    memcpy(c.data(), coords, sizeof(double) * 3 * (size_t)n);
+    chem::Topology top;
+    if (masses) {
+        top.Atoms.resize((size_t)n);
+        for (int i = 0; i < n; i++) top.Atoms[(size_t)i].Mass = masses[i];
+    }
+    return ret(chem::EasyShape(c, -1, masses ? &top : nullptr, linear, circular));
+}
+
+/* chem.EasyShape for every frame of a window of a device trajectory (gcb_traj handle) */
+int gch_easy_shape_traj(void* traj, long first, long nframes, const double* masses, int nmasses, double* linear, double* circular) {
+    std::vector<double> m, lin, circ;
+    if (masses) m.assign(masses, masses + nmasses);
+    Error e = chem::EasyShapeTraj((gcb_traj*)traj, first, nframes, m, &lin, &circ);
+    for (long f = 0; f < nframes && (size_t)f < lin.size(); f++) { linear[f] = lin[(size_t)f]; circular[f] = circ[(size_t)f]; }
+    return ret(e);
+}
+
 int gch_stf_zstd_available(void) { return stf::StfR::ZstdAvailable() ? 1 : 0; }
 
 /* header_text: "key=value\n" lines or NULL */

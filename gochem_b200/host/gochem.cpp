@@ -1627,6 +1627,21 @@ static void symEigenvalues3(const double* m, double* ev) {
     ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
 }
 
+// chem.Rhos on the nine numbers of a moment tensor
+static Error rhosOf(const double* moment9, std::vector<double>* rhos) {
+    double ev[3];
+    symEigenvalues3(moment9, ev);
+    std::sort(ev, ev + 3);  // EigenWrap sorts the pairs by eigenvalue, ascending (v3/gonum.go:343-345, 400-401)
+    // geometric.go:534-537 tests evals[2] of the ascending list, the LARGEST eigenvalue: only a structure without any extent fails,
+    // and the values go back in ascending order then
+    if (ev[2] <= kAppZero) {
+        rhos->assign({ev[0], ev[1], ev[2]});
+        return Error("goChem: Molecule colapsed to a single point. Check for blackholes", {"Rhos"});
+    }
+    rhos->assign({ev[2], ev[1], ev[0]});  // largest first (geometric.go:538-544)
+    return Error();
+}
+
 Error EllipsoidAxes(const v3::Matrix& coords, double /*epsilon*/, const chem::Topology* mol, std::vector<double>* rhos) {
     std::vector<double> masses;
     Error err2;
@@ -1635,14 +1650,63 @@ Error EllipsoidAxes(const v3::Matrix& coords, double /*epsilon*/, const chem::To
     }
     v3::Matrix moment;
     if (Error e = chem::MomentTensor(coords, &moment, masses)) return e;
-    double ev[3];
-    symEigenvalues3(moment.data(), ev);
-    std::sort(ev, ev + 3);  // EigenWrap sorts the pairs by eigenvalue, ascending (v3/gonum.go:343-345, 400-401)
-    if (ev[2] <= kAppZero)  // geometric.go:535-537
-        return Error("goChem: Molecule colapsed to a single point. Check for blackholes", {"Rhos"});
-    rhos->assign({ev[2], ev[1], ev[0]});  // largest first (geometric.go:538-544)
+    if (Error e = rhosOf(moment.data(), rhos)) return e;
     return err2;
 }
+
+}  // namespace solv
+
+namespace chem {
+
+Error Rhos(const v3::Matrix& momentTensor, std::vector<double>* rhos, double /*epsilon*/) {
+    if (momentTensor.NVecs() != 3) return Error("error in EigenWrap: mat.Eigen.Factorize", {"Rhos"});
+    return solv::rhosOf(momentTensor.data(), rhos);
+}
+
+Error RhoShapeIndexes(const std::vector<double>& rhos, double* linear, double* circular) {
+    if (rhos.size() < 3) { *linear = -1; *circular = -1; return Error("goChe: Not enough or nil rhos", {"RhoShapeIndexes"}); }
+    *linear = (1 - (rhos[1] / rhos[0])) * 100;     // prolate
+    *circular = (1 - (rhos[2] / rhos[1])) * 100;   // oblate
+    return Error();
+}
+
+Error EasyShape(const v3::Matrix& coords, double /*epsilon*/, const Topology* mol, double* linear, double* circular) {
+    *linear = -1; *circular = -1;
+    std::vector<double> masses;
+    Error err2;
+    if (mol) {
+        if (Error e = mol->Masses(&masses)) { masses.clear(); err2 = e; }   // handy.go:110-116
+    }
+    v3::Matrix moment;
+    if (Error e = MomentTensor(coords, &moment, masses)) return e;
+    std::vector<double> rhos;
+    if (Error e = Rhos(moment, &rhos)) return e;
+    if (Error e = RhoShapeIndexes(rhos, linear, circular)) return e;
+    return err2;
+}
+
+Error EasyShapeTraj(gcb_traj* t, long first, long nframes, const std::vector<double>& masses, std::vector<double>* linear,
+                    std::vector<double>* circular) {
+    linear->assign((size_t)nframes, -1.0);
+    circular->assign((size_t)nframes, -1.0);
+    if (nframes <= 0) return Error();
+    if (!masses.empty() && (int)masses.size() != gcb_traj_natoms(t)) return Error("MomentTensor: as many masses as atoms are needed", {"EasyShapeTraj"});
+    std::vector<double> center(3 * (size_t)nframes), moment(9 * (size_t)nframes);
+    int rc = gcb_moments(t, first, nframes, masses.empty() ? nullptr : masses.data(), nullptr, 0, center.data(), moment.data());
+    if (rc) return deviceError(rc, "MomentTensor");
+    Error firstErr;
+    std::vector<double> rhos;
+    for (long f = 0; f < nframes; f++) {
+        Error e = solv::rhosOf(moment.data() + 9 * (size_t)f, &rhos);
+        if (!e) e = RhoShapeIndexes(rhos, &(*linear)[(size_t)f], &(*circular)[(size_t)f]);
+        if (e && !firstErr) firstErr = errDecorate(e, "EasyShapeTraj: frame " + std::to_string(first + f));
+    }
+    return firstErr;
+}
+
+}  // namespace chem
+
+namespace solv {
 
 Error MDFFromCDF(std::vector<double>& ret, int framesread, double A, double B, double step, std::vector<double>* ret2) {
     if (A < 1.0 || B < 1.0)

@@ -103,6 +103,20 @@ Error MemPerAtomRMSD(const v3::Matrix& test, const v3::Matrix& templa, v3::Matri
 // geometric.go:609-631 and :705-733.  mass empty = unit masses (geometric centre).
 Error CenterOfMass(const v3::Matrix& geometry, v3::Matrix* center, const std::vector<double>& mass = {});
 Error MomentTensor(const v3::Matrix& A, v3::Matrix* moment, const std::vector<double>& mass = {});
+// geometric.go:523-545: the eigenvalues of the moment tensor, largest first (v3.EigenWrap sorts them; a smallest eigenvalue
+// <= appzero is the "collapsed to a single point" error, with the eigenvalues still returned as the reference does)
+Error Rhos(const v3::Matrix& momentTensor, std::vector<double>* rhos, double epsilon = -1);
+// geometric.go:511-520: linear (prolate) and circular (oblate) distortion in percent
+Error RhoShapeIndexes(const std::vector<double>& rhos, double* linear, double* circular);
+// handy.go:103-129: MomentTensor -> Rhos -> RhoShapeIndexes; (-1, -1) with the error on failure; a Masses() failure falls back
+// to unit masses and comes back as the error beside valid indexes, as in the reference
+class Topology;
+Error EasyShape(const v3::Matrix& coords, double epsilon, const Topology* mol, double* linear, double* circular);
+// The same for every resident frame of a device trajectory (SURVEY §8 f rank 3): the moment tensors come from one sweep on the
+// device (gcb_moments), the 3 x 3 eigenvalues and the indexes are formed on the host.  A frame that fails (collapsed) gets -1, -1
+// and the first such error is returned after all frames are done.
+Error EasyShapeTraj(gcb_traj* t, long first, long nframes, const std::vector<double>& masses, std::vector<double>* linear,
+                    std::vector<double>* circular);
 
 // Topology side: only what align.res2atoms reads (chem.go Atom fields, lovo.go:504-516).
 struct Atom {

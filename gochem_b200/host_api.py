@@ -368,3 +368,37 @@ def stf_read(path, cap_frames, natoms, raw=False, want_box=False):
     header = dict(line.split("=", 1) for line in head.value.decode().splitlines() if "=" in line)
     res = (out[: min(nf.value, cap_frames)], nf.value, na.value, header)
     return res + (box,) if want_box else res
+
+
+# ---- chem.Rhos / RhoShapeIndexes / EasyShape (geometric.go:511-545, handy.go:103-129) ----
+def rhos_shape(moment):
+    m = np.ascontiguousarray(moment, dtype=np.float64)
+    rhos = np.zeros(3)
+    lin, circ = C.c_double(0), C.c_double(0)
+    rc = load().gch_rhos_shape(_d(m), _d(rhos), C.byref(lin), C.byref(circ))
+    if rc:
+        raise _err(rc)
+    return rhos, lin.value, circ.value
+
+
+def EasyShape(coords, masses=None):
+    c = np.ascontiguousarray(coords, dtype=np.float64)
+    m = None if masses is None else np.ascontiguousarray(masses, dtype=np.float64)
+    lin, circ = C.c_double(0), C.c_double(0)
+    rc = load().gch_easy_shape(_d(c), c.shape[0], _d(m) if m is not None else None, C.byref(lin), C.byref(circ))
+    if rc:
+        raise _err(rc)
+    return lin.value, circ.value
+
+
+def EasyShapeTraj(traj, masses=None, first=0, nframes=None):
+    """EasyShape of every frame of a _lib.DeviceTraj -> (linear[], circular[])."""
+    n = traj.nframes - first if nframes is None else nframes
+    m = None if masses is None else np.ascontiguousarray(masses, dtype=np.float64)
+    lin, circ = np.zeros(n), np.zeros(n)
+    fn = load().gch_easy_shape_traj
+    fn.argtypes = [C.c_void_p, C.c_long, C.c_long, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rc = fn(traj.h, first, n, _d(m) if m is not None else None, 0 if m is None else m.size, _d(lin), _d(circ))
+    if rc:
+        raise _err(rc)
+    return lin, circ

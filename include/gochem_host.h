@@ -107,6 +107,12 @@ int gch_stf_read(const char *path, double *out_aos, long cap_frames, long *nfram
  * the file through a device window instead of making it resident.  comm may be NULL. */
 int gch_mdf_from_cdf(double *ret, int n, int framesread, double A, double B, double step, double *ret2);
 int gch_ellipsoid_axes(const double *coords, int n, const double *masses, double *rhos3);
+/* chem.Rhos + chem.RhoShapeIndexes (geometric.go:511-545) on a 3 x 3 moment tensor; chem.EasyShape (handy.go:103-129) of one
+ * structure; and EasyShape for every frame of a window of a device trajectory (moment tensors from gcb_moments, eigenvalues on
+ * the host; SURVEY section 8 f rank 3).  A collapsed structure gives -1, -1 and an error. */
+int gch_rhos_shape(const double *moment9, double *rhos3, double *linear, double *circular);
+int gch_easy_shape(const double *coords, int n, const double *masses, double *linear, double *circular);
+int gch_easy_shape_traj(void *traj, long first, long nframes, const double *masses, int nmasses, double *linear, double *circular);
 int gch_conc_mol_rdf(const char *dcd_path, const double *coords0, int natoms, const char *const *molnames, const int *molids,
                      const char *const *chains, const double *masses, const int *refidx, int nref, const char *const *residues,
                      int nres, int com, int cpus, double step, double end, long window_frames, int dev, int rank, int nranks,

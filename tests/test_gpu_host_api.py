@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
+from gochem_b200 import _lib
 from gochem_b200 import host_api as H
 from gochem_b200 import synth
 
@@ -219,3 +220,35 @@ def test_lovo_on_a_solvated_system_reads_the_candidates_only(tmp_path):
     assert got["N"] == want["N"] and got["Iterations"] == want["Iterations"] and got["FramesRead"] == want["FramesRead"]
     assert list(got["Natoms"]) == list(want["Natoms"])
     assert np.abs(got["RMSD"] - want["RMSD"]).max() < 1e-10
+
+
+def test_easy_shape_single_and_batched():
+    """chem.EasyShape (handy.go:103-129) of one structure and of every resident frame (moment tensors from the device sweep,
+    eigenvalues on the host): against numpy on M = sum m (x - c)(x - c)^T, c the centre of mass (geometric.go:670-733)."""
+    natoms, nframes = 700, 37
+    ref, frames = synth.make_case(natoms, nframes)
+    frames[:, :, 0] *= 2.5                       # make the ellipsoid clearly prolate
+    mass = np.linspace(1.0, 16.0, natoms)
+
+    def shape(x, m):
+        c = (x * m[:, None]).sum(0) / m.sum()
+        d = (x - c) * np.sqrt(m)[:, None]
+        ev = np.sort(np.linalg.eigvalsh(d.T @ d))[::-1]
+        return (1 - ev[1] / ev[0]) * 100, (1 - ev[2] / ev[1]) * 100
+
+    for m in (None, mass):
+        lin, circ = H.EasyShape(frames[3], m)
+        wl, wc = shape(frames[3], np.ones(natoms) if m is None else m)
+        assert abs(lin - wl) < 1e-8 and abs(circ - wc) < 1e-8
+        t = _lib.DeviceTraj(natoms, nframes)
+        t.upload(frames)
+        L, Cc = H.EasyShapeTraj(t, m)
+        for f in range(nframes):
+            wl, wc = shape(frames[f], np.ones(natoms) if m is None else m)
+            assert abs(L[f] - wl) < 1e-8 and abs(Cc[f] - wc) < 1e-8
+        L2, _ = H.EasyShapeTraj(t, m, first=5, nframes=4)
+        assert np.array_equal(L2, L[5:9])
+        t.close()
+    # every atom on one point: the reference's "collapsed" error, -1 / -1
+    with pytest.raises(H.GoChemError, match="colapsed"):
+        H.EasyShape(np.zeros((10, 3)))

@@ -485,3 +485,20 @@ def test_stf_lzw_form(tmp_path):
         f.write(raw[: len(raw) // 2])
     with pytest.raises(H.GoChemError):
         H.stf_read(str(tmp_path / "cut.stl"), 50, 400)
+
+
+def test_rhos_and_shape_indexes():
+    """chem.Rhos (geometric.go:523-545): eigenvalues of the moment tensor, largest first; chem.RhoShapeIndexes (:511-520);
+    the 'collapsed to a single point' error when even the largest eigenvalue vanishes."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        a = rng.normal(0, 1, (3, 3)) * rng.uniform(0.1, 30)
+        m = a @ a.T
+        rhos, lin, circ = H.rhos_shape(m)
+        want = np.sort(np.linalg.eigvalsh(m))[::-1]
+        assert np.abs(rhos - want).max() < 1e-10 * max(1.0, want[0])
+        assert abs(lin - (1 - want[1] / want[0]) * 100) < 1e-8 and abs(circ - (1 - want[2] / want[1]) * 100) < 1e-6
+    rhos, lin, circ = H.rhos_shape(np.diag([4.0, 1.0, 0.25]))
+    assert rhos.tolist() == [4.0, 1.0, 0.25] and lin == 75.0 and circ == 75.0
+    with pytest.raises(H.GoChemError, match="colapsed to a single point"):
+        H.rhos_shape(np.zeros((3, 3)))
