@@ -8,7 +8,13 @@ A "step" is one pass of chem.Super + chem.RMSD (fit mode: RMSD, rotation, transl
 rewritten) over the whole resident trajectory of BASELINE.json configs[1]: 100,000 frames x 10,000
 atoms per GPU, float64 SoA, 24 GB in HBM -- far larger than the 126 MB L2, so nothing is cached between
 timed iterations.  N > 1: every rank holds its own 100k-frame shard (weak scaling), no data-path
-collective.  Prints ONE JSON line (rank 0).
+collective in that region.  Prints ONE JSON line (rank 0).
+
+After the timed region the same line gets sub-records, each with its own device timing, for the other BASELINE configs and
+chem.Super's write-back mode: `super_mode` (48 B/atom), `lovo` (configs[2]: 50k x 5k, frames sharded over the ranks, the
+per-atom sums combined through the library's own communicator), `allpairs` (configs[3]: 20k x 3k fp64 DMMA, tiles gathered over
+NVLink at N > 1, cuBLAS DGEMM on the same box beside it), `stream` (configs[4]: this GPU's 125k-frame share streamed from pinned
+host memory as raw DCD records).  --no-extra skips them.
 """
 from __future__ import annotations
 
@@ -45,6 +51,14 @@ def parse():
     ap.add_argument("--write-back", type=int, default=0, help="1 = Super mode (frames rewritten, 48 B/atom)")
     ap.add_argument("--variant", default="auto", choices=["auto", "generic", "cluster"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the super_mode / lovo / allpairs / stream records")
+    ap.add_argument("--lovo-atoms", type=int, default=5000)
+    ap.add_argument("--lovo-frames", type=int, default=50000, help="total over all GPUs (BASELINE configs[2])")
+    ap.add_argument("--lovo-check-frames", type=int, default=2048)
+    ap.add_argument("--pairs-atoms", type=int, default=3000)
+    ap.add_argument("--pairs-frames", type=int, default=20000, help="BASELINE configs[3]")
+    ap.add_argument("--stream-atoms", type=int, default=20000)
+    ap.add_argument("--stream-frames", type=int, default=125000, help="per GPU (BASELINE configs[4]: 1M frames over 8 GPUs)")
     return ap.parse_args()
 
 
@@ -212,6 +226,286 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- our arm
+def make_comm(d, _lib, dev):
+    """The product's own NCCL communicator (csrc/comm.cu: gcb_comm_init).  torch.distributed only carries the 128-byte unique id."""
+    if d.world == 1:
+        return _lib.Comm(dev, 1, 0, _lib.Comm.unique_id())
+    torch = d.torch
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if d.rank == 0:
+        uid = torch.tensor(list(_lib.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+    d.dist.broadcast(uid, 0)
+    return _lib.Comm(dev, d.world, d.rank, bytes(uid.cpu().tolist()))
+
+
+def sub_super_mode(a, d, traj, ref, peak):
+    """chem.Super's own semantics on config 2: every frame rewritten in place (handy.go:207-211), 48 B per atom."""
+    natoms, nframes = a.atoms, a.frames
+    for _ in range(2):
+        traj.super_rmsd_async(ref, write_back=True)
+    traj.sync()
+    d.barrier()
+    steps = 5
+    traj.timer_start()
+    for _ in range(steps):
+        traj.super_rmsd_async(ref, write_back=True)
+    ms = d.max(traj.timer_stop()) / steps
+    alg = 48.0 * natoms * nframes
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"workload": f"chem.Super with write-back + RMSD, {nframes} frames x {natoms} atoms per GPU (BASELINE configs[1], Super mode)",
+            "value": nframes * d.world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": alg, "traffic": recorded_traffic(1)},
+            "cluster_plan": traj.last_cluster_plan()}
+
+
+def sub_lovo(a, d, comm, dev, peak):
+    """BASELINE configs[2]: align.LOVO, 50 000 frames x 5 000 atoms in total, frames sharded over the ranks, the per-atom
+    deviation sums combined across ranks by the library's own communicator (gcb_peratom_dev_sum(..., comm))."""
+    import zlib
+
+    from gochem_b200 import _lib, synth
+    from gochem_b200 import host_api as H
+
+    natoms, total = a.lovo_atoms, a.lovo_frames
+    ref, sig = synth.make_reference(natoms), synth.atom_sigmas(natoms)
+    first, count = H.shard_range(total, d.rank, d.world)
+    t = _lib.DeviceTraj(natoms, max(count, 1), dev=dev)
+    t.synth_fill(ref, sig, count, frame_id0=first)
+    t.sync()
+    kw = dict(nselected_total=total, cpus=8, comm=comm if d.world > 1 else None, rank=d.rank, nranks=d.world)
+    got = H.LOVOResident(t, ref, **kw)          # warm-up: allocations, NCCL connections
+    runs = []
+    for _ in range(3):
+        d.barrier()
+        t0 = time.perf_counter()
+        got = H.LOVOResident(t, ref, **kw)
+        t.sync()
+        runs.append(d.max(time.perf_counter() - t0))
+    best = min(runs)
+    # one RMSDTraj pass (what every LOVO iteration costs on the device): subset fit + per-atom distances + the exchange
+    idx = np.ascontiguousarray(got["Natoms"], dtype=np.int32) if got["N"] > 0 else np.arange(natoms, dtype=np.int32)
+    c = comm if d.world > 1 else None
+    for _ in range(2):
+        t.peratom_dev_sum(ref, idx, comm=c)
+    d.barrier()
+    reps = 5
+    t.timer_start()
+    for _ in range(reps):
+        t.peratom_dev_sum(ref, idx, comm=c)
+    pass_ms = d.max(t.timer_stop()) / reps
+    plan = t.last_cluster_plan()
+    walls = []
+    for _ in range(reps):
+        d.barrier()
+        t0 = time.perf_counter()
+        t.peratom_dev_sum(ref, idx, comm=c)
+        walls.append(time.perf_counter() - t0)
+    pass_wall_ms = d.max(min(walls)) * 1e3
+    alg = 24.0 * natoms * count
+    ach = alg / (pass_ms * 1e-3) / 1e9
+    rec = {"workload": f"align.LOVO, {total} frames x {natoms} atoms (BASELINE configs[2]), frames sharded x{d.world}, "
+                       "lessThanRMSD 1.0, minimumN 10, chunk 8",
+           "lovo_ms_best_of_3": best * 1e3, "lovo_ms_runs": [r * 1e3 for r in runs], "iterations": got["Iterations"], "N": got["N"],
+           "natoms_crc32": zlib.crc32(np.ascontiguousarray(got["Natoms"], dtype=np.int32).tobytes()),
+           "frames_per_s_per_iteration": total * got["Iterations"] / best,
+           "pass_ms_device": pass_ms, "pass_ms_wall": pass_wall_ms, "pass_frames_per_s": total / (pass_ms * 1e-3),
+           "pass_fit_atoms": int(idx.size),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "algorithmic_bytes_per_launch": alg,
+                        "note": "per GPU: 24 B/atom/frame of this rank's shard, one fused kernel (fit on the subset + per-atom distances); "
+                                "the device time of the pass includes the cross-rank sum"},
+           "collective": ("gcb_peratom_dev_sum(comm): per-rank sums into peer-mapped slots over NVLink + rank-ordered sum, "
+                          f"{natoms * 8} bytes per rank per iteration") if d.world > 1 else None,
+           "cluster_plan": plan}
+    # Natoms equality against the oracle on a stated subsample (rank 0, its first frames, single-rank LOVO on both sides)
+    if d.rank == 0 and not a.no_cpu_baseline:
+        import oracle
+
+        sub = min(a.lovo_check_frames, count)
+        sub -= sub % 8
+        frames = t.download(0, sub)
+        ts = _lib.DeviceTraj(natoms, sub, dev=dev)
+        ts.upload(frames)
+        g = H.LOVOResident(ts, ref, cpus=8)
+        ts.close()
+        t0 = time.perf_counter()
+        w = oracle.lovo(frames, ref, np.arange(natoms), cpus=8, less_than_rmsd=1.0, minimum_n=10, nthreads=os.cpu_count() or 1)
+        cpu_s = time.perf_counter() - t0
+        rec["check_vs_oracle"] = {"frames": sub, "N_equal": bool(g["N"] == w["N"]), "iterations_equal": bool(g["Iterations"] == w["Iterations"]),
+                                  "natoms_ordered_list_equal": bool(list(g["Natoms"]) == list(w["Natoms"])),
+                                  "max_abs_rmsd_diff": float(np.abs(g["RMSD"] - w["RMSD"]).max()),
+                                  "oracle_seconds": cpu_s, "oracle_frames_per_s_per_iteration": sub * w["Iterations"] / cpu_s}
+    t.close()
+    return rec
+
+
+def sub_allpairs(a, d, comm, dev):
+    """BASELINE configs[3]: all-pairs RMSD matrix of 20 000 frames x 3 000 atoms as fp64 DMMA GEMM tiles; at N > 1 the tiles are
+    dealt over the ranks and stored straight into the owners' row blocks over NVLink (gcb_allpairs_rmsd_sharded)."""
+    from gochem_b200 import _lib, synth
+    from gochem_b200 import host_api as H
+
+    natoms, nframes = a.pairs_atoms, a.pairs_frames
+    ref, sig = synth.make_reference(natoms), synth.atom_sigmas(natoms)
+    counts = [H.shard_range(nframes, r, d.world)[1] for r in range(d.world)]
+    first = sum(counts[:d.rank])
+    t = _lib.DeviceTraj(natoms, nframes, dev=dev)
+    t.synth_fill(ref, sig, counts[d.rank], first=first, frame_id0=first)
+    t.set_nframes(nframes)
+    t.super_rmsd(ref, first=first, nframes=counts[d.rank], write_back=True, want=())    # definition (i): frames pre-superposed
+    t.sync()
+    gather_ms = 0.0
+    if d.world > 1:
+        t.allgather(comm, counts)        # first NCCL broadcast: connection set-up
+        d.barrier()
+        t.timer_start()
+        t.allgather(comm, counts)
+        gather_ms = d.max(t.timer_stop())
+    out = {}
+    for fit in (False, True):
+        t.allpairs_rmsd_sharded(comm, fit=fit, fetch=False)       # warm-up: blocks allocated and mapped
+        res = []
+        for _ in range(2 if fit else 3):
+            _, row0, gms, tms, redone = t.allpairs_rmsd_sharded(comm, fit=fit, fetch=False)
+            res.append((gms, tms))
+        gemm = d.max(min(r[0] for r in res))
+        tot = d.max(min(r[1] for r in res))
+        npad = (natoms + 15) // 16 * 16
+        tf, side, kdim = (32, 96, npad) if fit else (128, 128, 3 * npad)
+        nt = (nframes + tf - 1) // tf
+        flops = 2.0 * (nt * (nt + 1) // 2) * side * side * kdim       # the tiles on or above the diagonal, as executed
+        out["per_pair_fit" if fit else "no_fit"] = {
+            "total_ms": tot, "gemm_ms_max_over_ranks": gemm, "dmma_tflops_aggregate": flops / (tot * 1e-3) / 1e12,
+            "dmma_tflops_per_gpu_kernel": flops / d.world / (gemm * 1e-3) / 1e12, "pairs_redone_explicitly": int(redone),
+            "flops_executed": flops}
+    rec = {"workload": f"all-pairs RMSD matrix, {nframes} frames x {natoms} atoms (BASELINE configs[3]), fp64 DMMA (mma.sync.m8n8k4.f64)",
+           "frames_allgather_ms": gather_ms, **out,
+           "matrix": f"{nframes} x {nframes} fp64, row blocks left on their owners' devices ({nframes * nframes * 8 / d.world / 1e9:.2f} GB per rank)",
+           "collective": ("tiles dealt round-robin; every finished tile and its mirror image stored into the owners' blocks through "
+                          "cudaIpc peer mappings (comm_peer_blocks), NCCL only for the frame all-gather and the two barriers") if d.world > 1 else None}
+    t.close()
+    # the library it replaces, same box: cuBLAS DGEMM through torch.matmul on the same operand shape (rank 0)
+    if d.rank == 0:
+        try:
+            import torch
+
+            torch.cuda.set_device(dev)
+            x = torch.randn(nframes, 3 * natoms, dtype=torch.float64, device="cuda")
+            y = torch.empty(nframes, nframes, dtype=torch.float64, device="cuda")
+            torch.matmul(x, x.t(), out=y)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e30
+            for _ in range(2):
+                e0.record()
+                torch.matmul(x, x.t(), out=y)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            del x, y
+            torch.cuda.empty_cache()
+            full = 2.0 * nframes * nframes * 3 * natoms
+            rec["cublas_dgemm_same_box"] = {"ms_full_product": best, "tflops": full / (best * 1e-3) / 1e12,
+                                            "note": "torch.matmul fp64 (cuBLAS), X X^T with X = [frames x 3 atoms], whole product (no symmetry)"}
+            rec["no_fit"]["kernel_rate_vs_cublas"] = rec["no_fit"]["dmma_tflops_per_gpu_kernel"] / rec["cublas_dgemm_same_box"]["tflops"]
+        except Exception as exc:   # informational
+            rec["cublas_dgemm_same_box"] = {"error": str(exc)[:200]}
+    d.barrier()
+    return rec
+
+
+def sub_stream(a, d, dev, ref_unused=None):
+    """BASELINE configs[4], this GPU's share: frames streamed from C-owned pinned host memory through the reader staging path
+    (raw DCD records: gcb_traj_upload_records_async, float32 planes picked out of the records on the device) into the fused pass."""
+    from gochem_b200 import _lib, synth
+
+    lib = _lib.load()
+    natoms, nframes = a.stream_atoms, a.stream_frames
+    ref, sig = synth.make_reference(natoms), synth.atom_sigmas(natoms)
+    # a DCD frame as it sits in the file: [4-byte marker | x[] | marker][marker | y[] | marker][marker | z[] | marker] (dcd.go:380-413)
+    plane = 4 * natoms
+    rec_bytes = 3 * (plane + 8)
+    off = (4, plane + 12, 2 * plane + 20)
+    stage = 64 << 20
+    chunk = max(1, stage // rec_bytes)
+    src = _lib.DeviceTraj(natoms, chunk, dev=dev)
+    src.synth_fill(ref, sig, chunk, through_f32=True)
+    host = src.download().astype(np.float32)
+    src.close()
+    affinity = os.sched_getaffinity(0)
+    lib.gcb_bind_host_thread(dev)
+    ring = [_lib.PinnedBuffer(chunk * rec_bytes) for _ in range(2)]
+    for r in ring:
+        v = r.u8[: chunk * rec_bytes].reshape(chunk, rec_bytes)
+        for c in range(3):
+            v[:, off[c] - 4: off[c]] = np.frombuffer(np.int32(plane).tobytes(), dtype=np.uint8)
+            v[:, off[c]: off[c] + plane] = np.ascontiguousarray(host[:, :, c]).view(np.uint8).reshape(chunk, plane)
+            v[:, off[c] + plane: off[c] + plane + 4] = np.frombuffer(np.int32(plane).tobytes(), dtype=np.uint8)
+    os.sched_setaffinity(0, affinity)
+    t = _lib.DeviceTraj(natoms, 2 * chunk, dev=dev)
+    nchunks = (nframes + chunk - 1) // chunk
+
+    def run(compute):
+        t.sync()
+        d.barrier()
+        t0 = time.perf_counter()
+        done = 0
+        for c in range(nchunks):
+            n = min(chunk, nframes - done)
+            s = c & 1
+            t.wait(s)                                     # the reader may refill ring slot s from here on
+            _lib.check(lib.gcb_traj_upload_records_async(t.h, s * chunk, ring[s].ptr, n, rec_bytes, off[0], off[1], off[2], 1.0, s))
+            if compute:
+                t.super_rmsd_async(ref, first=s * chunk, nframes=n)
+            done += n
+        t.sync()
+        return d.max(time.perf_counter() - t0)
+
+    run(True)
+    copy_only = run(False)
+    total = run(True)
+    rm = t.fetch(0, chunk, want=("rmsd",))["rmsd"]
+    want = None
+    if d.rank == 0 and not a.no_cpu_baseline:
+        import oracle
+
+        want = oracle.super_rmsd_traj(host[:8].astype(np.float64), ref, None, details=False)
+    rec = {"workload": f"{nframes} frames x {natoms} atoms per GPU streamed from pinned host memory as raw DCD records "
+                       f"(BASELINE configs[4]: 1M x 20k over 8 GPUs = 125 000 frames per GPU), x{d.world} GPUs at once",
+           "value": nframes * d.world / total, "unit": UNIT, "seconds": total, "h2d_GBs_per_gpu": nframes * rec_bytes / total / 1e9,
+           "copy_only_seconds": copy_only, "overlap_efficiency": copy_only / total, "chunk_frames": chunk,
+           "bound": "PCIe host->device", "rmsd_first_frames_vs_oracle_max_abs": (float(np.abs(rm[:8] - want).max()) if want is not None else None)}
+    t.close()
+    for r in ring:
+        r.free()
+    return rec
+
+
+def bare_copy_bandwidth(d, dev, nbytes, steps):
+    """Bare pinned cudaMemcpyAsync host->device on all ranks at once (no kernels, torch's copy engine call): the ceiling of the e2e leg."""
+    try:
+        import torch
+
+        torch.cuda.set_device(dev)
+        src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        src.zero_()
+        dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        d.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = d.max(time.perf_counter() - t0)
+        del src, dst
+        torch.cuda.empty_cache()
+        return nbytes * steps / dt / 1e9
+    except Exception:
+        return None
+
+
 def run_ours(a):
     from gochem_b200 import _lib, synth
 
@@ -221,14 +515,15 @@ def run_ours(a):
     d = Dist(a.gpus, cuda=True)
     dev = d.local
     variant = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "cluster": _lib.KERNEL_CLUSTER}[a.variant]
-    _lib.check(lib.gcb_set_kernel_variant(variant))
     natoms, nframes = a.atoms, a.frames
     ref = synth.make_reference(natoms)
     sig = synth.atom_sigmas(natoms)
     traj = _lib.DeviceTraj(natoms, nframes, dev=dev)
+    traj.set_kernel_variant(variant)
     # every rank generates its own shard: global frame ids [rank*F, (rank+1)*F)
     traj.synth_fill(ref, sig, nframes, frame_id0=d.rank * nframes, frame0_is_ref=True)
     wb = bool(a.write_back)
+    comm = make_comm(d, _lib, dev)     # the library's own NCCL communicator: used by the LOVO and all-pairs records below
 
     def step():
         traj.super_rmsd_async(ref, write_back=wb)
@@ -253,7 +548,7 @@ def run_ours(a):
     ms_per_step = ms / a.steps
     total_frames = nframes * d.world
     value = total_frames / (ms_per_step * 1e-3)
-    plan = _lib.last_cluster_plan() if a.variant != "generic" else None
+    plan = traj.last_cluster_plan() if a.variant != "generic" else None
     res = traj.fetch(want=("rmsd",))
     rmsd_gpu = res["rmsd"]
 
@@ -272,9 +567,7 @@ def run_ours(a):
     e2e_frames = min(a.e2e_frames, nframes)
     frame_bytes = natoms * 3 * 8
     chunk = max(1, min(e2e_frames, (64 << 20) // frame_bytes))
-    host_sample = traj.download(0, e2e_frames) if not wb else None
-    if host_sample is None:
-        host_sample = traj.download(0, e2e_frames)
+    host_sample = traj.download(0, e2e_frames)
     # the pinned staging buffer is allocated and first touched on the CPUs next to this GPU's PCIe link (NUMA-local)
     affinity = os.sched_getaffinity(0)
     numa_bound = lib.gcb_bind_host_thread(dev) == 0
@@ -283,6 +576,7 @@ def run_ours(a):
     pv[...] = host_sample
     os.sched_setaffinity(0, affinity)
     e2e_traj = _lib.DeviceTraj(natoms, e2e_frames, dev=dev)
+    e2e_traj.set_kernel_variant(variant)
     out_rmsd = np.empty(e2e_frames)
 
     def e2e_step():
@@ -313,6 +607,10 @@ def run_ours(a):
            "pinned_numa_local": bool(numa_bound),
            "path": "pinned float64 AoS host frames -> gcb_traj_upload_async (2 slots) -> gcb_super_rmsd_async -> gcb_fetch_results"}
     e2e_check = float(np.abs(out_rmsd - rmsd_gpu[:e2e_frames]).max()) if not wb else None
+    # the ceiling of that leg on this box: the same bytes per step as bare pinned copies on all ranks at once, no kernels
+    e2e["host_limit_gbs"] = bare_copy_bandwidth(d, dev, e2e_frames * frame_bytes, e2e_steps)
+    e2e["host_limit_note"] = ("bare pinned cudaMemcpyAsync host->device (torch copy, no kernels), all ranks at the same time, same bytes per step: "
+                              "what the box's PCIe / host memory path gives each GPU; e2e h2d_gbs_per_gpu is to be read against it")
     # the same loop fed as a DCD reader feeds it: float32 x[] y[] z[] records in pinned memory (dcd.go:380-413), widened on the device
     if numa_bound:
         lib.gcb_bind_host_thread(dev)
@@ -342,7 +640,11 @@ def run_ours(a):
     d.barrier()
     e2e["f32_soa_feed"] = {"value": e2e_frames * d.world * e2e_steps / e2e32_dt, "unit": UNIT,
                            "h2d_bytes_per_step": e2e_frames * frame_bytes // 2,
+                           "h2d_gbs_per_gpu": e2e_frames * (frame_bytes // 2) * e2e_steps / e2e32_dt / 1e9,
                            "note": "same calls, host frames as float32 DCD records (what traj/dcd decodes), widened on the device"}
+    pinned32.free()
+    pinned.free()
+    e2e_traj.close()
 
     # CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample of the same frames
     cpu = None
@@ -366,9 +668,7 @@ def run_ours(a):
         # the reference AS WRITTEN also forms an N x N identity / ones product per frame (geometric.go:145-149): 1.6 GB per frame at
         # 10 000 atoms, so that cost model is only runnable at the size of BASELINE configs[0] (1500 atoms); reported beside the port
         try:
-            from gochem_b200 import synth as _synth
-
-            ref_s, frames_s = _synth.make_case(1500, max(cores, 16), frame0_is_ref=True)
+            ref_s, frames_s = synth.make_case(1500, max(cores, 16), frame0_is_ref=True)
             oracle.super_rmsd_traj(frames_s[:cores], ref_s, None, as_written=True, nthreads=cores, details=False)
             t1 = time.perf_counter()
             oracle.super_rmsd_traj(frames_s, ref_s, None, as_written=True, nthreads=cores, details=False)
@@ -385,6 +685,28 @@ def run_ours(a):
             got = traj.fetch(0, n_cpu, want=("rmsd", "rot"))
             parity = {"frames_checked": n_cpu, "max_abs_rmsd_diff": float(np.abs(got["rmsd"] - rm_cpu).max()),
                       "max_abs_rot_diff": float(np.abs(got["rot"] - rot_cpu).max())}
+    del host_sample
+
+    # ---- the other BASELINE configs and Super mode, measured after the timed region (each with its own device timing) ----
+    extra = {}
+    launches_before_extra = lib.gcb_launch_count()
+    if not a.no_extra:
+        for name, fn in (("super_mode", lambda: sub_super_mode(a, d, traj, ref, peak)),):
+            try:
+                extra[name] = fn() if not wb else None
+            except Exception as exc:   # a sub-record never takes the headline line down
+                extra[name] = {"error": repr(exc)[:300]}
+    traj.close()
+    if not a.no_extra:
+        for name, fn in (("lovo", lambda: sub_lovo(a, d, comm, dev, peak)),
+                         ("allpairs", lambda: sub_allpairs(a, d, comm, dev)),
+                         ("stream", lambda: sub_stream(a, d, dev))):
+            try:
+                extra[name] = fn()
+            except Exception as exc:
+                extra[name] = {"error": repr(exc)[:300]}
+            d.barrier()
+    extra_launches = lib.gcb_launch_count() - launches_before_extra
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": d.world, "steps": a.steps, "warmup": a.warmup,
@@ -392,18 +714,20 @@ def run_ours(a):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"fused chem.Super + per-frame chem.RMSD, {nframes} frames x {natoms} atoms per GPU resident in HBM (BASELINE configs[1])",
                    "mode": "super (write-back, 48 B/atom)" if wb else "fit (RMSD + R + translations, 24 B/atom)",
-                   "frames_per_gpu": nframes, "natoms": natoms, "sharding": f"frames x{d.world}, no collective",
+                   "frames_per_gpu": nframes, "natoms": natoms, "sharding": f"frames x{d.world}, no collective in the timed region",
                    "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9 if not wb else alg_bytes / 2e9),
                    "kernel_variant": a.variant, "cluster_plan": plan},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "check": {"rmsd_frame0": float(rmsd_gpu[0]), "rmsd_mean": float(rmsd_gpu.mean()), "e2e_vs_resident_max_abs": e2e_check,
                   "parity_vs_oracle": parity},
+        "comm": {"created_by": "gcb_comm_init (csrc/comm.cu, ncclCommInitRank)", "nranks": comm.nranks,
+                 "used_by": ["lovo", "allpairs"] if not a.no_extra else []},
+        "extra_gpu_launches": int(extra_launches),
+        **extra,
     }
     if d.rank == 0:
         print(json.dumps(line), flush=True)
-    pinned.free()
-    e2e_traj.close()
-    traj.close()
+    comm.close()
     d.close()
 
 

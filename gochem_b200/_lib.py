@@ -52,7 +52,11 @@ def load() -> C.CDLL:
         "gcb_device_info": (I, [I, C.POINTER(I), C.POINTER(C.c_size_t), C.POINTER(I), C.POINTER(I)]),
         "gcb_set_kernel_variant": (I, [I]),
         "gcb_set_cluster_tuning": (I, [I, I, I, I]),
-        "gcb_last_cluster_plan": (I, [C.POINTER(I)]),
+        "gcb_traj_last_cluster_plan": (I, [P, C.POINTER(I)]),
+        "gcb_traj_set_kernel_variant": (I, [P, I]),
+        "gcb_traj_set_cluster_tuning": (I, [P, I, I, I, I]),
+        "gcb_traj_set_rmsd_mode": (I, [P, I]),
+        "gcb_traj_set_split_thresholds": (I, [P, I, I]),
         "gcb_set_rmsd_mode": (I, [I]),
         "gcb_set_split_thresholds": (I, [I, I]),
         "gcb_pinned_alloc": (I, [C.c_size_t, C.POINTER(P)]),
@@ -124,13 +128,6 @@ def _idx(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-def last_cluster_plan() -> dict:
-    out = (C.c_int * 8)()
-    check(load().gcb_last_cluster_plan(out))
-    keys = ["cluster", "part", "atoms_per_thread", "stages", "depth", "resident", "clusters", "smem"]
-    return dict(zip(keys, list(out)))
-
-
 def device_count() -> int:
     n = C.c_int(0)
     rc = load().gcb_device_count(C.byref(n))
@@ -193,6 +190,25 @@ class DeviceTraj:
         self.h = C.c_void_p()
         check(self.lib.gcb_traj_create(dev, natoms, cap_frames, C.byref(self.h)))
         self.natoms, self.cap, self.dev = natoms, cap_frames, dev
+
+    # --- settings of this handle (the gcb_set_* forms only change the defaults of handles created later) ---
+    def set_kernel_variant(self, variant: int):
+        check(self.lib.gcb_traj_set_kernel_variant(self.h, variant))
+
+    def set_cluster_tuning(self, cluster=0, stages=0, depth=0, resident=-1):
+        check(self.lib.gcb_traj_set_cluster_tuning(self.h, cluster, stages, depth, resident))
+
+    def set_rmsd_mode(self, explicit_only: int):
+        check(self.lib.gcb_traj_set_rmsd_mode(self.h, int(explicit_only)))
+
+    def set_split_thresholds(self, write_back_max_atoms=-1, per_atom_max_atoms=-1):
+        check(self.lib.gcb_traj_set_split_thresholds(self.h, write_back_max_atoms, per_atom_max_atoms))
+
+    def last_cluster_plan(self) -> dict:
+        out = (C.c_int * 8)()
+        check(self.lib.gcb_traj_last_cluster_plan(self.h, out))
+        keys = ["cluster", "part", "atoms_per_thread", "stages", "depth", "resident", "clusters", "smem"]
+        return dict(zip(keys, list(out)))
 
     # --- data movement ---
     def upload(self, frames: np.ndarray, first: int = 0, layout: int = F64_AOS, scale: float = 1.0):

@@ -640,7 +640,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     AP_TRY(cudaEventCreate(&e0));
     AP_TRY(cudaEventCreate(&e1));
     if (fit) {
-        AP_TRY(cudaFuncSetAttribute(allpairs_fit_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AP_TRY(opt_in_smem(allpairs_fit_dmma_kernel, t->dev));
         AP_TRY(cudaEventRecord(e0, s));
         allpairs_fit_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, kdim, nframes, norms, 1.0 / (double)natoms_used,
                                                                                   d_tiles, po, nframes, 1e-7, redo);
@@ -649,7 +649,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
         redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
         GCB_LAUNCHED();
     } else {
-        AP_TRY(cudaFuncSetAttribute(allpairs_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AP_TRY(opt_in_smem(allpairs_dmma_kernel, t->dev));
         AP_TRY(cudaEventRecord(e0, s));
         allpairs_dmma_kernel<<<(unsigned)tiles.size(), AP_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used,
                                                                               d_tiles, po, nframes, 1e-7, redo);

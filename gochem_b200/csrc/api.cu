@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -19,14 +20,20 @@ namespace gcb {
 
 static thread_local std::string t_error;
 std::atomic<long> g_launches{0};
-int g_variant = GCB_KERNEL_AUTO;
 // Small structures, passes that visit every atom twice: up to these atom counts the fit-only launch plus one elementwise sweep
 // (transform.cu) beats the fused kernels, whose second sweep misses L2 there (gcb_set_split_thresholds; measured defaults)
 // 100 000 frames, tools/split_small_probe.py, profiles/r1_s5_split_small_probe.jsonl: write-back 300 atoms 510 -> 392 us, 512 atoms
 // 720 -> 627 us, a tie at 600, the cluster kernel ahead above (and the fused warp-per-frame kernel below 64 atoms); per-atom sums
 // 300 atoms 644 -> 416 us, 800 atoms 827 -> 773 us, the cluster kernel ahead from 1000 atoms
 constexpr int kSplitWbMinAtoms = 64, kSplitWbMaxDefault = 560, kSplitDevMaxDefault = 900;
-int g_split_wb_max = kSplitWbMaxDefault, g_split_dev_max = kSplitDevMaxDefault;
+
+// defaults a new handle copies (gcb_set_*); a handle's own settings are changed with gcb_traj_set_*
+static std::mutex g_defaults_mu;
+static Tuning g_defaults;
+Tuning default_tuning() {
+    std::lock_guard<std::mutex> lock(g_defaults_mu);
+    return g_defaults;
+}
 
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -103,35 +110,86 @@ int gcb_device_info(int dev, int* sm_count, size_t* total_mem, int* cc_major, in
     return GCB_OK;
 }
 
-int gcb_set_kernel_variant(int variant) {
+static int check_variant(int variant) {
     if (variant < GCB_KERNEL_AUTO || variant > GCB_KERNEL_CLUSTER) { set_error("bad kernel variant %d", variant); return GCB_ERR_ARG; }
-    g_variant = variant;
     return GCB_OK;
 }
 
-int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident) {
+static int check_cluster_tuning(int cluster, int stages, int depth, int resident) {
     if (cluster < 0 || cluster > 8 || stages < 0 || stages > 8 || depth < 0 || depth > 6 || resident < -1 || resident > 1) {
         set_error("bad cluster tuning (%d, %d, %d, %d)", cluster, stages, depth, resident);
         return GCB_ERR_ARG;
     }
-    set_cluster_tuning(cluster, stages, depth == 0 ? -1 : depth, resident);
+    return GCB_OK;
+}
+
+static void apply_cluster_tuning(Tuning* tu, int cluster, int stages, int depth, int resident) {
+    tu->cluster = cluster; tu->stages = stages; tu->depth = depth == 0 ? -1 : depth; tu->resident = resident;
+}
+
+/* process-wide DEFAULTS: copied by handles created afterwards, never read by a running call */
+int gcb_set_kernel_variant(int variant) {
+    int rc = check_variant(variant);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_defaults_mu);
+    g_defaults.variant = variant;
+    return GCB_OK;
+}
+
+int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident) {
+    int rc = check_cluster_tuning(cluster, stages, depth, resident);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_defaults_mu);
+    apply_cluster_tuning(&g_defaults, cluster, stages, depth, resident);
     return GCB_OK;
 }
 
 int gcb_set_split_thresholds(int write_back_max_atoms, int per_atom_max_atoms) {
-    g_split_wb_max = write_back_max_atoms < 0 ? kSplitWbMaxDefault : write_back_max_atoms;
-    g_split_dev_max = per_atom_max_atoms < 0 ? kSplitDevMaxDefault : per_atom_max_atoms;
+    std::lock_guard<std::mutex> lock(g_defaults_mu);
+    g_defaults.split_wb_max = write_back_max_atoms < 0 ? -1 : write_back_max_atoms;
+    g_defaults.split_dev_max = per_atom_max_atoms < 0 ? -1 : per_atom_max_atoms;
     return GCB_OK;
 }
 
 int gcb_set_rmsd_mode(int explicit_only) {
-    set_force_explicit(explicit_only ? 1 : 0);
+    std::lock_guard<std::mutex> lock(g_defaults_mu);
+    g_defaults.force_explicit = explicit_only ? 1 : 0;
     return GCB_OK;
 }
 
-int gcb_last_cluster_plan(int* out8) {
-    if (!out8) return GCB_ERR_ARG;
-    get_last_plan(out8);
+/* the same settings of ONE handle; the caller orders them against its own calls on that handle */
+int gcb_traj_set_kernel_variant(gcb_traj* t, int variant) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    int rc = check_variant(variant);
+    if (rc) return rc;
+    t->tune.variant = variant;
+    return GCB_OK;
+}
+
+int gcb_traj_set_cluster_tuning(gcb_traj* t, int cluster, int stages, int depth, int resident) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    int rc = check_cluster_tuning(cluster, stages, depth, resident);
+    if (rc) return rc;
+    apply_cluster_tuning(&t->tune, cluster, stages, depth, resident);
+    return GCB_OK;
+}
+
+int gcb_traj_set_split_thresholds(gcb_traj* t, int write_back_max_atoms, int per_atom_max_atoms) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    t->tune.split_wb_max = write_back_max_atoms < 0 ? -1 : write_back_max_atoms;
+    t->tune.split_dev_max = per_atom_max_atoms < 0 ? -1 : per_atom_max_atoms;
+    return GCB_OK;
+}
+
+int gcb_traj_set_rmsd_mode(gcb_traj* t, int explicit_only) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    t->tune.force_explicit = explicit_only ? 1 : 0;
+    return GCB_OK;
+}
+
+int gcb_traj_last_cluster_plan(const gcb_traj* t, int* out8) {
+    if (!t || !out8) return GCB_ERR_ARG;
+    for (int i = 0; i < 8; i++) out8[i] = t->last_plan[i];
     return GCB_OK;
 }
 
@@ -201,6 +259,7 @@ int gcb_traj_destroy(gcb_traj* tb) {
     cudaFree(t->d_devpart); cudaFree(t->d_devsum); cudaFree(t->d_refplanes); cudaFree(t->d_want); cudaFree(t->d_wantref);
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     cudaFree(t->d_ap_ws);
+    cudaFree(t->d_epart); cudaFree(t->d_pdist);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
     for (int s = 0; s < 2; s++) {
         if (t->h_bounce[s]) cudaFreeHost(t->h_bounce[s]);
@@ -228,6 +287,7 @@ int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj** out) {
     t->cap = cap_frames;
     t->nframes = 0;
     t->sm_count = pr.multiProcessorCount;
+    t->tune = default_tuning();
     int rc = GCB_OK;
 #define TRY(call)                                                                                     \
     do {                                                                                              \
@@ -672,7 +732,7 @@ int check_status(gcb_traj_ext* t) {
 }
 
 bool use_cluster(const gcb_traj_ext* t, bool heavy) {
-    if (g_variant == GCB_KERNEL_GENERIC) return false;
+    if (t->tune.variant == GCB_KERNEL_GENERIC) return false;
     return cluster_kernel_supported(t, heavy);
 }
 
@@ -683,9 +743,13 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
     // Frames beyond the cluster kernel's capacity whose every atom must be visited a second time (write-back, per-atom sums):
     // the fit and the elementwise sweep are separate launches (transform.cu) instead of the generic kernel's re-read.
-    const bool small_split = (write_back && !want_dev && t->natoms >= kSplitWbMinAtoms && t->natoms <= g_split_wb_max) ||
-                             (want_dev && !write_back && t->natoms <= g_split_dev_max);
-    if (g_variant == GCB_KERNEL_AUTO && (write_back || want_dev) && nframes > 0 && !force_explicit_mode() &&
+    const int variant = t->tune.variant;
+    const int split_wb_max = t->tune.split_wb_max < 0 ? kSplitWbMaxDefault : t->tune.split_wb_max;
+    const int split_dev_max = t->tune.split_dev_max < 0 ? kSplitDevMaxDefault : t->tune.split_dev_max;
+    auto force_explicit_mode = [t] { return t->tune.force_explicit; };
+    const bool small_split = (write_back && !want_dev && t->natoms >= kSplitWbMinAtoms && t->natoms <= split_wb_max) ||
+                             (want_dev && !write_back && t->natoms <= split_dev_max);
+    if (variant == GCB_KERNEL_AUTO && (write_back || want_dev) && nframes > 0 && !force_explicit_mode() &&
         (small_split || !cluster_kernel_supported(t, true)))
         return launch_super_split(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back, want_dev, dev_rows);
     int mode = MODE_ALL;
@@ -693,7 +757,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     // plus a per-frame cost, streaming the frame 24 bytes per atom of the WHOLE frame.  Measured (tools/misc_bench.py): the
     // warp-per-frame gather (<= 512 atoms, ~20 ns per frame at 300 atoms) wins once the frame is 16 times the subset; the
     // CTA-per-frame gather kernel (~0.2 us per frame) only against frames the cluster kernel cannot take (> 28 672 atoms).
-    const bool prefer_gather = g_variant == GCB_KERNEL_AUTO && !write_back && !want_dev && idx_test && nidx > 0 &&
+    const bool prefer_gather = variant == GCB_KERNEL_AUTO && !write_back && !want_dev && idx_test && nidx > 0 &&
                                (nidx <= 512 ? 16L * nidx <= t->natoms
                                 : nidx <= small_gather_max_atoms() ? 8L * nidx <= t->natoms
                                                                    : (t->natoms > 28672 && 12L * nidx <= t->natoms));
@@ -704,7 +768,7 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     fill_params(t, first, nframes, write_back, &p);
     if (mode == MODE_GATHER) {
         if (want_dev) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
-        if (g_variant == GCB_KERNEL_AUTO && !write_back && nidx <= small_gather_max_atoms())
+        if (variant == GCB_KERNEL_AUTO && !write_back && nidx <= small_gather_max_atoms())
             return launch_super_small_gather(t, p, t->d_refpairs, t->d_idx, nidx, force_explicit_mode());
         return launch_super_gather(t, p, t->d_refpairs, t->d_idx, nidx);
     }
@@ -712,12 +776,12 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
     if (want_dev && mode == MODE_WEIGHTED && t->cache.paired) { set_error("per-atom deviation sums need identical test/templa index lists"); return GCB_ERR_INDEXES; }
     // the cluster kernel takes the fit subset as a 0/1 mask; index lists with repeats (multiplicities) go to the generic kernel
     const bool cluster = use_cluster(t, write_back != 0 || want_dev) && !(mode == MODE_WEIGHTED && t->cache.repeated);
-    if (g_variant == GCB_KERNEL_CLUSTER && !cluster && !(mode == MODE_WEIGHTED && t->cache.repeated)) {
+    if (variant == GCB_KERNEL_CLUSTER && !cluster && !(mode == MODE_WEIGHTED && t->cache.repeated)) {
         set_error("cluster kernel requested but not available for %d atoms", t->natoms);
         return GCB_ERR_ARG;
     }
     // structures of at most 512 atoms: every warp owns frames (super_small.cu); the explicit variants keep their meaning
-    const bool small = g_variant == GCB_KERNEL_AUTO && small_kernel_supported(t, want_dev || write_back != 0 || force_explicit_mode() != 0) && !(mode == MODE_WEIGHTED && t->cache.repeated);
+    const bool small = variant == GCB_KERNEL_AUTO && small_kernel_supported(t, want_dev || write_back != 0 || force_explicit_mode() != 0) && !(mode == MODE_WEIGHTED && t->cache.repeated);
     if (want_dev) {
         const size_t rows = small ? (size_t)small_kernel_rows(t) : (size_t)t->sm_count * 8;
         rc = ensure_devpart(t, rows);
@@ -818,7 +882,7 @@ int gcb_rmsd(gcb_traj* tb, long first, long nframes, const double* ref_aos, int 
     GCB_CUDA(cudaSetDevice(t->dev));
     int mode = MODE_ALL;
     // a small subset of a large frame: read only its atoms (one CTA per frame, ~0.1 us per frame) instead of streaming the frame
-    const bool prefer_gather = g_variant == GCB_KERNEL_AUTO && idx_test && nidx > 0 && 32L * nidx <= t->natoms && t->natoms >= 16384;
+    const bool prefer_gather = t->tune.variant == GCB_KERNEL_AUTO && idx_test && nidx > 0 && 32L * nidx <= t->natoms && t->natoms >= 16384;
     rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, false, &mode, prefer_gather);
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;
@@ -861,14 +925,18 @@ int gcb_peratom_dist(gcb_traj* tb, long frame, const double* ref_aos, int natoms
         GCB_CUDA(cudaMalloc(&t->d_idx, sizeof(int) * (size_t)n));
         t->idx_cap = n;
     }
-    double* d_out = nullptr;
-    GCB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+    if ((size_t)n > t->pdist_cap) {   // output scratch kept in the handle: no allocation per call
+        cudaFree(t->d_pdist);
+        t->d_pdist = nullptr; t->pdist_cap = 0;
+        GCB_CUDA(cudaMalloc(&t->d_pdist, sizeof(double) * (size_t)n));
+        t->pdist_cap = (size_t)n;
+    }
+    double* d_out = t->d_pdist;
     cudaMemcpyAsync(t->d_refpairs, pairs.data(), sizeof(double) * pairs.size(), cudaMemcpyHostToDevice, t->stream);
     cudaMemcpyAsync(t->d_idx, it.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, t->stream);
     rc = launch_peratom_dist(t, t->d_frames + frame * 3L * t->np, t->d_refpairs, t->d_idx, n, d_out);
     if (rc == GCB_OK) cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, t->stream);
     cudaError_t e = cudaStreamSynchronize(t->stream);
-    cudaFree(d_out);
     if (rc) return rc;
     if (e != cudaSuccess) { set_error("per-atom distance kernel failed: %s", cudaGetErrorString(e)); return GCB_ERR_CUDA; }
     return GCB_OK;

@@ -12,6 +12,7 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -35,9 +36,8 @@ struct NcclApi {
 
 static NcclApi* nccl() {
     static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (api.h) {
@@ -50,7 +50,7 @@ static NcclApi* nccl() {
             api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.h, "ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
         }
-    }
+    });
     if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Broadcast || !api.GroupStart ||
         !api.GroupEnd) {
         set_error("NCCL (libnccl.so.2) is not loadable: %s", api.h ? "missing symbols" : dlerror());

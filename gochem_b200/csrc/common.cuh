@@ -13,7 +13,17 @@ namespace gcb {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long> g_launches;
-extern int g_variant;
+
+// Everything that steers kernel choice and shape lives in the handle (gcb_traj::tune), never in process globals: two handles
+// driven from two threads (goroutines call chem.Super concurrently on distinct matrices, align/lovo.go:290-295, 329) must not see
+// each other's settings.  The gcb_set_* entry points only change the defaults a handle copies when it is created.
+struct Tuning {
+    int variant = GCB_KERNEL_AUTO;
+    int split_wb_max = -1, split_dev_max = -1;          // -1 = built-in thresholds (api.cu)
+    int cluster = 0, stages = 0, depth = -1, resident = -1;   // cluster-kernel overrides (0 / -1 = built-in choice)
+    int force_explicit = 0;                              // 1 = the RMSD always comes from the explicit residual
+};
+Tuning default_tuning();
 
 #define GCB_CUDA(call)                                                                       \
     do {                                                                                     \
@@ -27,6 +37,19 @@ extern int g_variant;
 #define GCB_LAUNCHED() (gcb::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Dynamic shared memory above 48 KB is an opt-in per (kernel, device).  It is raised to the device limit once and never lowered,
+// so concurrent callers with different launch shapes cannot shrink it under one another.
+constexpr int kMaxOptinSmem = 227 * 1024;
+template <typename Kern>
+static inline cudaError_t opt_in_smem(Kern kern, int dev) {
+    static std::atomic<unsigned long long> done{0};   // one bit per device, per kernel instantiation
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 // Atoms per plane are padded to a multiple of 16 doubles (128 B) so every plane of every frame
 // starts on a 128-byte boundary: 16-byte TMA bulk copies and double2 loads are always legal.
@@ -107,6 +130,13 @@ struct gcb_traj {
     void* h_bounce[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    // per-handle settings and scratch (nothing of a call's state is process-global)
+    gcb::Tuning tune;
+    int last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // shape of this handle's last cluster-kernel launch
+    double* d_epart = nullptr;                     // cluster kernel: per-warp squared-error partials of pass 2
+    size_t epart_bytes = 0;
+    double* d_pdist = nullptr;                     // gcb_peratom_dist output scratch
+    size_t pdist_cap = 0;
 };
 
 // NCCL communicator wrapper (comm.cu) plus the peer-mapped row blocks of the multi-GPU all-pairs matrix
@@ -142,11 +172,7 @@ int launch_peratom_dist(gcb_traj* t, const double* frame, const double* refpairs
 int launch_synth(gcb_traj* t, long first, long nframes, const double* d_ref_aos, const double* d_sigma,
                  unsigned long long seed, long frame_id0, int frame0_is_ref, int through_f32);
 bool cluster_kernel_supported(const gcb_traj* t, bool heavy = false);
-void set_cluster_tuning(int cluster, int stages, int depth, int resident);
-void get_last_plan(int* out8);
-void set_force_explicit(int on);
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out);
-int force_explicit_mode();
 bool small_kernel_supported(const gcb_traj* t, bool heavy);
 int small_kernel_rows(const gcb_traj* t);
 int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int force_explicit, int* rows_out);

@@ -193,7 +193,7 @@ extern "C" int gcb_moments_async(gcb_traj* t, long first, long nframes, const do
     if (stages > kMomMaxStages) stages = kMomMaxStages;
     if (stages < 2) { set_error("moments: no stage plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     const size_t smem = fixed + sizeof(double) * 4 * (size_t)chunk * stages;
-    GCB_CUDA(cudaFuncSetAttribute(moments_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCB_CUDA(opt_in_smem(moments_stream_kernel, t->dev));
     long grid = t->sm_count;
     if (grid > nframes) grid = nframes;
     moments_stream_kernel<<<(unsigned)grid, kMomThreads, smem, t->stream>>>(t->d_frames + first * 3L * t->np, 3L * t->np, t->np, nframes,

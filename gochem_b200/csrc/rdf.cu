@@ -340,7 +340,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         p.cdf = d_cdf;
         const size_t smem = sizeof(double) * 3 * (size_t)p.tile + (sizeof(unsigned long long) + sizeof(int2)) * kListCap +
                             sizeof(unsigned int) * (size_t)(totalsteps + 1);
-        RDF_TRY(cudaFuncSetAttribute(rdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RDF_TRY(opt_in_smem(rdf_kernel, t->dev));
         int per_sm = 1;
         RDF_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rdf_kernel, RT, smem));
         long grid = (long)t->sm_count * (per_sm > 0 ? per_sm : 1);

@@ -48,8 +48,13 @@ constexpr int kConsumers = 32 * kConsumerWarps;   // consumer threads per CTA
 constexpr int kSolverWarps = 3;
 constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
 constexpr int kMaxStages = 8;
-constexpr int kMaxSlots = 13;            // exchange slots (>= 2*D+1 with D <= 6, and > kSolverWarps)
-constexpr int kResidentSlots = 7;        // plans that keep the part resident run at most D = 3 frames ahead
+// Exchange slots.  Slot j mod NS is rewritten by the peers' pushes of frame j + NS.  A peer can start pass 1 of frame j + NS once
+// it has finished pass 2 of frame j + NS - D - 1, which needs every CTA's partial sums of that frame, i.e. this CTA's consumers
+// are past pass 2 of frame j + NS - 2D - 2.  With NS >= 2D + 2 that frame is >= j, whose pass 2 waited for this CTA's solver to
+// publish frame j -- after it had read the slot.  (NS = 2D + 1 left a window in which a delayed solver warp could read sums of
+// frame j + NS.)
+constexpr int kMaxSlots = 14;            // >= 2*D+2 with D <= 6, and > kSolverWarps
+constexpr int kResidentSlots = 8;        // plans that keep the part resident run at most D = 3 frames ahead
 constexpr int kRedRow = 33;              // transposition scratch of the per-frame reduction: [13 sums][32 lanes], rows padded by one
 constexpr int kRedWarpDoubles = 13 * kRedRow;
 constexpr size_t kRedScratchBytes = ((sizeof(double) * kRedWarpDoubles * kConsumerWarps + 127) / 128) * 128;
@@ -62,7 +67,7 @@ struct ClusterParams {
     int part;           // P: atoms per CTA (multiple of 16)
     int stages;         // S
     int depth;          // D
-    int slots;          // NS = 2*D+1
+    int slots;          // NS >= 2*D+2
     int nclusters;      // G
     int write_back;
     int always_explicit;  // pass 2 runs for every frame (write-back / per-atom sums / caller's choice)
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         // ===================== solvers: warp w takes local frames w, w + kSolverWarps, ... =====================
         // Per frame: rank-ordered sum of the cluster's partial sums, 3x3 solve, publish R and centroid R.
         const int sw = warp - (kConsumerWarps + 1);
-        int slot = sw;                                  // NS = 7 > kSolverWarps
+        int slot = sw;                                  // NS > kSolverWarps
         uint32_t sph = 0;
         for (int j = sw; j < nloc; j += kSolverWarps) {
             {
@@ -482,43 +487,41 @@ struct Plan {
 
 constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14};
 
-// tuning overrides (0 / -1 = built-in choice)
-int g_tune_cluster = 0, g_tune_depth = -1, g_tune_stages = 0, g_tune_resident = -1;
-int g_force_explicit = 0;
-
 // Choose CTAs per frame, atoms per thread, stage count, pipeline depth.
 //  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
 //  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
-bool make_plan(int np, bool heavy, Plan* pl) {
+bool make_plan(const Tuning& tu, int np, bool heavy, Plan* pl) {
+    const int tune_cluster = tu.cluster, tune_depth = tu.depth, tune_stages = tu.stages, tune_resident = tu.resident;
     // Measured on B200 (profiles/r1_tuning.md).  Fit-only passes skip pass 2 for almost every frame, so the stage can be
     // released right after pass 1 (pass 2, when needed, re-reads the part from L2): two stages of the fattest part that
     // fits win (up to 14 atoms per thread, fewest CTAs per frame, clusters of <= 3 tile the GPCs almost exactly).
     // Passes that always run pass 2 (write-back, per-atom sums) keep the part resident in shared memory: <= 10 atoms per
     // thread, >= 3 stages.
-    const int resident = g_tune_resident >= 0 ? g_tune_resident : (heavy ? 1 : 0);
+    const int resident = tune_resident >= 0 ? tune_resident : (heavy ? 1 : 0);
     const int kmax = resident ? (heavy ? 10 : 10) : 14;
     const size_t fixed = fixed_smem(resident != 0);
     for (int c = 1; c <= kMaxCluster; c++) {
-        if (g_tune_cluster && c != g_tune_cluster) continue;
+        if (tune_cluster && c != tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
         const int kneed = (part + kConsumers - 1) / kConsumers;
         int kinst = 0;
         for (int k : kInst) if (k >= kneed) { kinst = k; break; }
         if (!kinst) continue;
-        if (!g_tune_cluster && kinst > kmax && c < kMaxCluster) continue;
+        if (!tune_cluster && kinst > kmax && c < kMaxCluster) continue;
         const size_t stage = (size_t)3 * kinst * kConsumers * sizeof(double);
         int stages = (int)((kSmemBudget - fixed) / stage);
         if (stages > kMaxStages) stages = kMaxStages;
         if (!resident && stages > (kinst <= 6 ? 4 : 2)) stages = (kinst <= 6 ? 4 : 2);
-        if (g_tune_stages && g_tune_stages < stages) stages = g_tune_stages;
+        if (tune_stages && tune_stages < stages) stages = tune_stages;
         if (stages < (resident ? 3 : 2)) continue;
         int depth;
         if (resident) {
             depth = stages - 2 > 2 ? 2 : stages - 2;
-            if (g_tune_depth >= 1 && g_tune_depth <= stages - 2 && 2 * g_tune_depth + 1 <= kResidentSlots) depth = g_tune_depth;
+            if (tune_depth >= 1 && tune_depth <= stages - 2 && 2 * tune_depth + 2 <= kResidentSlots) depth = tune_depth;
         } else {
             depth = kinst <= 6 ? 6 : 3;   // costs no shared memory here: only the exchange slots
-            if (g_tune_depth >= 1 && g_tune_depth <= 6) depth = g_tune_depth;
+            if (tune_depth >= 1 && tune_depth <= 6) depth = tune_depth;
+            static_assert(2 * 6 + 2 <= kMaxSlots, "exchange slots must cover 2 D + 2 frames");
         }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
         pl->resident = resident;
@@ -528,18 +531,22 @@ bool make_plan(int np, bool heavy, Plan* pl) {
     return false;
 }
 
-int g_last_plan[8] = {0};
-
 template <int K, bool W, bool DV, bool RES>
 int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
     auto kern = super_cluster_kernel<K, W, DV, RES>;
-    // the attribute call and the occupancy query cost tens of microseconds each: once per (instance, device, shape)
+    // the occupancy query costs tens of microseconds: once per (instance, device, shape).  The cache is shared by every handle
+    // of the process and guarded; a miss only repeats the query.
     static std::mutex cache_mu;
     static int cached_dev = -1, cached_cluster = 0, cached_max = 0;
     static size_t cached_smem = 0;
-    std::lock_guard<std::mutex> lock(cache_mu);
-    const bool hit = cached_dev == t->dev && cached_cluster == pl.cluster && cached_smem == pl.smem;
-    if (!hit) GCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    GCB_CUDA(opt_in_smem(kern, t->dev));
+    bool hit;
+    int max_clusters;
+    {
+        std::lock_guard<std::mutex> lock(cache_mu);
+        hit = cached_dev == t->dev && cached_cluster == pl.cluster && cached_smem == pl.smem;
+        max_clusters = cached_max;
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -552,9 +559,9 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = t->stream;
     cfg.gridDim = dim3(pl.cluster * (t->sm_count / pl.cluster));
-    int max_clusters = cached_max;
     if (!hit) {
         GCB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        std::lock_guard<std::mutex> lock(cache_mu);
         cached_dev = t->dev; cached_cluster = pl.cluster; cached_smem = pl.smem; cached_max = max_clusters;
     }
     if (max_clusters < 1) { set_error("cluster of %d CTAs with %zu bytes of shared memory cannot be scheduled", pl.cluster, pl.smem); return GCB_ERR_CUDA; }
@@ -566,8 +573,8 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     GCB_CUDA(cudaLaunchKernelEx(&cfg, kern, c2));
     GCB_LAUNCHED();
     *nclusters_out = (int)g;
-    g_last_plan[0] = pl.cluster; g_last_plan[1] = pl.part; g_last_plan[2] = pl.kinst; g_last_plan[3] = pl.stages;
-    g_last_plan[4] = pl.depth; g_last_plan[5] = pl.resident; g_last_plan[6] = (int)g; g_last_plan[7] = (int)pl.smem;
+    t->last_plan[0] = pl.cluster; t->last_plan[1] = pl.part; t->last_plan[2] = pl.kinst; t->last_plan[3] = pl.stages;
+    t->last_plan[4] = pl.depth; t->last_plan[5] = pl.resident; t->last_plan[6] = (int)g; t->last_plan[7] = (int)pl.smem;
     return GCB_OK;
 }
 
@@ -596,9 +603,6 @@ int launch_r(gcb_traj* t, const ClusterParams& cp, const Plan& pl, bool weighted
     return want_dev ? launch_k<false, true, RES>(t, cp, pl, g) : launch_k<false, false, RES>(t, cp, pl, g);
 }
 
-double* g_epart[16] = {nullptr};
-size_t g_epart_cap[16] = {0};
-
 }  // namespace
 
 #ifdef GCB_TRACE
@@ -607,37 +611,26 @@ extern "C" int gcb_trace_read(long long* out) {
 }
 #endif
 
-void get_last_plan(int* out8) { for (int i = 0; i < 8; i++) out8[i] = g_last_plan[i]; }
-
-void set_force_explicit(int on) { g_force_explicit = on; }
-int force_explicit_mode() { return g_force_explicit; }
-
-void set_cluster_tuning(int cluster, int stages, int depth, int resident) {
-    g_tune_cluster = cluster;
-    g_tune_stages = stages;
-    g_tune_depth = depth;
-    g_tune_resident = resident;
-}
-
 // heavy: the pass visits every atom twice (write-back, per-atom sums, explicit residuals on request) and keeps the part resident
 // in shared memory, which holds fewer atoms per CTA (20 480 per frame against 28 672 for fit-only passes)
 bool cluster_kernel_supported(const gcb_traj* t, bool heavy) {
     Plan pl;
-    return make_plan(t->np, heavy || g_force_explicit, &pl);
+    return make_plan(t->tune, t->np, heavy || t->tune.force_explicit, &pl);
 }
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
     Plan pl;
-    if (!make_plan(t->np, want_dev || p.frames_rw != nullptr || g_force_explicit, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
-    const int dev = t->dev & 15;
+    const int force_explicit = t->tune.force_explicit;
+    if (!make_plan(t->tune, t->np, want_dev || p.frames_rw != nullptr || force_explicit, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    // pass 2's squared-error partials: scratch of THIS handle (its stream orders every use)
     const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * kConsumerWarps;
-    if (need > g_epart_cap[dev]) {
+    if (need > t->epart_bytes) {
         GCB_CUDA(cudaStreamSynchronize(t->stream));
-        cudaFree(g_epart[dev]);
-        g_epart[dev] = nullptr;
-        g_epart_cap[dev] = 0;
-        GCB_CUDA(cudaMalloc(&g_epart[dev], need));
-        g_epart_cap[dev] = need;
+        cudaFree(t->d_epart);
+        t->d_epart = nullptr;
+        t->epart_bytes = 0;
+        GCB_CUDA(cudaMalloc(&t->d_epart, need));
+        t->epart_bytes = need;
     }
     ClusterParams cp;
     cp.p = p;
@@ -648,8 +641,8 @@ int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     cp.slots = kMaxSlots;
     cp.nclusters = 0;
     cp.write_back = p.frames_rw != nullptr;
-    cp.always_explicit = (cp.write_back || want_dev || g_force_explicit) ? 1 : 0;
-    cp.epart = g_epart[dev];
+    cp.always_explicit = (cp.write_back || want_dev || force_explicit) ? 1 : 0;
+    cp.epart = t->d_epart;
     int g = 0;
     int rc = pl.resident ? launch_r<true>(t, cp, pl, weighted, want_dev, &g) : launch_r<false>(t, cp, pl, weighted, want_dev, &g);
     if (rc) return rc;

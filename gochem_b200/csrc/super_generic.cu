@@ -341,7 +341,7 @@ int launch_super_generic(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     const int grid = frames_grid(t, p.nframes, 3);
     if (grid_out) *grid_out = grid;
     const bool wb = p.frames_rw != nullptr;
-#define GCB_GEN(W, B, D) super_generic_kernel<W, B, D><<<grid, kThreads, 0, t->stream>>>(p, force_explicit_mode() ? 0 : 1)
+#define GCB_GEN(W, B, D) super_generic_kernel<W, B, D><<<grid, kThreads, 0, t->stream>>>(p, t->tune.force_explicit ? 0 : 1)
     if (weighted) {
         if (wb) { if (want_dev) GCB_GEN(true, true, true); else GCB_GEN(true, true, false); }
         else    { if (want_dev) GCB_GEN(true, false, true); else GCB_GEN(true, false, false); }

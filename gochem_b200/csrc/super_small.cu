@@ -416,7 +416,7 @@ template <int K>
 int launch_small_k(gcb_traj* t, const SuperParams& p, bool masked, bool want_dev, int always_explicit, int& grid, size_t smem) {
 #define GCB_SMALL_LAUNCH(M, D)                                                                                   \
     do {                                                                                                         \
-        GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<K, M, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GCB_CUDA(opt_in_smem(super_small_kernel<K, M, D>, t->dev)); \
         int per_sm = 1;                                                                                          \
         GCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, super_small_kernel<K, M, D>, kSmallThreads, smem)); \
         if (per_sm < 1) per_sm = 1;                                                                              \
@@ -449,7 +449,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
         const long need = (p.nframes + (long)kSmallWarps * kMinRun - 1) / ((long)kSmallWarps * kMinRun);
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GCB_CUDA(opt_in_smem(super_mid_kernel<false, true>, t->dev));
         super_mid_kernel<false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, nch, refpairs, idx, nidx);
         GCB_LAUNCHED();
         GCB_CUDA(cudaGetLastError());
@@ -464,7 +464,7 @@ int launch_super_small_gather(gcb_traj* t, const SuperParams& p, const double* r
     if (grid < 1) grid = 1;
 #define GCB_GATHER_LAUNCH(KK)                                                                                                  \
     do {                                                                                                                       \
-        GCB_CUDA(cudaFuncSetAttribute(super_small_kernel<KK, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GCB_CUDA(opt_in_smem(super_small_kernel<KK, false, false, true>, t->dev)); \
         super_small_kernel<KK, false, false, true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, force_explicit ? 1 : 0, refpairs, idx, nidx); \
     } while (0)
     switch (K) {
@@ -509,10 +509,10 @@ int launch_super_small(gcb_traj* t, const SuperParams& p, bool masked, bool want
         if (grid < 1) grid = 1;
         const int always = (force_explicit || p.frames_rw != nullptr) ? 1 : 0;
         if (masked) {
-            GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GCB_CUDA(opt_in_smem(super_mid_kernel<true>, t->dev));
             super_mid_kernel<true><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nch);
         } else {
-            GCB_CUDA(cudaFuncSetAttribute(super_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GCB_CUDA(opt_in_smem(super_mid_kernel<false>, t->dev));
             super_mid_kernel<false><<<(int)grid, kSmallThreads, smem, t->stream>>>(p, always, nch);
         }
         GCB_LAUNCHED();

@@ -98,12 +98,12 @@ int gch_mem_per_atom_rmsd(const double* test, int ntest, const double* templa, i
     return 0;
 }
 
-int gch_rotator_translator_to_super(const double* test, const double* templa, int n, double* transformed, double* rot, double* t1,
-                                    double* t2) {
+int gch_rotator_translator_to_super(const double* test, int ntest, const double* templa, int ntempla, double* transformed, double* rot,
+                                    double* t1, double* t2) {
     v3::Matrix tr, r, a, b;
-    Error e = chem::RotatorTranslatorToSuper(mat(test, n), mat(templa, n), transformed ? &tr : nullptr, &r, &a, &b);
+    Error e = chem::RotatorTranslatorToSuper(mat(test, ntest), mat(templa, ntempla), transformed ? &tr : nullptr, &r, &a, &b);
     if (e) return fail(e);
-    if (transformed) memcpy(transformed, tr.data(), sizeof(double) * 3 * (size_t)n);
+    if (transformed) memcpy(transformed, tr.data(), sizeof(double) * 3 * (size_t)ntest);
     if (rot) memcpy(rot, r.data(), sizeof(double) * 9);
     if (t1) memcpy(t1, a.data(), sizeof(double) * 3);
     if (t2) memcpy(t2, b.data(), sizeof(double) * 3);

@@ -102,13 +102,10 @@ def MemPerAtomRMSD(test, templa, *indexes):
 def RotatorTranslatorToSuper(test, templa):
     t = np.ascontiguousarray(test, dtype=np.float64)
     m = np.ascontiguousarray(templa, dtype=np.float64)
-    if t.shape != m.shape:
-        # let the library produce the reference's error
-        n = min(t.shape[0], m.shape[0])
-        raise GoChemError(-1, "goChem: Ill-formed matrices")
     n = t.shape[0]
     tr, r, a, b = np.zeros((n, 3)), np.zeros((3, 3)), np.zeros(3), np.zeros(3)
-    rc = load().gch_rotator_translator_to_super(_d(t), _d(m), n, _d(tr), _d(r), _d(a), _d(b))
+    # shape mismatches are the library's to report (geometric.go:130-132), not this wrapper's
+    rc = load().gch_rotator_translator_to_super(_d(t), n, _d(m), m.shape[0], _d(tr), _d(r), _d(a), _d(b))
     if rc:
         raise _err(rc)
     return tr, r, a, b

@@ -55,22 +55,31 @@ size_t gcb_last_error(char *buf, size_t cap);
 int gcb_device_count(int *n);
 /* Properties the host side sizes its work by: SM count, bytes of device memory, compute capability. */
 int gcb_device_info(int dev, int *sm_count, size_t *total_mem, int *cc_major, int *cc_minor);
+/* ---- settings ----
+ * Every setting that steers kernel choice or shape belongs to ONE trajectory handle (gcb_traj_set_*): calls on distinct handles
+ * are reentrant and may run concurrently from different threads, as the reference's functions are on distinct matrices
+ * (align/lovo.go:290-295, 329).  The gcb_set_* forms change the process-wide DEFAULTS that a handle copies when it is created;
+ * they never affect an existing handle. */
 int gcb_set_kernel_variant(int variant);
+int gcb_traj_set_kernel_variant(gcb_traj *t, int variant);
 /* Tuning hook for the cluster kernel: CTAs per frame (1..8), shared-memory stages, how many frames pass 2
  * trails pass 1 (1..6), and where pass 2 reads the frame from (1 = its shared-memory stage, 0 = L2,
  * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice. */
 int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident);
+int gcb_traj_set_cluster_tuning(gcb_traj *t, int cluster, int stages, int depth, int resident);
 /* Tuning hook: structures of at most this many atoms take the split form (a fit-only launch, then one elementwise sweep) for
  * write-back / per-atom-sum passes instead of the fused kernels.  A negative value restores the built-in threshold. */
 int gcb_set_split_thresholds(int write_back_max_atoms, int per_atom_max_atoms);
+int gcb_traj_set_split_thresholds(gcb_traj *t, int write_back_max_atoms, int per_atom_max_atoms);
 /* How the per-frame RMSD of a fit-only call (no write-back) is formed.  0 (default): from the inner products of
  * the single sweep, E = Ga + Gb - 2 tr(R^T H), whenever its rounding bound moves the RMSD by < 1e-10 A, and from
  * the explicit residual of a second sweep otherwise (frames within ~0.3 A of the template).  1: always the explicit
  * residual, exactly as the reference computes it (geometric.go:284-286). */
 int gcb_set_rmsd_mode(int explicit_only);
-/* Shape of the last cluster-kernel launch: {CTAs per frame, atoms per CTA, atoms per thread, stages, depth,
+int gcb_traj_set_rmsd_mode(gcb_traj *t, int explicit_only);
+/* Shape of the handle's last cluster-kernel launch: {CTAs per frame, atoms per CTA, atoms per thread, stages, depth,
  * resident, clusters launched, dynamic shared memory bytes}. */
-int gcb_last_cluster_plan(int *out8);
+int gcb_traj_last_cluster_plan(const gcb_traj *t, int *out8);
 
 /* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
 int gcb_pinned_alloc(size_t bytes, void **p);

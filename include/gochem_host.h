@@ -31,8 +31,9 @@ int gch_rmsd(const double *test, int ntest, const double *templa, int ntempla, c
 /* chem.MemPerAtomRMSD (geometric.go:294-321); out has n0 entries (ntest when no lists). */
 int gch_mem_per_atom_rmsd(const double *test, int ntest, const double *templa, int ntempla, const int *idx0, int n0,
                           const int *idx1, int n1, int nlists, double *out);
-/* chem.RotatorTranslatorToSuper (geometric.go:127-208). */
-int gch_rotator_translator_to_super(const double *test, const double *templa, int n, double *transformed,
+/* chem.RotatorTranslatorToSuper (geometric.go:127-208).  Different row counts give the reference's
+ * "goChem: Ill-formed matrices" (geometric.go:130-132); transformed holds ntest x 3. */
+int gch_rotator_translator_to_super(const double *test, int ntest, const double *templa, int ntempla, double *transformed,
                                     double *rot, double *trans1, double *trans2);
 
 /* chem.CenterOfMass (geometric.go:609-631) + chem.MomentTensor (geometric.go:705-733); mass NULL = unit masses. */

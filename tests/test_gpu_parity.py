@@ -203,8 +203,6 @@ def test_small_structure_kernel(natoms):
     """Structures of at most 512 atoms take the warp-per-frame kernel under KERNEL_AUTO, up to 2048 atoms its chunked form (the
     per-atom sums of those go to the cluster kernel): every mode against the oracle, with a frame count that is not a multiple of
     the 32-frame batches and a near-template frame that needs the explicit residual."""
-    lib = _lib.load()
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
     nframes = 75
     ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
     frames[40] = frames[0] + 1e-6                      # almost the template: the one-pass RMSD is not allowed here
@@ -225,11 +223,9 @@ def test_small_structure_kernel(natoms):
         assert total == nframes and np.abs(dev / nframes - want).max() < 1e-10
         assert np.abs(t.download() - aligned).max() < TOL_XYZ
         t.upload(frames)
-    _lib.check(lib.gcb_set_rmsd_mode(1))               # explicit residual for every frame
-    try:
-        ex = t.super_rmsd(ref, write_back=True)
-    finally:
-        lib.gcb_set_rmsd_mode(0)
+    t.set_rmsd_mode(1)                                 # explicit residual for every frame
+    ex = t.super_rmsd(ref, write_back=True)
+    t.set_rmsd_mode(0)
     assert np.abs(ex["rmsd"] - rm).max() < TOL_RMSD
     moved = t.download()
     for f in (0, 31, 32, 74):
@@ -370,8 +366,8 @@ def test_cluster_kernel_tunings(natoms, cluster, stages, depth, resident):
     idx = np.arange(0, natoms, 3)
     t = device_traj(frames)
     try:
-        _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
-        _lib.check(lib.gcb_set_cluster_tuning(cluster, stages, depth, resident))
+        t.set_kernel_variant(_lib.KERNEL_CLUSTER)
+        t.set_cluster_tuning(cluster, stages, depth, resident)
         out = t.super_rmsd(ref)
         rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, None, nthreads=8)
         assert np.abs(out["rmsd"] - rm).max() < TOL_RMSD
@@ -384,8 +380,6 @@ def test_cluster_kernel_tunings(natoms, cluster, stages, depth, resident):
         assert np.abs(dev / nframes - want).max() < 1e-10
         assert np.abs(t.download() - aligned).max() < TOL_XYZ
     finally:
-        lib.gcb_set_cluster_tuning(0, 0, 0, -1)
-        lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
         t.close()
 
 
@@ -456,12 +450,12 @@ def test_one_pass_rmsd_agrees_with_explicit_residual(natoms):
     want, *_ = oracle.super_rmsd_traj(frames, ref, None, nthreads=8)
     t = device_traj(frames)
     try:
-        _lib.check(lib.gcb_set_rmsd_mode(0))
+        t.set_rmsd_mode(0)
         one = t.super_rmsd(ref)["rmsd"]
-        _lib.check(lib.gcb_set_rmsd_mode(1))
+        t.set_rmsd_mode(1)
         two = t.super_rmsd(ref)["rmsd"]
     finally:
-        lib.gcb_set_rmsd_mode(0)
+        t.close()
     assert np.abs(two - want).max() < 1e-11          # explicit residual: rounding only
     assert np.abs(one - want).max() < 5e-10          # one-pass where its bound allows, explicit elsewhere
     assert one[0] < 1e-12                            # the template against itself goes through the explicit path
@@ -589,18 +583,14 @@ def test_small_subset_of_a_large_frame(nidx):
     ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
     idx = np.sort(np.random.default_rng(nidx).choice(natoms, nidx, replace=False))
     t = device_traj(frames)
-    lib = _lib.load()
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    t.set_kernel_variant(_lib.KERNEL_AUTO)
     got = t.super_rmsd(ref, idx, idx)
     if nidx >= 30:
         rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, idx)
         assert np.abs(got["rmsd"] - rm).max() < TOL_RMSD and np.abs(got["rot"] - rot).max() < TOL_ROT
         assert np.abs(got["trans1"] - t1).max() < TOL_XYZ and np.abs(got["trans2"] - t2).max() < TOL_XYZ
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER if natoms <= 28672 else _lib.KERNEL_GENERIC))
-    try:
-        ref_path = t.super_rmsd(ref, idx, idx)       # the streaming kernel with the subset as a mask
-    finally:
-        lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
+    t.set_kernel_variant(_lib.KERNEL_CLUSTER if natoms <= 28672 else _lib.KERNEL_GENERIC)
+    ref_path = t.super_rmsd(ref, idx, idx)           # the streaming kernel with the subset as a mask
     assert np.abs(got["rmsd"] - ref_path["rmsd"]).max() < TOL_RMSD
     if nidx >= 30:
         assert np.abs(got["rot"] - ref_path["rot"]).max() < TOL_ROT
@@ -713,9 +703,9 @@ def test_small_structures_split_form(natoms):
             s = sel if sel is not None else np.arange(natoms)
             want, total = oracle.rmsd_traj(frames, ref, s, cpus=7)
             assert total == nframes and np.abs(dev / nframes - want).max() < 1e-10
-            _lib.check(lib.gcb_set_split_thresholds(0, 0))
+            t.set_split_thresholds(0, 0)
             fused = t.peratom_dev_sum(ref, sel)
-            _lib.check(lib.gcb_set_split_thresholds(-1, -1))
+            t.set_split_thresholds(-1, -1)
             assert np.abs(dev - fused).max() < 1e-10 * nframes
             assert np.array_equal(t.download(), frames)
             out = t.super_rmsd(ref, sel, sel, write_back=True)
@@ -726,5 +716,4 @@ def test_small_structures_split_form(natoms):
             assert np.abs(t.download() - work).max() < TOL_XYZ
             t.upload(frames)
     finally:
-        lib.gcb_set_split_thresholds(-1, -1)
         t.close()

@@ -137,10 +137,9 @@ def test_dcd_round_trip(tmp_path):
 
 def test_xtc_reader_over_libxdrfile(tmp_path):
     """traj/xtc mirror: XTCObj.Next (x10, widened per element, xtc.go:129-134) and the raw float32 feed the device staging uses,
-    on a file written with the codec's own writer.  The codec is the third-party libxdrfile the reference links; skipped when
-    it cannot be loaded."""
-    if not H.xtc_available():
-        pytest.skip("libxdrfile is not installed on this host")
+    on a file written with the codec's own writer.  The codec is the third-party libxdrfile the reference links where it is
+    installed, tests/xdrshim elsewhere (conftest.py)."""
+    assert H.xtc_available()
     rng = np.random.default_rng(0)
     frames = rng.normal(0, 15, (9, 61, 3))
     p = str(tmp_path / "t.xtc")
@@ -152,6 +151,43 @@ def test_xtc_reader_over_libxdrfile(tmp_path):
     assert nf2 == 9 and np.array_equal(a, b)          # 10 * float64(float32) either way
     with pytest.raises(H.GoChemError):
         H.xtc_read(str(tmp_path / "missing.xtc"), 1, 1)
+
+
+def test_xtc_reader_over_the_shim_in_a_fresh_process(tmp_path):
+    """The same reader bound to tests/xdrshim (what the GPU box uses, where libxdrfile is absent).  The binding is made once per
+    process, hence the subprocess.  The shim stores float32 nanometres uncompressed, so the round trip is exact to float32."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT, build_xdrshim
+
+    code = (
+        "import numpy as np\n"
+        "from gochem_b200 import host_api as H\n"
+        "assert H.xtc_available()\n"
+        "rng = np.random.default_rng(0)\n"
+        "frames = rng.normal(0, 15, (9, 61, 3))\n"
+        "H.xtc_write(r'%s', frames)\n"
+        "a, nf, na = H.xtc_read(r'%s', 20, 61)\n"
+        "assert (nf, na) == (9, 61)\n"
+        "want = 10.0 * (frames / 10.0).astype(np.float32).astype(np.float64)\n"
+        "assert np.array_equal(a, want), np.abs(a - want).max()\n"
+        "b, nf2, _ = H.xtc_read(r'%s', 20, 61, raw=True)\n"
+        "assert nf2 == 9 and np.array_equal(a, b)\n"
+        "print('shim ok')\n"
+    ) % ((str(tmp_path / "s.xtc"),) * 3)
+    env = dict(os.environ, GOCHEM_XDRFILE=build_xdrshim(), PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "shim ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_rotator_shape_error_comes_from_the_library():
+    """geometric.go:130-132: different row counts -> "goChem: Ill-formed matrices", raised by the host library itself (the check
+    precedes any device work, so it runs without a GPU)."""
+    a, b = np.zeros((5, 3)), np.zeros((4, 3))
+    with pytest.raises(H.GoChemError, match="Ill-formed matrices") as e:
+        H.RotatorTranslatorToSuper(a, b)
+    assert "RotatorTranslatorToSuper" in str(e.value)
 
 
 def test_dcd_bulk_record_feed(tmp_path):

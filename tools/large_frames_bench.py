@@ -28,14 +28,14 @@ for n_sub in (300, 3000, 0):
     sub = np.sort(np.random.default_rng(n_sub).choice(na, n_sub, replace=False)) if n_sub else None
     res = {}
     for name, var in (("auto", _lib.KERNEL_AUTO), ("generic", _lib.KERNEL_GENERIC)):
-        _lib.check(lib.gcb_set_kernel_variant(var))
+        t.set_kernel_variant(var)
         ms = timed(lambda: t.super_rmsd_async(r, sub, sub, write_back=True))
         res[name + "_write_back_ms"] = ms
         res[name + "_write_back_GBs_48B"] = 48.0 * na * nf / ms / 1e6
         ms = timed(lambda: t.peratom_dev_sum(r, sub))
         res[name + "_per_atom_sums_ms"] = ms
         res[name + "_per_atom_sums_GBs_24B"] = 24.0 * na * nf / ms / 1e6
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    t.set_kernel_variant(_lib.KERNEL_AUTO)
     out["fit_on_%s" % (n_sub or "all")] = res
 # align.LOVO on such a system only needs the sums of its candidates (the CA atoms): 1000 atoms asked for, fit on 300 of them
 cand = np.sort(np.random.default_rng(5).choice(na, 1000, replace=False))

@@ -46,7 +46,7 @@ for na, nf in ((1500, 100000), (500, 200000), (100, 500000)):
     tt = _lib.DeviceTraj(na, nf)
     tt.synth_fill(r, s, nf)
     ms = timed(tt, lambda: tt.super_rmsd_async(r))
-    out["fit_%dx%d" % (nf, na)] = {"ms": ms, "frames_per_s": nf / ms * 1e3, "GBs": 24.0 * na * nf / ms / 1e6, "plan": _lib.last_cluster_plan()}
+    out["fit_%dx%d" % (nf, na)] = {"ms": ms, "frames_per_s": nf / ms * 1e3, "GBs": 24.0 * na * nf / ms / 1e6, "plan": tt.last_cluster_plan()}
     tt.close()
 # a solvated system: 100 000 atoms per frame, the fit on a small subset (frames untouched: RMSD + rotation only)
 na, nf = 100000, 20000
@@ -57,11 +57,11 @@ for n_sub in (300, 3000, 20000):
     sub = np.sort(np.random.default_rng(n_sub).choice(na, n_sub, replace=False))
     res = {}
     for name, var in (("auto", _lib.KERNEL_AUTO), ("generic", _lib.KERNEL_GENERIC)):
-        _lib.check(lib.gcb_set_kernel_variant(var))
+        tb.set_kernel_variant(var)
         ms = timed(tb, lambda: tb.super_rmsd_async(r, sub, sub))
         res[name + "_ms"] = ms
         res[name + "_frames_per_s"] = nf / ms * 1e3
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    tb.set_kernel_variant(_lib.KERNEL_AUTO)
     out["solvated_100k_atoms_subset_%d" % n_sub] = res
 tb.close()
 # latency of one chem.Super on host matrices (batch of one through the host mirror)

@@ -16,10 +16,10 @@ sig = synth.atom_sigmas(natoms)
 t = _lib.DeviceTraj(natoms, nframes)
 t.synth_fill(ref, sig, nframes, frame0_is_ref=True)
 if c < 0:
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_GENERIC))
+    t.set_kernel_variant(_lib.KERNEL_GENERIC)
 else:
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
-    _lib.check(lib.gcb_set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1'))))
+    t.set_kernel_variant(_lib.KERNEL_AUTO)
+    t.set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1')))
 idx = np.arange(0, natoms, 2)
 t.sync()
 t.timer_start()

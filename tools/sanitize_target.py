@@ -18,9 +18,9 @@ def check_super(natoms, nframes, idx=None, variant=_lib.KERNEL_AUTO, tuning=None
     ref, frames = synth.make_case(natoms, nframes, frame0_is_ref=True)
     t = _lib.DeviceTraj(natoms, nframes)
     t.upload(frames)
-    _lib.check(lib.gcb_set_kernel_variant(variant))
+    t.set_kernel_variant(variant)
     if tuning:
-        _lib.check(lib.gcb_set_cluster_tuning(*tuning))
+        t.set_cluster_tuning(*tuning)
     try:
         out = t.super_rmsd(ref, idx, idx)
         rm, rot, t1, t2 = oracle.super_rmsd_traj(frames, ref, idx)
@@ -35,8 +35,8 @@ def check_super(natoms, nframes, idx=None, variant=_lib.KERNEL_AUTO, tuning=None
         oracle.super_rmsd_traj(work, ref, idx, write_back=True)
         assert np.abs(t.download() - work).max() < 1e-9, label
     finally:
-        lib.gcb_set_cluster_tuning(0, 0, 0, -1)
-        lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO)
+        t.set_cluster_tuning(0, 0, 0, -1)
+        t.set_kernel_variant(_lib.KERNEL_AUTO)
         t.close()
     print("ok", label or f"{natoms} atoms x {nframes} frames", flush=True)
 

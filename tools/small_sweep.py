@@ -12,7 +12,7 @@ for na in (50, 100, 200, 300, 512, 600, 800, 1000, 1250, 1500, 2000):
     t.synth_fill(r, s, nf)
     res = {"natoms": na, "nframes": nf}
     for name, var in (("auto", _lib.KERNEL_AUTO), ("cluster", _lib.KERNEL_CLUSTER)):
-        _lib.check(lib.gcb_set_kernel_variant(var))
+        t.set_kernel_variant(var)
         for mode in ("fit", "wb"):
             fn = (lambda: t.super_rmsd_async(r)) if mode == "fit" else (lambda: t.super_rmsd_async(r, write_back=True))
             fn(); fn(); t.sync(); t.timer_start()
@@ -21,6 +21,6 @@ for na in (50, 100, 200, 300, 512, 600, 800, 1000, 1250, 1500, 2000):
             ms = t.timer_stop() / 5
             res[f"{name}_{mode}_GBs"] = round((24 if mode == "fit" else 48) * na * nf / ms / 1e6, 1)
             res[f"{name}_{mode}_Mframes_s"] = round(nf / ms / 1e3, 1)
-    _lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_AUTO))
+    t.set_kernel_variant(_lib.KERNEL_AUTO)
     print(json.dumps(res), flush=True)
     t.close()

@@ -13,7 +13,7 @@ for na in (50, 100, 200, 300, 440, 512, 600, 700, 800, 1000, 1250, 1500):
     idx = np.arange(0, na, 2)
     res = {"natoms": na, "nframes": nf}
     for name, thr in (("fused", 0), ("split", 1 << 30)):
-        _lib.check(lib.gcb_set_split_thresholds(thr, thr))
+        t.set_split_thresholds(thr, thr)
         for mode in ("wb", "lovo", "wb_subset"):
             fn = {"wb": lambda: t.super_rmsd_async(r, write_back=True), "lovo": lambda: t.peratom_dev_sum(r, idx),
                   "wb_subset": lambda: t.super_rmsd_async(r, idx, idx, write_back=True)}[mode]
@@ -21,6 +21,6 @@ for na in (50, 100, 200, 300, 440, 512, 600, 700, 800, 1000, 1250, 1500):
             for _ in range(10):
                 fn()
             res[f"{name}_{mode}_us"] = round(t.timer_stop() / 10 * 1e3, 1)
-    _lib.check(lib.gcb_set_split_thresholds(-1, -1))
+    t.set_split_thresholds(-1, -1)
     print(json.dumps(res), flush=True)
     t.close()

@@ -14,13 +14,20 @@ lib = _lib.load()
 ref = synth.make_reference(natoms)
 t = _lib.DeviceTraj(natoms, nframes)
 t.synth_fill(ref, synth.atom_sigmas(natoms), nframes, frame0_is_ref=True)
-_lib.check(lib.gcb_set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1'))))
+t.set_cluster_tuning(c, s, d, int(os.environ.get('GCB_RES', '-1')))
+mode = sys.argv[6] if len(sys.argv) > 6 else "fit"
+idx = np.arange(0, natoms, 2)
 for _ in range(2):
-    t.super_rmsd_async(ref)
+    if mode == "fit":
+        t.super_rmsd_async(ref)
+    elif mode == "wb":
+        t.super_rmsd_async(ref, write_back=True)
+    else:
+        t.peratom_dev_sum(ref, idx)
 t.sync()
 buf = np.zeros((8, 512), dtype=np.int64)
 assert lib.gcb_trace_read(buf.ctypes.data_as(C.c_void_p)) == 0
-plan = _lib.last_cluster_plan()
+plan = t.last_cluster_plan()
 D = plan["depth"]
 print("plan", plan)
 sl = slice(40, 120)

@@ -40,9 +40,9 @@ def run(label):
     print(json.dumps({"cfg": label, "ms": round(ms, 4), "GBs": round(gbs, 1), "Mframes_s": round(nframes / ms / 1e3, 3)}), flush=True)
 
 
-_lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_GENERIC))
+t.set_kernel_variant(_lib.KERNEL_GENERIC)
 run("generic")
-_lib.check(lib.gcb_set_kernel_variant(_lib.KERNEL_CLUSTER))
+t.set_kernel_variant(_lib.KERNEL_CLUSTER)
 cfgs = []
 for res in (0, 1):
     for c in (1, 2, 3, 4, 5, 6, 7, 8):
@@ -53,8 +53,8 @@ if len(sys.argv) > 4:
     cfgs = [tuple(int(x) for x in a.split(",")) for a in sys.argv[4:]]
 for c, st, d, res in cfgs:
     try:
-        _lib.check(lib.gcb_set_cluster_tuning(c, st, d, res))
+        t.set_cluster_tuning(c, st, d, res)
         run(f"C{c} S{st} D{d} R{res}")
-        print("   plan", _lib.last_cluster_plan(), flush=True)
+        print("   plan", t.last_cluster_plan(), flush=True)
     except _lib.GcbError as e:
         print(json.dumps({"cfg": f"C{c} S{st} D{d} R{res}", "err": e.msg[:80]}), flush=True)
