@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <set>
 #include <thread>
 #include <vector>
 
@@ -33,6 +34,14 @@ static Tuning g_defaults;
 Tuning default_tuning() {
     std::lock_guard<std::mutex> lock(g_defaults_mu);
     return g_defaults;
+}
+
+bool smem_opted_in(const void* kern, int dev, bool mark) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (mark) { done.insert({kern, dev}); return true; }
+    return done.count({kern, dev}) != 0;
 }
 
 void set_error(const char* fmt, ...) {

@@ -39,15 +39,19 @@ Tuning default_tuning();
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // Dynamic shared memory above 48 KB is an opt-in per (kernel, device).  It is raised to the device limit once and never lowered,
-// so concurrent callers with different launch shapes cannot shrink it under one another.
+// so concurrent callers with different launch shapes cannot shrink it under one another.  The set is keyed by the kernel's
+// ADDRESS (all instances of a kernel template share one function-pointer type).
 constexpr int kMaxOptinSmem = 227 * 1024;
+bool smem_opted_in(const void* kern, int dev, bool mark);
 template <typename Kern>
 static inline cudaError_t opt_in_smem(Kern kern, int dev) {
-    static std::atomic<unsigned long long> done{0};   // one bit per device, per kernel instantiation
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
-    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    const void* key = reinterpret_cast<const void*>(kern);
+    if (smem_opted_in(key, dev, false)) return cudaSuccess;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);    // statically declared shared memory counts against the same limit
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) smem_opted_in(key, dev, true);
     return e;
 }
 

@@ -92,7 +92,7 @@ struct __align__(16) SharedT {
     double partials[NSLOTS][kMaxCluster][14];   // 12 sums + sum w|a|^2
     double xf[NSLOTS][16];                // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
     double red[NSLOTS][kConsumerWarps][14];     // per-warp totals of a frame's sums
-    unsigned int red_count[NSLOTS];       // consumer warps that have delivered red[slot]; the last one sums and pushes
+    uint64_t red_full[NSLOTS];            // consumers -> solver: red[slot] holds every consumer warp's totals of the frame
 };
 // bytes in front of the stage ring: barriers and exchange slots, then the reduction scratch
 constexpr size_t fixed_smem(bool resident) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 
     const SuperParams& p = cp.p;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5, lane = tid & 31;   // warps: consumers 0..kConsumerWarps-1, producer, solvers
     const int C = cp.cluster, S = cp.stages, D = cp.depth, G = cp.nclusters;
     const uint32_t rank = cluster_ctarank();
     const long cid = cluster_id_x();
@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kConsumerWarps); }
         for (int s = 0; s < NS; s++) {
-            sh.red_count[s] = 0;
             mbar_init(&sh.part_full[s], 1);
             mbar_init(&sh.solved[s], 1);
+            mbar_init(&sh.red_full[s], kConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -254,6 +254,23 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         uint32_t sph = 0;
         for (int j = sw; j < nloc; j += kSolverWarps) {
             {
+                // the CTA's own sums: every consumer warp has delivered its totals of frame j; add them in a fixed tree and push
+                // the result to every CTA of the cluster (data + complete_tx on the receiver's barrier in one DSMEM transaction)
+                mbar_wait(&sh.red_full[slot], sph);
+                if (lane < 13) {
+                    double wv[kConsumerWarps];
+#pragma unroll
+                    for (int w = 0; w < kConsumerWarps; w++) wv[w] = sh.red[slot][w][lane];
+#pragma unroll
+                    for (int span = 1; span < kConsumerWarps; span *= 2) {
+#pragma unroll
+                        for (int w = 0; w + span < kConsumerWarps; w += 2 * span) wv[w] += wv[w + span];
+                    }
+                    const uint32_t dst = smem_u32(&sh.partials[slot][rank][lane]);
+                    const uint32_t bar = smem_u32(&sh.part_full[slot]);
+                    for (int c = 0; c < C; c++) st_async_f64(mapa(dst, (uint32_t)c), wv[0], mapa(bar, (uint32_t)c));
+                }
+                if (lane == 0) TRACE(1, j);
                 mbar_wait(&sh.part_full[slot], sph);
                 if (lane == 0) TRACE(2, j);
                 double s = 0.0;
@@ -268,10 +285,9 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     const long f = cid + (long)j * G;
                     const double cen[3] = {sums[0] * p.inv_n, sums[1] * p.inv_n, sums[2] * p.inv_n};
                     double h[9], r[9];
-                    bool finite = true;
 #pragma unroll
-                    for (int k = 0; k < 9; k++) { h[k] = sums[3 + k]; finite = finite && (fabs(h[k]) < 1.79e308); }
-                    int rc = finite ? k3::kabsch3(h, r) : -4;
+                    for (int k = 0; k < 9; k++) h[k] = sums[3 + k];
+                    int rc = k3::kabsch3(h, r);   // non-finite sums fail the norm guards of both solvers
                     if (rc != 0) {
                         if (p.status) atomicExch(p.status, (int)GCB_ERR_SVD);
 #pragma unroll
@@ -283,26 +299,23 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     xf[9] = fma(cen[2], r[6], fma(cen[1], r[3], cen[0] * r[0]));
                     xf[10] = fma(cen[2], r[7], fma(cen[1], r[4], cen[0] * r[1]));
                     xf[11] = fma(cen[2], r[8], fma(cen[1], r[5], cen[0] * r[2]));
-                    // RMSD without a second sweep when that is provably accurate: E = Ga + Gb - 2 tr(R^T H), the
-                    // inner-product (QCP) form.  Its rounding error is about kappa*eps*(sum w|a|^2 + Gb); it is used only when
-                    // that bound moves the RMSD by < 1e-10 A, i.e. when  kappa eps Smax <= 2e-10 sqrt(n E).  Otherwise
-                    // (frames very close to the template, e.g. the template itself) pass 2 forms the explicit residual as
-                    // the reference does (geometric.go:284-286).  Modes that run pass 2 anyway always use the explicit one.
-                    const double ga = sums[12] - (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) * p.inv_n;
-                    const double trrh = fma(r[8], h[8], fma(r[7], h[7], fma(r[6], h[6], fma(r[5], h[5], fma(r[4], h[4],
-                                        fma(r[3], h[3], fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]))))))));
-                    const double e = ga + p.gb - 2.0 * trrh;
-                    const double smax = sums[12] + p.gb;
-                    const bool formula_ok = !cp.always_explicit && rc == 0 && e > 0.0 &&
-                                            (64.0 * 2.220446049250313e-16) * smax <= 2e-10 * sqrt(p.n_fit * e);
+                    bool formula_ok = false;
+                    double e = 0.0;
+                    if (!cp.always_explicit) {
+                        const double ga = sums[12] - (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) * p.inv_n;
+                        const double tr0 = fma(r[2], h[2], fma(r[1], h[1], r[0] * h[0]));
+                        const double tr1 = fma(r[5], h[5], fma(r[4], h[4], r[3] * h[3]));
+                        const double tr2 = fma(r[8], h[8], fma(r[7], h[7], r[6] * h[6]));
+                        e = ga + p.gb - 2.0 * ((tr0 + tr1) + tr2);
+                        const double lhs = (64.0 * 2.220446049250313e-16) * (sums[12] + p.gb);
+                        formula_ok = rc == 0 && e > 0.0 && lhs * lhs <= 4e-20 * (p.n_fit * e);
+                    }
                     xf[12] = formula_ok ? 0.0 : 1.0;
                     TRACE(3, j);
                     mbar_arrive(&sh.solved[slot]);
                     if (rank == 0) {
                         if (p.need_explicit) p.need_explicit[f] = formula_ok ? 0 : 1;
                         if (formula_ok && p.rmsd) p.rmsd[f] = sqrt(e * p.inv_n);
-                    }
-                    if (rank == 0) {
                         if (p.rot) {
 #pragma unroll
                             for (int k = 0; k < 9; k++) p.rot[f * 9 + k] = r[k];
@@ -333,8 +346,6 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             if (DEV) dev[k] = 0.0;
             if (in && gi < p.natoms) real_mask |= 1u << k;   // slots that are real atoms of THIS part
         }
-        const uint32_t my_part_addr = smem_u32(&sh.partials[0][rank][0]);
-        const uint32_t part_bar_addr = smem_u32(&sh.part_full[0]);
         uint32_t in_mask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) if (tid + k * kConsumers < part_len) in_mask |= 1u << k;
@@ -403,22 +414,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 }
                 __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below; the scratch is free again
                 if (tid == 0) TRACE(7, j);
-                unsigned int prev = 0;
-                if (lane == 0) prev = atom_add_acq_rel_cta(&sh.red_count[slot1], 1u);
-                prev = __shfl_sync(0xffffffffu, prev, 0);
-                if (prev == kConsumerWarps - 1) {
-                    __syncwarp();   // lane 0's acquire is ordered before the other lanes' loads of red[]
-                    if (lane < 13) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int w = 0; w < kConsumerWarps; w++) v += sh.red[slot1][w][lane];
-                        const uint32_t off = (uint32_t)(slot1 * (int)sizeof(sh.partials[0]));
-                        for (int c = 0; c < C; c++)
-                            st_async_f64(mapa(my_part_addr + off + (uint32_t)lane * 8u, (uint32_t)c), v,
-                                         mapa(part_bar_addr + (uint32_t)slot1 * 8u, (uint32_t)c));
-                    }
-                    if (lane == 0) { atomicExch(&sh.red_count[slot1], 0u); TRACE(1, j); }
-                }
+                if (lane == 0) mbar_arrive(&sh.red_full[slot1]);   // release: the warp's stores to red[] (ordered by the __syncwarp above)
                 if (++s1 == S) { s1 = 0; ph1 ^= 1u; }
                 if (++slot1 == NS) slot1 = 0;
             }
