@@ -509,6 +509,12 @@ def bare_copy_bandwidth(d, dev, nbytes, steps):
 def run_ours(a):
     from gochem_b200 import _lib, synth
 
+    # torch (plumbing: the N > 1 rendezvous, the bare-copy and cuBLAS reference measurements) is imported BEFORE the library binds
+    # NCCL: torch brings its own libnccl.so.2, and whichever copy is loaded first serves both
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
     lib = _lib.load()
     if _lib.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")

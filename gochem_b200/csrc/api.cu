@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <set>
 #include <thread>
@@ -770,7 +771,10 @@ int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_ao
                                (nidx <= 512 ? 16L * nidx <= t->natoms
                                 : nidx <= small_gather_max_atoms() ? 8L * nidx <= t->natoms
                                                                    : (t->natoms > 28672 && 12L * nidx <= t->natoms));
+    static const bool timing = getenv("GCB_TIMING") != nullptr;
+    const auto tp0 = std::chrono::steady_clock::now();
     int rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, true, &mode, prefer_gather);
+    if (timing) fprintf(stderr, "[gcb] prepare_template %.1f us\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count());
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;
     SuperParams p;

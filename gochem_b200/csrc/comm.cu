@@ -10,8 +10,10 @@
 // NCCL is bound with dlopen at first use so the library itself loads on hosts without NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -92,8 +94,125 @@ static int comm_reserve(gcb_comm* c, long n) {
     return GCB_OK;
 }
 
+namespace gcb {
+
+// ---- the small all-reduce as ONE kernel over peer-mapped memory ----
+// LOVO's exchange is 8 bytes per atom and rank (40 KB at 5000 atoms): far below the size at which a library collective's
+// bandwidth matters, so what counts is latency.  Every rank stores its vector straight into a mailbox slot of every peer
+// (plain stores through the cudaIpc mapping, i.e. NVLink writes), publishes a sequence number with a system-scope release,
+// waits for the peers' numbers with system-scope acquires, and adds the nranks vectors of its own mailbox in rank order --
+// bit-identical totals on every rank, no NCCL call, no second kernel.  Two parities: a rank that has started exchange s + 1
+// has finished reading exchange s, and nobody can reach s + 2 before everybody has started s + 1.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct MailPtrs { double* box[8]; };
+
+__global__ void __launch_bounds__(1024) peer_exchange_sum_kernel(MailPtrs mp, int nranks, int rank, long cap, long n, unsigned long long seq,
+                                                                  double* __restrict__ vec) {
+    const int par = (int)(seq & 1ull);
+    const size_t slot = ((size_t)par * nranks + rank) * (size_t)cap;       // where this rank's vector goes in every box
+    for (int r = 0; r < nranks; r++) {
+        double* dst = mp.box[r] + slot;
+        for (long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    const size_t flags_off = (size_t)2 * nranks * (size_t)cap;              // doubles in front of the flags
+    if (threadIdx.x < nranks) {
+        unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(mp.box[threadIdx.x] + flags_off);
+        st_release_sys(peer_flags + (size_t)par * nranks + rank, seq);
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(mp.box[rank] + flags_off) + (size_t)par * nranks + threadIdx.x;
+        while (ld_acquire_sys(mine) < seq) {}
+    }
+    __threadfence_system();
+    __syncthreads();
+    const double* box = mp.box[rank] + (size_t)par * nranks * (size_t)cap;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < nranks; r++) s += __ldcg(box + (size_t)r * cap + i);   // rank order; L2, never a stale L1 line
+        vec[i] = s;
+    }
+}
+
+}  // namespace gcb
+using namespace gcb;
+
+// Collective: (re)allocate the mailboxes for vectors of up to n doubles and map every peer's.  Returns GCB_OK with
+// c->mail_state = 1, or leaves mail_state = -1 when the peers' memory cannot be mapped (the caller uses NCCL then).
+static int mail_setup(gcb_comm* c, long n) {
+    NcclApi* api = nccl();
+    if (!api) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < c->nranks; r++)
+        if (r != c->rank && c->mail[r]) { cudaIpcCloseMemHandle(c->mail[r]); c->mail[r] = nullptr; }
+    int rc = comm_barrier(c, c->stream);       // every rank has dropped its mappings before anybody frees a box
+    if (rc) return rc;
+    GCB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->mail[c->rank]);
+    c->mail[c->rank] = nullptr;
+    const long cap = (n + 511) / 512 * 512;
+    const size_t bytes = sizeof(double) * 2 * (size_t)c->nranks * (size_t)cap + sizeof(unsigned long long) * 2 * (size_t)c->nranks;
+    void* mine = nullptr;
+    GCB_CUDA(cudaMalloc(&mine, bytes));
+    GCB_CUDA(cudaMemset(mine, 0, bytes));
+    c->mail[c->rank] = (double*)mine;
+    cudaIpcMemHandle_t h;
+    GCB_CUDA(cudaIpcGetMemHandle(&h, mine));
+    unsigned char* d_h = nullptr;
+    GCB_CUDA(cudaMalloc(&d_h, 64 * (size_t)(c->nranks + 1)));
+    GCB_CUDA(cudaMemcpyAsync(d_h, &h, 64, cudaMemcpyHostToDevice, c->stream));
+    GCB_NCCL(api, api->AllGather(d_h, d_h + 64, 64, ncclChar, c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+    GCB_CUDA(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    GCB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_h);
+    int ok = 1;
+    for (int r = 0; r < c->nranks && ok; r++) {
+        if (r == c->rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->mail[r] = (double*)p;
+    }
+    // all ranks must agree on the path: one rank without peer access sends everybody to NCCL
+    int* d_ok = nullptr;
+    GCB_CUDA(cudaMalloc(&d_ok, sizeof(int) * (size_t)(c->nranks + 1)));
+    GCB_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    GCB_NCCL(api, api->AllGather(d_ok, d_ok + 1, sizeof(int), ncclChar, c->comm, c->stream));
+    std::vector<int> oks((size_t)c->nranks);
+    GCB_CUDA(cudaMemcpyAsync(oks.data(), d_ok + 1, sizeof(int) * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    GCB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_ok);
+    for (int v : oks) ok = ok && v;
+    c->mail_cap = cap;
+    c->mail_seq = 0;
+    c->mail_state = ok ? 1 : -1;
+    return GCB_OK;
+}
+
 // device vector d_vec[n] (on stream s) -> same vector summed over ranks in rank order
 static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s) {
+    static const bool force_nccl = getenv("GCB_ALLREDUCE_NCCL") != nullptr;   // the library all-gather path, for comparison
+    if (!force_nccl && c->nranks <= 8 && (c->mail_state == 0 || (c->mail_state == 1 && n > c->mail_cap))) {
+        GCB_CUDA(cudaStreamSynchronize(s));   // set-up is collective and rare; the exchange itself never synchronises
+        int rc = mail_setup(c, n);
+        if (rc) return rc;
+    }
+    if (!force_nccl && c->mail_state == 1) {
+        MailPtrs mp;
+        for (int r = 0; r < 8; r++) mp.box[r] = r < c->nranks ? c->mail[r] : nullptr;
+        c->mail_seq++;
+        peer_exchange_sum_kernel<<<1, 1024, 0, s>>>(mp, c->nranks, c->rank, c->mail_cap, n, c->mail_seq, d_vec);
+        GCB_LAUNCHED();
+        GCB_CUDA(cudaGetLastError());
+        return GCB_OK;
+    }
     NcclApi* api = nccl();
     if (!api) return GCB_ERR_CUDA;
     int rc = comm_reserve(c, n);
@@ -247,6 +366,10 @@ int gcb_comm_destroy(gcb_comm* c) {
         if (!c->peer_blk[r]) continue;
         if (r == c->rank) cudaFree(c->peer_blk[r]); else cudaIpcCloseMemHandle(c->peer_blk[r]);
     }
+    for (int r = 0; r < c->nranks; r++) {
+        if (!c->mail[r]) continue;
+        if (r == c->rank) cudaFree(c->mail[r]); else cudaIpcCloseMemHandle(c->mail[r]);
+    }
     NcclApi* api = nccl();
     if (api && c->comm) api->CommDestroy(c->comm);
     delete c;
@@ -272,15 +395,24 @@ int gcb_peratom_dev_sum(gcb_traj* t, long first, long nframes, const double* ref
     if (first < 0 || nframes < 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
     if (!sum) { set_error("NULL output"); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
+    static const bool timing = getenv("GCB_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = peratom_local(t, first, nframes, ref_aos, idx, nidx, write_back);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     if (comm && comm->nranks > 1) {
         if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
         rc = allreduce_device(comm, t->d_devsum, t->natoms, t->stream);
         if (rc) return rc;
     }
     GCB_CUDA(cudaMemcpyAsync(sum, t->d_devsum, sizeof(double) * (size_t)t->natoms, cudaMemcpyDeviceToHost, t->stream));
-    return peratom_finish(t);
+    rc = peratom_finish(t);
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gcb] peratom_dev_sum: launch side %.1f us, until results on the host %.1f us\n",
+                std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t0).count());
+    }
+    return rc;
 }
 
 int gcb_peratom_dev_sum_atoms(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want,

@@ -155,6 +155,12 @@ struct gcb_comm {
     unsigned char* d_flags = nullptr;     // barrier scratch
     double* peer_blk[8] = {nullptr};      // [rank] own block (cudaMalloc), others: cudaIpcOpenMemHandle mappings
     size_t blk_bytes = 0;
+    // mailboxes of the small all-reduce (LOVO's per-atom sums): rank r's box holds [2 parities][nranks][mail_cap] doubles that the
+    // peers store into over NVLink, then [2][nranks] sequence flags; mail[r] = rank r's box as seen from here
+    double* mail[8] = {nullptr};
+    long mail_cap = 0;                    // doubles per (parity, rank) slot
+    unsigned long long mail_seq = 0;      // exchanges done so far (the same on every rank: the call is collective)
+    int mail_state = 0;                   // 0 = not tried, 1 = usable, -1 = peer mapping failed: NCCL all-gather instead
 };
 
 namespace gcb {

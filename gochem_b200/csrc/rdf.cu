@@ -46,6 +46,7 @@ struct RdfParams {
     int nruns;
     const int* chunk_first;       // [nchunks + 1] run ranges whose atoms fit one work list
     int nchunks;
+    const int* run_key;           // per run: id of its (MolID, chain) pair; NULL when no pair names two runs (no skip rule needed)
     const unsigned char* flags;   // per atom: bit 0 = may start a residue, bit 1 = pre-screened water
     const int* refidx;
     int nref;
@@ -94,6 +95,8 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
     unsigned long long* best = reinterpret_cast<unsigned long long*>(rz + p.tile);   // [kListCap] min squared distance per slot
     int2* ent = reinterpret_cast<int2*>(best + kListCap);                             // [kListCap] (atom, slot) or (start, stop)
     unsigned int* hist = reinterpret_cast<unsigned int*>(ent + kListCap);             // [nsteps + 1]
+    int* rstart = reinterpret_cast<int*>(hist + p.nsteps + 1);                        // [kListCap] (skip rule only): first atom of a run's residue, -1 = none
+    __shared__ int carry_key;      // (MolID, chain) id of the last run that passed in the earlier chunks of the frame
     __shared__ double red[RT / 32][4];
     __shared__ double sphere[4];   // centre of the solute's bounding sphere, radius
     __shared__ int nent, nslot;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
         const double* Z = Y + p.np;
         __syncthreads();   // the previous frame's tile and histogram are no longer read
         for (int k = tid; k <= p.nsteps; k += RT) hist[k] = 0u;
+        if (tid == 0) carry_key = -1;
         if (one_tile)
             for (int j = tid; j < p.nref; j += RT) { const int a = p.refidx[j]; rx[j] = X[a]; ry[j] = Y[a]; rz[j] = Z[a]; }
         // bounding sphere of the solute: centre = mean position, radius = largest distance from it
@@ -148,16 +152,41 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
             __syncthreads();
             if (tid == 0) { nent = 0; nslot = 0; }
             __syncthreads();
-            for (int r = p.chunk_first[c] + tid; r < p.chunk_first[c + 1]; r += RT) {
-                const Run run = p.runs[r];
-                int start = -1;
-                for (int a = run.s; a < run.e; a++) {   // first atom that begins the residue (solvation.go:478-486)
+            // first atom that begins the residue of run r in this frame (solvation.go:478-486), -1 when none does
+            auto residue_start = [&](const Run& run) {
+                for (int a = run.s; a < run.e; a++) {
                     const unsigned char fl = p.flags[a];
                     if (fl & 2) {
                         const double dx = fx - X[a], dy = fy - Y[a], dz = fz - Z[a];
                         if (sqrt(dx * dx + dy * dy + dz * dz) > cutoffplus) continue;
                     }
-                    if (fl & 1) { start = a; break; }
+                    if (fl & 1) return a;
+                }
+                return -1;
+            };
+            const int r0 = p.chunk_first[c], r1 = p.chunk_first[c + 1];
+            if (p.run_key) {
+                // The reference remembers (MolID, chain) of the residue it started last and passes over atoms that carry the same
+                // pair (molid_skip / chain_skip, :486, :537-538).  Inside a run that skips the rest of the residue just read; across
+                // runs it drops a residue whose pair equals that of the last one started -- which happens in real topologies, where
+                // residue numbers wrap (9999 in PDB files) and the chain is blank.  Whether or not the previous passing run was
+                // itself dropped, the pair remembered after it equals its own, so: a run that passes starts a residue iff its pair
+                // differs from that of the PREVIOUS PASSING run of the frame.
+                for (int r = r0 + tid; r < r1; r += RT) rstart[r - r0] = residue_start(p.runs[r]);
+                __syncthreads();
+            }
+            for (int r = r0 + tid; r < r1; r += RT) {
+                const Run run = p.runs[r];
+                int start;
+                if (p.run_key) {
+                    start = rstart[r - r0];
+                    if (start < 0) continue;
+                    int prev = carry_key;
+                    for (int q = r - r0 - 1; q >= 0; q--)
+                        if (rstart[q] >= 0) { prev = p.run_key[r0 + q]; break; }
+                    if (prev == p.run_key[r]) continue;
+                } else {
+                    start = residue_start(run);
                 }
                 if (start < 0) continue;
                 if (p.com) {   // chem.CenterOfMass with nil masses: column sums in row order times 1/n (geometric.go:615-629)
@@ -181,6 +210,10 @@ __global__ void __launch_bounds__(RT) rdf_kernel(const RdfParams p) {
                 }
             }
             __syncthreads();
+            if (p.run_key && tid == 0) {
+                for (int q = r1 - r0 - 1; q >= 0; q--)
+                    if (rstart[q] >= 0) { carry_key = p.run_key[r0 + q]; break; }
+            }
             // ---- step B: every listed point against the solute ----
             const int ne = nent;
             for (int t0 = 0; t0 < p.nref; t0 += p.tile) {
@@ -259,7 +292,9 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     // runs of one MolID; a run can start a residue when it holds a candidate atom outside the solute's residues
     std::vector<Run> runs;
     std::vector<unsigned char> fl((size_t)t->np, 0);
-    std::map<std::pair<int, int>, int> seen;
+    std::map<std::pair<int, int>, int> seen;   // (MolID, chain) -> id
+    std::vector<int> run_key;
+    bool repeated_pairs = false;
     for (int s = 0; s < natoms;) {
         int e = s + 1;
         while (e < natoms && molid[e] == molid[s]) e++;
@@ -271,14 +306,12 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         }
         if (cand) {
             // The reference carries (MolID, chain) of the last residue it started and passes over atoms that match it
-            // (molid_skip / chain_skip, :486, :537-538).  With one chain per run and no (MolID, chain) pair repeated among the
-            // candidate runs that rule only ever skips the rest of the run just handled, which is what a run is here.
+            // (molid_skip / chain_skip, :486, :537-538).  With one chain per run that rule skips the rest of the run just handled,
+            // which is what a run is here; when a pair names several runs the kernel applies it across runs too (run_key).
             if (!chain_const) { set_error("gcb_rdf_cdf_sum: atoms %d..%d share MolID %d but not the chain; not supported", s, e - 1, molid[s]); return GCB_ERR_ARG; }
-            if (seen.count({molid[s], chain[s]})) {
-                set_error("gcb_rdf_cdf_sum: MolID %d / chain id %d names two separate solvent residues; renumber the topology", molid[s], chain[s]);
-                return GCB_ERR_ARG;
-            }
-            seen[{molid[s], chain[s]}] = 1;
+            auto ins = seen.emplace(std::make_pair(molid[s], chain[s]), (int)seen.size());
+            if (!ins.second) repeated_pairs = true;   // e.g. residue numbers that wrap at 9999 with a blank chain
+            run_key.push_back(ins.first->second);
             runs.push_back({s, e});
         }
         s = e;
@@ -304,6 +337,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     int* d_chunks = nullptr;
     unsigned char* d_fl = nullptr;
     int* d_ref = nullptr;
+    int* d_keys = nullptr;
     unsigned long long* d_cdf = nullptr;
     std::vector<unsigned long long> h_cdf((size_t)totalsteps, 0ull);
     int rc = GCB_OK;
@@ -314,6 +348,10 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     RDF_TRY(cudaMalloc(&d_chunks, sizeof(int) * chunk_first.size()));
     RDF_TRY(cudaMemcpyAsync(d_chunks, chunk_first.data(), sizeof(int) * chunk_first.size(), cudaMemcpyHostToDevice, t->stream));
     RDF_TRY(cudaMalloc(&d_ref, sizeof(int) * (size_t)nref));
+    if (repeated_pairs) {
+        RDF_TRY(cudaMalloc(&d_keys, sizeof(int) * run_key.size()));
+        RDF_TRY(cudaMemcpyAsync(d_keys, run_key.data(), sizeof(int) * run_key.size(), cudaMemcpyHostToDevice, t->stream));
+    }
     RDF_TRY(cudaMalloc(&d_cdf, sizeof(unsigned long long) * (size_t)totalsteps));
     RDF_TRY(cudaMemcpyAsync(d_runs, runs.data(), sizeof(Run) * runs.size(), cudaMemcpyHostToDevice, t->stream));
     RDF_TRY(cudaMemcpyAsync(d_fl, fl.data(), (size_t)t->np, cudaMemcpyHostToDevice, t->stream));
@@ -331,6 +369,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         p.nchunks = (int)chunk_first.size() - 1;
         p.tile = nref <= kRefTileMax ? (nref + 1) / 2 * 2 : kRefTileMax;
         p.flags = d_fl;
+        p.run_key = d_keys;
         p.refidx = d_ref;
         p.nref = nref;
         p.com = com ? 1 : 0;
@@ -339,7 +378,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         p.nsteps = totalsteps;
         p.cdf = d_cdf;
         const size_t smem = sizeof(double) * 3 * (size_t)p.tile + (sizeof(unsigned long long) + sizeof(int2)) * kListCap +
-                            sizeof(unsigned int) * (size_t)(totalsteps + 1);
+                            sizeof(unsigned int) * (size_t)(totalsteps + 1) + (d_keys ? sizeof(int) * kListCap : 0);
         RDF_TRY(opt_in_smem(rdf_kernel, t->dev));
         int per_sm = 1;
         RDF_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rdf_kernel, RT, smem));
@@ -354,7 +393,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     for (int k = 0; k < totalsteps; k++) cdf_sum[k] = (double)h_cdf[(size_t)k];
 done:
 #undef RDF_TRY
-    cudaFree(d_runs); cudaFree(d_chunks); cudaFree(d_fl); cudaFree(d_ref); cudaFree(d_cdf);
+    cudaFree(d_runs); cudaFree(d_chunks); cudaFree(d_fl); cudaFree(d_ref); cudaFree(d_keys); cudaFree(d_cdf);
     if (rc) return rc;
     if (comm) {   // frames sharded over ranks: the counts add up (integers below 2^53: exact in any order)
         rc = gcb_allreduce_sum_f64(comm, cdf_sum, totalsteps);

@@ -99,12 +99,13 @@ constexpr size_t fixed_smem(bool resident) {
     return ((resident ? sizeof(SharedT<kResidentSlots>) : sizeof(SharedT<kMaxSlots>)) + 127) / 128 * 128 + kRedScratchBytes;
 }
 
-// sqrt of a non-negative double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
+// sqrt of a positive double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
 // error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
 // 1/(1+e) = (1-2r)^(-1/2) = 1 + r + 3/2 r^2 + O(r^3), so sqrt(x) = g + g r (1 + 3/2 r) with relative error 2.5 |e|^3 <
 // 2^-58 -- one correction of cubic order, four dependent fp64 operations after the seed (six in all) instead of two Newton
-// steps.  Zero and denormal arguments (seed = inf) return 0: the error is below 1.5e-154.
-__device__ __forceinline__ double fast_sqrt(double x) {
+// steps.  The argument must be bounded away from zero (a zero or denormal gives seed = inf): the caller folds 1e-290 into the
+// sum of squares, which moves the square root by less than 1e-145 and saves the three integer instructions of a guard.
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double g = x * y;
@@ -112,9 +113,22 @@ __device__ __forceinline__ double fast_sqrt(double x) {
     const double r = fma(-g, h, 0.5);
     const double p = fma(1.5, r, 1.0);
     const double gr = g * r;
-    const double out = fma(gr, p, g);
-    return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
+    return fma(gr, p, g);
 }
+
+// Slot k of a consumer thread <-> atom of the CTA's part.  With an even K a thread owns PAIRS of neighbouring atoms (2 tid and
+// 2 tid + 1 of every block of 512 atoms), so its loads and stores are 16 bytes wide (LDS.128 / LDG.128 / STG.128): half the
+// memory instructions of the one-atom-per-256 layout, which remains for odd K.  Parts hold a multiple of 16 atoms, so a pair is
+// inside the part or outside it as a whole.
+// Measured (profiles/r2_tuning.md): the pairs pay in the per-atom-distance pass (50 k x 5 k: 1.141 -> 1.126 ms); the wider
+// loads cost registers, and the fit-only K = 14 instance (3.27 -> 3.33 ms) and the write-back K = 10 instance (7.7 -> 10.6 ms,
+// spills inside the store loop) lose, so only the DEV instances pair.
+template <int K, bool DEV>
+struct Slots {
+    static constexpr bool PAIR = DEV && (K % 2 == 0);
+    static __device__ __forceinline__ int base(int tid) { return PAIR ? 2 * tid : tid; }
+    static __device__ __forceinline__ constexpr int off(int k) { return PAIR ? (k >> 1) * 2 * kConsumers + (k & 1) : k * kConsumers; }
+};
 
 // pass 2 for one thread's K atom slots.  RESIDENT: the frame part is still in its shared-memory stage
 // (plane stride K*256); otherwise it is re-read from global memory, where it still sits in L2 (plane
@@ -126,13 +140,15 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
                                               const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
                                               uint32_t fit_mask, double (&dev)[DEV ? K : 1], double* frw, int np,
                                               uint32_t real_mask, uint32_t in_mask, double b0, double b1, double b2) {
+    using SL = Slots<K, DEV>;
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
 #ifdef GCB_PASS2_CH
-    constexpr int CH = GCB_PASS2_CH < K ? GCB_PASS2_CH : K;   // tuning builds
+    constexpr int CH = GCB_PASS2_CH < K ? GCB_PASS2_CH : K;   // tuning builds (even for even K)
 #else
-    constexpr int CH = (K % 5 == 0) ? 5 : 4;   // atoms in flight per thread: enough independent chains, bounded register use
+    // atoms in flight per thread: enough independent chains, bounded register use; whole pairs when the slots are paired
+    constexpr int CH = SL::PAIR ? 4 : ((K % 5 == 0) ? 5 : 4);
 #endif
 #pragma unroll
     for (int kb = 0; kb < K; kb += CH) {
@@ -141,34 +157,76 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
         for (int c = 0; c < CH; c++) {
             const int k = kb + c;
             if (k >= K) { x[c] = y[c] = z[c] = 0.0; continue; }
-            if (RESIDENT) {
-                x[c] = src[k * kConsumers]; y[c] = src[plane + k * kConsumers]; z[c] = src[2 * plane + k * kConsumers];
+            if (SL::PAIR) {
+                if (c & 1) continue;   // loaded together with its even neighbour
+                const double* q = src + SL::off(k);
+                double2 vx, vy, vz;
+                if (RESIDENT) {
+                    vx = *reinterpret_cast<const double2*>(q); vy = *reinterpret_cast<const double2*>(q + plane);
+                    vz = *reinterpret_cast<const double2*>(q + 2 * plane);
+                } else if ((in_mask >> k) & 1u) {
+                    vx = __ldcs(reinterpret_cast<const double2*>(q)); vy = __ldcs(reinterpret_cast<const double2*>(q + plane));
+                    vz = __ldcs(reinterpret_cast<const double2*>(q + 2 * plane));
+                } else {
+                    vx = vy = vz = make_double2(0.0, 0.0);
+                }
+                x[c] = vx.x; y[c] = vy.x; z[c] = vz.x;
+                if (c + 1 < CH) { x[c + 1] = vx.y; y[c + 1] = vy.y; z[c + 1] = vz.y; }
+            } else if (RESIDENT) {
+                x[c] = src[SL::off(k)]; y[c] = src[plane + SL::off(k)]; z[c] = src[2 * plane + SL::off(k)];
             } else if ((in_mask >> k) & 1u) {
-                x[c] = __ldcs(src + k * kConsumers); y[c] = __ldcs(src + plane + k * kConsumers); z[c] = __ldcs(src + 2 * plane + k * kConsumers);
+                x[c] = __ldcs(src + SL::off(k)); y[c] = __ldcs(src + plane + SL::off(k)); z[c] = __ldcs(src + 2 * plane + SL::off(k));
             } else {
                 x[c] = 0.0; y[c] = 0.0; z[c] = 0.0;
             }
         }
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
+        // one atom: rotate, distance to the template, sums; returns the superposed coordinates for the write-back
+        auto atom = [&](int c, double& ox, double& oy, double& oz) {
             const int k = kb + c;
-            if (k >= K) continue;
             // (a - centroid) R  computed as  a R - centroid R
             const double qx = fma(z[c], r6, fma(y[c], r3, fma(x[c], r0, g0)));
             const double qy = fma(z[c], r7, fma(y[c], r4, fma(x[c], r1, g1)));
             const double qz = fma(z[c], r8, fma(y[c], r5, fma(x[c], r2, g2)));
             const double dx = qx - bx[k], dy = qy - by[k], dz = qz - bz[k];
-            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (DEV) {
-                dev[k] += fast_sqrt(d2);
+                // 1e-290 keeps the argument of the guard-free square root away from zero (it moves the distance by < 1e-145)
+                dev[k] += fast_sqrt_pos(fma(dz, dz, fma(dy, dy, fma(dx, dx, 1e-290))));
             } else if (((MASKED ? fit_mask : real_mask) >> k) & 1u) {   // atoms of the fit count once; padding slots never
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
                 if (k & 1) e1 += d2; else e0 += d2;
             }
-            if (WB) {
-                if ((real_mask >> k) & 1u) {
-                    frw[k * kConsumers] = qx + b0;
-                    frw[np + k * kConsumers] = qy + b1;
-                    frw[2L * np + k * kConsumers] = qz + b2;
+            if (WB) { ox = qx + b0; oy = qy + b1; oz = qz + b2; }
+        };
+        if (SL::PAIR) {
+#pragma unroll
+            for (int c = 0; c < CH; c += 2) {
+                const int k = kb + c;
+                if (k >= K) continue;
+                double ax = 0.0, ay = 0.0, az = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+                atom(c, ax, ay, az);
+                atom(c + 1, cx, cy, cz);
+                if (WB) {
+                    double* q = frw + SL::off(k);
+                    const uint32_t both = (real_mask >> k) & 3u;
+                    if (both == 3u) {
+                        *reinterpret_cast<double2*>(q) = make_double2(ax, cx);
+                        *reinterpret_cast<double2*>(q + np) = make_double2(ay, cy);
+                        *reinterpret_cast<double2*>(q + 2L * np) = make_double2(az, cz);
+                    } else if (both == 1u) {   // the last real atom of an odd count
+                        q[0] = ax; q[np] = ay; q[2L * np] = az;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int k = kb + c;
+                if (k >= K) continue;
+                double ax = 0.0, ay = 0.0, az = 0.0;
+                atom(c, ax, ay, az);
+                if (WB && ((real_mask >> k) & 1u)) {
+                    double* q = frw + SL::off(k);
+                    q[0] = ax; q[np] = ay; q[2L * np] = az;
                 }
             }
         }
@@ -331,12 +389,14 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         }
     } else {
         // ===================== consumers (warps run free of one another) =====================
-        // fixed atom slots: local index tid + k*256; template and weights stay in registers
+        // fixed atom slots (Slots<K>: pairs of neighbouring atoms when K is even); template and weights stay in registers
+        using SL = Slots<K, DEV>;
+        const int tbase = SL::base(tid);
         double bx[K], by[K], bz[K], dev[DEV ? K : 1];
         uint32_t real_mask = 0, fit_mask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const int li = tid + k * kConsumers;
+            const int li = tbase + SL::off(k);
             const int gi = part0 + li;
             const bool in = li < part_len;
             bx[k] = in ? p.refc[gi] : 0.0;
@@ -348,12 +408,12 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
         }
         uint32_t in_mask = 0;
 #pragma unroll
-        for (int k = 0; k < K; k++) if (tid + k * kConsumers < part_len) in_mask |= 1u << k;
+        for (int k = 0; k < K; k++) if (tbase + SL::off(k) < part_len) in_mask |= 1u << k;
         int s1 = 0, s2 = 0, slot1 = 0, slot2 = 0;      // stage / exchange slot of pass 1 (frame j) and pass 2 (frame j-D)
         uint32_t ph1 = 0, ph2 = 0;                     // parities: full[s1], solved[slot2]
         const long fstep = (long)G * p.frame_stride;
-        const double* fr2 = p.frames + cid * p.frame_stride + part0 + tid;     // frame of pass 2 (global / L2 copy)
-        double* frw = cp.write_back ? (p.frames_rw + cid * p.frame_stride + part0 + tid) : nullptr;
+        const double* fr2 = p.frames + cid * p.frame_stride + part0 + tbase;     // frame of pass 2 (global / L2 copy)
+        double* frw = cp.write_back ? (p.frames_rw + cid * p.frame_stride + part0 + tbase) : nullptr;
         double* ep = cp.epart + (cid * C + rank) * kConsumerWarps + warp;
         const long ep_step = (long)G * C * kConsumerWarps;
         for (int j = 0; j < nloc + D; j++) {
@@ -366,15 +426,19 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 if (tid == 0) TRACE(4, j);
                 mbar_wait(&sh.full[s1], ph1);
                 if (tid == 0) TRACE(5, j);
-                const double* sx = stage_base + (long)s1 * kStageDoubles + tid;
+                const double* sx = stage_base + (long)s1 * kStageDoubles + tbase;
                 const double* sy = sx + K * kConsumers;
                 const double* sz = sy + K * kConsumers;
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    double x = sx[k * kConsumers], y = sy[k * kConsumers], z = sz[k * kConsumers];
-                    if (MASKED) {   // atoms outside the fit contribute zeros (selects, not fp64 multiplies)
+                // one atom of pass 1: S += w a, H += (w a) b'^T, sum w|a|^2
+                auto atom = [&](double x, double y, double z, int k) {
+                    if (MASKED) {
+                        // Atoms outside the fit must contribute nothing.  Clearing the HIGH word alone leaves a denormal below
+                        // 2^32 * 2^-1074 = 2e-314 -- nothing a sum of coordinates can see -- for one select per coordinate instead
+                        // of two (and no fp64 multiply by a weight).
                         const bool on = (fit_mask >> k) & 1u;
-                        x = on ? x : 0.0; y = on ? y : 0.0; z = on ? z : 0.0;
+                        x = __hiloint2double(on ? __double2hiint(x) : 0, __double2loint(x));
+                        y = __hiloint2double(on ? __double2hiint(y) : 0, __double2loint(y));
+                        z = __hiloint2double(on ? __double2hiint(z) : 0, __double2loint(z));
                     }
                     if (!DEV) {   // only the one-pass RMSD needs sum w|a|^2; the per-atom-distance pass always runs pass 2
                         const double n2 = fma(z, z, fma(y, y, x * x));
@@ -384,6 +448,19 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     acc[3] = fma(x, bx[k], acc[3]); acc[4] = fma(x, by[k], acc[4]); acc[5] = fma(x, bz[k], acc[5]);
                     acc[6] = fma(y, bx[k], acc[6]); acc[7] = fma(y, by[k], acc[7]); acc[8] = fma(y, bz[k], acc[8]);
                     acc[9] = fma(z, bx[k], acc[9]); acc[10] = fma(z, by[k], acc[10]); acc[11] = fma(z, bz[k], acc[11]);
+                };
+                if (SL::PAIR) {
+#pragma unroll
+                    for (int k = 0; k < K; k += 2) {
+                        const double2 vx = *reinterpret_cast<const double2*>(sx + SL::off(k));
+                        const double2 vy = *reinterpret_cast<const double2*>(sy + SL::off(k));
+                        const double2 vz = *reinterpret_cast<const double2*>(sz + SL::off(k));
+                        atom(vx.x, vy.x, vz.x, k);
+                        atom(vx.y, vy.y, vz.y, k + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; k++) atom(sx[SL::off(k)], sy[SL::off(k)], sz[SL::off(k)], k);
                 }
                 if (!RESIDENT) {
                     __syncwarp();
@@ -431,7 +508,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                         if (++s2 == S) s2 = 0;
                     }
                 } else if (RESIDENT) {
-                    const double* sx = stage_base + (long)s2 * kStageDoubles + tid;
+                    const double* sx = stage_base + (long)s2 * kStageDoubles + tbase;
                     if (frw) e = pass2_atoms<K, MASKED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
                     else e = pass2_atoms<K, MASKED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
@@ -456,7 +533,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             double* row = p.devpart + cid * (long)p.np;
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                const int li = tid + k * kConsumers;
+                const int li = tbase + SL::off(k);
                 if (li < part_len) row[part0 + li] = dev[k];
             }
         }

@@ -3,6 +3,7 @@
 #include "gochem.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 
 #include "../../include/gochem_b200.h"
@@ -796,6 +798,48 @@ Error mobileLimit(double limit, int tolerance, const std::vector<double>& rmsd, 
     return Error();
 }
 
+// The permutation sort.Stable leaves (lovo.go:429-432, Less = rMSDs[i] < rMSDs[j]): ascending values, ties in their original
+// order.  Non-negative finite doubles order like their bit patterns, so the common case is an LSD radix sort on the 64-bit keys
+// (stable by construction, ~10x faster than a comparison sort with indirection at 5000 candidates -- the sort was a third of a
+// LOVO iteration's host time); anything else (negative values, NaN) takes std::stable_sort with the same comparison.
+void stableOrderByValue(const std::vector<double>& v, std::vector<int>* order) {
+    const size_t n = v.size();
+    order->resize(n);
+    bool radix_ok = n >= 64;
+    for (size_t k = 0; k < n && radix_ok; k++) radix_ok = v[k] >= 0.0 && v[k] <= 1.79e308;   // false for NaN as well
+    if (!radix_ok) {
+        for (size_t k = 0; k < n; k++) (*order)[k] = (int)k;
+        std::stable_sort(order->begin(), order->end(), [&](int a, int b) { return v[(size_t)a] < v[(size_t)b]; });
+        return;
+    }
+    // Three 11-bit passes over the TOP 33 bits (sign, exponent, 20 bits of mantissa) put almost everything in place; one
+    // insertion pass on the full keys (strict comparisons, so ties keep their order) finishes the few neighbours that agree
+    // in those bits.
+    struct Item { uint64_t key; int idx; };
+    static thread_local std::vector<Item> a, b;   // scratch kept between calls: two fresh 80 KB vectors cost as much as the sort
+    if (a.size() < n) { a.resize(n); b.resize(n); }
+    for (size_t k = 0; k < n; k++) {
+        const double d = v[k] + 0.0;   // -0.0 -> +0.0
+        memcpy(&a[k].key, &d, 8);
+        a[k].idx = (int)k;
+    }
+    constexpr int kBits = 11, kBuckets = 1 << kBits;
+    for (int shift = 31; shift < 64; shift += kBits) {
+        uint32_t count[kBuckets + 1] = {0};
+        for (size_t k = 0; k < n; k++) count[((a[k].key >> shift) & (kBuckets - 1)) + 1]++;
+        for (int q = 0; q < kBuckets; q++) count[q + 1] += count[q];
+        for (size_t k = 0; k < n; k++) b[count[(a[k].key >> shift) & (kBuckets - 1)]++] = a[k];
+        a.swap(b);
+    }
+    for (size_t k = 1; k < n; k++) {
+        const Item it = a[k];
+        size_t j = k;
+        while (j > 0 && a[j - 1].key > it.key) { a[j] = a[j - 1]; j--; }
+        a[j] = it;
+    }
+    for (size_t k = 0; k < n; k++) (*order)[k] = a[k].idx;
+}
+
 bool approxEq(double i, double j, double epsilon) { return std::fabs(i) - std::fabs(j) <= epsilon; }
 
 // The reference answers "is v in the list" with a linear search (lovo.go:474-484), O(n^2) per LOVO iteration -- 75 M
@@ -856,11 +900,14 @@ std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::strin
 std::vector<MolIDandChain> iDs2MolIDandChains(const chem::Atomer& mol, const std::vector<int>& indexes) {
     // first occurrences in list order, as the reference's search over the growing result (lovo.go:540-551)
     std::vector<MolIDandChain> ret;
-    std::map<std::pair<int, std::string>, bool> seen;
+    std::unordered_map<std::string, int> chain_id;            // chains are few: intern them, then hash (molid, chain id)
+    std::unordered_set<uint64_t> seen;
+    seen.reserve(indexes.size() * 2);
     for (int v : indexes) {
         const chem::Atom& at = mol.Atom(v);
-        auto ins = seen.emplace(std::make_pair(at.MolID, at.Chain), true);
-        if (ins.second) ret.push_back(MolIDandChain{at.MolID, at.Chain});
+        auto c = chain_id.emplace(at.Chain, (int)chain_id.size());
+        const uint64_t key = ((uint64_t)(uint32_t)at.MolID << 32) | (uint32_t)c.first->second;
+        if (seen.insert(key).second) ret.push_back(MolIDandChain{at.MolID, at.Chain});
     }
     return ret;
 }
@@ -909,9 +956,8 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
         *err = Error("Inconsistent data, if given, the number of initial RMSD values must match the number of residues");  // :373-375 panic
         return true;
     }
-    std::vector<int> order(full_.size());
-    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return filtered[(size_t)a] < filtered[(size_t)b]; });  // sort.Stable, :429-432
+    std::vector<int> order;
+    stableOrderByValue(filtered, &order);   // sort.Stable by rMSDs[i] < rMSDs[j], :418-432
     ids_.resize(order.size());
     vals_.resize(order.size());
     for (size_t k = 0; k < order.size(); k++) { ids_[k] = full_[(size_t)order[k]]; vals_[k] = filtered[(size_t)order[k]]; }
@@ -934,11 +980,11 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
 
 void LovoState::Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const {
     // RMSD.SortBy("molid") (:254): stable by candidate atom index
-    std::vector<int> order(ids_.size());
-    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ids_[(size_t)a] < ids_[(size_t)b]; });
-    out->RMSD.resize(order.size());
-    for (size_t k = 0; k < order.size(); k++) out->RMSD[k] = vals_[(size_t)order[k]];
+    std::vector<std::pair<int, double>> byid(ids_.size());
+    for (size_t k = 0; k < byid.size(); k++) byid[k] = {ids_[k], vals_[k]};
+    std::stable_sort(byid.begin(), byid.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+    out->RMSD.resize(byid.size());
+    for (size_t k = 0; k < byid.size(); k++) out->RMSD[k] = byid[k].second;
     out->N = n_;
     out->Natoms.assign(indexesold_.begin(), indexesold_.begin() + n_);  // previous order, new n (:255)
     out->Nmols = iDs2MolIDandChains(mol, out->Natoms);
@@ -1367,7 +1413,9 @@ Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_p
         if (dbg) fprintf(stderr, "[LOVO] iteration %d, fit on %zu atoms, local frames %ld\n", st.Iterations(), st.FitIndexes().size(), d->LocalFrames());
         if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228
         const bool wb = !o->writeTraj_.empty();
+        const auto t0 = std::chrono::steady_clock::now();
         if (Error e = d->MeanDeviations(ref, st.FitIndexes(), *o, wb, &rmsd, &fullindexes)) return e;
+        const auto t1 = std::chrono::steady_clock::now();
         if (wb) {
             if (Error e = d->WriteDCD(o->writeTraj_)) return e;
             // the pass rewrote the resident frames; later passes start from the source again (the reference
@@ -1376,6 +1424,11 @@ Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_p
         }
         Error serr;
         const bool converged = st.Step(rmsd, &serr);
+        if (dbg) {
+            const auto t2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[LOVO]   pass %.1f us, bookkeeping %.1f us\n", std::chrono::duration<double, std::micro>(t1 - t0).count(),
+                    std::chrono::duration<double, std::micro>(t2 - t1).count());
+        }
         if (serr) return serr;
         if (converged) break;
         if (st.Iterations() >= o->maxIter_) return Error("align.LOVO: no convergence after " + std::to_string(st.Iterations()) + " iterations");

@@ -441,6 +441,7 @@ struct LOVOReturn {  // lovo.go:68-150
 // lovo.go:175-188 and its helpers; exposed because the index sets must match the reference bit for bit.
 Error mobileLimit(double limit, int tolerance, const std::vector<double>& sorted_rmsd, int* n, double* newlimit);
 bool approxEq(double i, double j, double epsilon);                       // :436-442
+void stableOrderByValue(const std::vector<double>& v, std::vector<int>* order);   // the permutation of sort.Stable by value, :429-432
 bool sameElementsInt(const std::vector<int>& a, const std::vector<int>& b);  // :446-457
 int disagreementInt(const std::vector<int>& a, const std::vector<int>& b);   // :459-471
 std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::string>& names, const std::vector<std::string>& chains);  // :504-516

@@ -205,7 +205,8 @@ int gcb_moments_fetch(gcb_traj *t, long nframes, double *center, double *moment)
  *   refidx[nref]: the solute atoms; com: solv.Options.COM (distance from the residue's centre).
  *   cpus: frames are consumed in chunks of cpus; a trailing partial chunk is not read (as with a DCD source, dcd.go:520-523).
  *   comm (may be NULL): ranks hold disjoint frame shards; the counts and frames_read are summed over the ranks.
- * Topologies in which one (MolID, chain) pair names two separate solvent residues are refused (GCB_ERR_ARG). */
+ * A (MolID, chain) pair may name several separate solvent residues (residue numbers wrap at 9999 in PDB topologies): the
+ * reference's molid_skip / chain_skip rule (:486, :537-538) is applied across them as it would be atom by atom. */
 int gcb_rdf_cdf_sum(gcb_traj *t, long first, long nframes, const int *molid, const int *chain, const unsigned char *flags,
                     const int *refidx, int nref, int com, double step, double end, int cpus, gcb_comm *comm,
                     double *cdf_sum, long *frames_read);

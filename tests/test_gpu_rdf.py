@@ -133,3 +133,64 @@ def test_rdf_golden_fixture(golden_dir, com):
     one, _ = t.rdf_cdf_sum(z["molid"], z["chain"], z["flags"], z["refidx"], com=bool(com), first=4, nframes=1)
     assert np.array_equal(one, z["cdf_frames_com%d" % com][4])
     t.close()
+
+
+def test_rdf_residue_numbers_that_wrap():
+    """A solvated box whose water numbering wraps (resSeq is four digits in PDB files) and whose chain is blank: the same
+    (MolID, chain) pair names several waters.  The reference only passes over a residue whose pair equals that of the residue it
+    started LAST (molid_skip / chain_skip, solvation.go:486, 537-538); the counts must equal the oracle's, which walks the atoms
+    one by one like the reference."""
+    frames, molid, chain, flags, refidx, _, _ = solvated_system(nsolute=40, nwater=10500, nions=30, nframes=3, seed=21, box=60.0)
+    nsol = 40
+    wat = np.arange(10500)
+    molid[nsol:nsol + 3 * 10500] = np.repeat(5 + wat % 9999, 3)            # 10500 waters numbered 5 .. 10003, then 5 .. again
+    chain[:] = 0                                                            # blank chain everywhere
+    molid[nsol + 3 * 10500:] = 20000 + np.arange(30)
+    t = device_traj(frames)
+    try:
+        for com in (False, True):
+            got, read = t.rdf_cdf_sum(molid, chain, flags, refidx, com=com, end=12.0)
+            want, wread = oracle.rdf_cdf_sum(frames, molid, chain, flags, refidx, com=com, end=12.0)
+            assert read == wread and want.max() > 10
+            assert np.array_equal(got, want)
+    finally:
+        t.close()
+
+
+def test_rdf_skip_rule_fires_across_runs():
+    """Two waters with the same (MolID, chain) and no residue started between them: the reference drops the second one, and a
+    third one with the pair again, and counts the next residue with another pair.  Also across the boundary of a work-list chunk
+    (more than 4096 candidate atoms between the two) and when the first of the pair is itself dropped."""
+    rng = np.random.default_rng(8)
+    nsol = 6
+    sol = rng.normal(0, 1.0, (nsol, 3))
+    near = lambda k: np.array([3.0 + 0.3 * k, 0.0, 0.0]) + rng.normal(0, 0.05, (3, 3))     # a water about 3 A from the solute
+    far = lambda: np.array([40.0, 40.0, 40.0]) + rng.normal(0, 3.0, (3, 3))                # beyond end + 3: never starts
+    waters, ids = [], []
+    # id 7 near, (far ones), id 7 near again -> dropped, id 7 near -> dropped, id 8 near -> counted, id 7 near -> counted again
+    for k, (pos, i) in enumerate([(near(0), 7), (far(), 9), (far(), 10), (near(1), 7), (near(2), 7), (near(3), 8), (near(4), 7)]):
+        waters.append(pos); ids.append(i)
+    # 1500 far waters (4500 atoms: the next near pair straddles a chunk of the work list), then the pair 8 / 8
+    for k in range(1500):
+        waters.append(far()); ids.append(100 + k)
+    waters.append(near(5)); ids.append(3000)
+    for k in range(1500):
+        waters.append(far()); ids.append(4000 + k)
+    waters.append(near(6)); ids.append(3000)          # same pair as the last one started, 4500 atoms earlier -> dropped
+    waters.append(near(7)); ids.append(3001)
+    coords = np.concatenate([sol] + waters)
+    n = coords.shape[0]
+    frames = np.stack([coords + rng.normal(0, 0.01, (n, 3)) for _ in range(5)]).astype(np.float32).astype(np.float64)
+    molid = np.concatenate([np.ones(nsol), np.repeat(ids, 3)]).astype(np.int32)
+    chain = np.zeros(n, dtype=np.int32)
+    flags = np.concatenate([np.zeros(nsol), np.full(n - nsol, 3)]).astype(np.uint8)
+    refidx = np.arange(nsol)
+    t = device_traj(frames)
+    try:
+        got, read = t.rdf_cdf_sum(molid, chain, flags, refidx, step=0.5, end=10.0)
+        want, _ = oracle.rdf_cdf_sum(frames, molid, chain, flags, refidx, step=0.5, end=10.0)
+        assert np.array_equal(got, want)
+        # 8 near waters, 3 of them dropped by the rule: 5 ranked per frame, minus one (solvation.go:402-404), 5 frames
+        assert got[-1] == 5 * (5 - 1)
+    finally:
+        t.close()
