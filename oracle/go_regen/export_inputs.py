@@ -49,7 +49,45 @@ def export_lovo(path: str) -> str:
         np.array([ref.shape[0], frames.shape[0], 0, int(z["cpus"])], "<i8").tofile(f)
         ref.tofile(f)
         frames.tofile(f)
+        if "begin_skip" in z.files:   # (begin, skip) pairs of the align.RMSDTraj runs
+            combos = z["begin_skip"].astype("<i8")
+            np.array([combos.shape[0]], "<i8").tofile(f)
+            combos.tofile(f)
     return out
+
+
+def export_rdf(path: str) -> str:
+    """The solv.FrameUMolCRDF case: topology as three integer arrays, the solute, float64 frames."""
+    z = np.load(path)
+    frames = z["frames"].astype("<f8")
+    os.makedirs(OUT, exist_ok=True)
+    out = os.path.join(OUT, os.path.basename(path)[:-4] + ".rdf.in.bin")
+    with open(out, "wb") as f:
+        np.array([frames.shape[1], frames.shape[0], z["refidx"].size], "<i8").tofile(f)
+        np.array([float(z["step"]), float(z["end"])], "<f8").tofile(f)
+        for k in ("molid", "chain", "flags", "refidx"):
+            z[k].astype("<i8").tofile(f)
+        frames.tofile(f)
+    return out
+
+
+def read_moments(path: str, nframes: int) -> dict:
+    a = np.fromfile(path, "<f8").reshape(nframes, 12)
+    return {"center": a[:, :3], "moment": a[:, 3:].reshape(nframes, 3, 3)}
+
+
+def read_rmsdtraj(path: str, natoms: int, ncombos: int) -> list:
+    out = []
+    with open(path, "rb") as f:
+        for _ in range(ncombos):
+            read = int(np.fromfile(f, "<i8", 1)[0])
+            out.append((read, np.fromfile(f, "<f8", natoms)))
+    return out
+
+
+def read_rdf(path: str, nframes: int, nsteps: int) -> dict:
+    a = np.fromfile(path, "<f8").reshape(2, nframes, nsteps)
+    return {"com0": a[0], "com1": a[1]}
 
 
 def read_lovo_outputs(path: str) -> dict:
@@ -65,3 +103,5 @@ if __name__ == "__main__":
         print(export(p))
     for p in sorted(glob.glob(os.path.join(GOLDEN, "lovo_*.npz"))):
         print(export_lovo(p))
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "rdf_*.npz"))):
+        print(export_rdf(p))

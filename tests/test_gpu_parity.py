@@ -38,7 +38,8 @@ def device_traj(frames):
     return t
 
 
-@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
+@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500", "super_edge_mirror_n120", "super_edge_planar_n120",
+                                  "super_edge_neardeg_n120"])
 def test_golden_vectors(golden_dir, name, variant):
     g = load(golden_dir, name)
     ref = g["ref"].astype(np.float64)

