@@ -339,7 +339,9 @@ int gch_lovo(const char* path, const double* ref, int natoms, const char* const*
 int gch_lovo_resident(void* traj_handle, long nlocal, long nselected_total, const double* ref, int natoms, int cpus,
                       double less_than, int minimum_n, void* comm, int rank, int nranks, int* N, int* natoms_out, double* rmsd_out,
                       int* iterations) {
-    FlatTopology top = topology(natoms, nullptr, nullptr, nullptr);
+    // the all-CA topology of the synthetic configs is the caller's in real use: built once per atom count, not per call
+    static thread_local FlatTopology top;
+    if (top.Len() != natoms) top = topology(natoms, nullptr, nullptr, nullptr);
     std::unique_ptr<align::Options> o(align::DefaultOptions());
     o->Cpus(&cpus);
     o->LessThanRMSD(&less_than);

@@ -86,14 +86,17 @@ def test_rdf_prescreen_quirk_and_own_residues():
     assert 5 in ids and not set(ids) & {1, 2, 3, 4}
 
 
-def test_rdf_refuses_repeated_residue_ids():
-    frames, molid, chain, flags, refidx, _, _ = solvated_system(nwater=30, nions=0, nframes=2)
+def test_rdf_repeated_residue_ids_follow_the_reference():
+    """A water that reuses another water's MolID (same chain) used to be refused; the reference handles it with its
+    molid_skip / chain_skip rule, and so does the kernel now -- equal to the oracle in both Options.COM modes."""
+    frames, molid, chain, flags, refidx, _, _ = solvated_system(nwater=30, nions=0, nframes=4)
     molid = molid.copy()
     molid[-3:] = molid[40]                           # the last water reuses the first water's MolID
     t = device_traj(frames)
-    with pytest.raises(_lib.GcbError) as e:
-        t.rdf_cdf_sum(molid, chain, flags, refidx)
-    assert e.value.code == _lib.ERR_ARG
+    for com in (False, True):
+        got, _ = t.rdf_cdf_sum(molid, chain, flags, refidx, com=com)
+        want, _ = oracle.rdf_cdf_sum(frames, molid, chain, flags, refidx, com=com)
+        assert np.array_equal(got, want)
     t.close()
 
 
