@@ -9,12 +9,17 @@
 // of that expression are recomputed from the explicit differences.
 //
 // The contraction is the one dense GEMM of the path, so it runs on the tensor cores: tcgen05 has no fp64 kind, the
-// fp64 tensor path on sm_100a is mma.sync.m8n8k4.f64 (DMMA).  128 x 128 x 16 CTA tiles, 8 warps (64 x 32 each),
-// 3-stage cp.async pipeline, only tiles on or above the diagonal are computed and mirrored in the epilogue.
+// fp64 tensor path on sm_100a is mma.sync.m8n8k4.f64 (DMMA).  128 x 128 CTA tiles, 8 MMA warps (64 x 32 each) fed by one
+// producer warp: 2-D TMA (cp.async.bulk.tensor, 128-byte swizzle) into a ring of shared-memory stages handed over with
+// full / empty mbarriers -- no CTA-wide barrier and no address arithmetic in the MMA warps.  Only tiles on or above the
+// diagonal are computed and mirrored in the epilogue.
+#include <cuda.h>
+
 #include <vector>
 
 #include "common.cuh"
 #include "kabsch3.cuh"
+#include "ptx.cuh"
 
 namespace gcb {
 
@@ -27,7 +32,10 @@ namespace {
 #define GCB_AP_STAGES 2
 #endif
 constexpr int BM = 128, BN = 128, BK = GCB_AP_BK;
-constexpr int LDS = BK + 4;           // row stride in doubles: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts
+// Row stride of the staged operands in doubles.  A lane's fragments for TWO consecutive DMMA k-steps are neighbours in
+// memory (lane t takes k = 2t, 2t + 1 of every group of 8: the order of k inside a tile is free as long as both operands agree),
+// so one 16-byte load feeds two DMMAs; rows 64 bytes apart modulo 128 keep the eight lanes of a quarter warp on distinct banks.
+constexpr int LDS = BK + 8;
 constexpr int STAGES = GCB_AP_STAGES;  // BK = 32 double-buffered: one barrier per 8 DMMA k-steps (BK = 16 x 3 stages: per 4)
 constexpr int GEMM_THREADS = 256;
 #ifndef GCB_AP_WARPS
@@ -157,20 +165,42 @@ __device__ __forceinline__ double* peer_row(const PeerOut& po, long i, long ld) 
     return po.blk[o] + (i - po.row0[o]) * ld;
 }
 
+// ---- the GEMM main loop, TMA-fed ----
+// Stage = 16 k of both operands: two boxes of 128 rows x 16 doubles (128 bytes per row, the span of the 128-byte swizzle), 32 KB.
+// Inside a stage the 16-byte chunk c of row r sits at chunk position c ^ (r & 7).  The order of k inside a stage is free as long
+// as both operands use the same one, so lane t of an MMA quad takes the chunks 2t (k = 4t, 4t + 1: DMMAs 0 and 1 of the stage)
+// and 2t + 1 (k = 4t + 2, 4t + 3: DMMAs 2 and 3): one 16-byte load feeds two DMMAs, and the eight lanes of a quarter warp
+// (two rows g, four t) land on eight different chunk positions -- conflict-free.
+constexpr int TK = 16;                                    // k per stage
+constexpr int TSTAGES = 6;
+constexpr int kTmaThreads = AP_THREADS;                   // eight MMA warps; lane 0 of warp 0 also feeds the ring (a ninth warp would
+                                                          // cost the register file a whole allocation unit: 168 registers per thread)
+constexpr size_t kStageBytes = (size_t)(BM + BN) * TK * sizeof(double);   // 32 KB
+constexpr size_t kTmaSmem = TSTAGES * kStageBytes + 1024;  // + room to align the ring to 1024 bytes (swizzle atom)
+static_assert(64 * TLD * sizeof(double) <= TSTAGES * kStageBytes, "the epilogue staging buffer reuses the stage ring");
+
 // One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T and delivers D for the block and for its mirror
 // image to the owners of those rows (PeerOut): the block is staged in shared memory, 64 rows at a time, and leaves as
 // whole-row segments (256-byte stores per warp), the mirror image read transposed from the same staging buffer.
-__global__ void __launch_bounds__(AP_THREADS, 1)
-allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
+__global__ void __launch_bounds__(kTmaThreads, 1)
+allpairs_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
                      const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
-    extern __shared__ __align__(16) double smem[];
-    double* sA = smem;                              // [STAGES][BM][LDS]
-    double* sB = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BN][LDS]
+    using namespace ptx;
+    extern __shared__ unsigned char smem_raw_ap[];
+    __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_ap) + 1023) & ~(uintptr_t)1023);
     const int2 tile = tiles[blockIdx.x];
     const long i0 = (long)tile.x * BM, j0 = (long)tile.y * BN;   // global frame indexes
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;        // (AP_WARPS / 4) x 4 warps -> AP_WR x 32 warp tiles
     const int g = lane >> 2, t = lane & 3;
+    const int nk = (kdim + TK - 1) / TK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], AP_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     double acc[AP_MI][4][2];
 #pragma unroll
@@ -178,59 +208,71 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const int nk = (kdim + BK - 1) / BK;
-    // 128 rows x BK doubles per operand and stage = 64 * BK chunks of 2 doubles (16 B), BK / 4 per thread
-    auto load_stage = [&](int stage, int kt) {
-        const int k0 = kt * BK;
-#pragma unroll
-        for (int r = 0; r < 64 * BK / AP_THREADS; r++) {
-            const int chunk = tid + r * AP_THREADS;
-            const int row = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
-            const bool kin = k0 + kc < kdim;
-            {
-                const long fr = i0 + row;
-                const bool ok = kin && fr < nframes;
-                cp_async16(sA + ((size_t)stage * BM + row) * LDS + kc, Y + (ok ? fr : 0) * ld + (ok ? k0 + kc : 0), ok);
+    {
+        // byte offsets of this lane's chunks inside an operand box: row r = base + 8 mi + g (base a multiple of 8, so r & 7 = g)
+        const uint32_t ring_u32 = smem_u32(ring);
+        const uint32_t a_row = (uint32_t)(wm * AP_WR + g) * (TK * 8u);
+        const uint32_t b_row = (uint32_t)(BM * TK * 8) + (uint32_t)(wn * 32 + g) * (TK * 8u);
+        const uint32_t ch0 = (uint32_t)((2 * t) ^ g) * 16u, ch1 = (uint32_t)((2 * t + 1) ^ g) * 16u;
+        // Not volatile: the scheduler may start a stage's loads early and spread them between the DMMAs.  They cannot move above the
+        // wait for the stage (their address comes from the token taken after it) nor below the release (the DMMAs that consume them
+        // are volatile and stay in front of the arrive).
+        auto lds2 = [](uint32_t addr, double& x, double& y) {
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+        };
+        // producer state (thread 0 only): next k-step to load, its stage and the parity of that stage's previous release
+        const bool producer = tid == 0;
+        int pk = 0, ps = 0;
+        uint32_t pph = 1;
+        auto issue = [&]() {
+            unsigned char* st = ring + (size_t)ps * kStageBytes;
+            mbar_arrive_expect_tx(&full[ps], (uint32_t)kStageBytes);
+            tma_load_2d(st, &tmap, pk * TK, (int)i0, &full[ps]);                                      // rows i0 .. i0+127
+            tma_load_2d(st + (size_t)BM * TK * sizeof(double), &tmap, pk * TK, (int)j0, &full[ps]);      // rows j0 .. j0+127
+            pk++;
+            if (++ps == TSTAGES) { ps = 0; pph ^= 1u; }
+        };
+        if (producer) {
+            prefetch_tensormap(&tmap);
+            while (pk < nk && pk < TSTAGES) issue();     // the ring starts empty
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kt = 0; kt < nk; kt++) {
+            if (producer) {
+                // refill every stage the eight warps have released (non-blocking test); a stage this warp is about to wait for
+                // must have been requested, so that one is waited for
+                while (pk < nk && mbar_test(&empty[ps], pph)) issue();
+                if (pk <= kt) { mbar_wait(&empty[ps], pph); issue(); }
             }
-            {
-                const long fr = j0 + row;
-                const bool ok = kin && fr < nframes;
-                cp_async16(sB + ((size_t)stage * BN + row) * LDS + kc, Y + (ok ? fr : 0) * ld + (ok ? k0 + kc : 0), ok);
+            mbar_wait(&full[s], ph);
+            uint32_t st;
+            asm volatile("mov.u32 %0, %1;" : "=r"(st) : "r"(ring_u32 + (uint32_t)s * (uint32_t)kStageBytes) : "memory");
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t ch = h ? ch1 : ch0;
+                double ax[AP_MI], ay[AP_MI], bx[4], by[4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) lds2(st + b_row + (uint32_t)ni * (8u * TK * 8u) + ch, bx[ni], by[ni]);
+#pragma unroll
+                for (int mi = 0; mi < AP_MI; mi++) lds2(st + a_row + (uint32_t)mi * (8u * TK * 8u) + ch, ax[mi], ay[mi]);
+#pragma unroll
+                for (int mi = 0; mi < AP_MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ax[mi], bx[ni]);
+#pragma unroll
+                for (int mi = 0; mi < AP_MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ay[mi], by[ni]);
             }
-        }
-    };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nk) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            const int nxt = kt + STAGES - 1;
-            if (nxt < nk) load_stage(nxt % STAGES, nxt);
-            cp_async_commit();
-        }
-        const double* a = sA + ((size_t)(kt % STAGES) * BM + wm * AP_WR) * LDS;
-        const double* b = sB + ((size_t)(kt % STAGES) * BN + wn * 32) * LDS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[AP_MI], bf[4];
-#pragma unroll
-            for (int mi = 0; mi < AP_MI; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) bf[ni] = b[(ni * 8 + g) * LDS + kk + t];
-#pragma unroll
-            for (int mi = 0; mi < AP_MI; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with the stage
+            if (++s == TSTAGES) { s = 0; ph ^= 1u; }
         }
     }
-    cp_async_wait<0>();
-    __syncthreads();   // every warp is done with the pipeline buffers: reuse them as the staging buffer
+    __syncthreads();   // every warp is done with the ring (all TMA writes were waited for): reuse it as the staging buffer
     // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
-    double* sT = smem;   // [64][TLD]
+    double* sT = reinterpret_cast<double*>(ring);   // [64][TLD]
     for (int half = 0; half < 2; half++) {
         if ((wm * AP_WR) / 64 == half) {
             const int rbase = wm * AP_WR - half * 64;   // first staged row of this warp
@@ -262,26 +304,28 @@ allpairs_dmma_kernel(const double* __restrict__ Y, long ld, int kdim, long nfram
         }
         __syncthreads();
         const long ib = i0 + half * 64;   // first row staged
-        for (int r = warp; r < 64; r += AP_WARPS) {          // rows of the block: 128 contiguous doubles each
-            const long i = ib + r;
-            if (i >= nframes) break;
-            double* dst = peer_row(po, i, ldd);
-            if (!dst) continue;
-            dst += j0;
-#pragma unroll
-            for (int c = lane; c < BN; c += 32)
-                if (j0 + c < nframes) dst[c] = sT[r * TLD + c];
-        }
-        if (tile.x != tile.y) {                       // mirror image: rows j of the matrix, 64 contiguous doubles each
-            for (int c = warp; c < BN; c += AP_WARPS) {
-                const long j = j0 + c;
-                if (j >= nframes) break;
-                double* dst = peer_row(po, j, ldd);
+        {
+            for (int r = warp; r < 64; r += AP_WARPS) {          // rows of the block: 128 contiguous doubles each
+                const long i = ib + r;
+                if (i >= nframes) break;
+                double* dst = peer_row(po, i, ldd);
                 if (!dst) continue;
-                dst += ib;
+                dst += j0;
 #pragma unroll
-                for (int r = lane; r < 64; r += 32)
-                    if (ib + r < nframes) dst[r] = sT[r * TLD + c];
+                for (int c = lane; c < BN; c += 32)
+                    if (j0 + c < nframes) dst[c] = sT[r * TLD + c];
+            }
+            if (tile.x != tile.y) {                       // mirror image: rows j of the matrix, 64 contiguous doubles each
+                for (int c = warp; c < BN; c += AP_WARPS) {
+                    const long j = j0 + c;
+                    if (j >= nframes) break;
+                    double* dst = peer_row(po, j, ldd);
+                    if (!dst) continue;
+                    dst += ib;
+#pragma unroll
+                    for (int r = lane; r < 64; r += 32)
+                        if (ib + r < nframes) dst[r] = sT[r * TLD + c];
+                }
             }
         }
         __syncthreads();
@@ -321,6 +365,7 @@ __global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restric
 // rotations of ||Y_i R - Y_j||^2 is G_i + G_j - 2 tr(R^T H_ij) with R from the same 3x3 solve as everywhere else
 // (kabsch3.cuh; geometric.go:154-190), evaluated per pair in the epilogue.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int FLDS = BK + 4;        // row stride of the staged operands: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts of 8-byte loads
 constexpr int FT = 32;              // frames per tile side
 constexpr int FM = 3 * FT;          // 96 rows
 constexpr int FLDC = FM + 1;        // padded row of the staged C tile
@@ -373,8 +418,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
                          const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
     extern __shared__ __align__(16) double smem[];
-    double* sA = smem;                               // [STAGES][FM][LDS]
-    double* sB = smem + (size_t)STAGES * FM * LDS;    // [STAGES][FM][LDS]
+    double* sA = smem;                               // [STAGES][FM][FLDS]
+    double* sB = smem + (size_t)STAGES * FM * FLDS;    // [STAGES][FM][FLDS]
     const int2 tile = tiles[blockIdx.x];
     const long fi0 = (long)tile.x * FT, fj0 = (long)tile.y * FT;   // first frames of the tile
     const long nrow_total = 3 * nframes;
@@ -397,12 +442,12 @@ allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, c
             {
                 const long gr = 3 * fi0 + row;
                 const bool ok = kin && gr < nrow_total;
-                cp_async16(sA + ((size_t)stage * FM + row) * LDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
+                cp_async16(sA + ((size_t)stage * FM + row) * FLDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
             }
             {
                 const long gr = 3 * fj0 + row;
                 const bool ok = kin && gr < nrow_total;
-                cp_async16(sB + ((size_t)stage * FM + row) * LDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
+                cp_async16(sB + ((size_t)stage * FM + row) * FLDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
             }
         }
     };
@@ -419,15 +464,15 @@ allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, c
             if (nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* a = sA + ((size_t)(kt % STAGES) * FM + wm * 48) * LDS;
-        const double* b = sB + ((size_t)(kt % STAGES) * FM + wn * 24) * LDS;
+        const double* a = sA + ((size_t)(kt % STAGES) * FM + wm * 48) * FLDS;
+        const double* b = sB + ((size_t)(kt % STAGES) * FM + wn * 24) * FLDS;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double af[6], bf[3];
 #pragma unroll
-            for (int mi = 0; mi < 6; mi++) af[mi] = a[(mi * 8 + g) * LDS + kk + t];
+            for (int mi = 0; mi < 6; mi++) af[mi] = a[(mi * 8 + g) * FLDS + kk + t];
 #pragma unroll
-            for (int ni = 0; ni < 3; ni++) bf[ni] = b[(ni * 8 + g) * LDS + kk + t];
+            for (int ni = 0; ni < 3; ni++) bf[ni] = b[(ni * 8 + g) * FLDS + kk + t];
 #pragma unroll
             for (int mi = 0; mi < 6; mi++)
 #pragma unroll
@@ -539,6 +584,33 @@ __global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __res
 //                through its mirror image, is computed here.
 //   deal_n  > 1: the tiles on or above the diagonal are dealt round-robin to deal_n ranks (this one is deal_rank) and
 //                each finished tile is stored into the row blocks of its owners, local or peer.
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links the runtime only)
+static int make_tensor_map(CUtensorMap* out, const double* base, unsigned long long cols, unsigned long long rows, unsigned long long pitch_bytes) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return GCB_ERR_CUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for %llu x %llu doubles, pitch %llu", (int)r, rows, cols, pitch_bytes);
+        return GCB_ERR_CUDA;
+    }
+    return GCB_OK;
+}
+
 static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_idx, int nidx, const PeerOut& po, int deal_rank,
                            int deal_n, float* gemm_ms, long* redone, bool fit) {
     cudaStream_t s = t->stream;
@@ -553,7 +625,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     std::vector<int2> tiles;
     const int tile_frames = fit ? FT : BM;
     const int nt = (int)((nframes + tile_frames - 1) / tile_frames);
-    const size_t smem = fit ? sizeof(double) * (size_t)STAGES * 2 * FM * LDS : sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
+    const size_t smem = fit ? sizeof(double) * (size_t)STAGES * 2 * FM * FLDS : sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 #define AP_TRY(call)                                                                              \
     do {                                                                                          \
@@ -649,10 +721,15 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
         redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
         GCB_LAUNCHED();
     } else {
+        // tensor map of Y: nframes rows of kdim doubles (row pitch ld), boxes of 128 rows x 16 doubles, 128-byte swizzle,
+        // zeros beyond either extent (the tails of k and of the frames need no predicates in the kernel)
+        CUtensorMap tmap;
+        rc = make_tensor_map(&tmap, Y, (unsigned long long)kdim, (unsigned long long)nframes, (unsigned long long)ld * sizeof(double));
+        if (rc) goto done;
         AP_TRY(opt_in_smem(allpairs_dmma_kernel, t->dev));
         AP_TRY(cudaEventRecord(e0, s));
-        allpairs_dmma_kernel<<<(unsigned)tiles.size(), AP_THREADS, smem, s>>>(Y, ld, kdim, nframes, norms, 1.0 / (double)natoms_used,
-                                                                              d_tiles, po, nframes, 1e-7, redo);
+        allpairs_dmma_kernel<<<(unsigned)tiles.size(), kTmaThreads, kTmaSmem, s>>>(tmap, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                                   d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
         AP_TRY(cudaEventRecord(e1, s));
         redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
