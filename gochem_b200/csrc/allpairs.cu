@@ -661,6 +661,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
         d_tiles = (int2*)(w + oTiles);
     }
     AP_TRY(cudaMemsetAsync(redo.count, 0, sizeof(unsigned int), s));
+    if ((rc = deps_before_compute(t, first, nframes)) != GCB_OK) goto done;
     {
         const double* src = t->d_frames + first * 3L * t->np;
         long ldx = 3L * t->np;

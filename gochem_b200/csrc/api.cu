@@ -90,6 +90,64 @@ static int check_window(const gcb_traj* t, long first, long nframes, bool within
     return GCB_OK;
 }
 
+namespace gcb {
+
+static inline bool ranges_meet(long a0, long a1, long b0, long b1) { return a0 < b1 && b0 < a1; }
+
+int deps_before_compute(gcb_traj* t, long first, long nframes) {
+    for (int s = 0; s < 2; s++)
+        if (t->up_pending[s] && ranges_meet(first, first + nframes, t->up_lo[s], t->up_hi[s])) {
+            GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[s], 0));
+            t->up_pending[s] = false;
+        }
+    return GCB_OK;
+}
+
+int deps_after_compute(gcb_traj* t, long first, long nframes) {
+    if (nframes <= 0) return GCB_OK;
+    bool covered = false;
+    for (int s = 0; s < 2; s++)
+        if (t->up_hi[s] > t->up_lo[s] && ranges_meet(first, first + nframes, t->up_lo[s], t->up_hi[s])) {
+            GCB_CUDA(cudaEventRecord(t->use_done[s], t->stream));
+            t->use_valid[s] = true;
+            covered = covered || (first >= t->up_lo[s] && first + nframes <= t->up_hi[s]);
+        }
+    if (!covered) {   // frames outside the slots' windows (a resident trajectory): one event for their union
+        GCB_CUDA(cudaEventRecord(t->any_done, t->stream));
+        if (t->any_hi <= t->any_lo) { t->any_lo = first; t->any_hi = first + nframes; }
+        else { if (first < t->any_lo) t->any_lo = first; if (first + nframes > t->any_hi) t->any_hi = first + nframes; }
+    }
+    return GCB_OK;
+}
+
+// an asynchronous upload into [first, first+n) through `slot`: its copy stream waits for the kernels that use those frames (and,
+// through the slot's own stream order, for the slot's previous copy); a range the compute stream never waited for is closed first
+static int deps_before_upload(gcb_traj* t, long first, long nframes, int slot) {
+    cudaStream_t cs = t->copy_stream[slot];
+    if (t->up_pending[slot]) {   // the previous upload through this slot was never consumed: order it before later kernels now
+        GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));
+        t->up_pending[slot] = false;
+    }
+    for (int s = 0; s < 2; s++)
+        if (t->use_valid[s] && ranges_meet(first, first + nframes, t->up_lo[s], t->up_hi[s]))
+            GCB_CUDA(cudaStreamWaitEvent(cs, t->use_done[s], 0));
+    if (t->any_hi > t->any_lo && ranges_meet(first, first + nframes, t->any_lo, t->any_hi)) GCB_CUDA(cudaStreamWaitEvent(cs, t->any_done, 0));
+    // the other slot's upload may still be writing frames of this range (overlapping windows): keep the copies in order
+    const int o = slot ^ 1;
+    if (t->up_hi[o] > t->up_lo[o] && ranges_meet(first, first + nframes, t->up_lo[o], t->up_hi[o]))
+        GCB_CUDA(cudaStreamWaitEvent(cs, t->copy_done[o], 0));
+    return GCB_OK;
+}
+
+static void deps_after_upload(gcb_traj* t, long first, long nframes, int slot) {
+    t->up_lo[slot] = first;
+    t->up_hi[slot] = first + nframes;
+    t->up_pending[slot] = true;
+    t->use_valid[slot] = false;   // the new range has no users yet
+}
+
+}  // namespace gcb
+
 extern "C" {
 
 int gcb_version(void) { return 100; }
@@ -263,6 +321,8 @@ int gcb_traj_destroy(gcb_traj* tb) {
     }
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
+    for (int s = 0; s < 2; s++) if (t->use_done[s]) cudaEventDestroy(t->use_done[s]);
+    if (t->any_done) cudaEventDestroy(t->any_done);
     if (t->stream) cudaStreamDestroy(t->stream);
     cudaFree(t->d_frames); cudaFree(t->d_refc); cudaFree(t->d_weight); cudaFree(t->d_refpairs); cudaFree(t->d_idx);
     cudaFree(t->d_rmsd); cudaFree(t->d_rot); cudaFree(t->d_t1); cudaFree(t->d_t2); cudaFree(t->d_status); cudaFree(t->d_flag);
@@ -317,6 +377,8 @@ int gcb_traj_create(int dev, int natoms, long cap_frames, gcb_traj** out) {
         }
         TRY(cudaEventCreate(&t->ev0));
         TRY(cudaEventCreate(&t->ev1));
+        for (int s = 0; s < 2; s++) TRY(cudaEventCreateWithFlags(&t->use_done[s], cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&t->any_done, cudaEventDisableTiming));
         TRY(cudaMalloc(&t->d_frames, frame_bytes * (size_t)cap_frames));
         t->stage_bytes = kStageBytes;
         if (t->stage_bytes < frame_bytes) t->stage_bytes = frame_bytes;
@@ -420,6 +482,9 @@ int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int
     if (!host && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
     if (layout < GCB_F64_AOS || layout > GCB_I32_AOS) { set_error("unknown host layout %d", layout); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaStreamSynchronize(t->stream));   // synchronous call: queued kernels may still read the frames being replaced
+    t->use_valid[0] = t->use_valid[1] = false;
+    t->any_lo = t->any_hi = 0;
     const size_t fb = host_frame_bytes(t, layout);
     if (nframes > 0 && (size_t)nframes * fb >= (1u << 20) && is_pageable(host)) {
         rc = ensure_bounce(t);
@@ -438,6 +503,7 @@ int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int
         }
         GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
         GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+        t->up_pending[0] = t->up_pending[1] = false;   // everything uploaded so far is resident
         if (first + nframes > t->nframes) t->nframes = first + nframes;
         return GCB_OK;
     }
@@ -452,6 +518,7 @@ int gcb_traj_upload(gcb_traj* t, long first, const void* host, long nframes, int
     }
     GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
     GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+    t->up_pending[0] = t->up_pending[1] = false;   // everything uploaded so far is resident
     if (first + nframes > t->nframes) t->nframes = first + nframes;
     return GCB_OK;
 }
@@ -465,14 +532,13 @@ int gcb_traj_upload_async(gcb_traj* t, long first, const void* pinned, long nfra
     if (bytes > t->stage_bytes) { set_error("async upload of %zu bytes exceeds the %zu-byte staging slot", bytes, t->stage_bytes); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     cudaStream_t s = t->copy_stream[slot];
-    // do not overwrite frame slots a queued kernel still reads
-    GCB_CUDA(cudaEventRecord(t->ev1, t->stream));
-    GCB_CUDA(cudaStreamWaitEvent(s, t->ev1, 0));
+    rc = deps_before_upload(t, first, nframes, slot);   // do not overwrite frames a queued kernel still reads
+    if (rc) return rc;
     GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], pinned, bytes, cudaMemcpyHostToDevice, s));
     rc = launch_upload_convert(t, s, t->d_stage[slot], first, nframes, layout, scale);
     if (rc) return rc;
     GCB_CUDA(cudaEventRecord(t->copy_done[slot], s));
-    GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));  // later kernels see the frames
+    deps_after_upload(t, first, nframes, slot);          // kernels that read these frames wait for copy_done[slot], others do not
     if (first + nframes > t->nframes) t->nframes = first + nframes;
     return GCB_OK;
 }
@@ -493,13 +559,13 @@ int gcb_traj_upload_records_async(gcb_traj* t, long first, const void* pinned, l
     if (bytes > t->stage_bytes) { set_error("async upload of %zu bytes exceeds the %zu-byte staging slot", bytes, t->stage_bytes); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
     cudaStream_t s = t->copy_stream[slot];
-    GCB_CUDA(cudaEventRecord(t->ev1, t->stream));   // do not overwrite frame slots a queued kernel still reads
-    GCB_CUDA(cudaStreamWaitEvent(s, t->ev1, 0));
+    rc = deps_before_upload(t, first, nframes, slot);   // do not overwrite frames a queued kernel still reads
+    if (rc) return rc;
     GCB_CUDA(cudaMemcpyAsync(t->d_stage[slot], pinned, bytes, cudaMemcpyHostToDevice, s));
     rc = launch_upload_records(t, s, t->d_stage[slot], first, nframes, record_bytes, off_x, off_y, off_z, scale);
     if (rc) return rc;
     GCB_CUDA(cudaEventRecord(t->copy_done[slot], s));
-    GCB_CUDA(cudaStreamWaitEvent(t->stream, t->copy_done[slot], 0));
+    deps_after_upload(t, first, nframes, slot);
     if (first + nframes > t->nframes) t->nframes = first + nframes;
     return GCB_OK;
 }
@@ -516,14 +582,15 @@ int gcb_traj_download(gcb_traj* t, long first, long nframes, double* host_aos) {
     if (rc) return rc;
     if (!host_aos && nframes) { set_error("NULL host buffer"); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));   // the staging slots may still feed an upload; uploads are resident after this
+    GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+    t->up_pending[0] = t->up_pending[1] = false;
     const size_t fb = sizeof(double) * 3 * (size_t)t->natoms;
     if (nframes > 0 && (size_t)nframes * fb >= (1u << 20) && is_pageable(host_aos)) {
         // chunk c: layout kernel -> device staging slot -> pinned buffer (DMA); the memcpy of chunk c - 1 into the caller's
         // memory runs on the host meanwhile
         rc = ensure_bounce(t);
         if (rc) return rc;
-        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));   // the staging slots may still feed an upload
-        GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
         const long per = (long)(t->bounce_bytes / fb);
         long prev_done = -1, prev_n = 0;
         int slot = 0;
@@ -749,8 +816,22 @@ bool use_cluster(const gcb_traj_ext* t, bool heavy) {
 int launch_super_split(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
                        const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows);
 
+int launch_super_impl(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                      const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows);
+
+// every fused pass goes through here: it waits for the uploads of the frames it touches (and for no others) and leaves a mark
+// for later uploads into the same frames
 int launch_super(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
                  const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
+    int rc = deps_before_compute(t, first, nframes);
+    if (rc) return rc;
+    rc = launch_super_impl(t, first, nframes, ref_aos, natoms_ref, idx_test, idx_ref, nidx, write_back, want_dev, dev_rows);
+    if (rc) return rc;
+    return deps_after_compute(t, first, nframes);
+}
+
+int launch_super_impl(gcb_traj_ext* t, long first, long nframes, const double* ref_aos, int natoms_ref, const int* idx_test,
+                      const int* idx_ref, int nidx, int write_back, bool want_dev, int* dev_rows) {
     // Frames beyond the cluster kernel's capacity whose every atom must be visited a second time (write-back, per-atom sums):
     // the fit and the elementwise sweep are separate launches (transform.cu) instead of the generic kernel's re-read.
     const int variant = t->tune.variant;
@@ -899,13 +980,15 @@ int gcb_rmsd(gcb_traj* tb, long first, long nframes, const double* ref_aos, int 
     rc = prepare_template(t, ref_aos, natoms_ref, idx_test, idx_ref, nidx, false, &mode, prefer_gather);
     if (rc) return rc;
     if (nframes == 0) return GCB_OK;
+    rc = deps_before_compute(t, first, nframes);
+    if (rc) return rc;
     const double* frames = t->d_frames + first * 3L * t->np;
     if (mode == MODE_GATHER) rc = launch_rmsd_nofit_gather(t, frames, nframes, t->d_refpairs, t->d_idx, nidx, t->d_rmsd + first);
     else rc = launch_rmsd_nofit(t, frames, nframes, t->d_refc, mode == MODE_WEIGHTED ? t->d_weight : nullptr, t->cache.n_fit, t->d_rmsd + first);
     if (rc) return rc;
     if (rmsd) GCB_CUDA(cudaMemcpyAsync(rmsd, t->d_rmsd + first, sizeof(double) * (size_t)nframes, cudaMemcpyDeviceToHost, t->stream));
     GCB_CUDA(cudaStreamSynchronize(t->stream));
-    return GCB_OK;
+    return deps_after_compute(t, first, nframes);
 }
 
 int gcb_peratom_dist(gcb_traj* tb, long frame, const double* ref_aos, int natoms_ref, const int* idx_test,
@@ -947,6 +1030,8 @@ int gcb_peratom_dist(gcb_traj* tb, long frame, const double* ref_aos, int natoms
     double* d_out = t->d_pdist;
     cudaMemcpyAsync(t->d_refpairs, pairs.data(), sizeof(double) * pairs.size(), cudaMemcpyHostToDevice, t->stream);
     cudaMemcpyAsync(t->d_idx, it.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, t->stream);
+    rc = deps_before_compute(t, frame, 1);
+    if (rc) return rc;
     rc = launch_peratom_dist(t, t->d_frames + frame * 3L * t->np, t->d_refpairs, t->d_idx, n, d_out);
     if (rc == GCB_OK) cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, t->stream);
     cudaError_t e = cudaStreamSynchronize(t->stream);
@@ -977,6 +1062,9 @@ int gcb_sync(gcb_traj* t) {
     GCB_CUDA(cudaStreamSynchronize(t->stream));
     GCB_CUDA(cudaStreamSynchronize(t->copy_stream[0]));
     GCB_CUDA(cudaStreamSynchronize(t->copy_stream[1]));
+    t->up_pending[0] = t->up_pending[1] = false;
+    t->use_valid[0] = t->use_valid[1] = false;
+    t->any_lo = t->any_hi = 0;
     return GCB_OK;
 }
 

@@ -302,6 +302,7 @@ int gcb_traj_allgather(gcb_traj* t, gcb_comm* c, const long* counts) {
     for (int r = 0; r < c->nranks; r++) { if (counts[r] < 0) { set_error("negative frame count"); return GCB_ERR_ARG; } total += counts[r]; }
     if (total > t->cap) { set_error("all-gather of %ld frames into a trajectory of capacity %ld", total, t->cap); return GCB_ERR_ARG; }
     GCB_CUDA(cudaSetDevice(t->dev));
+    { int rc = deps_before_compute(t, 0, total); if (rc) return rc; }
     if (c->nranks > 1) {
         NcclApi* api = nccl();
         if (!api) return GCB_ERR_CUDA;

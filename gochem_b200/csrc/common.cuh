@@ -134,6 +134,15 @@ struct gcb_traj {
     void* h_bounce[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    // Ordering between the two copy streams and the compute stream, by frame range (api.cu: deps_*): a kernel waits only for the
+    // uploads whose frames it reads, an upload only for the kernels that still use the frames it overwrites -- so the copy of
+    // window k + 1 runs under the kernels of window k.
+    long up_lo[2] = {0, 0}, up_hi[2] = {0, 0};     // frames written by the last asynchronous upload through each slot
+    bool up_pending[2] = {false, false};           // the compute stream has not been made to wait for copy_done[slot] yet
+    cudaEvent_t use_done[2] = {nullptr, nullptr};  // recorded on the compute stream after the last call that touched the slot's frames
+    bool use_valid[2] = {false, false};
+    cudaEvent_t any_done = nullptr;                // ... after calls on frames outside both slots' ranges: [any_lo, any_hi)
+    long any_lo = 0, any_hi = 0;
     // per-handle settings and scratch (nothing of a call's state is process-global)
     gcb::Tuning tune;
     int last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // shape of this handle's last cluster-kernel launch
@@ -164,6 +173,9 @@ struct gcb_comm {
 };
 
 namespace gcb {
+// frame-range dependencies between uploads and kernels (api.cu)
+int deps_before_compute(gcb_traj* t, long first, long nframes);   // the compute stream waits for pending uploads into [first, first+n)
+int deps_after_compute(gcb_traj* t, long first, long nframes);    // remembers that queued work uses [first, first+n)
 int comm_barrier(gcb_comm* c, cudaStream_t s);
 int comm_peer_blocks(gcb_comm* c, size_t bytes, double** blk);
 // kernels / launchers implemented across the .cu files

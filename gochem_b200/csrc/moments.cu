@@ -36,7 +36,7 @@ struct MomShared {
 // chunk: atoms per stage (multiple of 256 unless the whole padded frame is one chunk); nchunks = ceil(np / chunk).
 __global__ void __launch_bounds__(kMomThreads, 1) moments_stream_kernel(const double* __restrict__ frames, long stride, int np,
                                                                       long nframes, const double* __restrict__ mass, double msum,
-                                                                      int chunk, int nchunks, int stages,
+                                                                      int chunk, int nchunks, int stages, int origin_atom,
                                                                       double* __restrict__ center, double* __restrict__ moment) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MomShared& sh = *reinterpret_cast<MomShared*>(smem_raw);
@@ -84,6 +84,12 @@ __global__ void __launch_bounds__(kMomThreads, 1) moments_stream_kernel(const do
         double a[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) a[k] = 0.0;
+        // The second moments are taken about a point INSIDE the selection (its first atom), not about the coordinate origin: the
+        // reference centres before it multiplies (geometric.go:719-731), and S2 - M c c^T from raw coordinates would lose
+        // (|c| / extent)^2 * eps for a small selection far from the origin (a ligand in a large box).  The shift is undone
+        // exactly below.
+        const double* fr0 = frames + (blockIdx.x + j * (long)gridDim.x) * stride;
+        const double ox = __ldg(fr0 + origin_atom), oy = __ldg(fr0 + np + origin_atom), oz = __ldg(fr0 + 2L * np + origin_atom);
         for (int c = 0; c < nchunks; c++) {
             const int len = (np - c * chunk < chunk) ? (np - c * chunk) : chunk;
             mbar_wait(&sh.full[s], ph);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(kMomThreads, 1) moments_stream_kernel(const do
             const double* M = Z + chunk;
 #pragma unroll 4
             for (int i = tid; i < len; i += kMomConsumers) {
-                const double x = X[i], y = Y[i], z = Z[i], m = M[i];
+                const double x = X[i] - ox, y = Y[i] - oy, z = Z[i] - oz, m = M[i];
                 const double mx = m * x, my = m * y, mz = m * z;
                 a[0] += mx; a[1] += my; a[2] += mz;
                 a[3] = fma(mx, x, a[3]); a[4] = fma(mx, y, a[4]); a[5] = fma(mx, z, a[5]);
@@ -131,8 +137,8 @@ __global__ void __launch_bounds__(kMomThreads, 1) moments_stream_kernel(const do
             if (lane == 0) {
                 const long f = blockIdx.x + j * (long)gridDim.x;
                 const double inv = 1.0 / msum;
-                const double cx = sum[0] * inv, cy = sum[1] * inv, cz = sum[2] * inv;
-                if (center) { center[3 * f] = cx; center[3 * f + 1] = cy; center[3 * f + 2] = cz; }
+                const double cx = sum[0] * inv, cy = sum[1] * inv, cz = sum[2] * inv;   // centre relative to the frame's origin atom
+                if (center) { center[3 * f] = ox + cx; center[3 * f + 1] = oy + cy; center[3 * f + 2] = oz + cz; }
                 if (moment) {
                     double* m = moment + 9 * f;
                     const double xx = sum[3] - msum * cx * cx, xy = sum[4] - msum * cx * cy, xz = sum[5] - msum * cx * cz;
@@ -178,6 +184,8 @@ extern "C" int gcb_moments_async(gcb_traj* t, long first, long nframes, const do
     } else {
         for (int i = 0; i < t->natoms; i++) w[(size_t)i] = mass ? mass[i] : 1.0;
     }
+    int origin_atom = 0;
+    for (int i = t->natoms - 1; i >= 0; i--) if (w[(size_t)i] != 0.0) origin_atom = i;   // first atom that counts
     for (int i = 0; i < t->natoms; i++) msum += w[(size_t)i];   // mat.Sum(mass), geometric.go:629
     if (!(msum > 0.0)) { set_error("goChem: the masses add up to %g", msum); return GCB_ERR_SHAPE; }
     int rc = ensure_moment_buffers(t, nframes);
@@ -194,14 +202,16 @@ extern "C" int gcb_moments_async(gcb_traj* t, long first, long nframes, const do
     if (stages < 2) { set_error("moments: no stage plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     const size_t smem = fixed + sizeof(double) * 4 * (size_t)chunk * stages;
     GCB_CUDA(opt_in_smem(moments_stream_kernel, t->dev));
+    rc = deps_before_compute(t, first, nframes);
+    if (rc) return rc;
     long grid = t->sm_count;
     if (grid > nframes) grid = nframes;
     moments_stream_kernel<<<(unsigned)grid, kMomThreads, smem, t->stream>>>(t->d_frames + first * 3L * t->np, 3L * t->np, t->np, nframes,
-                                                                            t->d_mom_w, msum, chunk, nchunks, stages, t->d_mom_c, t->d_mom_m);
+                                                                            t->d_mom_w, msum, chunk, nchunks, stages, origin_atom, t->d_mom_c, t->d_mom_m);
     GCB_LAUNCHED();
     GCB_CUDA(cudaGetLastError());
     t->mom_frames = nframes;
-    return GCB_OK;
+    return deps_after_compute(t, first, nframes);
 }
 
 extern "C" int gcb_moments_fetch(gcb_traj* t, long nframes, double* center, double* moment) {

@@ -358,6 +358,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
     RDF_TRY(cudaMemcpyAsync(d_ref, refidx, sizeof(int) * (size_t)nref, cudaMemcpyHostToDevice, t->stream));
     RDF_TRY(cudaMemsetAsync(d_cdf, 0, sizeof(unsigned long long) * (size_t)totalsteps, t->stream));
     if (used > 0 && !runs.empty()) {
+        if ((rc = deps_before_compute(t, first, used)) != GCB_OK) goto done;
         RdfParams p;
         p.frames = t->d_frames + first * 3L * t->np;
         p.stride = 3L * t->np;
@@ -386,6 +387,7 @@ extern "C" int gcb_rdf_cdf_sum(gcb_traj* t, long first, long nframes, const int*
         if (grid > used) grid = used;
         rdf_kernel<<<(unsigned)grid, RT, smem, t->stream>>>(p);
         GCB_LAUNCHED();
+        if ((rc = deps_after_compute(t, first, used)) != GCB_OK) goto done;
     }
     RDF_TRY(cudaMemcpyAsync(h_cdf.data(), d_cdf, sizeof(unsigned long long) * (size_t)totalsteps, cudaMemcpyDeviceToHost, t->stream));
     RDF_TRY(cudaStreamSynchronize(t->stream));

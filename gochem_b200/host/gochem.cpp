@@ -554,6 +554,12 @@ long DCDObj::RecordsAvailable() {
     const long pos = ftell(f_);
     struct stat st;
     if (pos < 0 || fstat(fileno(f_), &st) != 0) return -1;
+    // The bulk feed assumes every frame is laid out like the first.  The reference's nextRaw (dcd.go:359-378, 415-431) also reads
+    // files in which some frames lack the unit-cell block, and a last frame without the fourth-dimension block; those go
+    // through the frame-by-frame reader: the feed is offered only when the rest of the file is a whole number of records and
+    // no fourth-dimension block is flagged.
+    if (charmm_ && fourdim_) return -1;
+    if (((long)st.st_size - pos) % rec_bytes_ != 0) return -1;
     const long n = ((long)st.st_size - pos) / rec_bytes_;
     return n < 0 ? 0 : n;
 }
@@ -1208,7 +1214,7 @@ Error streamSelected(chem::ConcTraj& traj, int natoms, const Options& o,
     const long begin = o.begin_ / chunksize, skip = o.skip_ / chunksize;
     const bool raw = traj.HasRawFeed();
     // bulk path: whole runs of frames read() straight into the pinned buffer as they sit in the file (no begin / skip gaps)
-    bool records = traj.HasRecordFeed() && begin == 0 && skip == 0;
+    bool records = traj.HasRecordFeed() && begin == 0 && skip == 0 && traj.RecordsAvailable() >= 0;   // uniform records only
     long rec_bytes = 0, rec_off[3] = {0, 0, 0};
     double rec_scale = 1.0;
     if (records) {

@@ -556,6 +556,25 @@ def test_center_of_mass_and_moment_tensor_batched():
     assert np.abs(hc - oc).max() < 1e-10 and np.abs(hm - om).max() < 1e-10 * np.abs(om).max()
 
 
+def test_moment_tensor_of_a_small_selection_far_from_the_origin():
+    """A ligand of 30 atoms (1 A across) at 400 A from the coordinate origin, in a frame of 6000 atoms: the reference centres the
+    coordinates before it forms the tensor (geometric.go:719-731), so its result does not lose (|c| / extent)^2 * eps; the kernel
+    takes its second moments about the first selected atom for the same reason."""
+    rng = np.random.default_rng(4)
+    natoms, nframes = 6000, 9
+    frames = rng.normal(0, 30, (nframes, natoms, 3))
+    lig = np.arange(5100, 5130)
+    frames[:, lig, :] = np.array([400.0, -390.0, 410.0]) + rng.normal(0, 0.5, (nframes, lig.size, 3))
+    mass = rng.uniform(1.0, 16.0, natoms)
+    t = device_traj(frames)
+    cen, mom = t.moments(mass, lig)
+    t.close()
+    for f in range(nframes):
+        oc, om = oracle.center_and_moment(frames[f][lig], mass[lig])
+        assert np.abs(cen[f] - oc).max() < 1e-10
+        assert np.abs(mom[f] - om).max() < 1e-12 * np.abs(om).max()     # S2 - M c c^T from raw coordinates is good to 1e-10 here
+
+
 @pytest.mark.parametrize("natoms,nframes", [(1, 3), (17, 5), (2048, 300), (2049, 7), (5003, 333), (10000, 150)])
 def test_moments_stream_kernel_chunked_frames(natoms, nframes):
     """Frames of one chunk, several chunks with a ragged last chunk, more frames than CTAs: every frame checked."""
