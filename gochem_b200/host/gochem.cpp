@@ -906,14 +906,34 @@ std::vector<int> res2atoms(const chem::Atomer& mol, const std::vector<std::strin
 std::vector<MolIDandChain> iDs2MolIDandChains(const chem::Atomer& mol, const std::vector<int>& indexes) {
     // first occurrences in list order, as the reference's search over the growing result (lovo.go:540-551)
     std::vector<MolIDandChain> ret;
-    std::unordered_map<std::string, int> chain_id;            // chains are few: intern them, then hash (molid, chain id)
+    if (indexes.empty()) return ret;
+    // chains are few: a short list searched linearly (the previous atom's chain first); "seen" is a bitmap over
+    // (chain, MolID - min MolID) when that is small, a hash set otherwise
+    std::vector<const std::string*> chains;
+    int lo = mol.Atom(indexes[0]).MolID, hi = lo;
+    for (int v : indexes) { const int m = mol.Atom(v).MolID; lo = std::min(lo, m); hi = std::max(hi, m); }
+    const uint64_t span = (uint64_t)((long)hi - lo + 1);
+    std::vector<char> bits;
     std::unordered_set<uint64_t> seen;
-    seen.reserve(indexes.size() * 2);
+    ret.reserve(indexes.size());
+    int last_chain = -1;
     for (int v : indexes) {
         const chem::Atom& at = mol.Atom(v);
-        auto c = chain_id.emplace(at.Chain, (int)chain_id.size());
-        const uint64_t key = ((uint64_t)(uint32_t)at.MolID << 32) | (uint32_t)c.first->second;
-        if (seen.insert(key).second) ret.push_back(MolIDandChain{at.MolID, at.Chain});
+        int c = -1;
+        if (last_chain >= 0 && *chains[(size_t)last_chain] == at.Chain) c = last_chain;
+        for (size_t q = 0; c < 0 && q < chains.size(); q++) if (*chains[q] == at.Chain) c = (int)q;
+        if (c < 0) { chains.push_back(&at.Chain); c = (int)chains.size() - 1; }
+        last_chain = c;
+        const uint64_t key = (uint64_t)c * span + (uint64_t)((long)at.MolID - lo);
+        bool fresh;
+        if ((uint64_t)(c + 1) * span <= (1u << 24)) {
+            if (bits.size() < (size_t)((uint64_t)(c + 1) * span)) bits.resize((size_t)((uint64_t)(c + 1) * span), 0);
+            fresh = !bits[(size_t)key];
+            bits[(size_t)key] = 1;
+        } else {
+            fresh = seen.insert(((uint64_t)c << 40) ^ (uint64_t)((long)at.MolID - lo)).second;
+        }
+        if (fresh) ret.push_back(MolIDandChain{at.MolID, at.Chain});
     }
     return ret;
 }
@@ -986,11 +1006,20 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
 
 void LovoState::Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const {
     // RMSD.SortBy("molid") (:254): stable by candidate atom index
-    std::vector<std::pair<int, double>> byid(ids_.size());
-    for (size_t k = 0; k < byid.size(); k++) byid[k] = {ids_[k], vals_[k]};
-    std::stable_sort(byid.begin(), byid.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
-    out->RMSD.resize(byid.size());
-    for (size_t k = 0; k < byid.size(); k++) out->RMSD[k] = byid[k].second;
+    // the ids are the candidate atoms, each once: when the candidate list is ascending (res2atoms walks the atoms in order) the
+    // sorted values are the values in candidate order, scattered through a rank table; otherwise a stable sort on the ids
+    out->RMSD.resize(ids_.size());
+    if (std::is_sorted(full_.begin(), full_.end()) && std::adjacent_find(full_.begin(), full_.end()) == full_.end() && !full_.empty()) {
+        const int lo = full_.front();
+        std::vector<int> rank((size_t)(full_.back() - lo + 1), -1);
+        for (size_t k = 0; k < full_.size(); k++) rank[(size_t)(full_[k] - lo)] = (int)k;
+        for (size_t k = 0; k < ids_.size(); k++) out->RMSD[(size_t)rank[(size_t)(ids_[k] - lo)]] = vals_[k];
+    } else {
+        std::vector<std::pair<int, double>> byid(ids_.size());
+        for (size_t k = 0; k < byid.size(); k++) byid[k] = {ids_[k], vals_[k]};
+        std::stable_sort(byid.begin(), byid.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+        for (size_t k = 0; k < byid.size(); k++) out->RMSD[k] = byid[k].second;
+    }
     out->N = n_;
     out->Natoms.assign(indexesold_.begin(), indexesold_.begin() + n_);  // previous order, new n (:255)
     out->Nmols = iDs2MolIDandChains(mol, out->Natoms);
