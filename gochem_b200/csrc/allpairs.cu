@@ -25,18 +25,7 @@ namespace gcb {
 
 namespace {
 
-#ifndef GCB_AP_BK
-#define GCB_AP_BK 32
-#endif
-#ifndef GCB_AP_STAGES
-#define GCB_AP_STAGES 2
-#endif
-constexpr int BM = 128, BN = 128, BK = GCB_AP_BK;
-// Row stride of the staged operands in doubles.  A lane's fragments for TWO consecutive DMMA k-steps are neighbours in
-// memory (lane t takes k = 2t, 2t + 1 of every group of 8: the order of k inside a tile is free as long as both operands agree),
-// so one 16-byte load feeds two DMMAs; rows 64 bytes apart modulo 128 keep the eight lanes of a quarter warp on distinct banks.
-constexpr int LDS = BK + 8;
-constexpr int STAGES = GCB_AP_STAGES;  // BK = 32 double-buffered: one barrier per 8 DMMA k-steps (BK = 16 x 3 stages: per 4)
+constexpr int BM = 128, BN = 128;
 constexpr int GEMM_THREADS = 256;
 #ifndef GCB_AP_WARPS
 #define GCB_AP_WARPS 8
@@ -47,15 +36,6 @@ constexpr int AP_WR = BM / (AP_WARPS / 4);        // rows of a warp tile: 64 (8 
 constexpr int AP_MI = AP_WR / 8;
 constexpr int TLD = BN + 1;           // staging row stride: transposed reads touch every bank once per half warp
 constexpr int kMaxPeers = 8;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    const int bytes = pred ? 16 : 0;   // src-size 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -179,6 +159,82 @@ constexpr size_t kStageBytes = (size_t)(BM + BN) * TK * sizeof(double);   // 32 
 constexpr size_t kTmaSmem = TSTAGES * kStageBytes + 1024;  // + room to align the ring to 1024 bytes (swizzle atom)
 static_assert(64 * TLD * sizeof(double) <= TSTAGES * kStageBytes, "the epilogue staging buffer reuses the stage ring");
 
+// The main loop shared by both GEMM kernels: C (TM x TM, this warp's 8 MI x 8 NI part in acc) += A_rows . B_rows^T over kdim,
+// operands fetched with the tensor map (box = TM rows x TK doubles) into ring (1024-byte aligned, TSTAGES stages of 2 boxes).
+// Eight warps as 2 x 4; thread 0 is also the producer.  full / empty: TSTAGES mbarriers each, initialised by the caller
+// (full: 1 arrival + bytes, empty: 8 arrivals).  Returns when every warp has consumed every stage (no trailing barrier).
+template <int TM, int MI, int NI>
+__device__ __forceinline__ void tma_dmma_mainloop(const CUtensorMap* tmap, unsigned char* ring, uint64_t* full, uint64_t* empty, int rowA, int rowB,
+                                                  int kdim, double (&acc)[MI][NI][2]) {
+    using namespace ptx;
+    constexpr uint32_t kBox = (uint32_t)TM * TK * sizeof(double);
+    constexpr uint32_t kStage = 2 * kBox;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const int nk = (kdim + TK - 1) / TK;
+    // byte offsets of this lane's chunks inside an operand box: row r = base + 8 mi + g (base a multiple of 8, so r & 7 = g)
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t a_row = (uint32_t)(wm * 8 * MI + g) * (TK * 8u);
+    const uint32_t b_row = kBox + (uint32_t)(wn * 8 * NI + g) * (TK * 8u);
+    const uint32_t ch0 = (uint32_t)((2 * t) ^ g) * 16u, ch1 = (uint32_t)((2 * t + 1) ^ g) * 16u;
+    // Not volatile: the scheduler may start a stage's loads early and spread them between the DMMAs.  They cannot move above the
+    // wait for the stage (their address comes from the token taken after it) nor below the release (the DMMAs that consume them
+    // are volatile and stay in front of the arrive).
+    auto lds2 = [](uint32_t addr, double& x, double& y) {
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+    };
+    // producer state (thread 0 only): next k-step to load, its stage and the parity of that stage's previous release
+    const bool producer = tid == 0;
+    int pk = 0, ps = 0;
+    uint32_t pph = 1;
+    auto issue = [&]() {
+        unsigned char* st = ring + (size_t)ps * kStage;
+        mbar_arrive_expect_tx(&full[ps], kStage);
+        tma_load_2d(st, tmap, pk * TK, rowA, &full[ps]);
+        tma_load_2d(st + kBox, tmap, pk * TK, rowB, &full[ps]);
+        pk++;
+        if (++ps == TSTAGES) { ps = 0; pph ^= 1u; }
+    };
+    if (producer) {
+        prefetch_tensormap(tmap);
+        while (pk < nk && pk < TSTAGES) issue();     // the ring starts empty
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kt = 0; kt < nk; kt++) {
+        if (producer) {
+            // refill every stage the eight warps have released (non-blocking test); a stage this warp is about to wait for
+            // must have been requested, so that one is waited for
+            while (pk < nk && mbar_test(&empty[ps], pph)) issue();
+            if (pk <= kt) { mbar_wait(&empty[ps], pph); issue(); }
+        }
+        mbar_wait(&full[s], ph);
+        uint32_t st;
+        asm volatile("mov.u32 %0, %1;" : "=r"(st) : "r"(ring_u32 + (uint32_t)s * kStage) : "memory");
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t ch = h ? ch1 : ch0;
+            double ax[MI], ay[MI], bx[NI], by[NI];
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) lds2(st + b_row + (uint32_t)ni * (8u * TK * 8u) + ch, bx[ni], by[ni]);
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) lds2(st + a_row + (uint32_t)mi * (8u * TK * 8u) + ch, ax[mi], ay[mi]);
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ax[mi], bx[ni]);
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ay[mi], by[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with the stage
+        if (++s == TSTAGES) { s = 0; ph ^= 1u; }
+    }
+}
+
 // One CTA computes the BM x BN block (bi, bj), bj >= bi, of G = Y Y^T and delivers D for the block and for its mirror
 // image to the owners of those rows (PeerOut): the block is staged in shared memory, 64 rows at a time, and leaves as
 // whole-row segments (256-byte stores per warp), the mirror image read transposed from the same staging buffer.
@@ -194,7 +250,6 @@ allpairs_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nf
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;        // (AP_WARPS / 4) x 4 warps -> AP_WR x 32 warp tiles
     const int g = lane >> 2, t = lane & 3;
-    const int nk = (kdim + TK - 1) / TK;
 
     if (tid == 0) {
         for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], AP_WARPS); }
@@ -208,68 +263,7 @@ allpairs_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nf
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    {
-        // byte offsets of this lane's chunks inside an operand box: row r = base + 8 mi + g (base a multiple of 8, so r & 7 = g)
-        const uint32_t ring_u32 = smem_u32(ring);
-        const uint32_t a_row = (uint32_t)(wm * AP_WR + g) * (TK * 8u);
-        const uint32_t b_row = (uint32_t)(BM * TK * 8) + (uint32_t)(wn * 32 + g) * (TK * 8u);
-        const uint32_t ch0 = (uint32_t)((2 * t) ^ g) * 16u, ch1 = (uint32_t)((2 * t + 1) ^ g) * 16u;
-        // Not volatile: the scheduler may start a stage's loads early and spread them between the DMMAs.  They cannot move above the
-        // wait for the stage (their address comes from the token taken after it) nor below the release (the DMMAs that consume them
-        // are volatile and stay in front of the arrive).
-        auto lds2 = [](uint32_t addr, double& x, double& y) {
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
-        };
-        // producer state (thread 0 only): next k-step to load, its stage and the parity of that stage's previous release
-        const bool producer = tid == 0;
-        int pk = 0, ps = 0;
-        uint32_t pph = 1;
-        auto issue = [&]() {
-            unsigned char* st = ring + (size_t)ps * kStageBytes;
-            mbar_arrive_expect_tx(&full[ps], (uint32_t)kStageBytes);
-            tma_load_2d(st, &tmap, pk * TK, (int)i0, &full[ps]);                                      // rows i0 .. i0+127
-            tma_load_2d(st + (size_t)BM * TK * sizeof(double), &tmap, pk * TK, (int)j0, &full[ps]);      // rows j0 .. j0+127
-            pk++;
-            if (++ps == TSTAGES) { ps = 0; pph ^= 1u; }
-        };
-        if (producer) {
-            prefetch_tensormap(&tmap);
-            while (pk < nk && pk < TSTAGES) issue();     // the ring starts empty
-        }
-        int s = 0;
-        uint32_t ph = 0;
-        for (int kt = 0; kt < nk; kt++) {
-            if (producer) {
-                // refill every stage the eight warps have released (non-blocking test); a stage this warp is about to wait for
-                // must have been requested, so that one is waited for
-                while (pk < nk && mbar_test(&empty[ps], pph)) issue();
-                if (pk <= kt) { mbar_wait(&empty[ps], pph); issue(); }
-            }
-            mbar_wait(&full[s], ph);
-            uint32_t st;
-            asm volatile("mov.u32 %0, %1;" : "=r"(st) : "r"(ring_u32 + (uint32_t)s * (uint32_t)kStageBytes) : "memory");
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t ch = h ? ch1 : ch0;
-                double ax[AP_MI], ay[AP_MI], bx[4], by[4];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) lds2(st + b_row + (uint32_t)ni * (8u * TK * 8u) + ch, bx[ni], by[ni]);
-#pragma unroll
-                for (int mi = 0; mi < AP_MI; mi++) lds2(st + a_row + (uint32_t)mi * (8u * TK * 8u) + ch, ax[mi], ay[mi]);
-#pragma unroll
-                for (int mi = 0; mi < AP_MI; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ax[mi], bx[ni]);
-#pragma unroll
-                for (int mi = 0; mi < AP_MI; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], ay[mi], by[ni]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done with the stage
-            if (++s == TSTAGES) { s = 0; ph ^= 1u; }
-        }
-    }
+    tma_dmma_mainloop<BM, AP_MI, 4>(&tmap, ring, full, empty, (int)i0, (int)j0, kdim, acc);
     __syncthreads();   // every warp is done with the ring (all TMA writes were waited for): reuse it as the staging buffer
     // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
     double* sT = reinterpret_cast<double*>(ring);   // [64][TLD]
@@ -365,7 +359,6 @@ __global__ void __launch_bounds__(256) redo_pairs_kernel(const double* __restric
 // rotations of ||Y_i R - Y_j||^2 is G_i + G_j - 2 tr(R^T H_ij) with R from the same 3x3 solve as everywhere else
 // (kabsch3.cuh; geometric.go:154-190), evaluated per pair in the epilogue.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int FLDS = BK + 4;        // row stride of the staged operands: (8*row + 2*k) mod 32 banks -> two conflict-free wavefronts of 8-byte loads
 constexpr int FT = 32;              // frames per tile side
 constexpr int FM = 3 * FT;          // 96 rows
 constexpr int FLDC = FM + 1;        // padded row of the staged C tile
@@ -414,73 +407,36 @@ __global__ void __launch_bounds__(256) centre_frames_kernel(const double* __rest
     }
 }
 
+constexpr size_t kFitStageBytes = (size_t)2 * FM * TK * sizeof(double);   // two boxes of 96 rows x 16 doubles
+constexpr size_t kFitSmem = TSTAGES * kFitStageBytes + 1024;
+static_assert((size_t)FM * FLDC * sizeof(double) <= TSTAGES * kFitStageBytes, "the staged C tile reuses the stage ring");
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-allpairs_fit_dmma_kernel(const double* __restrict__ Z, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
+allpairs_fit_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nframes, const double* __restrict__ norms, double inv_n,
                          const int2* __restrict__ tiles, const PeerOut po, long ldd, double floor_rel, PairList redo) {
-    extern __shared__ __align__(16) double smem[];
-    double* sA = smem;                               // [STAGES][FM][FLDS]
-    double* sB = smem + (size_t)STAGES * FM * FLDS;    // [STAGES][FM][FLDS]
+    using namespace ptx;
+    extern __shared__ unsigned char smem_raw_fit[];
+    __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_fit) + 1023) & ~(uintptr_t)1023);
     const int2 tile = tiles[blockIdx.x];
     const long fi0 = (long)tile.x * FT, fj0 = (long)tile.y * FT;   // first frames of the tile
-    const long nrow_total = 3 * nframes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;         // 2 x 4 warps -> 48 x 24 warp tiles
     const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], GEMM_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     double acc[6][3][2];
 #pragma unroll
     for (int a = 0; a < 6; a++)
 #pragma unroll
         for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-    const int nk = (kdim + BK - 1) / BK;
-    auto load_stage = [&](int stage, int kt) {
-        const int k0 = kt * BK;
-#pragma unroll
-        for (int r = 0; r < 3 * BK / 16; r++) {
-            const int chunk = tid + r * GEMM_THREADS;   // 96 rows x BK / 2 chunks of 2 doubles
-            const int row = chunk / (BK / 2), kc = (chunk % (BK / 2)) * 2;
-            const bool kin = k0 + kc < kdim;
-            {
-                const long gr = 3 * fi0 + row;
-                const bool ok = kin && gr < nrow_total;
-                cp_async16(sA + ((size_t)stage * FM + row) * FLDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
-            }
-            {
-                const long gr = 3 * fj0 + row;
-                const bool ok = kin && gr < nrow_total;
-                cp_async16(sB + ((size_t)stage * FM + row) * FLDS + kc, Z + (ok ? gr : 0) * (long)kdim + (ok ? k0 + kc : 0), ok);
-            }
-        }
-    };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nk) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            const int nxt = kt + STAGES - 1;
-            if (nxt < nk) load_stage(nxt % STAGES, nxt);
-            cp_async_commit();
-        }
-        const double* a = sA + ((size_t)(kt % STAGES) * FM + wm * 48) * FLDS;
-        const double* b = sB + ((size_t)(kt % STAGES) * FM + wn * 24) * FLDS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[6], bf[3];
-#pragma unroll
-            for (int mi = 0; mi < 6; mi++) af[mi] = a[(mi * 8 + g) * FLDS + kk + t];
-#pragma unroll
-            for (int ni = 0; ni < 3; ni++) bf[ni] = b[(ni * 8 + g) * FLDS + kk + t];
-#pragma unroll
-            for (int mi = 0; mi < 6; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 3; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();   // everyone is done with the pipeline buffers: reuse them for the C tile
+    // rows of Z are coordinate planes: frame f owns rows 3f .. 3f+2; rows beyond 3 * nframes arrive as zeros
+    tma_dmma_mainloop<FM, 6, 3>(&tmap, ring, full, empty, (int)(3 * fi0), (int)(3 * fj0), kdim, acc);
+    __syncthreads();   // everyone is done with the ring: reuse it for the C tile
+    double* smem = reinterpret_cast<double*>(ring);
     double* sC = smem;  // [FM][FLDC]
 #pragma unroll
     for (int mi = 0; mi < 6; mi++)
@@ -585,7 +541,8 @@ __global__ void __launch_bounds__(256) redo_fit_pairs_kernel(const double* __res
 //   deal_n  > 1: the tiles on or above the diagonal are dealt round-robin to deal_n ranks (this one is deal_rank) and
 //                each finished tile is stored into the row blocks of its owners, local or peer.
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library links the runtime only)
-static int make_tensor_map(CUtensorMap* out, const double* base, unsigned long long cols, unsigned long long rows, unsigned long long pitch_bytes) {
+static int make_tensor_map(CUtensorMap* out, const double* base, unsigned long long cols, unsigned long long rows, unsigned long long pitch_bytes,
+                           int box_rows = BM) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
@@ -600,7 +557,7 @@ static int make_tensor_map(CUtensorMap* out, const double* base, unsigned long l
     }
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {pitch_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)BM};
+    const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -625,7 +582,6 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     std::vector<int2> tiles;
     const int tile_frames = fit ? FT : BM;
     const int nt = (int)((nframes + tile_frames - 1) / tile_frames);
-    const size_t smem = fit ? sizeof(double) * (size_t)STAGES * 2 * FM * FLDS : sizeof(double) * (size_t)STAGES * (BM + BN) * LDS;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 #define AP_TRY(call)                                                                              \
     do {                                                                                          \
@@ -713,10 +669,14 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     AP_TRY(cudaEventCreate(&e0));
     AP_TRY(cudaEventCreate(&e1));
     if (fit) {
+        // tensor map of Z: 3 * nframes rows (coordinate planes) of kdim doubles, boxes of 96 rows x 16 doubles
+        CUtensorMap tmap;
+        rc = make_tensor_map(&tmap, Y, (unsigned long long)kdim, 3ull * (unsigned long long)nframes, (unsigned long long)kdim * sizeof(double), FM);
+        if (rc) goto done;
         AP_TRY(opt_in_smem(allpairs_fit_dmma_kernel, t->dev));
         AP_TRY(cudaEventRecord(e0, s));
-        allpairs_fit_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, smem, s>>>(Y, kdim, nframes, norms, 1.0 / (double)natoms_used,
-                                                                                  d_tiles, po, nframes, 1e-7, redo);
+        allpairs_fit_dmma_kernel<<<(unsigned)tiles.size(), GEMM_THREADS, kFitSmem, s>>>(tmap, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                                      d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
         AP_TRY(cudaEventRecord(e1, s));
         redo_fit_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
