@@ -27,7 +27,10 @@ std::atomic<long> g_launches{0};
 // 100 000 frames, tools/split_small_probe.py, profiles/r1_s5_split_small_probe.jsonl: write-back 300 atoms 510 -> 392 us, 512 atoms
 // 720 -> 627 us, a tie at 600, the cluster kernel ahead above (and the fused warp-per-frame kernel below 64 atoms); per-atom sums
 // 300 atoms 644 -> 416 us, 800 atoms 827 -> 773 us, the cluster kernel ahead from 1000 atoms
-constexpr int kSplitWbMinAtoms = 64, kSplitWbMaxDefault = 560, kSplitDevMaxDefault = 900;
+// Round 2 (profiles/r2_dispatch_probe.jsonl): with the mbarrier hand-over the cluster kernel needs ~530 us per 100 000 frames
+// whatever the frame holds below 500 atoms, so it is ahead from ~480 atoms for both passes (write-back 512 atoms: 576 vs 630 us;
+// per-atom sums 640 / 800 / 900 atoms: 602 / 634 / 653 vs 655 / 764 / 851 us).
+constexpr int kSplitWbMinAtoms = 64, kSplitWbMaxDefault = 480, kSplitDevMaxDefault = 480;
 
 // defaults a new handle copies (gcb_set_*); a handle's own settings are changed with gcb_traj_set_*
 static std::mutex g_defaults_mu;

@@ -708,7 +708,7 @@ def test_large_frame_split_path_on_a_window():
     t.close()
 
 
-@pytest.mark.parametrize("natoms", [64, 100, 300, 333, 560, 561, 900, 901])
+@pytest.mark.parametrize("natoms", [64, 100, 300, 333, 480, 481, 560, 900, 901])
 def test_small_structures_split_form(natoms):
     """Write-back and per-atom sums on a few hundred atoms take the split form by default (fit-only launch, then one elementwise
     sweep whose threads own a column and walk the frames): against the oracle and against the fused kernels."""
