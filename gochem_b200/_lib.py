@@ -208,7 +208,9 @@ class DeviceTraj:
         out = (C.c_int * 8)()
         check(self.lib.gcb_traj_last_cluster_plan(self.h, out))
         keys = ["cluster", "part", "atoms_per_thread", "stages", "depth", "resident", "clusters", "smem"]
-        return dict(zip(keys, list(out)))
+        d = dict(zip(keys, list(out)))
+        d["consumer_warps"], d["resident"] = d["resident"] >> 4, d["resident"] & 1
+        return d
 
     # --- data movement ---
     def upload(self, frames: np.ndarray, first: int = 0, layout: int = F64_AOS, scale: float = 1.0):

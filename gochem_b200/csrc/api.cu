@@ -187,7 +187,8 @@ static int check_variant(int variant) {
 }
 
 static int check_cluster_tuning(int cluster, int stages, int depth, int resident) {
-    if (cluster < 0 || cluster > 8 || stages < 0 || stages > 8 || depth < 0 || depth > 6 || resident < -1 || resident > 1) {
+    if (cluster < 0 || cluster > 8 || stages < 0 || stages > 8 || depth < 0 || depth > 6 || resident < -1 ||
+        (resident > 1 && resident != (1 | (8 << 4)) && resident != (1 | (12 << 4)))) {
         set_error("bad cluster tuning (%d, %d, %d, %d)", cluster, stages, depth, resident);
         return GCB_ERR_ARG;
     }

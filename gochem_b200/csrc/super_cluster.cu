@@ -43,10 +43,25 @@ namespace {
 #ifndef GCB_CONSUMER_WARPS
 #define GCB_CONSUMER_WARPS 8
 #endif
-constexpr int kConsumerWarps = GCB_CONSUMER_WARPS;
-constexpr int kConsumers = 32 * kConsumerWarps;   // consumer threads per CTA
+// Consumer warps per CTA (template parameter W of the kernel): 8 in every instance of the product build.
+// A build with -DGCB_DEV_WARPS=12 gives the per-atom-distance instances a third consumer warp per scheduler: 16 warps start
+// with 128 registers, the producer / solver warpgroup gives up 48 with setmaxnreg and the three consumer warpgroups take 144
+// each (no spills up to 8 atoms per thread), the per-frame reduction runs in two rounds of 6 sums so that its scratch still
+// fits beside three resident stages.  Measured slower on every frame size (50 k x 5 k: 1.384 against 1.136 ms, 100 k x 10 k:
+// 6.13 against 5.09, profiles/r2_tuning.md): the pass is bound by the chain last-warp-delivered -> cluster sums -> 3x3 solve ->
+// pass 2 as much as by the consumers' issue rate, and twelve warps deliver later and reduce 1.5 x as much.  Kept as a tuning
+// build only.
+constexpr int kDefaultWarps = GCB_CONSUMER_WARPS;
+#ifndef GCB_DEV_WARPS
+#define GCB_DEV_WARPS GCB_CONSUMER_WARPS
+#endif
+constexpr int kDevWarps = GCB_DEV_WARPS;
+#ifndef GCB_DEV_WARPS_MIN_K
+#define GCB_DEV_WARPS_MIN_K 6     // atoms per thread of the 8-warp plan from which the 12-warp instance takes over
+#endif
 constexpr int kSolverWarps = 3;
-constexpr int kThreadsCta = kConsumers + 32 + 32 * kSolverWarps;  // + producer warp + solver warps
+constexpr int threads_cta(int W) { return 32 * W + 32 + 32 * kSolverWarps; }  // consumers + producer warp + solver warps
+constexpr int kRegsHelper = 80, kRegsConsumer = 144;   // setmaxnreg targets of the 16-warp block: 3 * 128 * 144 + 128 * 80 = 64 K
 constexpr int kMaxStages = 8;
 // Exchange slots.  Slot j mod NS is rewritten by the peers' pushes of frame j + NS.  A peer can start pass 1 of frame j + NS once
 // it has finished pass 2 of frame j + NS - D - 1, which needs every CTA's partial sums of that frame, i.e. this CTA's consumers
@@ -56,8 +71,12 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxSlots = 14;            // >= 2*D+2 with D <= 6, and > kSolverWarps
 constexpr int kResidentSlots = 8;        // plans that keep the part resident run at most D = 3 frames ahead
 constexpr int kRedRow = 33;              // transposition scratch of the per-frame reduction: [13 sums][32 lanes], rows padded by one
-constexpr int kRedWarpDoubles = 13 * kRedRow;
-constexpr size_t kRedScratchBytes = ((sizeof(double) * kRedWarpDoubles * kConsumerWarps + 127) / 128) * 128;
+// The transposition runs in R rounds of QR sums: one round of 13 with 8 warps; with 12 warps (12 sums: those instances never
+// carry sum w|a|^2) two rounds of 6, so that the scratch of 12 warps still fits beside three resident stages.
+constexpr int red_rounds(int W) { return W > 8 ? 2 : 1; }
+constexpr int red_per_round(int W) { return W > 8 ? 6 : 13; }
+constexpr int red_warp_doubles(int W) { return red_per_round(W) * kRedRow; }
+constexpr size_t red_scratch_bytes(int W) { return ((sizeof(double) * red_warp_doubles(W) * W + 127) / 128) * 128; }
 constexpr int kMaxCluster = 8;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -83,7 +102,7 @@ __device__ long long g_trace[8][512];
 #define TRACE(row, j) do {} while (0)
 #endif
 
-template <int NSLOTS>
+template <int NSLOTS, int W>
 struct __align__(16) SharedT {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
@@ -91,13 +110,15 @@ struct __align__(16) SharedT {
     uint64_t solved[NSLOTS];              // solver -> consumers: xf[slot] holds the frame's transform
     double partials[NSLOTS][kMaxCluster][14];   // 12 sums + sum w|a|^2
     double xf[NSLOTS][16];                // R[9], centroid*R [3], [12] = 1.0 when pass 2 must run for the RMSD
-    double red[NSLOTS][kConsumerWarps][14];     // per-warp totals of a frame's sums
+    double red[NSLOTS][W][14];            // per-warp totals of a frame's sums
     uint64_t red_full[NSLOTS];            // consumers -> solver: red[slot] holds every consumer warp's totals of the frame
 };
 // bytes in front of the stage ring: barriers and exchange slots, then the reduction scratch
-constexpr size_t fixed_smem(bool resident) {
-    return ((resident ? sizeof(SharedT<kResidentSlots>) : sizeof(SharedT<kMaxSlots>)) + 127) / 128 * 128 + kRedScratchBytes;
+template <int W>
+constexpr size_t fixed_smem_w(bool resident) {
+    return ((resident ? sizeof(SharedT<kResidentSlots, W>) : sizeof(SharedT<kMaxSlots, W>)) + 127) / 128 * 128 + red_scratch_bytes(W);
 }
+constexpr size_t fixed_smem(bool resident, int W) { return W == kDevWarps ? fixed_smem_w<kDevWarps>(resident) : fixed_smem_w<kDefaultWarps>(resident); }
 
 // sqrt of a positive double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
 // error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
@@ -123,8 +144,9 @@ __device__ __forceinline__ double fast_sqrt_pos(double x) {
 // Measured (profiles/r2_tuning.md): the pairs pay in the per-atom-distance pass (50 k x 5 k: 1.141 -> 1.126 ms); the wider
 // loads cost registers, and the fit-only K = 14 instance (3.27 -> 3.33 ms) and the write-back K = 10 instance (7.7 -> 10.6 ms,
 // spills inside the store loop) lose, so only the DEV instances pair.
-template <int K, bool DEV>
+template <int K, bool DEV, int W>
 struct Slots {
+    static constexpr int kConsumers = 32 * W;
     static constexpr bool PAIR = DEV && (K % 2 == 0);
     static __device__ __forceinline__ int base(int tid) { return PAIR ? 2 * tid : tid; }
     static __device__ __forceinline__ constexpr int off(int k) { return PAIR ? (k >> 1) * 2 * kConsumers + (k & 1) : k * kConsumers; }
@@ -135,12 +157,12 @@ struct Slots {
 // stride np, streaming loads).  WB = also store the superposed coordinates.
 // MASKED: the fit uses a subset of the atoms (fit_mask bit k = slot k is in it); otherwise every real atom is.
 // DEV: per-atom distances are accumulated and the frame's squared error is not (align.RMSDTraj never asks for it).
-template <int K, bool MASKED, bool DEV, bool WB, bool RESIDENT>
+template <int K, bool MASKED, bool DEV, bool WB, bool RESIDENT, int W>
 __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, long plane, const double* xf,
                                               const double (&bx)[K], const double (&by)[K], const double (&bz)[K],
                                               uint32_t fit_mask, double (&dev)[DEV ? K : 1], double* frw, int np,
                                               uint32_t real_mask, uint32_t in_mask, double b0, double b1, double b2) {
-    using SL = Slots<K, DEV>;
+    using SL = Slots<K, DEV, W>;
     const double r0 = xf[0], r1 = xf[1], r2 = xf[2], r3 = xf[3], r4 = xf[4], r5 = xf[5], r6 = xf[6], r7 = xf[7], r8 = xf[8];
     const double g0 = -xf[9], g1 = -xf[10], g2 = -xf[11];
     double e0 = 0.0, e1 = 0.0;
@@ -234,15 +256,18 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     return e0 + e1;
 }
 
-template <int K, bool MASKED, bool DEV, bool RESIDENT>
-__global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const ClusterParams cp) {
+template <int K, bool MASKED, bool DEV, bool RESIDENT, int W>
+__global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NS = RESIDENT ? kResidentSlots : kMaxSlots;
-    using Shared = SharedT<NS>;
+    constexpr int kConsumerWarps = W, kConsumers = 32 * W, kThreadsCta = threads_cta(W);
+    constexpr bool REDEAL = threads_cta(W) == 512;   // four warpgroups: registers re-dealt between the roles (setmaxnreg)
+    static_assert(DEV || red_rounds(W) == 1, "two-round reduction carries 12 sums only");
+    using Shared = SharedT<NS, W>;
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
     constexpr int kStageDoubles = 3 * K * kConsumers;
-    double* red_scratch = reinterpret_cast<double*>(smem_raw + fixed_smem(RESIDENT) - kRedScratchBytes);
-    double* stage_base = reinterpret_cast<double*>(smem_raw + fixed_smem(RESIDENT));
+    double* red_scratch = reinterpret_cast<double*>(smem_raw + fixed_smem_w<W>(RESIDENT) - red_scratch_bytes(W));
+    double* stage_base = reinterpret_cast<double*>(smem_raw + fixed_smem_w<W>(RESIDENT));
 
     const SuperParams& p = cp.p;
     const int tid = threadIdx.x;
@@ -258,6 +283,9 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
 
     // zero the stage ring once: slots beyond part_len are never written by TMA and must read as 0
     for (int i = tid; i < S * kStageDoubles; i += kThreadsCta) stage_base[i] = 0.0;
+    if (red_rounds(W) > 1) {   // entry 12 of red[][] (sum w|a|^2) is not written by the two-round reduction and travels as 0
+        for (int i = tid; i < NS * W * 14; i += kThreadsCta) (&sh.red[0][0][0])[i] = 0.0;
+    }
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kConsumerWarps); }
         for (int s = 0; s < NS; s++) {
@@ -275,6 +303,10 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     }
     cluster_sync_all();   // every CTA's barriers are initialised and armed before any remote store
 
+    // REDEAL: all four warps of a warpgroup execute the same setmaxnreg, first thing in their role; the consumers' request waits
+    // for the helpers' release
+    if (warp >= kConsumerWarps) {
+    if (REDEAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
     if (warp == kConsumerWarps) {
         // ===================== producer =====================
         if (lane == 0 && part_len > 0) {
@@ -304,7 +336,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             }
         }
         __syncwarp();
-    } else if (warp > kConsumerWarps) {
+    } else {
         // ===================== solvers: warp w takes local frames w, w + kSolverWarps, ... =====================
         // Per frame: rank-ordered sum of the cluster's partial sums, 3x3 solve, publish R and centroid R.
         const int sw = warp - (kConsumerWarps + 1);
@@ -387,10 +419,12 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
             slot += kSolverWarps;
             if (slot >= NS) { slot -= NS; sph ^= 1u; }
         }
+    }
     } else {
+        if (REDEAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
         // ===================== consumers (warps run free of one another) =====================
         // fixed atom slots (Slots<K>: pairs of neighbouring atoms when K is even); template and weights stay in registers
-        using SL = Slots<K, DEV>;
+        using SL = Slots<K, DEV, W>;
         const int tbase = SL::base(tid);
         double bx[K], by[K], bz[K], dev[DEV ? K : 1];
         uint32_t real_mask = 0, fit_mask = 0;
@@ -472,22 +506,30 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                 // are conflict-free): lane q + 16 h adds half h of sum q in a fixed tree and one shuffle joins the halves --
                 // 13 stores, 16 loads and one shuffle per lane instead of a 15-shuffle butterfly with its selects.
                 {
-                    double* tr = red_scratch + warp * kRedWarpDoubles;
-#pragma unroll
-                    for (int q = 0; q < 12; q++) tr[q * kRedRow + lane] = acc[q];
-                    if (!DEV) tr[12 * kRedRow + lane] = aa0 + aa1;
-                    __syncwarp();
+                    constexpr int R = red_rounds(W), QR = red_per_round(W);
                     constexpr int NQ = DEV ? 12 : 13;
-                    const int q = lane & 15;
-                    double v = 0.0;
-                    if (q < NQ) {
-                        const double* row = tr + q * kRedRow + (lane & 16);
-                        const double s0 = row[0] + row[1], s1 = row[2] + row[3], s2 = row[4] + row[5], s3 = row[6] + row[7];
-                        const double s4 = row[8] + row[9], s5 = row[10] + row[11], s6 = row[12] + row[13], s7 = row[14] + row[15];
-                        v = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+                    double* tr = red_scratch + warp * red_warp_doubles(W);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if (r > 0) __syncwarp();   // the previous round's loads are done with the scratch
+#pragma unroll
+                        for (int qq = 0; qq < QR; qq++) {
+                            const int q = r * QR + qq;
+                            if (q < 12) tr[qq * kRedRow + lane] = acc[q];
+                            else if (q == 12 && !DEV) tr[qq * kRedRow + lane] = aa0 + aa1;
+                        }
+                        __syncwarp();
+                        const int ql = lane & 15;
+                        double v = 0.0;
+                        if (ql < QR && r * QR + ql < NQ) {
+                            const double* row = tr + ql * kRedRow + (lane & 16);
+                            const double s0 = row[0] + row[1], s1 = row[2] + row[3], s2 = row[4] + row[5], s3 = row[6] + row[7];
+                            const double s4 = row[8] + row[9], s5 = row[10] + row[11], s6 = row[12] + row[13], s7 = row[14] + row[15];
+                            v = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+                        }
+                        v += __shfl_down_sync(0xffffffffu, v, 16);
+                        if (lane < QR && r * QR + lane < 13) sh.red[slot1][warp][r * QR + lane] = v;   // DEV: entry 12 is 0 (no sum w|a|^2 in that mode)
                     }
-                    v += __shfl_down_sync(0xffffffffu, v, 16);
-                    if (lane < 13) sh.red[slot1][warp][lane] = v;   // DEV: entry 12 is 0 (no sum w|a|^2 in that mode)
                 }
                 __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below; the scratch is free again
                 if (tid == 0) TRACE(7, j);
@@ -509,14 +551,14 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
                     }
                 } else if (RESIDENT) {
                     const double* sx = stage_base + (long)s2 * kStageDoubles + tbase;
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, MASKED, DEV, false, true>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true, W>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, true, W>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
                     if (++s2 == S) s2 = 0;
                 } else {
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
-                    else e = pass2_atoms<K, MASKED, DEV, false, false>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
+                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false, W>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    else e = pass2_atoms<K, MASKED, DEV, false, false, W>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                 }
                 if (run_pass2 && !DEV) {
 #pragma unroll
@@ -543,7 +585,7 @@ __global__ void __launch_bounds__(kThreadsCta, 1) super_cluster_kernel(const Clu
     cluster_sync_all();
 }
 
-__global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restrict__ epart, int C, long nframes, double inv_n,
+__global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restrict__ epart, int C, int kConsumerWarps, long nframes, double inv_n,
                                                          const unsigned char* __restrict__ need_explicit, double* __restrict__ rmsd) {
     const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
@@ -554,7 +596,7 @@ __global__ void __launch_bounds__(256) finish_rmsd_kernel(const double* __restri
 }
 
 struct Plan {
-    int cluster, part, kinst, stages, depth, resident;
+    int cluster, part, kinst, stages, depth, resident, warps;
     size_t smem;
 };
 
@@ -563,8 +605,10 @@ constexpr int kInst[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14};
 // Choose CTAs per frame, atoms per thread, stage count, pipeline depth.
 //  resident = 1: pass 2 reads the frame part from its shared-memory stage (needs depth <= stages - 2)
 //  resident = 0: pass 2 re-reads the part from L2; stages only cover the HBM latency, depth <= 6
-bool make_plan(const Tuning& tu, int np, bool heavy, Plan* pl) {
-    const int tune_cluster = tu.cluster, tune_depth = tu.depth, tune_stages = tu.stages, tune_resident = tu.resident;
+bool make_plan_w(const Tuning& tu, int np, bool heavy, int W, Plan* pl) {
+    const int kConsumers = 32 * W;
+    const int tune_cluster = tu.cluster, tune_depth = tu.depth, tune_stages = tu.stages;
+    const int tune_resident = tu.resident < 0 ? -1 : (tu.resident & 1);
     // Measured on B200 (profiles/r1_tuning.md).  Fit-only passes skip pass 2 for almost every frame, so the stage can be
     // released right after pass 1 (pass 2, when needed, re-reads the part from L2): two stages of the fattest part that
     // fits win (up to 14 atoms per thread, fewest CTAs per frame, clusters of <= 3 tile the GPCs almost exactly).
@@ -572,7 +616,7 @@ bool make_plan(const Tuning& tu, int np, bool heavy, Plan* pl) {
     // thread, >= 3 stages.
     const int resident = tune_resident >= 0 ? tune_resident : (heavy ? 1 : 0);
     const int kmax = resident ? (heavy ? 10 : 10) : 14;
-    const size_t fixed = fixed_smem(resident != 0);
+    const size_t fixed = fixed_smem(resident != 0, W);
     for (int c = 1; c <= kMaxCluster; c++) {
         if (tune_cluster && c != tune_cluster) continue;
         const int part = round_up((np + c - 1) / c, 16);
@@ -598,15 +642,28 @@ bool make_plan(const Tuning& tu, int np, bool heavy, Plan* pl) {
         }
         pl->cluster = c; pl->part = part; pl->kinst = kinst; pl->stages = stages; pl->depth = depth;
         pl->resident = resident;
+        pl->warps = W;
         pl->smem = fixed + stage * stages;
         return true;
     }
     return false;
 }
 
-template <int K, bool W, bool DV, bool RES>
+// dev = the pass accumulates per-atom distances.  In a -DGCB_DEV_WARPS=12 build that pass runs the 12-warp instance on fat parts
+// (>= GCB_DEV_WARPS_MIN_K atoms per thread of the 8-warp plan); tuning: resident = 1 | (warps << 4) forces the warp count.
+bool make_plan(const Tuning& tu, int np, bool heavy, bool dev, Plan* pl) {
+    if (!make_plan_w(tu, np, heavy, kDefaultWarps, pl)) return false;
+    const int forced = tu.resident > 0 ? (tu.resident >> 4) : 0;
+    if (!dev || !pl->resident || kDevWarps == kDefaultWarps || forced == kDefaultWarps) return true;
+    if (forced != kDevWarps && pl->kinst < GCB_DEV_WARPS_MIN_K) return true;
+    Plan p12;
+    if (make_plan_w(tu, np, heavy, kDevWarps, &p12) && p12.resident && p12.kinst <= 8) *pl = p12;
+    return true;
+}
+
+template <int K, bool WT, bool DV, bool RES, int W>
 int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
-    auto kern = super_cluster_kernel<K, W, DV, RES>;
+    auto kern = super_cluster_kernel<K, WT, DV, RES, W>;
     // the occupancy query costs tens of microseconds: once per (instance, device, shape).  The cache is shared by every handle
     // of the process and guarded; a miss only repeats the query.
     static std::mutex cache_mu;
@@ -628,7 +685,7 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cfg.blockDim = dim3(kThreadsCta);
+    cfg.blockDim = dim3(threads_cta(W));
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = t->stream;
     cfg.gridDim = dim3(pl.cluster * (t->sm_count / pl.cluster));
@@ -647,24 +704,41 @@ int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclus
     GCB_LAUNCHED();
     *nclusters_out = (int)g;
     t->last_plan[0] = pl.cluster; t->last_plan[1] = pl.part; t->last_plan[2] = pl.kinst; t->last_plan[3] = pl.stages;
-    t->last_plan[4] = pl.depth; t->last_plan[5] = pl.resident; t->last_plan[6] = (int)g; t->last_plan[7] = (int)pl.smem;
+    t->last_plan[4] = pl.depth; t->last_plan[5] = pl.resident | (pl.warps << 4); t->last_plan[6] = (int)g; t->last_plan[7] = (int)pl.smem;
     return GCB_OK;
 }
 
-template <bool W, bool DV, bool RES>
+template <bool WT, bool DV, bool RES>
 int launch_k(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* g) {
+    constexpr int W8 = kDefaultWarps;
+    if constexpr (DV && RES && kDevWarps != kDefaultWarps) {
+        if (pl.warps == kDevWarps) {
+            switch (pl.kinst) {   // 144 registers hold the template and the sums of up to 8 atoms
+                case 1: return launch_inst<1, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 2: return launch_inst<2, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 3: return launch_inst<3, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 4: return launch_inst<4, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 5: return launch_inst<5, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 6: return launch_inst<6, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 7: return launch_inst<7, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+                case 8: return launch_inst<8, WT, DV, RES, kDevWarps>(t, cp, pl, g);
+            }
+            set_error("no 12-warp kernel instance for %d atoms per thread", pl.kinst);
+            return GCB_ERR_ARG;
+        }
+    }
     switch (pl.kinst) {
-        case 1: return launch_inst<1, W, DV, RES>(t, cp, pl, g);
-        case 2: return launch_inst<2, W, DV, RES>(t, cp, pl, g);
-        case 3: return launch_inst<3, W, DV, RES>(t, cp, pl, g);
-        case 4: return launch_inst<4, W, DV, RES>(t, cp, pl, g);
-        case 5: return launch_inst<5, W, DV, RES>(t, cp, pl, g);
-        case 6: return launch_inst<6, W, DV, RES>(t, cp, pl, g);
-        case 7: return launch_inst<7, W, DV, RES>(t, cp, pl, g);
-        case 8: return launch_inst<8, W, DV, RES>(t, cp, pl, g);
-        case 10: return launch_inst<10, W, DV, RES>(t, cp, pl, g);
-        case 12: return launch_inst<12, W, DV, RES>(t, cp, pl, g);
-        case 14: return launch_inst<14, W, DV, RES>(t, cp, pl, g);
+        case 1: return launch_inst<1, WT, DV, RES, W8>(t, cp, pl, g);
+        case 2: return launch_inst<2, WT, DV, RES, W8>(t, cp, pl, g);
+        case 3: return launch_inst<3, WT, DV, RES, W8>(t, cp, pl, g);
+        case 4: return launch_inst<4, WT, DV, RES, W8>(t, cp, pl, g);
+        case 5: return launch_inst<5, WT, DV, RES, W8>(t, cp, pl, g);
+        case 6: return launch_inst<6, WT, DV, RES, W8>(t, cp, pl, g);
+        case 7: return launch_inst<7, WT, DV, RES, W8>(t, cp, pl, g);
+        case 8: return launch_inst<8, WT, DV, RES, W8>(t, cp, pl, g);
+        case 10: return launch_inst<10, WT, DV, RES, W8>(t, cp, pl, g);
+        case 12: return launch_inst<12, WT, DV, RES, W8>(t, cp, pl, g);
+        case 14: return launch_inst<14, WT, DV, RES, W8>(t, cp, pl, g);
     }
     set_error("no kernel instance for %d atoms per thread", pl.kinst);
     return GCB_ERR_ARG;
@@ -688,15 +762,15 @@ extern "C" int gcb_trace_read(long long* out) {
 // in shared memory, which holds fewer atoms per CTA (20 480 per frame against 28 672 for fit-only passes)
 bool cluster_kernel_supported(const gcb_traj* t, bool heavy) {
     Plan pl;
-    return make_plan(t->tune, t->np, heavy || t->tune.force_explicit, &pl);
+    return make_plan(t->tune, t->np, heavy || t->tune.force_explicit, false, &pl);
 }
 
 int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool want_dev, int* rows_out) {
     Plan pl;
     const int force_explicit = t->tune.force_explicit;
-    if (!make_plan(t->tune, t->np, want_dev || p.frames_rw != nullptr || force_explicit, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
+    if (!make_plan(t->tune, t->np, want_dev || p.frames_rw != nullptr || force_explicit, want_dev, &pl)) { set_error("no cluster plan for %d atoms", t->natoms); return GCB_ERR_ARG; }
     // pass 2's squared-error partials: scratch of THIS handle (its stream orders every use)
-    const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * kConsumerWarps;
+    const size_t need = sizeof(double) * (size_t)p.nframes * (size_t)pl.cluster * pl.warps;
     if (need > t->epart_bytes) {
         GCB_CUDA(cudaStreamSynchronize(t->stream));
         cudaFree(t->d_epart);
@@ -721,7 +795,7 @@ int launch_super_cluster(gcb_traj* t, const SuperParams& p, bool weighted, bool 
     if (rc) return rc;
     if (rows_out) *rows_out = g;
     if (p.rmsd) {
-        finish_rmsd_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, t->stream>>>(cp.epart, pl.cluster, p.nframes, p.inv_n, p.need_explicit, p.rmsd);
+        finish_rmsd_kernel<<<(unsigned)((p.nframes + 255) / 256), 256, 0, t->stream>>>(cp.epart, pl.cluster, pl.warps, p.nframes, p.inv_n, p.need_explicit, p.rmsd);
         GCB_LAUNCHED();
     }
     GCB_CUDA(cudaGetLastError());

@@ -64,7 +64,8 @@ int gcb_set_kernel_variant(int variant);
 int gcb_traj_set_kernel_variant(gcb_traj *t, int variant);
 /* Tuning hook for the cluster kernel: CTAs per frame (1..8), shared-memory stages, how many frames pass 2
  * trails pass 1 (1..6), and where pass 2 reads the frame from (1 = its shared-memory stage, 0 = L2,
- * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice. */
+ * -1 = built-in choice).  0 / 0 / 0 / -1 restores the built-in choice.  resident = 1 | (warps << 4) with warps = 8 or 12 also
+ * forces the number of consumer warps of the per-atom-distance instances (12 exists in -DGCB_DEV_WARPS=12 tuning builds only). */
 int gcb_set_cluster_tuning(int cluster, int stages, int depth, int resident);
 int gcb_traj_set_cluster_tuning(gcb_traj *t, int cluster, int stages, int depth, int resident);
 /* Tuning hook: structures of at most this many atoms take the split form (a fit-only launch, then one elementwise sweep) for
@@ -78,7 +79,7 @@ int gcb_traj_set_split_thresholds(gcb_traj *t, int write_back_max_atoms, int per
 int gcb_set_rmsd_mode(int explicit_only);
 int gcb_traj_set_rmsd_mode(gcb_traj *t, int explicit_only);
 /* Shape of the handle's last cluster-kernel launch: {CTAs per frame, atoms per CTA, atoms per thread, stages, depth,
- * resident, clusters launched, dynamic shared memory bytes}. */
+ * resident | consumer warps << 4, clusters launched, dynamic shared memory bytes}. */
 int gcb_traj_last_cluster_plan(const gcb_traj *t, int *out8);
 
 /* ---- C-owned pinned staging (Go memory may not be retained across an async copy) ---- */
