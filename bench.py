@@ -275,6 +275,16 @@ def sub_lovo(a, d, comm, dev, peak):
     t.sync()
     kw = dict(nselected_total=total, cpus=8, comm=comm if d.world > 1 else None, rank=d.rank, nranks=d.world)
     got = H.LOVOResident(t, ref, **kw)          # warm-up: allocations, NCCL connections
+    # The GPU has idled through the CPU baseline (seconds of host work) and sits at its idle clocks; a LOVO run lasts a few
+    # milliseconds, less than the clock ramp.  Keep the device busy with the same pass for a fixed time first (every rank the
+    # same number of calls when a communicator is involved).
+    warm_idx = np.arange(natoms, dtype=np.int32)
+    t_warm = time.perf_counter()
+    while True:
+        for _ in range(20):
+            t.peratom_dev_sum(ref, warm_idx, comm=comm if d.world > 1 else None)
+        if d.max(time.perf_counter() - t_warm) > 0.4:
+            break
     runs = []
     for _ in range(3):
         d.barrier()

@@ -806,6 +806,10 @@ int check_status(gcb_traj_ext* t) {
     GCB_CUDA(cudaStreamSynchronize(t->stream));
     if (st != 0) {
         cudaMemsetAsync(t->d_status, 0, sizeof(int), t->stream);
+        if (st == (int)GCB_ERR_CUDA) {
+            set_error("the exchange of the per-atom sums timed out: a peer rank never delivered its vector (GCB_EXCHANGE_TIMEOUT_S)");
+            return GCB_ERR_CUDA;
+        }
         set_error("RotatorTranslatorToSuper: mat.SVD failed (non-finite correlation matrix in at least one frame)");
         return GCB_ERR_SVD;
     }

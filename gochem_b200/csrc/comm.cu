@@ -114,8 +114,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 struct MailPtrs { double* box[8]; };
 
+// A peer that never arrives (its process died before the call) must not hang this GPU: the wait gives up after timeout_ns,
+// fills the vector with NaN and leaves GCB_ERR_CUDA in *status (the trajectory's status word, read at the end of every pass).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(1024) peer_exchange_sum_kernel(MailPtrs mp, int nranks, int rank, long cap, long n, unsigned long long seq,
-                                                                  double* __restrict__ vec) {
+                                                                  double* __restrict__ vec, unsigned long long timeout_ns, int* status) {
+    __shared__ int lost;
+    if (threadIdx.x == 0) lost = 0;
     const int par = (int)(seq & 1ull);
     const size_t slot = ((size_t)par * nranks + rank) * (size_t)cap;       // where this rank's vector goes in every box
     for (int r = 0; r < nranks; r++) {
@@ -129,10 +139,19 @@ __global__ void __launch_bounds__(1024) peer_exchange_sum_kernel(MailPtrs mp, in
         unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(mp.box[threadIdx.x] + flags_off);
         st_release_sys(peer_flags + (size_t)par * nranks + rank, seq);
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(mp.box[rank] + flags_off) + (size_t)par * nranks + threadIdx.x;
-        while (ld_acquire_sys(mine) < seq) {}
+        const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
+        while (ld_acquire_sys(mine) < seq) {
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) { lost = 1; break; }
+        }
     }
     __threadfence_system();
     __syncthreads();
+    if (lost) {
+        for (long i = threadIdx.x; i < n; i += blockDim.x) vec[i] = __longlong_as_double(0x7ff8000000000000LL);
+        if (threadIdx.x == 0 && status) atomicExch(status, (int)GCB_ERR_CUDA);
+        return;
+    }
     const double* box = mp.box[rank] + (size_t)par * nranks * (size_t)cap;
     for (long i = threadIdx.x; i < n; i += blockDim.x) {
         double s = 0.0;
@@ -197,7 +216,12 @@ static int mail_setup(gcb_comm* c, long n) {
 }
 
 // device vector d_vec[n] (on stream s) -> same vector summed over ranks in rank order
-static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s) {
+static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s, int* d_status = nullptr) {
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("GCB_EXCHANGE_TIMEOUT_S");
+        const double sec = e ? atof(e) : 30.0;
+        return (unsigned long long)((sec > 0.0 ? sec : 30.0) * 1e9);
+    }();
     static const bool force_nccl = getenv("GCB_ALLREDUCE_NCCL") != nullptr;   // the library all-gather path, for comparison
     if (!force_nccl && c->nranks <= 8 && (c->mail_state == 0 || (c->mail_state == 1 && n > c->mail_cap))) {
         GCB_CUDA(cudaStreamSynchronize(s));   // set-up is collective and rare; the exchange itself never synchronises
@@ -208,7 +232,7 @@ static int allreduce_device(gcb_comm* c, double* d_vec, long n, cudaStream_t s) 
         MailPtrs mp;
         for (int r = 0; r < 8; r++) mp.box[r] = r < c->nranks ? c->mail[r] : nullptr;
         c->mail_seq++;
-        peer_exchange_sum_kernel<<<1, 1024, 0, s>>>(mp, c->nranks, c->rank, c->mail_cap, n, c->mail_seq, d_vec);
+        peer_exchange_sum_kernel<<<1, 1024, 0, s>>>(mp, c->nranks, c->rank, c->mail_cap, n, c->mail_seq, d_vec, timeout_ns, d_status);
         GCB_LAUNCHED();
         GCB_CUDA(cudaGetLastError());
         return GCB_OK;
@@ -403,7 +427,7 @@ int gcb_peratom_dev_sum(gcb_traj* t, long first, long nframes, const double* ref
     const auto t1 = std::chrono::steady_clock::now();
     if (comm && comm->nranks > 1) {
         if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
-        rc = allreduce_device(comm, t->d_devsum, t->natoms, t->stream);
+        rc = allreduce_device(comm, t->d_devsum, t->natoms, t->stream, t->d_status);
         if (rc) return rc;
     }
     GCB_CUDA(cudaMemcpyAsync(sum, t->d_devsum, sizeof(double) * (size_t)t->natoms, cudaMemcpyDeviceToHost, t->stream));
@@ -426,7 +450,7 @@ int gcb_peratom_dev_sum_atoms(gcb_traj* t, long first, long nframes, const doubl
     if (rc) return rc;
     if (comm && comm->nranks > 1) {
         if (comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
-        rc = allreduce_device(comm, t->d_devsum, nwant, t->stream);
+        rc = allreduce_device(comm, t->d_devsum, nwant, t->stream, t->d_status);
         if (rc) return rc;
     }
     GCB_CUDA(cudaMemcpyAsync(sum_want, t->d_devsum, sizeof(double) * (size_t)nwant, cudaMemcpyDeviceToHost, t->stream));

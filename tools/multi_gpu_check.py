@@ -102,6 +102,17 @@ if rank == 0:
                                      and single["Iterations"] == got["Iterations"])
     out["max_abs_rmsd_diff_vs_single"] = float(np.abs(single["RMSD"] - got["RMSD"]).max())
     whole.close()
+# 5. last (the communicator is unusable afterwards): a peer that never delivers its vector gives an error after
+#    GCB_EXCHANGE_TIMEOUT_S seconds, not a hung GPU.  Only run when that variable is set (to something short).
+if os.environ.get("GCB_EXCHANGE_TIMEOUT_S"):
+    if rank == 0:
+        t0 = time.perf_counter()
+        try:
+            t.peratom_dev_sum(ref, np.arange(natoms, dtype=np.int32), comm=comm)
+            out["exchange_timeout"] = "no error raised"
+        except _lib.GcbError as e:
+            out["exchange_timeout"] = {"seconds": time.perf_counter() - t0, "error": e.msg[:160]}
+if rank == 0:
     print(json.dumps(out), flush=True)
 dist.barrier()
 t.close()
