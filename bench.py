@@ -584,7 +584,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(a.write_back), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                "note": "per GPU; 24 B/atom/frame fit mode (48 with write-back), template re-reads excluded; the peak is a read+write copy, a read-only stream can exceed it (frac > 1 = faster than the copy, not faster than the memory; ncu: 88 % of the DRAM peak)"}
+                "note": "per GPU; 24 B/atom/frame fit mode (48 with write-back), template re-reads excluded; the peak is a read+write copy, a read-only stream can exceed it (frac > 1 = faster than the copy, not faster than the memory; ncu: 88 % of the DRAM peak; a plain read-only stream of 24 GiB, tools/micro/read_bw.cu, reaches 7329 GB/s on this pool: profiles/r2_read_only_ceiling.txt)"}
 
     # end to end through the C ABI with HOST buffers: pinned float64 AoS frames -> device -> kernel -> rmsd back
     e2e_frames = min(a.e2e_frames, nframes)
