@@ -36,6 +36,9 @@ var (
 	B200WindowBytes = int64(8) << 30
 )
 
+// the reference's loop has no bound (lovo.go:221); the library's wants one
+const b200MaxIterations = 1 << 20
+
 // deviceFrames is the selected part of a trajectory, resident on the device as one or more windows.
 type deviceFrames struct {
 	windows []*v3gpu.Traj
@@ -205,6 +208,21 @@ func LOVO(mol chem.Atomer, ref *v3.Matrix, trajname string, opt ...*Options) (*L
 		return nil, err
 	}
 	defer func() { d.Close() }()
+	// One device window and no aligned trajectory to write: the whole iteration runs in the library, the bookkeeping below on
+	// the device (gcb_lovo_resident).  It declines what it does not cover; the loop below gives the same answers bit for bit.
+	if printtraj == "" && len(d.windows) == 1 {
+		res, taken, err := d.windows[0].LOVOResident(0, d.counts[0], ref, fullindexes, d.total, o.lessThanRMSD, o.minimumN, b200MaxIterations, nil)
+		if err != nil {
+			return nil, err
+		}
+		if taken {
+			RMSD = newRMSD(res.IDs, res.Vals)
+			RMSD.SortBy("molid")
+			natoms := res.IndexesOld[0:res.N]
+			return &LOVOReturn{N: res.N, Natoms: natoms, Nmols: iDs2MolIDandChains(mol, natoms), RMSD: RMSD.rMSDs, FramesRead: d.total,
+				Iterations: res.Iterations}, nil
+		}
+	}
 	for {
 		if disagreement == 1 && printtraj != "" {
 			o.writeTraj = printtraj

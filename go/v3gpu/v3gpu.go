@@ -352,6 +352,50 @@ func (t *Traj) PerAtomDevSumAtoms(first, n int64, ref *v3.Matrix, idx, want []in
 	return sum, err
 }
 
+// LOVOResult is what the library's own LOVO iteration leaves: LOVOReturn.N and .Iterations, indexesold (its first N entries
+// are LOVOReturn.Natoms) and the candidates with their mean deviations in the order of the last sort.
+type LOVOResult struct {
+	N, Iterations, Disagreement int
+	IndexesOld, IDs             []int
+	Vals                        []float64
+}
+
+// LOVOResident runs align.LOVO's fixed-point iteration (align/lovo.go:212-252) over the resident frames with the bookkeeping of
+// lovo.go:229-252 on the device (gcb_lovo_resident): 64 bytes come back per iteration instead of the per-atom means.  taken is
+// false when the library leaves the case to the caller (candidates not ascending, more than 16384 of them, small frames ...):
+// run the loop with PerAtomDevSum then -- the answers are the same bit for bit.
+func (t *Traj) LOVOResident(first, n int64, ref *v3.Matrix, cand []int, totalFrames int, lessThanRMSD float64, minimumN, maxIter int,
+	comm *Comm) (res *LOVOResult, taken bool, err error) {
+	if len(cand) == 0 {
+		return nil, false, nil
+	}
+	keep, cp := cints(cand)
+	old, ids := make([]C.int, len(cand)), make([]C.int, len(cand))
+	vals := make([]float64, len(cand))
+	var nOut, iters, dis C.int
+	raw := ref.RawSlice()
+	var rc C.int
+	err = call(func() C.int {
+		rc = C.gcb_lovo_resident(t.h, C.long(first), C.long(n), (*C.double)(&raw[0]), cp, C.int(len(cand)), C.double(totalFrames),
+			C.double(lessThanRMSD), C.int(minimumN), C.int(maxIter), comm.handle(), &nOut, &iters, &dis, &old[0], &ids[0],
+			(*C.double)(&vals[0]))
+		if rc == 1 { // not taken: not an error
+			return 0
+		}
+		return rc
+	})
+	runtime.KeepAlive(keep)
+	if err != nil || rc == 1 {
+		return nil, false, err
+	}
+	res = &LOVOResult{N: int(nOut), Iterations: int(iters), Disagreement: int(dis), IndexesOld: make([]int, len(cand)),
+		IDs: make([]int, len(cand)), Vals: vals}
+	for i := range old {
+		res.IndexesOld[i], res.IDs[i] = int(old[i]), int(ids[i])
+	}
+	return res, true, nil
+}
+
 // AllPairsRMSD fills rows [row0, row0+nrows) of the nframes x nframes matrix D[i][j] = chem.RMSD(frame_i, frame_j)
 // (fit = false; superpose first) or chem.RMSD(chem.Super(frame_i, frame_j), frame_j) (fit = true), one fp64 tensor-core GEMM.
 func (t *Traj) AllPairsRMSD(idx []int, row0, nrows int64, fit bool) ([]float64, error) {

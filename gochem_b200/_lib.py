@@ -80,6 +80,7 @@ def load() -> C.CDLL:
         "gcb_rmsd": (I, [P, L, L, P, I, P, P, I, P]),
         "gcb_peratom_dist": (I, [P, L, P, I, P, P, I, P]),
         "gcb_peratom_dev_sum": (I, [P, L, L, P, P, I, I, P, P]),
+        "gcb_lovo_resident": (I, [P, L, L, P, P, I, D, D, I, I, P, C.POINTER(I), C.POINTER(I), C.POINTER(I), P, P, P]),
         "gcb_allpairs_rmsd": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_allpairs_rmsd_fit": (I, [P, L, L, P, I, L, L, P, C.POINTER(C.c_float), C.POINTER(L)]),
         "gcb_moments": (I, [P, L, L, P, P, I, P, P]),
@@ -311,6 +312,24 @@ class DeviceTraj:
         check(self.lib.gcb_peratom_dev_sum_atoms(self.h, first, n, _ptr(ref), _ptr(it), 0 if it is None else it.size, _ptr(iw), iw.size,
                                                  comm.h if comm else None, _ptr(out)))
         return out
+
+    def lovo_resident(self, ref, cand, total_frames=None, less_than_rmsd=1.0, minimum_n=10, max_iter=100000, first=0, nframes=None,
+                      comm: Comm | None = None):
+        """align.LOVO's iteration with the bookkeeping on the device (gcb_lovo_resident).  None when the library does not take
+        the case (return code 1): run the host loop then."""
+        n = self.nframes - first if nframes is None else nframes
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        ic = _idx(cand)
+        nout, iters, dis = C.c_int(0), C.c_int(0), C.c_int(0)
+        old, ids, vals = np.zeros(ic.size, dtype=np.int32), np.zeros(ic.size, dtype=np.int32), np.zeros(ic.size)
+        rc = self.lib.gcb_lovo_resident(self.h, first, n, _ptr(ref), _ptr(ic), ic.size, float(n if total_frames is None else total_frames),
+                                        float(less_than_rmsd), int(minimum_n), int(max_iter), comm.h if comm else None,
+                                        C.byref(nout), C.byref(iters), C.byref(dis), _ptr(old), _ptr(ids), _ptr(vals))
+        if rc == 1:
+            return None
+        check(rc)
+        return dict(N=nout.value, Iterations=iters.value, Disagreement=dis.value, indexesold=old, ids=ids, vals=vals,
+                    Natoms=old[: nout.value].copy())
 
     def allpairs_rmsd(self, idx=None, first=0, nframes=None, row0=0, nrows=None, fit=False):
         n = self.nframes - first if nframes is None else nframes

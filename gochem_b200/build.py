@@ -13,7 +13,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = (["-DGCB_TRACE"] if os.environ.get("GCB_TRACE") else []) + \
     (["-DGCB_CONSUMER_WARPS=" + os.environ["GCB_CONSUMER_WARPS"]] if os.environ.get("GCB_CONSUMER_WARPS") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
-SOURCES = ["api.cu", "layout.cu", "super_generic.cu", "super_cluster.cu", "synth.cu", "comm.cu", "allpairs.cu", "moments.cu", "rdf.cu", "super_small.cu", "transform.cu"]
+SOURCES = ["api.cu", "layout.cu", "super_generic.cu", "super_cluster.cu", "synth.cu", "comm.cu", "allpairs.cu", "moments.cu", "rdf.cu", "super_small.cu", "transform.cu", "lovo_ctl.cu"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:

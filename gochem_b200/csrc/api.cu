@@ -333,7 +333,8 @@ int gcb_traj_destroy(gcb_traj* tb) {
     cudaFree(t->d_devpart); cudaFree(t->d_devsum); cudaFree(t->d_refplanes); cudaFree(t->d_want); cudaFree(t->d_wantref);
     cudaFree(t->d_mom_w); cudaFree(t->d_mom_c); cudaFree(t->d_mom_m);
     cudaFree(t->d_ap_ws);
-    cudaFree(t->d_epart); cudaFree(t->d_pdist);
+    cudaFree(t->d_epart); cudaFree(t->d_pdist); cudaFree(t->d_lovo_ws);
+    if (t->h_lovo) cudaFreeHost(t->h_lovo);
     if (t->h_scratch) cudaFreeHost(t->h_scratch);
     for (int s = 0; s < 2; s++) {
         if (t->h_bounce[s]) cudaFreeHost(t->h_bounce[s]);
@@ -1114,6 +1115,49 @@ int peratom_local(gcb_traj* tb, long first, long nframes, const double* ref_aos,
     return launch_dev_reduce(t, rows, t->d_devsum);
 }
 int peratom_finish(gcb_traj* tb) { return check_status(X(tb)); }
+
+// Would a per-atom-distance pass with a subset fit go to the cluster kernel (launch_super_impl's choice)?  Only that path can run
+// on a template prepared on the device (gcb_lovo_resident).
+bool peratom_prepared_supported(gcb_traj* tb) {
+    gcb_traj_ext* t = X(tb);
+    const int variant = t->tune.variant;
+    if (variant == GCB_KERNEL_GENERIC) return false;
+    const int split_dev_max = t->tune.split_dev_max < 0 ? kSplitDevMaxDefault : t->tune.split_dev_max;
+    if (variant == GCB_KERNEL_AUTO && (t->natoms <= split_dev_max || small_kernel_supported(t, true))) return false;
+    return cluster_kernel_supported(t, true);
+}
+
+// The pass of peratom_local over the template lovo_controller_kernel left in d_refc / d_weight (n_fit atoms in the fit): no host
+// preparation, no upload.  The template cache no longer describes the device buffers afterwards.
+int peratom_prepared(gcb_traj* tb, long first, long nframes, int n_fit) {
+    gcb_traj_ext* t = X(tb);
+    if (n_fit <= 0) { set_error("a fit on no atoms"); return GCB_ERR_ARG; }
+    t->cache.valid = false;
+    t->cache.n_fit = (double)n_fit;
+    t->cache.bbar[0] = t->cache.bbar[1] = t->cache.bbar[2] = 0.0;   // only the write-back adds it; this pass never writes back
+    t->cache.gb = 0.0;                                              // only the one-pass RMSD reads it; this pass never asks for one
+    if (nframes == 0) {
+        GCB_CUDA(cudaMemsetAsync(t->d_devsum, 0, sizeof(double) * (size_t)t->np, t->stream));
+        return GCB_OK;
+    }
+    int rc = deps_before_compute(t, first, nframes);
+    if (rc) return rc;
+    SuperParams p;
+    fill_params(t, first, nframes, 0, &p);
+    p.weight = t->d_weight;
+    const size_t rows = (size_t)t->sm_count * 8;
+    rc = ensure_devpart(t, rows);
+    if (rc) return rc;
+    GCB_CUDA(cudaMemsetAsync(t->d_devpart, 0, sizeof(double) * rows * (size_t)t->np, t->stream));
+    p.devpart = t->d_devpart;
+    p.rmsd = nullptr;
+    int rows_used = 0;
+    rc = launch_super_cluster(t, p, true, true, &rows_used);
+    if (rc) return rc;
+    rc = deps_after_compute(t, first, nframes);
+    if (rc) return rc;
+    return launch_dev_reduce(t, rows_used, t->d_devsum);
+}
 
 // per-atom sums for the atoms of `want` only: d_devsum[k] belongs to want[k]
 int peratom_local_atoms(gcb_traj* tb, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want, int nwant) {

@@ -440,6 +440,127 @@ int gcb_peratom_dev_sum(gcb_traj* t, long first, long nframes, const double* ref
     return rc;
 }
 
+// align.LOVO's whole fixed-point iteration (align/lovo.go:212-252) over resident frames with the bookkeeping on the device
+// (lovo_ctl.cu): per iteration one fused pass, the cross-rank sum, one controller CTA, and 64 bytes back to the host.
+// Returns GCB_OK, an error, or 1 = "not taken" (shape or tuning that the device loop does not cover, or values the host mirror
+// must sort): the caller then runs the loop on the host with gcb_peratom_dev_sum -- same answers, bit for bit.
+int gcb_lovo_resident(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* cand, int ncand, double total_frames,
+                      double less_than_rmsd, int minimum_n, int max_iter, gcb_comm* comm, int* n_out, int* iterations_out,
+                      int* disagreement_out, int* indexesold_out, int* ids_out, double* vals_out) {
+    if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }
+    if (first < 0 || nframes < 0 || first + nframes > t->nframes) { set_error("frame window outside the trajectory"); return GCB_ERR_ARG; }
+    if (!ref_aos || !cand || ncand <= 0 || !n_out || !iterations_out || !indexesold_out || !ids_out || !vals_out) {
+        set_error("bad LOVO arguments");
+        return GCB_ERR_ARG;
+    }
+    if (ncand > lovo_ctl_slots() || 8L * ncand <= t->natoms || !(total_frames > 0.0)) return 1;   // big candidate lists sort on the host; sparse ones read their sectors only
+    for (int k = 0; k < ncand; k++) {
+        if (cand[k] < 0 || cand[k] >= t->natoms) { set_error("candidate atom %d is out of range (%d)", k, cand[k]); return GCB_ERR_INDEXES; }
+        if (k > 0 && cand[k] <= cand[k - 1]) return 1;                                // the mirror pairs values and candidates by position
+    }
+    GCB_CUDA(cudaSetDevice(t->dev));
+    const auto t_enter = std::chrono::steady_clock::now();
+    if (!peratom_prepared_supported(t)) return 1;
+    if (comm && comm->nranks > 1 && comm->dev != t->dev) { set_error("communicator and trajectory live on different devices"); return GCB_ERR_ARG; }
+    // workspace of this handle: [state | cand | old | ids | vals | template copy]
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t oSt = carve(sizeof(LovoDevState)), oCand = carve(sizeof(int) * (size_t)ncand), oOld = carve(sizeof(int) * (size_t)ncand),
+                 oIds = carve(sizeof(int) * (size_t)ncand), oVals = carve(sizeof(double) * (size_t)ncand),
+                 oRef = carve(sizeof(double) * 3 * (size_t)t->natoms);
+    if (off > t->lovo_ws_bytes) {
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+        cudaFree(t->d_lovo_ws);
+        t->d_lovo_ws = nullptr;
+        t->lovo_ws_bytes = 0;
+        GCB_CUDA(cudaMalloc(&t->d_lovo_ws, off));
+        t->lovo_ws_bytes = off;
+    }
+    if (!t->h_lovo) GCB_CUDA(cudaHostAlloc(&t->h_lovo, 2 * sizeof(LovoDevState) + sizeof(int) * (size_t)lovo_ctl_slots(), cudaHostAllocMapped));
+    unsigned char* w = (unsigned char*)t->d_lovo_ws;
+    LovoDevState* hst = (LovoDevState*)t->h_lovo;            // [0]: what the controller reports; [1]: the initial state, staged
+    int* h_iota = (int*)(hst + 2);
+    LovoCtl c = {};
+    c.devsum = t->d_devsum;
+    c.total = total_frames;
+    c.cand = (const int*)(w + oCand);
+    c.ncand = ncand;
+    c.old = (int*)(w + oOld);
+    c.ids = (int*)(w + oIds);
+    c.vals = (double*)(w + oVals);
+    c.st = (LovoDevState*)(w + oSt);
+    c.host = hst;
+    c.less_than = less_than_rmsd;
+    c.minimum_n = minimum_n;
+    c.ref_aos = (const double*)(w + oRef);
+    c.natoms = t->natoms;
+    c.np = t->np;
+    c.refc = t->d_refc;
+    c.weight = t->d_weight;
+    c.status = t->d_status;
+    GCB_CUDA(cudaStreamSynchronize(t->stream));              // the staging words below may still feed an earlier run's copies
+    memset(&hst[1], 0, sizeof(LovoDevState));
+    hst[1].n = ncand;                                        // lovo.go:212-213: indexesold = fullindexes, n = len
+    for (int k = 0; k < ncand; k++) h_iota[k] = k;
+    GCB_CUDA(cudaMemcpyAsync(c.st, &hst[1], sizeof(LovoDevState), cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaMemcpyAsync(c.old, h_iota, sizeof(int) * (size_t)ncand, cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaMemcpyAsync((void*)c.cand, cand, sizeof(int) * (size_t)ncand, cudaMemcpyHostToDevice, t->stream));
+    GCB_CUDA(cudaMemcpyAsync((void*)c.ref_aos, ref_aos, sizeof(double) * 3 * (size_t)t->natoms, cudaMemcpyHostToDevice, t->stream));
+    int rc = GCB_OK;
+    int n_fit = ncand;
+    static const bool timing = getenv("GCB_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto tl0 = now();
+    for (int it = 0;; it++) {
+        const auto ti0 = now();
+        // every pass fits on the template the controller left on the device: before the first one that of the whole candidate list
+        if (it == 0) {
+            rc = launch_lovo_first_template(t, c);
+            if (rc) return rc;
+        }
+        rc = peratom_prepared(t, first, nframes, n_fit);
+        if (rc) return rc;
+        if (comm && comm->nranks > 1) {
+            rc = allreduce_device(comm, t->d_devsum, t->natoms, t->stream, t->d_status);
+            if (rc) return rc;
+        }
+        const auto ti1 = now();
+        rc = launch_lovo_controller(t, c);
+        if (rc) return rc;
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+        const LovoDevState st = hst[0];
+        if (timing) fprintf(stderr, "[gcb] lovo_resident: iteration %d: launches %.1f us, until the state is back %.1f us (setup before the loop %.1f us)\n",
+                            it, us(ti0, ti1), us(ti0, now()), it == 0 ? us(t_enter, tl0) : 0.0);
+        if (st.dev_status != 0) return peratom_finish(t);     // SVD failure or exchange timeout: the usual message, status word cleared
+        if (st.err == LOVO_ERR_VALUES) return 1;   // nothing of the template was touched
+        if (st.err == LOVO_ERR_MINIMUM_N) {
+            set_error("align.mobileLimit: fewer candidate atoms than MinimumN; the reference would loop forever here (lovo.go:177-186)");
+            return GCB_ERR_ARG;
+        }
+        if (st.err == LOVO_ERR_BOUNDS) { set_error("align.LOVO: slice bounds out of range (n outside the candidate list)"); return GCB_ERR_ARG; }
+        n_fit = st.n;
+        if (st.converged) break;
+        if (st.itercount >= max_iter) { set_error("align.LOVO: no convergence after %d iterations", st.itercount); return GCB_ERR_ARG; }
+    }
+    const LovoDevState st = hst[0];
+    *n_out = st.n;
+    *iterations_out = st.itercount;
+    if (disagreement_out) *disagreement_out = st.disagreement;
+    // candidate positions -> atoms; the three arrays sit next to one another in the workspace: one copy
+    {
+        const size_t span = oVals + sizeof(double) * (size_t)ncand - oOld;
+        std::vector<unsigned char> back(span);
+        GCB_CUDA(cudaMemcpy(back.data(), w + oOld, span, cudaMemcpyDeviceToHost));
+        const int* h_old = (const int*)back.data();
+        const int* h_ids = (const int*)(back.data() + (oIds - oOld));
+        for (int k = 0; k < ncand; k++) { indexesold_out[k] = cand[h_old[k]]; ids_out[k] = cand[h_ids[k]]; }
+        memcpy(vals_out, back.data() + (oVals - oOld), sizeof(double) * (size_t)ncand);
+    }
+    if (timing) fprintf(stderr, "[gcb] lovo_resident: whole call %.1f us\n", us(t_enter, now()));
+    return GCB_OK;
+}
+
 int gcb_peratom_dev_sum_atoms(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, const int* want,
                               int nwant, gcb_comm* comm, double* sum_want) {
     if (!t) { set_error("NULL trajectory handle"); return GCB_ERR_ARG; }

@@ -150,6 +150,9 @@ struct gcb_traj {
     size_t epart_bytes = 0;
     double* d_pdist = nullptr;                     // gcb_peratom_dist output scratch
     size_t pdist_cap = 0;
+    void* d_lovo_ws = nullptr;                     // gcb_lovo_resident: candidates, sorted ids / values, template copy, state
+    size_t lovo_ws_bytes = 0;
+    void* h_lovo = nullptr;                        // ... and the 64 bytes the host reads back per iteration (mapped pinned memory)
 };
 
 // NCCL communicator wrapper (comm.cu) plus the peer-mapped row blocks of the multi-GPU all-pairs matrix
@@ -173,6 +176,42 @@ struct gcb_comm {
 };
 
 namespace gcb {
+// ---- align.LOVO's bookkeeping on the device (lovo_ctl.cu) ----
+enum { LOVO_ERR_VALUES = 1,       // a mean that is negative or not a number, or a fit on no atoms: the host mirror takes over
+       LOVO_ERR_MINIMUM_N = 2,    // mobileLimit cannot reach MinimumN (the reference loops forever, lovo.go:177-186)
+       LOVO_ERR_BOUNDS = 3 };     // n outside the candidate list (a slice panic in the reference)
+struct LovoDevState {
+    int n, itercount, disagreement, converged, err, dev_status;
+    double prevlim, newlim;
+    long pad[3];
+};
+static_assert(sizeof(LovoDevState) == 64, "the host reads this back whole");
+struct LovoCtl {
+    const double* devsum;   // per-atom sums over all selected frames (all ranks)
+    double total;           // frames behind those sums
+    const int* cand;        // candidate atoms (ascending), ncand of them
+    int ncand;
+    int* old;               // indexesold as candidate positions
+    int* ids;               // sorted candidate positions of this iteration
+    double* vals;           // their means
+    LovoDevState* st;       // device copy of the state
+    LovoDevState* host;     // mapped pinned copy the host reads
+    double less_than;
+    int minimum_n;
+    const double* ref_aos;  // template, natoms x 3
+    int natoms, np;
+    double* refc;           // next pass: centred template planes, 3 * np
+    double* weight;         // next pass: 0 / 1 per atom
+    const int* status;      // the trajectory's status word (SVD failure, exchange timeout)
+};
+int lovo_ctl_slots();   // the most candidates the device loop takes
+int launch_lovo_controller(gcb_traj* t, const LovoCtl& c);       // rank kernel + controller: after a pass
+int launch_lovo_first_template(gcb_traj* t, const LovoCtl& c);   // before the first pass
+// api.cu: one per-atom-distance pass over the template the controller left on the device (cluster kernel only)
+bool peratom_prepared_supported(gcb_traj* t);
+int peratom_prepared(gcb_traj* t, long first, long nframes, int n_fit);
+int peratom_local(gcb_traj* t, long first, long nframes, const double* ref_aos, const int* idx, int nidx, int write_back);
+int peratom_finish(gcb_traj* t);
 // frame-range dependencies between uploads and kernels (api.cu)
 int deps_before_compute(gcb_traj* t, long first, long nframes);   // the compute stream waits for pending uploads into [first, first+n)
 int deps_after_compute(gcb_traj* t, long first, long nframes);    // remembers that queued work uses [first, first+n)

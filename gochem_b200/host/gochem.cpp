@@ -1004,6 +1004,16 @@ bool LovoState::Step(const std::vector<double>& rmsd, Error* err) {
     return false;
 }
 
+void LovoState::Restore(std::vector<int> indexesold, std::vector<int> ids, std::vector<double> vals, int n, int iterations, int disagreement) {
+    indexesold_ = std::move(indexesold);
+    ids_ = std::move(ids);
+    vals_ = std::move(vals);
+    n_ = n;
+    itercount_ = iterations;
+    disagreement_ = disagreement;
+    fit_.assign(indexesold_.begin(), indexesold_.begin() + n_);
+}
+
 void LovoState::Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const {
     // RMSD.SortBy("molid") (:254): stable by candidate atom index
     // the ids are the candidate atoms, each once: when the candidate list is ascending (res2atoms walks the atoms in order) the
@@ -1444,6 +1454,23 @@ Error LOVOResident(const chem::Atomer& mol, const v3::Matrix& ref, std::unique_p
     LovoState st(fullindexes, o->lessThanRMSD_, o->minimumN_);
     std::vector<double> rmsd;
     const bool dbg = getenv("GCH_DEBUG") != nullptr;
+    // The whole iteration in the library, bookkeeping on the device (gcb_lovo_resident), when nothing needs the host in between:
+    // no aligned trajectory to write, the exchange (if any) through the library's communicator.  1 = not taken: the loop below.
+    const bool host_loop = getenv("GCH_LOVO_HOST") != nullptr;   // tests compare the two
+    if (!host_loop && !dbg && printtraj.empty() && !fullindexes.empty() && (o->comm_ || !o->allreduce_) && ref.NVecs() == d->Natoms()) {
+        const size_t nc = fullindexes.size();
+        std::vector<int> old(nc), ids(nc);
+        std::vector<double> vals(nc);
+        int n = 0, iters = 0, dis = 0;
+        const int rc = gcb_lovo_resident(d->Handle(), 0, d->LocalFrames(), ref.data(), fullindexes.data(), (int)nc, (double)d->SelectedFrames(),
+                                         o->lessThanRMSD_, o->minimumN_, o->maxIter_, o->comm_, &n, &iters, &dis, old.data(), ids.data(), vals.data());
+        if (rc == 0) {
+            st.Restore(std::move(old), std::move(ids), std::move(vals), n, iters, dis);
+            st.Finish(mol, (int)d->SelectedFrames(), out);
+            return Error();
+        }
+        if (rc != 1) return deviceError(rc, "LOVO");
+    }
     for (;;) {
         if (dbg) fprintf(stderr, "[LOVO] iteration %d, fit on %zu atoms, local frames %ld\n", st.Iterations(), st.FitIndexes().size(), d->LocalFrames());
         if (st.Disagreement() == 1 && !printtraj.empty()) o->writeTraj_ = printtraj;  // :226-228

@@ -462,6 +462,8 @@ class LovoState {
     int Disagreement() const { return disagreement_; }
     int Iterations() const { return itercount_; }
     void Finish(const chem::Atomer& mol, int framesRead, LOVOReturn* out) const;
+    // state after a loop that ran on the device (gcb_lovo_resident): what Finish reads
+    void Restore(std::vector<int> indexesold, std::vector<int> ids, std::vector<double> vals, int n, int iterations, int disagreement);
 
   private:
     std::vector<int> full_, indexesold_, fit_, ids_;
@@ -482,6 +484,7 @@ class DeviceTrajectory {
     static std::unique_ptr<DeviceTrajectory> Adopt(gcb_traj* t, int natoms, long nlocal, long nselected_total);
     long LocalFrames() const { return nlocal_; }
     long SelectedFrames() const { return nselected_; }
+    int Natoms() const { return natoms_; }
     gcb_traj* Handle() { return t_; }
     // one RMSDTraj pass over the resident frames: per-atom mean deviations over ALL selected frames (all ranks)
     // only != nullptr: the caller reads the means of these atoms alone (align.LOVO: its candidates, lovo.go:519-528); when they

@@ -159,6 +159,21 @@ int gcb_peratom_dev_sum(gcb_traj *t, long first, long nframes, const double *ref
 int gcb_peratom_dev_sum_atoms(gcb_traj *t, long first, long nframes, const double *ref_aos, const int *idx, int nidx,
                               const int *want, int nwant, gcb_comm *comm, double *sum_want);
 
+/* ---- align.LOVO's fixed-point iteration over resident frames (align/lovo.go:212-252), bookkeeping on the device ----
+ * Runs RMSDTraj passes (fit on the current subset of the candidate atoms `cand`, ascending, per-atom mean deviations of all
+ * atoms over total_frames frames, sums combined across the ranks of comm when given) until the subset below less_than_rmsd
+ * repeats.  Between two passes one CTA does what lovo.go:229-252 does on the host -- rmsdFilter, sort.Stable by value,
+ * mobileLimit, sameElementsInt / approxEq, disagreementInt -- and prepares the next template in place; the host reads 64 bytes
+ * per iteration.  Outputs (ncand entries each but the scalars): n and iterations (LOVOReturn.N, .Iterations), the last
+ * disagreement, indexesold (atoms; its first n entries are LOVOReturn.Natoms), ids / vals = the candidates and their mean
+ * deviations in the order of the last sort (LOVOReturn.RMSD is vals re-ordered by atom).
+ * Returns 0, a GCB_ERR_*, or 1 = not taken (more than 16384 candidates, candidates not ascending or at most an eighth of the
+ * frame, frames that do not go to the cluster kernel, values the host must sort): run the loop on the host with
+ * gcb_peratom_dev_sum then -- the answers are the same bit for bit. */
+int gcb_lovo_resident(gcb_traj *t, long first, long nframes, const double *ref_aos, const int *cand, int ncand,
+                      double total_frames, double less_than_rmsd, int minimum_n, int max_iter, gcb_comm *comm, int *n_out,
+                      int *iterations_out, int *disagreement_out, int *indexesold_out, int *ids_out, double *vals_out);
+
 /* ---- all-pairs frame RMSD matrix (BASELINE configs[3]) ----
  * D[i][j] = chem.RMSD(frame_i, frame_j) over the atoms in idx (NULL = all), no superposition inside (geometric.go:
  * 232-288; superpose first with gcb_super_rmsd(write_back = 1)).  Computed as one fp64 tensor-core GEMM (DMMA) on
