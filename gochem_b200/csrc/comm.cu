@@ -476,7 +476,7 @@ int gcb_lovo_resident(gcb_traj* t, long first, long nframes, const double* ref_a
         GCB_CUDA(cudaMalloc(&t->d_lovo_ws, off));
         t->lovo_ws_bytes = off;
     }
-    if (!t->h_lovo) GCB_CUDA(cudaHostAlloc(&t->h_lovo, 2 * sizeof(LovoDevState) + sizeof(int) * (size_t)lovo_ctl_slots(), cudaHostAllocMapped));
+    if (!t->h_lovo) GCB_CUDA(cudaHostAlloc(&t->h_lovo, 2 * sizeof(LovoDevState) + 768 + (3 * sizeof(int) + sizeof(double)) * (size_t)lovo_ctl_slots(), cudaHostAllocMapped));
     unsigned char* w = (unsigned char*)t->d_lovo_ws;
     LovoDevState* hst = (LovoDevState*)t->h_lovo;            // [0]: what the controller reports; [1]: the initial state, staged
     int* h_iota = (int*)(hst + 2);
@@ -549,13 +549,14 @@ int gcb_lovo_resident(gcb_traj* t, long first, long nframes, const double* ref_a
     if (disagreement_out) *disagreement_out = st.disagreement;
     // candidate positions -> atoms; the three arrays sit next to one another in the workspace: one copy
     {
-        const size_t span = oVals + sizeof(double) * (size_t)ncand - oOld;
-        std::vector<unsigned char> back(span);
-        GCB_CUDA(cudaMemcpy(back.data(), w + oOld, span, cudaMemcpyDeviceToHost));
-        const int* h_old = (const int*)back.data();
-        const int* h_ids = (const int*)(back.data() + (oIds - oOld));
+        const size_t span = oVals + sizeof(double) * (size_t)ncand - oOld;   // <= (4 + 4 + 8) * ncand + 2 * 255 bytes of padding
+        unsigned char* back = (unsigned char*)(h_iota + lovo_ctl_slots());     // pinned: the copy is one short DMA
+        GCB_CUDA(cudaMemcpyAsync(back, w + oOld, span, cudaMemcpyDeviceToHost, t->stream));
+        GCB_CUDA(cudaStreamSynchronize(t->stream));
+        const int* h_old = (const int*)back;
+        const int* h_ids = (const int*)(back + (oIds - oOld));
         for (int k = 0; k < ncand; k++) { indexesold_out[k] = cand[h_old[k]]; ids_out[k] = cand[h_ids[k]]; }
-        memcpy(vals_out, back.data() + (oVals - oOld), sizeof(double) * (size_t)ncand);
+        memcpy(vals_out, back + (oVals - oOld), sizeof(double) * (size_t)ncand);
     }
     if (timing) fprintf(stderr, "[gcb] lovo_resident: whole call %.1f us\n", us(t_enter, now()));
     return GCB_OK;
