@@ -17,6 +17,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kabsch3.cuh"
 #include "ptx.cuh"
@@ -159,16 +161,19 @@ constexpr size_t kStageBytes = (size_t)(BM + BN) * TK * sizeof(double);   // 32 
 constexpr size_t kTmaSmem = TSTAGES * kStageBytes + 1024;  // + room to align the ring to 1024 bytes (swizzle atom)
 static_assert(64 * TLD * sizeof(double) <= TSTAGES * kStageBytes, "the epilogue staging buffer reuses the stage ring");
 
-// The main loop shared by both GEMM kernels: C (TM x TM, this warp's 8 MI x 8 NI part in acc) += A_rows . B_rows^T over kdim,
-// operands fetched with the tensor map (box = TM rows x TK doubles) into ring (1024-byte aligned, TSTAGES stages of 2 boxes).
+// The main loop shared by the GEMM kernels: C (TMA x TMB, this warp's 8 MI x 8 NI part in acc) += A_rows . B_rows^T over kdim,
+// operands fetched with the tensor maps (boxes of TMA resp. TMB rows x TK doubles) into ring (1024-byte aligned, TSTAGES stages
+// of the two boxes).
 // Eight warps as 2 x 4; thread 0 is also the producer.  full / empty: TSTAGES mbarriers each, initialised by the caller
 // (full: 1 arrival + bytes, empty: 8 arrivals).  Returns when every warp has consumed every stage (no trailing barrier).
-template <int TM, int MI, int NI>
-__device__ __forceinline__ void tma_dmma_mainloop(const CUtensorMap* tmap, unsigned char* ring, uint64_t* full, uint64_t* empty, int rowA, int rowB,
-                                                  int kdim, double (&acc)[MI][NI][2]) {
+template <int TMA, int TMB, int MI, int NI>
+__device__ __forceinline__ void tma_dmma_mainloop(const CUtensorMap* tmapA, const CUtensorMap* tmapB, unsigned char* ring, uint64_t* full,
+                                                  uint64_t* empty, int rowA, int rowB, int kdim, double (&acc)[MI][NI][2]) {
     using namespace ptx;
-    constexpr uint32_t kBox = (uint32_t)TM * TK * sizeof(double);
-    constexpr uint32_t kStage = 2 * kBox;
+    constexpr uint32_t kBox = (uint32_t)TMA * TK * sizeof(double);      // the A box; B follows it in a stage
+    constexpr uint32_t kBoxB = (uint32_t)TMB * TK * sizeof(double);
+    constexpr uint32_t kStage = kBox + kBoxB;
+    static_assert(kBox % 1024 == 0 && kStage % 1024 == 0, "boxes start on swizzle atoms");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, t = lane & 3;
@@ -191,13 +196,14 @@ __device__ __forceinline__ void tma_dmma_mainloop(const CUtensorMap* tmap, unsig
     auto issue = [&]() {
         unsigned char* st = ring + (size_t)ps * kStage;
         mbar_arrive_expect_tx(&full[ps], kStage);
-        tma_load_2d(st, tmap, pk * TK, rowA, &full[ps]);
-        tma_load_2d(st + kBox, tmap, pk * TK, rowB, &full[ps]);
+        tma_load_2d(st, tmapA, pk * TK, rowA, &full[ps]);
+        tma_load_2d(st + kBox, tmapB, pk * TK, rowB, &full[ps]);
         pk++;
         if (++ps == TSTAGES) { ps = 0; pph ^= 1u; }
     };
     if (producer) {
-        prefetch_tensormap(tmap);
+        prefetch_tensormap(tmapA);
+        if (tmapB != tmapA) prefetch_tensormap(tmapB);
         while (pk < nk && pk < TSTAGES) issue();     // the ring starts empty
     }
     int s = 0;
@@ -263,7 +269,7 @@ allpairs_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nf
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    tma_dmma_mainloop<BM, AP_MI, 4>(&tmap, ring, full, empty, (int)i0, (int)j0, kdim, acc);
+    tma_dmma_mainloop<BM, BN, AP_MI, 4>(&tmap, &tmap, ring, full, empty, (int)i0, (int)j0, kdim, acc);
     __syncthreads();   // every warp is done with the ring (all TMA writes were waited for): reuse it as the staging buffer
     // epilogue: D^2 = (n_i + n_j - 2 g_ij) / n, both triangles
     double* sT = reinterpret_cast<double*>(ring);   // [64][TLD]
@@ -323,6 +329,92 @@ allpairs_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, long nf
             }
         }
         __syncthreads();
+    }
+}
+
+// The same block computation for HALF a block: rows [64 hx, 64 hx + 64) x columns [128 by, 128 by + 128), eight warps of 32 x 32.
+// A rank's share of the blocks rarely fills its last wave of CTAs (1550 blocks on 148 SMs: the eleventh wave is 70 blocks); cutting
+// those blocks in two makes it one wave of half the length.  Every element still adds the same products in the same order
+// (the k order inside a stage depends on the lane's place in its MMA quad only), so the matrix does not change by a bit.
+constexpr int HM = 64;
+constexpr size_t kHalfStageBytes = (size_t)(HM + BN) * TK * sizeof(double);   // 24 KB
+constexpr size_t kHalfSmem = TSTAGES * kHalfStageBytes + 1024;
+static_assert(HM * TLD * sizeof(double) <= TSTAGES * kHalfStageBytes, "the epilogue staging buffer reuses the stage ring");
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+allpairs_dmma_half_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int kdim, long nframes,
+                          const double* __restrict__ norms, double inv_n, const int2* __restrict__ tiles, const PeerOut po, long ldd,
+                          double floor_rel, PairList redo) {
+    using namespace ptx;
+    static_assert(AP_WARPS == 8, "half blocks are written for eight warps");
+    extern __shared__ unsigned char smem_raw_ap[];
+    __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_ap) + 1023) & ~(uintptr_t)1023);
+    const int2 tile = tiles[blockIdx.x];            // x: half-block row (64 frames), y: block column (128 frames)
+    const long i0 = (long)tile.x * HM, j0 = (long)tile.y * BN;
+    const bool diagonal = (tile.x >> 1) == tile.y;  // the two halves of a diagonal block cover each other's mirror image
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;        // 2 x 4 warps -> 32 x 32 warp tiles
+    const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], AP_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    tma_dmma_mainloop<HM, BN, 4, 4>(&tmapA, &tmapB, ring, full, empty, (int)i0, (int)j0, kdim, acc);
+    __syncthreads();
+    double* sT = reinterpret_cast<double*>(ring);   // [64][TLD]
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const long i = i0 + wm * 32 + mi * 8 + g;
+        const double ni_ = i < nframes ? norms[i] : 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = wn * 32 + ni * 8 + 2 * t + e;
+                const long j = j0 + c;
+                double d = 0.0;
+                if (i < nframes && j < nframes && i != j) {
+                    const double nj_ = norms[j];
+                    const double d2 = (ni_ + nj_ - 2.0 * acc[mi][ni][e]) * inv_n;
+                    if (d2 < floor_rel * (ni_ + nj_) * inv_n && j > i) {
+                        const unsigned int slot = atomicAdd(redo.count, 1u);
+                        if (slot < redo.cap) redo.pairs[slot] = make_uint2((unsigned int)i, (unsigned int)j);
+                    }
+                    d = sqrt(d2 > 0.0 ? d2 : 0.0);
+                }
+                sT[(wm * 32 + mi * 8 + g) * TLD + c] = d;
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < HM; r += AP_WARPS) {          // rows of the half block: 128 contiguous doubles each
+        const long i = i0 + r;
+        if (i >= nframes) break;
+        double* dst = peer_row(po, i, ldd);
+        if (!dst) continue;
+        dst += j0;
+#pragma unroll
+        for (int c = lane; c < BN; c += 32)
+            if (j0 + c < nframes) dst[c] = sT[r * TLD + c];
+    }
+    if (!diagonal) {                                      // mirror image: rows j of the matrix, 64 contiguous doubles each
+        for (int c = warp; c < BN; c += AP_WARPS) {
+            const long j = j0 + c;
+            if (j >= nframes) break;
+            double* dst = peer_row(po, j, ldd);
+            if (!dst) continue;
+            dst += i0;
+#pragma unroll
+            for (int r = lane; r < HM; r += 32)
+                if (i0 + r < nframes) dst[r] = sT[r * TLD + c];
+        }
     }
 }
 
@@ -434,7 +526,7 @@ allpairs_fit_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int kdim, lon
 #pragma unroll
         for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
     // rows of Z are coordinate planes: frame f owns rows 3f .. 3f+2; rows beyond 3 * nframes arrive as zeros
-    tma_dmma_mainloop<FM, 6, 3>(&tmap, ring, full, empty, (int)(3 * fi0), (int)(3 * fj0), kdim, acc);
+    tma_dmma_mainloop<FM, FM, 6, 3>(&tmap, &tmap, ring, full, empty, (int)(3 * fi0), (int)(3 * fj0), kdim, acc);
     __syncthreads();   // everyone is done with the ring: reuse it for the C tile
     double* smem = reinterpret_cast<double*>(ring);
     double* sC = smem;  // [FM][FLDC]
@@ -583,6 +675,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
     const int tile_frames = fit ? FT : BM;
     const int nt = (int)((nframes + tile_frames - 1) / tile_frames);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    size_t nfull = 0, nhalf = 0;   // blocks of the GEMM launch, half blocks of its split last wave
 #define AP_TRY(call)                                                                              \
     do {                                                                                          \
         cudaError_t e__ = (call);                                                                 \
@@ -596,7 +689,7 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
         // one workspace per trajectory handle, grown on demand and kept: no cudaMalloc / cudaFree (both synchronise the
         // device) inside repeated calls
         const size_t ybytes = sizeof(double) * (size_t)nframes * (size_t)(fit ? 3 * ld : ld);
-        const size_t ntile_max = (size_t)nt * ((size_t)nt + 1) / 2 + 1;
+        const size_t ntile_max = (size_t)nt * ((size_t)nt + 1) / 2 + 1 + (size_t)t->sm_count;   // + the halves of a split last wave
         size_t off = 0;
         auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
         const size_t oY = carve(ybytes), oX = carve(d_idx ? ybytes : 0), oMu = carve(sizeof(double) * (size_t)kdim),
@@ -665,6 +758,23 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
             }
     }
     if (tiles.empty()) tiles.push_back(make_int2(nt, nt));   // a block outside the matrix: nothing is stored
+    // A last wave that fills at most half of the SMs is computed as half blocks (allpairs_dmma_half_kernel): one wave of half the
+    // length instead of a whole one.  The full blocks come first in the list, the halves after them.
+    nfull = tiles.size();
+    nhalf = 0;
+    if (!fit && AP_WARPS == 8 && !getenv("GCB_AP_NO_SPLIT")) {   // the variable is for tests: both ways give the same bits
+        const size_t sms = (size_t)t->sm_count, rem = tiles.size() % sms;
+        if (tiles.size() > sms && rem > 0 && 2 * rem <= sms) {
+            nfull = tiles.size() - rem;
+            std::vector<int2> halves;
+            for (size_t k = nfull; k < tiles.size(); k++)
+                for (int h = 0; h < 2; h++)
+                    if ((long)(2 * tiles[k].x + h) * HM < nframes) halves.push_back(make_int2(2 * tiles[k].x + h, tiles[k].y));
+            tiles.resize(nfull);
+            tiles.insert(tiles.end(), halves.begin(), halves.end());
+            nhalf = halves.size();
+        }
+    }
     AP_TRY(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
     AP_TRY(cudaEventCreate(&e0));
     AP_TRY(cudaEventCreate(&e1));
@@ -688,10 +798,21 @@ static int allpairs_device(gcb_traj* t, long first, long nframes, const int* d_i
         rc = make_tensor_map(&tmap, Y, (unsigned long long)kdim, (unsigned long long)nframes, (unsigned long long)ld * sizeof(double));
         if (rc) goto done;
         AP_TRY(opt_in_smem(allpairs_dmma_kernel, t->dev));
+        CUtensorMap tmap_half;
+        if (nhalf) {
+            rc = make_tensor_map(&tmap_half, Y, (unsigned long long)kdim, (unsigned long long)nframes, (unsigned long long)ld * sizeof(double), HM);
+            if (rc) goto done;
+            AP_TRY(opt_in_smem(allpairs_dmma_half_kernel, t->dev));
+        }
         AP_TRY(cudaEventRecord(e0, s));
-        allpairs_dmma_kernel<<<(unsigned)tiles.size(), kTmaThreads, kTmaSmem, s>>>(tmap, kdim, nframes, norms, 1.0 / (double)natoms_used,
-                                                                                   d_tiles, po, nframes, 1e-7, redo);
+        allpairs_dmma_kernel<<<(unsigned)nfull, kTmaThreads, kTmaSmem, s>>>(tmap, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                            d_tiles, po, nframes, 1e-7, redo);
         GCB_LAUNCHED();
+        if (nhalf) {
+            allpairs_dmma_half_kernel<<<(unsigned)nhalf, kTmaThreads, kHalfSmem, s>>>(tmap_half, tmap, kdim, nframes, norms, 1.0 / (double)natoms_used,
+                                                                                      d_tiles + nfull, po, nframes, 1e-7, redo);
+            GCB_LAUNCHED();
+        }
         AP_TRY(cudaEventRecord(e1, s));
         redo_pairs_kernel<<<t->sm_count * 4, 256, 0, s>>>(Y, ld, kdim, 1.0 / (double)natoms_used, redo, po, nframes);
         GCB_LAUNCHED();

@@ -414,6 +414,31 @@ def test_allpairs_rmsd_matrix(natoms, nframes):
     t.close()
 
 
+def test_allpairs_last_wave_as_half_blocks_is_bit_identical():
+    """17 block rows = 153 blocks: on 148 SMs the last wave (5 blocks) is computed as half blocks of 64 x 128
+    (allpairs_dmma_half_kernel).  Same bits as without the split, and the rows agree with numpy; the last block row holds 52
+    frames only, so the lower half of its diagonal block lies outside the matrix."""
+    natoms, nframes = 40, 2100
+    ref, frames = synth.make_case(natoms, nframes)
+    frames[2099] = frames[11] + 1e-7
+    t = device_traj(frames)
+    t.super_rmsd(ref, write_back=True)
+    aligned = t.download()
+    got, _, redone = t.allpairs_rmsd()
+    os.environ["GCB_AP_NO_SPLIT"] = "1"
+    try:
+        plain, _, _ = t.allpairs_rmsd()
+    finally:
+        del os.environ["GCB_AP_NO_SPLIT"]
+    assert np.array_equal(got, plain)
+    assert np.array_equal(got, got.T) and (np.diag(got) == 0).all() and redone >= 1
+    for i in (0, 63, 64, 127, 1990, 2047, 2048, 2099):
+        d = aligned - aligned[i][None]
+        want = np.sqrt((d * d).sum(axis=(1, 2)) / natoms)
+        assert np.abs(got[i] - want).max() < 1e-9
+    t.close()
+
+
 @pytest.mark.parametrize("fit", [False, True])
 def test_allpairs_sharded_entry_single_rank(fit):
     """The multi-GPU entry point with a one-rank communicator: same tiles, same owner-directed epilogue, one owner."""
