@@ -322,6 +322,8 @@ def sub_lovo(a, d, comm, dev, peak):
     ach = alg / (pass_ms * 1e-3) / 1e9
     rec = {"workload": f"align.LOVO, {total} frames x {natoms} atoms (BASELINE configs[2]), frames sharded x{d.world}, "
                        "lessThanRMSD 1.0, minimumN 10, chunk 8",
+           "loop": "gcb_lovo_resident: the iteration's bookkeeping (rmsdFilter, stable order, mobileLimit, set comparison, next template) "
+                   "on the device, 64 bytes back per iteration; bit-identical to the host loop (tests/test_gpu_lovo_device.py)",
            "lovo_ms_best_of_3": best * 1e3, "lovo_ms_runs": [r * 1e3 for r in runs], "iterations": got["Iterations"], "N": got["N"],
            "natoms_crc32": zlib.crc32(np.ascontiguousarray(got["Natoms"], dtype=np.int32).tobytes()),
            "frames_per_s_per_iteration": total * got["Iterations"] / best,
