@@ -98,8 +98,13 @@ using namespace ptx;
 #ifdef GCB_TRACE
 __device__ long long g_trace[8][512];
 #define TRACE(row, j) do { if (blockIdx.x == 0 && (j) < 512) g_trace[row][j] = clock64(); } while (0)
+#ifndef GCB_TRACE_WARP
+#define GCB_TRACE_WARP 0      // the consumer warp whose times rows 4..7 hold
+#endif
+#define TRACE_TID (32 * GCB_TRACE_WARP)
 #else
 #define TRACE(row, j) do {} while (0)
+#define TRACE_TID 0
 #endif
 
 template <int NSLOTS, int W>
@@ -457,9 +462,9 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
 #pragma unroll
                 for (int k = 0; k < 12; k++) acc[k] = 0.0;
                 double aa0 = 0.0, aa1 = 0.0;   // sum w |a|^2 for the one-pass RMSD
-                if (tid == 0) TRACE(4, j);
+                if (tid == TRACE_TID) TRACE(4, j);
                 mbar_wait(&sh.full[s1], ph1);
-                if (tid == 0) TRACE(5, j);
+                if (tid == TRACE_TID) TRACE(5, j);
                 const double* sx = stage_base + (long)s1 * kStageDoubles + tbase;
                 const double* sy = sx + K * kConsumers;
                 const double* sz = sy + K * kConsumers;
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
                     }
                 }
                 __syncwarp();   // the lanes' stores to red[] are ordered before lane 0's release below; the scratch is free again
-                if (tid == 0) TRACE(7, j);
+                if (tid == TRACE_TID) TRACE(7, j);
                 if (lane == 0) mbar_arrive(&sh.red_full[slot1]);   // release: the warp's stores to red[] (ordered by the __syncwarp above)
                 if (++s1 == S) { s1 = 0; ph1 ^= 1u; }
                 if (++slot1 == NS) slot1 = 0;
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
             if (j >= D) {
                 // ---- pass 2 of local frame j - D ----
                 mbar_wait(&sh.solved[slot2], ph2);
-                if (tid == 0) TRACE(6, j - D);
+                if (tid == TRACE_TID) TRACE(6, j - D);
                 double e = 0.0;
                 const bool run_pass2 = cp.always_explicit || sh.xf[slot2][12] != 0.0;   // warp-uniform
                 if (!run_pass2) {
