@@ -65,7 +65,7 @@ def build_host(force: bool = False) -> str:
     host = os.path.join(HERE, "host")
     srcs = [os.path.join(host, f) for f in ("gochem.cpp", "capi.cpp", "stf.cpp")]
     deps = srcs + [os.path.join(host, "gochem.hpp"), os.path.join(HERE, "..", "include", "gochem_host.h"),
-                   os.path.join(HERE, "..", "include", "gochem_b200.h")]
+                   os.path.join(HERE, "..", "include", "gochem_b200.h"), os.path.join(CSRC, "kabsch3.cuh")]   # capi.cpp compiles the solver for the host
     if force or _stale(HOST_LIB, deps):
         cmd = [CXX, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-o", HOST_LIB, *srcs,
                "-L" + LIB_DIR, "-lgochem_b200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz", "-ldl"]
