@@ -102,16 +102,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 // sqrt of a non-negative double from the hardware reciprocal-square-root seed and one correction of cubic order (relative
-// error < 2^-58; derivation at fast_sqrt in super_cluster.cu).  Zero and denormal arguments return 0.
+// error < 2^-58; derivation at fast_sqrt_pos in super_cluster.cu: five operations).  Zero and denormal arguments return 0.
 __device__ __forceinline__ double sqrt_cubic(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double g = x * y;
-    const double h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    const double p = fma(1.5, r, 1.0);
-    const double gr = g * r;
-    const double out = fma(gr, p, g);
+    const double e = fma(-g, y, 1.0);
+    const double c = fma(e, 0.375, 0.5);
+    const double out = fma(g, e * c, g);
     return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
 }
 

@@ -125,21 +125,21 @@ constexpr size_t fixed_smem_w(bool resident) {
 }
 constexpr size_t fixed_smem(bool resident, int W) { return W == kDevWarps ? fixed_smem_w<kDevWarps>(resident) : fixed_smem_w<kDefaultWarps>(resident); }
 
-// sqrt of a positive double with a short dependency chain.  y0 = hardware reciprocal-square-root seed (relative
-// error e, |e| < 2^-20).  With g = x y0 = sqrt(x)(1+e), h = y0/2 and r = 1/2 - g h = -(e + e^2/2):
-// 1/(1+e) = (1-2r)^(-1/2) = 1 + r + 3/2 r^2 + O(r^3), so sqrt(x) = g + g r (1 + 3/2 r) with relative error 2.5 |e|^3 <
-// 2^-58 -- one correction of cubic order, four dependent fp64 operations after the seed (six in all) instead of two Newton
-// steps.  The argument must be bounded away from zero (a zero or denormal gives seed = inf): the caller folds 1e-290 into the
-// sum of squares, which moves the square root by less than 1e-145 and saves the three integer instructions of a guard.
+// sqrt of a positive double in five fp64 operations after the hardware seed.  y = reciprocal-square-root seed (relative error
+// eps, |eps| < 2^-20), g = x y = sqrt(x) (1 + eps), e = 1 - g y = -(2 eps + eps^2); since (1 - e)^(-1/2) = 1 + e/2 + 3 e^2/8 + O(e^3),
+// sqrt(x) = g (1 + e (1/2 + 3/8 e)) with relative error ~2.5 |eps|^3 < 2^-58 before rounding -- one correction of cubic order.
+// (Round 1 wrote the same correction in six operations; this pass is bound by the schedulers' issue ports, two cycles per fp64
+// instruction, so the sixth cost 2 % of it: profiles/r2_tuning.md, section 12.)  The argument must be bounded away from zero (a
+// zero or denormal gives seed = inf): the caller folds 1e-290 into the sum of squares, which moves the square root by less than
+// 1e-145 and saves the three integer instructions of a guard.
 __device__ __forceinline__ double fast_sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double g = x * y;
-    const double h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    const double p = fma(1.5, r, 1.0);
-    const double gr = g * r;
-    return fma(gr, p, g);
+    const double e = fma(-g, y, 1.0);
+    const double c = fma(e, 0.375, 0.5);
+    const double ec = e * c;
+    return fma(g, ec, g);
 }
 
 // Slot k of a consumer thread <-> atom of the CTA's part.  With an even K a thread owns PAIRS of neighbouring atoms (2 tid and

@@ -51,9 +51,9 @@ struct SmallShared {
 __device__ __forceinline__ double small_sqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double g = x * y, h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    const double out = fma(g * r, fma(1.5, r, 1.0), g);
+    const double g = x * y;
+    const double e = fma(-g, y, 1.0);
+    const double out = fma(g, e * fma(e, 0.375, 0.5), g);
     return (__double2hiint(x) < 0x00200000) ? 0.0 : out;
 }
 
