@@ -107,3 +107,35 @@ def test_host_mirror_gives_the_same_answer_through_either_loop():
     assert dev["N"] == want["N"] and dev["Iterations"] == want["Iterations"] and list(dev["Natoms"]) == list(want["Natoms"])
     assert np.abs(dev["RMSD"] - want["RMSD"]).max() < 1e-10
     t.close()
+
+
+def test_two_handles_from_two_threads():
+    """The device loop keeps its workspace, staging words and template in the handle: two handles driven from two threads at the
+    same time give what they give one after the other."""
+    import threading
+
+    cases = [(3000, 2000, 0.8), (5000, 1500, 1.0)]
+    handles, refs, serial = [], [], []
+    for natoms, nframes, less in cases:
+        ref, sig = synth.make_reference(natoms), synth.atom_sigmas(natoms)
+        t = _lib.DeviceTraj(natoms, nframes)
+        t.synth_fill(ref, sig, nframes)
+        handles.append(t)
+        refs.append(ref)
+        serial.append(t.lovo_resident(ref, np.arange(natoms, dtype=np.int32), less_than_rmsd=less))
+    out = [None, None]
+
+    def work(k):
+        natoms, _, less = cases[k]
+        for _ in range(5):
+            out[k] = handles[k].lovo_resident(refs[k], np.arange(natoms, dtype=np.int32), less_than_rmsd=less)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for k in range(2):
+        assert out[k]["N"] == serial[k]["N"] and out[k]["Iterations"] == serial[k]["Iterations"]
+        assert np.array_equal(out[k]["indexesold"], serial[k]["indexesold"]) and np.array_equal(out[k]["vals"], serial[k]["vals"])
+        handles[k].close()
