@@ -29,6 +29,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries the one JSON line and nothing else: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+# version banner to stdout when NCCL_DEBUG is set, libraries may print more) and the line is written to the saved descriptor
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 import numpy as np  # noqa: E402
 
 METRIC = "frames/sec superposed+RMSD"
@@ -222,7 +234,7 @@ def run_reference(a):
         "gpu_launches": 0,
         "check": {"rmsd_mean": float(np.mean(rm))},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -777,7 +789,7 @@ def run_ours(a):
         **extra,
     }
     if d.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     comm.close()
     d.close()
 
