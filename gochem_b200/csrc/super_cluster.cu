@@ -12,10 +12,10 @@
 //  * 256 consumer threads (8 warps that never wait for one another) each own K fixed atom slots of
 //    the part.  The centred template b' and the weights of those slots live in REGISTERS for the
 //    whole kernel, so the template costs no shared-memory or L2 bandwidth per frame.
-//  * Pass 1 (S = sum w a, H = sum (w a) b'^T, sum w|a|^2) reads the stage once; a 15-shuffle halving
-//    butterfly gives warp totals; the last warp to arrive adds the 8 warps in fixed order and pushes the
-//    CTA's 13 partial sums to every CTA of the cluster with st.async (data + mbarrier complete_tx in one
-//    DSMEM transaction).
+//  * Pass 1 (S = sum w a, H = sum (w a) b'^T, sum w|a|^2) reads the stage once; each warp transposes its 32 x 13 per-lane
+//    sums through a padded shared-memory scratch (13 stores, 16 loads, one shuffle per lane), leaves its totals in red[slot] and
+//    arrives on the frame's red_full mbarrier; the solver warp that owns the frame adds the 8 warps in a fixed tree and pushes
+//    the CTA's 13 partial sums to every CTA of the cluster with st.async (data + mbarrier complete_tx in one DSMEM transaction).
 //  * Solver warps add the C partials in rank order (bit-identical in every CTA), solve the 3x3
 //    problem (kabsch3.cuh), publish R and centroid*R, and decide where the RMSD comes from: the
 //    inner-product form E = Ga + Gb - 2 tr(R^T H) when its rounding bound moves the RMSD by less than
