@@ -346,10 +346,10 @@ allpairs_dmma_half_kernel(const __grid_constant__ CUtensorMap tmapA, const __gri
                           const double* __restrict__ norms, double inv_n, const int2* __restrict__ tiles, const PeerOut po, long ldd,
                           double floor_rel, PairList redo) {
     using namespace ptx;
-    static_assert(AP_WARPS == 8, "half blocks are written for eight warps");
     extern __shared__ unsigned char smem_raw_ap[];
     __shared__ uint64_t full[TSTAGES], empty[TSTAGES];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_ap) + 1023) & ~(uintptr_t)1023);
+    if (AP_WARPS != 8) return;                      // written for eight warps of 32 x 32; other builds never launch it
     const int2 tile = tiles[blockIdx.x];            // x: half-block row (64 frames), y: block column (128 frames)
     const long i0 = (long)tile.x * HM, j0 = (long)tile.y * BN;
     const bool diagonal = (tile.x >> 1) == tile.y;  // the two halves of a diagonal block cover each other's mirror image
