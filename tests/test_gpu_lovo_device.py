@@ -42,6 +42,8 @@ CASES = [  # natoms, nframes, candidates, lessThanRMSD, minimumN
     (1000, 6000, "even", 0.5, 10),
     (10000, 600, "even", 1.2, 25),     # frames of 10 000 atoms (four CTAs per frame), 5000 candidates
     (12000, 300, "all", 1.0, 10),      # 12 000 candidates: the rank kernel's shared memory beyond 64 KB
+    (3000, 1000, "all", 0.0, 10),      # lessThanRMSD <= 0: mobileLimit is skipped, n stays the whole list (lovo.go:238-240)
+    (3000, 1000, "no5", 5.0, 10),      # every candidate below the limit: n = the whole list
 ]
 
 
