@@ -70,7 +70,12 @@ constexpr int kMaxStages = 8;
 // frame j + NS.)
 constexpr int kMaxSlots = 14;            // >= 2*D+2 with D <= 6, and > kSolverWarps
 constexpr int kResidentSlots = 8;        // plans that keep the part resident run at most D = 3 frames ahead
-constexpr int kRedRow = 33;              // transposition scratch of the per-frame reduction: [13 sums][32 lanes], rows padded by one
+#ifndef GCB_RED_ROW
+#define GCB_RED_ROW 34
+#endif
+constexpr int kRedRow = GCB_RED_ROW;     // transposition scratch of the per-frame reduction: [13 sums][32 lanes], rows padded by two:
+                                         // 16-byte aligned rows (the tree reads them with LDS.128: 8 loads instead of 16) whose
+                                         // starts fall on different bank groups
 // The transposition runs in R rounds of QR sums: one round of 13 with 8 warps; with 12 warps (12 sums: those instances never
 // carry sum w|a|^2) two rounds of 6, so that the scratch of 12 warps still fits beside three resident stages.
 constexpr int red_rounds(int W) { return W > 8 ? 2 : 1; }
@@ -528,8 +533,16 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
                         double v = 0.0;
                         if (ql < QR && r * QR + ql < NQ) {
                             const double* row = tr + ql * kRedRow + (lane & 16);
-                            const double s0 = row[0] + row[1], s1 = row[2] + row[3], s2 = row[4] + row[5], s3 = row[6] + row[7];
-                            const double s4 = row[8] + row[9], s5 = row[10] + row[11], s6 = row[12] + row[13], s7 = row[14] + row[15];
+                            double s0, s1, s2, s3, s4, s5, s6, s7;
+                            if constexpr (kRedRow % 2 == 0) {
+                                const double2* r2 = reinterpret_cast<const double2*>(row);
+                                const double2 u0 = r2[0], u1 = r2[1], u2 = r2[2], u3 = r2[3], u4 = r2[4], u5 = r2[5], u6 = r2[6], u7 = r2[7];
+                                s0 = u0.x + u0.y; s1 = u1.x + u1.y; s2 = u2.x + u2.y; s3 = u3.x + u3.y;
+                                s4 = u4.x + u4.y; s5 = u5.x + u5.y; s6 = u6.x + u6.y; s7 = u7.x + u7.y;
+                            } else {
+                                s0 = row[0] + row[1]; s1 = row[2] + row[3]; s2 = row[4] + row[5]; s3 = row[6] + row[7];
+                                s4 = row[8] + row[9]; s5 = row[10] + row[11]; s6 = row[12] + row[13]; s7 = row[14] + row[15];
+                            }
                             v = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
                         }
                         v += __shfl_down_sync(0xffffffffu, v, 16);
