@@ -266,7 +266,10 @@ __device__ __forceinline__ double pass2_atoms(const double* __restrict__ src, lo
     return e0 + e1;
 }
 
-template <int K, bool MASKED, bool DEV, bool RESIDENT, int W>
+// NOWB: this instance never writes frames back (the per-atom-distance pass of align.RMSDTraj without an aligned trajectory): the
+// write pointer, its per-frame update and the write-back variants of pass 2 are not compiled in -- ~20 instructions per warp and
+// frame of a pass that is bound by issue slots (profiles/r2_tuning.md, section 12).
+template <int K, bool MASKED, bool DEV, bool RESIDENT, int W, bool NOWB = false>
 __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const ClusterParams cp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NS = RESIDENT ? kResidentSlots : kMaxSlots;
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
         uint32_t ph1 = 0, ph2 = 0;                     // parities: full[s1], solved[slot2]
         const long fstep = (long)G * p.frame_stride;
         const double* fr2 = p.frames + cid * p.frame_stride + part0 + tbase;     // frame of pass 2 (global / L2 copy)
-        double* frw = cp.write_back ? (p.frames_rw + cid * p.frame_stride + part0 + tbase) : nullptr;
+        double* frw = (!NOWB && cp.write_back) ? (p.frames_rw + cid * p.frame_stride + part0 + tbase) : nullptr;
         double* ep = cp.epart + (cid * C + rank) * kConsumerWarps + warp;
         const long ep_step = (long)G * C * kConsumerWarps;
         for (int j = 0; j < nloc + D; j++) {
@@ -569,13 +572,13 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
                     }
                 } else if (RESIDENT) {
                     const double* sx = stage_base + (long)s2 * kStageDoubles + tbase;
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, true, W>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    if (!NOWB && frw) e = pass2_atoms<K, MASKED, DEV, true, true, W>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
                     else e = pass2_atoms<K, MASKED, DEV, false, true, W>(sx, K * kConsumers, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.empty[s2]);   // this warp is done reading the stage
                     if (++s2 == S) s2 = 0;
                 } else {
-                    if (frw) e = pass2_atoms<K, MASKED, DEV, true, false, W>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
+                    if (!NOWB && frw) e = pass2_atoms<K, MASKED, DEV, true, false, W>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, frw, p.np, real_mask, in_mask, p.bbar[0], p.bbar[1], p.bbar[2]);
                     else e = pass2_atoms<K, MASKED, DEV, false, false, W>(fr2, p.np, sh.xf[slot2], bx, by, bz, fit_mask, dev, nullptr, p.np, real_mask, in_mask, 0.0, 0.0, 0.0);
                 }
                 if (run_pass2 && !DEV) {
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
                 }
                 ep += ep_step;
                 fr2 += fstep;
-                if (frw) frw += fstep;
+                if (!NOWB && frw) frw += fstep;
                 if (++slot2 == NS) { slot2 = 0; ph2 ^= 1u; }
             }
         }
@@ -679,9 +682,14 @@ bool make_plan(const Tuning& tu, int np, bool heavy, bool dev, Plan* pl) {
     return true;
 }
 
-template <int K, bool WT, bool DV, bool RES, int W>
+template <int K, bool WT, bool DV, bool RES, int W, bool NOWB = false>
 int launch_inst(gcb_traj* t, const ClusterParams& cp, const Plan& pl, int* nclusters_out) {
-    auto kern = super_cluster_kernel<K, WT, DV, RES, W>;
+#ifndef GCB_NO_NOWB
+    if constexpr (DV && RES && !NOWB) {
+        if (!cp.write_back) return launch_inst<K, WT, DV, RES, W, true>(t, cp, pl, nclusters_out);   // the instance without write-back code
+    }
+#endif
+    auto kern = super_cluster_kernel<K, WT, DV, RES, W, NOWB>;
     // the occupancy query costs tens of microseconds: once per (instance, device, shape).  The cache is shared by every handle
     // of the process and guarded; a miss only repeats the query.
     static std::mutex cache_mu;
