@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(threads_cta(W), 1) super_cluster_kernel(const 
                 mbar_wait(&sh.solved[slot2], ph2);
                 if (tid == TRACE_TID) TRACE(6, j - D);
                 double e = 0.0;
-                const bool run_pass2 = cp.always_explicit || sh.xf[slot2][12] != 0.0;   // warp-uniform
+                const bool run_pass2 = DEV || cp.always_explicit || sh.xf[slot2][12] != 0.0;   // warp-uniform; DEV: known at compile time
                 if (!run_pass2) {
                     if (RESIDENT) {
                         __syncwarp();
