@@ -1144,7 +1144,10 @@ int peratom_prepared(gcb_traj* tb, long first, long nframes, int n_fit) {
     if (rc) return rc;
     SuperParams p;
     fill_params(t, first, nframes, 0, &p);
-    p.weight = t->d_weight;
+    // A fit on every atom (the first LOVO iteration when all atoms are candidates) needs no mask: the unmasked instance does the
+    // same arithmetic (a mask with every bit set selects nothing away) without the per-atom selects.
+    const bool weighted = n_fit != t->natoms;
+    p.weight = weighted ? t->d_weight : nullptr;
     const size_t rows = (size_t)t->sm_count * 8;
     rc = ensure_devpart(t, rows);
     if (rc) return rc;
@@ -1152,7 +1155,7 @@ int peratom_prepared(gcb_traj* tb, long first, long nframes, int n_fit) {
     p.devpart = t->d_devpart;
     p.rmsd = nullptr;
     int rows_used = 0;
-    rc = launch_super_cluster(t, p, true, true, &rows_used);
+    rc = launch_super_cluster(t, p, weighted, true, &rows_used);
     if (rc) return rc;
     rc = deps_after_compute(t, first, nframes);
     if (rc) return rc;
