@@ -642,7 +642,15 @@ int prepare_template(gcb_traj_ext* t, const double* ref_aos, int natoms_ref, con
                      int nidx, bool centred, int* mode_out, bool prefer_gather = false) {
     if (!ref_aos) { set_error("NULL template"); return GCB_ERR_ARG; }
     if (nidx < 0) { set_error("negative index count"); return GCB_ERR_ARG; }
-    const bool all = (idx_test == nullptr || nidx == 0);
+    bool all = (idx_test == nullptr || nidx == 0);
+    if (!all && nidx == t->natoms && natoms_ref == t->natoms) {
+        // both lists name every atom once, in order (align.LOVO's first iteration when every atom is a candidate): the fit on
+        // all atoms -- the same arithmetic without a mask or weights
+        const int* r0 = idx_ref ? idx_ref : idx_test;
+        bool identity = true;
+        for (int k = 0; k < nidx && identity; k++) identity = idx_test[k] == k && r0[k] == k;
+        if (identity) all = true;
+    }
     if (all && natoms_ref != t->natoms) {
         set_error("chem.Super: Ill formed coordinates for Superposition (test %d atoms, templa %d)", t->natoms, natoms_ref);
         return GCB_ERR_SHAPE;
